@@ -186,6 +186,8 @@ int kcma_k_rank_mu(int device, uint64_t n, uint64_t rows, const double* t, const
 /* Philox4x32-10 normals as the device generates them (counter layout in DESIGN.md). */
 int kcma_k_philox_normal(int device, uint64_t seed, uint64_t generation, uint64_t row_begin, uint64_t rows,
                          uint64_t n, double* z_out);
+/* One raw Philox4x32-10 block (known-answer tests against the Random123 vectors). */
+int kcma_k_philox_raw(int device, const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 /* Batched objective (device conduit) on host X. */
 int kcma_k_objective(int device, int objective, uint64_t n, uint64_t rows, const double* x,
                      const double* coef, double* f_out);

@@ -1,0 +1,163 @@
+"""Loader of korali_b200/libkcma.so (CUDA kernels + C ABI, include/kcma.h).
+
+There is no CPU fallback: if the shared library is missing this raises, and kcma_create itself fails
+when no CUDA device is visible."""
+import ctypes as C
+import os
+import numpy as np
+from ._abi import Handle, KcmaError, OBJECTIVES, _as_dp, _dp
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libkcma.so")
+_LIB = None
+
+# every symbol include/kcma.h declares
+EXPORTS = [
+    "kcma_cfg_defaults", "kcma_create", "kcma_destroy", "kcma_last_error", "kcma_take_warnings",
+    "kcma_comm_unique_id", "kcma_comm_init", "kcma_shard_range",
+    "kcma_run_generation", "kcma_ask", "kcma_eval", "kcma_tell", "kcma_check_termination", "kcma_run",
+    "kcma_inject", "kcma_get_array", "kcma_set_array", "kcma_get_index_array", "kcma_get_scalar", "kcma_set_scalar",
+    "kcma_timing_enable", "kcma_timing_get", "kcma_timing_reset", "kcma_launch_count", "kcma_flush_l2",
+    "kcma_k_sort_index", "kcma_k_eigen", "kcma_k_sample", "kcma_k_rank_mu", "kcma_k_philox_normal",
+    "kcma_k_philox_raw", "kcma_k_objective",
+]
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "korali_b200/libkcma.so is missing: build it with `python -m korali_b200.build` "
+                "(nvcc, sm_100a). korali_b200 has no CPU fallback.")
+        _LIB = C.CDLL(LIB_PATH)
+    return _LIB
+
+
+def _kerr():
+    f = lib().kcma_last_error
+    f.restype, f.argtypes = C.c_char_p, [C.c_void_p]
+    return KcmaError(f(None).decode())
+
+
+class Solver(Handle):
+    """One CMA-ES solver state resident on one B200 (a handle of libkcma.so)."""
+
+    def __init__(self, **kw):
+        super().__init__(lib(), "kcma_", **kw)
+
+    def comm_init(self, unique_id):
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
+        self._check(self._fn("comm_init", C.c_int, [C.c_void_p, C.POINTER(C.c_uint8)])(self._h, buf))
+
+    def timing_enable(self, on=True):
+        self._fn("timing_enable", C.c_int, [C.c_void_p, C.c_int])(self._h, int(on))
+
+    def timing_reset(self):
+        self._fn("timing_reset", C.c_int, [C.c_void_p])(self._h)
+
+    def timing(self, phase):
+        ms, calls = C.c_double(0), C.c_uint64(0)
+        self._fn("timing_get", C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)])(
+            self._h, phase.encode(), C.byref(ms), C.byref(calls))
+        return ms.value, calls.value
+
+    def launch_count(self):
+        return self._fn("launch_count", C.c_uint64, [C.c_void_p])(self._h)
+
+    def flush_l2(self):
+        self._check(self._fn("flush_l2", C.c_int, [C.c_void_p])(self._h))
+
+
+def comm_unique_id():
+    out = (C.c_uint8 * 128)()
+    f = lib().kcma_comm_unique_id
+    f.restype, f.argtypes = C.c_int, [C.POINTER(C.c_uint8)]
+    if f(out) != 0:
+        raise _kerr()
+    return bytes(out)
+
+
+def shard_range(population, mirrored, rank, nranks):
+    b, e = C.c_uint64(0), C.c_uint64(0)
+    f = lib().kcma_shard_range
+    f.restype, f.argtypes = None, [C.c_uint64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    f(population, int(mirrored), rank, nranks, C.byref(b), C.byref(e))
+    return b.value, e.value
+
+
+# ---- single kernels on host buffers --------------------------------------------------------------------
+def k_sort_index(f, device=0):
+    f = np.ascontiguousarray(f, dtype=np.float64)
+    out = np.empty(f.size, dtype=np.uint64)
+    fn = lib().kcma_k_sort_index
+    fn.restype, fn.argtypes = C.c_int, [C.c_int, _dp, C.c_uint64, C.POINTER(C.c_uint64)]
+    if fn(device, _as_dp(f), f.size, out.ctypes.data_as(C.POINTER(C.c_uint64))) != 0:
+        raise _kerr()
+    return out
+
+
+def k_eigen(c, device=0):
+    c = np.ascontiguousarray(c, dtype=np.float64)
+    n = c.shape[0]
+    w, q = np.empty(n), np.empty((n, n))
+    fn = lib().kcma_k_eigen
+    fn.restype, fn.argtypes = C.c_int, [C.c_int, C.c_uint64, _dp, _dp, _dp]
+    if fn(device, n, _as_dp(c), _as_dp(w), _as_dp(q)) != 0:
+        raise _kerr()
+    return w, q
+
+
+def k_sample(z, b, d, mean, sigma, device=0):
+    z = np.ascontiguousarray(z, dtype=np.float64); b = np.ascontiguousarray(b, dtype=np.float64)
+    d = np.ascontiguousarray(d, dtype=np.float64); mean = np.ascontiguousarray(mean, dtype=np.float64)
+    rows, n = z.shape
+    y, x = np.empty((rows, n)), np.empty((rows, n))
+    fn = lib().kcma_k_sample
+    fn.restype, fn.argtypes = C.c_int, [C.c_int, C.c_uint64, C.c_uint64, _dp, _dp, _dp, _dp, C.c_double, _dp, _dp]
+    if fn(device, n, rows, _as_dp(z), _as_dp(b), _as_dp(d), _as_dp(mean), float(sigma), _as_dp(y), _as_dp(x)) != 0:
+        raise _kerr()
+    return y, x
+
+
+def k_rank_mu(t, w, device=0):
+    t = np.ascontiguousarray(t, dtype=np.float64); w = np.ascontiguousarray(w, dtype=np.float64)
+    rows, n = t.shape
+    p = np.empty((n, n))
+    fn = lib().kcma_k_rank_mu
+    fn.restype, fn.argtypes = C.c_int, [C.c_int, C.c_uint64, C.c_uint64, _dp, _dp, _dp]
+    if fn(device, n, rows, _as_dp(t), _as_dp(w), _as_dp(p)) != 0:
+        raise _kerr()
+    return p
+
+
+def k_philox_normal(seed, generation, row_begin, rows, n, device=0):
+    out = np.empty((rows, n))
+    fn = lib().kcma_k_philox_normal
+    fn.restype, fn.argtypes = C.c_int, [C.c_int] + [C.c_uint64] * 5 + [_dp]
+    if fn(device, seed, generation, row_begin, rows, n, _as_dp(out)) != 0:
+        raise _kerr()
+    return out
+
+
+def k_philox_raw(ctr, key, device=0):
+    c = (C.c_uint32 * 4)(*ctr); k = (C.c_uint32 * 2)(*key); o = (C.c_uint32 * 4)()
+    fn = lib().kcma_k_philox_raw
+    fn.restype, fn.argtypes = C.c_int, [C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    if fn(device, c, k, o) != 0:
+        raise _kerr()
+    return list(o)
+
+
+def k_objective(obj, x, coef=None, device=0):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    rows, n = x.shape
+    f = np.empty(rows)
+    cp = None
+    if coef is not None:
+        coef = np.ascontiguousarray(coef, dtype=np.float64); cp = _as_dp(coef)
+    fn = lib().kcma_k_objective
+    fn.restype, fn.argtypes = C.c_int, [C.c_int, C.c_int, C.c_uint64, C.c_uint64, _dp, _dp, _dp]
+    if fn(device, OBJECTIVES[obj] if isinstance(obj, str) else obj, n, rows, _as_dp(x), cp, _as_dp(f)) != 0:
+        raise _kerr()
+    return f

@@ -1,0 +1,53 @@
+"""Builds korali_b200/libkcma.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+    python -m korali_b200.build [--force]
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "libkcma.so")
+OBJ = os.path.join(HERE, "build")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall"] + ARCH
+# files whose arithmetic must round like the reference's scalar code (no fused multiply-add)
+NO_FMA = {"objective.cu", "update.cu"}
+SOURCES = ["api.cu", "gemm.cu", "rng.cu", "objective.cu", "sort.cu", "update.cu", "eigen.cu"]
+
+
+def _newer(src, dst):
+    return not os.path.exists(dst) or os.path.getmtime(src) > os.path.getmtime(dst)
+
+
+def build(force=False, verbose=False):
+    os.makedirs(OBJ, exist_ok=True)
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
+    headers.append(os.path.join(HERE, "..", "include", "kcma.h"))
+    objs, rebuilt = [], False
+    procs = []
+    for s in SOURCES:
+        src = os.path.join(CSRC, s)
+        obj = os.path.join(OBJ, s.replace(".cu", ".o"))
+        objs.append(obj)
+        if force or _newer(src, obj) or any(_newer(hd, obj) for hd in headers):
+            cmd = ["nvcc", "-c", src, "-o", obj] + COMMON + (["--fmad=false"] if s in NO_FMA else [])
+            if verbose:
+                cmd += ["-Xptxas", "-v"]
+            procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+            rebuilt = True
+    for s, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError("nvcc failed for %s:\n%s" % (s, out))
+        if verbose or out.strip():
+            sys.stderr.write(out)
+    if rebuilt or not os.path.exists(OUT):
+        cmd = ["nvcc", "-shared", "-o", OUT] + objs + ARCH + ["-Xcompiler", "-fPIC", "-ldl"]
+        subprocess.check_call(cmd)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,1206 @@
+// api.cu — the C ABI of libkcma.so (include/kcma.h) and the host-side orchestration of one CMA-ES generation.
+// The host code only sequences kernel launches on one stream; all solver state stays in HBM.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <nccl.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/kcma.h"
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace kc;
+
+namespace {
+
+char g_create_err[1024] = "";
+
+// ---- NCCL through dlopen: no link-time dependency; prefers the copy torch already loaded ---------------
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool load(std::string& err) {
+    if (lib) return true;
+    lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) { err = std::string("cannot load libnccl.so.2: ") + dlerror(); return false; }
+#define SYM(F) F = (decltype(F))dlsym(lib, "nccl" #F); if (!F) { err = "missing symbol nccl" #F; return false; }
+    SYM(GetUniqueId) SYM(CommInitRank) SYM(CommDestroy) SYM(AllGather) SYM(AllReduce) SYM(GetErrorString)
+#undef SYM
+    return true;
+  }
+} g_nccl;
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+struct Phase { double ms = 0; uint64_t calls = 0; };
+
+}  // namespace
+
+struct kcma {
+  kcma_cfg cfg;
+  int N = 0, ld = 0, device = 0, num_sms = 148;
+  cudaStream_t stream = 0;
+  std::vector<double> lower, upper, init_val, init_sd, min_sd, coef, con_shift;
+  bool has_bounds = false, any_min_sd = false;
+  uint64_t lambda = 0, mu = 0, vlambda = 0, vmu = 0, cur_lambda = 0, cur_mu = 0, s_max = 0, mu_max = 0;
+  uint64_t shard_lo = 0, shard_hi = 0;       // this rank's samples of the CURRENT population
+  uint64_t max_local = 0, max_zrows = 0;     // allocation bounds
+  double mueff = 0, cs = 0, cc = 0, damp = 0, chi_n = 0, trace = 0;
+  std::vector<double> h_weights;
+  double tc_max_condition = INFINITY, tc_min_sd = -INFINITY, tc_max_sd = INFINITY, tc_max_value = INFINITY,
+         tc_min_value_diff = -INFINITY, tc_max_model_evaluations = 1e9, tc_max_generations = 1e10;
+  uint64_t gen = 1, model_evals = 0;
+  int is_viability = 0, has_constraints = 0;
+  uint64_t n_con = 0;
+  // device state
+  double *dC = nullptr, *dB = nullptr, *dA = nullptr, *dD = nullptr, *dVT = nullptr, *dVTw = nullptr, *dGT = nullptr, *dEv = nullptr;
+  int* dPerm = nullptr;
+  double *dMean = nullptr, *dMeanOld = nullptr, *dMeanUpd = nullptr, *dT = nullptr, *dPs = nullptr, *dPc = nullptr;
+  double *dZ = nullptr, *dY = nullptr, *dX = nullptr, *dF = nullptr;
+  unsigned* dIdx = nullptr;
+  void* dSortWs = nullptr;
+  double *dW = nullptr, *dSelW = nullptr;
+  int *dSelS = nullptr, *dCount = nullptr;
+  double *dS = nullptr, *dPartial = nullptr, *dWsplit = nullptr, *dRed = nullptr;
+  double *dBestEver = nullptr, *dCurBest = nullptr;
+  double *dLower = nullptr, *dUpper = nullptr, *dMinSd = nullptr, *dCoef = nullptr, *dShift = nullptr;
+  double* dSigmaSampling = nullptr;
+  unsigned char* dInfeasible = nullptr;
+  void* dFlush = nullptr; size_t flush_bytes = 0;
+  DevScalars* dSc = nullptr;
+  DevScalars* hSc = nullptr;  // pinned mirror
+  int* hCount = nullptr;      // pinned
+  int s_rows_padded = 0, rows_per_cta = 64, max_splits = 16, cur_splits = 1;
+  bool scalars_fresh = false;
+  bool sampled_pending = false;  // ask done, tell not yet: X uses (mean, sigma); afterwards (mean_old, sigma_sampling)
+  // injections
+  bool inj_z = false, inj_bd = false, inj_y = false, inj_x = false, inj_f = false;
+  bool vt_valid = false;
+  // nccl
+  ncclComm_t comm = nullptr;
+  // timing
+  bool timing = false;
+  std::map<std::string, Phase> phases;
+  struct Pending { std::string name; cudaEvent_t a, b; };
+  std::vector<Pending> pending;
+  std::vector<cudaEvent_t> event_pool;
+  uint64_t launches = 0;
+  std::string err, warn, reason;
+  char warn_out[4096];
+};
+
+namespace {
+
+int fail(kcma* h, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf;
+  else strncpy(g_create_err, buf, sizeof(g_create_err) - 1);
+  return 1;
+}
+
+#define CUDA_OK(h, call)                                                                      \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) return fail(h, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(e_), __FILE__, __LINE__, #call); \
+  } while (0)
+
+template <typename T>
+cudaError_t dmalloc(T** p, size_t count) {
+  cudaError_t e = cudaMalloc((void**)p, sizeof(T) * (count ? count : 1));
+  if (e == cudaSuccess) e = cudaMemset(*p, 0, sizeof(T) * (count ? count : 1));
+  return e;
+}
+
+struct PhaseTimer {
+  kcma* h; const char* name; cudaEvent_t a = nullptr, b = nullptr;
+  PhaseTimer(kcma* h_, const char* n) : h(h_), name(n) {
+    if (!h->timing) return;
+    auto get = [&]() { cudaEvent_t e; if (!h->event_pool.empty()) { e = h->event_pool.back(); h->event_pool.pop_back(); } else cudaEventCreate(&e); return e; };
+    a = get(); b = get();
+    cudaEventRecord(a, h->stream);
+  }
+  ~PhaseTimer() {
+    if (!h->timing) return;
+    cudaEventRecord(b, h->stream);
+    h->pending.push_back({name, a, b});
+  }
+};
+
+void resolve_timers(kcma* h) {
+  for (auto& p : h->pending) {
+    cudaEventSynchronize(p.b);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, p.a, p.b);
+    auto& ph = h->phases[p.name];
+    ph.ms += ms; ph.calls++;
+    h->event_pool.push_back(p.a); h->event_pool.push_back(p.b);
+  }
+  h->pending.clear();
+}
+
+// ref: CMAES.cpp.base:233-284 (host arithmetic identical to the oracle's so the constants are bit-equal)
+int init_mu_weights(kcma* h, uint64_t numsamplesmu) {
+  const uint64_t N = h->N;
+  std::vector<double>& w = h->h_weights;
+  std::fill(w.begin(), w.end(), 0.0);
+  switch (h->cfg.mu_type) {
+    case KCMA_MU_LINEAR: for (uint64_t i = 0; i < numsamplesmu; i++) w[i] = (double)(numsamplesmu - i); break;
+    case KCMA_MU_EQUAL: for (uint64_t i = 0; i < numsamplesmu; i++) w[i] = 1.; break;
+    case KCMA_MU_LOGARITHMIC:
+      for (uint64_t i = 0; i < numsamplesmu; i++) w[i] = log(std::max((double)numsamplesmu, 0.5 * h->cur_lambda) + 0.5) - log(i + 1.);
+      break;
+    case KCMA_MU_PROPORTIONAL: for (uint64_t i = 0; i < numsamplesmu; i++) w[i] = 1.; break;
+    default: return fail(h, "Invalid setting of Mu Type (%d) (Linear, Equal, Logarithmic, or Proportional accepted).", h->cfg.mu_type);
+  }
+  double s1 = 0.0, s2 = 0.0;
+  for (uint64_t i = 0; i < numsamplesmu; i++) { s1 += w[i]; s2 += w[i] * w[i]; }
+  h->mueff = s1 * s1 / s2;
+  for (uint64_t i = 0; i < numsamplesmu; i++) w[i] /= s1;
+  if ((h->cfg.initial_cumulative_covariance <= 0) || (h->cfg.initial_cumulative_covariance > 1))
+    h->cc = (4.0 + h->mueff / (1.0 * N)) / (N + 4.0 + 2.0 * h->mueff / (1.0 * N));
+  else
+    h->cc = h->cfg.initial_cumulative_covariance;
+  h->cs = h->cfg.initial_sigma_cumulation_factor;
+  if (h->cs <= 0 || h->cs >= 1) {
+    if (h->has_constraints) h->cs = sqrt(h->mueff) / (sqrt(h->mueff) + sqrt((double)N));
+    else h->cs = (h->mueff + 2.0) / (N + h->mueff + 3.0);
+  }
+  h->damp = h->cfg.initial_damp_factor;
+  if (h->damp <= 0.0) h->damp = (1.0 + 2 * std::max(0.0, sqrt((h->mueff - 1.0) / (N + 1.0)) - 1)) + h->cs;
+  cudaMemcpyAsync(h->dW, w.data(), sizeof(double) * h->mu_max, cudaMemcpyHostToDevice, h->stream);
+  return 0;
+}
+
+// ref: CMAES.cpp.base:286-313. Only diagonals of C and B are written.
+int init_covariance(kcma* h) {
+  const int N = h->N, ld = h->ld;
+  h->trace = 0.0;
+  for (int i = 0; i < N; ++i) h->trace += h->init_sd[i] * h->init_sd[i];
+  const double sigma = sqrt(h->trace / N);
+  std::vector<double> D(N), Cd(N), one(N, 1.0);
+  for (int i = 0; i < N; ++i) {
+    D[i] = h->init_sd[i] * sqrt(N / h->trace);
+    Cd[i] = D[i];
+    Cd[i] *= Cd[i];
+  }
+  cudaStreamSynchronize(h->stream);
+  // diagonals via strided 2D copies
+  cudaMemcpy2D(h->dC, sizeof(double) * (ld + 1), Cd.data(), sizeof(double), sizeof(double), N, cudaMemcpyHostToDevice);
+  cudaMemcpy2D(h->dB, sizeof(double) * (ld + 1), one.data(), sizeof(double), sizeof(double), N, cudaMemcpyHostToDevice);
+  cudaMemcpy(h->dD, D.data(), sizeof(double) * N, cudaMemcpyHostToDevice);
+  h->vt_valid = false;  // B changed outside the eigensolver: rebuild VT = B^T lazily
+  double mn = D[0], mx = D[0];
+  for (int i = 1; i < N; i++) { mn = std::min(mn, D[i]); mx = std::max(mx, D[i]); }
+  double maxd = Cd[0], mind = Cd[0];
+  for (int i = 1; i < N; i++) { maxd = std::max(maxd, Cd[i]); mind = std::min(mind, Cd[i]); }
+  cudaMemcpy(h->hSc, h->dSc, sizeof(DevScalars), cudaMemcpyDeviceToHost);
+  h->hSc->sigma = sigma;
+  h->hSc->min_eig = mn * mn; h->hSc->max_eig = mx * mx;
+  h->hSc->max_diag_c = maxd; h->hSc->min_diag_c = mind;
+  cudaMemcpy(h->dSc, h->hSc, sizeof(DevScalars), cudaMemcpyHostToDevice);
+  h->scalars_fresh = true;
+  return 0;
+}
+
+int pull_scalars(kcma* h) {
+  if (h->scalars_fresh) return 0;
+  CUDA_OK(h, cudaMemcpyAsync(h->hSc, h->dSc, sizeof(DevScalars), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  h->scalars_fresh = true;
+  return 0;
+}
+int push_scalars(kcma* h) {
+  CUDA_OK(h, cudaMemcpyAsync(h->dSc, h->hSc, sizeof(DevScalars), cudaMemcpyHostToDevice, h->stream));
+  CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+void set_population(kcma* h, uint64_t lambda, uint64_t mu) {
+  h->cur_lambda = lambda;
+  h->cur_mu = mu;
+  kcma_shard_range(lambda, h->cfg.mirrored_sampling, h->cfg.rank, h->cfg.nranks, &h->shard_lo, &h->shard_hi);
+}
+
+uint64_t local_samples(const kcma* h) { return h->shard_hi - h->shard_lo; }
+uint64_t local_zrows(const kcma* h) { return h->cfg.mirrored_sampling ? local_samples(h) / 2 : local_samples(h); }
+
+// VT = B^T (vectors as rows) after B was set from outside the eigensolver.
+__global__ void transpose_kernel(const double* __restrict__ in, double* __restrict__ out, int ld, int n) {
+  __shared__ double tile[32][33];
+  const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) tile[r][tx] = (y0 + r < n && x0 + tx < n) ? in[(size_t)(y0 + r) * ld + x0 + tx] : 0.0;
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8)
+    if (x0 + r < n && y0 + tx < n) out[(size_t)(x0 + r) * ld + y0 + tx] = tile[tx][r];
+}
+
+__global__ void copy_sigma_kernel(const DevScalars* sc, double* out) { *out = sc->sigma; }
+
+// infeasible flags -> list of z-rows to resample + counters (prepareGeneration :455-459, :484-490). Single block.
+__global__ void __launch_bounds__(1024)
+infeasible_compact_kernel(const unsigned char* __restrict__ flags, int samples, int mirrored, int* __restrict__ rows,
+                          int* __restrict__ count_out, DevScalars* __restrict__ sc) {
+  __shared__ int warp_tot[32];
+  __shared__ int carry;
+  __shared__ unsigned long long bad_total;
+  if (threadIdx.x == 0) { carry = 0; bad_total = 0; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int items = mirrored ? samples / 2 : samples;
+  for (int base = 0; base < items; base += 1024) {
+    const int j = base + threadIdx.x;
+    int bad = 0; bool take = false;
+    if (j < items) {
+      if (mirrored) { bad = flags[2 * j] + flags[2 * j + 1]; take = (bad == 2); }
+      else { bad = flags[j]; take = bad != 0; }
+    }
+    if (bad) atomicAdd(&bad_total, (unsigned long long)bad);
+    const unsigned m = __ballot_sync(0xffffffffu, take);
+    if (lane == 0) warp_tot[warp] = __popc(m);
+    __syncthreads();
+    if (warp == 0) {
+      int x = warp_tot[lane];
+      for (int off = 1; off < 32; off <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, off); if (lane >= off) x += y; }
+      warp_tot[lane] = x;
+    }
+    __syncthreads();
+    const int c = carry;
+    if (take) rows[c + (warp ? warp_tot[warp - 1] : 0) + __popc(m & ((1u << lane) - 1u))] = j;
+    __syncthreads();
+    if (threadIdx.x == 0) carry = c + warp_tot[31];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { *count_out = carry; sc->infeasible_this_round = bad_total; }
+}
+
+__global__ void bump_attempts_kernel(unsigned* attempt, const int* rows, int count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) attempt[rows[i]]++;
+}
+
+// y_row = A z_row for listed rows (resampling only; one warp per output element).
+__global__ void __launch_bounds__(256)
+resample_rows_kernel(const double* __restrict__ Z, double* __restrict__ Y, int ld, const double* __restrict__ A, int n,
+                     const int* __restrict__ rows, int diagonal, const double* __restrict__ D) {
+  const int lane = threadIdx.x & 31;
+  const int d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (d >= n) return;
+  const int row = rows[blockIdx.y];
+  const double* z = Z + (size_t)row * ld;
+  double a = 0.0;
+  if (diagonal) { if (lane == 0) a = D[d] * z[d]; }
+  else for (int e = lane; e < n; e += 32) a += A[(size_t)d * ld + e] * z[e];
+  a = warp_sum_butterfly(a);
+  if (lane == 0) Y[(size_t)row * ld + d] = a;
+}
+
+// Diagonal Covariance sampling (:498-502): y = D o z.
+__global__ void __launch_bounds__(256)
+diag_sample_kernel(const double* __restrict__ Z, double* __restrict__ Y, int ld, long long rows, int n, const double* __restrict__ D) {
+  const long long total = rows * ld;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int d = (int)(i % ld);
+    Y[i] = d < n ? D[d] * Z[i] : 0.0;
+  }
+}
+
+__global__ void add_infeasible_kernel(DevScalars* sc, unsigned long long v) { sc->infeasible_sample_count += v; }
+__global__ void add_infeasible_from_round_kernel(DevScalars* sc) { sc->infeasible_sample_count += sc->infeasible_this_round; }
+__global__ void flush_kernel(double* p, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = (double)i;
+}
+__global__ void expand_mirrored_kernel(const double* Y, double* out, int ld, long long samples, int n) {
+  const long long total = samples * n;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long s = i / n; const int d = (int)(i - s * n);
+    const double v = Y[(size_t)(s >> 1) * ld + d];
+    out[i] = (s & 1) ? -v : v;
+  }
+}
+
+int ensure_vt(kcma* h) {
+  if (h->vt_valid) return 0;
+  dim3 grid((h->N + 31) / 32, (h->N + 31) / 32);
+  transpose_kernel<<<grid, 256, 0, h->stream>>>(h->dB, h->dVT, h->ld, h->N);
+  launch_scale_bd(h->stream, h->dB, h->ld, h->dD, h->dA, h->ld, h->N);
+  h->launches += 2;
+  h->vt_valid = true;
+  return 0;
+}
+
+// updateEigensystem (CMAES.cpp.base:869-890) + eigen (:896-938)
+int update_eigensystem(kcma* h, const double* dM) {
+  PhaseTimer t(h, "eigen");
+  const int N = h->N, ld = h->ld;
+  if (h->inj_bd) { h->inj_bd = false; return ensure_vt(h); }
+  if (h->cfg.diagonal_covariance) {
+    launch_eig_diagonal(h->stream, dM, ld, N, h->dD, h->dSc);
+    h->launches += 1;
+    h->scalars_fresh = false;
+    return 0;
+  }
+  ensure_vt(h);
+  CUDA_OK(h, cudaMemcpyAsync(h->dVTw, h->dVT, sizeof(double) * (size_t)N * ld, cudaMemcpyDeviceToDevice, h->stream));
+  // GT = VT * M  (M symmetric): GT[i][j] = sum_k VT[i][k] M[j][k]
+  launch_gemm_tn(h->stream, N, N, N, h->dVTw, ld, dM, ld, h->dGT, ld);
+  h->launches += 1;
+  const double tol = 4.0 * 2.220446049250313e-16 * sqrt((double)N);
+  const int max_sweeps = 40;
+  for (int sweep = 0; sweep < max_sweeps; sweep++) {
+    int l = 0;
+    launch_jacobi_sweep(h->stream, h->dGT, h->dVTw, ld, N, tol, h->dSc, &l);
+    h->launches += l;
+    h->scalars_fresh = false;
+    if (pull_scalars(h)) return 1;
+    if (h->hSc->jacobi_rotations == 0) break;
+  }
+  launch_rayleigh(h->stream, h->dGT, h->dVTw, ld, N, h->dEv);
+  launch_eig_order(h->stream, h->dEv, N, h->dPerm, h->dSc);
+  launch_eig_commit(h->stream, h->dVTw, ld, N, h->dPerm, h->dEv, h->dB, h->dA, h->dD, h->dVT, h->dSc);
+  h->launches += 3;
+  h->scalars_fresh = false;
+  return 0;
+}
+
+int sample_population(kcma* h) {
+  const int N = h->N, ld = h->ld;
+  const long long zrows = (long long)local_zrows(h);
+  const unsigned long long zrow_begin = h->cfg.mirrored_sampling ? h->shard_lo / 2 : h->shard_lo;
+  if (!h->inj_y && !h->inj_x) {
+    if (!h->inj_z) {
+      PhaseTimer t(h, "rng");
+      launch_philox_normal(h->stream, h->dZ, ld, zrows, N, h->cfg.seed, (unsigned)h->gen, zrow_begin, nullptr, nullptr, h->num_sms);
+      h->launches++;
+    }
+    h->inj_z = false;
+    PhaseTimer t(h, "sample_gemm");
+    if (h->cfg.diagonal_covariance) {
+      diag_sample_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(h->dZ, h->dY, ld, zrows, N, h->dD);
+    } else {
+      launch_gemm_tn(h->stream, (int)zrows, N, N, h->dZ, ld, h->dA, ld, h->dY, ld);
+    }
+    h->launches++;
+  }
+  copy_sigma_kernel<<<1, 1, 0, h->stream>>>(h->dSc, h->dSigmaSampling);
+  h->launches++;
+  // feasibility (isSampleFeasible) and resampling
+  const long long ls = (long long)local_samples(h);
+  if ((h->has_bounds || h->cfg.keep_population) && !h->inj_x) {
+    PhaseTimer t(h, "feasibility");
+    launch_feasibility(h->stream, h->dY, ld, ls, N, h->cfg.mirrored_sampling, h->dMean, h->dSc,
+                       h->has_bounds ? h->dLower : nullptr, h->dUpper, h->has_bounds ? h->dInfeasible : nullptr,
+                       h->cfg.keep_population ? h->dX : nullptr, ld, nullptr, h->num_sms);
+    h->launches++;
+    if (h->has_bounds) {
+      int* dRows = (int*)h->dSelS;                     // reuse: selection list is rebuilt in tell()
+      unsigned* dAttempt = (unsigned*)h->dSelW;        // zeroed per generation
+      CUDA_OK(h, cudaMemsetAsync(dAttempt, 0, sizeof(unsigned) * (size_t)zrows, h->stream));
+      const uint64_t maxres = h->cfg.max_infeasible_resamplings;
+      for (int round = 0; round < 1000000; round++) {
+        infeasible_compact_kernel<<<1, 1024, 0, h->stream>>>(h->dInfeasible, (int)ls, h->cfg.mirrored_sampling, dRows, h->dCount, h->dSc);
+        add_infeasible_from_round_kernel<<<1, 1, 0, h->stream>>>(h->dSc);
+        h->launches += 2;
+        h->scalars_fresh = false;
+        if (maxres == 0) break;  // reference release build: size_t(Infinity) == 0 -> never resamples
+        CUDA_OK(h, cudaMemcpyAsync(h->hCount, h->dCount, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        if (pull_scalars(h)) return 1;
+        const int cnt = *h->hCount;
+        if (cnt == 0 || h->hSc->infeasible_sample_count >= maxres) break;
+        bump_attempts_kernel<<<(cnt + 255) / 256, 256, 0, h->stream>>>(dAttempt, dRows, cnt);
+        launch_philox_normal(h->stream, h->dZ, ld, cnt, N, h->cfg.seed, (unsigned)h->gen, zrow_begin, dAttempt, dRows, h->num_sms);
+        dim3 grid((N + 7) / 8, cnt);
+        resample_rows_kernel<<<grid, 256, 0, h->stream>>>(h->dZ, h->dY, ld, h->dA, N, dRows, h->cfg.diagonal_covariance, h->dD);
+        // re-check only the resampled rows (sample list = z-rows, or both members when mirrored)
+        launch_feasibility(h->stream, h->dY, ld, ls, N, h->cfg.mirrored_sampling, h->dMean, h->dSc, h->dLower, h->dUpper,
+                           h->dInfeasible, h->cfg.keep_population ? h->dX : nullptr, ld, nullptr, h->num_sms);
+        h->launches += 4;
+      }
+    }
+  }
+  h->inj_y = false;
+  h->sampled_pending = true;
+  return 0;
+}
+
+int do_ask(kcma* h) {
+  if (h->has_constraints) return fail(h, "constraint path (viability regime) is not built into this libkcma yet");
+  if (update_eigensystem(h, h->dC)) return 1;
+  return sample_population(h);
+}
+
+int do_eval(kcma* h) {
+  h->model_evals += h->cur_lambda;  // ref :214
+  if (h->inj_f) { h->inj_f = false; return 0; }
+  if (h->cfg.objective == KCMA_OBJ_EXTERNAL) return fail(h, "objective is External: inject the Value Vector with kcma_inject(KCMA_INJ_F) before eval");
+  PhaseTimer t(h, "objective");
+  const long long ls = (long long)local_samples(h);
+  double* f_local = h->dF + h->shard_lo;
+  const double* src = h->inj_x ? h->dX : h->dY;
+  if (launch_objective(h->stream, h->cfg.objective, src, h->ld, ls, h->N, h->cfg.mirrored_sampling, h->inj_x ? 1 : 0, h->dMean,
+                       h->dSc, h->dCoef, f_local, h->num_sms))
+    return fail(h, "unknown objective id %d", h->cfg.objective);
+  h->launches++;
+  h->scalars_fresh = false;
+  return 0;
+}
+
+int nccl_check(kcma* h, ncclResult_t r, const char* what) {
+  if (r == ncclSuccess) return 0;
+  return fail(h, "NCCL error in %s: %s", what, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+}
+
+int do_tell(kcma* h) {
+  const int N = h->N, ld = h->ld;
+  const int lambda = (int)h->cur_lambda, mu = (int)h->cur_mu;
+  const int multi = h->cfg.nranks > 1;
+  const int from_x = h->inj_x ? 1 : 0;
+  const double* rows_src = from_x ? h->dX : h->dY;
+  if (multi) {
+    if (!h->comm) return fail(h, "nranks > 1 but kcma_comm_init was not called");
+    PhaseTimer t(h, "collectives");
+    if (nccl_check(h, g_nccl.AllGather(h->dF + h->shard_lo, h->dF, local_samples(h), ncclFloat64, h->comm, h->stream), "all-gather(F)")) return 1;
+  }
+  {
+    PhaseTimer t(h, "sort");
+    h->launches += launch_sort_index(h->stream, h->dF, lambda, h->dSortWs, h->dIdx, h->num_sms);
+    launch_rank_bookkeeping(h->stream, h->dF, h->dIdx, lambda, mu, nullptr, 1, h->dSc);
+    h->launches++;
+    if (h->cfg.mu_type == KCMA_MU_PROPORTIONAL) { launch_proportional_weights(h->stream, h->dF, h->dIdx, mu, h->dW); h->launches++; }
+  }
+  int max_count;
+  {
+    PhaseTimer t(h, "gather_mean");
+    launch_select_local(h->stream, h->dIdx, h->dW, mu, (unsigned)h->shard_lo, (unsigned)h->shard_hi, h->dSelS, h->dSelW, h->dCount);
+    max_count = (int)std::min<uint64_t>(mu, local_samples(h));
+    launch_gather_mean(h->stream, rows_src, ld, h->cfg.mirrored_sampling, from_x, h->dSelS, h->dSelW, h->dCount, max_count, h->rows_per_cta,
+                       N, ld, h->dMean, h->dSc, h->dS, ld, h->s_rows_padded, h->dPartial);
+    double* mean_new = h->dRed + (size_t)N * ld;
+    double* best_x = mean_new + ld;
+    launch_mean_reduce(h->stream, h->dPartial, h->dCount, h->rows_per_cta, N, ld, mean_new, rows_src, ld, h->cfg.mirrored_sampling, from_x,
+                       h->dMean, h->dSc, (unsigned)h->shard_lo, (unsigned)h->shard_hi, best_x);
+    h->launches += 4;
+  }
+  int splits;
+  {
+    PhaseTimer t(h, "rank_mu");
+    if (h->cfg.diagonal_covariance) {
+      splits = std::max(1, (max_count + h->rows_per_cta * 8 - 1) / (h->rows_per_cta * 8));
+      if (splits > h->max_splits) splits = h->max_splits;
+      const int rows_per = (max_count + splits - 1) / splits;
+      launch_diag_rank_mu(h->stream, h->dS, ld, h->dCount, max_count, rows_per > 0 ? rows_per : 1, N, h->dWsplit, ld, splits);
+    } else {
+      splits = syrk_pick_splits(N, max_count, h->num_sms, h->max_splits);
+      launch_syrk_tt(h->stream, N, max_count, h->dS, ld, h->dWsplit, ld, splits);
+    }
+    h->launches++;
+    if (multi) { launch_reduce_splits(h->stream, h->dWsplit, ld, splits, N, h->dRed); h->launches++; }
+  }
+  if (multi) {
+    PhaseTimer t(h, "collectives");
+    const size_t cnt = (size_t)N * ld + 2 * (size_t)ld;
+    if (nccl_check(h, g_nccl.AllReduce(h->dRed, h->dRed, cnt, ncclFloat64, ncclSum, h->comm, h->stream), "all-reduce(P|mean|best)")) return 1;
+  }
+  {
+    PhaseTimer t(h, "paths");
+    double* mean_new = h->dRed + (size_t)N * ld;
+    double* best_x = mean_new + ld;
+    launch_best_update(h->stream, best_x, N, (unsigned)h->gen, h->dCurBest, h->dBestEver, h->dSc, nullptr, 0, 0, nullptr);
+    launch_paths(h->stream, mean_new, h->dMean, h->dMeanOld, h->dMeanUpd, h->dT, h->dPs, h->dPc, h->dB, ld, h->dD, N,
+                 h->cfg.diagonal_covariance, h->cs, h->cc, h->mueff, h->chi_n, (unsigned)h->gen, h->dSc);
+    const double c1 = 2.0 / (pow(N + 1.3, 2) + h->mueff);
+    const double cmu = std::min(1.0 - c1, 2.0 * (h->mueff - 2. + 1. / h->mueff) / (pow(N + 2.0, 2) + h->mueff));
+    if (multi) launch_adapt_c(h->stream, h->dC, ld, h->dRed, ld, 1, N, h->dPc, c1, cmu, h->cc, h->cfg.diagonal_covariance, h->dSc);
+    else launch_adapt_c(h->stream, h->dC, ld, h->dWsplit, ld, splits, N, h->dPc, c1, cmu, h->cc, h->cfg.diagonal_covariance, h->dSc);
+    launch_sigma(h->stream, h->dC, ld, N, h->dMinSd, h->any_min_sd ? 1 : 0, h->cs, h->damp, h->chi_n, h->trace, h->cfg.is_sigma_bounded,
+                 h->cfg.mu_value > 1 ? 1 : 0, 0, h->cfg.global_success_learning_rate, h->cfg.target_success_rate, h->dSc);
+    h->launches += 7;
+  }
+  h->inj_x = false;
+  h->sampled_pending = false;
+  h->scalars_fresh = false;
+  h->gen++;
+  return 0;
+}
+
+int end_of_generation(kcma* h) {
+  if (pull_scalars(h)) return 1;
+  if (h->timing) resolve_timers(h);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(h, "CUDA error after generation: %s", cudaGetErrorString(e));
+  if (h->hSc->nonfinite) {
+    h->hSc->nonfinite = 0;
+    push_scalars(h);
+    return fail(h, "Non finite value of function evaluation detected: nan\n");
+  }
+  if (h->hSc->eig_rejected) h->warn += "Min Eigenvalue smaller or equal 0.0 after Eigen decomp (no update possible).\n";
+  if (h->hSc->warn_flat) { h->warn += "Sigma increased due to equal function values.\n"; }
+  if (h->hSc->warn_minsd) { h->warn += "Sigma increased due to minimal standard deviation.\n"; }
+  if (h->hSc->warn_flat || h->hSc->warn_minsd) {
+    h->hSc->warn_flat = h->hSc->warn_minsd = 0;
+    if (push_scalars(h)) return 1;
+  }
+  if (h->warn.size() > 3000) h->warn.erase(0, h->warn.size() - 3000);
+  return 0;
+}
+
+}  // namespace
+
+// =================================================== C ABI ===================================================
+extern "C" {
+
+void kcma_cfg_defaults(kcma_cfg* c) {
+  memset(c, 0, sizeof(*c));
+  c->abi_version = KCMA_ABI_VERSION;
+  c->mu_type = KCMA_MU_LOGARITHMIC;
+  c->initial_sigma_cumulation_factor = -1.0;
+  c->initial_damp_factor = -1.0;
+  c->initial_cumulative_covariance = -1.0;
+  c->viability_population_size = 2;
+  c->max_covariance_matrix_corrections = 1000000;
+  c->target_success_rate = 0.1818;
+  c->covariance_matrix_adaption_strength = 0.1;
+  c->normal_vector_learning_rate = -1.0;
+  c->global_success_learning_rate = 0.2;
+  c->nranks = 1;
+}
+
+void kcma_shard_range(uint64_t population, int mirrored, int rank, int nranks, uint64_t* begin, uint64_t* end) {
+  // contiguous equal shards in units of samples (pairs when mirrored); remainder units go to the low ranks
+  const uint64_t unit = mirrored ? 2 : 1;
+  const uint64_t units = population / unit;
+  const uint64_t base = units / (uint64_t)nranks, rem = units % (uint64_t)nranks;
+  const uint64_t r = (uint64_t)rank;
+  const uint64_t b = r * base + std::min(r, rem);
+  const uint64_t e = b + base + (r < rem ? 1 : 0);
+  *begin = b * unit;
+  *end = e * unit;
+}
+
+const char* kcma_last_error(const kcma_t* h) { return h ? h->err.c_str() : g_create_err; }
+
+const char* kcma_take_warnings(kcma_t* h) {
+  strncpy(h->warn_out, h->warn.c_str(), sizeof(h->warn_out) - 1);
+  h->warn_out[sizeof(h->warn_out) - 1] = 0;
+  h->warn.clear();
+  return h->warn_out;
+}
+
+void kcma_destroy(kcma_t* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  void* ptrs[] = {h->dC, h->dB, h->dA, h->dD, h->dVT, h->dVTw, h->dGT, h->dEv, h->dPerm, h->dMean, h->dMeanOld, h->dMeanUpd, h->dT,
+                  h->dPs, h->dPc, h->dZ, h->dY, h->dX, h->dF, h->dIdx, h->dSortWs, h->dW, h->dSelW, h->dSelS, h->dCount, h->dS,
+                  h->dPartial, h->dWsplit, h->dRed, h->dBestEver, h->dCurBest, h->dLower, h->dUpper, h->dMinSd, h->dCoef, h->dShift,
+                  h->dSigmaSampling, h->dInfeasible, h->dFlush, h->dSc};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  if (h->hSc) cudaFreeHost(h->hSc);
+  if (h->hCount) cudaFreeHost(h->hCount);
+  for (auto& p : h->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+  for (auto e : h->event_pool) cudaEventDestroy(e);
+  delete h;
+}
+
+int kcma_create(const kcma_cfg* cfg, kcma_t** out) {
+  *out = nullptr;
+  g_create_err[0] = 0;
+  if (!cfg || cfg->abi_version != KCMA_ABI_VERSION) return fail(nullptr, "kcma_cfg ABI version mismatch");
+  if (cfg->n == 0) return fail(nullptr, "Optimization Evaluation problems require at least one variable.\n");
+  if (cfg->n > 32768) return fail(nullptr, "Variable Count %zu exceeds the supported maximum (32768)", (size_t)cfg->n);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(nullptr, "libkcma needs a CUDA device (sm_100a); none is visible. There is no CPU fallback.");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, "invalid CUDA device %d", cfg->device);
+  kcma* h = new kcma();
+  h->cfg = *cfg;
+  h->device = cfg->device;
+#define CREATE_FAIL(...) do { fail(nullptr, __VA_ARGS__); kcma_destroy(h); return 1; } while (0)
+#define CREATE_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) CREATE_FAIL("CUDA error %s (%s)", cudaGetErrorString(e_), #call); } while (0)
+  CREATE_CUDA(cudaSetDevice(h->device));
+  cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device);
+  const int N = h->N = (int)cfg->n;
+  const int ld = h->ld = round_up(N, 16);
+  auto copyv = [&](const double* p, size_t n, double fill) { std::vector<double> v(n, fill); if (p) std::copy(p, p + n, v.begin()); return v; };
+  h->lower = copyv(cfg->lower_bound, N, -INFINITY);
+  h->upper = copyv(cfg->upper_bound, N, INFINITY);
+  h->init_val = copyv(cfg->initial_value, N, NAN);
+  h->init_sd = copyv(cfg->initial_stddev, N, NAN);
+  h->min_sd = copyv(cfg->min_stddev_update, N, 0.0);
+  h->coef.resize(N);
+  for (int i = 0; i < N; i++) h->coef[i] = cfg->objective_coef ? cfg->objective_coef[i] : (N > 1 ? pow(10.0, 6.0 * (double)i / (double)(N - 1)) : 1.0);
+  h->n_con = (cfg->constraint_family == KCMA_CON_NONE && !cfg->n_constraints) ? 0 : cfg->n_constraints;
+  h->con_shift = copyv(cfg->constraint_shift, h->n_con, 0.0);
+  h->cfg.lower_bound = h->cfg.upper_bound = h->cfg.initial_value = h->cfg.initial_stddev = h->cfg.min_stddev_update = nullptr;
+  h->cfg.objective_coef = h->cfg.constraint_shift = nullptr;
+  for (int i = 0; i < N; i++) {
+    if (std::isfinite(h->lower[i]) || std::isfinite(h->upper[i])) h->has_bounds = true;
+    if (h->min_sd[i] > 0.0) h->any_min_sd = true;
+  }
+  // ref :26-31
+  uint64_t lambda = cfg->population_size, mu = cfg->mu_value, vlambda = cfg->viability_population_size, vmu = cfg->viability_mu_value;
+  if (lambda <= 1) CREATE_FAIL("'Population Size' must be larger 1.");
+  if (mu == 0) mu = lambda / 2;
+  if (vmu == 0) vmu = vlambda / 2;
+  if (mu > lambda) CREATE_FAIL("'Mu Value' (%zu) must not exceed 'Population Size' (%zu).", (size_t)mu, (size_t)lambda);
+  h->lambda = lambda; h->mu = mu; h->vlambda = vlambda; h->vmu = vmu;
+  h->cfg.mu_value = mu; h->cfg.viability_mu_value = vmu;
+  h->has_constraints = h->n_con > 0;
+  h->s_max = std::max(lambda, h->has_constraints ? vlambda : lambda);
+  h->mu_max = std::max(mu, h->has_constraints ? vmu : mu);
+  if (h->s_max >= (1ull << 31)) CREATE_FAIL("'Population Size' too large");
+  h->chi_n = sqrt((double)N) * (1. - 1. / (4. * N) + 1. / (21. * N * N));
+  h->is_viability = h->has_constraints;
+  if (cfg->mirrored_sampling) {  // ref :89-93
+    if (lambda % 2 == 1) CREATE_FAIL("Mirrored Sampling can only be applied with an even Sample Population (is %zu)", (size_t)lambda);
+    if (h->has_constraints) CREATE_FAIL("Mirrored Sampling not applicable to problems with constraints");
+  }
+  if (cfg->nranks < 1 || cfg->rank < 0 || cfg->rank >= cfg->nranks) CREATE_FAIL("invalid rank %d of %d", cfg->rank, cfg->nranks);
+  if (cfg->nranks > 1) {
+    const uint64_t unit = (cfg->mirrored_sampling ? 2 : 1) * (uint64_t)cfg->nranks;
+    if (lambda % unit || (h->has_constraints && vlambda % unit))
+      CREATE_FAIL("population size must be divisible by %zu to shard it across %d GPUs", (size_t)unit, cfg->nranks);
+  }
+  for (int i = 0; i < N; ++i) {  // ref :111-126
+    if (!std::isfinite(h->init_val[i])) {
+      if (!std::isfinite(h->lower[i])) CREATE_FAIL("'Initial Value' of variable 'X%d' not defined, and cannot be inferred because variable lower bound is not finite.\n", i);
+      if (!std::isfinite(h->upper[i])) CREATE_FAIL("'Initial Value' of variable 'X%d' not defined, and cannot be inferred because variable upper bound is not finite.\n", i);
+      h->init_val[i] = (h->upper[i] + h->lower[i]) * 0.5;
+    }
+    if (!std::isfinite(h->init_sd[i])) {
+      if (!std::isfinite(h->lower[i])) CREATE_FAIL("Initial (Mean) Value of variable 'X%d' not defined, and cannot be inferred because variable lower bound is not finite.\n", i);
+      if (!std::isfinite(h->upper[i])) CREATE_FAIL("Initial Standard Deviation 'X%d' not defined, and cannot be inferred because variable upper bound is not finite.\n", i);
+      h->init_sd[i] = (h->upper[i] - h->lower[i]) * 0.3;
+    }
+  }
+  if (h->has_constraints) {
+    if ((cfg->global_success_learning_rate <= 0.0) || (cfg->global_success_learning_rate > 1.0)) CREATE_FAIL("Invalid Global Success Learning Rate (%f), must be greater than 0.0 and less than 1.0\n", cfg->global_success_learning_rate);
+    if ((cfg->target_success_rate <= 0.0) || (cfg->target_success_rate > 1.0)) CREATE_FAIL("Invalid Target Success Rate (%f), must be greater than 0.0 and less than 1.0\n", cfg->target_success_rate);
+    if (cfg->covariance_matrix_adaption_strength <= 0.0) CREATE_FAIL("Invalid Adaption Size (%f), must be greater than 0.0\n", cfg->covariance_matrix_adaption_strength);
+  }
+  set_population(h, h->is_viability ? vlambda : lambda, h->is_viability ? vmu : mu);
+  {
+    uint64_t lo, hi;
+    kcma_shard_range(h->s_max, cfg->mirrored_sampling, cfg->rank, cfg->nranks, &lo, &hi);
+    h->max_local = hi - lo;
+    if (h->has_constraints) h->max_local = (h->s_max + cfg->nranks - 1) / cfg->nranks + 1;
+    h->max_zrows = cfg->mirrored_sampling ? h->max_local / 2 : h->max_local;
+  }
+  const size_t nn = (size_t)N * ld;
+  CREATE_CUDA(dmalloc(&h->dC, nn)); CREATE_CUDA(dmalloc(&h->dB, nn)); CREATE_CUDA(dmalloc(&h->dA, nn));
+  CREATE_CUDA(dmalloc(&h->dVT, nn)); CREATE_CUDA(dmalloc(&h->dVTw, nn)); CREATE_CUDA(dmalloc(&h->dGT, nn));
+  CREATE_CUDA(dmalloc(&h->dD, ld)); CREATE_CUDA(dmalloc(&h->dEv, ld)); CREATE_CUDA(dmalloc(&h->dPerm, ld));
+  CREATE_CUDA(dmalloc(&h->dMean, ld)); CREATE_CUDA(dmalloc(&h->dMeanOld, ld)); CREATE_CUDA(dmalloc(&h->dMeanUpd, ld));
+  CREATE_CUDA(dmalloc(&h->dT, ld)); CREATE_CUDA(dmalloc(&h->dPs, ld)); CREATE_CUDA(dmalloc(&h->dPc, ld));
+  CREATE_CUDA(dmalloc(&h->dBestEver, ld)); CREATE_CUDA(dmalloc(&h->dCurBest, ld));
+  CREATE_CUDA(dmalloc(&h->dZ, h->max_zrows * ld)); CREATE_CUDA(dmalloc(&h->dY, h->max_zrows * ld));
+  CREATE_CUDA(dmalloc(&h->dX, (cfg->keep_population ? h->max_local : 1) * (size_t)ld));
+  CREATE_CUDA(dmalloc(&h->dF, h->s_max)); CREATE_CUDA(dmalloc(&h->dIdx, h->s_max));
+  CREATE_CUDA(cudaMalloc(&h->dSortWs, sort_workspace_bytes((int)h->s_max)));
+  CREATE_CUDA(dmalloc(&h->dW, h->mu_max));
+  const uint64_t max_sel = std::max<uint64_t>(std::min(h->mu_max, h->max_local), h->max_zrows);
+  CREATE_CUDA(dmalloc(&h->dSelW, max_sel + 16)); CREATE_CUDA(dmalloc(&h->dSelS, max_sel + 16)); CREATE_CUDA(dmalloc(&h->dCount, 4));
+  h->s_rows_padded = round_up((int)std::min(h->mu_max, h->max_local), 16) + 16;
+  CREATE_CUDA(dmalloc(&h->dS, (size_t)h->s_rows_padded * ld));
+  CREATE_CUDA(dmalloc(&h->dPartial, ((size_t)h->s_rows_padded / h->rows_per_cta + 2) * ld));
+  CREATE_CUDA(dmalloc(&h->dWsplit, (size_t)h->max_splits * nn));
+  CREATE_CUDA(dmalloc(&h->dRed, nn + 2 * (size_t)ld));
+  CREATE_CUDA(dmalloc(&h->dLower, ld)); CREATE_CUDA(dmalloc(&h->dUpper, ld)); CREATE_CUDA(dmalloc(&h->dMinSd, ld));
+  CREATE_CUDA(dmalloc(&h->dCoef, ld)); CREATE_CUDA(dmalloc(&h->dShift, h->n_con + 1));
+  CREATE_CUDA(dmalloc(&h->dSigmaSampling, 2)); CREATE_CUDA(dmalloc(&h->dInfeasible, h->max_local + 16));
+  CREATE_CUDA(dmalloc(&h->dSc, 1));
+  CREATE_CUDA(cudaMallocHost((void**)&h->hSc, sizeof(DevScalars)));
+  CREATE_CUDA(cudaMallocHost((void**)&h->hCount, 4 * sizeof(int)));
+  memset(h->hSc, 0, sizeof(DevScalars));
+  CREATE_CUDA(cudaMemcpy(h->dLower, h->lower.data(), sizeof(double) * N, cudaMemcpyHostToDevice));
+  CREATE_CUDA(cudaMemcpy(h->dUpper, h->upper.data(), sizeof(double) * N, cudaMemcpyHostToDevice));
+  CREATE_CUDA(cudaMemcpy(h->dMinSd, h->min_sd.data(), sizeof(double) * N, cudaMemcpyHostToDevice));
+  CREATE_CUDA(cudaMemcpy(h->dCoef, h->coef.data(), sizeof(double) * N, cudaMemcpyHostToDevice));
+  if (h->n_con) CREATE_CUDA(cudaMemcpy(h->dShift, h->con_shift.data(), sizeof(double) * h->n_con, cudaMemcpyHostToDevice));
+  // ref :20-24, :138/159, :175-183
+  DevScalars s; memset(&s, 0, sizeof(s));
+  s.best_ever_value = s.previous_best_ever_value = s.previous_best_value = s.current_best_value = -INFINITY;
+  s.cur_min_sd = INFINITY; s.cur_max_sd = -INFINITY;
+  s.global_success_rate = h->has_constraints ? 0.5 : -1.0;
+  s.best_valid_sample = h->has_constraints ? ~0ull : 0ull;
+  *h->hSc = s;
+  CREATE_CUDA(cudaMemcpy(h->dSc, h->hSc, sizeof(DevScalars), cudaMemcpyHostToDevice));
+  h->h_weights.assign(h->mu_max, 0.0);
+  if (init_mu_weights(h, h->is_viability ? vmu : mu)) { strncpy(g_create_err, h->err.c_str(), sizeof(g_create_err) - 1); kcma_destroy(h); return 1; }
+  init_covariance(h);
+  CREATE_CUDA(cudaMemcpy(h->dMean, h->init_val.data(), sizeof(double) * N, cudaMemcpyHostToDevice));
+  CREATE_CUDA(cudaMemcpy(h->dMeanOld, h->init_val.data(), sizeof(double) * N, cudaMemcpyHostToDevice));
+  CREATE_CUDA(cudaDeviceSynchronize());
+#undef CREATE_FAIL
+#undef CREATE_CUDA
+  *out = h;
+  return 0;
+}
+
+int kcma_comm_unique_id(uint8_t id_out[128]) {
+  std::string err;
+  if (!g_nccl.load(err)) return fail(nullptr, "%s", err.c_str());
+  ncclUniqueId id;
+  if (g_nccl.GetUniqueId(&id) != ncclSuccess) return fail(nullptr, "ncclGetUniqueId failed");
+  memcpy(id_out, id.internal, 128);
+  return 0;
+}
+
+int kcma_comm_init(kcma_t* h, const uint8_t id_in[128]) {
+  std::string err;
+  if (!g_nccl.load(err)) return fail(h, "%s", err.c_str());
+  CUDA_OK(h, cudaSetDevice(h->device));
+  ncclUniqueId id;
+  memcpy(id.internal, id_in, 128);
+  return nccl_check(h, g_nccl.CommInitRank(&h->comm, h->cfg.nranks, id, h->cfg.rank), "ncclCommInitRank");
+}
+
+int kcma_ask(kcma_t* h) { CUDA_OK(h, cudaSetDevice(h->device)); return do_ask(h); }
+
+int kcma_eval(kcma_t* h) {
+  CUDA_OK(h, cudaSetDevice(h->device));
+  if (do_eval(h)) return 1;
+  if (pull_scalars(h)) return 1;
+  if (h->hSc->nonfinite) {
+    h->hSc->nonfinite = 0;
+    push_scalars(h);
+    return fail(h, "Non finite value of function evaluation detected: nan\n");
+  }
+  return 0;
+}
+
+int kcma_tell(kcma_t* h) {
+  CUDA_OK(h, cudaSetDevice(h->device));
+  if (do_tell(h)) return 1;
+  return end_of_generation(h);
+}
+
+int kcma_run_generation(kcma_t* h) {
+  CUDA_OK(h, cudaSetDevice(h->device));
+  PhaseTimer* t = h->timing ? new PhaseTimer(h, "generation") : nullptr;
+  int rc = do_ask(h) || do_eval(h) || do_tell(h);
+  delete t;
+  if (rc) return 1;
+  return end_of_generation(h);
+}
+
+int kcma_check_termination(kcma_t* h, int* finished, const char** reason) {
+  if (pull_scalars(h)) return 1;
+  const DevScalars& s = *h->hSc;
+  int fin = 0;
+  h->reason.clear();
+  const uint64_t gen = h->gen, maxres = h->cfg.max_infeasible_resamplings;
+  if (gen > 1 && ((maxres > 0) && (s.infeasible_sample_count >= maxres))) { h->reason += "CMAES['Max Infeasible Resamplings'];"; fin = 1; }
+  if (gen > 1 && (s.max_eig >= h->tc_max_condition * s.min_eig)) { h->reason += "CMAES['Max Condition Covariance Matrix'];"; fin = 1; }
+  if (gen > 1 && (s.cur_min_sd <= h->tc_min_sd)) { h->reason += "CMAES['Min Standard Deviation'];"; fin = 1; }
+  if (gen > 1 && (s.cur_max_sd >= h->tc_max_sd)) { h->reason += "CMAES['Max Standard Deviation'];"; fin = 1; }
+  if (!fin) {
+    if (gen > 1 && (+s.best_ever_value > h->tc_max_value)) { h->reason += "optimizer['Max Value'];"; fin = 1; }
+    // the base-class _previousBestValue is never written and stays 0.0
+    if (gen > 1 && (fabs(s.current_best_value - 0.0) < h->tc_min_value_diff)) { h->reason += "optimizer['Min Value Difference Threshold'];"; fin = 1; }
+    if (!fin) {
+      if (h->tc_max_model_evaluations <= (double)h->model_evals) { h->reason += "solver['Max Model Evaluations'];"; fin = 1; }
+      if ((double)gen > h->tc_max_generations) { h->reason += "solver['Max Generations'];"; fin = 1; }
+    }
+  }
+  *finished = fin;
+  if (reason) *reason = h->reason.c_str();
+  return 0;
+}
+
+int kcma_run(kcma_t* h, uint64_t max_generations, uint64_t* done) {
+  uint64_t n = 0;
+  int fin = 0;
+  while (n < max_generations) {
+    if (kcma_check_termination(h, &fin, nullptr)) { if (done) *done = n; return 1; }
+    if (fin) break;
+    if (kcma_run_generation(h)) { if (done) *done = n; return 1; }
+    n++;
+  }
+  if (done) *done = n;
+  return 0;
+}
+
+// ---- injection ---------------------------------------------------------------------------------------------
+static int upload_rows(kcma* h, double* dst, const double* src, size_t rows) {
+  CUDA_OK(h, cudaMemcpy2DAsync(dst, sizeof(double) * h->ld, src, sizeof(double) * h->N, sizeof(double) * h->N, rows,
+                               cudaMemcpyHostToDevice, h->stream));
+  CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int kcma_inject(kcma_t* h, int kind, const double* src, size_t count) {
+  CUDA_OK(h, cudaSetDevice(h->device));
+  const size_t N = h->N;
+  const size_t zunit = h->cfg.mirrored_sampling ? 2 : 1;
+  switch (kind) {
+    case KCMA_INJ_Z: {
+      if (count != h->cur_lambda / zunit * N) return fail(h, "inject Z: expected %zu values", (size_t)(h->cur_lambda / zunit * N));
+      if (upload_rows(h, h->dZ, src + (h->shard_lo / zunit) * N, local_zrows(h))) return 1;
+      h->inj_z = true;
+      return 0;
+    }
+    case KCMA_INJ_BDZ: {
+      if (count != h->cur_lambda * N) return fail(h, "inject BDZ: expected %zu values", (size_t)(h->cur_lambda * N));
+      if (zunit == 1) { if (upload_rows(h, h->dY, src + h->shard_lo * N, local_samples(h))) return 1; }
+      else {  // even members carry +y
+        CUDA_OK(h, cudaMemcpy2DAsync(h->dY, sizeof(double) * h->ld, src + h->shard_lo * N, sizeof(double) * 2 * N, sizeof(double) * N,
+                                     local_zrows(h), cudaMemcpyHostToDevice, h->stream));
+        CUDA_OK(h, cudaStreamSynchronize(h->stream));
+      }
+      h->inj_y = true;
+      return 0;
+    }
+    case KCMA_INJ_X: {
+      if (count != h->cur_lambda * N) return fail(h, "inject X: expected %zu values", (size_t)(h->cur_lambda * N));
+      if (!h->cfg.keep_population) return fail(h, "inject X needs keep_population = 1 (the Sample Population buffer)");
+      if (upload_rows(h, h->dX, src + h->shard_lo * N, local_samples(h))) return 1;
+      h->inj_x = true;
+      return 0;
+    }
+    case KCMA_INJ_F: {
+      if (count != h->cur_lambda) return fail(h, "inject F: expected %zu values", (size_t)h->cur_lambda);
+      for (size_t i = 0; i < count; i++)
+        if (!std::isfinite(src[i])) return fail(h, "Non finite value of function evaluation detected: %f\n", src[i]);
+      CUDA_OK(h, cudaMemcpyAsync(h->dF, src, sizeof(double) * count, cudaMemcpyHostToDevice, h->stream));
+      CUDA_OK(h, cudaStreamSynchronize(h->stream));
+      h->inj_f = true;
+      return 0;
+    }
+    case KCMA_INJ_BD: {
+      if (count != N * N + N) return fail(h, "inject BD: expected N*N+N values");
+      if (upload_rows(h, h->dB, src, N)) return 1;
+      CUDA_OK(h, cudaMemcpy(h->dD, src + N * N, sizeof(double) * N, cudaMemcpyHostToDevice));
+      if (pull_scalars(h)) return 1;
+      double mn = INFINITY, mx = -INFINITY;
+      for (size_t d = 0; d < N; d++) { const double ev = src[N * N + d] * src[N * N + d]; mn = std::min(mn, ev); mx = std::max(mx, ev); }
+      h->hSc->min_eig = mn; h->hSc->max_eig = mx;
+      if (push_scalars(h)) return 1;
+      h->vt_valid = false;
+      h->inj_bd = true;
+      return 0;
+    }
+  }
+  return fail(h, "unknown injection kind %d", kind);
+}
+
+// ---- state access ---------------------------------------------------------------------------------------------
+namespace {
+struct ArrRef { double* p; size_t rows, cols; int ld; };  // rows x cols with leading dimension ld (ld = cols: dense)
+bool find_array(kcma* h, const char* key, ArrRef* r) {
+  const size_t N = h->N; const int ld = h->ld;
+#define A(K, P, R, C, LD) if (!strcmp(key, K)) { r->p = (P); r->rows = (R); r->cols = (C); r->ld = (LD); return true; }
+  A("Covariance Matrix", h->dC, N, N, ld)
+  A("Covariance Eigenvector Matrix", h->dB, N, N, ld)
+  A("Axis Lengths", h->dD, 1, N, ld)
+  A("Current Mean", h->dMean, 1, N, ld)
+  A("Previous Mean", h->dMeanOld, 1, N, ld)
+  A("Mean Update", h->dMeanUpd, 1, N, ld)
+  A("Evolution Path", h->dPc, 1, N, ld)
+  A("Conjugate Evolution Path", h->dPs, 1, N, ld)
+  A("Auxiliar BDZ Matrix", h->dT, 1, N, ld)
+  A("Mu Weights", h->dW, 1, h->cur_mu, (int)h->cur_mu)
+  A("Value Vector", h->dF, 1, h->cur_lambda, (int)h->cur_lambda)
+  A("Best Ever Variables", h->dBestEver, 1, N, ld)
+  A("Current Best Variables", h->dCurBest, 1, N, ld)
+  A("Objective Coefficients", h->dCoef, 1, N, ld)
+#undef A
+  return false;
+}
+}  // namespace
+
+int kcma_get_array(kcma_t* h, const char* key, double* out, size_t cap, size_t* count) {
+  CUDA_OK(h, cudaSetDevice(h->device));
+  const size_t N = h->N;
+  if (!strcmp(key, "BDZ Matrix") || !strcmp(key, "Sample Population")) {
+    // LOCAL shard rows [shard_lo, shard_hi) of the population
+    const size_t ls = local_samples(h), n = ls * N;
+    if (count) *count = n;
+    if (!out) return 0;
+    if (cap < n) return fail(h, "buffer too small for '%s'", key);
+    double* tmp = nullptr;
+    CUDA_OK(h, cudaMalloc(&tmp, sizeof(double) * (n ? n : 1)));
+    if (!strcmp(key, "BDZ Matrix")) {
+      if (h->cfg.mirrored_sampling) expand_mirrored_kernel<<<h->num_sms * 4, 256, 0, h->stream>>>(h->dY, tmp, h->ld, (long long)ls, (int)N);
+      else cudaMemcpy2DAsync(tmp, sizeof(double) * N, h->dY, sizeof(double) * h->ld, sizeof(double) * N, ls, cudaMemcpyDeviceToDevice, h->stream);
+    } else if (h->cfg.keep_population) {
+      cudaMemcpy2DAsync(tmp, sizeof(double) * N, h->dX, sizeof(double) * h->ld, sizeof(double) * N, ls, cudaMemcpyDeviceToDevice, h->stream);
+    } else {
+      cudaFree(tmp);
+      return fail(h, "'Sample Population' is not materialised: create the handle with keep_population = 1");
+    }
+    cudaError_t e = cudaMemcpyAsync(out, tmp, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream);
+    cudaStreamSynchronize(h->stream);
+    cudaFree(tmp);
+    CUDA_OK(h, e);
+    return 0;
+  }
+  ArrRef r;
+  if (!find_array(h, key, &r)) return fail(h, "unknown array key '%s'", key);
+  const size_t n = r.rows * r.cols;
+  if (count) *count = n;
+  if (!out) return 0;
+  if (cap < n) return fail(h, "buffer too small for '%s' (%zu < %zu)", key, cap, n);
+  if (n == 0) return 0;
+  CUDA_OK(h, cudaMemcpy2DAsync(out, sizeof(double) * r.cols, r.p, sizeof(double) * r.ld, sizeof(double) * r.cols, r.rows,
+                               cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int kcma_set_array(kcma_t* h, const char* key, const double* in, size_t count) {
+  CUDA_OK(h, cudaSetDevice(h->device));
+  ArrRef r;
+  if (!find_array(h, key, &r)) return fail(h, "unknown array key '%s'", key);
+  if (count != r.rows * r.cols) return fail(h, "size mismatch for '%s' (%zu != %zu)", key, count, r.rows * r.cols);
+  CUDA_OK(h, cudaMemcpy2DAsync(r.p, sizeof(double) * r.ld, in, sizeof(double) * r.cols, sizeof(double) * r.cols, r.rows,
+                               cudaMemcpyHostToDevice, h->stream));
+  CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  if (!strcmp(key, "Covariance Eigenvector Matrix") || !strcmp(key, "Axis Lengths")) h->vt_valid = false;
+  if (!strcmp(key, "Mu Weights")) std::copy(in, in + count, h->h_weights.begin());
+  return 0;
+}
+
+int kcma_get_index_array(kcma_t* h, const char* key, uint64_t* out, size_t cap, size_t* count) {
+  CUDA_OK(h, cudaSetDevice(h->device));
+  if (strcmp(key, "Sorting Index")) return fail(h, "unknown index key '%s'", key);
+  const size_t n = h->cur_lambda;
+  if (count) *count = n;
+  if (!out) return 0;
+  if (cap < n) return fail(h, "buffer too small for '%s'", key);
+  std::vector<unsigned> tmp(n);
+  CUDA_OK(h, cudaMemcpyAsync(tmp.data(), h->dIdx, sizeof(unsigned) * n, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  for (size_t i = 0; i < n; i++) out[i] = tmp[i];
+  return 0;
+}
+
+namespace {
+double* find_dev_scalar(kcma* h, const char* key) {
+  DevScalars* s = h->hSc;
+#define S(K, F) if (!strcmp(key, K)) return &s->F;
+  S("Sigma", sigma) S("Conjugate Evolution Path L2 Norm", ps_l2norm)
+  S("Best Ever Value", best_ever_value) S("Previous Best Ever Value", previous_best_ever_value)
+  S("Previous Best Value", previous_best_value) S("Current Best Value", current_best_value)
+  S("Maximum Diagonal Covariance Matrix Element", max_diag_c) S("Minimum Diagonal Covariance Matrix Element", min_diag_c)
+  S("Maximum Covariance Eigenvalue", max_eig) S("Minimum Covariance Eigenvalue", min_eig)
+  S("Current Min Standard Deviation", cur_min_sd) S("Current Max Standard Deviation", cur_max_sd)
+  S("Global Success Rate", global_success_rate)
+#undef S
+  return nullptr;
+}
+double* find_host_scalar(kcma* h, const char* key) {
+#define S(K, F) if (!strcmp(key, K)) return &h->F;
+  S("Trace", trace) S("Effective Mu", mueff) S("Sigma Cumulation Factor", cs) S("Damp Factor", damp)
+  S("Cumulative Covariance", cc) S("Chi Square Number", chi_n)
+  S("Termination Criteria/Max Condition Covariance Matrix", tc_max_condition)
+  S("Termination Criteria/Min Standard Deviation", tc_min_sd)
+  S("Termination Criteria/Max Standard Deviation", tc_max_sd)
+  S("Termination Criteria/Max Value", tc_max_value)
+  S("Termination Criteria/Min Value Difference Threshold", tc_min_value_diff)
+  S("Termination Criteria/Max Model Evaluations", tc_max_model_evaluations)
+  S("Termination Criteria/Max Generations", tc_max_generations)
+#undef S
+  return nullptr;
+}
+}  // namespace
+
+int kcma_get_scalar(kcma_t* h, const char* key, double* out) {
+  CUDA_OK(h, cudaSetDevice(h->device));
+  if (double* p = find_host_scalar(h, key)) { *out = *p; return 0; }
+  if (pull_scalars(h)) return 1;
+  if (double* p = find_dev_scalar(h, key)) { *out = *p; return 0; }
+#define U(K, V) if (!strcmp(key, K)) { *out = (double)(V); return 0; }
+  U("Current Generation", h->gen - 1) U("Model Evaluation Count", h->model_evals) U("Variable Count", h->N)
+  U("Current Population Size", h->cur_lambda) U("Current Mu Value", h->cur_mu)
+  U("Infeasible Sample Count", h->hSc->infeasible_sample_count)
+  U("Is Viability Regime", h->is_viability) U("Has Constraints", h->has_constraints)
+  U("Best Valid Sample", (long long)h->hSc->best_valid_sample)
+  U("Termination Criteria/Max Infeasible Resamplings", h->cfg.max_infeasible_resamplings)
+  U("Shard Begin", h->shard_lo) U("Shard End", h->shard_hi)
+#undef U
+  return fail(h, "unknown scalar key '%s'", key);
+}
+
+int kcma_set_scalar(kcma_t* h, const char* key, double v) {
+  CUDA_OK(h, cudaSetDevice(h->device));
+  if (double* p = find_host_scalar(h, key)) { *p = v; return 0; }
+  if (pull_scalars(h)) return 1;
+  if (double* p = find_dev_scalar(h, key)) { *p = v; return push_scalars(h); }
+#define U(K, STMT) if (!strcmp(key, K)) { STMT; return 0; }
+  U("Current Generation", h->gen = (uint64_t)v + 1)
+  U("Model Evaluation Count", h->model_evals = (uint64_t)v)
+  U("Termination Criteria/Max Infeasible Resamplings", h->cfg.max_infeasible_resamplings = (uint64_t)v)
+#undef U
+  if (!strcmp(key, "Infeasible Sample Count")) { h->hSc->infeasible_sample_count = (unsigned long long)v; return push_scalars(h); }
+  return fail(h, "unknown scalar key '%s'", key);
+}
+
+// ---- measurement ------------------------------------------------------------------------------------------
+int kcma_timing_enable(kcma_t* h, int on) { h->timing = on != 0; return 0; }
+int kcma_timing_get(kcma_t* h, const char* phase, double* ms, uint64_t* calls) {
+  resolve_timers(h);
+  auto it = h->phases.find(phase);
+  if (ms) *ms = it == h->phases.end() ? 0.0 : it->second.ms;
+  if (calls) *calls = it == h->phases.end() ? 0 : it->second.calls;
+  return 0;
+}
+int kcma_timing_reset(kcma_t* h) { resolve_timers(h); h->phases.clear(); return 0; }
+uint64_t kcma_launch_count(const kcma_t* h) { return h->launches; }
+int kcma_flush_l2(kcma_t* h) {
+  CUDA_OK(h, cudaSetDevice(h->device));
+  if (!h->dFlush) { h->flush_bytes = 256ull << 20; CUDA_OK(h, cudaMalloc(&h->dFlush, h->flush_bytes)); }
+  flush_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>((double*)h->dFlush, h->flush_bytes / sizeof(double));
+  return 0;
+}
+
+// ---- single kernels on host buffers -----------------------------------------------------------------------
+#define K_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(nullptr, "CUDA error %s (%s)", cudaGetErrorString(e_), #call); } while (0)
+
+int kcma_k_sort_index(int device, const double* f, uint64_t n, uint64_t* index_out) {
+  if (n == 0) return 0;
+  K_CUDA(cudaSetDevice(device));
+  int sms; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  double* df; unsigned* di; void* ws;
+  K_CUDA(cudaMalloc(&df, sizeof(double) * n)); K_CUDA(cudaMalloc(&di, sizeof(unsigned) * n));
+  K_CUDA(cudaMalloc(&ws, sort_workspace_bytes((int)n)));
+  K_CUDA(cudaMemcpy(df, f, sizeof(double) * n, cudaMemcpyHostToDevice));
+  launch_sort_index(0, df, (int)n, ws, di, sms);
+  std::vector<unsigned> tmp(n);
+  K_CUDA(cudaMemcpy(tmp.data(), di, sizeof(unsigned) * n, cudaMemcpyDeviceToHost));
+  for (uint64_t i = 0; i < n; i++) index_out[i] = tmp[i];
+  cudaFree(df); cudaFree(di); cudaFree(ws);
+  return 0;
+}
+
+int kcma_k_sample(int device, uint64_t n, uint64_t rows, const double* z, const double* b, const double* d, const double* mean,
+                  double sigma, double* y_out, double* x_out) {
+  K_CUDA(cudaSetDevice(device));
+  const int N = (int)n, ld = round_up(N, 16);
+  double *dZ, *dB, *dA, *dD, *dY;
+  K_CUDA(dmalloc(&dZ, rows * ld)); K_CUDA(dmalloc(&dY, rows * ld)); K_CUDA(dmalloc(&dB, (size_t)N * ld)); K_CUDA(dmalloc(&dA, (size_t)N * ld));
+  K_CUDA(dmalloc(&dD, ld));
+  K_CUDA(cudaMemcpy2D(dZ, sizeof(double) * ld, z, sizeof(double) * N, sizeof(double) * N, rows, cudaMemcpyHostToDevice));
+  K_CUDA(cudaMemcpy2D(dB, sizeof(double) * ld, b, sizeof(double) * N, sizeof(double) * N, N, cudaMemcpyHostToDevice));
+  K_CUDA(cudaMemcpy(dD, d, sizeof(double) * N, cudaMemcpyHostToDevice));
+  launch_scale_bd(0, dB, ld, dD, dA, ld, N);
+  launch_gemm_tn(0, (int)rows, N, N, dZ, ld, dA, ld, dY, ld);
+  K_CUDA(cudaMemcpy2D(y_out, sizeof(double) * N, dY, sizeof(double) * ld, sizeof(double) * N, rows, cudaMemcpyDeviceToHost));
+  if (x_out)
+    for (uint64_t i = 0; i < rows; i++)
+      for (int k = 0; k < N; k++) x_out[i * N + k] = mean[k] + sigma * y_out[i * N + k];
+  cudaFree(dZ); cudaFree(dY); cudaFree(dB); cudaFree(dA); cudaFree(dD);
+  K_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int kcma_k_rank_mu(int device, uint64_t n, uint64_t rows, const double* t, const double* w, double* p_out) {
+  K_CUDA(cudaSetDevice(device));
+  int sms; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  const int N = (int)n, ld = round_up(N, 16);
+  const size_t rp = round_up((int)rows, 16) + 16;
+  std::vector<double> s(rows * N);
+  for (uint64_t k = 0; k < rows; k++) {
+    const double rw = sqrt(w[k]);
+    for (int d = 0; d < N; d++) s[k * N + d] = rw * t[k * N + d];
+  }
+  double *dS, *dW, *dP;
+  K_CUDA(dmalloc(&dS, rp * ld));
+  const int splits = syrk_pick_splits(N, (int)rows, sms, 16);
+  K_CUDA(dmalloc(&dW, (size_t)splits * N * ld)); K_CUDA(dmalloc(&dP, (size_t)N * ld));
+  K_CUDA(cudaMemcpy2D(dS, sizeof(double) * ld, s.data(), sizeof(double) * N, sizeof(double) * N, rows, cudaMemcpyHostToDevice));
+  launch_syrk_tt(0, N, (int)rows, dS, ld, dW, ld, splits);
+  launch_reduce_splits(0, dW, ld, splits, N, dP);
+  std::vector<double> p((size_t)N * N);
+  K_CUDA(cudaMemcpy2D(p.data(), sizeof(double) * N, dP, sizeof(double) * ld, sizeof(double) * N, N, cudaMemcpyDeviceToHost));
+  for (int d = 0; d < N; d++)
+    for (int e = 0; e <= d; e++) p_out[(size_t)d * N + e] = p_out[(size_t)e * N + d] = p[(size_t)d * N + e];
+  cudaFree(dS); cudaFree(dW); cudaFree(dP);
+  K_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int kcma_k_philox_normal(int device, uint64_t seed, uint64_t generation, uint64_t row_begin, uint64_t rows, uint64_t n, double* z_out) {
+  K_CUDA(cudaSetDevice(device));
+  int sms; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  const int N = (int)n, ld = round_up(N, 16);
+  double* dZ;
+  K_CUDA(dmalloc(&dZ, rows * ld));
+  launch_philox_normal(0, dZ, ld, (long long)rows, N, seed, (unsigned)generation, row_begin, nullptr, nullptr, sms);
+  K_CUDA(cudaMemcpy2D(z_out, sizeof(double) * N, dZ, sizeof(double) * ld, sizeof(double) * N, rows, cudaMemcpyDeviceToHost));
+  cudaFree(dZ);
+  K_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int kcma_k_philox_raw(int device, const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  K_CUDA(cudaSetDevice(device));
+  uint32_t in[6] = {ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1]};
+  uint32_t *din, *dout;
+  K_CUDA(cudaMalloc(&din, sizeof(in))); K_CUDA(cudaMalloc(&dout, 16));
+  K_CUDA(cudaMemcpy(din, in, sizeof(in), cudaMemcpyHostToDevice));
+  launch_philox_raw(0, din, dout);
+  K_CUDA(cudaMemcpy(out, dout, 16, cudaMemcpyDeviceToHost));
+  cudaFree(din); cudaFree(dout);
+  return 0;
+}
+
+int kcma_k_objective(int device, int objective, uint64_t n, uint64_t rows, const double* x, const double* coef, double* f_out) {
+  K_CUDA(cudaSetDevice(device));
+  int sms; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  const int N = (int)n, ld = round_up(N, 16);
+  double *dX, *dCoef, *dF; DevScalars* dSc;
+  K_CUDA(dmalloc(&dX, rows * ld)); K_CUDA(dmalloc(&dCoef, ld)); K_CUDA(dmalloc(&dF, rows)); K_CUDA(dmalloc(&dSc, 1));
+  K_CUDA(cudaMemcpy2D(dX, sizeof(double) * ld, x, sizeof(double) * N, sizeof(double) * N, rows, cudaMemcpyHostToDevice));
+  std::vector<double> c(N);
+  for (int i = 0; i < N; i++) c[i] = coef ? coef[i] : (N > 1 ? pow(10.0, 6.0 * (double)i / (double)(N - 1)) : 1.0);
+  K_CUDA(cudaMemcpy(dCoef, c.data(), sizeof(double) * N, cudaMemcpyHostToDevice));
+  if (launch_objective(0, objective, dX, ld, (long long)rows, N, 0, 1, dCoef, dSc, dCoef, dF, sms)) return fail(nullptr, "unknown objective id %d", objective);
+  K_CUDA(cudaMemcpy(f_out, dF, sizeof(double) * rows, cudaMemcpyDeviceToHost));
+  cudaFree(dX); cudaFree(dCoef); cudaFree(dF); cudaFree(dSc);
+  K_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int kcma_k_eigen(int device, uint64_t n, const double* c, double* eigenvalues, double* q) {
+  kcma_cfg cfg;
+  kcma_cfg_defaults(&cfg);
+  cfg.n = n; cfg.population_size = 4; cfg.device = device; cfg.objective = KCMA_OBJ_EXTERNAL;
+  std::vector<double> zero(n, 0.0), one(n, 1.0);
+  cfg.initial_value = zero.data(); cfg.initial_stddev = one.data();
+  kcma_t* h = nullptr;
+  if (kcma_create(&cfg, &h)) return 1;
+  int rc = kcma_set_array(h, "Covariance Matrix", c, n * n);
+  if (!rc) rc = update_eigensystem(h, h->dC);
+  if (!rc) rc = pull_scalars(h);
+  if (!rc && h->hSc->eig_rejected) {  // report the raw spectrum anyway (unsorted acceptance is the caller's business)
+    rc = fail(nullptr, "matrix is not positive definite: eigensystem rejected (CMAES.cpp.base:876-880)");
+  }
+  if (!rc) rc = kcma_get_array(h, "Covariance Eigenvector Matrix", q, n * n, nullptr);
+  if (!rc) {
+    rc = kcma_get_array(h, "Axis Lengths", eigenvalues, n, nullptr);
+    for (uint64_t i = 0; i < n; i++) eigenvalues[i] *= eigenvalues[i];
+  } else if (h->err.size()) strncpy(g_create_err, h->err.c_str(), sizeof(g_create_err) - 1);
+  kcma_destroy(h);
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,76 @@
+// kernels.h — host-side launchers of the libkcma CUDA kernels (internal; the public surface is include/kcma.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace kc {
+struct DevScalars;
+
+// gemm.cu
+size_t gemm_tn_smem_bytes();
+size_t syrk_tt_smem_bytes();
+void launch_gemm_tn(cudaStream_t st, int M, int Nc, int K, const double* A, int lda, const double* B, int ldb, double* C, int ldc);
+int syrk_tiles(int n);
+int syrk_pick_splits(int n, int K, int num_sms, int max_splits);
+void launch_syrk_tt(cudaStream_t st, int n, int K, const double* S, int lds, double* W, int ldw, int splits);
+
+// rng.cu
+void launch_philox_normal(cudaStream_t st, double* Z, int ldz, long long rows, int n, unsigned long long seed, unsigned generation,
+                          unsigned long long row_begin, const unsigned* attempt, const int* row_list, int num_sms);
+void launch_philox_raw(cudaStream_t st, const uint32_t* in6, uint32_t* out4);
+
+// objective.cu
+int launch_objective(cudaStream_t st, int objective, const double* Y, int ldy, long long samples, int n, int mirrored, int from_x,
+                     const double* mean, DevScalars* sc, const double* coef, double* f, int num_sms);
+void launch_feasibility(cudaStream_t st, const double* Y, int ldy, long long samples, int n, int mirrored, const double* mean,
+                        const DevScalars* sc, const double* lower, const double* upper, unsigned char* infeasible, double* X,
+                        int ldx, const int* row_list, int num_sms);
+void launch_constraints_halfspace(cudaStream_t st, const double* Y, int ldy, long long samples, int n, const double* mean,
+                                  DevScalars* sc, const double* shift, int n_con, double* G, long long ldg, const int* row_list,
+                                  int num_sms);
+
+// sort.cu
+size_t sort_workspace_bytes(int n);
+int launch_sort_index(cudaStream_t st, const double* f, int n, void* workspace, unsigned* sorted_idx, int num_sms);
+
+// update.cu
+void launch_scale_bd(cudaStream_t st, const double* B, int ldb, const double* D, double* A, int lda, int n);
+void launch_rank_bookkeeping(cudaStream_t st, const double* f, const unsigned* idx, int lambda, int mu,
+                             const unsigned long long* viol, int best_is_first, DevScalars* sc);
+void launch_proportional_weights(cudaStream_t st, const double* f, const unsigned* idx, int mu, double* w);
+void launch_select_local(cudaStream_t st, const unsigned* idx, const double* w, int mu, unsigned lo, unsigned hi, int* sel_sample,
+                         double* sel_weight, int* count_out);
+void launch_gather_mean(cudaStream_t st, const double* Y, int ldy, int mirrored, int from_x, const int* sel_sample,
+                        const double* sel_weight, const int* count_ptr, int max_count, int rows_per_cta, int n, int ld,
+                        const double* mean, const DevScalars* sc, double* S, int lds, int rows_padded, double* partial);
+void launch_mean_reduce(cudaStream_t st, const double* partial, const int* count_ptr, int rows_per_cta, int n, int ld,
+                        double* mean_out, const double* Y, int ldy, int mirrored, int from_x, const double* mean,
+                        const DevScalars* sc, unsigned lo, unsigned hi, double* best_x);
+void launch_best_update(cudaStream_t st, const double* best_x, int n, unsigned generation, double* cur_best_vars,
+                        double* best_ever_vars, DevScalars* sc, const double* con_evals, long long ldg, int n_con,
+                        double* best_con_evals);
+void launch_paths(cudaStream_t st, const double* mean_new, double* mean, double* mean_old, double* y, double* tvec, double* ps,
+                  double* pc, const double* B, int ldb, const double* D, int n, int diagonal, double cs, double cc, double mueff,
+                  double chi_n, unsigned generation, DevScalars* sc);
+void launch_adapt_c(cudaStream_t st, double* C, int ldc, const double* W, int ldw, int splits, int n, const double* pc, double c1,
+                    double cmu, double cc, int diagonal, const DevScalars* sc);
+void launch_reduce_splits(cudaStream_t st, const double* W, int ldw, int splits, int n, double* P);
+void launch_diag_rank_mu(cudaStream_t st, const double* S, int lds, const int* count_ptr, int max_count, int rows_per_cta, int n,
+                         double* W, int ldw, int slabs);
+void launch_sigma(cudaStream_t st, const double* C, int ldc, int n, const double* min_sd_update, int any_min_sd, double cs,
+                  double damp, double chi_n, double trace, int is_sigma_bounded, int mu_value_gt1, int viability_regime,
+                  double global_success_lr, double target_success_rate, DevScalars* sc);
+void launch_viability_boundaries(cudaStream_t st, const double* G, long long ldg, int n_con, const unsigned* idx, int mu,
+                                 double* bounds);
+
+// eigen.cu
+void launch_set_identity(cudaStream_t st, double* M, int ld, int n);
+void launch_jacobi_sweep(cudaStream_t st, double* GT, double* VT, int ld, int n, double tol, DevScalars* sc, int* launches);
+void launch_rayleigh(cudaStream_t st, const double* GT, const double* VT, int ld, int n, double* ev);
+void launch_eig_order(cudaStream_t st, const double* ev, int n, int* perm, DevScalars* sc);
+void launch_eig_commit(cudaStream_t st, const double* VTw, int ld, int n, const int* perm, const double* ev, double* B, double* A,
+                       double* D, double* VT, const DevScalars* sc);
+void launch_eig_diagonal(cudaStream_t st, const double* C, int ldc, int n, double* D, DevScalars* sc);
+
+}  // namespace kc

@@ -1,0 +1,86 @@
+// rng.cu — K1: counter-based Philox4x32-10 -> N(0,1) draws (replaces the MT19937/gsl_ran_gaussian loop of
+// prepareGeneration, CMAES.cpp.base:449-450 and :467-473; draw order there is sample-major, dimension-minor).
+//
+// Counter layout (restated on the CPU in oracle/okcma.c philox_normal_pair):
+//   ctr = { column pair p = d/2, z-row index (sample, or pair when mirrored), resampling attempt, generation }
+//   key = 64-bit seed ("Random Seed" of the Normal Generator)
+// Each Philox block gives two 52-bit uniforms in (0,1) -> Box-Muller -> (z[2p], z[2p+1]).
+// Results are independent of the launch geometry and of how the population is sharded across GPUs.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace kc {
+
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__device__ __forceinline__ double unit_open52(uint32_t lo, uint32_t hi) {
+  const unsigned long long v = ((unsigned long long)hi << 32) | lo;
+  return (double)(v >> 12) * 0x1.0p-52 + 0x1.0p-53;  // exact, in [2^-53, 1-2^-53]
+}
+
+// One thread per (row, column pair). Z is row-major with leading dimension ldz (even), pads stay zero.
+// row_list (nullable): regenerate only these local rows (resampling); attempt (nullable): per-row attempt counters.
+__global__ void __launch_bounds__(256)
+philox_normal_kernel(double* __restrict__ Z, int ldz, long long rows, int n, unsigned long long seed, unsigned generation,
+                     unsigned long long row_begin, const unsigned* __restrict__ attempt,
+                     const int* __restrict__ row_list) {
+  const int npairs = (n + 1) >> 1;
+  const long long total = rows * npairs;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long li = idx / npairs;
+    const int p = (int)(idx - li * npairs);
+    const long long row = row_list ? row_list[li] : li;
+    const unsigned long long grow = row_begin + (unsigned long long)row;
+    const unsigned att = attempt ? attempt[row] : 0u;
+    uint32_t r[4];
+    philox4x32_10((uint32_t)p, (uint32_t)grow, att, generation, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    const double u1 = unit_open52(r[0], r[1]);
+    const double u2 = unit_open52(r[2], r[3]);
+    const double rad = sqrt(-2.0 * log(u1));
+    double s, c;
+    sincospi(2.0 * u2, &s, &c);
+    double* dst = Z + (size_t)row * ldz + 2 * p;
+    if (2 * p + 1 < n) {
+      *reinterpret_cast<double2*>(dst) = make_double2(rad * c, rad * s);
+    } else {
+      dst[0] = rad * c;
+    }
+  }
+}
+
+// Raw Philox block (known-answer tests).
+__global__ void philox_raw_kernel(const uint32_t* in, uint32_t* out) {
+  uint32_t r[4];
+  philox4x32_10(in[0], in[1], in[2], in[3], in[4], in[5], r);
+  out[0] = r[0]; out[1] = r[1]; out[2] = r[2]; out[3] = r[3];
+}
+
+void launch_philox_normal(cudaStream_t st, double* Z, int ldz, long long rows, int n, unsigned long long seed,
+                          unsigned generation, unsigned long long row_begin, const unsigned* attempt,
+                          const int* row_list, int num_sms) {
+  if (rows <= 0) return;
+  const long long total = rows * ((n + 1) / 2);
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)num_sms * 16;
+  if (blocks > cap) blocks = cap;
+  philox_normal_kernel<<<(unsigned)blocks, 256, 0, st>>>(Z, ldz, rows, n, seed, generation, row_begin, attempt, row_list);
+}
+
+void launch_philox_raw(cudaStream_t st, const uint32_t* in6, uint32_t* out4) {
+  philox_raw_kernel<<<1, 1, 0, st>>>(in6, out4);
+}
+
+}  // namespace kc

@@ -105,7 +105,7 @@ void okcma_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t 
 
 static inline double u64_to_unit_open(uint32_t lo, uint32_t hi) {
   uint64_t v = ((uint64_t)hi << 32) | lo;
-  return (double)(v >> 11) * 0x1.0p-53 + 0x1.0p-54; /* in (0,1), 53 bits */
+  return (double)(v >> 12) * 0x1.0p-52 + 0x1.0p-53; /* exact, in [2^-53, 1-2^-53] */
 }
 
 static void philox_normal_pair(uint64_t seed, uint32_t generation, uint32_t attempt, uint64_t row, uint32_t pair, double* z0, double* z1) {

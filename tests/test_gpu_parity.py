@@ -1,0 +1,296 @@
+"""GPU parity tests proper: every call goes through the C ABI of korali_b200/libkcma.so and is compared with the
+CPU oracle (oracle/okcma.c) or with the reference's own saved trajectory (tests/golden).
+
+Bars (BASELINE.json north_star): ranking / selection indices bit-exact; mean, paths, sigma and C within a relative
+1e-11 in FP64 (TOL below); polynomial objectives bit-exact; optimum within 1e-8.
+"""
+import numpy as np
+import pytest
+import torch
+from conftest import relerr
+from korali_b200 import _lib
+from korali_b200._abi import INJ_BD, INJ_BDZ, INJ_F, INJ_X, INJ_Z, KcmaError
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-11  # stated FP64 tolerance for mean, evolution paths, sigma and C
+
+if not torch.cuda.is_available():
+    pytest.skip("needs a CUDA device", allow_module_level=True)
+
+
+# ---------------------------------------------------------------- K1 Philox ---------------------------------
+def test_philox_known_answers_on_device():
+    assert _lib.k_philox_raw([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert _lib.k_philox_raw([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert _lib.k_philox_raw([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+    for ctr, key in [([1, 2, 3, 4], [5, 6]), ([123456, 7, 0, 99], [0xdeadbeef, 0x1337])]:
+        assert _lib.k_philox_raw(ctr, key) == O.philox4x32_10(ctr, key)
+
+
+@pytest.mark.parametrize("rows,n,row_begin,gen", [(64, 10, 0, 1), (33, 7, 1000, 5), (4096, 100, 0, 2), (512, 1000, 65000, 3)])
+def test_philox_normals_match_oracle(rows, n, row_begin, gen):
+    z = _lib.k_philox_normal(1337, gen, row_begin, rows, n)
+    zo = O.philox_normal(1337, gen, row_begin, rows, n)
+    # same integer stream; log / sincos differ by a few ulp between libdevice and glibc
+    assert np.abs(z - zo).max() < 5e-15 * max(1.0, np.abs(zo).max())
+    assert np.isfinite(z).all()
+
+
+def test_philox_independent_of_sharding():
+    a = _lib.k_philox_normal(7, 3, 0, 256, 50)
+    b = np.concatenate([_lib.k_philox_normal(7, 3, 0, 100, 50), _lib.k_philox_normal(7, 3, 100, 156, 50)])
+    assert np.array_equal(a, b)
+
+
+# ---------------------------------------------------------------- K4 sort -----------------------------------
+@pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 2047, 2048, 2049, 4096, 8192, 65536, 100003, 1 << 20])
+def test_sort_index_bit_exact(n):
+    rng = np.random.default_rng(n)
+    f = rng.standard_normal(n) * 10.0 ** rng.integers(-30, 30, n)
+    assert np.array_equal(_lib.k_sort_index(f), O.sort_index(f))
+
+
+def test_sort_index_ties_and_signed_zero():
+    rng = np.random.default_rng(1)
+    f = rng.integers(-3, 4, 50000).astype(np.float64)
+    f[::7] = -0.0
+    f[3::11] = 0.0
+    got = _lib.k_sort_index(f)
+    assert np.array_equal(got, O.sort_index(f))
+    assert np.array_equal(got, np.argsort(-f, kind="stable").astype(np.uint64))
+    const = np.full(5000, -2.5)
+    assert np.array_equal(_lib.k_sort_index(const), np.arange(5000, dtype=np.uint64))
+    ext = np.array([1e308, -1e308, 5e-324, -5e-324, 0.0, 1.0, -1.0, 2.2250738585072014e-308])
+    assert np.array_equal(_lib.k_sort_index(ext), O.sort_index(ext))
+
+
+# ---------------------------------------------------------------- K2 sampling GEMM --------------------------
+@pytest.mark.parametrize("rows,n", [(32, 10), (100, 100), (257, 129), (300, 257), (1000, 1000), (130, 999)])
+def test_sampling_gemm_matches_oracle(rows, n):
+    rng = np.random.default_rng(rows * 1000 + n)
+    z = rng.standard_normal((rows, n))
+    q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    d = 10.0 ** rng.uniform(-3, 1, n)
+    mean = rng.standard_normal(n) * 3
+    sigma = 0.37
+    y, x = _lib.k_sample(z, q, d, mean, sigma)
+    yo, xo = O.sample(z, q, d, mean, sigma)
+    assert relerr(y, yo) < 2e-14
+    assert relerr(x, xo) < 2e-14
+
+
+# ---------------------------------------------------------------- K6 rank-mu SYRK ---------------------------
+@pytest.mark.parametrize("rows,n", [(16, 10), (5, 10), (500, 100), (2048, 129), (777, 257), (4096, 1000), (33, 999)])
+def test_rank_mu_matches_oracle(rows, n):
+    rng = np.random.default_rng(rows + n)
+    t = rng.standard_normal((rows, n)) * 10.0 ** rng.uniform(-2, 2, n)[None, :]
+    w = np.log(rows + 0.5) - np.log(np.arange(rows) + 1.0)
+    w /= w.sum()
+    p = _lib.k_rank_mu(t, w)
+    po = O.rank_mu(t, w)
+    scale = np.sqrt(np.outer(np.diag(po), np.diag(po)))
+    assert (np.abs(p - po) / scale).max() < 1e-13
+    assert np.array_equal(p, p.T)
+
+
+# ---------------------------------------------------------------- K3 objectives -----------------------------
+@pytest.mark.parametrize("obj", ["NegSphere", "NegSumSq", "NegRosenbrock", "NegEllipsoid"])
+@pytest.mark.parametrize("rows,n", [(32, 10), (100, 100), (64, 1000), (9, 33), (3, 1)])
+def test_polynomial_objectives_bit_exact(obj, rows, n):
+    x = np.random.default_rng(n).standard_normal((rows, n)) * 3
+    assert np.array_equal(_lib.k_objective(obj, x), O.objective(obj, x))
+
+
+@pytest.mark.parametrize("obj", ["NegAckley", "NegSphereSin2"])
+def test_transcendental_objectives(obj):
+    x = np.random.default_rng(5).standard_normal((200, 100)) * 2
+    assert relerr(_lib.k_objective(obj, x), O.objective(obj, x)) < 1e-14
+
+
+# ---------------------------------------------------------------- K8 eigen ----------------------------------
+@pytest.mark.parametrize("n,cond", [(2, 10.0), (10, 1e3), (33, 1e6), (100, 1e8), (257, 1e4)])
+def test_eigen_residuals_and_eigenvalues(n, cond):
+    rng = np.random.default_rng(n)
+    q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    lam = np.sort(10.0 ** rng.uniform(0, np.log10(cond), n))
+    c = (q * lam) @ q.T
+    c = 0.5 * (c + c.T)
+    w, v = _lib.k_eigen(c)
+    assert np.all(np.diff(w) >= 0)
+    assert np.abs(v @ np.diag(w) @ v.T - c).max() < 1e-12 * np.abs(c).max()
+    assert np.abs(v.T @ v - np.eye(n)).max() < 1e-12
+    wo, _ = O.eigen(c)
+    assert np.abs(w - wo).max() < 1e-12 * lam.max()
+
+
+def test_eigen_identity_and_rejection():
+    w, v = _lib.k_eigen(np.eye(7) * 2.0)
+    assert np.allclose(w, 2.0) and np.abs(v.T @ v - np.eye(7)).max() < 1e-14
+    with pytest.raises(KcmaError, match="positive definite"):
+        _lib.k_eigen(np.diag([1.0, -1.0, 2.0]))
+
+
+# ---------------------------------------------------------------- golden trajectory on the GPU --------------
+N, LAM = 10, 32
+STATE_ARR = ["Covariance Matrix", "Current Mean", "Previous Mean", "Evolution Path", "Conjugate Evolution Path", "Best Ever Variables"]
+STATE_SCA = ["Sigma", "Best Ever Value", "Current Best Value", "Previous Best Value", "Previous Best Ever Value"]
+
+
+def make_gpu(golden, **kw):
+    return _lib.Solver(n=N, population_size=LAM, objective="NegSphere", seed=int(golden["Normal Generator Seed"][0]),
+                       lower_bound=golden["Lower Bound"], upper_bound=golden["Upper Bound"], keep_population=1,
+                       initial_value=golden["Initial Value"], initial_stddev=golden["Initial Standard Deviation"], **kw)
+
+
+def test_init_constants_bit_exact_on_gpu(golden):
+    s = make_gpu(golden)
+    assert np.array_equal(s.get("Mu Weights"), golden["Mu Weights"][1])
+    for k in ["Effective Mu", "Sigma Cumulation Factor", "Damp Factor", "Cumulative Covariance", "Chi Square Number", "Trace"]:
+        assert s.scalar(k) == golden[k][1], k
+    assert s.scalar("Sigma") == np.sqrt(22.5)
+    assert np.array_equal(s.get("Covariance Eigenvector Matrix").reshape(N, N), np.eye(N))
+    assert np.array_equal(s.get("Covariance Matrix").reshape(N, N), np.eye(N))
+
+
+def test_golden_trajectory_all_transitions_on_gpu(golden):
+    """State(g-1) + the reference's own {B, D, X, F}(g) -> State(g), g = 1..100, against the reference's dumps."""
+    worst = 0.0
+    for g in range(1, 101):
+        s = make_gpu(golden)
+        if g > 1:
+            for k in STATE_ARR:
+                s.set(k, golden[k][g - 1])
+            for k in STATE_SCA:
+                s.set_scalar(k, golden[k][g - 1])
+            s.set_scalar("Current Generation", g - 1)
+            s.set_scalar("Model Evaluation Count", golden["Model Evaluation Count"][g - 1])
+        s.inject(INJ_BD, np.concatenate([golden["Covariance Eigenvector Matrix"][g], golden["Axis Lengths"][g]]))
+        s.inject(INJ_X, golden["Sample Population"][g])
+        s.inject(INJ_F, golden["Value Vector"][g])
+        s.run_generation()
+        assert np.array_equal(s.get_index("Sorting Index"), golden["Sorting Index"][g].astype(np.uint64)), g
+        for k in ["Current Mean", "Previous Mean", "Mean Update", "Evolution Path", "Conjugate Evolution Path", "Covariance Matrix",
+                  "Best Ever Variables", "Current Best Variables"]:
+            e = relerr(s.get(k), golden[k][g]); worst = max(worst, e)
+            assert e < TOL, (g, k, e)
+        for k in ["Sigma", "Conjugate Evolution Path L2 Norm", "Best Ever Value", "Current Best Value",
+                  "Maximum Diagonal Covariance Matrix Element", "Minimum Diagonal Covariance Matrix Element",
+                  "Current Min Standard Deviation", "Current Max Standard Deviation"]:
+            a, b = s.scalar(k), golden[k][g]
+            assert abs(a - b) <= TOL * abs(b), (g, k, a, b)
+        assert s.scalar("Current Generation") == g
+        assert s.scalar("Model Evaluation Count") == golden["Model Evaluation Count"][g]
+        s.close()
+    print("worst relative deviation from the reference dumps over 100 transitions: %.2e" % worst)
+
+
+def test_golden_sampling_from_reference_z(golden):
+    """Injecting the reference's own z draws (MT19937 stream) and its (B, D) reproduces its BDZ Matrix / Sample Population."""
+    for g in (1, 2, 50):
+        s = make_gpu(golden)
+        if g > 1:
+            for k in STATE_ARR:
+                s.set(k, golden[k][g - 1])
+            s.set_scalar("Sigma", golden["Sigma"][g - 1])
+            s.set_scalar("Current Generation", g - 1)
+        b = golden["Covariance Eigenvector Matrix"][g].reshape(N, N)
+        d = golden["Axis Lengths"][g]
+        # z = D^-1 B^T y of the reference's BDZ (exact for g=1 where B=I, D=1)
+        z = (golden["BDZ Matrix"][g].reshape(LAM, N) @ b) / d
+        s.inject(INJ_BD, np.concatenate([b.ravel(), d]))
+        s.inject(INJ_Z, z)
+        s.ask()
+        assert relerr(s.get("BDZ Matrix"), golden["BDZ Matrix"][g]) < 1e-13
+        assert relerr(s.get("Sample Population"), golden["Sample Population"][g]) < 1e-13
+        s.close()
+
+
+# ---------------------------------------------------------------- lockstep with the oracle ------------------
+CASES = [
+    dict(n=10, population_size=32, objective="NegRosenbrock", initial_value=0.3, initial_stddev=1.5),                   # config 1
+    dict(n=100, population_size=4096, objective="NegAckley", initial_value=1.0, initial_stddev=3.0),                   # config 2
+    dict(n=64, population_size=256, objective="NegSphere", mirrored_sampling=1, initial_value=1.0, initial_stddev=1.0),  # mirrored
+    dict(n=50, population_size=128, objective="NegEllipsoid", diagonal_covariance=1, initial_value=3.0, initial_stddev=1.0),
+    dict(n=33, population_size=40, mu_value=7, mu_type="Linear", objective="NegSumSq", initial_value=2.0, initial_stddev=0.5),
+    dict(n=20, population_size=64, mu_type="Equal", objective="NegSphereSin2", initial_value=1.0, initial_stddev=2.0),
+    dict(n=257, population_size=2048, objective="NegEllipsoid", initial_value=3.0, initial_stddev=1.0),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "%s-N%d-l%d" % (c["objective"], c["n"], c["population_size"]))
+def test_lockstep_generations_against_oracle(case):
+    """Same (B, D, y) and F injected into both each generation; state must track within TOL for 15 generations."""
+    o = O.Oracle(seed=11, **case)
+    s = _lib.Solver(seed=11, keep_population=1, **case)
+    o.set_scalar("Oracle/RNG Kind", 1)
+    n, lam = case["n"], case["population_size"]
+    exact_f = case["objective"] in ("NegRosenbrock", "NegSphere", "NegEllipsoid", "NegSumSq")
+    for g in range(15):
+        o.ask()
+        bd = np.concatenate([o.get("Covariance Eigenvector Matrix"), o.get("Axis Lengths")])
+        s.inject(INJ_BD, bd)
+        s.inject(INJ_BDZ, o.get("BDZ Matrix"))
+        s.ask()
+        assert np.array_equal(s.get("Sample Population"), o.get("Sample Population")), g
+        o.eval()
+        fo = o.get("Value Vector")
+        if exact_f:
+            s.eval()
+            assert np.array_equal(s.get("Value Vector"), fo), g   # device objective bit-identical
+        else:
+            s.eval()
+            assert relerr(s.get("Value Vector"), fo) < 1e-13
+            s.inject(INJ_F, fo)   # keep the ranking in lockstep
+            s.set_scalar("Model Evaluation Count", s.scalar("Model Evaluation Count") - lam)
+            s.eval()
+        o.tell(); s.tell()
+        assert np.array_equal(s.get_index("Sorting Index"), o.get_index("Sorting Index")), g
+        for k in ["Current Mean", "Mean Update", "Evolution Path", "Conjugate Evolution Path", "Covariance Matrix",
+                  "Best Ever Variables", "Current Best Variables"]:
+            assert relerr(s.get(k), o.get(k)) < TOL, (g, k, relerr(s.get(k), o.get(k)))
+        for k in ["Sigma", "Conjugate Evolution Path L2 Norm", "Best Ever Value", "Current Best Value",
+                  "Current Min Standard Deviation", "Current Max Standard Deviation"]:
+            a, b = s.scalar(k), o.scalar(k)
+            assert abs(a - b) <= TOL * max(abs(b), 1e-300), (g, k, a, b)
+
+
+def test_device_eigensystem_reproduces_covariance_each_generation():
+    """Free-running (own Philox draws, own eigensolver): B D^2 B^T == C and B orthogonal at every generation."""
+    s = _lib.Solver(n=40, population_size=200, objective="NegEllipsoid", seed=3, initial_value=3.0, initial_stddev=1.0)
+    for g in range(30):
+        c = s.get("Covariance Matrix").reshape(40, 40)
+        s.ask()
+        b = s.get("Covariance Eigenvector Matrix").reshape(40, 40)
+        d = s.get("Axis Lengths")
+        assert np.abs((b * d**2) @ b.T - c).max() < 1e-12 * np.abs(c).max(), g
+        assert np.abs(b.T @ b - np.eye(40)).max() < 1e-12
+        assert np.all(np.diff(d) >= 0)
+        s.eval(); s.tell()
+
+
+# ---------------------------------------------------------------- convergence -------------------------------
+CONV = [
+    ("config1: 10-D Rosenbrock, lambda 32", dict(n=10, population_size=32, objective="NegRosenbrock", initial_value=0.0, initial_stddev=0.5), 6000),
+    ("config2: 100-D Ackley, lambda 4096", dict(n=100, population_size=4096, objective="NegAckley", initial_value=1.0, initial_stddev=3.0), 600),
+    ("config3 (reduced): 200-D ellipsoid, lambda 2048", dict(n=200, population_size=2048, objective="NegEllipsoid", initial_value=3.0, initial_stddev=1.0), 2500),
+    ("config4 (reduced): 256-D sphere mirrored", dict(n=256, population_size=4096, objective="NegSphere", mirrored_sampling=1, initial_value=1.0, initial_stddev=1.0), 800),
+    ("diagonal covariance: 100-D sphere", dict(n=100, population_size=256, objective="NegSphere", diagonal_covariance=1, initial_value=1.0, initial_stddev=1.0), 1500),
+]
+
+
+@pytest.mark.parametrize("name,case,max_gens", CONV, ids=[c[0].split(":")[0] for c in CONV])
+def test_converges_to_the_optimum_within_1e8(name, case, max_gens):
+    s = _lib.Solver(seed=1337, **case)
+    s.set_scalar("Termination Criteria/Max Value", -1e-9)
+    s.set_scalar("Termination Criteria/Max Generations", max_gens)
+    s.set_scalar("Termination Criteria/Max Model Evaluations", 1e15)
+    done = s.run(max_gens + 1)
+    best = s.scalar("Best Ever Value")
+    fin, reason = s.check_termination()
+    print("%s: best %.3e after %d generations (%s)" % (name, best, done, reason))
+    assert fin and abs(best) < 1e-8, (name, best, done, reason)
+    xb = s.get("Best Ever Variables")
+    target = 1.0 if case["objective"] == "NegRosenbrock" else 0.0
+    assert np.abs(xb - target).max() < 1e-3
