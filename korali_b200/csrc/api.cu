@@ -80,6 +80,14 @@ struct kcma {
   double *dLower = nullptr, *dUpper = nullptr, *dMinSd = nullptr, *dCoef = nullptr, *dShift = nullptr;
   double* dSigmaSampling = nullptr;
   unsigned char* dInfeasible = nullptr;
+  // constraint path (K9)
+  double *dG = nullptr, *dBounds = nullptr, *dNormal = nullptr, *dCaux = nullptr, *dBestCon = nullptr, *dU = nullptr;
+  unsigned long long* dViol = nullptr;
+  unsigned char* dIndicator = nullptr;
+  int *dEvSample = nullptr, *dEvCon = nullptr, *dVioRows = nullptr;
+  unsigned* dAttempt = nullptr;
+  long long ldg = 0; int u_rows = 0;
+  double normal_lr = -1.0, cov_adaption_factor = -1.0;
   void* dFlush = nullptr; size_t flush_bytes = 0;
   DevScalars* dSc = nullptr;
   DevScalars* hSc = nullptr;  // pinned mirror
@@ -206,7 +214,10 @@ int init_covariance(kcma* h) {
   cudaMemcpy2D(h->dC, sizeof(double) * (ld + 1), Cd.data(), sizeof(double), sizeof(double), N, cudaMemcpyHostToDevice);
   cudaMemcpy2D(h->dB, sizeof(double) * (ld + 1), one.data(), sizeof(double), sizeof(double), N, cudaMemcpyHostToDevice);
   cudaMemcpy(h->dD, D.data(), sizeof(double) * N, cudaMemcpyHostToDevice);
-  h->vt_valid = false;  // B changed outside the eigensolver: rebuild VT = B^T lazily
+  // B is only meaningful until the next eigen(); restart the warm-started solver from the identity basis
+  launch_set_identity(h->stream, h->dVT, ld, N);
+  cudaStreamSynchronize(h->stream);
+  h->vt_valid = true;
   double mn = D[0], mx = D[0];
   for (int i = 1; i < N; i++) { mn = std::min(mn, D[i]); mx = std::max(mx, D[i]); }
   double maxd = Cd[0], mind = Cd[0];
@@ -401,6 +412,7 @@ int sample_population(kcma* h) {
   }
   copy_sigma_kernel<<<1, 1, 0, h->stream>>>(h->dSc, h->dSigmaSampling);
   h->launches++;
+  CUDA_OK(h, cudaMemsetAsync(h->dAttempt, 0, sizeof(unsigned) * (size_t)(zrows > 0 ? zrows : 1), h->stream));
   // feasibility (isSampleFeasible) and resampling
   const long long ls = (long long)local_samples(h);
   if ((h->has_bounds || h->cfg.keep_population) && !h->inj_x) {
@@ -411,8 +423,7 @@ int sample_population(kcma* h) {
     h->launches++;
     if (h->has_bounds) {
       int* dRows = (int*)h->dSelS;                     // reuse: selection list is rebuilt in tell()
-      unsigned* dAttempt = (unsigned*)h->dSelW;        // zeroed per generation
-      CUDA_OK(h, cudaMemsetAsync(dAttempt, 0, sizeof(unsigned) * (size_t)zrows, h->stream));
+      unsigned* dAttempt = h->dAttempt;                // zeroed per generation
       const uint64_t maxres = h->cfg.max_infeasible_resamplings;
       for (int round = 0; round < 1000000; round++) {
         infeasible_compact_kernel<<<1, 1024, 0, h->stream>>>(h->dInfeasible, (int)ls, h->cfg.mirrored_sampling, dRows, h->dCount, h->dSc);
@@ -440,10 +451,110 @@ int sample_population(kcma* h) {
   return 0;
 }
 
+// checkMeanAndSetRegime (CMAES.cpp.base:315-345)
+int check_mean_and_set_regime(kcma* h) {
+  if (!h->is_viability) return 0;
+  if (h->cfg.constraint_family != KCMA_CON_HALFSPACE) return fail(h, "no constraint functions defined");
+  launch_constraints_mean(h->stream, h->dMean, h->dShift, h->N, (int)h->n_con, h->dSc);
+  h->launches++;
+  h->scalars_fresh = false;
+  if (pull_scalars(h)) return 1;
+  if (h->hSc->nonfinite) return fail(h, "Non finite value of constraint evaluation detected\n");
+  if (!h->hSc->mean_feasible) return 0;
+  // mean inside the domain: leave the viability regime for good and re-initialise (:336-344)
+  h->is_viability = 0;
+  CUDA_OK(h, cudaMemsetAsync(h->dBounds, 0, sizeof(double) * h->n_con, h->stream));
+  set_population(h, h->lambda, h->mu);
+  if (init_mu_weights(h, h->cur_mu)) return 1;
+  return init_covariance(h);
+}
+
+// re-draw the listed samples: z (next Philox attempt), y = A z, x; bounds-rejection rounds bounded by the cumulative
+// _resampledParameterCount (:816-826). nv = number of listed rows (host copy).
+int resample_violators(kcma* h, int nv) {
+  const int N = h->N, ld = h->ld;
+  if (nv <= 0) return 0;
+  launch_add_resampled(h->stream, h->dSc, h->dCount);
+  bump_attempts_kernel<<<(nv + 255) / 256, 256, 0, h->stream>>>(h->dAttempt, h->dVioRows, nv);
+  launch_philox_normal(h->stream, h->dZ, ld, nv, N, h->cfg.seed, (unsigned)h->gen, h->shard_lo, h->dAttempt, h->dVioRows, h->num_sms);
+  dim3 grid((N + 7) / 8, nv);
+  resample_rows_kernel<<<grid, 256, 0, h->stream>>>(h->dZ, h->dY, ld, h->dA, N, h->dVioRows, h->cfg.diagonal_covariance, h->dD);
+  h->launches += 4;
+  if (h->cfg.keep_population || h->has_bounds) {
+    launch_feasibility(h->stream, h->dY, ld, nv, N, 0, h->dMean, h->dSc, h->has_bounds ? h->dLower : nullptr, h->dUpper,
+                       h->has_bounds ? h->dInfeasible : nullptr, h->cfg.keep_population ? h->dX : nullptr, ld, h->dVioRows, h->num_sms);
+    h->launches++;
+  }
+  return 0;
+}
+
+// updateConstraints (:347-385) + handleConstraints (:774-832)
+int update_and_handle_constraints(kcma* h) {
+  const int N = h->N, ld = h->ld, nc = (int)h->n_con;
+  const int lambda = (int)h->cur_lambda;
+  {
+    PhaseTimer t(h, "constraints");
+    launch_constraints_halfspace(h->stream, h->dY, ld, lambda, N, h->dMean, h->dSc, h->dShift, nc, h->dG, h->ldg, nullptr, h->num_sms);
+    launch_constraint_count(h->stream, h->dG, h->ldg, lambda, nc, h->dBounds, (h->gen == 1 && h->is_viability) ? 1 : 0, h->dViol, h->dSc);
+    h->launches += 2;
+    h->scalars_fresh = false;
+  }
+  for (int iter = 0; iter < 100000; iter++) {
+    if (pull_scalars(h)) return 1;
+    if (h->hSc->nonfinite) return fail(h, "Non finite value of constraint evaluation detected\n");
+    if (h->hSc->max_violation_count == 0) break;
+    int J, nv, aborted;
+    {
+      PhaseTimer t(h, "constraints");
+      launch_constraint_events(h->stream, h->dViol, h->dIndicator, h->ldg, lambda, nc, h->cfg.max_covariance_matrix_corrections, h->dEvSample,
+                               h->dEvCon, h->dVioRows, h->dCount, h->dSc);
+      h->launches++;
+      h->scalars_fresh = false;
+      CUDA_OK(h, cudaMemcpyAsync(h->hCount, h->dCount, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      if (pull_scalars(h)) return 1;
+      J = h->hCount[0]; nv = h->hCount[1]; aborted = h->hSc->adaptation_abort;
+      int splits = 1;
+      if (J > 0) {
+        launch_constraint_normals(h->stream, h->dEvSample, h->dEvCon, h->dCount, h->dY, ld, h->dNormal, ld, h->normal_lr, h->dU, ld, N, nc);
+        h->launches++;
+        if (!aborted) {
+          const int rows_padded = std::min(h->u_rows, round_up(J, 16) + 16);
+          launch_constraint_scale(h->stream, h->dU, ld, N, h->dEvSample, h->dCount, h->dViol, h->cov_adaption_factor, rows_padded);
+          splits = syrk_pick_splits(N, J, h->num_sms, h->max_splits);
+          launch_syrk_tt(h->stream, N, J, h->dU, ld, h->dWsplit, ld, splits);
+          h->launches += 2;
+        }
+      }
+      if (aborted) {
+        char buf[128];
+        snprintf(buf, sizeof(buf), "Exiting adaption loop, max adaptions (%zu) reached.\n", (size_t)h->cfg.max_covariance_matrix_corrections);
+        h->warn += buf;
+        break;
+      }
+      launch_caux(h->stream, h->dC, h->dCaux, ld, h->dWsplit, ld, splits, N, h->dCount);
+      h->launches++;
+    }
+    if (update_eigensystem(h, h->dCaux)) return 1;
+    {
+      PhaseTimer t(h, "constraints");
+      if (resample_violators(h, nv)) return 1;
+      // reEvaluateConstraints (:387-424)
+      launch_constraints_halfspace(h->stream, h->dY, ld, nv, N, h->dMean, h->dSc, h->dShift, nc, h->dG, h->ldg, h->dVioRows, h->num_sms);
+      launch_constraint_recount(h->stream, h->dG, h->ldg, nc, h->dBounds, h->dVioRows, h->dCount, nv, h->dViol, h->dIndicator);
+      launch_constraint_max(h->stream, h->dViol, lambda, h->dCount, h->dSc);
+      h->launches += 3;
+      h->scalars_fresh = false;
+    }
+  }
+  return 0;
+}
+
 int do_ask(kcma* h) {
-  if (h->has_constraints) return fail(h, "constraint path (viability regime) is not built into this libkcma yet");
+  if (h->has_constraints && check_mean_and_set_regime(h)) return 1;
   if (update_eigensystem(h, h->dC)) return 1;
-  return sample_population(h);
+  if (sample_population(h)) return 1;
+  if (h->has_constraints) return update_and_handle_constraints(h);
+  return 0;
 }
 
 int do_eval(kcma* h) {
@@ -481,7 +592,8 @@ int do_tell(kcma* h) {
   {
     PhaseTimer t(h, "sort");
     h->launches += launch_sort_index(h->stream, h->dF, lambda, h->dSortWs, h->dIdx, h->num_sms);
-    launch_rank_bookkeeping(h->stream, h->dF, h->dIdx, lambda, mu, nullptr, 1, h->dSc);
+    const int best_is_first = (!h->has_constraints || h->is_viability) ? 1 : 0;
+    launch_rank_bookkeeping(h->stream, h->dF, h->dIdx, lambda, mu, best_is_first ? nullptr : h->dViol, best_is_first, h->dSc);
     h->launches++;
     if (h->cfg.mu_type == KCMA_MU_PROPORTIONAL) { launch_proportional_weights(h->stream, h->dF, h->dIdx, mu, h->dW); h->launches++; }
   }
@@ -522,15 +634,18 @@ int do_tell(kcma* h) {
     PhaseTimer t(h, "paths");
     double* mean_new = h->dRed + (size_t)N * ld;
     double* best_x = mean_new + ld;
-    launch_best_update(h->stream, best_x, N, (unsigned)h->gen, h->dCurBest, h->dBestEver, h->dSc, nullptr, 0, 0, nullptr);
+    launch_best_update(h->stream, best_x, N, (unsigned)h->gen, h->dCurBest, h->dBestEver, h->dSc, h->has_constraints ? h->dG : nullptr, h->ldg,
+                       (int)h->n_con, h->dBestCon);
     launch_paths(h->stream, mean_new, h->dMean, h->dMeanOld, h->dMeanUpd, h->dT, h->dPs, h->dPc, h->dB, ld, h->dD, N,
                  h->cfg.diagonal_covariance, h->cs, h->cc, h->mueff, h->chi_n, (unsigned)h->gen, h->dSc);
     const double c1 = 2.0 / (pow(N + 1.3, 2) + h->mueff);
     const double cmu = std::min(1.0 - c1, 2.0 * (h->mueff - 2. + 1. / h->mueff) / (pow(N + 2.0, 2) + h->mueff));
     if (multi) launch_adapt_c(h->stream, h->dC, ld, h->dRed, ld, 1, N, h->dPc, c1, cmu, h->cc, h->cfg.diagonal_covariance, h->dSc);
     else launch_adapt_c(h->stream, h->dC, ld, h->dWsplit, ld, splits, N, h->dPc, c1, cmu, h->cc, h->cfg.diagonal_covariance, h->dSc);
+    const int viab = (h->has_constraints && h->is_viability) ? 1 : 0;
+    if (viab) { launch_viability_boundaries(h->stream, h->dG, h->ldg, (int)h->n_con, h->dIdx, mu, h->dBounds); h->launches++; }
     launch_sigma(h->stream, h->dC, ld, N, h->dMinSd, h->any_min_sd ? 1 : 0, h->cs, h->damp, h->chi_n, h->trace, h->cfg.is_sigma_bounded,
-                 h->cfg.mu_value > 1 ? 1 : 0, 0, h->cfg.global_success_learning_rate, h->cfg.target_success_rate, h->dSc);
+                 h->cfg.mu_value > 1 ? 1 : 0, viab, h->cfg.global_success_learning_rate, h->cfg.target_success_rate, h->dSc);
     h->launches += 7;
   }
   h->inj_x = false;
@@ -550,6 +665,8 @@ int end_of_generation(kcma* h) {
     push_scalars(h);
     return fail(h, "Non finite value of function evaluation detected: nan\n");
   }
+  if (h->hSc->best_valid_sample == ~0ull)
+    return fail(h, "no sample without constraint violations in this generation (the reference reads out of bounds here, CMAES.cpp.base:565)");
   if (h->hSc->eig_rejected) h->warn += "Min Eigenvalue smaller or equal 0.0 after Eigen decomp (no update possible).\n";
   if (h->hSc->warn_flat) { h->warn += "Sigma increased due to equal function values.\n"; }
   if (h->hSc->warn_minsd) { h->warn += "Sigma increased due to minimal standard deviation.\n"; }
@@ -611,7 +728,8 @@ void kcma_destroy(kcma_t* h) {
   void* ptrs[] = {h->dC, h->dB, h->dA, h->dD, h->dVT, h->dVTw, h->dGT, h->dEv, h->dPerm, h->dMean, h->dMeanOld, h->dMeanUpd, h->dT,
                   h->dPs, h->dPc, h->dZ, h->dY, h->dX, h->dF, h->dIdx, h->dSortWs, h->dW, h->dSelW, h->dSelS, h->dCount, h->dS,
                   h->dPartial, h->dWsplit, h->dRed, h->dBestEver, h->dCurBest, h->dLower, h->dUpper, h->dMinSd, h->dCoef, h->dShift,
-                  h->dSigmaSampling, h->dInfeasible, h->dFlush, h->dSc};
+                  h->dSigmaSampling, h->dInfeasible, h->dFlush, h->dSc, h->dG, h->dBounds, h->dNormal, h->dCaux, h->dBestCon, h->dU, h->dViol,
+                  h->dIndicator, h->dEvSample, h->dEvCon, h->dVioRows, h->dAttempt};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->hSc) cudaFreeHost(h->hSc);
   if (h->hCount) cudaFreeHost(h->hCount);
@@ -727,6 +845,20 @@ int kcma_create(const kcma_cfg* cfg, kcma_t** out) {
   CREATE_CUDA(dmalloc(&h->dCoef, ld)); CREATE_CUDA(dmalloc(&h->dShift, h->n_con + 1));
   CREATE_CUDA(dmalloc(&h->dSigmaSampling, 2)); CREATE_CUDA(dmalloc(&h->dInfeasible, h->max_local + 16));
   CREATE_CUDA(dmalloc(&h->dSc, 1));
+  CREATE_CUDA(dmalloc(&h->dAttempt, h->max_zrows + 16));
+  if (h->has_constraints) {
+    if (cfg->nranks > 1) CREATE_FAIL("the constraint path (viability regime) runs on one GPU in this build (nranks must be 1)");
+    if (cfg->constraint_family != KCMA_CON_HALFSPACE) CREATE_FAIL("unknown constraint family %d", cfg->constraint_family);
+    h->ldg = (long long)h->s_max;
+    h->u_rows = round_up((int)std::min<uint64_t>(h->n_con * h->s_max, 1u << 22), 16) + 32;
+    CREATE_CUDA(dmalloc(&h->dG, h->n_con * h->s_max)); CREATE_CUDA(dmalloc(&h->dBounds, h->n_con)); CREATE_CUDA(dmalloc(&h->dNormal, h->n_con * ld));
+    CREATE_CUDA(dmalloc(&h->dCaux, nn)); CREATE_CUDA(dmalloc(&h->dBestCon, h->n_con)); CREATE_CUDA(dmalloc(&h->dU, (size_t)h->u_rows * ld));
+    CREATE_CUDA(dmalloc(&h->dViol, h->s_max)); CREATE_CUDA(dmalloc(&h->dIndicator, h->n_con * h->s_max));
+    CREATE_CUDA(dmalloc(&h->dEvSample, h->n_con * h->s_max + 16)); CREATE_CUDA(dmalloc(&h->dEvCon, h->n_con * h->s_max + 16));
+    CREATE_CUDA(dmalloc(&h->dVioRows, h->s_max + 16));
+    h->normal_lr = 1.0 / (2.0 + N);                                           // ref :154
+    h->cov_adaption_factor = cfg->covariance_matrix_adaption_strength / (N + 2.);  // ref :155
+  }
   CREATE_CUDA(cudaMallocHost((void**)&h->hSc, sizeof(DevScalars)));
   CREATE_CUDA(cudaMallocHost((void**)&h->hCount, 4 * sizeof(int)));
   memset(h->hSc, 0, sizeof(DevScalars));
@@ -922,6 +1054,13 @@ bool find_array(kcma* h, const char* key, ArrRef* r) {
   A("Best Ever Variables", h->dBestEver, 1, N, ld)
   A("Current Best Variables", h->dCurBest, 1, N, ld)
   A("Objective Coefficients", h->dCoef, 1, N, ld)
+  if (h->has_constraints) {
+    A("Viability Boundaries", h->dBounds, 1, h->n_con, (int)h->n_con)
+    A("Normal Constraint Approximation", h->dNormal, h->n_con, N, ld)
+    A("Best Constraint Evaluations", h->dBestCon, 1, h->n_con, (int)h->n_con)
+    A("Constraint Evaluations", h->dG, h->n_con, h->s_max, (int)h->s_max)
+    A("Auxiliar Covariance Matrix", h->dCaux, N, N, ld)
+  }
 #undef A
   return false;
 }
@@ -981,8 +1120,16 @@ int kcma_set_array(kcma_t* h, const char* key, const double* in, size_t count) {
 
 int kcma_get_index_array(kcma_t* h, const char* key, uint64_t* out, size_t cap, size_t* count) {
   CUDA_OK(h, cudaSetDevice(h->device));
-  if (strcmp(key, "Sorting Index")) return fail(h, "unknown index key '%s'", key);
   const size_t n = h->cur_lambda;
+  if (!strcmp(key, "Sample Constraint Violation Counts")) {
+    const size_t m = h->has_constraints ? n : 0;
+    if (count) *count = m;
+    if (!out) return 0;
+    if (cap < m) return fail(h, "buffer too small for '%s'", key);
+    if (m) { CUDA_OK(h, cudaMemcpyAsync(out, h->dViol, sizeof(uint64_t) * m, cudaMemcpyDeviceToHost, h->stream)); CUDA_OK(h, cudaStreamSynchronize(h->stream)); }
+    return 0;
+  }
+  if (strcmp(key, "Sorting Index")) return fail(h, "unknown index key '%s'", key);
   if (count) *count = n;
   if (!out) return 0;
   if (cap < n) return fail(h, "buffer too small for '%s'", key);
@@ -1032,6 +1179,11 @@ int kcma_get_scalar(kcma_t* h, const char* key, double* out) {
   U("Current Generation", h->gen - 1) U("Model Evaluation Count", h->model_evals) U("Variable Count", h->N)
   U("Current Population Size", h->cur_lambda) U("Current Mu Value", h->cur_mu)
   U("Infeasible Sample Count", h->hSc->infeasible_sample_count)
+  U("Resampled Parameter Count", h->hSc->resampled_parameter_count)
+  U("Covariance Matrix Adaptation Count", h->hSc->cov_adaptation_count)
+  U("Max Constraint Violation Count", h->hSc->max_violation_count)
+  U("Constraint Evaluation Count", h->hSc->constraint_evaluation_count)
+  U("Covariance Matrix Adaption Factor", h->cov_adaption_factor) U("Normal Vector Learning Rate", h->normal_lr)
   U("Is Viability Regime", h->is_viability) U("Has Constraints", h->has_constraints)
   U("Best Valid Sample", (long long)h->hSc->best_valid_sample)
   U("Termination Criteria/Max Infeasible Resamplings", h->cfg.max_infeasible_resamplings)

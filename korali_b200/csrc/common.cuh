@@ -60,6 +60,13 @@ struct DevScalars {
   unsigned long long best_valid_sample;
   unsigned long long violating_samples;
   unsigned long long max_violation_count;
+  unsigned long long cov_adaptation_count;        // _covarianceMatrixAdaptationCount
+  unsigned long long resampled_parameter_count;   // _resampledParameterCount
+  unsigned long long constraint_evaluation_count; // _constraintEvaluationCount
+  int n_events;              // rank-1 corrections applied in this handleConstraints iteration
+  int adaptation_abort;      // "Exiting adaption loop, max adaptions reached" (CMAES.cpp.base:789-793)
+  int mean_feasible;         // checkMeanAndSetRegime: all g_c(mean) <= 0
+  int pad2;
   int nonfinite;             // a non-finite F(x) / constraint value was produced
   int eig_rejected;          // min eigenvalue <= 0: previous B, D kept (CMAES.cpp.base:876-880)
   int warn_flat;             // "Sigma increased due to equal function values."

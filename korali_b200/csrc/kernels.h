@@ -73,4 +73,21 @@ void launch_eig_commit(cudaStream_t st, const double* VTw, int ld, int n, const 
                        double* D, double* VT, const DevScalars* sc);
 void launch_eig_diagonal(cudaStream_t st, const double* C, int ldc, int n, double* D, DevScalars* sc);
 
+// constraints.cu
+void launch_constraints_mean(cudaStream_t st, const double* mean, const double* shift, int n, int n_con, DevScalars* sc);
+void launch_constraint_count(cudaStream_t st, const double* G, long long ldg, int lambda, int n_con, double* bounds, int set_bounds,
+                             unsigned long long* viol, DevScalars* sc);
+void launch_constraint_events(cudaStream_t st, const unsigned long long* viol, const unsigned char* indicator, long long ldg, int lambda,
+                              int n_con, unsigned long long max_corrections, int* ev_sample, int* ev_con, int* vio_rows, int* counts_out,
+                              DevScalars* sc);
+void launch_constraint_normals(cudaStream_t st, const int* ev_sample, const int* ev_con, const int* counts, const double* Y, int ldy,
+                               double* normal, int ldn, double lr, double* U, int ldu, int n, int n_con);
+void launch_constraint_scale(cudaStream_t st, double* U, int ldu, int n, const int* ev_sample, const int* counts,
+                             const unsigned long long* viol, double beta, int rows_padded);
+void launch_caux(cudaStream_t st, const double* C, double* Caux, int ldc, const double* W, int ldw, int splits, int n, const int* counts);
+void launch_constraint_recount(cudaStream_t st, const double* G, long long ldg, int n_con, const double* bounds, const int* rows,
+                               const int* counts, int max_rows, unsigned long long* viol, unsigned char* indicator);
+void launch_constraint_max(cudaStream_t st, const unsigned long long* viol, int lambda, const int* counts, DevScalars* sc);
+void launch_add_resampled(cudaStream_t st, DevScalars* sc, const int* counts);
+
 }  // namespace kc
