@@ -383,9 +383,9 @@ int update_eigensystem(kcma* h, const double* dM) {
     if (pull_scalars(h)) return 1;
     if (h->hSc->jacobi_rotations == 0) break;
   }
-  launch_rayleigh(h->stream, h->dGT, h->dVTw, ld, N, h->dEv);
+  launch_rayleigh(h->stream, h->dGT, h->dVTw, ld, N, h->dEv, h->dT);   // dT (scratch of tell()) holds the signs here
   launch_eig_order(h->stream, h->dEv, N, h->dPerm, h->dSc);
-  launch_eig_commit(h->stream, h->dVTw, ld, N, h->dPerm, h->dEv, h->dB, h->dA, h->dD, h->dVT, h->dSc);
+  launch_eig_commit(h->stream, h->dVTw, ld, N, h->dPerm, h->dEv, h->dT, h->dB, h->dA, h->dD, h->dVT, h->dSc);
   h->launches += 3;
   h->scalars_fresh = false;
   return 0;

@@ -66,20 +66,30 @@ jacobi_step_kernel(double* __restrict__ GT, double* __restrict__ VT, int ld, int
   }
 }
 
-// ev[i] = v_i . g_i ; one warp per vector.
+// ev[i] = v_i . g_i ; sign[i] = -1 if the component of largest magnitude (first on ties) is negative
+// (sign convention shared with the CPU oracle). One warp per vector.
 __global__ void __launch_bounds__(256)
-rayleigh_kernel(const double* __restrict__ GT, const double* __restrict__ VT, int ld, int n, double* __restrict__ ev) {
+rayleigh_kernel(const double* __restrict__ GT, const double* __restrict__ VT, int ld, int n, double* __restrict__ ev,
+                double* __restrict__ sign) {
   const int lane = threadIdx.x & 31;
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (i >= n) return;
-  double a = 0.0, nv = 0.0;
+  double a = 0.0, nv = 0.0, best = -1.0, bval = 0.0;
+  int bidx = 0x7fffffff;
   for (int k = lane; k < n; k += 32) {
     const double v = VT[(size_t)i * ld + k];
     a += v * GT[(size_t)i * ld + k];
     nv += v * v;
+    if (fabs(v) > best) { best = fabs(v); bval = v; bidx = k; }
   }
   a = warp_sum_butterfly(a); nv = warp_sum_butterfly(nv);
-  if (lane == 0) ev[i] = a / nv;
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const double ob = __shfl_xor_sync(0xffffffffu, best, off), ov = __shfl_xor_sync(0xffffffffu, bval, off);
+    const int oi = __shfl_xor_sync(0xffffffffu, bidx, off);
+    if (ob > best || (ob == best && oi < bidx)) { best = ob; bval = ov; bidx = oi; }
+  }
+  if (lane == 0) { ev[i] = a / nv; sign[i] = bval < 0.0 ? -1.0 : 1.0; }
 }
 
 // perm = ascending order of |ev| (GSL_EIGEN_SORT_ABS_ASC; ties by index), min/max eigenvalue, acceptance test
@@ -117,7 +127,7 @@ eig_order_kernel(const double* __restrict__ ev, int n, int* __restrict__ perm, D
 // 32x32 smem transpose tiles. On rejection nothing is written.
 __global__ void __launch_bounds__(256)
 eig_commit_kernel(const double* __restrict__ VTw, int ld, int n, const int* __restrict__ perm, const double* __restrict__ ev,
-                  double* __restrict__ B, double* __restrict__ A, double* __restrict__ D, double* __restrict__ VT,
+                  const double* __restrict__ sign, double* __restrict__ B, double* __restrict__ A, double* __restrict__ D, double* __restrict__ VT,
                   const DevScalars* __restrict__ sc) {
   if (sc->eig_rejected) return;
   __shared__ double tile[32][33];
@@ -127,7 +137,7 @@ eig_commit_kernel(const double* __restrict__ VTw, int ld, int n, const int* __re
     const int e = e0 + r, d = d0 + tx;
     double v = 0.0;
     if (e < n && d < n) {
-      v = VTw[(size_t)perm[e] * ld + d];
+      v = sign[perm[e]] * VTw[(size_t)perm[e] * ld + d];
       VT[(size_t)e * ld + d] = v;
     }
     tile[r][tx] = v;
@@ -183,16 +193,16 @@ void launch_jacobi_sweep(cudaStream_t st, double* GT, double* VT, int ld, int n,
   for (int step = 0; step < np - 1; step++) jacobi_step_kernel<<<np / 2, 128, 0, st>>>(GT, VT, ld, n, np, step, tol, sc);
   if (launches) *launches += np;
 }
-void launch_rayleigh(cudaStream_t st, const double* GT, const double* VT, int ld, int n, double* ev) {
-  rayleigh_kernel<<<(n + 7) / 8, 256, 0, st>>>(GT, VT, ld, n, ev);
+void launch_rayleigh(cudaStream_t st, const double* GT, const double* VT, int ld, int n, double* ev, double* sign) {
+  rayleigh_kernel<<<(n + 7) / 8, 256, 0, st>>>(GT, VT, ld, n, ev, sign);
 }
 void launch_eig_order(cudaStream_t st, const double* ev, int n, int* perm, DevScalars* sc) {
   eig_order_kernel<<<1, 1024, 0, st>>>(ev, n, perm, sc);
 }
-void launch_eig_commit(cudaStream_t st, const double* VTw, int ld, int n, const int* perm, const double* ev, double* B, double* A,
-                       double* D, double* VT, const DevScalars* sc) {
+void launch_eig_commit(cudaStream_t st, const double* VTw, int ld, int n, const int* perm, const double* ev, const double* sign,
+                       double* B, double* A, double* D, double* VT, const DevScalars* sc) {
   dim3 grid((n + 31) / 32, (n + 31) / 32);
-  eig_commit_kernel<<<grid, 256, 0, st>>>(VTw, ld, n, perm, ev, B, A, D, VT, sc);
+  eig_commit_kernel<<<grid, 256, 0, st>>>(VTw, ld, n, perm, ev, sign, B, A, D, VT, sc);
 }
 void launch_eig_diagonal(cudaStream_t st, const double* C, int ldc, int n, double* D, DevScalars* sc) {
   eig_diagonal_kernel<<<1, 256, 0, st>>>(C, ldc, n, D, sc);

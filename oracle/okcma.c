@@ -394,7 +394,14 @@ int okcma_eigen(uint64_t n64, const double* c, double* w, double* q) {
   }
   for (int i = 0; i < n; i++) {
     w[i] = d[ord[i]];
-    for (int j = 0; j < n; j++) q[j * n + i] = V[j * n + ord[i]];
+    /* Sign convention (eigenvectors are defined up to sign; GSL's choice is an implementation detail): the
+     * component of largest magnitude (first one on ties) is made positive. The device solver does the same, so
+     * free-running device and oracle runs draw the same samples from the same z. */
+    int jm = 0;
+    for (int j = 1; j < n; j++)
+      if (fabs(V[j * n + ord[i]]) > fabs(V[jm * n + ord[i]])) jm = j;
+    const double sg = V[jm * n + ord[i]] < 0 ? -1.0 : 1.0;
+    for (int j = 0; j < n; j++) q[j * n + i] = sg * V[j * n + ord[i]];
   }
   free(ord); free(d); free(e); free(V);
   return rc;

@@ -300,3 +300,74 @@ def test_converges_to_the_optimum_within_1e8(name, case, max_gens):
     xb = s.get("Best Ever Variables")
     target = 1.0 if case["objective"] == "NegRosenbrock" else 0.0
     assert np.abs(xb - target).max() < 1e-3
+
+
+# ---------------------------------------------------------------- free-running (no injection) ---------------
+def _track(s, o, gens, tol, int_keys=(), label=""):
+    for g in range(gens):
+        s.run_generation(); o.run_generation()
+        for k in int_keys:
+            assert s.scalar(k) == o.scalar(k), (label, g, k, s.scalar(k), o.scalar(k))
+        assert np.array_equal(s.get_index("Sorting Index"), o.get_index("Sorting Index")), (label, g)
+        for k in ["Current Mean", "Evolution Path", "Conjugate Evolution Path", "Covariance Matrix"]:
+            e = relerr(s.get(k), o.get(k))
+            assert e < tol, (label, g, k, e)
+        assert abs(s.scalar("Sigma") - o.scalar("Sigma")) < tol * o.scalar("Sigma"), (label, g)
+
+
+def test_free_running_matches_oracle_philox_stream():
+    """No injection at all: device Philox + device eigensolver vs the oracle's restatement of both (same counters,
+    same eigenvector sign convention). Looser tolerance: eigenvectors of two different solvers agree to ~eps*|C|/gap."""
+    case = dict(n=16, population_size=48, objective="NegRosenbrock", initial_value=0.1, initial_stddev=0.7, seed=99)
+    s = _lib.Solver(**case); o = O.Oracle(**case); o.set_scalar("Oracle/RNG Kind", 1)
+    _track(s, o, 25, 1e-8, label="rosenbrock")
+
+
+def _constrained_problem(n):
+    """4 half-space constraints g_c(x) = -(x_c - shift_c) <= 0 after helpers.py activeMax*: x_0, x_1 >= 1 (active at the
+    optimum), x_2, x_3 >= -1 (violated by the initial mean -> viability regime, inactive at the optimum)."""
+    iv = np.zeros(n); iv[0] = iv[1] = 4.0; iv[2] = iv[3] = -2.0
+    return dict(objective="NegSphereSin2", constraint_family="HalfSpace", n_constraints=4,
+                constraint_shift=np.array([1.0, 1.0, -1.0, -1.0]), lower_bound=-10.0, upper_bound=10.0, initial_value=iv,
+                initial_stddev=1.0, is_sigma_bounded=1)
+
+
+def test_constraint_path_viability_regime_against_oracle():
+    """config 5 (reduced): 4 half-space constraints, infeasible initial mean -> viability regime -> regime switch.
+    Counters must agree exactly, state within tolerance (sequential EMA restated in parallel)."""
+    case = dict(n=20, population_size=64, viability_population_size=64, seed=1337, **_constrained_problem(20))
+    s = _lib.Solver(**case); o = O.Oracle(**case); o.set_scalar("Oracle/RNG Kind", 1)
+    ints = ["Is Viability Regime", "Current Population Size", "Covariance Matrix Adaptation Count", "Resampled Parameter Count",
+            "Constraint Evaluation Count", "Max Constraint Violation Count", "Infeasible Sample Count", "Best Valid Sample"]
+    saw_regime_switch = False
+    for g in range(40):
+        s.run_generation(); o.run_generation()
+        for k in ints:
+            assert s.scalar(k) == o.scalar(k), (g, k, s.scalar(k), o.scalar(k))
+        saw_regime_switch |= (s.scalar("Is Viability Regime") == 0)
+        assert np.array_equal(s.get_index("Sorting Index"), o.get_index("Sorting Index")), g
+        assert np.array_equal(s.get_index("Sample Constraint Violation Counts"), o.get_index("Sample Constraint Violation Counts")), g
+        for k in ["Current Mean", "Evolution Path", "Conjugate Evolution Path", "Covariance Matrix", "Viability Boundaries",
+                  "Normal Constraint Approximation", "Best Ever Variables"]:
+            e = relerr(s.get(k), o.get(k))
+            assert e < 1e-8, (g, k, e)
+        assert abs(s.scalar("Sigma") - o.scalar("Sigma")) < 1e-8 * o.scalar("Sigma"), g
+    assert saw_regime_switch
+    assert o.scalar("Covariance Matrix Adaptation Count") > 0
+
+
+def test_constrained_optimum_config5():
+    """config 5: N=100, lambda=8192 (both population sizes), 4 synthetic constraints, infeasible initial mean. Optimum of
+    -sum(x^2+sin^2 x) on the feasible set: x_0 = x_1 = 1, all else 0: F* = -2 (1 + sin(1)^2)."""
+    case = dict(n=100, population_size=8192, viability_population_size=8192, seed=1337, **_constrained_problem(100))
+    s = _lib.Solver(**case)
+    s.set_scalar("Termination Criteria/Max Generations", 400)
+    s.set_scalar("Termination Criteria/Max Model Evaluations", 1e15)
+    done = s.run(401)
+    fstar = -2 * (1 + np.sin(1.0) ** 2)
+    best = s.scalar("Best Ever Value")
+    xb = s.get("Best Ever Variables")
+    print("config5: best %.10f (F* %.10f) after %d generations, corrections %d" % (best, fstar, done, s.scalar("Covariance Matrix Adaptation Count")))
+    assert s.scalar("Is Viability Regime") == 0
+    assert np.all(xb[:2] >= 1.0 - 1e-9) and np.all(xb[2:4] >= -1.0)
+    assert abs(best - fstar) < 1e-6 and best <= fstar + 1e-9
