@@ -217,6 +217,7 @@ def ours_arm(args, rank, world):
         "phases_ms_per_generation": {k: (v[0] / args.steps) for k, v in phases.items()},
         "rank_mu": {"kernel": "syrk_tt_kernel", "avg_ms": rk_avg, "achieved_tflops": (f_rank / (rk_avg * 1e-3) * 1e-12) if rk_avg > 0 else 0.0,
                     "algorithmic_flops_per_launch": f_rank},
+        "eigen_sweeps_per_generation": s.timing("eigen_sweeps")[1] / args.steps,
         "gens_per_sec_excluding_eigen": 1e3 / max(ms_step - phases["eigen"][0] / args.steps, 1e-9),
     }
     if cpu:

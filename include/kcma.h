@@ -47,7 +47,8 @@ enum {
 /* Built-in constraint families g_c(x) <= 0 feasible (CMAES.cpp.base:333-334). */
 enum {
   KCMA_CON_NONE = 0,
-  KCMA_CON_HALFSPACE = 1      /* g_c(x) = -(x_{c} - shift_c), c < n_constraints <= N  (helpers.py:20-37 activeMax*) */
+  KCMA_CON_HALFSPACE = 1,     /* g_c(x) = -(x_{c} - shift_c), c < n_constraints <= N  (helpers.py:20-37 activeMax*) */
+  KCMA_CON_EXTERNAL = 100     /* constraints evaluated by kcma_set_host_constraints() */
 };
 
 /* What kcma_inject overwrites (parity hooks: "injecting the reference's own z draws and fitness values"). */
@@ -144,6 +145,18 @@ int kcma_check_termination(kcma_t* h, int* finished, const char** reason);
 /* Experiment::run loop (experiment.cpp.base:57-100): while (!checkTermination) runGeneration.
  * Runs at most max_generations more generations; *done = number actually run. */
 int kcma_run(kcma_t* h, uint64_t max_generations, uint64_t* done);
+
+/* ---- batched HOST conduit (user-supplied Python / C++ models) -------------------------
+ * The reference ships every sample to the user model as a JSON message (Conduit::runSample, conduit.cpp.base:29-88,
+ * Optimization::evaluate / evaluateConstraints, optimization.cpp.base:11-34). Here the whole population crosses the
+ * boundary once per generation: X is copied to the host, the callback fills F (or G), the values go back to HBM.
+ * This is a conduit for models that only exist on the host, not a compute fallback: sampling, ranking and the
+ * distribution update stay on the device. x is row-major rows x n; g_out is [n_constraints][rows]. */
+typedef void (*kcma_host_objective_fn)(void* user, const double* x, uint64_t rows, uint64_t n, double* f_out);
+typedef void (*kcma_host_constraints_fn)(void* user, const double* x, uint64_t rows, uint64_t n, double* g_out,
+                                         uint64_t n_constraints);
+int kcma_set_host_objective(kcma_t* h, kcma_host_objective_fn fn, void* user);
+int kcma_set_host_constraints(kcma_t* h, kcma_host_constraints_fn fn, void* user);
 
 /* ---- parity hooks ------------------------------------------------------------------- */
 int kcma_inject(kcma_t* h, int kind, const double* host, size_t count);

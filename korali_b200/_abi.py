@@ -12,7 +12,7 @@ KCMA_ABI_VERSION = 1
 MU_TYPES = {"Linear": 0, "Equal": 1, "Logarithmic": 2, "Proportional": 3}
 OBJECTIVES = {"NegSphere": 0, "NegRosenbrock": 1, "NegAckley": 2, "NegEllipsoid": 3, "NegSumSq": 4,
               "NegSphereSin2": 5, "External": 100}
-CONSTRAINTS = {"None": 0, "HalfSpace": 1}
+CONSTRAINTS = {"None": 0, "HalfSpace": 1, "External": 100}
 INJ_Z, INJ_BDZ, INJ_X, INJ_F, INJ_BD = 0, 1, 2, 3, 4
 
 _dp = C.POINTER(C.c_double)

@@ -46,7 +46,22 @@ def build(force=False, verbose=False):
     if rebuilt or not os.path.exists(OUT):
         cmd = ["nvcc", "-shared", "-o", OUT] + objs + ARCH + ["-Xcompiler", "-fPIC", "-ldl"]
         subprocess.check_call(cmd)
+    build_host(force)
     return OUT
+
+
+def build_host(force=False):
+    """The pybind11 host shim (korali_b200/_host*.so): Korali's Engine/Experiment surface above the C ABI."""
+    import sysconfig
+    import pybind11
+    src = os.path.join(HERE, "host", "korali_host.cpp")
+    out = os.path.join(HERE, "_host" + sysconfig.get_config_var("EXT_SUFFIX"))
+    if not (force or _newer(src, out) or _newer(OUT, out) or _newer(os.path.join(HERE, "..", "include", "kcma.h"), out)):
+        return out
+    cmd = ["g++", "-O2", "-shared", "-fPIC", "-std=c++17", "-fvisibility=hidden", "-I", pybind11.get_include(),
+           "-I", sysconfig.get_paths()["include"], src, "-o", out, "-L", HERE, "-lkcma", "-Wl,-rpath,$ORIGIN"]
+    subprocess.check_call(cmd)
+    return out
 
 
 if __name__ == "__main__":

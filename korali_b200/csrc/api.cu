@@ -98,6 +98,10 @@ struct kcma {
   // injections
   bool inj_z = false, inj_bd = false, inj_y = false, inj_x = false, inj_f = false;
   bool vt_valid = false;
+  // batched host conduit
+  kcma_host_objective_fn host_obj = nullptr; void* host_obj_user = nullptr;
+  kcma_host_constraints_fn host_con = nullptr; void* host_con_user = nullptr;
+  std::vector<double> hX, hF, hG;
   // nccl
   ncclComm_t comm = nullptr;
   // timing
@@ -369,19 +373,31 @@ int update_eigensystem(kcma* h, const double* dM) {
     return 0;
   }
   ensure_vt(h);
+  const double tol = 4.0 * 2.220446049250313e-16 * sqrt((double)N);
+  const int max_sweeps = 40;
+  if (eigen_small_fits(N)) {  // the whole solver in one launch, everything in one SM's shared memory
+    launch_eigen_small(h->stream, dM, ld, N, h->dVT, h->dB, h->dA, h->dD, tol, max_sweeps, h->dSc);
+    h->launches += 1;
+    h->scalars_fresh = false;
+    return 0;
+  }
   CUDA_OK(h, cudaMemcpyAsync(h->dVTw, h->dVT, sizeof(double) * (size_t)N * ld, cudaMemcpyDeviceToDevice, h->stream));
   // GT = VT * M  (M symmetric): GT[i][j] = sum_k VT[i][k] M[j][k]
   launch_gemm_tn(h->stream, N, N, N, h->dVTw, ld, dM, ld, h->dGT, ld);
   h->launches += 1;
-  const double tol = 4.0 * 2.220446049250313e-16 * sqrt((double)N);
-  const int max_sweeps = 40;
   for (int sweep = 0; sweep < max_sweeps; sweep++) {
     int l = 0;
-    launch_jacobi_sweep(h->stream, h->dGT, h->dVTw, ld, N, tol, h->dSc, &l);
+    h->phases["eigen_sweeps"].calls++;
+    launch_jacobi_block_sweep(h->stream, h->dGT, h->dVTw, ld, N, tol, h->dSc, &l);
     h->launches += l;
     h->scalars_fresh = false;
     if (pull_scalars(h)) return 1;
     if (h->hSc->jacobi_rotations == 0) break;
+    // quadratic convergence: once every rotated pair was already orthogonal to 1e-10, what is left after this sweep is
+    // ~1e-20/gap and the confirmation sweep (a full pass that rotates nothing) can be skipped
+    double max_rel;
+    memcpy(&max_rel, &h->hSc->jacobi_max_rel_bits, sizeof(double));
+    if (max_rel < 1e-10) break;
   }
   launch_rayleigh(h->stream, h->dGT, h->dVTw, ld, N, h->dEv, h->dT);   // dT (scratch of tell()) holds the signs here
   launch_eig_order(h->stream, h->dEv, N, h->dPerm, h->dSc);
@@ -451,14 +467,75 @@ int sample_population(kcma* h) {
   return 0;
 }
 
+__global__ void gather_rows_kernel(const double* __restrict__ X, int ld, int n, const int* __restrict__ rows, int count, double* __restrict__ out) {
+  const long long total = (long long)count * n;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int li = (int)(i / n), d = (int)(i - (long long)li * n);
+    out[i] = X[(size_t)rows[li] * ld + d];
+  }
+}
+__global__ void scatter_g_kernel(const double* __restrict__ gin, int count, int n_con, const int* __restrict__ rows, double* __restrict__ G,
+                                 long long ldg, DevScalars* sc) {
+  const long long total = (long long)count * n_con;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i / count), li = (int)(i - (long long)c * count);
+    const double g = gin[i];
+    if (!isfinite(g)) atomicExch(&sc->nonfinite, 1);
+    G[(size_t)c * ldg + (rows ? rows[li] : li)] = g;
+  }
+}
+
+// Constraint evaluations of the listed samples (rows == nullptr: all `count` samples) into dG, either with the built-in
+// device family or through the batched host conduit (X -> host, user functions, G -> device).
+int evaluate_constraints(kcma* h, const int* dRows, int count) {
+  const int N = h->N, ld = h->ld, nc = (int)h->n_con;
+  if (count <= 0) return 0;
+  if (!h->host_con) {
+    launch_constraints_halfspace(h->stream, h->dY, ld, count, N, h->dMean, h->dSc, h->dShift, nc, h->dG, h->ldg, dRows, h->num_sms);
+    h->launches++;
+    return 0;
+  }
+  // X of these samples is current in dX (keep_population is forced on with a host conduit)
+  h->hX.resize((size_t)count * N); h->hG.resize((size_t)count * nc);
+  double* dTmp = h->dU;  // scratch: at least n_con*s_max rows x ld
+  if (dRows) {
+    gather_rows_kernel<<<h->num_sms * 4, 256, 0, h->stream>>>(h->dX, ld, N, dRows, count, dTmp);
+    CUDA_OK(h, cudaMemcpyAsync(h->hX.data(), dTmp, sizeof(double) * (size_t)count * N, cudaMemcpyDeviceToHost, h->stream));
+  } else {
+    CUDA_OK(h, cudaMemcpy2DAsync(h->hX.data(), sizeof(double) * N, h->dX, sizeof(double) * ld, sizeof(double) * N, count, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  h->host_con(h->host_con_user, h->hX.data(), (uint64_t)count, (uint64_t)N, h->hG.data(), (uint64_t)nc);
+  CUDA_OK(h, cudaMemcpyAsync(dTmp, h->hG.data(), sizeof(double) * (size_t)count * nc, cudaMemcpyHostToDevice, h->stream));
+  scatter_g_kernel<<<h->num_sms * 2, 256, 0, h->stream>>>(dTmp, count, nc, dRows, h->dG, h->ldg, h->dSc);
+  h->launches += 2;
+  return 0;
+}
+
 // checkMeanAndSetRegime (CMAES.cpp.base:315-345)
 int check_mean_and_set_regime(kcma* h) {
   if (!h->is_viability) return 0;
-  if (h->cfg.constraint_family != KCMA_CON_HALFSPACE) return fail(h, "no constraint functions defined");
-  launch_constraints_mean(h->stream, h->dMean, h->dShift, h->N, (int)h->n_con, h->dSc);
-  h->launches++;
-  h->scalars_fresh = false;
-  if (pull_scalars(h)) return 1;
+  if (h->host_con) {
+    std::vector<double> m(h->N), g(h->n_con);
+    CUDA_OK(h, cudaMemcpyAsync(m.data(), h->dMean, sizeof(double) * h->N, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    h->host_con(h->host_con_user, m.data(), 1, (uint64_t)h->N, g.data(), h->n_con);
+    if (pull_scalars(h)) return 1;
+    h->hSc->constraint_evaluation_count += 1;
+    int ok = 1;
+    for (uint64_t c = 0; c < h->n_con; c++) {
+      if (!std::isfinite(g[c])) return fail(h, "Non finite value of constraint evaluation %lu detected: %f\n", (unsigned long)c, g[c]);
+      if (g[c] > 0.0) ok = 0;
+    }
+    h->hSc->mean_feasible = ok;
+    if (push_scalars(h)) return 1;
+  } else {
+    if (h->cfg.constraint_family != KCMA_CON_HALFSPACE) return fail(h, "no constraint functions defined");
+    launch_constraints_mean(h->stream, h->dMean, h->dShift, h->N, (int)h->n_con, h->dSc);
+    h->launches++;
+    h->scalars_fresh = false;
+    if (pull_scalars(h)) return 1;
+  }
   if (h->hSc->nonfinite) return fail(h, "Non finite value of constraint evaluation detected\n");
   if (!h->hSc->mean_feasible) return 0;
   // mean inside the domain: leave the viability regime for good and re-initialise (:336-344)
@@ -494,9 +571,9 @@ int update_and_handle_constraints(kcma* h) {
   const int lambda = (int)h->cur_lambda;
   {
     PhaseTimer t(h, "constraints");
-    launch_constraints_halfspace(h->stream, h->dY, ld, lambda, N, h->dMean, h->dSc, h->dShift, nc, h->dG, h->ldg, nullptr, h->num_sms);
+    if (evaluate_constraints(h, nullptr, lambda)) return 1;
     launch_constraint_count(h->stream, h->dG, h->ldg, lambda, nc, h->dBounds, (h->gen == 1 && h->is_viability) ? 1 : 0, h->dViol, h->dSc);
-    h->launches += 2;
+    h->launches += 1;
     h->scalars_fresh = false;
   }
   for (int iter = 0; iter < 100000; iter++) {
@@ -539,10 +616,10 @@ int update_and_handle_constraints(kcma* h) {
       PhaseTimer t(h, "constraints");
       if (resample_violators(h, nv)) return 1;
       // reEvaluateConstraints (:387-424)
-      launch_constraints_halfspace(h->stream, h->dY, ld, nv, N, h->dMean, h->dSc, h->dShift, nc, h->dG, h->ldg, h->dVioRows, h->num_sms);
+      if (evaluate_constraints(h, h->dVioRows, nv)) return 1;
       launch_constraint_recount(h->stream, h->dG, h->ldg, nc, h->dBounds, h->dVioRows, h->dCount, nv, h->dViol, h->dIndicator);
       launch_constraint_max(h->stream, h->dViol, lambda, h->dCount, h->dSc);
-      h->launches += 3;
+      h->launches += 2;
       h->scalars_fresh = false;
     }
   }
@@ -560,7 +637,19 @@ int do_ask(kcma* h) {
 int do_eval(kcma* h) {
   h->model_evals += h->cur_lambda;  // ref :214
   if (h->inj_f) { h->inj_f = false; return 0; }
-  if (h->cfg.objective == KCMA_OBJ_EXTERNAL) return fail(h, "objective is External: inject the Value Vector with kcma_inject(KCMA_INJ_F) before eval");
+  if (h->host_obj) {  // batched host conduit
+    PhaseTimer t(h, "host_objective");
+    const size_t ls = local_samples(h), N = h->N;
+    h->hX.resize(ls * N); h->hF.resize(ls);
+    CUDA_OK(h, cudaMemcpy2DAsync(h->hX.data(), sizeof(double) * N, h->dX, sizeof(double) * h->ld, sizeof(double) * N, ls, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    h->host_obj(h->host_obj_user, h->hX.data(), (uint64_t)ls, (uint64_t)N, h->hF.data());
+    for (size_t i = 0; i < ls; i++)  // ref: optimization.cpp.base:32-33
+      if (!std::isfinite(h->hF[i])) return fail(h, "Non finite value of function evaluation detected: %f\n", h->hF[i]);
+    CUDA_OK(h, cudaMemcpyAsync(h->dF + h->shard_lo, h->hF.data(), sizeof(double) * ls, cudaMemcpyHostToDevice, h->stream));
+    return 0;
+  }
+  if (h->cfg.objective == KCMA_OBJ_EXTERNAL) return fail(h, "objective is External: inject the Value Vector with kcma_inject(KCMA_INJ_F) or set a host objective before eval");
   PhaseTimer t(h, "objective");
   const long long ls = (long long)local_samples(h);
   double* f_local = h->dF + h->shard_lo;
@@ -848,7 +937,7 @@ int kcma_create(const kcma_cfg* cfg, kcma_t** out) {
   CREATE_CUDA(dmalloc(&h->dAttempt, h->max_zrows + 16));
   if (h->has_constraints) {
     if (cfg->nranks > 1) CREATE_FAIL("the constraint path (viability regime) runs on one GPU in this build (nranks must be 1)");
-    if (cfg->constraint_family != KCMA_CON_HALFSPACE) CREATE_FAIL("unknown constraint family %d", cfg->constraint_family);
+    if (cfg->constraint_family != KCMA_CON_HALFSPACE && cfg->constraint_family != KCMA_CON_EXTERNAL) CREATE_FAIL("unknown constraint family %d", cfg->constraint_family);
     h->ldg = (long long)h->s_max;
     h->u_rows = round_up((int)std::min<uint64_t>(h->n_con * h->s_max, 1u << 22), 16) + 32;
     CREATE_CUDA(dmalloc(&h->dG, h->n_con * h->s_max)); CREATE_CUDA(dmalloc(&h->dBounds, h->n_con)); CREATE_CUDA(dmalloc(&h->dNormal, h->n_con * ld));
@@ -884,6 +973,18 @@ int kcma_create(const kcma_cfg* cfg, kcma_t** out) {
 #undef CREATE_FAIL
 #undef CREATE_CUDA
   *out = h;
+  return 0;
+}
+
+int kcma_set_host_objective(kcma_t* h, kcma_host_objective_fn fn, void* user) {
+  if (fn && !h->cfg.keep_population) return fail(h, "a host objective needs keep_population = 1 (X is copied to the host every generation)");
+  h->host_obj = fn; h->host_obj_user = user;
+  return 0;
+}
+int kcma_set_host_constraints(kcma_t* h, kcma_host_constraints_fn fn, void* user) {
+  if (!h->has_constraints) return fail(h, "the problem has no constraints (n_constraints = 0)");
+  if (fn && !h->cfg.keep_population) return fail(h, "host constraints need keep_population = 1 (X is copied to the host)");
+  h->host_con = fn; h->host_con_user = user;
   return 0;
 }
 
@@ -1343,6 +1444,7 @@ int kcma_k_eigen(int device, uint64_t n, const double* c, double* eigenvalues, d
   int rc = kcma_set_array(h, "Covariance Matrix", c, n * n);
   if (!rc) rc = update_eigensystem(h, h->dC);
   if (!rc) rc = pull_scalars(h);
+  if (!rc) { cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) rc = fail(nullptr, "CUDA error in the eigensolver: %s", cudaGetErrorString(e)); }
   if (!rc && h->hSc->eig_rejected) {  // report the raw spectrum anyway (unsorted acceptance is the caller's business)
     rc = fail(nullptr, "matrix is not positive definite: eigensystem rejected (CMAES.cpp.base:876-880)");
   }

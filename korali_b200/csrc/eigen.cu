@@ -9,9 +9,12 @@
 // signed). Vectors are stored as ROWS (VT, GT) so each rotation touches contiguous memory.
 // One launch per round-robin step (n/2 disjoint pairs), one CTA per pair.
 #include "common.cuh"
+#include <stdlib.h>
 #include "kernels.h"
 
 namespace kc {
+
+__global__ void reset_rotations_kernel(DevScalars* sc) { sc->jacobi_rotations = 0; sc->jacobi_max_rel_bits = 0ull; }
 
 // Round-robin (chess tournament) schedule over np = even number of players; step in [0, np-1), k in [0, np/2).
 __device__ __forceinline__ void rr_pair(int np, int step, int k, int& p, int& q) {
@@ -63,6 +66,225 @@ jacobi_step_kernel(double* __restrict__ GT, double* __restrict__ VT, int ld, int
     gp[i] = c * x - s * y; gq[i] = s * x + c * y;
     const double u = vp[i], v = vq[i];
     vp[i] = c * u - s * v; vq[i] = s * u + c * v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Version 2a: BLOCKED one-sided Jacobi step. The unblocked step above streams all of G and V (16 MB at N=1000)
+// through the SMs for every one of the N-1 steps of a sweep. Here a CTA owns a PAIR OF ROW BLOCKS (BR rows of GT and
+// of VT each), stages them in shared memory (2*2*BR*N*8 B = 128 KB at N=1000, BR=4), performs all BR*BR cross-block
+// rotations on-chip (BR rounds of BR disjoint pairs, one thread group per pair), and writes the blocks back:
+// BR x fewer launches and BR x less L2 traffic per sweep. Step 0 of a sweep also rotates the pairs inside each block.
+// ------------------------------------------------------------------------------------------------------
+template <int BR, int NT>
+__global__ void __launch_bounds__(NT, 1)
+jacobi_block_kernel(double* __restrict__ GT, double* __restrict__ VT, int ld, int n, int nb, int step, int with_intra, double tol,
+                    DevScalars* __restrict__ sc) {
+  extern __shared__ __align__(16) double sm[];
+  constexpr int R2 = 2 * BR;
+  constexpr int TPG = NT / BR;           // threads per pair group
+  constexpr int WPG = TPG / 32;          // warps per group
+  double* Gs = sm;                       // [R2][ld]
+  double* Vs = sm + (size_t)R2 * ld;     // [R2][ld]
+  __shared__ double red[BR][WPG][3];
+  __shared__ int rot_count;
+  __shared__ unsigned long long max_rel;   // bits of the largest |cos(g_p, g_q)| rotated away (positive doubles order like integers)
+  int I, J;
+  rr_pair(nb, step, blockIdx.x, I, J);
+  const int tid = threadIdx.x;
+  if (tid == 0) { rot_count = 0; max_rel = 0ull; }
+  // stage the 2*BR rows of both matrices
+  for (int r = 0; r < R2; r++) {
+    const int grow = (r < BR ? I * BR + r : J * BR + (r - BR));
+    const bool valid = grow < n;
+    for (int c = 2 * tid; c < ld; c += 2 * NT) {
+      double2 g = make_double2(0.0, 0.0), v = g;
+      if (valid) {
+        g = *reinterpret_cast<const double2*>(GT + (size_t)grow * ld + c);
+        v = *reinterpret_cast<const double2*>(VT + (size_t)grow * ld + c);
+      }
+      *reinterpret_cast<double2*>(Gs + (size_t)r * ld + c) = g;
+      *reinterpret_cast<double2*>(Vs + (size_t)r * ld + c) = v;
+    }
+  }
+  __syncthreads();
+  const int grp = tid / TPG, j = tid % TPG, wig = j >> 5, lane = tid & 31;
+
+  auto rotate_round = [&](int p, int q, bool active) {
+    double a = 0, b = 0, g = 0;
+    if (active) {
+      const double* gp = Gs + (size_t)p * ld; const double* gq = Gs + (size_t)q * ld;
+      for (int c = j; c < n; c += TPG) { const double x = gp[c], y = gq[c]; a += x * x; b += y * y; g += x * y; }
+    }
+    a = warp_sum_butterfly(a); b = warp_sum_butterfly(b); g = warp_sum_butterfly(g);
+    if (lane == 0) { red[grp][wig][0] = a; red[grp][wig][1] = b; red[grp][wig][2] = g; }
+    __syncthreads();
+    if (active) {
+      double alpha = 0, beta = 0, gamma = 0;
+#pragma unroll
+      for (int w = 0; w < WPG; w++) { alpha += red[grp][w][0]; beta += red[grp][w][1]; gamma += red[grp][w][2]; }
+      if (fabs(gamma) > tol * sqrt(alpha * beta) && gamma != 0.0) {
+        const double zeta = (beta - alpha) / (2.0 * gamma);
+        const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+        if (j == 0) {
+          atomicAdd(&rot_count, 1);
+          atomicMax(&max_rel, (unsigned long long)__double_as_longlong(fabs(gamma) / sqrt(alpha * beta)));
+        }
+        double* gp = Gs + (size_t)p * ld; double* gq = Gs + (size_t)q * ld;
+        double* vp = Vs + (size_t)p * ld; double* vq = Vs + (size_t)q * ld;
+        for (int cidx = j; cidx < n; cidx += TPG) {
+          const double x = gp[cidx], y = gq[cidx];
+          gp[cidx] = c * x - s * y; gq[cidx] = s * x + c * y;
+          const double u = vp[cidx], v = vq[cidx];
+          vp[cidx] = c * u - s * v; vq[cidx] = s * u + c * v;
+        }
+      }
+    }
+    __syncthreads();
+  };
+
+  if (with_intra) {
+    if (BR == 4) {
+      // pairs inside a 4-row block: (0,1)(2,3) | (0,2)(1,3) | (0,3)(1,2); groups 0,1 -> block I, groups 2,3 -> block J
+      const int off = (grp >> 1) * BR, h = grp & 1;
+      const int pp[3][2][2] = {{{0, 1}, {2, 3}}, {{0, 2}, {1, 3}}, {{0, 3}, {1, 2}}};
+#pragma unroll
+      for (int r = 0; r < 3; r++) rotate_round(off + pp[r][h][0], off + pp[r][h][1], true);
+    } else if (BR == 2) {
+      rotate_round(grp * BR, grp * BR + 1, true);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < BR; r++) rotate_round(grp, BR + (grp + r) % BR, true);
+
+  if (rot_count == 0) return;  // nothing changed: skip the write-back
+  for (int r = 0; r < R2; r++) {
+    const int grow = (r < BR ? I * BR + r : J * BR + (r - BR));
+    if (grow >= n) continue;
+    for (int c = 2 * tid; c < ld; c += 2 * NT) {
+      *reinterpret_cast<double2*>(GT + (size_t)grow * ld + c) = *reinterpret_cast<const double2*>(Gs + (size_t)r * ld + c);
+      *reinterpret_cast<double2*>(VT + (size_t)grow * ld + c) = *reinterpret_cast<const double2*>(Vs + (size_t)r * ld + c);
+    }
+  }
+  if (tid == 0) {
+    atomicAdd(&sc->jacobi_rotations, rot_count);
+    atomicMax(&sc->jacobi_max_rel_bits, max_rel);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Version 2b: the WHOLE eigensolver in one launch for small N (N <= 116: G and V fit the 227 KB of one SM):
+// G = V C, cyclic one-sided Jacobi sweeps until no rotation fires, Rayleigh quotients, sign convention, ascending
+// |lambda| order, acceptance test and the commit of B, A = B D, D, VT. One warp per row pair.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024, 1)
+eigen_small_kernel(const double* __restrict__ C, int ld, int n, double* __restrict__ VT, double* __restrict__ B, double* __restrict__ A,
+                   double* __restrict__ D, double tol, int max_sweeps, DevScalars* __restrict__ sc) {
+  extern __shared__ __align__(16) double sm[];
+  const int np = (n + 1) & ~1;           // players of the round-robin (dummy when n is odd)
+  const int rs = n | 1;                  // odd row stride: conflict-free column access in the commit phase
+  double* Gs = sm;                       // [n][rs]
+  double* Vs = sm + (size_t)n * rs;      // [n][rs]
+  double* ev = Vs + (size_t)n * rs;      // [n]
+  double* sg = ev + n;                   // [n]
+  int* perm = reinterpret_cast<int*>(sg + n);  // [n]
+  __shared__ int rotations, rejected;
+  __shared__ double smin[32], smax[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  for (int i = tid; i < n * n; i += blockDim.x) Vs[(i / n) * rs + (i % n)] = VT[(size_t)(i / n) * ld + (i % n)];
+  __syncthreads();
+  // G[i][j] = sum_k V[i][k] C[j][k]   (C symmetric)
+  for (int i = tid; i < n * n; i += blockDim.x) {
+    const int r = i % n, c = i / n;      // a warp shares one row of C (broadcast) and walks rows of V (odd stride)
+    const double* crow = C + (size_t)c * ld;
+    const double* vrow = Vs + (size_t)r * rs;
+    double a = 0.0;
+    for (int k = 0; k < n; k++) a += vrow[k] * crow[k];
+    Gs[r * rs + c] = a;
+  }
+  __syncthreads();
+  for (int sweep = 0; sweep < max_sweeps; sweep++) {
+    if (tid == 0) rotations = 0;
+    __syncthreads();
+    for (int step = 0; step < np - 1; step++) {
+      for (int k = warp; k < np / 2; k += nwarps) {
+        int p, q;
+        rr_pair(np, step, k, p, q);
+        if (q >= n) continue;
+        double* gp = Gs + (size_t)p * rs; double* gq = Gs + (size_t)q * rs;
+        double a = 0, b = 0, g = 0;
+        for (int c = lane; c < n; c += 32) { const double x = gp[c], y = gq[c]; a += x * x; b += y * y; g += x * y; }
+        a = warp_sum_butterfly(a); b = warp_sum_butterfly(b); g = warp_sum_butterfly(g);
+        if (fabs(g) > tol * sqrt(a * b) && g != 0.0) {
+          const double zeta = (b - a) / (2.0 * g);
+          const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+          if (lane == 0) atomicAdd(&rotations, 1);
+          double* vp = Vs + (size_t)p * rs; double* vq = Vs + (size_t)q * rs;
+          for (int cidx = lane; cidx < n; cidx += 32) {
+            const double x = gp[cidx], y = gq[cidx];
+            gp[cidx] = c * x - s * y; gq[cidx] = s * x + c * y;
+            const double u = vp[cidx], v = vq[cidx];
+            vp[cidx] = c * u - s * v; vq[cidx] = s * u + c * v;
+          }
+        }
+      }
+      __syncthreads();
+    }
+    const int done = (rotations == 0);
+    __syncthreads();
+    if (done) break;
+  }
+  // Rayleigh quotients + sign convention
+  for (int i = warp; i < n; i += nwarps) {
+    double a = 0.0, nv = 0.0, best = -1.0, bval = 0.0;
+    int bidx = 0x7fffffff;
+    for (int k = lane; k < n; k += 32) {
+      const double v = Vs[(size_t)i * rs + k];
+      a += v * Gs[(size_t)i * rs + k]; nv += v * v;
+      if (fabs(v) > best) { best = fabs(v); bval = v; bidx = k; }
+    }
+    a = warp_sum_butterfly(a); nv = warp_sum_butterfly(nv);
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, off), ov = __shfl_xor_sync(0xffffffffu, bval, off);
+      const int oi = __shfl_xor_sync(0xffffffffu, bidx, off);
+      if (ob > best || (ob == best && oi < bidx)) { best = ob; bval = ov; bidx = oi; }
+    }
+    if (lane == 0) { ev[i] = a / nv; sg[i] = bval < 0.0 ? -1.0 : 1.0; }
+  }
+  __syncthreads();
+  double mn = INFINITY, mx = -INFINITY;
+  for (int i = tid; i < n; i += blockDim.x) {
+    const double a = fabs(ev[i]);
+    int r = 0;
+    for (int jx = 0; jx < n; jx++) { const double b = fabs(ev[jx]); r += (b < a) || (b == a && jx < i); }
+    perm[r] = i;
+    mn = fmin(mn, ev[i]); mx = fmax(mx, ev[i]);
+  }
+  mn = warp_min(mn); mx = warp_max(mx);
+  if (lane == 0) { smin[warp] = mn; smax[warp] = mx; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 0; w < nwarps; w++) { mn = fmin(mn, smin[w]); mx = fmax(mx, smax[w]); }
+    rejected = (mn <= 0.0 || !(mn == mn));
+    sc->eig_rejected = rejected;
+    if (!rejected) { sc->min_eig = mn; sc->max_eig = mx; }
+  }
+  __syncthreads();
+  if (rejected) return;
+  for (int i = tid; i < n * n; i += blockDim.x) {
+    const int e = i / n, d = i % n;      // VT[e][d] = sign * V[perm[e]][d]
+    VT[(size_t)e * ld + d] = sg[perm[e]] * Vs[(size_t)perm[e] * rs + d];
+  }
+  for (int i = tid; i < n * n; i += blockDim.x) {
+    const int d = i / n, e = i % n;      // B[d][e] = VT[e][d]
+    const double v = sg[perm[e]] * Vs[(size_t)perm[e] * rs + d];
+    const double dd = sqrt(ev[perm[e]]);
+    B[(size_t)d * ld + e] = v;
+    A[(size_t)d * ld + e] = v * dd;
+    if (d == 0) D[e] = dd;
   }
 }
 
@@ -181,8 +403,6 @@ __global__ void __launch_bounds__(256) set_identity_kernel(double* __restrict__ 
   if (j < ld) M[(size_t)i * ld + j] = (i == j && j < n) ? 1.0 : 0.0;
 }
 
-__global__ void reset_rotations_kernel(DevScalars* sc) { sc->jacobi_rotations = 0; }
-
 void launch_set_identity(cudaStream_t st, double* M, int ld, int n) {
   dim3 grid((ld + 255) / 256, n);
   set_identity_kernel<<<grid, 256, 0, st>>>(M, ld, n);
@@ -193,6 +413,49 @@ void launch_jacobi_sweep(cudaStream_t st, double* GT, double* VT, int ld, int n,
   for (int step = 0; step < np - 1; step++) jacobi_step_kernel<<<np / 2, 128, 0, st>>>(GT, VT, ld, n, np, step, tol, sc);
   if (launches) *launches += np;
 }
+constexpr size_t kMaxDynSmem = 227 * 1024 - 2048;  // leave room for the kernels' static shared memory
+size_t eigen_small_smem_bytes(int n) { return sizeof(double) * (2 * (size_t)n * (n | 1) + 2 * n) + sizeof(int) * n + 16; }
+bool eigen_small_fits(int n) { return eigen_small_smem_bytes(n) <= kMaxDynSmem; }
+void launch_eigen_small(cudaStream_t st, const double* C, int ld, int n, double* VT, double* B, double* A, double* D, double tol,
+                        int max_sweeps, DevScalars* sc) {
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(eigen_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem); attr = true; }
+  eigen_small_kernel<<<1, 1024, eigen_small_smem_bytes(n), st>>>(C, ld, n, VT, B, A, D, tol, max_sweeps, sc);
+}
+
+static int g_jacobi_threads = 1024;
+// rows per block the 227 KB of shared memory allows for this n (0: use the unblocked step kernel)
+int jacobi_block_rows(int ld) {
+  for (int br = 4; br >= 2; br >>= 1)
+    if (sizeof(double) * 4 * (size_t)br * ld <= kMaxDynSmem) return br;
+  return 0;
+}
+void launch_jacobi_block_sweep(cudaStream_t st, double* GT, double* VT, int ld, int n, double tol, DevScalars* sc, int* launches) {
+  const int br = jacobi_block_rows(ld);
+  if (br == 0) { launch_jacobi_sweep(st, GT, VT, ld, n, tol, sc, launches); return; }
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(jacobi_block_kernel<4, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
+    cudaFuncSetAttribute(jacobi_block_kernel<4, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
+    cudaFuncSetAttribute(jacobi_block_kernel<4, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
+    cudaFuncSetAttribute(jacobi_block_kernel<2, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
+    const char* e = getenv("KCMA_JACOBI_THREADS");
+    if (e) g_jacobi_threads = atoi(e);
+    attr = true;
+  }
+  int nb = (n + br - 1) / br;
+  nb = (nb + 1) & ~1;
+  const size_t smem = sizeof(double) * 4 * (size_t)br * ld;
+  reset_rotations_kernel<<<1, 1, 0, st>>>(sc);
+  for (int step = 0; step < nb - 1; step++) {
+    if (br == 4 && g_jacobi_threads == 1024) jacobi_block_kernel<4, 1024><<<nb / 2, 1024, smem, st>>>(GT, VT, ld, n, nb, step, step == 0, tol, sc);
+    else if (br == 4 && g_jacobi_threads == 256) jacobi_block_kernel<4, 256><<<nb / 2, 256, smem, st>>>(GT, VT, ld, n, nb, step, step == 0, tol, sc);
+    else if (br == 4) jacobi_block_kernel<4, 512><<<nb / 2, 512, smem, st>>>(GT, VT, ld, n, nb, step, step == 0, tol, sc);
+    else jacobi_block_kernel<2, 512><<<nb / 2, 512, smem, st>>>(GT, VT, ld, n, nb, step, step == 0, tol, sc);
+  }
+  if (launches) *launches += nb;
+}
+
 void launch_rayleigh(cudaStream_t st, const double* GT, const double* VT, int ld, int n, double* ev, double* sign) {
   rayleigh_kernel<<<(n + 7) / 8, 256, 0, st>>>(GT, VT, ld, n, ev, sign);
 }

