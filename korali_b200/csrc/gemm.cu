@@ -236,13 +236,18 @@ int syrk_tiles(int n) {
 }
 
 int syrk_pick_splits(int n, int K, int num_sms, int max_splits) {
+  // one CTA per SM: minimise (waves of CTAs) x (k-tiles per CTA); ties -> fewer splits (less reduction traffic)
   const int tiles = syrk_tiles(n);
   const int nk = (K + BK - 1) / BK;
-  int splits = (num_sms + tiles - 1) / tiles;  // about one wave of CTAs
-  if (splits < 1) splits = 1;
-  if (splits > nk) splits = nk > 0 ? nk : 1;
-  if (splits > max_splits) splits = max_splits;
-  return splits;
+  int best = 1;
+  long long best_cost = -1;
+  for (int s = 1; s <= max_splits && s <= (nk > 0 ? nk : 1); s++) {
+    const long long waves = ((long long)tiles * s + num_sms - 1) / num_sms;
+    const long long per = (nk + s - 1) / s;
+    const long long cost = waves * (per + 6);  // +6: pipeline fill / epilogue of a CTA in k-tile units
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = s; }
+  }
+  return best;
 }
 
 void launch_syrk_tt(cudaStream_t st, int n, int K, const double* S, int lds, double* W, int ldw, int splits) {

@@ -1,0 +1,59 @@
+"""Worker of tests/test_multi_gpu.py (launched with torch.distributed.run, one process per GPU): a population sharded
+over WORLD_SIZE ranks must reproduce the single-GPU run: same Philox samples (counters are global sample indices),
+identical ranking, and mean / paths / sigma / C equal up to the all-reduce summation order."""
+import os
+import sys
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from korali_b200 import _lib  # noqa: E402
+
+
+def relerr(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cases = [dict(n=64, population_size=512, objective="NegRosenbrock", initial_value=0.2, initial_stddev=0.8, seed=21),
+             dict(n=130, population_size=1024, objective="NegEllipsoid", mirrored_sampling=1, initial_value=3.0, initial_stddev=1.0, seed=5),
+             dict(n=40, population_size=256, objective="NegSphere", diagonal_covariance=1, initial_value=1.0, initial_stddev=1.0, seed=9)]
+    for case in cases:
+        s = _lib.Solver(device=local, rank=rank, nranks=world, **case)
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid = torch.tensor(list(_lib.comm_unique_id()), dtype=torch.uint8, device="cuda")
+        dist.broadcast(uid, 0)
+        s.comm_init(bytes(uid.cpu().tolist()))
+        ref = _lib.Solver(device=local, **case) if rank == 0 else None
+        for g in range(20):
+            s.run_generation()
+            if ref is not None:
+                ref.run_generation()
+                assert np.array_equal(s.get("Value Vector"), ref.get("Value Vector")), (case["objective"], g)
+                assert np.array_equal(s.get_index("Sorting Index"), ref.get_index("Sorting Index")), (case["objective"], g)
+                for k in ["Current Mean", "Evolution Path", "Conjugate Evolution Path", "Covariance Matrix", "Best Ever Variables"]:
+                    e = relerr(s.get(k), ref.get(k))
+                    assert e < 1e-11, (case["objective"], g, k, e)
+                assert abs(s.scalar("Sigma") - ref.scalar("Sigma")) < 1e-11 * ref.scalar("Sigma")
+                assert s.scalar("Best Ever Value") == ref.scalar("Best Ever Value")
+        # every rank holds the same replicated state
+        c = torch.tensor(s.get("Covariance Matrix"), device="cuda")
+        c0 = c.clone(); dist.broadcast(c0, 0)
+        assert torch.equal(c, c0), "replicated covariance differs between ranks"
+        lo, hi = int(s.scalar("Shard Begin")), int(s.scalar("Shard End"))
+        assert (lo, hi) == _lib.shard_range(case["population_size"], case.get("mirrored_sampling", 0), rank, world)
+        s.close()
+        if rank == 0:
+            print("ok", case["objective"], "world", world, flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,83 @@
+"""N > 1: the population is sharded across ranks; collectives are an all-gather of F and an all-reduce of
+[partial rank-mu sum | partial mean | best sample].
+ - GPU (needs >= 2 devices): torchrun + NCCL, checked against the single-GPU run.
+ - CPU: the same decomposition with world_size 2 over gloo, arithmetic done by the oracle (checker only)."""
+import os
+import subprocess
+import sys
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_sharded_population_matches_single_gpu():
+    n = 2
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(ROOT, "tests", "mgpu_worker.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert out.stdout.count("ok ") == 3
+
+
+def _gloo_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from korali_b200 import _lib
+    from oracle import oracle as O
+    N, lam, mu = 12, 64, 32
+    for mirrored in (0, 1):
+        rng = np.random.default_rng(3)                       # every rank draws the same global population
+        mean, sigma = rng.standard_normal(N), 0.7
+        y = rng.standard_normal((lam // (2 if mirrored else 1), N))
+        if mirrored:
+            y = np.repeat(y, 2, axis=0); y[1::2] *= -1
+        x = mean + sigma * y
+        w = np.log(mu + 0.5) - np.log(np.arange(mu) + 1.0); w /= w.sum()
+        lo, hi = _lib.shard_range(lam, mirrored, rank, world)
+        # local objective on the shard, all-gather(F)
+        f_local = torch.from_numpy(O.objective("NegRosenbrock", x[lo:hi]))
+        parts = [torch.empty(hi - lo, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(parts, f_local)
+        f = torch.cat(parts).numpy()
+        idx = O.sort_index(f)                                 # identical on every rank
+        sel = [(r, int(i)) for r, i in enumerate(idx[:mu]) if lo <= i < hi]
+        t = np.array([x[i] - mean for _, i in sel]).reshape(-1, N)
+        wl = np.array([w[r] for r, _ in sel])
+        part = np.zeros(N * N + N)
+        if len(sel):
+            part[:N * N] = O.rank_mu(t, wl).ravel()
+            part[N * N:] = (wl[:, None] * np.array([x[i] for _, i in sel])).sum(0)
+        red = torch.from_numpy(part)
+        dist.all_reduce(red)                                  # all-reduce([P | mean])
+        full_p = O.rank_mu(x[idx[:mu].astype(int)] - mean, w)
+        full_m = (w[:, None] * x[idx[:mu].astype(int)]).sum(0)
+        err_p = np.abs(red.numpy()[:N * N].reshape(N, N) - full_p).max() / np.abs(full_p).max()
+        err_m = np.abs(red.numpy()[N * N:] - full_m).max() / np.abs(full_m).max()
+        q.put((rank, mirrored, float(err_p), float(err_m), len(sel)))
+    dist.destroy_process_group()
+
+
+def test_sharded_update_decomposition_over_gloo():
+    """world_size 2 on CPU: shard ranges + all-gather(F) + all-reduce of the partial rank-mu sums reproduce the
+    single-rank update (host-side logic of the N > 1 path; the oracle stands in for the kernels)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + os.getpid() % 300
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(4)]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    for rank, mirrored, ep, em, nsel in res:
+        assert ep < 1e-13 and em < 1e-13, (rank, mirrored, ep, em)
+    for mirrored in (0, 1):
+        assert sum(r[4] for r in res if r[1] == mirrored) == 32   # every selected sample is owned by exactly one rank
