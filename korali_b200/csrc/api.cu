@@ -385,6 +385,11 @@ int update_eigensystem(kcma* h, const double* dM) {
   // GT = VT * M  (M symmetric): GT[i][j] = sum_k VT[i][k] M[j][k]
   launch_gemm_tn(h->stream, N, N, N, h->dVTw, ld, dM, ld, h->dGT, ld);
   h->launches += 1;
+  if (launch_jacobi_persistent(h->stream, h->dGT, h->dVTw, ld, N, tol, max_sweeps, h->dSc, h->num_sms, (unsigned*)h->dPerm)) {
+    h->launches += 1;
+    h->scalars_fresh = false;
+    if (h->timing) { if (pull_scalars(h)) return 1; h->phases["eigen_sweeps"].calls += h->hSc->jacobi_sweeps; }
+  } else
   for (int sweep = 0; sweep < max_sweeps; sweep++) {
     int l = 0;
     h->phases["eigen_sweeps"].calls++;
@@ -397,7 +402,7 @@ int update_eigensystem(kcma* h, const double* dM) {
     // ~1e-20/gap and the confirmation sweep (a full pass that rotates nothing) can be skipped
     double max_rel;
     memcpy(&max_rel, &h->hSc->jacobi_max_rel_bits, sizeof(double));
-    if (max_rel < 1e-10) break;
+    if (max_rel < 1e-20) break;   // the kernels record the SQUARED cosine
   }
   launch_rayleigh(h->stream, h->dGT, h->dVTw, ld, N, h->dEv, h->dT);   // dT (scratch of tell()) holds the signs here
   launch_eig_order(h->stream, h->dEv, N, h->dPerm, h->dSc);
@@ -598,7 +603,7 @@ int update_and_handle_constraints(kcma* h) {
           const int rows_padded = std::min(h->u_rows, round_up(J, 16) + 16);
           launch_constraint_scale(h->stream, h->dU, ld, N, h->dEvSample, h->dCount, h->dViol, h->cov_adaption_factor, rows_padded);
           splits = syrk_pick_splits(N, J, h->num_sms, h->max_splits);
-          launch_syrk_tt(h->stream, N, J, h->dU, ld, h->dWsplit, ld, splits);
+          launch_syrk_tt(h->stream, N, J, h->dU, ld, h->u_rows, h->dWsplit, ld, splits);
           h->launches += 2;
         }
       }
@@ -709,7 +714,7 @@ int do_tell(kcma* h) {
       launch_diag_rank_mu(h->stream, h->dS, ld, h->dCount, max_count, rows_per > 0 ? rows_per : 1, N, h->dWsplit, ld, splits);
     } else {
       splits = syrk_pick_splits(N, max_count, h->num_sms, h->max_splits);
-      launch_syrk_tt(h->stream, N, max_count, h->dS, ld, h->dWsplit, ld, splits);
+      launch_syrk_tt(h->stream, N, max_count, h->dS, ld, h->s_rows_padded, h->dWsplit, ld, splits);
     }
     h->launches++;
     if (multi) { launch_reduce_splits(h->stream, h->dWsplit, ld, splits, N, h->dRed); h->launches++; }
@@ -754,8 +759,11 @@ int end_of_generation(kcma* h) {
     push_scalars(h);
     return fail(h, "Non finite value of function evaluation detected: nan\n");
   }
-  if (h->hSc->best_valid_sample == ~0ull)
-    return fail(h, "no sample without constraint violations in this generation (the reference reads out of bounds here, CMAES.cpp.base:565)");
+  if (h->hSc->warn_no_valid) {
+    h->warn += "No sample without constraint violations in this generation: using the best-ranked sample (the reference reads out of bounds here).\n";
+    h->hSc->warn_no_valid = 0;
+    if (push_scalars(h)) return 1;
+  }
   if (h->hSc->eig_rejected) h->warn += "Min Eigenvalue smaller or equal 0.0 after Eigen decomp (no update possible).\n";
   if (h->hSc->warn_flat) { h->warn += "Sigma increased due to equal function values.\n"; }
   if (h->hSc->warn_minsd) { h->warn += "Sigma increased due to minimal standard deviation.\n"; }
@@ -1380,7 +1388,7 @@ int kcma_k_rank_mu(int device, uint64_t n, uint64_t rows, const double* t, const
   const int splits = syrk_pick_splits(N, (int)rows, sms, 16);
   K_CUDA(dmalloc(&dW, (size_t)splits * N * ld)); K_CUDA(dmalloc(&dP, (size_t)N * ld));
   K_CUDA(cudaMemcpy2D(dS, sizeof(double) * ld, s.data(), sizeof(double) * N, sizeof(double) * N, rows, cudaMemcpyHostToDevice));
-  launch_syrk_tt(0, N, (int)rows, dS, ld, dW, ld, splits);
+  launch_syrk_tt(0, N, (int)rows, dS, ld, (long long)rp, dW, ld, splits);
   launch_reduce_splits(0, dW, ld, splits, N, dP);
   std::vector<double> p((size_t)N * N);
   K_CUDA(cudaMemcpy2D(p.data(), sizeof(double) * N, dP, sizeof(double) * ld, sizeof(double) * N, N, cudaMemcpyDeviceToHost));

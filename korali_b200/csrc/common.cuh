@@ -64,6 +64,8 @@ struct DevScalars {
   unsigned long long resampled_parameter_count;   // _resampledParameterCount
   unsigned long long constraint_evaluation_count; // _constraintEvaluationCount
   unsigned long long jacobi_max_rel_bits;         // largest |cos| rotated away in the last sweep (double bits)
+  int jacobi_sweeps;         // sweeps the persistent Jacobi kernel ran
+  int warn_no_valid;         // no sample without constraint violations in a non-viability generation
   int n_events;              // rank-1 corrections applied in this handleConstraints iteration
   int adaptation_abort;      // "Exiting adaption loop, max adaptions reached" (CMAES.cpp.base:789-793)
   int mean_feasible;         // checkMeanAndSetRegime: all g_c(mean) <= 0

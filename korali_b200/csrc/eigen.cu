@@ -9,8 +9,11 @@
 // signed). Vectors are stored as ROWS (VT, GT) so each rotation touches contiguous memory.
 // One launch per round-robin step (n/2 disjoint pairs), one CTA per pair.
 #include "common.cuh"
+#include <cooperative_groups.h>
 #include <stdlib.h>
 #include "kernels.h"
+
+namespace cg = cooperative_groups;
 
 namespace kc {
 
@@ -123,13 +126,16 @@ jacobi_block_kernel(double* __restrict__ GT, double* __restrict__ VT, int ld, in
       double alpha = 0, beta = 0, gamma = 0;
 #pragma unroll
       for (int w = 0; w < WPG; w++) { alpha += red[grp][w][0]; beta += red[grp][w][1]; gamma += red[grp][w][2]; }
-      if (fabs(gamma) > tol * sqrt(alpha * beta) && gamma != 0.0) {
-        const double zeta = (beta - alpha) / (2.0 * gamma);
-        const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-        const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+      if (gamma * gamma > tol * tol * alpha * beta) {
+        // t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = (beta-alpha)/(2 gamma), written with one sqrt, one division
+        // and one rsqrt on the critical path
+        const double d = beta - alpha;
+        const double r = sqrt(d * d + 4.0 * gamma * gamma);
+        const double t = ((d == 0.0 || (d > 0.0) == (gamma > 0.0)) ? 2.0 : -2.0) * fabs(gamma) / (fabs(d) + r);
+        const double c = rsqrt(1.0 + t * t), s = c * t;
         if (j == 0) {
           atomicAdd(&rot_count, 1);
-          atomicMax(&max_rel, (unsigned long long)__double_as_longlong(fabs(gamma) / sqrt(alpha * beta)));
+          atomicMax(&max_rel, (unsigned long long)__double_as_longlong(gamma * gamma / (alpha * beta)));   // squared cosine
         }
         double* gp = Gs + (size_t)p * ld; double* gq = Gs + (size_t)q * ld;
         double* vp = Vs + (size_t)p * ld; double* vq = Vs + (size_t)q * ld;
@@ -170,6 +176,155 @@ jacobi_block_kernel(double* __restrict__ GT, double* __restrict__ VT, int ld, in
   if (tid == 0) {
     atomicAdd(&sc->jacobi_rotations, rot_count);
     atomicMax(&sc->jacobi_max_rel_bits, max_rel);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Version 2c: the blocked sweeps as ONE persistent cooperative kernel. Per-step launches cost ~10 us each on this
+// system (250 steps x 18 sweeps at N = 1000); here CTA k walks the round-robin schedule itself and the steps are
+// separated by grid-wide barriers; convergence is decided on the device, so the whole Jacobi phase needs no host
+// round trip. Requires nb/2 <= number of SMs (one co-resident CTA per SM): N <= 1184 with 4-row blocks.
+// ------------------------------------------------------------------------------------------------------
+template <int BR, int NT>
+__global__ void __launch_bounds__(NT, 1)
+jacobi_persistent_kernel(double* GT, double* VT, int ld, int n, int nb, double tol, int max_sweeps, DevScalars* sc,
+                         unsigned* ready /* [nb], zero on entry: epoch at which each row block was last completed */) {
+  cg::grid_group grid = cg::this_grid();
+  unsigned epoch = 0;   // global step counter across sweeps
+  extern __shared__ __align__(16) double sm[];
+  constexpr int R2 = 2 * BR;
+  constexpr int TPG = NT / BR;
+  constexpr int WPG = TPG / 32;
+  double* Gs = sm;
+  double* Vs = sm + (size_t)R2 * ld;
+  __shared__ double red[BR][WPG][3];
+  __shared__ int rot_count;
+  __shared__ unsigned long long max_rel;
+  const int tid = threadIdx.x;
+  const int grp = tid / TPG, j = tid % TPG, wig = j >> 5, lane = tid & 31;
+
+  auto rotate_round = [&](int p, int q) {
+    double a = 0, b = 0, g = 0;
+    {
+      const double* gp = Gs + (size_t)p * ld; const double* gq = Gs + (size_t)q * ld;
+      for (int c = j; c < n; c += TPG) { const double x = gp[c], y = gq[c]; a += x * x; b += y * y; g += x * y; }
+    }
+    a = warp_sum_butterfly(a); b = warp_sum_butterfly(b); g = warp_sum_butterfly(g);
+    if (lane == 0) { red[grp][wig][0] = a; red[grp][wig][1] = b; red[grp][wig][2] = g; }
+    __syncthreads();
+    double alpha = 0, beta = 0, gamma = 0;
+#pragma unroll
+    for (int w = 0; w < WPG; w++) { alpha += red[grp][w][0]; beta += red[grp][w][1]; gamma += red[grp][w][2]; }
+    if (gamma * gamma > tol * tol * alpha * beta) {
+      const double d = beta - alpha;
+      const double r = sqrt(d * d + 4.0 * gamma * gamma);
+      const double t = ((d == 0.0 || (d > 0.0) == (gamma > 0.0)) ? 2.0 : -2.0) * fabs(gamma) / (fabs(d) + r);
+      const double c = rsqrt(1.0 + t * t), s = c * t;
+      if (j == 0) {
+        atomicAdd(&rot_count, 1);
+        atomicMax(&max_rel, (unsigned long long)__double_as_longlong(gamma * gamma / (alpha * beta)));   // squared cosine
+      }
+      double* gp = Gs + (size_t)p * ld; double* gq = Gs + (size_t)q * ld;
+      double* vp = Vs + (size_t)p * ld; double* vq = Vs + (size_t)q * ld;
+      for (int cidx = j; cidx < n; cidx += TPG) {
+        const double x = gp[cidx], y = gq[cidx];
+        gp[cidx] = c * x - s * y; gq[cidx] = s * x + c * y;
+        const double u = vp[cidx], v = vq[cidx];
+        vp[cidx] = c * u - s * v; vq[cidx] = s * u + c * v;
+      }
+    }
+    __syncthreads();
+  };
+
+  for (int sweep = 0; sweep < max_sweeps; sweep++) {
+    if (blockIdx.x == 0 && tid == 0) { sc->jacobi_rotations = 0; sc->jacobi_max_rel_bits = 0ull; sc->jacobi_sweeps = sweep + 1; }
+    int sweep_rot = 0;
+    unsigned long long sweep_max = 0ull;
+    grid.sync();
+    for (int step = 0; step < nb - 1; step++) {
+      int I, J;
+      rr_pair(nb, step, blockIdx.x, I, J);
+      if (tid == 0) {
+        rot_count = 0; max_rel = 0ull;
+        // point-to-point dependency: the two blocks of this step were produced by (at most) two other CTAs in the
+        // previous step; wait for exactly those instead of a grid-wide barrier
+        volatile unsigned* rv = ready;
+        while (rv[I] < epoch || rv[J] < epoch) { }
+        __threadfence();
+      }
+      __syncthreads();
+      {
+        // all loads first (one L2 round trip), then the shared-memory stores. L2 loads (ld.global.cg): the rows were
+        // written by another SM.
+        constexpr int CH = (1184 + 2 * NT - 1) / (2 * NT);   // column chunks per row (ld <= 1184)
+        double2 gbuf[R2][CH], vbuf[R2][CH];
+#pragma unroll
+        for (int r = 0; r < R2; r++) {
+          const int grow = (r < BR ? I * BR + r : J * BR + (r - BR));
+          const bool valid = grow < n;
+#pragma unroll
+          for (int k = 0; k < CH; k++) {
+            const int c = 2 * tid + k * 2 * NT;
+            double2 g = make_double2(0.0, 0.0), v = g;
+            if (valid && c < ld) {
+              g = __ldcg(reinterpret_cast<const double2*>(GT + (size_t)grow * ld + c));
+              v = __ldcg(reinterpret_cast<const double2*>(VT + (size_t)grow * ld + c));
+            }
+            gbuf[r][k] = g; vbuf[r][k] = v;
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < R2; r++)
+#pragma unroll
+          for (int k = 0; k < CH; k++) {
+            const int c = 2 * tid + k * 2 * NT;
+            if (c < ld) {
+              *reinterpret_cast<double2*>(Gs + (size_t)r * ld + c) = gbuf[r][k];
+              *reinterpret_cast<double2*>(Vs + (size_t)r * ld + c) = vbuf[r][k];
+            }
+          }
+      }
+      __syncthreads();
+      if (step == 0) {
+        if (BR == 4) {
+          const int off = (grp >> 1) * BR, h = grp & 1;
+          const int pp[3][2][2] = {{{0, 1}, {2, 3}}, {{0, 2}, {1, 3}}, {{0, 3}, {1, 2}}};
+#pragma unroll
+          for (int r = 0; r < 3; r++) rotate_round(off + pp[r][h][0], off + pp[r][h][1]);
+        } else if (BR == 2) {
+          rotate_round(grp * BR, grp * BR + 1);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < BR; r++) rotate_round(grp, BR + (grp + r) % BR);
+      if (rot_count != 0) {
+        for (int r = 0; r < R2; r++) {
+          const int grow = (r < BR ? I * BR + r : J * BR + (r - BR));
+          if (grow >= n) continue;
+          for (int c = 2 * tid; c < ld; c += 2 * NT) {
+            __stcg(reinterpret_cast<double2*>(GT + (size_t)grow * ld + c), *reinterpret_cast<const double2*>(Gs + (size_t)r * ld + c));
+            __stcg(reinterpret_cast<double2*>(VT + (size_t)grow * ld + c), *reinterpret_cast<const double2*>(Vs + (size_t)r * ld + c));
+          }
+        }
+      }
+      epoch++;
+      __syncthreads();   // all global stores of this CTA are issued
+      if (tid == 0) {
+        sweep_rot += rot_count; sweep_max = max(sweep_max, max_rel);
+        __threadfence();  // ... and visible before the blocks are published
+        volatile unsigned* rv = ready;
+        rv[I] = epoch; rv[J] = epoch;
+      }
+    }
+    if (tid == 0 && sweep_rot) {
+      atomicAdd(&sc->jacobi_rotations, sweep_rot);
+      atomicMax(&sc->jacobi_max_rel_bits, sweep_max);
+    }
+    grid.sync();
+    const int total = *reinterpret_cast<volatile int*>(&sc->jacobi_rotations);
+    const unsigned long long mb = *reinterpret_cast<volatile unsigned long long*>(&sc->jacobi_max_rel_bits);
+    grid.sync();   // everybody has read the totals before block 0 resets them
+    if (total == 0 || __longlong_as_double((long long)mb) < 1e-20) break;   // squared cosine below (1e-10)^2
   }
 }
 
@@ -423,13 +578,37 @@ void launch_eigen_small(cudaStream_t st, const double* C, int ld, int n, double*
   eigen_small_kernel<<<1, 1024, eigen_small_smem_bytes(n), st>>>(C, ld, n, VT, B, A, D, tol, max_sweeps, sc);
 }
 
-static int g_jacobi_threads = 1024;
+static int g_jacobi_threads = 512;
 // rows per block the 227 KB of shared memory allows for this n (0: use the unblocked step kernel)
 int jacobi_block_rows(int ld) {
   for (int br = 4; br >= 2; br >>= 1)
     if (sizeof(double) * 4 * (size_t)br * ld <= kMaxDynSmem) return br;
   return 0;
 }
+// All sweeps in one cooperative launch. Returns false when the configuration does not fit (caller falls back to per-step launches).
+bool launch_jacobi_persistent(cudaStream_t st, double* GT, double* VT, int ld, int n, double tol, int max_sweeps, DevScalars* sc,
+                              int num_sms, unsigned* ready) {
+  const int br = jacobi_block_rows(ld);
+  if (br != 4 || ld > 1184) return false;
+  int nb = (n + br - 1) / br;
+  nb = (nb + 1) & ~1;
+  if (nb / 2 > num_sms) return false;
+  const char* e = getenv("KCMA_JACOBI_PERSISTENT");
+  if (e && atoi(e) == 0) return false;
+  static int ok = -1;
+  if (ok < 0) {
+    int dev = 0, coop = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    ok = coop && cudaFuncSetAttribute(jacobi_persistent_kernel<4, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem) == cudaSuccess;
+  }
+  if (!ok) return false;
+  size_t smem = sizeof(double) * 4 * (size_t)br * ld;
+  cudaMemsetAsync(ready, 0, sizeof(unsigned) * nb, st);
+  void* args[] = {&GT, &VT, &ld, &n, &nb, &tol, &max_sweeps, &sc, &ready};
+  return cudaLaunchCooperativeKernel((void*)jacobi_persistent_kernel<4, 512>, dim3(nb / 2), dim3(512), args, smem, st) == cudaSuccess;
+}
+
 void launch_jacobi_block_sweep(cudaStream_t st, double* GT, double* VT, int ld, int n, double tol, DevScalars* sc, int* launches) {
   const int br = jacobi_block_rows(ld);
   if (br == 0) { launch_jacobi_sweep(st, GT, VT, ld, n, tol, sc, launches); return; }

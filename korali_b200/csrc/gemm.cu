@@ -7,6 +7,8 @@
 //
 // Version 1 staging: 16-byte cp.async (LDGSTS) into padded shared-memory tiles whose row stride is
 // == 32 B (mod 128 B), which makes every LDS.64 fragment read of a half-warp hit 16 distinct bank pairs.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -222,9 +224,16 @@ static void ensure_attrs() {
 size_t gemm_tn_smem_bytes() { return sizeof(double) * STAGES * (BM + BN) * PADK; }
 size_t syrk_tt_smem_bytes() { return sizeof(double) * STAGES * 2 * BK * PADN; }
 
+// KCMA_GEMM=cpasync selects the version-1 staging (LDGSTS) for A/B comparisons; the default is the TMA pipeline.
+static bool want_tma() {
+  const char* e = getenv("KCMA_GEMM");
+  return !(e && e[0] == 'c');
+}
+
 void launch_gemm_tn(cudaStream_t st, int M, int Nc, int K, const double* A, int lda, const double* B, int ldb,
                     double* C, int ldc) {
   if (M <= 0 || Nc <= 0) return;
+  if (want_tma() && launch_gemm_tn_tma(st, M, Nc, K, A, lda, B, ldb, C, ldc)) return;
   ensure_attrs();
   dim3 grid((Nc + BN - 1) / BN, (M + BM - 1) / BM);
   gemm_tn_kernel<<<grid, THREADS, gemm_tn_smem_bytes(), st>>>(M, Nc, K, A, lda, B, ldb, C, ldc);
@@ -250,7 +259,8 @@ int syrk_pick_splits(int n, int K, int num_sms, int max_splits) {
   return best;
 }
 
-void launch_syrk_tt(cudaStream_t st, int n, int K, const double* S, int lds, double* W, int ldw, int splits) {
+void launch_syrk_tt(cudaStream_t st, int n, int K, const double* S, int lds, long long s_rows, double* W, int ldw, int splits) {
+  if (want_tma() && launch_syrk_tt_tma(st, n, K, S, lds, s_rows, W, ldw, splits)) return;
   ensure_attrs();
   const int nk = (K + BK - 1) / BK;
   const int per = (nk + splits - 1) / splits;

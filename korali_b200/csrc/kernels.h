@@ -13,7 +13,11 @@ size_t syrk_tt_smem_bytes();
 void launch_gemm_tn(cudaStream_t st, int M, int Nc, int K, const double* A, int lda, const double* B, int ldb, double* C, int ldc);
 int syrk_tiles(int n);
 int syrk_pick_splits(int n, int K, int num_sms, int max_splits);
-void launch_syrk_tt(cudaStream_t st, int n, int K, const double* S, int lds, double* W, int ldw, int splits);
+void launch_syrk_tt(cudaStream_t st, int n, int K, const double* S, int lds, long long s_rows, double* W, int ldw, int splits);
+
+// gemm_tma.cu (TMA + mbarrier staging; return false when the tensor maps cannot be built)
+bool launch_gemm_tn_tma(cudaStream_t st, int M, int Nc, int K, const double* A, int lda, const double* B, int ldb, double* C, int ldc);
+bool launch_syrk_tt_tma(cudaStream_t st, int n, int K, const double* S, int lds, long long s_rows, double* W, int ldw, int splits);
 
 // rng.cu
 void launch_philox_normal(cudaStream_t st, double* Z, int ldz, long long rows, int n, unsigned long long seed, unsigned generation,
@@ -70,6 +74,8 @@ void launch_jacobi_sweep(cudaStream_t st, double* GT, double* VT, int ld, int n,
 bool eigen_small_fits(int n);
 void launch_eigen_small(cudaStream_t st, const double* C, int ld, int n, double* VT, double* B, double* A, double* D, double tol,
                         int max_sweeps, DevScalars* sc);
+bool launch_jacobi_persistent(cudaStream_t st, double* GT, double* VT, int ld, int n, double tol, int max_sweeps, DevScalars* sc,
+                              int num_sms, unsigned* ready);
 void launch_jacobi_block_sweep(cudaStream_t st, double* GT, double* VT, int ld, int n, double tol, DevScalars* sc, int* launches);
 void launch_rayleigh(cudaStream_t st, const double* GT, const double* VT, int ld, int n, double* ev, double* sign);
 void launch_eig_order(cudaStream_t st, const double* ev, int n, int* perm, DevScalars* sc);

@@ -33,13 +33,12 @@ rank_bookkeeping_kernel(const double* __restrict__ f, const unsigned* __restrict
   }
   if (threadIdx.x == 0) {
     sc->previous_best_value = sc->current_best_value;
-    if (best_rank >= 0) {
-      const unsigned s = idx[best_rank];
-      sc->best_valid_sample = s;
-      sc->current_best_value = f[s];
-    } else {
-      sc->best_valid_sample = ~0ull;
-    }
+    // No sample without violations: the reference indexes _valueVector[-1] here (undefined behaviour, CMAES.cpp.base:556-565).
+    // Defined behaviour instead: fall back to the best-ranked sample and raise a warning.
+    if (best_rank < 0) { best_rank = 0; sc->warn_no_valid = 1; }
+    const unsigned s = idx[best_rank];
+    sc->best_valid_sample = s;
+    sc->current_best_value = f[s];
     sc->value_at_mu = f[idx[mu - 1]];
   }
 }

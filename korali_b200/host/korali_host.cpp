@@ -264,8 +264,16 @@ class CMAES {
       tc.finish();
     }
     cfg.max_infeasible_resamplings = (uint64_t)tc_max_infeasible;
-    // generators are part of the module defaults; accept and ignore their settings except the types
-    for (const char* g : {"Normal Generator", "Uniform Generator"}) if (s.has(g)) s.take(g);
+    // generators are part of the module defaults (CMAES.config:510-519). A saved state carries the Normal Generator's own
+    // "Random Seed" (distribution.cpp.base:36-37): resuming with it continues the counter-based Philox stream exactly.
+    for (const char* g : {"Normal Generator", "Uniform Generator"}) {
+      if (!s.has(g)) continue;
+      py::object go = s.take(g);
+      if (std::string(g) == "Normal Generator" && py::isinstance<py::dict>(go)) {
+        py::dict gd = py::reinterpret_borrow<py::dict>(go);
+        if (gd.contains("Random Seed") && is_number(gd["Random Seed"]) && gd["Random Seed"].cast<double>() > 0) seed = (uint64_t)gd["Random Seed"].cast<double>();
+      }
+    }
     // "Internal Settings" (CMAES.config:137-483, optimizer.config, solver.config): present when a saved state is loaded;
     // consumed here like the generated code does and restored after kcma_create (restore()).
     static const char* kInternal[] = {
@@ -487,6 +495,10 @@ class CMAES {
     tc["Max Model Evaluations"] = tc_max_model_evaluations;
     tc["Max Generations"] = tc_max_generations;
     js["Termination Criteria"] = tc;
+    py::dict ng, ug;
+    ng["Type"] = "Univariate/Normal"; ng["Mean"] = 0.0; ng["Standard Deviation"] = 1.0; ng["Random Seed"] = cfg.seed;
+    ug["Type"] = "Univariate/Uniform"; ug["Minimum"] = 0.0; ug["Maximum"] = 1.0; ug["Random Seed"] = cfg.seed + 1;
+    js["Normal Generator"] = ng; js["Uniform Generator"] = ug;
     for (const char* k : {"Sigma", "Trace", "Effective Mu", "Sigma Cumulation Factor", "Damp Factor", "Cumulative Covariance", "Chi Square Number",
                           "Conjugate Evolution Path L2 Norm", "Best Ever Value", "Previous Best Ever Value", "Current Best Value",
                           "Maximum Diagonal Covariance Matrix Element", "Minimum Diagonal Covariance Matrix Element",
