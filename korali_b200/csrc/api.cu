@@ -376,8 +376,8 @@ int update_eigensystem(kcma* h, const double* dM) {
   const double tol = 4.0 * 2.220446049250313e-16 * sqrt((double)N);
   const int max_sweeps = 40;
   if (eigen_small_fits(N)) {  // the whole solver in one launch, everything in one SM's shared memory
-    launch_eigen_small(h->stream, dM, ld, N, h->dVT, h->dB, h->dA, h->dD, tol, max_sweeps, h->dSc);
-    h->launches += 1;
+    launch_eigen_small(h->stream, dM, ld, N, h->dVT, h->dGT, h->dB, h->dA, h->dD, tol, max_sweeps, h->dSc);
+    h->launches += 2;
     h->scalars_fresh = false;
     return 0;
   }

@@ -19,6 +19,33 @@ namespace kc {
 
 __global__ void reset_rotations_kernel(DevScalars* sc) { sc->jacobi_rotations = 0; sc->jacobi_max_rel_bits = 0ull; }
 
+
+// Rotation that orthogonalises two rows with |g_p|^2 = alpha, |g_q|^2 = beta, g_p.g_q = gamma (gamma != 0):
+//   t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)),  zeta = (beta - alpha) / (2 gamma)   =   +-2|gamma| / (|d| + sqrt(d^2 + 4 gamma^2))
+// This scalar chain sits on the critical path of every Jacobi round (N-1 rounds per sweep), and FP64 sqrt / divide are
+// ~200-cycle software sequences. The ANGLE only needs a few digits (an error eps_t leaves a residual eps_t*|gamma|, so
+// quadratic convergence is kept down to 1e-7 per sweep), but the rotation must be orthonormal to FP64 precision. So: the
+// ratio is evaluated in FP32 on exponent-normalised inputs, and c = 1/sqrt(1+t^2) is refined in FP64 by two Newton steps.
+__device__ __forceinline__ void jacobi_cs(double alpha, double beta, double gamma, double& c, double& s) {
+  const double d = beta - alpha;
+  const double ad = fabs(d), g2 = 2.0 * fabs(gamma);
+  const double m = fmax(ad, g2);
+  int ex = ((__double2hiint(m) >> 20) & 0x7ff) - 1023;              // m = 1.x * 2^ex
+  ex = max(-1000, min(1000, ex));
+  const double scale = __hiloint2double((1023 - ex) << 20, 0);     // 2^-ex, exact
+  const float fd = (float)(ad * scale), fg = (float)(g2 * scale);  // both in [0, 2), the larger one in [1, 2)
+  const float r = sqrtf(fmaf(fd, fd, fg * fg));
+  const float ft = __fdividef(fg, fd + r);                          // in (0, 1]
+  const bool pos = (d == 0.0) || ((d > 0.0) == (gamma > 0.0));
+  const double t = pos ? (double)ft : -(double)ft;
+  const double x = fma(t, t, 1.0);
+  double c0 = (double)rsqrtf((float)x);
+  c0 = c0 * fma(-0.5 * x, c0 * c0, 1.5);
+  c0 = c0 * fma(-0.5 * x, c0 * c0, 1.5);
+  c = c0;
+  s = c0 * t;
+}
+
 // Round-robin (chess tournament) schedule over np = even number of players; step in [0, np-1), k in [0, np/2).
 __device__ __forceinline__ void rr_pair(int np, int step, int k, int& p, int& q) {
   const int m = np - 1;
@@ -52,11 +79,8 @@ jacobi_step_kernel(double* __restrict__ GT, double* __restrict__ VT, int ld, int
     const double beta = red[1][0] + red[1][1] + red[1][2] + red[1][3];
     const double gamma = red[2][0] + red[2][1] + red[2][2] + red[2][3];
     double c = 1.0, s = 0.0;
-    if (fabs(gamma) > tol * sqrt(alpha * beta) && gamma != 0.0) {
-      const double zeta = (beta - alpha) / (2.0 * gamma);
-      const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-      c = 1.0 / sqrt(1.0 + t * t);
-      s = c * t;
+    if (gamma * gamma > tol * tol * alpha * beta) {
+      jacobi_cs(alpha, beta, gamma, c, s);
       atomicAdd(&sc->jacobi_rotations, 1);
     }
     cs_s[0] = c; cs_s[1] = s;
@@ -129,10 +153,8 @@ jacobi_block_kernel(double* __restrict__ GT, double* __restrict__ VT, int ld, in
       if (gamma * gamma > tol * tol * alpha * beta) {
         // t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = (beta-alpha)/(2 gamma), written with one sqrt, one division
         // and one rsqrt on the critical path
-        const double d = beta - alpha;
-        const double r = sqrt(d * d + 4.0 * gamma * gamma);
-        const double t = ((d == 0.0 || (d > 0.0) == (gamma > 0.0)) ? 2.0 : -2.0) * fabs(gamma) / (fabs(d) + r);
-        const double c = rsqrt(1.0 + t * t), s = c * t;
+        double c, s;
+        jacobi_cs(alpha, beta, gamma, c, s);
         if (j == 0) {
           atomicAdd(&rot_count, 1);
           atomicMax(&max_rel, (unsigned long long)__double_as_longlong(gamma * gamma / (alpha * beta)));   // squared cosine
@@ -216,10 +238,8 @@ jacobi_persistent_kernel(double* GT, double* VT, int ld, int n, int nb, double t
 #pragma unroll
     for (int w = 0; w < WPG; w++) { alpha += red[grp][w][0]; beta += red[grp][w][1]; gamma += red[grp][w][2]; }
     if (gamma * gamma > tol * tol * alpha * beta) {
-      const double d = beta - alpha;
-      const double r = sqrt(d * d + 4.0 * gamma * gamma);
-      const double t = ((d == 0.0 || (d > 0.0) == (gamma > 0.0)) ? 2.0 : -2.0) * fabs(gamma) / (fabs(d) + r);
-      const double c = rsqrt(1.0 + t * t), s = c * t;
+      double c, s;
+      jacobi_cs(alpha, beta, gamma, c, s);
       if (j == 0) {
         atomicAdd(&rot_count, 1);
         atomicMax(&max_rel, (unsigned long long)__double_as_longlong(gamma * gamma / (alpha * beta)));   // squared cosine
@@ -334,7 +354,7 @@ jacobi_persistent_kernel(double* GT, double* VT, int ld, int n, int nb, double t
 // |lambda| order, acceptance test and the commit of B, A = B D, D, VT. One warp per row pair.
 // ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024, 1)
-eigen_small_kernel(const double* __restrict__ C, int ld, int n, double* __restrict__ VT, double* __restrict__ B, double* __restrict__ A,
+eigen_small_kernel(const double* __restrict__ GT, int ld, int n, double* __restrict__ VT, double* __restrict__ B, double* __restrict__ A,
                    double* __restrict__ D, double tol, int max_sweeps, DevScalars* __restrict__ sc) {
   extern __shared__ __align__(16) double sm[];
   const int np = (n + 1) & ~1;           // players of the round-robin (dummy when n is odd)
@@ -347,20 +367,15 @@ eigen_small_kernel(const double* __restrict__ C, int ld, int n, double* __restri
   __shared__ int rotations, rejected;
   __shared__ double smin[32], smax[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-  for (int i = tid; i < n * n; i += blockDim.x) Vs[(i / n) * rs + (i % n)] = VT[(size_t)(i / n) * ld + (i % n)];
-  __syncthreads();
-  // G[i][j] = sum_k V[i][k] C[j][k]   (C symmetric)
+  // G = V C was formed by the tensor-core GEMM just before this launch
   for (int i = tid; i < n * n; i += blockDim.x) {
-    const int r = i % n, c = i / n;      // a warp shares one row of C (broadcast) and walks rows of V (odd stride)
-    const double* crow = C + (size_t)c * ld;
-    const double* vrow = Vs + (size_t)r * rs;
-    double a = 0.0;
-    for (int k = 0; k < n; k++) a += vrow[k] * crow[k];
-    Gs[r * rs + c] = a;
+    Vs[(i / n) * rs + (i % n)] = VT[(size_t)(i / n) * ld + (i % n)];
+    Gs[(i / n) * rs + (i % n)] = GT[(size_t)(i / n) * ld + (i % n)];
   }
   __syncthreads();
   for (int sweep = 0; sweep < max_sweeps; sweep++) {
     if (tid == 0) rotations = 0;
+    int my_rot = 0;          // per-warp count, published once per sweep (one shared atomic per round per pair serialises)
     __syncthreads();
     for (int step = 0; step < np - 1; step++) {
       for (int k = warp; k < np / 2; k += nwarps) {
@@ -371,11 +386,10 @@ eigen_small_kernel(const double* __restrict__ C, int ld, int n, double* __restri
         double a = 0, b = 0, g = 0;
         for (int c = lane; c < n; c += 32) { const double x = gp[c], y = gq[c]; a += x * x; b += y * y; g += x * y; }
         a = warp_sum_butterfly(a); b = warp_sum_butterfly(b); g = warp_sum_butterfly(g);
-        if (fabs(g) > tol * sqrt(a * b) && g != 0.0) {
-          const double zeta = (b - a) / (2.0 * g);
-          const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-          const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
-          if (lane == 0) atomicAdd(&rotations, 1);
+        if (g * g > tol * tol * a * b) {
+          double c, s;
+          jacobi_cs(a, b, g, c, s);
+          my_rot++;
           double* vp = Vs + (size_t)p * rs; double* vq = Vs + (size_t)q * rs;
           for (int cidx = lane; cidx < n; cidx += 32) {
             const double x = gp[cidx], y = gq[cidx];
@@ -387,6 +401,8 @@ eigen_small_kernel(const double* __restrict__ C, int ld, int n, double* __restri
       }
       __syncthreads();
     }
+    if (lane == 0 && my_rot) atomicAdd(&rotations, my_rot);
+    __syncthreads();
     const int done = (rotations == 0);
     __syncthreads();
     if (done) break;
@@ -571,11 +587,12 @@ void launch_jacobi_sweep(cudaStream_t st, double* GT, double* VT, int ld, int n,
 constexpr size_t kMaxDynSmem = 227 * 1024 - 2048;  // leave room for the kernels' static shared memory
 size_t eigen_small_smem_bytes(int n) { return sizeof(double) * (2 * (size_t)n * (n | 1) + 2 * n) + sizeof(int) * n + 16; }
 bool eigen_small_fits(int n) { return eigen_small_smem_bytes(n) <= kMaxDynSmem; }
-void launch_eigen_small(cudaStream_t st, const double* C, int ld, int n, double* VT, double* B, double* A, double* D, double tol,
-                        int max_sweeps, DevScalars* sc) {
+void launch_eigen_small(cudaStream_t st, const double* C, int ld, int n, double* VT, double* GT, double* B, double* A, double* D,
+                        double tol, int max_sweeps, DevScalars* sc) {
+  launch_gemm_tn(st, n, n, n, VT, ld, C, ld, GT, ld);   // GT[i][j] = sum_k VT[i][k] C[j][k]
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(eigen_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem); attr = true; }
-  eigen_small_kernel<<<1, 1024, eigen_small_smem_bytes(n), st>>>(C, ld, n, VT, B, A, D, tol, max_sweeps, sc);
+  eigen_small_kernel<<<1, 1024, eigen_small_smem_bytes(n), st>>>(GT, ld, n, VT, B, A, D, tol, max_sweeps, sc);
 }
 
 static int g_jacobi_threads = 512;

@@ -72,8 +72,8 @@ void launch_viability_boundaries(cudaStream_t st, const double* G, long long ldg
 void launch_set_identity(cudaStream_t st, double* M, int ld, int n);
 void launch_jacobi_sweep(cudaStream_t st, double* GT, double* VT, int ld, int n, double tol, DevScalars* sc, int* launches);
 bool eigen_small_fits(int n);
-void launch_eigen_small(cudaStream_t st, const double* C, int ld, int n, double* VT, double* B, double* A, double* D, double tol,
-                        int max_sweeps, DevScalars* sc);
+void launch_eigen_small(cudaStream_t st, const double* C, int ld, int n, double* VT, double* GT, double* B, double* A, double* D,
+                        double tol, int max_sweeps, DevScalars* sc);
 bool launch_jacobi_persistent(cudaStream_t st, double* GT, double* VT, int ld, int n, double tol, int max_sweeps, DevScalars* sc,
                               int num_sms, unsigned* ready);
 void launch_jacobi_block_sweep(cudaStream_t st, double* GT, double* VT, int ld, int n, double tol, DevScalars* sc, int* launches);
