@@ -375,7 +375,8 @@ int update_eigensystem(kcma* h, const double* dM) {
   ensure_vt(h);
   const double tol = 4.0 * 2.220446049250313e-16 * sqrt((double)N);
   const int max_sweeps = 40;
-  if (eigen_small_fits(N)) {  // the whole solver in one launch, everything in one SM's shared memory
+  static const int small_max = getenv("KCMA_EIGEN_SMALL_MAX") ? atoi(getenv("KCMA_EIGEN_SMALL_MAX")) : 116;
+  if (eigen_small_fits(N) && N <= small_max) {  // the whole solver in one launch, everything in one SM's shared memory
     launch_eigen_small(h->stream, dM, ld, N, h->dVT, h->dGT, h->dB, h->dA, h->dD, tol, max_sweeps, h->dSc);
     h->launches += 2;
     h->scalars_fresh = false;
@@ -603,7 +604,7 @@ int update_and_handle_constraints(kcma* h) {
           const int rows_padded = std::min(h->u_rows, round_up(J, 16) + 16);
           launch_constraint_scale(h->stream, h->dU, ld, N, h->dEvSample, h->dCount, h->dViol, h->cov_adaption_factor, rows_padded);
           splits = syrk_pick_splits(N, J, h->num_sms, h->max_splits);
-          launch_syrk_tt(h->stream, N, J, h->dU, ld, h->u_rows, h->dWsplit, ld, splits);
+          launch_syrk_tt(h->stream, N, J, nullptr, h->dU, ld, h->u_rows, h->dWsplit, ld, splits);
           h->launches += 2;
         }
       }
@@ -713,8 +714,11 @@ int do_tell(kcma* h) {
       const int rows_per = (max_count + splits - 1) / splits;
       launch_diag_rank_mu(h->stream, h->dS, ld, h->dCount, max_count, rows_per > 0 ? rows_per : 1, N, h->dWsplit, ld, splits);
     } else {
-      splits = syrk_pick_splits(N, max_count, h->num_sms, h->max_splits);
-      launch_syrk_tt(h->stream, N, max_count, h->dS, ld, h->s_rows_padded, h->dWsplit, ld, splits);
+      // the number of selected samples this rank owns is only known on the device (dCount); size the split-K for its
+      // expectation mu * local / lambda and let the kernel read the exact row count
+      const int expect = (int)std::min<uint64_t>(max_count, (uint64_t)mu * local_samples(h) / h->cur_lambda + 1);
+      splits = syrk_pick_splits(N, expect, h->num_sms, h->max_splits);
+      launch_syrk_tt(h->stream, N, max_count, h->dCount, h->dS, ld, h->s_rows_padded, h->dWsplit, ld, splits);
     }
     h->launches++;
     if (multi) { launch_reduce_splits(h->stream, h->dWsplit, ld, splits, N, h->dRed); h->launches++; }
@@ -1388,7 +1392,7 @@ int kcma_k_rank_mu(int device, uint64_t n, uint64_t rows, const double* t, const
   const int splits = syrk_pick_splits(N, (int)rows, sms, 16);
   K_CUDA(dmalloc(&dW, (size_t)splits * N * ld)); K_CUDA(dmalloc(&dP, (size_t)N * ld));
   K_CUDA(cudaMemcpy2D(dS, sizeof(double) * ld, s.data(), sizeof(double) * N, sizeof(double) * N, rows, cudaMemcpyHostToDevice));
-  launch_syrk_tt(0, N, (int)rows, dS, ld, (long long)rp, dW, ld, splits);
+  launch_syrk_tt(0, N, (int)rows, nullptr, dS, ld, (long long)rp, dW, ld, splits);
   launch_reduce_splits(0, dW, ld, splits, N, dP);
   std::vector<double> p((size_t)N * N);
   K_CUDA(cudaMemcpy2D(p.data(), sizeof(double) * N, dP, sizeof(double) * ld, sizeof(double) * N, N, cudaMemcpyDeviceToHost));

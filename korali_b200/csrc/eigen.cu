@@ -349,6 +349,259 @@ jacobi_persistent_kernel(double* GT, double* VT, int ld, int n, int nb, double t
 }
 
 // ------------------------------------------------------------------------------------------------------
+// Version 3: GRAM-UPDATE one-sided Jacobi on the FP64 tensor pipe (persistent, cooperative).
+// ncu on version 2c: the blocked rounds are shared-memory-bandwidth bound — every rotation re-reads and re-writes its
+// four rows (80 KB per pair) and every round recomputes three N-long dot products. Here a CTA handling the block pair
+// (I, J) = 8 rows touches each row exactly twice per step:
+//   (i)   Gamma = G8 G8^T (8x8) in ONE pass over the 8 rows with DMMA.8x8x4, operands straight from L2 (fragment a == b);
+//   (ii)  the same sequence of plane rotations as before is carried out on Gamma alone (Gamma <- J Gamma J^T, exact
+//         algebra: the dot products of the rotated rows ARE the entries of the updated Gamma), accumulating R (8x8);
+//   (iii) rows <- R * rows for G and V as two DMMAs per 8 columns, written back once.
+// Steps are ordered by point-to-point ready flags (each block is produced by one CTA and consumed by one CTA).
+// ------------------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(NT, 1)
+jacobi_gram_kernel(double* GT, double* VT, int ld, int n, int nb, double tol, int max_sweeps, DevScalars* sc, unsigned* ready) {
+  cg::grid_group grid = cg::this_grid();
+  constexpr int NW = NT / 32;
+  constexpr int MAXG = 10;                 // 8-column groups per warp: ld <= 8 * NW * MAXG
+  __shared__ double part[NW][64];          // per-warp partial Gram tiles
+  __shared__ double Gam[8][9];             // Gamma (padded)
+  __shared__ double Rm[8][9];              // accumulated rotation, rows_new = R rows_old
+  __shared__ int s_rot;
+  __shared__ unsigned long long s_max;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int ngroups = ld >> 3;
+  unsigned epoch = 0;
+
+  for (int sweep = 0; sweep < max_sweeps; sweep++) {
+    if (blockIdx.x == 0 && tid == 0) { sc->jacobi_rotations = 0; sc->jacobi_max_rel_bits = 0ull; sc->jacobi_sweeps = sweep + 1; }
+    int sweep_rot = 0;
+    unsigned long long sweep_max = 0ull;
+    grid.sync();
+    for (int step = 0; step < nb - 1; step++) {
+      int I, J;
+      rr_pair(nb, step, blockIdx.x, I, J);
+      if (tid == 0) {
+        volatile unsigned* rv = ready;
+        while (rv[I] < epoch || rv[J] < epoch) { }
+        __threadfence();
+      }
+      __syncthreads();
+      // row g of the 8-row working set lives at global row rowg
+      const int rowg = (g < 4 ? I * 4 + g : J * 4 + (g - 4));
+      const bool rvalid = rowg < n;
+      const double* grow = GT + (size_t)rowg * ld;
+      // ---- (i) Gram: lane (g,t) feeds x = G[row g][8 grp + 2t (+1)] as both A and B fragment ----
+      double c0 = 0.0, c1 = 0.0;
+      for (int grp = warp; grp < ngroups; grp += NW) {
+        double2 x = make_double2(0.0, 0.0);
+        if (rvalid) x = __ldcg(reinterpret_cast<const double2*>(grow + 8 * grp + 2 * t));
+        dmma884(c0, c1, x.x, x.x);
+        dmma884(c0, c1, x.y, x.y);
+      }
+      part[warp][g * 8 + 2 * t] = c0;
+      part[warp][g * 8 + 2 * t + 1] = c1;
+      // prefetch the B fragments of the apply phase (they do not depend on R): B[k = t | t+4][n = g] = row (t | t+4), col 8 grp + g
+      double bg0[MAXG], bg1[MAXG], bv0[MAXG], bv1[MAXG];
+      {
+        const int r0 = (t < 4 ? I * 4 + t : 0), r1 = J * 4 + t;   // rows t and 4+t of the working set (t in 0..3)
+        const bool v0 = r0 < n, v1 = r1 < n;
+#pragma unroll
+        for (int k = 0; k < MAXG; k++) {
+          const int grp = warp + k * NW;
+          bg0[k] = bg1[k] = bv0[k] = bv1[k] = 0.0;
+          if (grp < ngroups) {
+            const int col = 8 * grp + g;
+            if (v0) { bg0[k] = __ldcg(GT + (size_t)r0 * ld + col); bv0[k] = __ldcg(VT + (size_t)r0 * ld + col); }
+            if (v1) { bg1[k] = __ldcg(GT + (size_t)r1 * ld + col); bv1[k] = __ldcg(VT + (size_t)r1 * ld + col); }
+          }
+        }
+      }
+      if (tid == 0) { s_rot = 0; s_max = 0ull; }
+      __syncthreads();
+      if (tid < 64) {
+        double a = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; w++) a += part[w][tid];
+        Gam[tid >> 3][tid & 7] = a;
+        Rm[tid >> 3][tid & 7] = ((tid >> 3) == (tid & 7)) ? 1.0 : 0.0;
+      }
+      __syncthreads();
+      // ---- (ii) rotations on Gamma, warp 0. lane = (pair k = lane>>3, index j = lane&7) ----
+      if (warp == 0) {
+        const int k = lane >> 3, j = lane & 7;
+        const int rounds = (step == 0) ? 7 : 4;
+        for (int r = 0; r < rounds; r++) {
+          int p, q;
+          if (step == 0) rr_pair(8, r, k, p, q);            // full sweep over the 8 rows (intra-block pairs included)
+          else { p = k; q = 4 + ((k + r) & 3); }            // cross pairs only
+          const double alpha = Gam[p][p], beta = Gam[q][q], gamma = Gam[p][q];
+          double c = 1.0, s = 0.0;
+          const bool rot = gamma * gamma > tol * tol * alpha * beta;
+          if (rot) {
+            jacobi_cs(alpha, beta, gamma, c, s);
+            if (j == 0) {
+              atomicAdd(&s_rot, 1);
+              atomicMax(&s_max, (unsigned long long)__double_as_longlong(gamma * gamma / (alpha * beta)));
+            }
+          }
+          __syncwarp();
+          {  // rows p, q of Gamma and of R
+            const double x = Gam[p][j], y = Gam[q][j];
+            const double u = Rm[p][j], v = Rm[q][j];
+            __syncwarp();
+            Gam[p][j] = c * x - s * y; Gam[q][j] = s * x + c * y;
+            Rm[p][j] = c * u - s * v; Rm[q][j] = s * u + c * v;
+          }
+          __syncwarp();
+          {  // columns p, q of Gamma
+            const double x = Gam[j][p], y = Gam[j][q];
+            __syncwarp();
+            Gam[j][p] = c * x - s * y; Gam[j][q] = s * x + c * y;
+          }
+          __syncwarp();
+        }
+      }
+      __syncthreads();
+      // ---- (iii) rows <- R rows (skipped when nothing rotated) ----
+      if (s_rot != 0) {
+        const double a_lo = Rm[g][t], a_hi = Rm[g][4 + t];
+        double* gout = GT + (size_t)rowg * ld;
+        double* vout = VT + (size_t)rowg * ld;
+#pragma unroll
+        for (int k = 0; k < MAXG; k++) {
+          const int grp = warp + k * NW;
+          if (grp < ngroups) {
+            double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0;
+            dmma884(d0, d1, a_lo, bg0[k]); dmma884(d0, d1, a_hi, bg1[k]);
+            dmma884(e0, e1, a_lo, bv0[k]); dmma884(e0, e1, a_hi, bv1[k]);
+            if (rvalid) {
+              __stcg(reinterpret_cast<double2*>(gout + 8 * grp + 2 * t), make_double2(d0, d1));
+              __stcg(reinterpret_cast<double2*>(vout + 8 * grp + 2 * t), make_double2(e0, e1));
+            }
+          }
+        }
+      }
+      epoch++;
+      __syncthreads();
+      if (tid == 0) {
+        sweep_rot += s_rot; sweep_max = max(sweep_max, s_max);
+        __threadfence();
+        volatile unsigned* rv = ready;
+        rv[I] = epoch; rv[J] = epoch;
+      }
+    }
+    if (tid == 0 && sweep_rot) {
+      atomicAdd(&sc->jacobi_rotations, sweep_rot);
+      atomicMax(&sc->jacobi_max_rel_bits, sweep_max);
+    }
+    grid.sync();
+    const int total = *reinterpret_cast<volatile int*>(&sc->jacobi_rotations);
+    const unsigned long long mb = *reinterpret_cast<volatile unsigned long long*>(&sc->jacobi_max_rel_bits);
+    grid.sync();
+    if (total == 0 || __longlong_as_double((long long)mb) < 1e-20) break;
+  }
+}
+
+// Version 3, one step per launch (N too large for one co-resident CTA per block pair, e.g. N = 4096: 512 pairs).
+// Same Gram-update step; the apply-phase operands are loaded after the rotations (no register prefetch: 32+ groups per warp).
+template <int NT>
+__global__ void __launch_bounds__(NT, 2)
+jacobi_gram_step_kernel(double* GT, double* VT, int ld, int n, int nb, int step, double tol, DevScalars* sc) {
+  constexpr int NW = NT / 32;
+  __shared__ double part[NW][64];
+  __shared__ double Gam[8][9];
+  __shared__ double Rm[8][9];
+  __shared__ int s_rot;
+  __shared__ unsigned long long s_max;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int ngroups = ld >> 3;
+  int I, J;
+  rr_pair(nb, step, blockIdx.x, I, J);
+  const int rowg = (g < 4 ? I * 4 + g : J * 4 + (g - 4));
+  const bool rvalid = rowg < n;
+  const double* grow = GT + (size_t)rowg * ld;
+  double c0 = 0.0, c1 = 0.0;
+  for (int grp = warp; grp < ngroups; grp += NW) {
+    double2 x = make_double2(0.0, 0.0);
+    if (rvalid) x = *reinterpret_cast<const double2*>(grow + 8 * grp + 2 * t);
+    dmma884(c0, c1, x.x, x.x);
+    dmma884(c0, c1, x.y, x.y);
+  }
+  part[warp][g * 8 + 2 * t] = c0;
+  part[warp][g * 8 + 2 * t + 1] = c1;
+  if (tid == 0) { s_rot = 0; s_max = 0ull; }
+  __syncthreads();
+  if (tid < 64) {
+    double a = 0.0;
+#pragma unroll
+    for (int w = 0; w < NW; w++) a += part[w][tid];
+    Gam[tid >> 3][tid & 7] = a;
+    Rm[tid >> 3][tid & 7] = ((tid >> 3) == (tid & 7)) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const int k = lane >> 3, j = lane & 7;
+    const int rounds = (step == 0) ? 7 : 4;
+    for (int r = 0; r < rounds; r++) {
+      int p, q;
+      if (step == 0) rr_pair(8, r, k, p, q);
+      else { p = k; q = 4 + ((k + r) & 3); }
+      const double alpha = Gam[p][p], beta = Gam[q][q], gamma = Gam[p][q];
+      double c = 1.0, s = 0.0;
+      if (gamma * gamma > tol * tol * alpha * beta) {
+        jacobi_cs(alpha, beta, gamma, c, s);
+        if (j == 0) {
+          atomicAdd(&s_rot, 1);
+          atomicMax(&s_max, (unsigned long long)__double_as_longlong(gamma * gamma / (alpha * beta)));
+        }
+      }
+      __syncwarp();
+      {
+        const double x = Gam[p][j], y = Gam[q][j];
+        const double u = Rm[p][j], v = Rm[q][j];
+        __syncwarp();
+        Gam[p][j] = c * x - s * y; Gam[q][j] = s * x + c * y;
+        Rm[p][j] = c * u - s * v; Rm[q][j] = s * u + c * v;
+      }
+      __syncwarp();
+      {
+        const double x = Gam[j][p], y = Gam[j][q];
+        __syncwarp();
+        Gam[j][p] = c * x - s * y; Gam[j][q] = s * x + c * y;
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  if (s_rot == 0) return;
+  const double a_lo = Rm[g][t], a_hi = Rm[g][4 + t];
+  const int r0 = I * 4 + t, r1 = J * 4 + t;
+  const bool v0 = r0 < n, v1 = r1 < n;
+  double* gout = GT + (size_t)rowg * ld;
+  double* vout = VT + (size_t)rowg * ld;
+  // every warp owns whole 8-column groups: it reads all 8 rows of a group before writing them, so in-place is safe
+  for (int grp = warp; grp < ngroups; grp += NW) {
+    const int col = 8 * grp + g;
+    const double bg0 = v0 ? GT[(size_t)r0 * ld + col] : 0.0, bg1 = v1 ? GT[(size_t)r1 * ld + col] : 0.0;
+    const double bv0 = v0 ? VT[(size_t)r0 * ld + col] : 0.0, bv1 = v1 ? VT[(size_t)r1 * ld + col] : 0.0;
+    double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0;
+    dmma884(d0, d1, a_lo, bg0); dmma884(d0, d1, a_hi, bg1);
+    dmma884(e0, e1, a_lo, bv0); dmma884(e0, e1, a_hi, bv1);
+    __syncwarp();
+    if (rvalid) {
+      *reinterpret_cast<double2*>(gout + 8 * grp + 2 * t) = make_double2(d0, d1);
+      *reinterpret_cast<double2*>(vout + 8 * grp + 2 * t) = make_double2(e0, e1);
+    }
+  }
+  if (tid == 0) {
+    atomicAdd(&sc->jacobi_rotations, s_rot);
+    atomicMax(&sc->jacobi_max_rel_bits, s_max);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // Version 2b: the WHOLE eigensolver in one launch for small N (N <= 116: G and V fit the 227 KB of one SM):
 // G = V C, cyclic one-sided Jacobi sweeps until no rotation fires, Rayleigh quotients, sign convention, ascending
 // |lambda| order, acceptance test and the commit of B, A = B D, D, VT. One warp per row pair.
@@ -612,6 +865,22 @@ bool launch_jacobi_persistent(cudaStream_t st, double* GT, double* VT, int ld, i
   if (nb / 2 > num_sms) return false;
   const char* e = getenv("KCMA_JACOBI_PERSISTENT");
   if (e && atoi(e) == 0) return false;
+  const bool gram = !(e && atoi(e) == 2);   // KCMA_JACOBI_PERSISTENT=2 selects the shared-memory version 2c
+  if (gram) {
+    static int okg = -1;
+    if (okg < 0) {
+      int dev = 0, coop = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+      okg = coop;
+    }
+    if (okg && ld <= 8 * 16 * 10) {
+      cudaMemsetAsync(ready, 0, sizeof(unsigned) * nb, st);
+      void* gargs[] = {&GT, &VT, &ld, &n, &nb, &tol, &max_sweeps, &sc, &ready};
+      if (cudaLaunchCooperativeKernel((void*)jacobi_gram_kernel<512>, dim3(nb / 2), dim3(512), gargs, 0, st) == cudaSuccess) return true;
+      cudaGetLastError();
+    }
+  }
   static int ok = -1;
   if (ok < 0) {
     int dev = 0, coop = 0;
@@ -627,6 +896,17 @@ bool launch_jacobi_persistent(cudaStream_t st, double* GT, double* VT, int ld, i
 }
 
 void launch_jacobi_block_sweep(cudaStream_t st, double* GT, double* VT, int ld, int n, double tol, DevScalars* sc, int* launches) {
+  {
+    const char* e = getenv("KCMA_JACOBI_GRAM");
+    if (!(e && atoi(e) == 0)) {   // Gram-update steps, one launch per step (any N)
+      int nb4 = (n + 3) / 4;
+      nb4 = (nb4 + 1) & ~1;
+      reset_rotations_kernel<<<1, 1, 0, st>>>(sc);
+      for (int step = 0; step < nb4 - 1; step++) jacobi_gram_step_kernel<256><<<nb4 / 2, 256, 0, st>>>(GT, VT, ld, n, nb4, step, tol, sc);
+      if (launches) *launches += nb4;
+      return;
+    }
+  }
   const int br = jacobi_block_rows(ld);
   if (br == 0) { launch_jacobi_sweep(st, GT, VT, ld, n, tol, sc, launches); return; }
   static bool attr = false;

@@ -121,7 +121,8 @@ gemm_tn_kernel(int M, int Nc, int K, const double* __restrict__ A, int lda, cons
 // W[split][n x ldw] (lower-triangular 128x128 tiles) = sum over this split's k-range of S[k][d]*S[k][e].
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(THREADS, 1)
-syrk_tt_kernel(int n, int K, const double* __restrict__ S, int lds, double* __restrict__ W, int ldw, int ktiles_per_split) {
+syrk_tt_kernel(int n, int K, const int* __restrict__ kptr, const double* __restrict__ S, int lds, double* __restrict__ W, int ldw) {
+  if (kptr) K = min(K, *kptr);   // actual number of operand rows, known only on the device (selected samples of this rank)
   extern __shared__ __align__(16) double smem[];
   double* Sa = smem;                          // [STAGES][BK][PADN]
   double* Sb = smem + STAGES * BK * PADN;
@@ -135,6 +136,7 @@ syrk_tt_kernel(int n, int K, const double* __restrict__ S, int lds, double* __re
   const bool diag = (bi == bj);
   const int d0 = bi * BM, e0 = bj * BN;
   const int nk_total = (K + BK - 1) / BK;
+  const int ktiles_per_split = (nk_total + (int)gridDim.y - 1) / (int)gridDim.y;
   const int kt_begin = blockIdx.y * ktiles_per_split;
   const int kt_end = min(nk_total, kt_begin + ktiles_per_split);
   const int nk = max(0, kt_end - kt_begin);
@@ -259,13 +261,12 @@ int syrk_pick_splits(int n, int K, int num_sms, int max_splits) {
   return best;
 }
 
-void launch_syrk_tt(cudaStream_t st, int n, int K, const double* S, int lds, long long s_rows, double* W, int ldw, int splits) {
-  if (want_tma() && launch_syrk_tt_tma(st, n, K, S, lds, s_rows, W, ldw, splits)) return;
+void launch_syrk_tt(cudaStream_t st, int n, int K, const int* kptr, const double* S, int lds, long long s_rows, double* W, int ldw,
+                    int splits) {
+  if (want_tma() && launch_syrk_tt_tma(st, n, K, kptr, S, lds, s_rows, W, ldw, splits)) return;
   ensure_attrs();
-  const int nk = (K + BK - 1) / BK;
-  const int per = (nk + splits - 1) / splits;
   dim3 grid(syrk_tiles(n), splits);
-  syrk_tt_kernel<<<grid, THREADS, syrk_tt_smem_bytes(), st>>>(n, K, S, lds, W, ldw, per > 0 ? per : 1);
+  syrk_tt_kernel<<<grid, THREADS, syrk_tt_smem_bytes(), st>>>(n, K, kptr, S, lds, W, ldw);
 }
 
 }  // namespace kc

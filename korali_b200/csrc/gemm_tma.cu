@@ -65,6 +65,9 @@ __device__ __forceinline__ void store_pair2(double* p, bool ok0, bool ok1, doubl
 // -----------------------------------------------------------------------------------------------------------------
 // tmA: tensor {K (ld), M rows}, box {16, 128}; tmB: tensor {K (ld), Nc rows}, box {16, 128}; both SWIZZLE_128B.
 // -----------------------------------------------------------------------------------------------------------------
+// PERSISTENT: grid = #SMs; every CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... (column tile fastest, so the
+// eight column tiles of one Z row panel are in flight together and share it in L2). The stage ring and its phases run
+// continuously across tiles, so the producer warp is already loading the next tile while the DMMA warps store this one.
 __global__ void __launch_bounds__(TTHREADS, 1)
 gemm_tn_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int Nc, int K,
                    double* __restrict__ C, int ldc) {
@@ -73,8 +76,9 @@ gemm_tn_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   uint64_t* full = reinterpret_cast<uint64_t*>(tiles + (size_t)TSTAGES * STAGE_BYTES);
   uint64_t* empty = full + TSTAGES;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row0 = blockIdx.y * TBM, col0 = blockIdx.x * TBN;
   const int nk = (K + TBK - 1) / TBK;
+  const int ntn = (Nc + TBN - 1) / TBN, ntm = (M + TBM - 1) / TBM;
+  const int ntiles = ntn * ntm;
   if (threadIdx.x == 0) {
     for (int s = 0; s < TSTAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], CONSUMER_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -84,12 +88,16 @@ gemm_tn_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   if (warp == CONSUMER_WARPS) {
     // ===== TMA producer warp (one elected lane) =====
     if (lane == 0) {
-      for (int kt = 0; kt < nk; kt++) {
-        const int s = kt % TSTAGES;
-        if (kt >= TSTAGES) mbar_wait(&empty[s], ((kt / TSTAGES) - 1) & 1);
-        mbar_expect_tx(&full[s], STAGE_BYTES);
-        tma_load_2d(tiles + (size_t)s * STAGE_BYTES, &tmA, kt * TBK, row0, &full[s]);
-        tma_load_2d(tiles + (size_t)s * STAGE_BYTES + TILE_BYTES, &tmB, kt * TBK, col0, &full[s]);
+      int it = 0;   // global k-tile counter across output tiles
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int row0 = (tile / ntn) * TBM, col0 = (tile % ntn) * TBN;
+        for (int kt = 0; kt < nk; kt++, it++) {
+          const int s = it % TSTAGES;
+          if (it >= TSTAGES) mbar_wait(&empty[s], ((it / TSTAGES) - 1) & 1);
+          mbar_expect_tx(&full[s], STAGE_BYTES);
+          tma_load_2d(tiles + (size_t)s * STAGE_BYTES, &tmA, kt * TBK, row0, &full[s]);
+          tma_load_2d(tiles + (size_t)s * STAGE_BYTES + TILE_BYTES, &tmB, kt * TBK, col0, &full[s]);
+        }
       }
     }
     return;
@@ -97,46 +105,49 @@ gemm_tn_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   // ===== DMMA consumer warps: 2 x 4 warps, warp tile 64 x 32 =====
   const int g = lane >> 2, t = lane & 3;
   const int wm = warp >> 2, wn = warp & 3;
-  double acc[8][4][2];
-#pragma unroll
-  for (int i = 0; i < 8; i++)
-#pragma unroll
-    for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
   // byte offset inside a tile of the element (row = base + 8 i + g, k = 2s + (t&1) + 8 (t>>1)):
   //   row*128 + (((s + 4 (t>>1)) ^ g) << 4) + (t&1)*8          (row & 7 == g)
   int koff[4];
 #pragma unroll
   for (int s = 0; s < 4; s++) koff[s] = (((s + 4 * (t >> 1)) ^ g) << 4) + (t & 1) * 8;
   const int a_row = (wm * 64 + g) * 128, b_row = (wn * 32 + g) * 128;
-
-  for (int kt = 0; kt < nk; kt++) {
-    const int s = kt % TSTAGES;
-    mbar_wait(&full[s], (kt / TSTAGES) & 1);
-    const uint8_t* as = tiles + (size_t)s * STAGE_BYTES + a_row;
-    const uint8_t* bs = tiles + (size_t)s * STAGE_BYTES + TILE_BYTES + b_row;
+  int it = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int row0 = (tile / ntn) * TBM, col0 = (tile % ntn) * TBN;
+    double acc[8][4][2];
 #pragma unroll
-    for (int kk = 0; kk < 4; kk++) {
-      double a[8], b[4];
+    for (int i = 0; i < 8; i++)
 #pragma unroll
-      for (int i = 0; i < 8; i++) a[i] = *reinterpret_cast<const double*>(as + i * 1024 + koff[kk]);
+      for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int kt = 0; kt < nk; kt++, it++) {
+      const int s = it % TSTAGES;
+      mbar_wait(&full[s], (it / TSTAGES) & 1);
+      const uint8_t* as = tiles + (size_t)s * STAGE_BYTES + a_row;
+      const uint8_t* bs = tiles + (size_t)s * STAGE_BYTES + TILE_BYTES + b_row;
 #pragma unroll
-      for (int j = 0; j < 4; j++) b[j] = *reinterpret_cast<const double*>(bs + j * 1024 + koff[kk]);
+      for (int kk = 0; kk < 4; kk++) {
+        double a[8], b[4];
 #pragma unroll
-      for (int i = 0; i < 8; i++)
+        for (int i = 0; i < 8; i++) a[i] = *reinterpret_cast<const double*>(as + i * 1024 + koff[kk]);
 #pragma unroll
-        for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        for (int j = 0; j < 4; j++) b[j] = *reinterpret_cast<const double*>(bs + j * 1024 + koff[kk]);
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[s]);
-  }
 #pragma unroll
-  for (int i = 0; i < 8; i++) {
-    const int row = row0 + wm * 64 + i * 8 + g;
-    if (row >= M) continue;
+    for (int i = 0; i < 8; i++) {
+      const int row = row0 + wm * 64 + i * 8 + g;
+      if (row >= M) continue;
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const int col = col0 + wn * 32 + j * 8 + 2 * t;
-      store_pair2(C + (size_t)row * ldc + col, col < Nc, col + 1 < Nc, acc[i][j][0], acc[i][j][1]);
+      for (int j = 0; j < 4; j++) {
+        const int col = col0 + wn * 32 + j * 8 + 2 * t;
+        store_pair2(C + (size_t)row * ldc + col, col < Nc, col + 1 < Nc, acc[i][j][0], acc[i][j][1]);
+      }
     }
   }
 }
@@ -145,7 +156,8 @@ gemm_tn_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 // tmS: tensor {n columns (ld), K rows}, box {16 columns, 16 rows}, SWIZZLE_128B. A 128-column operand tile = 8 boxes.
 // -----------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TTHREADS, 1)
-syrk_tt_tma_kernel(const __grid_constant__ CUtensorMap tmS, int n, int K, double* __restrict__ W, int ldw, int ktiles_per_split) {
+syrk_tt_tma_kernel(const __grid_constant__ CUtensorMap tmS, int n, int K, const int* __restrict__ kptr, double* __restrict__ W, int ldw) {
+  if (kptr) K = min(K, *kptr);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(tiles + (size_t)TSTAGES * STAGE_BYTES);
@@ -158,6 +170,7 @@ syrk_tt_tma_kernel(const __grid_constant__ CUtensorMap tmS, int n, int K, double
   const bool diag = (bi == bj);
   const int d0 = bi * TBM, e0 = bj * TBN;
   const int nk_total = (K + TBK - 1) / TBK;
+  const int ktiles_per_split = (nk_total + (int)gridDim.y - 1) / (int)gridDim.y;
   const int kt_begin = blockIdx.y * ktiles_per_split;
   const int kt_end = min(nk_total, kt_begin + ktiles_per_split);
   const int nk = max(0, kt_end - kt_begin);
@@ -281,20 +294,21 @@ bool launch_gemm_tn_tma(cudaStream_t st, int M, int Nc, int K, const double* A, 
   if ((lda % 2) || (ldb % 2) || ((uintptr_t)A & 15) || ((uintptr_t)B & 15)) return false;
   CUtensorMap ta, tb;
   if (!make_map(&ta, A, M, lda, TBK, TBM) || !make_map(&tb, B, Nc, ldb, TBK, TBN)) return false;
-  dim3 grid((Nc + TBN - 1) / TBN, (M + TBM - 1) / TBM);
-  gemm_tn_tma_kernel<<<grid, TTHREADS, TMA_SMEM, st>>>(ta, tb, M, Nc, K, C, ldc);
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  const int ntiles = ((Nc + TBN - 1) / TBN) * ((M + TBM - 1) / TBM);
+  gemm_tn_tma_kernel<<<ntiles < sms ? ntiles : sms, TTHREADS, TMA_SMEM, st>>>(ta, tb, M, Nc, K, C, ldc);
   return true;
 }
 
-bool launch_syrk_tt_tma(cudaStream_t st, int n, int K, const double* S, int lds, long long s_rows, double* W, int ldw, int splits) {
+bool launch_syrk_tt_tma(cudaStream_t st, int n, int K, const int* kptr, const double* S, int lds, long long s_rows, double* W, int ldw,
+                        int splits) {
   if (!tma_ready()) return false;
   if ((lds % 2) || ((uintptr_t)S & 15)) return false;
   CUtensorMap ts;
   if (!make_map(&ts, S, s_rows, lds, 16, TBK)) return false;
-  const int nk = (K + TBK - 1) / TBK;
-  const int per = (nk + splits - 1) / splits;
   dim3 grid(syrk_tiles(n), splits);
-  syrk_tt_tma_kernel<<<grid, TTHREADS, TMA_SMEM, st>>>(ts, n, K, W, ldw, per > 0 ? per : 1);
+  syrk_tt_tma_kernel<<<grid, TTHREADS, TMA_SMEM, st>>>(ts, n, K, kptr, W, ldw);
   return true;
 }
 

@@ -13,11 +13,13 @@ size_t syrk_tt_smem_bytes();
 void launch_gemm_tn(cudaStream_t st, int M, int Nc, int K, const double* A, int lda, const double* B, int ldb, double* C, int ldc);
 int syrk_tiles(int n);
 int syrk_pick_splits(int n, int K, int num_sms, int max_splits);
-void launch_syrk_tt(cudaStream_t st, int n, int K, const double* S, int lds, long long s_rows, double* W, int ldw, int splits);
+void launch_syrk_tt(cudaStream_t st, int n, int K, const int* kptr, const double* S, int lds, long long s_rows, double* W, int ldw,
+                    int splits);
 
 // gemm_tma.cu (TMA + mbarrier staging; return false when the tensor maps cannot be built)
 bool launch_gemm_tn_tma(cudaStream_t st, int M, int Nc, int K, const double* A, int lda, const double* B, int ldb, double* C, int ldc);
-bool launch_syrk_tt_tma(cudaStream_t st, int n, int K, const double* S, int lds, long long s_rows, double* W, int ldw, int splits);
+bool launch_syrk_tt_tma(cudaStream_t st, int n, int K, const int* kptr, const double* S, int lds, long long s_rows, double* W, int ldw,
+                        int splits);
 
 // rng.cu
 void launch_philox_normal(cudaStream_t st, double* Z, int ldz, long long rows, int n, unsigned long long seed, unsigned generation,
