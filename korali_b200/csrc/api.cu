@@ -18,6 +18,7 @@
 #include "kernels.h"
 
 using namespace kc;
+namespace kc { extern long long* g_jacobi_dbg; }
 
 namespace {
 
@@ -375,7 +376,7 @@ int update_eigensystem(kcma* h, const double* dM) {
   ensure_vt(h);
   const double tol = 4.0 * 2.220446049250313e-16 * sqrt((double)N);
   const int max_sweeps = 40;
-  static const int small_max = getenv("KCMA_EIGEN_SMALL_MAX") ? atoi(getenv("KCMA_EIGEN_SMALL_MAX")) : 116;
+  static const int small_max = getenv("KCMA_EIGEN_SMALL_MAX") ? atoi(getenv("KCMA_EIGEN_SMALL_MAX")) : 24;
   if (eigen_small_fits(N) && N <= small_max) {  // the whole solver in one launch, everything in one SM's shared memory
     launch_eigen_small(h->stream, dM, ld, N, h->dVT, h->dGT, h->dB, h->dA, h->dD, tol, max_sweeps, h->dSc);
     h->launches += 2;
@@ -1320,6 +1321,11 @@ int kcma_set_scalar(kcma_t* h, const char* key, double v) {
 }
 
 // ---- measurement ------------------------------------------------------------------------------------------
+// debug hook (not part of include/kcma.h): phase timestamps of the Gram Jacobi kernel, 32 steps x 8 slots
+extern "C" int kcma_debug_jacobi_timestamps(long long* out256) {
+  if (!kc::g_jacobi_dbg) return 1;
+  return cudaMemcpy(out256, kc::g_jacobi_dbg, sizeof(long long) * 256, cudaMemcpyDeviceToHost) != cudaSuccess;
+}
 int kcma_timing_enable(kcma_t* h, int on) { h->timing = on != 0; return 0; }
 int kcma_timing_get(kcma_t* h, const char* phase, double* ms, uint64_t* calls) {
   resolve_timers(h);

@@ -361,8 +361,10 @@ jacobi_persistent_kernel(double* GT, double* VT, int ld, int n, int nb, double t
 // ------------------------------------------------------------------------------------------------------
 template <int NT>
 __global__ void __launch_bounds__(NT, 1)
-jacobi_gram_kernel(double* GT, double* VT, int ld, int n, int nb, double tol, int max_sweeps, DevScalars* sc, unsigned* ready) {
+jacobi_gram_kernel(double* GT, double* VT, int ld, int n, int nb, double tol, int max_sweeps, DevScalars* sc, unsigned* ready,
+                   long long* dbg /* nullable: phase timestamps of CTA 0, sweep 1 (profiles/microbench/jacobi_phases.py) */) {
   cg::grid_group grid = cg::this_grid();
+#define KCMA_TS(slot) do { if (dbg && blockIdx.x == 1 && tid == 0 && sweep == 1 && step >= 8 && step < 40) dbg[(step - 8) * 8 + (slot)] = clock64(); } while (0)
   constexpr int NW = NT / 32;
   constexpr int MAXG = 10;                 // 8-column groups per warp: ld <= 8 * NW * MAXG
   __shared__ double part[NW][64];          // per-warp partial Gram tiles
@@ -382,26 +384,37 @@ jacobi_gram_kernel(double* GT, double* VT, int ld, int n, int nb, double tol, in
     for (int step = 0; step < nb - 1; step++) {
       int I, J;
       rr_pair(nb, step, blockIdx.x, I, J);
+      KCMA_TS(0);
       if (tid == 0) {
         volatile unsigned* rv = ready;
         while (rv[I] < epoch || rv[J] < epoch) { }
         __threadfence();
       }
+      KCMA_TS(1);
       __syncthreads();
+      KCMA_TS(2);
       // row g of the 8-row working set lives at global row rowg
       const int rowg = (g < 4 ? I * 4 + g : J * 4 + (g - 4));
       const bool rvalid = rowg < n;
       const double* grow = GT + (size_t)rowg * ld;
       // ---- (i) Gram: lane (g,t) feeds x = G[row g][8 grp + 2t (+1)] as both A and B fragment ----
-      double c0 = 0.0, c1 = 0.0;
-      for (int grp = warp; grp < ngroups; grp += NW) {
-        double2 x = make_double2(0.0, 0.0);
-        if (rvalid) x = __ldcg(reinterpret_cast<const double2*>(grow + 8 * grp + 2 * t));
-        dmma884(c0, c1, x.x, x.x);
-        dmma884(c0, c1, x.y, x.y);
+      double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+      {
+        double2 xs[MAXG];   // all loads in flight before the first DMMA: one L2 round trip instead of one per group
+#pragma unroll
+        for (int k = 0; k < MAXG; k++) {
+          const int grp = warp + k * NW;
+          xs[k] = make_double2(0.0, 0.0);
+          if (rvalid && grp < ngroups) xs[k] = __ldcg(reinterpret_cast<const double2*>(grow + 8 * grp + 2 * t));
+        }
+#pragma unroll
+        for (int k = 0; k < MAXG; k++) {   // two independent accumulator chains
+          dmma884(c0, c1, xs[k].x, xs[k].x);
+          dmma884(c2, c3, xs[k].y, xs[k].y);
+        }
       }
-      part[warp][g * 8 + 2 * t] = c0;
-      part[warp][g * 8 + 2 * t + 1] = c1;
+      part[warp][g * 8 + 2 * t] = c0 + c2;
+      part[warp][g * 8 + 2 * t + 1] = c1 + c3;
       // prefetch the B fragments of the apply phase (they do not depend on R): B[k = t | t+4][n = g] = row (t | t+4), col 8 grp + g
       double bg0[MAXG], bg1[MAXG], bv0[MAXG], bv1[MAXG];
       {
@@ -419,6 +432,7 @@ jacobi_gram_kernel(double* GT, double* VT, int ld, int n, int nb, double tol, in
         }
       }
       if (tid == 0) { s_rot = 0; s_max = 0ull; }
+      KCMA_TS(3);
       __syncthreads();
       if (tid < 64) {
         double a = 0.0;
@@ -428,10 +442,12 @@ jacobi_gram_kernel(double* GT, double* VT, int ld, int n, int nb, double tol, in
         Rm[tid >> 3][tid & 7] = ((tid >> 3) == (tid & 7)) ? 1.0 : 0.0;
       }
       __syncthreads();
+      KCMA_TS(4);
       // ---- (ii) rotations on Gamma, warp 0. lane = (pair k = lane>>3, index j = lane&7) ----
       if (warp == 0) {
         const int k = lane >> 3, j = lane & 7;
         const int rounds = (step == 0) ? 7 : 4;
+        int my_rot = 0, my_big = 0;
         for (int r = 0; r < rounds; r++) {
           int p, q;
           if (step == 0) rr_pair(8, r, k, p, q);            // full sweep over the 8 rows (intra-block pairs included)
@@ -441,10 +457,8 @@ jacobi_gram_kernel(double* GT, double* VT, int ld, int n, int nb, double tol, in
           const bool rot = gamma * gamma > tol * tol * alpha * beta;
           if (rot) {
             jacobi_cs(alpha, beta, gamma, c, s);
-            if (j == 0) {
-              atomicAdd(&s_rot, 1);
-              atomicMax(&s_max, (unsigned long long)__double_as_longlong(gamma * gamma / (alpha * beta)));
-            }
+            my_rot++;
+            my_big |= (gamma * gamma > 1e-20 * alpha * beta) ? 1 : 0;   // cos^2 >= (1e-10)^2: not yet in the quadratic tail
           }
           __syncwarp();
           {  // rows p, q of Gamma and of R
@@ -462,8 +476,14 @@ jacobi_gram_kernel(double* GT, double* VT, int ld, int n, int nb, double tol, in
           }
           __syncwarp();
         }
+        // lanes j == 0 of the four pair groups hold the counts
+        my_rot = (j == 0) ? my_rot : 0;
+        my_rot += __shfl_xor_sync(0xffffffffu, my_rot, 8); my_rot += __shfl_xor_sync(0xffffffffu, my_rot, 16);
+        my_big = __any_sync(0xffffffffu, my_big);
+        if (lane == 0) { s_rot = my_rot; s_max = my_big ? 0x3ff0000000000000ull : 0ull; }   // "max cos^2" collapsed to {0, 1.0}
       }
       __syncthreads();
+      KCMA_TS(5);
       // ---- (iii) rows <- R rows (skipped when nothing rotated) ----
       if (s_rot != 0) {
         const double a_lo = Rm[g][t], a_hi = Rm[g][4 + t];
@@ -484,6 +504,7 @@ jacobi_gram_kernel(double* GT, double* VT, int ld, int n, int nb, double tol, in
         }
       }
       epoch++;
+      KCMA_TS(6);
       __syncthreads();
       if (tid == 0) {
         sweep_rot += s_rot; sweep_max = max(sweep_max, s_max);
@@ -491,6 +512,7 @@ jacobi_gram_kernel(double* GT, double* VT, int ld, int n, int nb, double tol, in
         volatile unsigned* rv = ready;
         rv[I] = epoch; rv[J] = epoch;
       }
+      KCMA_TS(7);
     }
     if (tid == 0 && sweep_rot) {
       atomicAdd(&sc->jacobi_rotations, sweep_rot);
@@ -502,6 +524,7 @@ jacobi_gram_kernel(double* GT, double* VT, int ld, int n, int nb, double tol, in
     grid.sync();
     if (total == 0 || __longlong_as_double((long long)mb) < 1e-20) break;
   }
+#undef KCMA_TS
 }
 
 // Version 3, one step per launch (N too large for one co-resident CTA per block pair, e.g. N = 4096: 512 pairs).
@@ -544,6 +567,7 @@ jacobi_gram_step_kernel(double* GT, double* VT, int ld, int n, int nb, int step,
   if (warp == 0) {
     const int k = lane >> 3, j = lane & 7;
     const int rounds = (step == 0) ? 7 : 4;
+    int my_rot = 0, my_big = 0;
     for (int r = 0; r < rounds; r++) {
       int p, q;
       if (step == 0) rr_pair(8, r, k, p, q);
@@ -552,10 +576,8 @@ jacobi_gram_step_kernel(double* GT, double* VT, int ld, int n, int nb, int step,
       double c = 1.0, s = 0.0;
       if (gamma * gamma > tol * tol * alpha * beta) {
         jacobi_cs(alpha, beta, gamma, c, s);
-        if (j == 0) {
-          atomicAdd(&s_rot, 1);
-          atomicMax(&s_max, (unsigned long long)__double_as_longlong(gamma * gamma / (alpha * beta)));
-        }
+        my_rot++;
+        my_big |= (gamma * gamma > 1e-20 * alpha * beta) ? 1 : 0;
       }
       __syncwarp();
       {
@@ -573,6 +595,10 @@ jacobi_gram_step_kernel(double* GT, double* VT, int ld, int n, int nb, int step,
       }
       __syncwarp();
     }
+    my_rot = (j == 0) ? my_rot : 0;
+    my_rot += __shfl_xor_sync(0xffffffffu, my_rot, 8); my_rot += __shfl_xor_sync(0xffffffffu, my_rot, 16);
+    my_big = __any_sync(0xffffffffu, my_big);
+    if (lane == 0) { s_rot = my_rot; s_max = my_big ? 0x3ff0000000000000ull : 0ull; }
   }
   __syncthreads();
   if (s_rot == 0) return;
@@ -849,6 +875,7 @@ void launch_eigen_small(cudaStream_t st, const double* C, int ld, int n, double*
 }
 
 static int g_jacobi_threads = 512;
+long long* g_jacobi_dbg = nullptr;   // device buffer of phase timestamps (KCMA_JACOBI_DEBUG=1)
 // rows per block the 227 KB of shared memory allows for this n (0: use the unblocked step kernel)
 int jacobi_block_rows(int ld) {
   for (int br = 4; br >= 2; br >>= 1)
@@ -876,7 +903,9 @@ bool launch_jacobi_persistent(cudaStream_t st, double* GT, double* VT, int ld, i
     }
     if (okg && ld <= 8 * 16 * 10) {
       cudaMemsetAsync(ready, 0, sizeof(unsigned) * nb, st);
-      void* gargs[] = {&GT, &VT, &ld, &n, &nb, &tol, &max_sweeps, &sc, &ready};
+      static long long* dbg = nullptr;
+      if (getenv("KCMA_JACOBI_DEBUG") && !dbg) { cudaMalloc(&dbg, sizeof(long long) * 8 * 32); cudaMemset(dbg, 0, sizeof(long long) * 8 * 32); g_jacobi_dbg = dbg; }
+      void* gargs[] = {&GT, &VT, &ld, &n, &nb, &tol, &max_sweeps, &sc, &ready, &dbg};
       if (cudaLaunchCooperativeKernel((void*)jacobi_gram_kernel<512>, dim3(nb / 2), dim3(512), gargs, 0, st) == cudaSuccess) return true;
       cudaGetLastError();
     }
