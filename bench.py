@@ -210,8 +210,11 @@ def ours_arm(args, rank, world):
                         "Philox(seed, generation) counters)"},
         "gpu_launches": int(launches),
         "clocks": clk,
-        "roofline": {"kernel": "gemm_tn_kernel (sampling GEMM Y = Z (B D)^T)", "bound": "tensor", "achieved": achieved, "peak": peak,
-                     "unit": "TFLOP/s", "frac": (achieved / peak) if peak else None, "traffic": None,
+        "roofline": {"kernel": "gemm_tn_tma_kernel (sampling GEMM Y = Z (B D)^T, TMA + mbarrier + DMMA.8x8x4)", "bound": "tensor",
+                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if peak else None,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch at N=1 (profiles/r01_ncu_full_summary.md):
+                     # 537.5 MB + 492.0 MB = the algorithmic Z read + Y write, i.e. no re-reads
+                     "traffic": 1029548288 if world == 1 else None, "traffic_unit": "bytes per launch",
                      "peak_source": "MEASURED_FP64.json: cuBLAS DGEMM 8192^3 sustained on this pool's B200 (FP64 DMMA issue peak 37.1)",
                      "algorithmic_flops_per_launch": f_sample, "avg_launch_ms": gemm_avg},
         "phases_ms_per_generation": {k: (v[0] / args.steps) for k, v in phases.items()},
