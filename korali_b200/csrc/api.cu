@@ -709,7 +709,10 @@ int do_tell(kcma* h) {
   int splits;
   {
     PhaseTimer t(h, "rank_mu");
-    if (h->cfg.diagonal_covariance) {
+    if (h->cfg.mu_type == KCMA_MU_PROPORTIONAL && !h->cfg.diagonal_covariance) {
+      splits = 1;   // signed weights: see signed_rank_mu_kernel
+      launch_signed_rank_mu(h->stream, h->dS, ld, h->dCount, h->dSelW, N, h->dWsplit, ld);
+    } else if (h->cfg.diagonal_covariance) {
       splits = std::max(1, (max_count + h->rows_per_cta * 8 - 1) / (h->rows_per_cta * 8));
       if (splits > h->max_splits) splits = h->max_splits;
       const int rows_per = (max_count + splits - 1) / splits;

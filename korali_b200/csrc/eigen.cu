@@ -927,7 +927,7 @@ bool launch_jacobi_persistent(cudaStream_t st, double* GT, double* VT, int ld, i
 void launch_jacobi_block_sweep(cudaStream_t st, double* GT, double* VT, int ld, int n, double tol, DevScalars* sc, int* launches) {
   {
     const char* e = getenv("KCMA_JACOBI_GRAM");
-    if (!(e && atoi(e) == 0)) {   // Gram-update steps, one launch per step (any N)
+    if (e && atoi(e) == 1) {   // Gram-update steps, one launch per step (opt-in: at N = 4096 the unblocked step kernel is faster)
       int nb4 = (n + 3) / 4;
       nb4 = (nb4 + 1) & ~1;
       reset_rotations_kernel<<<1, 1, 0, st>>>(sc);

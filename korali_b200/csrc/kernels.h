@@ -64,6 +64,8 @@ void launch_adapt_c(cudaStream_t st, double* C, int ldc, const double* W, int ld
 void launch_reduce_splits(cudaStream_t st, const double* W, int ldw, int splits, int n, double* P);
 void launch_diag_rank_mu(cudaStream_t st, const double* S, int lds, const int* count_ptr, int max_count, int rows_per_cta, int n,
                          double* W, int ldw, int slabs);
+void launch_signed_rank_mu(cudaStream_t st, const double* S, int lds, const int* count_ptr, const double* sel_weight, int n, double* W,
+                           int ldw);
 void launch_sigma(cudaStream_t st, const double* C, int ldc, int n, const double* min_sd_update, int any_min_sd, double cs,
                   double damp, double chi_n, double trace, int is_sigma_bounded, int mu_value_gt1, int viability_regime,
                   double global_success_lr, double target_success_rate, DevScalars* sc);

@@ -126,7 +126,7 @@ gather_mean_kernel(const double* __restrict__ Y, int ldy, int mirrored, int from
         const double ss = (mirrored && (s & 1)) ? -sigma : sigma;
         x0 = m0 + ss * v.x; x1 = m1 + ss * v.y;
       }
-      const double rw = sqrt(w);
+      const double rw = sqrt(fabs(w));   // Proportional weights can be negative: the sign is applied by signed_rank_mu_kernel
       const double t0 = in0 ? rw * (x0 - m0) : 0.0, t1 = in1 ? rw * (x1 - m1) : 0.0;
       *reinterpret_cast<double2*>(S + (size_t)j * lds + d) = make_double2(t0, t1);
       a0 += w * x0; a1 += w * x1;
@@ -314,6 +314,24 @@ diag_rank_mu_kernel(const double* __restrict__ S, int lds, const int* __restrict
   W[(size_t)blockIdx.y * n * ldw + (size_t)d * ldw + d] = a;
 }
 
+// Mu Type "Proportional" (:584-600) can produce negative weights (F(x) of mixed sign), which the S^T S form cannot
+// express. P[d][e] = sum_j sign(w_j) S[j][d] S[j][e] with S = sqrt|w| t, one thread per lower-triangular entry.
+// Plain FP64 FMAs: this mode is a small-N convenience in the reference's tests, not a throughput path.
+__global__ void __launch_bounds__(256)
+signed_rank_mu_kernel(const double* __restrict__ S, int lds, const int* __restrict__ count_ptr, const double* __restrict__ sel_weight,
+                      int n, double* __restrict__ W, int ldw) {
+  const int e = blockIdx.x * 16 + (threadIdx.x & 15);
+  const int d = blockIdx.y * 16 + (threadIdx.x >> 4);
+  if (d >= n || e > d) return;
+  const int count = *count_ptr;
+  double a = 0.0;
+  for (int j = 0; j < count; j++) {
+    const double v = S[(size_t)j * lds + d] * S[(size_t)j * lds + e];
+    a += (sel_weight[j] < 0.0) ? -v : v;
+  }
+  W[(size_t)d * ldw + e] = a;
+}
+
 // ---- scalar tail: min/max diag (:709-717), viability boundaries (:426-437), updateSigma (:720-761),
 // numericalErrorTreatment (:763-772), min/max standard deviation (:679-687). Single block.
 __global__ void __launch_bounds__(1024)
@@ -433,6 +451,11 @@ void launch_diag_rank_mu(cudaStream_t st, const double* S, int lds, const int* c
                          int n, double* W, int ldw, int slabs) {
   dim3 grid((n + 255) / 256, slabs);
   diag_rank_mu_kernel<<<grid, 256, 0, st>>>(S, lds, count_ptr, rows_per_cta, n, W, ldw);
+}
+void launch_signed_rank_mu(cudaStream_t st, const double* S, int lds, const int* count_ptr, const double* sel_weight, int n, double* W,
+                           int ldw) {
+  dim3 grid((n + 15) / 16, (n + 15) / 16);
+  signed_rank_mu_kernel<<<grid, 256, 0, st>>>(S, lds, count_ptr, sel_weight, n, W, ldw);
 }
 void launch_sigma(cudaStream_t st, const double* C, int ldc, int n, const double* min_sd_update, int any_min_sd, double cs,
                   double damp, double chi_n, double trace, int is_sigma_bounded, int mu_value_gt1, int viability_regime,

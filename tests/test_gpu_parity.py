@@ -371,3 +371,20 @@ def test_constrained_optimum_config5():
     assert s.scalar("Is Viability Regime") == 0
     assert np.all(xb[:2] >= 1.0 - 1e-9) and np.all(xb[2:4] >= -1.0)
     assert abs(best - fstar) < 1e-6 and best <= fstar + 1e-9
+
+
+def test_warm_started_eigensolver_does_not_drift():
+    """The eigenvector basis is carried from generation to generation (warm start). After 1500 generations it must
+    still be orthonormal and reproduce C (no accumulation of rotation round-off)."""
+    n = 48
+    s = _lib.Solver(n=n, population_size=96, objective="NegRosenbrock", seed=4, initial_value=0.0, initial_stddev=0.5)
+    s.set_scalar("Termination Criteria/Max Model Evaluations", 1e15)
+    s.run(1500)
+    c = s.get("Covariance Matrix").reshape(n, n)
+    s.ask()
+    b = s.get("Covariance Eigenvector Matrix").reshape(n, n)
+    d = s.get("Axis Lengths")
+    orth = np.abs(b.T @ b - np.eye(n)).max()
+    res = np.abs((b * d**2) @ b.T - c).max() / np.abs(c).max()
+    print("after 1500 generations: |B^T B - I| = %.2e, |B D^2 B^T - C|/|C| = %.2e, cond = %.2e" % (orth, res, (d.max() / d.min())**2))
+    assert orth < 1e-12 and res < 1e-12

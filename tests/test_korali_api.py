@@ -112,8 +112,6 @@ class TestCorrectness:
     @pytest.mark.parametrize("mu_type,pop,tol", [("Linear", 8, 1e-4), ("Logarithmic", 8, 1e-4), ("Proportional", 64, 1e-3), ("Equal", 64, 1e-3)])
     def test_mu_types(self, mu_type, pop, tol):
         e = base_1d(pop); e["Solver"]["Mu Type"] = mu_type
-        if mu_type == "Proportional":
-            pytest.skip("Proportional weights with F(x) of mixed sign give negative weights (sqrt(w) operand of the SYRK): next row 8f-2")
         korali.Engine().run(e); checkMin(e, 0.23246, tol)
 
     def test_unsatisfiable_constraint(self):
