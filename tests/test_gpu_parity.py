@@ -388,3 +388,98 @@ def test_warm_started_eigensolver_does_not_drift():
     res = np.abs((b * d**2) @ b.T - c).max() / np.abs(c).max()
     print("after 1500 generations: |B^T B - I| = %.2e, |B D^2 B^T - C|/|C| = %.2e, cond = %.2e" % (orth, res, (d.max() / d.min())**2))
     assert orth < 1e-12 and res < 1e-12
+
+
+# ---------------------------------------------------------------- edge cases ---------------------------------
+@pytest.mark.parametrize("kw", [
+    dict(n=1, population_size=2, objective="NegSphere", initial_value=1.0, initial_stddev=1.0),
+    dict(n=1, population_size=8, objective="NegSumSq", mirrored_sampling=1, initial_value=2.0, initial_stddev=1.0),
+    dict(n=3, population_size=5, mu_value=2, objective="NegRosenbrock", initial_value=0.0, initial_stddev=0.3),   # mu = 1 would make C = aI + b y y^T degenerate: eigenbasis arbitrary
+    dict(n=17, population_size=34, objective="NegEllipsoid", mirrored_sampling=1, initial_value=1.0, initial_stddev=1.0),
+    dict(n=25, population_size=26, objective="NegSphere", initial_value=1.0, initial_stddev=1.0),      # smallest N on the Gram eigen path
+    dict(n=129, population_size=130, objective="NegSphere", diagonal_covariance=1, initial_value=1.0, initial_stddev=1.0),
+    dict(n=130, population_size=64, mu_type="Proportional", objective="NegSumSq", initial_value=1.0, initial_stddev=0.5),
+], ids=lambda k: "N%d-l%d" % (k["n"], k["population_size"]))
+def test_ragged_and_minimal_shapes_free_running(kw):
+    """Smallest / odd / ragged shapes through the whole generation loop against the oracle. When mu >= N the spectrum of C
+    is non-degenerate and both sides run free on the Philox stream; otherwise C = aI + (rank < N) has a degenerate
+    eigenspace whose basis is arbitrary, so the oracle's (B, D, y) are injected and the rest of the loop is compared."""
+    n, lam = kw["n"], kw["population_size"]
+    mu = kw.get("mu_value", lam // 2)
+    free = (mu >= n) and not kw.get("mirrored_sampling") or kw.get("diagonal_covariance")
+    s = _lib.Solver(seed=7, keep_population=1, **kw); o = O.Oracle(seed=7, **kw); o.set_scalar("Oracle/RNG Kind", 1)
+    for g in range(6):
+        if free:
+            s.run_generation(); o.run_generation()
+        else:
+            o.ask()
+            s.inject(INJ_BD, np.concatenate([o.get("Covariance Eigenvector Matrix"), o.get("Axis Lengths")]))
+            s.inject(INJ_BDZ, o.get("BDZ Matrix"))
+            s.ask()
+            assert relerr(s.get("Sample Population"), o.get("Sample Population")) < 1e-12
+            s.inject(INJ_X, o.get("Sample Population"))
+            s.eval(); o.eval(); s.tell(); o.tell()
+        assert np.array_equal(s.get_index("Sorting Index"), o.get_index("Sorting Index")), g
+        for k in ["Current Mean", "Evolution Path", "Conjugate Evolution Path", "Covariance Matrix"]:
+            assert relerr(s.get(k), o.get(k)) < 1e-9, (g, k)
+        assert abs(s.scalar("Sigma") - o.scalar("Sigma")) < 1e-9 * o.scalar("Sigma")
+    # the device's own eigensolver + sampler on this shape: B D^2 B^T == C, finite samples
+    c = s.get("Covariance Matrix").reshape(n, n)
+    s.ask()
+    b = s.get("Covariance Eigenvector Matrix").reshape(n, n); d = s.get("Axis Lengths")
+    if not kw.get("diagonal_covariance"):
+        assert np.abs((b * d**2) @ b.T - c).max() < 1e-12 * np.abs(c).max()
+        assert np.abs(b.T @ b - np.eye(n)).max() < 1e-12
+    assert np.isfinite(s.get("Sample Population")).all()
+
+
+def test_invalid_configurations_raise():
+    """setInitialConfiguration range checks (CMAES.cpp.base:26, 89-93, 111-126, 131-136)."""
+    base = dict(n=4, population_size=8, objective="NegSphere", initial_value=0.0, initial_stddev=1.0)
+    for bad, match in [(dict(population_size=1), "larger 1"), (dict(population_size=7, mirrored_sampling=1), "even Sample Population"),
+                       (dict(initial_value=None), "cannot be inferred"), (dict(initial_stddev=None), "cannot be inferred"),
+                       (dict(mirrored_sampling=1, constraint_family="HalfSpace", n_constraints=1), "not applicable to problems with constraints"),
+                       (dict(constraint_family="HalfSpace", n_constraints=2, target_success_rate=1.5), "Invalid Target Success Rate"),
+                       (dict(objective=77), None)]:
+        kw = dict(base); kw.update(bad)
+        if bad.get("objective") == 77:
+            s = _lib.Solver(**kw)
+            with pytest.raises(KcmaError, match="unknown objective"):
+                s.run_generation()
+            continue
+        with pytest.raises(KcmaError, match=match):
+            _lib.Solver(**kw)
+    # defaults inferred from the bounds: mid-domain start, 0.3 * width (:111-126)
+    s = _lib.Solver(n=2, population_size=4, objective="NegSphere", lower_bound=[-2.0, 0.0], upper_bound=[4.0, 10.0])
+    assert np.array_equal(s.get("Current Mean"), [1.0, 5.0])
+    assert abs(s.scalar("Sigma") - np.sqrt((1.8**2 + 3.0**2) / 2)) < 1e-14
+
+
+def test_bound_violations_counted_and_resampled_like_the_oracle():
+    """isSampleFeasible + the rejection loop of prepareGeneration (:446-459). Default (Max Infeasible Resamplings = 0):
+    violations are counted, never resampled. With a finite limit every infeasible sample is redrawn (Philox attempt counter)."""
+    kw = dict(n=6, population_size=64, objective="NegSphere", lower_bound=-1.0, upper_bound=1.0, initial_value=0.5, initial_stddev=1.0, seed=3)
+    s = _lib.Solver(keep_population=1, **kw); o = O.Oracle(**kw); o.set_scalar("Oracle/RNG Kind", 1)
+    s.ask(); o.ask()
+    assert s.scalar("Infeasible Sample Count") == o.scalar("Infeasible Sample Count") > 0
+    assert relerr(s.get("Sample Population"), o.get("Sample Population")) < 1e-13
+    kw["max_infeasible_resamplings"] = 100000
+    s = _lib.Solver(keep_population=1, **kw); o = O.Oracle(**kw); o.set_scalar("Oracle/RNG Kind", 1)
+    for g in range(3):
+        s.ask(); o.ask()
+        x = s.get("Sample Population")
+        assert np.all(np.abs(x) <= 1.0)                              # every sample feasible after resampling
+        assert s.scalar("Infeasible Sample Count") == o.scalar("Infeasible Sample Count")
+        assert relerr(x, o.get("Sample Population")) < 1e-12          # same (sample, attempt) Philox counters
+        s.eval(); o.eval(); s.tell(); o.tell()
+
+
+def test_nonfinite_objective_is_an_error():
+    """Optimization::evaluate throws on a non-finite F(x) (optimization.cpp.base:32-33)."""
+    s = _lib.Solver(n=4, population_size=8, objective="NegEllipsoid", objective_coef=[1.0, 1.0, np.inf, 1.0], initial_value=1.0, initial_stddev=1.0)
+    with pytest.raises(KcmaError, match="Non finite value of function evaluation"):
+        s.run_generation()
+    s = _lib.Solver(n=4, population_size=8, objective="External", initial_value=1.0, initial_stddev=1.0)
+    s.ask()
+    with pytest.raises(KcmaError, match="Non finite"):
+        s.inject(INJ_F, [1.0, 2.0, np.nan, 0, 0, 0, 0, 0])
