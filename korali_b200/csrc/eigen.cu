@@ -82,6 +82,7 @@ jacobi_step_kernel(double* __restrict__ GT, double* __restrict__ VT, int ld, int
     if (gamma * gamma > tol * tol * alpha * beta) {
       jacobi_cs(alpha, beta, gamma, c, s);
       atomicAdd(&sc->jacobi_rotations, 1);
+      if (gamma * gamma > 1e-20 * alpha * beta) atomicMax(&sc->jacobi_max_rel_bits, 0x3ff0000000000000ull);   // not yet in the quadratic tail
     }
     cs_s[0] = c; cs_s[1] = s;
   }
@@ -530,7 +531,7 @@ jacobi_gram_kernel(double* GT, double* VT, int ld, int n, int nb, double tol, in
 // Version 3, one step per launch (N too large for one co-resident CTA per block pair, e.g. N = 4096: 512 pairs).
 // Same Gram-update step; the apply-phase operands are loaded after the rotations (no register prefetch: 32+ groups per warp).
 template <int NT>
-__global__ void __launch_bounds__(NT, 2)
+__global__ void __launch_bounds__(NT, 1)
 jacobi_gram_step_kernel(double* GT, double* VT, int ld, int n, int nb, int step, double tol, DevScalars* sc) {
   constexpr int NW = NT / 32;
   __shared__ double part[NW][64];
@@ -545,15 +546,20 @@ jacobi_gram_step_kernel(double* GT, double* VT, int ld, int n, int nb, int step,
   const int rowg = (g < 4 ? I * 4 + g : J * 4 + (g - 4));
   const bool rvalid = rowg < n;
   const double* grow = GT + (size_t)rowg * ld;
-  double c0 = 0.0, c1 = 0.0;
-  for (int grp = warp; grp < ngroups; grp += NW) {
-    double2 x = make_double2(0.0, 0.0);
-    if (rvalid) x = *reinterpret_cast<const double2*>(grow + 8 * grp + 2 * t);
-    dmma884(c0, c1, x.x, x.x);
-    dmma884(c0, c1, x.y, x.y);
+  double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+  for (int grp0 = warp; grp0 < ngroups; grp0 += NW * 8) {   // 8 groups in flight per warp
+    double2 xs[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int grp = grp0 + k * NW;
+      xs[k] = make_double2(0.0, 0.0);
+      if (rvalid && grp < ngroups) xs[k] = *reinterpret_cast<const double2*>(grow + 8 * grp + 2 * t);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) { dmma884(c0, c1, xs[k].x, xs[k].x); dmma884(c2, c3, xs[k].y, xs[k].y); }
   }
-  part[warp][g * 8 + 2 * t] = c0;
-  part[warp][g * 8 + 2 * t + 1] = c1;
+  part[warp][g * 8 + 2 * t] = c0 + c2;
+  part[warp][g * 8 + 2 * t + 1] = c1 + c3;
   if (tid == 0) { s_rot = 0; s_max = 0ull; }
   __syncthreads();
   if (tid < 64) {
@@ -608,17 +614,27 @@ jacobi_gram_step_kernel(double* GT, double* VT, int ld, int n, int nb, int step,
   double* gout = GT + (size_t)rowg * ld;
   double* vout = VT + (size_t)rowg * ld;
   // every warp owns whole 8-column groups: it reads all 8 rows of a group before writing them, so in-place is safe
-  for (int grp = warp; grp < ngroups; grp += NW) {
-    const int col = 8 * grp + g;
-    const double bg0 = v0 ? GT[(size_t)r0 * ld + col] : 0.0, bg1 = v1 ? GT[(size_t)r1 * ld + col] : 0.0;
-    const double bv0 = v0 ? VT[(size_t)r0 * ld + col] : 0.0, bv1 = v1 ? VT[(size_t)r1 * ld + col] : 0.0;
-    double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0;
-    dmma884(d0, d1, a_lo, bg0); dmma884(d0, d1, a_hi, bg1);
-    dmma884(e0, e1, a_lo, bv0); dmma884(e0, e1, a_hi, bv1);
-    __syncwarp();
-    if (rvalid) {
-      *reinterpret_cast<double2*>(gout + 8 * grp + 2 * t) = make_double2(d0, d1);
-      *reinterpret_cast<double2*>(vout + 8 * grp + 2 * t) = make_double2(e0, e1);
+  for (int grp0 = warp; grp0 < ngroups; grp0 += NW * 4) {   // 4 groups (16 loads) in flight per warp
+    double bg0[4], bg1[4], bv0[4], bv1[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int grp = grp0 + k * NW;
+      const int col = 8 * grp + g;
+      const bool ok = grp < ngroups;
+      bg0[k] = (ok && v0) ? GT[(size_t)r0 * ld + col] : 0.0; bg1[k] = (ok && v1) ? GT[(size_t)r1 * ld + col] : 0.0;
+      bv0[k] = (ok && v0) ? VT[(size_t)r0 * ld + col] : 0.0; bv1[k] = (ok && v1) ? VT[(size_t)r1 * ld + col] : 0.0;
+    }
+    __syncwarp();   // the whole warp has read its 8-column groups before any lane overwrites them (in place)
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int grp = grp0 + k * NW;
+      double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0;
+      dmma884(d0, d1, a_lo, bg0[k]); dmma884(d0, d1, a_hi, bg1[k]);
+      dmma884(e0, e1, a_lo, bv0[k]); dmma884(e0, e1, a_hi, bv1[k]);
+      if (rvalid && grp < ngroups) {
+        *reinterpret_cast<double2*>(gout + 8 * grp + 2 * t) = make_double2(d0, d1);
+        *reinterpret_cast<double2*>(vout + 8 * grp + 2 * t) = make_double2(e0, e1);
+      }
     }
   }
   if (tid == 0) {
@@ -927,11 +943,11 @@ bool launch_jacobi_persistent(cudaStream_t st, double* GT, double* VT, int ld, i
 void launch_jacobi_block_sweep(cudaStream_t st, double* GT, double* VT, int ld, int n, double tol, DevScalars* sc, int* launches) {
   {
     const char* e = getenv("KCMA_JACOBI_GRAM");
-    if (e && atoi(e) == 1) {   // Gram-update steps, one launch per step (opt-in: at N = 4096 the unblocked step kernel is faster)
+    if (!(e && atoi(e) == 0)) {   // Gram-update steps, one launch per step (N too large for the persistent kernel)
       int nb4 = (n + 3) / 4;
       nb4 = (nb4 + 1) & ~1;
       reset_rotations_kernel<<<1, 1, 0, st>>>(sc);
-      for (int step = 0; step < nb4 - 1; step++) jacobi_gram_step_kernel<256><<<nb4 / 2, 256, 0, st>>>(GT, VT, ld, n, nb4, step, tol, sc);
+      for (int step = 0; step < nb4 - 1; step++) jacobi_gram_step_kernel<512><<<nb4 / 2, 512, 0, st>>>(GT, VT, ld, n, nb4, step, tol, sc);
       if (launches) *launches += nb4;
       return;
     }

@@ -111,7 +111,7 @@ def test_transcendental_objectives(obj):
 
 
 # ---------------------------------------------------------------- K8 eigen ----------------------------------
-@pytest.mark.parametrize("n,cond", [(2, 10.0), (10, 1e3), (33, 1e6), (100, 1e8), (257, 1e4)])
+@pytest.mark.parametrize("n,cond", [(2, 10.0), (10, 1e3), (33, 1e6), (100, 1e8), (257, 1e4), (1000, 1e6), (1300, 1e3)])
 def test_eigen_residuals_and_eigenvalues(n, cond):
     rng = np.random.default_rng(n)
     q, _ = np.linalg.qr(rng.standard_normal((n, n)))
