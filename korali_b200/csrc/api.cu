@@ -338,7 +338,6 @@ diag_sample_kernel(const double* __restrict__ Z, double* __restrict__ Y, int ld,
   }
 }
 
-__global__ void add_infeasible_kernel(DevScalars* sc, unsigned long long v) { sc->infeasible_sample_count += v; }
 __global__ void add_infeasible_from_round_kernel(DevScalars* sc) { sc->infeasible_sample_count += sc->infeasible_this_round; }
 __global__ void flush_kernel(double* p, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = (double)i;

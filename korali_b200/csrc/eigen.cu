@@ -2,15 +2,16 @@
 // Replaces eigen() (CMAES.cpp.base:896-938: gsl_eigen_symmv + sort ABS_ASC) — the one step of the loop that
 // is not population-parallel; timed separately ("eigen" phase).
 //
-// Method (version 1): WARM-STARTED one-sided (Hestenes) Jacobi. With V0 = the eigenvectors of the previous
-// generation (C changes by ~c1+cmu per generation, so V0 nearly diagonalises it), form G = C V0 with the FP64
-// tensor-core GEMM and orthogonalise the columns of G by plane rotations accumulated into V. At convergence
-// C V = G has orthogonal columns, i.e. V holds the eigenvectors and lambda_i = v_i . g_i (Rayleigh quotient,
-// signed). Vectors are stored as ROWS (VT, GT) so each rotation touches contiguous memory.
-// One launch per round-robin step (n/2 disjoint pairs), one CTA per pair.
-#include "common.cuh"
+// Method: WARM-STARTED one-sided (Hestenes) Jacobi. With V0 = the eigenvectors of the previous generation (C changes by
+// ~c1+cmu per generation), form G = C V0 with the FP64 tensor-core GEMM and orthogonalise the columns of G by plane
+// rotations accumulated into V. At convergence C V = G has orthogonal columns: V holds the eigenvectors and
+// lambda_i = v_i . g_i (Rayleigh quotient, signed). Vectors are stored as ROWS (VT, GT) so rotations touch contiguous memory.
+// Kernels: eigen_small_kernel (tiny N, everything in one launch), jacobi_gram_kernel (persistent cooperative, Gram-update
+// steps on the DMMA pipe), jacobi_gram_step_kernel (the same step, one launch each, for large N). DESIGN.md section 6.
 #include <cooperative_groups.h>
 #include <stdlib.h>
+
+#include "common.cuh"
 #include "kernels.h"
 
 namespace cg = cooperative_groups;
@@ -53,300 +54,6 @@ __device__ __forceinline__ void rr_pair(int np, int step, int k, int& p, int& q)
   if (k == 0) { a = m; b = step; }
   else { a = (step + k) % m; b = (step - k + m) % m; }
   p = min(a, b); q = max(a, b);
-}
-
-__global__ void __launch_bounds__(128)
-jacobi_step_kernel(double* __restrict__ GT, double* __restrict__ VT, int ld, int n, int np, int step, double tol,
-                   DevScalars* __restrict__ sc) {
-  int p, q;
-  rr_pair(np, step, blockIdx.x, p, q);
-  if (q >= n) return;  // dummy player when n is odd
-  double* gp = GT + (size_t)p * ld; double* gq = GT + (size_t)q * ld;
-  double* vp = VT + (size_t)p * ld; double* vq = VT + (size_t)q * ld;
-  __shared__ double red[3][4];
-  __shared__ double cs_s[2];
-  double a = 0, b = 0, g = 0;
-  for (int i = threadIdx.x; i < n; i += 128) {
-    const double x = gp[i], y = gq[i];
-    a += x * x; b += y * y; g += x * y;
-  }
-  a = warp_sum_butterfly(a); b = warp_sum_butterfly(b); g = warp_sum_butterfly(g);
-  const int w = threadIdx.x >> 5;
-  if ((threadIdx.x & 31) == 0) { red[0][w] = a; red[1][w] = b; red[2][w] = g; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const double alpha = red[0][0] + red[0][1] + red[0][2] + red[0][3];
-    const double beta = red[1][0] + red[1][1] + red[1][2] + red[1][3];
-    const double gamma = red[2][0] + red[2][1] + red[2][2] + red[2][3];
-    double c = 1.0, s = 0.0;
-    if (gamma * gamma > tol * tol * alpha * beta) {
-      jacobi_cs(alpha, beta, gamma, c, s);
-      atomicAdd(&sc->jacobi_rotations, 1);
-      if (gamma * gamma > 1e-20 * alpha * beta) atomicMax(&sc->jacobi_max_rel_bits, 0x3ff0000000000000ull);   // not yet in the quadratic tail
-    }
-    cs_s[0] = c; cs_s[1] = s;
-  }
-  __syncthreads();
-  const double c = cs_s[0], s = cs_s[1];
-  if (s == 0.0) return;
-  for (int i = threadIdx.x; i < n; i += 128) {
-    const double x = gp[i], y = gq[i];
-    gp[i] = c * x - s * y; gq[i] = s * x + c * y;
-    const double u = vp[i], v = vq[i];
-    vp[i] = c * u - s * v; vq[i] = s * u + c * v;
-  }
-}
-
-// ------------------------------------------------------------------------------------------------------
-// Version 2a: BLOCKED one-sided Jacobi step. The unblocked step above streams all of G and V (16 MB at N=1000)
-// through the SMs for every one of the N-1 steps of a sweep. Here a CTA owns a PAIR OF ROW BLOCKS (BR rows of GT and
-// of VT each), stages them in shared memory (2*2*BR*N*8 B = 128 KB at N=1000, BR=4), performs all BR*BR cross-block
-// rotations on-chip (BR rounds of BR disjoint pairs, one thread group per pair), and writes the blocks back:
-// BR x fewer launches and BR x less L2 traffic per sweep. Step 0 of a sweep also rotates the pairs inside each block.
-// ------------------------------------------------------------------------------------------------------
-template <int BR, int NT>
-__global__ void __launch_bounds__(NT, 1)
-jacobi_block_kernel(double* __restrict__ GT, double* __restrict__ VT, int ld, int n, int nb, int step, int with_intra, double tol,
-                    DevScalars* __restrict__ sc) {
-  extern __shared__ __align__(16) double sm[];
-  constexpr int R2 = 2 * BR;
-  constexpr int TPG = NT / BR;           // threads per pair group
-  constexpr int WPG = TPG / 32;          // warps per group
-  double* Gs = sm;                       // [R2][ld]
-  double* Vs = sm + (size_t)R2 * ld;     // [R2][ld]
-  __shared__ double red[BR][WPG][3];
-  __shared__ int rot_count;
-  __shared__ unsigned long long max_rel;   // bits of the largest |cos(g_p, g_q)| rotated away (positive doubles order like integers)
-  int I, J;
-  rr_pair(nb, step, blockIdx.x, I, J);
-  const int tid = threadIdx.x;
-  if (tid == 0) { rot_count = 0; max_rel = 0ull; }
-  // stage the 2*BR rows of both matrices
-  for (int r = 0; r < R2; r++) {
-    const int grow = (r < BR ? I * BR + r : J * BR + (r - BR));
-    const bool valid = grow < n;
-    for (int c = 2 * tid; c < ld; c += 2 * NT) {
-      double2 g = make_double2(0.0, 0.0), v = g;
-      if (valid) {
-        g = *reinterpret_cast<const double2*>(GT + (size_t)grow * ld + c);
-        v = *reinterpret_cast<const double2*>(VT + (size_t)grow * ld + c);
-      }
-      *reinterpret_cast<double2*>(Gs + (size_t)r * ld + c) = g;
-      *reinterpret_cast<double2*>(Vs + (size_t)r * ld + c) = v;
-    }
-  }
-  __syncthreads();
-  const int grp = tid / TPG, j = tid % TPG, wig = j >> 5, lane = tid & 31;
-
-  auto rotate_round = [&](int p, int q, bool active) {
-    double a = 0, b = 0, g = 0;
-    if (active) {
-      const double* gp = Gs + (size_t)p * ld; const double* gq = Gs + (size_t)q * ld;
-      for (int c = j; c < n; c += TPG) { const double x = gp[c], y = gq[c]; a += x * x; b += y * y; g += x * y; }
-    }
-    a = warp_sum_butterfly(a); b = warp_sum_butterfly(b); g = warp_sum_butterfly(g);
-    if (lane == 0) { red[grp][wig][0] = a; red[grp][wig][1] = b; red[grp][wig][2] = g; }
-    __syncthreads();
-    if (active) {
-      double alpha = 0, beta = 0, gamma = 0;
-#pragma unroll
-      for (int w = 0; w < WPG; w++) { alpha += red[grp][w][0]; beta += red[grp][w][1]; gamma += red[grp][w][2]; }
-      if (gamma * gamma > tol * tol * alpha * beta) {
-        // t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = (beta-alpha)/(2 gamma), written with one sqrt, one division
-        // and one rsqrt on the critical path
-        double c, s;
-        jacobi_cs(alpha, beta, gamma, c, s);
-        if (j == 0) {
-          atomicAdd(&rot_count, 1);
-          atomicMax(&max_rel, (unsigned long long)__double_as_longlong(gamma * gamma / (alpha * beta)));   // squared cosine
-        }
-        double* gp = Gs + (size_t)p * ld; double* gq = Gs + (size_t)q * ld;
-        double* vp = Vs + (size_t)p * ld; double* vq = Vs + (size_t)q * ld;
-        for (int cidx = j; cidx < n; cidx += TPG) {
-          const double x = gp[cidx], y = gq[cidx];
-          gp[cidx] = c * x - s * y; gq[cidx] = s * x + c * y;
-          const double u = vp[cidx], v = vq[cidx];
-          vp[cidx] = c * u - s * v; vq[cidx] = s * u + c * v;
-        }
-      }
-    }
-    __syncthreads();
-  };
-
-  if (with_intra) {
-    if (BR == 4) {
-      // pairs inside a 4-row block: (0,1)(2,3) | (0,2)(1,3) | (0,3)(1,2); groups 0,1 -> block I, groups 2,3 -> block J
-      const int off = (grp >> 1) * BR, h = grp & 1;
-      const int pp[3][2][2] = {{{0, 1}, {2, 3}}, {{0, 2}, {1, 3}}, {{0, 3}, {1, 2}}};
-#pragma unroll
-      for (int r = 0; r < 3; r++) rotate_round(off + pp[r][h][0], off + pp[r][h][1], true);
-    } else if (BR == 2) {
-      rotate_round(grp * BR, grp * BR + 1, true);
-    }
-  }
-#pragma unroll
-  for (int r = 0; r < BR; r++) rotate_round(grp, BR + (grp + r) % BR, true);
-
-  if (rot_count == 0) return;  // nothing changed: skip the write-back
-  for (int r = 0; r < R2; r++) {
-    const int grow = (r < BR ? I * BR + r : J * BR + (r - BR));
-    if (grow >= n) continue;
-    for (int c = 2 * tid; c < ld; c += 2 * NT) {
-      *reinterpret_cast<double2*>(GT + (size_t)grow * ld + c) = *reinterpret_cast<const double2*>(Gs + (size_t)r * ld + c);
-      *reinterpret_cast<double2*>(VT + (size_t)grow * ld + c) = *reinterpret_cast<const double2*>(Vs + (size_t)r * ld + c);
-    }
-  }
-  if (tid == 0) {
-    atomicAdd(&sc->jacobi_rotations, rot_count);
-    atomicMax(&sc->jacobi_max_rel_bits, max_rel);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------------
-// Version 2c: the blocked sweeps as ONE persistent cooperative kernel. Per-step launches cost ~10 us each on this
-// system (250 steps x 18 sweeps at N = 1000); here CTA k walks the round-robin schedule itself and the steps are
-// separated by grid-wide barriers; convergence is decided on the device, so the whole Jacobi phase needs no host
-// round trip. Requires nb/2 <= number of SMs (one co-resident CTA per SM): N <= 1184 with 4-row blocks.
-// ------------------------------------------------------------------------------------------------------
-template <int BR, int NT>
-__global__ void __launch_bounds__(NT, 1)
-jacobi_persistent_kernel(double* GT, double* VT, int ld, int n, int nb, double tol, int max_sweeps, DevScalars* sc,
-                         unsigned* ready /* [nb], zero on entry: epoch at which each row block was last completed */) {
-  cg::grid_group grid = cg::this_grid();
-  unsigned epoch = 0;   // global step counter across sweeps
-  extern __shared__ __align__(16) double sm[];
-  constexpr int R2 = 2 * BR;
-  constexpr int TPG = NT / BR;
-  constexpr int WPG = TPG / 32;
-  double* Gs = sm;
-  double* Vs = sm + (size_t)R2 * ld;
-  __shared__ double red[BR][WPG][3];
-  __shared__ int rot_count;
-  __shared__ unsigned long long max_rel;
-  const int tid = threadIdx.x;
-  const int grp = tid / TPG, j = tid % TPG, wig = j >> 5, lane = tid & 31;
-
-  auto rotate_round = [&](int p, int q) {
-    double a = 0, b = 0, g = 0;
-    {
-      const double* gp = Gs + (size_t)p * ld; const double* gq = Gs + (size_t)q * ld;
-      for (int c = j; c < n; c += TPG) { const double x = gp[c], y = gq[c]; a += x * x; b += y * y; g += x * y; }
-    }
-    a = warp_sum_butterfly(a); b = warp_sum_butterfly(b); g = warp_sum_butterfly(g);
-    if (lane == 0) { red[grp][wig][0] = a; red[grp][wig][1] = b; red[grp][wig][2] = g; }
-    __syncthreads();
-    double alpha = 0, beta = 0, gamma = 0;
-#pragma unroll
-    for (int w = 0; w < WPG; w++) { alpha += red[grp][w][0]; beta += red[grp][w][1]; gamma += red[grp][w][2]; }
-    if (gamma * gamma > tol * tol * alpha * beta) {
-      double c, s;
-      jacobi_cs(alpha, beta, gamma, c, s);
-      if (j == 0) {
-        atomicAdd(&rot_count, 1);
-        atomicMax(&max_rel, (unsigned long long)__double_as_longlong(gamma * gamma / (alpha * beta)));   // squared cosine
-      }
-      double* gp = Gs + (size_t)p * ld; double* gq = Gs + (size_t)q * ld;
-      double* vp = Vs + (size_t)p * ld; double* vq = Vs + (size_t)q * ld;
-      for (int cidx = j; cidx < n; cidx += TPG) {
-        const double x = gp[cidx], y = gq[cidx];
-        gp[cidx] = c * x - s * y; gq[cidx] = s * x + c * y;
-        const double u = vp[cidx], v = vq[cidx];
-        vp[cidx] = c * u - s * v; vq[cidx] = s * u + c * v;
-      }
-    }
-    __syncthreads();
-  };
-
-  for (int sweep = 0; sweep < max_sweeps; sweep++) {
-    if (blockIdx.x == 0 && tid == 0) { sc->jacobi_rotations = 0; sc->jacobi_max_rel_bits = 0ull; sc->jacobi_sweeps = sweep + 1; }
-    int sweep_rot = 0;
-    unsigned long long sweep_max = 0ull;
-    grid.sync();
-    for (int step = 0; step < nb - 1; step++) {
-      int I, J;
-      rr_pair(nb, step, blockIdx.x, I, J);
-      if (tid == 0) {
-        rot_count = 0; max_rel = 0ull;
-        // point-to-point dependency: the two blocks of this step were produced by (at most) two other CTAs in the
-        // previous step; wait for exactly those instead of a grid-wide barrier
-        volatile unsigned* rv = ready;
-        while (rv[I] < epoch || rv[J] < epoch) { }
-        __threadfence();
-      }
-      __syncthreads();
-      {
-        // all loads first (one L2 round trip), then the shared-memory stores. L2 loads (ld.global.cg): the rows were
-        // written by another SM.
-        constexpr int CH = (1184 + 2 * NT - 1) / (2 * NT);   // column chunks per row (ld <= 1184)
-        double2 gbuf[R2][CH], vbuf[R2][CH];
-#pragma unroll
-        for (int r = 0; r < R2; r++) {
-          const int grow = (r < BR ? I * BR + r : J * BR + (r - BR));
-          const bool valid = grow < n;
-#pragma unroll
-          for (int k = 0; k < CH; k++) {
-            const int c = 2 * tid + k * 2 * NT;
-            double2 g = make_double2(0.0, 0.0), v = g;
-            if (valid && c < ld) {
-              g = __ldcg(reinterpret_cast<const double2*>(GT + (size_t)grow * ld + c));
-              v = __ldcg(reinterpret_cast<const double2*>(VT + (size_t)grow * ld + c));
-            }
-            gbuf[r][k] = g; vbuf[r][k] = v;
-          }
-        }
-#pragma unroll
-        for (int r = 0; r < R2; r++)
-#pragma unroll
-          for (int k = 0; k < CH; k++) {
-            const int c = 2 * tid + k * 2 * NT;
-            if (c < ld) {
-              *reinterpret_cast<double2*>(Gs + (size_t)r * ld + c) = gbuf[r][k];
-              *reinterpret_cast<double2*>(Vs + (size_t)r * ld + c) = vbuf[r][k];
-            }
-          }
-      }
-      __syncthreads();
-      if (step == 0) {
-        if (BR == 4) {
-          const int off = (grp >> 1) * BR, h = grp & 1;
-          const int pp[3][2][2] = {{{0, 1}, {2, 3}}, {{0, 2}, {1, 3}}, {{0, 3}, {1, 2}}};
-#pragma unroll
-          for (int r = 0; r < 3; r++) rotate_round(off + pp[r][h][0], off + pp[r][h][1]);
-        } else if (BR == 2) {
-          rotate_round(grp * BR, grp * BR + 1);
-        }
-      }
-#pragma unroll
-      for (int r = 0; r < BR; r++) rotate_round(grp, BR + (grp + r) % BR);
-      if (rot_count != 0) {
-        for (int r = 0; r < R2; r++) {
-          const int grow = (r < BR ? I * BR + r : J * BR + (r - BR));
-          if (grow >= n) continue;
-          for (int c = 2 * tid; c < ld; c += 2 * NT) {
-            __stcg(reinterpret_cast<double2*>(GT + (size_t)grow * ld + c), *reinterpret_cast<const double2*>(Gs + (size_t)r * ld + c));
-            __stcg(reinterpret_cast<double2*>(VT + (size_t)grow * ld + c), *reinterpret_cast<const double2*>(Vs + (size_t)r * ld + c));
-          }
-        }
-      }
-      epoch++;
-      __syncthreads();   // all global stores of this CTA are issued
-      if (tid == 0) {
-        sweep_rot += rot_count; sweep_max = max(sweep_max, max_rel);
-        __threadfence();  // ... and visible before the blocks are published
-        volatile unsigned* rv = ready;
-        rv[I] = epoch; rv[J] = epoch;
-      }
-    }
-    if (tid == 0 && sweep_rot) {
-      atomicAdd(&sc->jacobi_rotations, sweep_rot);
-      atomicMax(&sc->jacobi_max_rel_bits, sweep_max);
-    }
-    grid.sync();
-    const int total = *reinterpret_cast<volatile int*>(&sc->jacobi_rotations);
-    const unsigned long long mb = *reinterpret_cast<volatile unsigned long long*>(&sc->jacobi_max_rel_bits);
-    grid.sync();   // everybody has read the totals before block 0 resets them
-    if (total == 0 || __longlong_as_double((long long)mb) < 1e-20) break;   // squared cosine below (1e-10)^2
-  }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -873,12 +580,7 @@ void launch_set_identity(cudaStream_t st, double* M, int ld, int n) {
   dim3 grid((ld + 255) / 256, n);
   set_identity_kernel<<<grid, 256, 0, st>>>(M, ld, n);
 }
-void launch_jacobi_sweep(cudaStream_t st, double* GT, double* VT, int ld, int n, double tol, DevScalars* sc, int* launches) {
-  const int np = (n + 1) & ~1;
-  reset_rotations_kernel<<<1, 1, 0, st>>>(sc);
-  for (int step = 0; step < np - 1; step++) jacobi_step_kernel<<<np / 2, 128, 0, st>>>(GT, VT, ld, n, np, step, tol, sc);
-  if (launches) *launches += np;
-}
+
 constexpr size_t kMaxDynSmem = 227 * 1024 - 2048;  // leave room for the kernels' static shared memory
 size_t eigen_small_smem_bytes(int n) { return sizeof(double) * (2 * (size_t)n * (n | 1) + 2 * n) + sizeof(int) * n + 16; }
 bool eigen_small_fits(int n) { return eigen_small_smem_bytes(n) <= kMaxDynSmem; }
@@ -890,90 +592,42 @@ void launch_eigen_small(cudaStream_t st, const double* C, int ld, int n, double*
   eigen_small_kernel<<<1, 1024, eigen_small_smem_bytes(n), st>>>(GT, ld, n, VT, B, A, D, tol, max_sweeps, sc);
 }
 
-static int g_jacobi_threads = 512;
 long long* g_jacobi_dbg = nullptr;   // device buffer of phase timestamps (KCMA_JACOBI_DEBUG=1)
-// rows per block the 227 KB of shared memory allows for this n (0: use the unblocked step kernel)
-int jacobi_block_rows(int ld) {
-  for (int br = 4; br >= 2; br >>= 1)
-    if (sizeof(double) * 4 * (size_t)br * ld <= kMaxDynSmem) return br;
-  return 0;
-}
-// All sweeps in one cooperative launch. Returns false when the configuration does not fit (caller falls back to per-step launches).
+
+// All sweeps in one cooperative launch: one CTA per pair of 4-row blocks, so the whole tournament round must be
+// co-resident. Returns false when it is not (N > 8*num_sms, or rows longer than the kernel's register tile covers);
+// the caller then launches one jacobi_gram_step_kernel per tournament round.
 bool launch_jacobi_persistent(cudaStream_t st, double* GT, double* VT, int ld, int n, double tol, int max_sweeps, DevScalars* sc,
                               int num_sms, unsigned* ready) {
-  const int br = jacobi_block_rows(ld);
-  if (br != 4 || ld > 1184) return false;
-  int nb = (n + br - 1) / br;
-  nb = (nb + 1) & ~1;
-  if (nb / 2 > num_sms) return false;
+  int nb = ((n + 3) / 4 + 1) & ~1;
+  if (nb / 2 > num_sms || ld > 8 * 16 * 10) return false;
   const char* e = getenv("KCMA_JACOBI_PERSISTENT");
   if (e && atoi(e) == 0) return false;
-  const bool gram = !(e && atoi(e) == 2);   // KCMA_JACOBI_PERSISTENT=2 selects the shared-memory version 2c
-  if (gram) {
-    static int okg = -1;
-    if (okg < 0) {
-      int dev = 0, coop = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-      okg = coop;
-    }
-    if (okg && ld <= 8 * 16 * 10) {
-      cudaMemsetAsync(ready, 0, sizeof(unsigned) * nb, st);
-      static long long* dbg = nullptr;
-      if (getenv("KCMA_JACOBI_DEBUG") && !dbg) { cudaMalloc(&dbg, sizeof(long long) * 8 * 32); cudaMemset(dbg, 0, sizeof(long long) * 8 * 32); g_jacobi_dbg = dbg; }
-      void* gargs[] = {&GT, &VT, &ld, &n, &nb, &tol, &max_sweeps, &sc, &ready, &dbg};
-      if (cudaLaunchCooperativeKernel((void*)jacobi_gram_kernel<512>, dim3(nb / 2), dim3(512), gargs, 0, st) == cudaSuccess) return true;
-      cudaGetLastError();
-    }
-  }
-  static int ok = -1;
-  if (ok < 0) {
-    int dev = 0, coop = 0;
+  static int coop = -1;
+  if (coop < 0) {
+    int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-    ok = coop && cudaFuncSetAttribute(jacobi_persistent_kernel<4, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem) == cudaSuccess;
   }
-  if (!ok) return false;
-  size_t smem = sizeof(double) * 4 * (size_t)br * ld;
+  if (!coop) return false;
   cudaMemsetAsync(ready, 0, sizeof(unsigned) * nb, st);
-  void* args[] = {&GT, &VT, &ld, &n, &nb, &tol, &max_sweeps, &sc, &ready};
-  return cudaLaunchCooperativeKernel((void*)jacobi_persistent_kernel<4, 512>, dim3(nb / 2), dim3(512), args, smem, st) == cudaSuccess;
+  static long long* dbg = nullptr;
+  if (getenv("KCMA_JACOBI_DEBUG") && !dbg) {
+    cudaMalloc(&dbg, sizeof(long long) * 8 * 32);
+    cudaMemset(dbg, 0, sizeof(long long) * 8 * 32);
+    g_jacobi_dbg = dbg;
+  }
+  void* args[] = {&GT, &VT, &ld, &n, &nb, &tol, &max_sweeps, &sc, &ready, &dbg};
+  if (cudaLaunchCooperativeKernel((void*)jacobi_gram_kernel<512>, dim3(nb / 2), dim3(512), args, 0, st) == cudaSuccess) return true;
+  cudaGetLastError();
+  return false;
 }
 
+// One sweep as nb-1 launches (N too large for the persistent kernel); the host checks sc->jacobi_max_rel_bits between sweeps.
 void launch_jacobi_block_sweep(cudaStream_t st, double* GT, double* VT, int ld, int n, double tol, DevScalars* sc, int* launches) {
-  {
-    const char* e = getenv("KCMA_JACOBI_GRAM");
-    if (!(e && atoi(e) == 0)) {   // Gram-update steps, one launch per step (N too large for the persistent kernel)
-      int nb4 = (n + 3) / 4;
-      nb4 = (nb4 + 1) & ~1;
-      reset_rotations_kernel<<<1, 1, 0, st>>>(sc);
-      for (int step = 0; step < nb4 - 1; step++) jacobi_gram_step_kernel<512><<<nb4 / 2, 512, 0, st>>>(GT, VT, ld, n, nb4, step, tol, sc);
-      if (launches) *launches += nb4;
-      return;
-    }
-  }
-  const int br = jacobi_block_rows(ld);
-  if (br == 0) { launch_jacobi_sweep(st, GT, VT, ld, n, tol, sc, launches); return; }
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(jacobi_block_kernel<4, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
-    cudaFuncSetAttribute(jacobi_block_kernel<4, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
-    cudaFuncSetAttribute(jacobi_block_kernel<4, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
-    cudaFuncSetAttribute(jacobi_block_kernel<2, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
-    const char* e = getenv("KCMA_JACOBI_THREADS");
-    if (e) g_jacobi_threads = atoi(e);
-    attr = true;
-  }
-  int nb = (n + br - 1) / br;
-  nb = (nb + 1) & ~1;
-  const size_t smem = sizeof(double) * 4 * (size_t)br * ld;
+  const int nb = ((n + 3) / 4 + 1) & ~1;
   reset_rotations_kernel<<<1, 1, 0, st>>>(sc);
-  for (int step = 0; step < nb - 1; step++) {
-    if (br == 4 && g_jacobi_threads == 1024) jacobi_block_kernel<4, 1024><<<nb / 2, 1024, smem, st>>>(GT, VT, ld, n, nb, step, step == 0, tol, sc);
-    else if (br == 4 && g_jacobi_threads == 256) jacobi_block_kernel<4, 256><<<nb / 2, 256, smem, st>>>(GT, VT, ld, n, nb, step, step == 0, tol, sc);
-    else if (br == 4) jacobi_block_kernel<4, 512><<<nb / 2, 512, smem, st>>>(GT, VT, ld, n, nb, step, step == 0, tol, sc);
-    else jacobi_block_kernel<2, 512><<<nb / 2, 512, smem, st>>>(GT, VT, ld, n, nb, step, step == 0, tol, sc);
-  }
+  for (int step = 0; step < nb - 1; step++) jacobi_gram_step_kernel<512><<<nb / 2, 512, 0, st>>>(GT, VT, ld, n, nb, step, tol, sc);
   if (launches) *launches += nb;
 }
 

@@ -74,7 +74,6 @@ void launch_viability_boundaries(cudaStream_t st, const double* G, long long ldg
 
 // eigen.cu
 void launch_set_identity(cudaStream_t st, double* M, int ld, int n);
-void launch_jacobi_sweep(cudaStream_t st, double* GT, double* VT, int ld, int n, double tol, DevScalars* sc, int* launches);
 bool eigen_small_fits(int n);
 void launch_eigen_small(cudaStream_t st, const double* C, int ld, int n, double* VT, double* GT, double* B, double* A, double* D,
                         double tol, int max_sweeps, DevScalars* sc);
