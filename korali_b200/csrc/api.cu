@@ -1324,9 +1324,9 @@ int kcma_set_scalar(kcma_t* h, const char* key, double v) {
 
 // ---- measurement ------------------------------------------------------------------------------------------
 // debug hook (not part of include/kcma.h): phase timestamps of the Gram Jacobi kernel, 32 steps x 8 slots
-extern "C" int kcma_debug_jacobi_timestamps(long long* out256) {
+extern "C" int kcma_debug_jacobi_timestamps(long long* out3584) {
   if (!kc::g_jacobi_dbg) return 1;
-  return cudaMemcpy(out256, kc::g_jacobi_dbg, sizeof(long long) * 256, cudaMemcpyDeviceToHost) != cudaSuccess;
+  return cudaMemcpy(out3584, kc::g_jacobi_dbg, sizeof(long long) * 3584, cudaMemcpyDeviceToHost) != cudaSuccess;
 }
 int kcma_timing_enable(kcma_t* h, int on) { h->timing = on != 0; return 0; }
 int kcma_timing_get(kcma_t* h, const char* phase, double* ms, uint64_t* calls) {

@@ -12,6 +12,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "jacobi_inner.cuh"
 #include "kernels.h"
 
 namespace cg = cooperative_groups;
@@ -233,6 +234,246 @@ jacobi_gram_kernel(double* GT, double* VT, int ld, int n, int nb, double tol, in
     if (total == 0 || __longlong_as_double((long long)mb) < 1e-20) break;
   }
 #undef KCMA_TS
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Version 4: the same Gram-update step, WARP-SPECIALISED around what the phase timestamps of version 3 showed
+// (profiles/microbench/jacobi_phases.py; 18-20k cycles per step): 40 % of a step were the 4 rotation rounds on Gamma in
+// shared memory (LDS/STS round trips queue behind the step's own global loads in the MIO pipe), 30 % the loads (G fetched
+// twice, in the Gram and in the apply layout, plus V), 20 % apply + stores of G AND V, 10 % the flag handshake. Here:
+//   * G group (warps 0..NWG-1) runs the critical path: flag -> G load (once: Gram fragments straight from the registers,
+//     staged to shared memory for the apply layout) -> Gram (DMMA) -> rotations on Gamma held in REGISTERS by warp 0
+//     (jacobi_inner.cuh) -> apply G (DMMA) -> store -> flag;
+//   * V group (the last NWV warps, none on warp 0's scheduler) applies the same R to the V rows behind it, decoupled:
+//     R travels through a small ring in shared memory, V blocks have their own ready flags, nothing on the G path waits for V.
+// ------------------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(NT, 1)
+jacobi_pipe_kernel(double* GT, double* VT, int ld, int n, int nb, double tol, int max_sweeps, DevScalars* sc, unsigned* readyG,
+                   unsigned* readyV, long long* dbg /* nullable: phase timestamps (profiles/microbench/jacobi_phases.py) */, int dbg_sweep, int dbg_step0) {
+  cg::grid_group grid = cg::this_grid();
+#define KCMA_TS(slot) do { if (dbg && blockIdx.x == 1 && tid == 0 && sweep == dbg_sweep && step >= dbg_step0 && step < dbg_step0 + 32) dbg[(step - dbg_step0) * 16 + (slot)] = clock64(); } while (0)
+#define KCMA_TSV(slot) do { if (dbg && blockIdx.x == 1 && tid == NWG * 32 && sweep == dbg_sweep && step >= dbg_step0 && step < dbg_step0 + 32) dbg[(step - dbg_step0) * 16 + (slot)] = clock64(); } while (0)
+  constexpr int NW = NT / 32;                       // 8: warp 0 | data warps 1..4 | V warps 5..7
+  constexpr int NWV = 3;                            // V warps on schedulers 1, 2, 3 (none shares the FP64 pipe of warp 0)
+  constexpr int NWG = NW - NWV;                     // G group: warp 0 (flags, rotations) + NWD data warps
+  constexpr int NWD = NWG - 1;                      // 4 data warps, one per scheduler: the DMMA pipe (one 8x8x4 per 16 cycles
+                                                    // per scheduler) is saturated by one warp with two accumulator chains
+  static_assert(NWD == 4, "partial tiles are read back as two double2 per entry");
+  constexpr int BG = 32;                            // 8-column groups per data warp and batch (loads in flight: BG x 512 B per warp)
+  constexpr int RING = 4;
+  extern __shared__ double dyn_smem[];
+  const int S = ld + 8;                             // row stride = 8 mod 16 doubles: STS.128 / LDS.64 fragments conflict-free
+  double* Gs = dyn_smem;                            // [8][S] rows of G of this step
+  double* Vs = dyn_smem + 8 * S;                    // [8][S] rows of V of the step the V group works on
+  __shared__ double2 part[64][NWD / 2];             // partial Gram tiles, entry-major: one shared-memory round trip for warp 0
+  __shared__ double Rring[RING][64];                // rows_new = R rows_old, one entry per step in flight
+  __shared__ int rot_ring[RING];
+  __shared__ volatile unsigned g_head, v_tail;      // steps whose R is posted / whose V rows are done
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int ngroups = ld >> 3;
+  const double tol2 = tol * tol;
+  unsigned epoch = 0;                               // steps completed by this group of this CTA
+  if (tid == 0) { g_head = 0; v_tail = 0; }
+  __syncthreads();
+
+  for (int sweep = 0; sweep < max_sweeps; sweep++) {
+    if (blockIdx.x == 0 && tid == 0) { sc->jacobi_rotations = 0; sc->jacobi_max_rel_bits = 0ull; sc->jacobi_sweeps = sweep + 1; }
+    int sweep_rot = 0, sweep_big = 0;
+    grid.sync();
+    if (warp < NWG) {
+      // =========================== G group: the critical path ===========================
+      for (int step = 0; step < nb - 1; step++) {
+        int I, J;
+        rr_pair(nb, step, blockIdx.x, I, J);
+        const int slot = epoch & (RING - 1);
+        KCMA_TS(0);
+        if (dbg && blockIdx.x == 1 && tid == 0 && sweep == dbg_sweep && step < 1024) dbg[512 + step] = clock64();
+        if (warp == 0) {   // lanes 0 and 1 each watch one flag (acquire loads: no fence, no serialised round trips)
+          if (lane < 2) {
+            const unsigned* f = readyG + (lane == 0 ? I : J);
+            unsigned v;
+            do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory"); } while (v < epoch);
+          }
+          __syncwarp();
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(NWG * 32));
+        KCMA_TS(1);
+        const int rowg = (g < 4 ? I * 4 + g : J * 4 + (g - 4));
+        const bool rvalid = rowg < n;
+        if (warp != 0) {
+          // ---- Gram: lane (g,t) feeds x = G[row g][8 grp + 2t (+1)] as both A and B fragment; the same registers are staged ----
+          const int dw = warp - 1;
+          const double* grow = GT + (size_t)rowg * ld;
+          double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+          for (int kb = 0; dw + kb * NWD < ngroups; kb += BG) {
+            double2 xs[BG];   // all loads of the batch in flight before its first DMMA
+#pragma unroll
+            for (int k = 0; k < BG; k++) {
+              const int grp = dw + (kb + k) * NWD;
+              xs[k] = make_double2(0.0, 0.0);
+              if (rvalid && grp < ngroups) xs[k] = __ldcg(reinterpret_cast<const double2*>(grow + 8 * grp + 2 * t));
+            }
+#pragma unroll
+            for (int k = 0; k < BG; k++) {   // two independent accumulator chains
+              const int grp = dw + (kb + k) * NWD;
+              if (grp < ngroups) *reinterpret_cast<double2*>(Gs + g * S + 8 * grp + 2 * t) = xs[k];
+              dmma884(c0, c1, xs[k].x, xs[k].x);
+              dmma884(c2, c3, xs[k].y, xs[k].y);
+            }
+          }
+          double* pw = reinterpret_cast<double*>(&part[0][0]) + dw;   // part[e][dw]
+          pw[(g * 8 + 2 * t) * NWD] = c0 + c2;
+          pw[(g * 8 + 2 * t + 1) * NWD] = c1 + c3;
+        }
+        KCMA_TS(2);
+        asm volatile("bar.sync 1, %0;" ::"n"(NWG * 32));
+        KCMA_TS(3);
+        // ---- warp 0: sum the partial tiles into registers, then the step's rotations on Gamma ----
+        if (warp == 0) {
+          Inner8 m;
+#pragma unroll
+          for (int a = 0; a < 8; a++) {
+#pragma unroll
+            for (int b = a; b < 8; b++) {
+              const double2 p0 = part[a * 8 + b][0], p1 = part[a * 8 + b][1];
+              m.g[a][b] = (p0.x + p0.y) + (p1.x + p1.y);
+            }
+          }
+#pragma unroll
+          for (int a = 0; a < 8; a++) m.rc[a] = (a == (lane & 7)) ? 1.0 : 0.0;
+          m.rotations = 0; m.big = 0;
+          KCMA_TS(14);
+          if (step == 0) inner_full(m, tol2); else inner_cross(m, tol2);
+          KCMA_TS(8);
+          while (epoch - v_tail >= RING) { }        // ring slot still in use by the V group (it lags by < RING steps)
+          if (lane < 8) {
+#pragma unroll
+            for (int a = 0; a < 8; a++) Rring[slot][a * 8 + lane] = m.rc[a];
+          }
+          if (lane == 0) { rot_ring[slot] = m.rotations; sweep_rot += m.rotations; sweep_big |= m.big; }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(NWG * 32));
+        KCMA_TS(4);
+        // ---- rows of G <- R rows (skipped when nothing rotated) ----
+        const int rot = rot_ring[slot];
+        if (rot != 0 && warp != 0) {
+          const int dw = warp - 1;
+          const double a_lo = Rring[slot][g * 8 + t], a_hi = Rring[slot][g * 8 + 4 + t];
+          double* gout = GT + (size_t)rowg * ld;
+          for (int g0 = dw; g0 < ngroups; g0 += NWD * 16) {   // 16 groups (32 operand loads) in flight per warp
+            double b0[16], b1[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+              const int grp = g0 + k * NWD;
+              const int col = 8 * grp + g;
+              b0[k] = grp < ngroups ? Gs[t * S + col] : 0.0;
+              b1[k] = grp < ngroups ? Gs[(4 + t) * S + col] : 0.0;
+            }
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+              const int grp = g0 + k * NWD;
+              double d0 = 0.0, d1 = 0.0;
+              dmma884(d0, d1, a_lo, b0[k]);
+              dmma884(d0, d1, a_hi, b1[k]);
+              if (grp < ngroups && rvalid) __stcg(reinterpret_cast<double2*>(gout + 8 * grp + 2 * t), make_double2(d0, d1));
+            }
+          }
+        }
+        KCMA_TS(5);
+        asm volatile("bar.sync 1, %0;" ::"n"(NWG * 32));
+        if (tid == 0) {
+          __threadfence();                          // gpu scope: the G rows; also orders Rring before g_head for the V group
+          volatile unsigned* rg = readyG;
+          rg[I] = epoch + 1; rg[J] = epoch + 1;
+          g_head = epoch + 1;
+        }
+        KCMA_TS(6);
+        epoch++;
+      }
+    } else {
+      // =========================== V group: rows of V <- R rows, behind the G group ===========================
+      const int vtid = tid - NWG * 32, vw = warp - NWG;
+      for (int step = 0; step < nb - 1; step++) {
+        int I, J;
+        rr_pair(nb, step, blockIdx.x, I, J);
+        const int slot = epoch & (RING - 1);
+        KCMA_TSV(9);
+        if (dbg && blockIdx.x == 1 && tid == NWG * 32 && sweep == dbg_sweep && step < 1024) dbg[512 + 1024 + step] = clock64();
+        if (vtid == 0) {
+          while (g_head <= epoch) { }
+          __threadfence_block();
+        }
+        asm volatile("bar.sync 2, %0;" ::"n"(NWV * 32));
+        KCMA_TSV(10);
+        const int rot = rot_ring[slot];
+        if (vtid < 2) {                             // the previous owners are done with these V blocks (also when nothing rotates here:
+          const unsigned* f = readyV + (vtid == 0 ? I : J);   // publishing them early would let the next owner overtake a pending update)
+          unsigned v;
+          do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory"); } while (v < epoch);
+        }
+        __syncwarp();
+        if (rot != 0) {
+          asm volatile("bar.sync 2, %0;" ::"n"(NWV * 32));
+          const int chunks = ld >> 1;   // 16-byte chunks per row
+#pragma unroll
+          for (int r = 0; r < 8; r++) {
+            const int row = (r < 4 ? I * 4 + r : J * 4 + (r - 4));
+            const bool ok = row < n;
+            const double* src = VT + (ok ? (size_t)row * ld : 0);
+            for (int c = vtid; c < chunks; c += NWV * 32) cp_async16(Vs + r * S + 2 * c, src + (ok ? 2 * c : 0), ok ? 16 : 0);
+          }
+          cp_async_commit();
+          KCMA_TSV(11);
+          const int prow = (g < 4 ? I * 4 + g : J * 4 + (g - 4));
+          const double a_lo = Rring[slot][g * 8 + t], a_hi = Rring[slot][g * 8 + 4 + t];
+          double* vout = VT + (size_t)prow * ld;
+          cp_async_wait<0>();
+          asm volatile("bar.sync 2, %0;" ::"n"(NWV * 32));
+          KCMA_TSV(12);
+          for (int g0 = vw; g0 < ngroups; g0 += NWV * 8) {   // 8 groups (16 operand loads) in flight per warp
+            double b0[8], b1[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+              const int grp = g0 + k * NWV;
+              const int col = 8 * grp + g;
+              b0[k] = grp < ngroups ? Vs[t * S + col] : 0.0;
+              b1[k] = grp < ngroups ? Vs[(4 + t) * S + col] : 0.0;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+              const int grp = g0 + k * NWV;
+              double e0 = 0.0, e1 = 0.0;
+              dmma884(e0, e1, a_lo, b0[k]);
+              dmma884(e0, e1, a_hi, b1[k]);
+              if (grp < ngroups && prow < n) __stcg(reinterpret_cast<double2*>(vout + 8 * grp + 2 * t), make_double2(e0, e1));
+            }
+          }
+        }
+        KCMA_TSV(13);
+        asm volatile("bar.sync 2, %0;" ::"n"(NWV * 32));
+        if (vtid == 0) {
+          if (rot != 0) __threadfence();
+          volatile unsigned* rv = readyV;
+          rv[I] = epoch + 1; rv[J] = epoch + 1;
+          v_tail = epoch + 1;
+        }
+        KCMA_TSV(15);
+        epoch++;
+      }
+    }
+    if (tid == 0 && sweep_rot) {
+      atomicAdd(&sc->jacobi_rotations, sweep_rot);
+      if (sweep_big) atomicMax(&sc->jacobi_max_rel_bits, 0x3ff0000000000000ull);   // "max cos^2" collapsed to {0, 1.0}
+    }
+    grid.sync();
+    const int total = *reinterpret_cast<volatile int*>(&sc->jacobi_rotations);
+    const unsigned long long mb = *reinterpret_cast<volatile unsigned long long*>(&sc->jacobi_max_rel_bits);
+    grid.sync();
+    if (total == 0 || __longlong_as_double((long long)mb) < 1e-20) break;
+  }
+#undef KCMA_TS
+#undef KCMA_TSV
 }
 
 // Version 3, one step per launch (N too large for one co-resident CTA per block pair, e.g. N = 4096: 512 pairs).
@@ -610,13 +851,27 @@ bool launch_jacobi_persistent(cudaStream_t st, double* GT, double* VT, int ld, i
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
   }
   if (!coop) return false;
-  cudaMemsetAsync(ready, 0, sizeof(unsigned) * nb, st);
   static long long* dbg = nullptr;
   if (getenv("KCMA_JACOBI_DEBUG") && !dbg) {
-    cudaMalloc(&dbg, sizeof(long long) * 8 * 32);
-    cudaMemset(dbg, 0, sizeof(long long) * 8 * 32);
+    cudaMalloc(&dbg, sizeof(long long) * (2560 + 1024));
+    cudaMemset(dbg, 0, sizeof(long long) * (2560 + 1024));
     g_jacobi_dbg = dbg;
   }
+  const char* pe = getenv("KCMA_JACOBI_PIPE");
+  if (!(pe && atoi(pe) == 0)) {   // version 4 (default); KCMA_JACOBI_PIPE=0 selects version 3
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(jacobi_pipe_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem - 16 * 1024); attr = true; }
+    const size_t smem = sizeof(double) * 16 * (size_t)(ld + 8);
+    cudaMemsetAsync(ready, 0, sizeof(unsigned) * 2 * nb, st);
+    unsigned* ready_v = ready + nb;
+    int dbg_sweep = getenv("KCMA_JACOBI_DEBUG") ? atoi(getenv("KCMA_JACOBI_DEBUG")) : -1;
+    int dbg_step0 = getenv("KCMA_JACOBI_DEBUG_STEP0") ? atoi(getenv("KCMA_JACOBI_DEBUG_STEP0")) : 8;
+    void* pargs[] = {&GT, &VT, &ld, &n, &nb, &tol, &max_sweeps, &sc, &ready, &ready_v, &dbg, &dbg_sweep, &dbg_step0};
+    if (cudaLaunchCooperativeKernel((void*)jacobi_pipe_kernel<256>, dim3(nb / 2), dim3(256), pargs, smem, st) == cudaSuccess) return true;
+    cudaGetLastError();
+    return false;
+  }
+  cudaMemsetAsync(ready, 0, sizeof(unsigned) * nb, st);
   void* args[] = {&GT, &VT, &ld, &n, &nb, &tol, &max_sweeps, &sc, &ready, &dbg};
   if (cudaLaunchCooperativeKernel((void*)jacobi_gram_kernel<512>, dim3(nb / 2), dim3(512), args, 0, st) == cudaSuccess) return true;
   cudaGetLastError();
