@@ -236,6 +236,18 @@ jacobi_gram_kernel(double* GT, double* VT, int ld, int n, int nb, double tol, in
 #undef KCMA_TS
 }
 
+// 256-bit global accesses (SASS LDG.E.ENL2.256 / STG.E.ENL2.256, sm_100+): a lane moves 4 consecutive doubles, so the four
+// t-lanes of a row cover one full 128-byte line per request instead of half of it (the LSU wavefront count per byte halves).
+struct double4x { double a, b, c, d; };
+__device__ __forceinline__ double4x ldcg_256(const double* p) {
+  double4x v;
+  asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.a), "=d"(v.b), "=d"(v.c), "=d"(v.d) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stcg_256(double* p, double a, double b, double c, double d) {
+  asm volatile("st.global.cg.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------------
 // Version 4: the same Gram-update step, WARP-SPECIALISED around what the phase timestamps of version 3 showed
 // (profiles/microbench/jacobi_phases.py; 18-20k cycles per step): 40 % of a step were the 4 rotation rounds on Gamma in
@@ -260,10 +272,13 @@ jacobi_pipe_kernel(double* GT, double* VT, int ld, int n, int nb, double tol, in
   constexpr int NWD = NWG - 1;                      // 4 data warps, one per scheduler: the DMMA pipe (one 8x8x4 per 16 cycles
                                                     // per scheduler) is saturated by one warp with two accumulator chains
   static_assert(NWD == 4, "partial tiles are read back as two double2 per entry");
-  constexpr int BG = 32;                            // 8-column groups per data warp and batch (loads in flight: BG x 512 B per warp)
+  constexpr int BG = 16;                            // 16-column spans per data warp and batch (loads in flight: BG x 1 KB per warp)
   constexpr int RING = 4;
-  extern __shared__ double dyn_smem[];
-  const int S = ld + 8;                             // row stride = 8 mod 16 doubles: STS.128 / LDS.64 fragments conflict-free
+  extern __shared__ __align__(16) double dyn_smem[];
+  // Columns are handled in SPANS of 16 (one 128-byte line per row): lane (g,t) owns columns 4t..4t+3 of the span in row g.
+  // The Gram sum does not care which column sits in which k-slot; for the apply, N-tile A takes columns 4q + {0,1} and
+  // N-tile B columns 4q + {2,3} (q = 0..3), so that a lane's two D fragments are again 4 consecutive doubles.
+  const int S = ld + 2;                             // row stride = 2 mod 16 doubles: STS.128 / LDS.64 fragments conflict-free
   double* Gs = dyn_smem;                            // [8][S] rows of G of this step
   double* Vs = dyn_smem + 8 * S;                    // [8][S] rows of V of the step the V group works on
   __shared__ double2 part[64][NWD / 2];             // partial Gram tiles, entry-major: one shared-memory round trip for warp 0
@@ -271,7 +286,7 @@ jacobi_pipe_kernel(double* GT, double* VT, int ld, int n, int nb, double tol, in
   __shared__ int rot_ring[RING];
   __shared__ volatile unsigned g_head, v_tail;      // steps whose R is posted / whose V rows are done
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int ngroups = ld >> 3;
+  const int nspans = ld >> 4;
   const double tol2 = tol * tol;
   unsigned epoch = 0;                               // steps completed by this group of this CTA
   if (tid == 0) { g_head = 0; v_tail = 0; }
@@ -306,20 +321,26 @@ jacobi_pipe_kernel(double* GT, double* VT, int ld, int n, int nb, double tol, in
           const int dw = warp - 1;
           const double* grow = GT + (size_t)rowg * ld;
           double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
-          for (int kb = 0; dw + kb * NWD < ngroups; kb += BG) {
-            double2 xs[BG];   // all loads of the batch in flight before its first DMMA
+          for (int kb = 0; dw + kb * NWD < nspans; kb += BG) {
+            double4x xs[BG];   // all loads of the batch in flight before its first DMMA
 #pragma unroll
             for (int k = 0; k < BG; k++) {
-              const int grp = dw + (kb + k) * NWD;
-              xs[k] = make_double2(0.0, 0.0);
-              if (rvalid && grp < ngroups) xs[k] = __ldcg(reinterpret_cast<const double2*>(grow + 8 * grp + 2 * t));
+              const int h = dw + (kb + k) * NWD;
+              xs[k].a = xs[k].b = xs[k].c = xs[k].d = 0.0;
+              if (rvalid && h < nspans) xs[k] = ldcg_256(grow + 16 * h + 4 * t);
             }
 #pragma unroll
             for (int k = 0; k < BG; k++) {   // two independent accumulator chains
-              const int grp = dw + (kb + k) * NWD;
-              if (grp < ngroups) *reinterpret_cast<double2*>(Gs + g * S + 8 * grp + 2 * t) = xs[k];
-              dmma884(c0, c1, xs[k].x, xs[k].x);
-              dmma884(c2, c3, xs[k].y, xs[k].y);
+              const int h = dw + (kb + k) * NWD;
+              if (h < nspans) {
+                double* dst = Gs + g * S + 16 * h + 4 * t;
+                *reinterpret_cast<double2*>(dst) = make_double2(xs[k].a, xs[k].b);
+                *reinterpret_cast<double2*>(dst + 2) = make_double2(xs[k].c, xs[k].d);
+              }
+              dmma884(c0, c1, xs[k].a, xs[k].a);
+              dmma884(c2, c3, xs[k].b, xs[k].b);
+              dmma884(c0, c1, xs[k].c, xs[k].c);
+              dmma884(c2, c3, xs[k].d, xs[k].d);
             }
           }
           double* pw = reinterpret_cast<double*>(&part[0][0]) + dw;   // part[e][dw]
@@ -361,22 +382,24 @@ jacobi_pipe_kernel(double* GT, double* VT, int ld, int n, int nb, double tol, in
           const int dw = warp - 1;
           const double a_lo = Rring[slot][g * 8 + t], a_hi = Rring[slot][g * 8 + 4 + t];
           double* gout = GT + (size_t)rowg * ld;
-          for (int g0 = dw; g0 < ngroups; g0 += NWD * 16) {   // 16 groups (32 operand loads) in flight per warp
-            double b0[16], b1[16];
+          const int cA = 4 * (g >> 1) + (g & 1);              // column of N-index g inside the span, tile A (tile B: + 2)
+          for (int h0 = dw; h0 < nspans; h0 += NWD * 8) {     // 8 spans (32 operand loads) in flight per warp
+            double bA0[8], bA1[8], bB0[8], bB1[8];
 #pragma unroll
-            for (int k = 0; k < 16; k++) {
-              const int grp = g0 + k * NWD;
-              const int col = 8 * grp + g;
-              b0[k] = grp < ngroups ? Gs[t * S + col] : 0.0;
-              b1[k] = grp < ngroups ? Gs[(4 + t) * S + col] : 0.0;
+            for (int k = 0; k < 8; k++) {
+              const int h = h0 + k * NWD;
+              const double* src = Gs + t * S + 16 * h + cA;
+              const bool ok = h < nspans;
+              bA0[k] = ok ? src[0] : 0.0;         bB0[k] = ok ? src[2] : 0.0;
+              bA1[k] = ok ? src[4 * S] : 0.0;     bB1[k] = ok ? src[4 * S + 2] : 0.0;
             }
 #pragma unroll
-            for (int k = 0; k < 16; k++) {
-              const int grp = g0 + k * NWD;
-              double d0 = 0.0, d1 = 0.0;
-              dmma884(d0, d1, a_lo, b0[k]);
-              dmma884(d0, d1, a_hi, b1[k]);
-              if (grp < ngroups && rvalid) __stcg(reinterpret_cast<double2*>(gout + 8 * grp + 2 * t), make_double2(d0, d1));
+            for (int k = 0; k < 8; k++) {
+              const int h = h0 + k * NWD;
+              double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0;
+              dmma884(d0, d1, a_lo, bA0[k]); dmma884(e0, e1, a_lo, bB0[k]);
+              dmma884(d0, d1, a_hi, bA1[k]); dmma884(e0, e1, a_hi, bB1[k]);
+              if (h < nspans && rvalid) stcg_256(gout + 16 * h + 4 * t, d0, d1, e0, e1);
             }
           }
         }
@@ -431,22 +454,24 @@ jacobi_pipe_kernel(double* GT, double* VT, int ld, int n, int nb, double tol, in
           cp_async_wait<0>();
           asm volatile("bar.sync 2, %0;" ::"n"(NWV * 32));
           KCMA_TSV(12);
-          for (int g0 = vw; g0 < ngroups; g0 += NWV * 8) {   // 8 groups (16 operand loads) in flight per warp
-            double b0[8], b1[8];
+          const int cA = 4 * (g >> 1) + (g & 1);
+          for (int h0 = vw; h0 < nspans; h0 += NWV * 8) {     // 8 spans (32 operand loads) in flight per warp
+            double bA0[8], bA1[8], bB0[8], bB1[8];
 #pragma unroll
             for (int k = 0; k < 8; k++) {
-              const int grp = g0 + k * NWV;
-              const int col = 8 * grp + g;
-              b0[k] = grp < ngroups ? Vs[t * S + col] : 0.0;
-              b1[k] = grp < ngroups ? Vs[(4 + t) * S + col] : 0.0;
+              const int h = h0 + k * NWV;
+              const double* src = Vs + t * S + 16 * h + cA;
+              const bool ok = h < nspans;
+              bA0[k] = ok ? src[0] : 0.0;         bB0[k] = ok ? src[2] : 0.0;
+              bA1[k] = ok ? src[4 * S] : 0.0;     bB1[k] = ok ? src[4 * S + 2] : 0.0;
             }
 #pragma unroll
             for (int k = 0; k < 8; k++) {
-              const int grp = g0 + k * NWV;
-              double e0 = 0.0, e1 = 0.0;
-              dmma884(e0, e1, a_lo, b0[k]);
-              dmma884(e0, e1, a_hi, b1[k]);
-              if (grp < ngroups && prow < n) __stcg(reinterpret_cast<double2*>(vout + 8 * grp + 2 * t), make_double2(e0, e1));
+              const int h = h0 + k * NWV;
+              double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0;
+              dmma884(d0, d1, a_lo, bA0[k]); dmma884(e0, e1, a_lo, bB0[k]);
+              dmma884(d0, d1, a_hi, bA1[k]); dmma884(e0, e1, a_hi, bB1[k]);
+              if (h < nspans && prow < n) stcg_256(vout + 16 * h + 4 * t, d0, d1, e0, e1);
             }
           }
         }
@@ -861,7 +886,7 @@ bool launch_jacobi_persistent(cudaStream_t st, double* GT, double* VT, int ld, i
   if (!(pe && atoi(pe) == 0)) {   // version 4 (default); KCMA_JACOBI_PIPE=0 selects version 3
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(jacobi_pipe_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem - 16 * 1024); attr = true; }
-    const size_t smem = sizeof(double) * 16 * (size_t)(ld + 8);
+    const size_t smem = sizeof(double) * 16 * (size_t)(ld + 2);
     cudaMemsetAsync(ready, 0, sizeof(unsigned) * 2 * nb, st);
     unsigned* ready_v = ready + nb;
     int dbg_sweep = getenv("KCMA_JACOBI_DEBUG") ? atoi(getenv("KCMA_JACOBI_DEBUG")) : -1;
