@@ -6,8 +6,8 @@
 // ~c1+cmu per generation), form G = C V0 with the FP64 tensor-core GEMM and orthogonalise the columns of G by plane
 // rotations accumulated into V. At convergence C V = G has orthogonal columns: V holds the eigenvectors and
 // lambda_i = v_i . g_i (Rayleigh quotient, signed). Vectors are stored as ROWS (VT, GT) so rotations touch contiguous memory.
-// Kernels: eigen_small_kernel (tiny N, everything in one launch), jacobi_gram_kernel (persistent cooperative, Gram-update
-// steps on the DMMA pipe), jacobi_gram_step_kernel (the same step, one launch each, for large N). DESIGN.md section 6.
+// Kernels: eigen_small_kernel (tiny N, everything in one launch), jacobi_pipe_kernel (persistent cooperative, warp-specialised
+// Gram-update steps on the DMMA pipe), jacobi_gram_step_kernel (the same step, one launch each, for large N). DESIGN.md section 6.
 #include <cooperative_groups.h>
 #include <stdlib.h>
 
@@ -22,32 +22,6 @@ namespace kc {
 __global__ void reset_rotations_kernel(DevScalars* sc) { sc->jacobi_rotations = 0; sc->jacobi_max_rel_bits = 0ull; }
 
 
-// Rotation that orthogonalises two rows with |g_p|^2 = alpha, |g_q|^2 = beta, g_p.g_q = gamma (gamma != 0):
-//   t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)),  zeta = (beta - alpha) / (2 gamma)   =   +-2|gamma| / (|d| + sqrt(d^2 + 4 gamma^2))
-// This scalar chain sits on the critical path of every Jacobi round (N-1 rounds per sweep), and FP64 sqrt / divide are
-// ~200-cycle software sequences. The ANGLE only needs a few digits (an error eps_t leaves a residual eps_t*|gamma|, so
-// quadratic convergence is kept down to 1e-7 per sweep), but the rotation must be orthonormal to FP64 precision. So: the
-// ratio is evaluated in FP32 on exponent-normalised inputs, and c = 1/sqrt(1+t^2) is refined in FP64 by two Newton steps.
-__device__ __forceinline__ void jacobi_cs(double alpha, double beta, double gamma, double& c, double& s) {
-  const double d = beta - alpha;
-  const double ad = fabs(d), g2 = 2.0 * fabs(gamma);
-  const double m = fmax(ad, g2);
-  int ex = ((__double2hiint(m) >> 20) & 0x7ff) - 1023;              // m = 1.x * 2^ex
-  ex = max(-1000, min(1000, ex));
-  const double scale = __hiloint2double((1023 - ex) << 20, 0);     // 2^-ex, exact
-  const float fd = (float)(ad * scale), fg = (float)(g2 * scale);  // both in [0, 2), the larger one in [1, 2)
-  const float r = sqrtf(fmaf(fd, fd, fg * fg));
-  const float ft = __fdividef(fg, fd + r);                          // in (0, 1]
-  const bool pos = (d == 0.0) || ((d > 0.0) == (gamma > 0.0));
-  const double t = pos ? (double)ft : -(double)ft;
-  const double x = fma(t, t, 1.0);
-  double c0 = (double)rsqrtf((float)x);
-  c0 = c0 * fma(-0.5 * x, c0 * c0, 1.5);
-  c0 = c0 * fma(-0.5 * x, c0 * c0, 1.5);
-  c = c0;
-  s = c0 * t;
-}
-
 // Round-robin (chess tournament) schedule over np = even number of players; step in [0, np-1), k in [0, np/2).
 __device__ __forceinline__ void rr_pair(int np, int step, int k, int& p, int& q) {
   const int m = np - 1;
@@ -55,185 +29,6 @@ __device__ __forceinline__ void rr_pair(int np, int step, int k, int& p, int& q)
   if (k == 0) { a = m; b = step; }
   else { a = (step + k) % m; b = (step - k + m) % m; }
   p = min(a, b); q = max(a, b);
-}
-
-// ------------------------------------------------------------------------------------------------------
-// Version 3: GRAM-UPDATE one-sided Jacobi on the FP64 tensor pipe (persistent, cooperative).
-// ncu on version 2c: the blocked rounds are shared-memory-bandwidth bound — every rotation re-reads and re-writes its
-// four rows (80 KB per pair) and every round recomputes three N-long dot products. Here a CTA handling the block pair
-// (I, J) = 8 rows touches each row exactly twice per step:
-//   (i)   Gamma = G8 G8^T (8x8) in ONE pass over the 8 rows with DMMA.8x8x4, operands straight from L2 (fragment a == b);
-//   (ii)  the same sequence of plane rotations as before is carried out on Gamma alone (Gamma <- J Gamma J^T, exact
-//         algebra: the dot products of the rotated rows ARE the entries of the updated Gamma), accumulating R (8x8);
-//   (iii) rows <- R * rows for G and V as two DMMAs per 8 columns, written back once.
-// Steps are ordered by point-to-point ready flags (each block is produced by one CTA and consumed by one CTA).
-// ------------------------------------------------------------------------------------------------------
-template <int NT>
-__global__ void __launch_bounds__(NT, 1)
-jacobi_gram_kernel(double* GT, double* VT, int ld, int n, int nb, double tol, int max_sweeps, DevScalars* sc, unsigned* ready,
-                   long long* dbg /* nullable: phase timestamps of CTA 0, sweep 1 (profiles/microbench/jacobi_phases.py) */) {
-  cg::grid_group grid = cg::this_grid();
-#define KCMA_TS(slot) do { if (dbg && blockIdx.x == 1 && tid == 0 && sweep == 1 && step >= 8 && step < 40) dbg[(step - 8) * 8 + (slot)] = clock64(); } while (0)
-  constexpr int NW = NT / 32;
-  constexpr int MAXG = 10;                 // 8-column groups per warp: ld <= 8 * NW * MAXG
-  __shared__ double part[NW][64];          // per-warp partial Gram tiles
-  __shared__ double Gam[8][9];             // Gamma (padded)
-  __shared__ double Rm[8][9];              // accumulated rotation, rows_new = R rows_old
-  __shared__ int s_rot;
-  __shared__ unsigned long long s_max;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int ngroups = ld >> 3;
-  unsigned epoch = 0;
-
-  for (int sweep = 0; sweep < max_sweeps; sweep++) {
-    if (blockIdx.x == 0 && tid == 0) { sc->jacobi_rotations = 0; sc->jacobi_max_rel_bits = 0ull; sc->jacobi_sweeps = sweep + 1; }
-    int sweep_rot = 0;
-    unsigned long long sweep_max = 0ull;
-    grid.sync();
-    for (int step = 0; step < nb - 1; step++) {
-      int I, J;
-      rr_pair(nb, step, blockIdx.x, I, J);
-      KCMA_TS(0);
-      if (tid == 0) {
-        volatile unsigned* rv = ready;
-        while (rv[I] < epoch || rv[J] < epoch) { }
-        __threadfence();
-      }
-      KCMA_TS(1);
-      __syncthreads();
-      KCMA_TS(2);
-      // row g of the 8-row working set lives at global row rowg
-      const int rowg = (g < 4 ? I * 4 + g : J * 4 + (g - 4));
-      const bool rvalid = rowg < n;
-      const double* grow = GT + (size_t)rowg * ld;
-      // ---- (i) Gram: lane (g,t) feeds x = G[row g][8 grp + 2t (+1)] as both A and B fragment ----
-      double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
-      {
-        double2 xs[MAXG];   // all loads in flight before the first DMMA: one L2 round trip instead of one per group
-#pragma unroll
-        for (int k = 0; k < MAXG; k++) {
-          const int grp = warp + k * NW;
-          xs[k] = make_double2(0.0, 0.0);
-          if (rvalid && grp < ngroups) xs[k] = __ldcg(reinterpret_cast<const double2*>(grow + 8 * grp + 2 * t));
-        }
-#pragma unroll
-        for (int k = 0; k < MAXG; k++) {   // two independent accumulator chains
-          dmma884(c0, c1, xs[k].x, xs[k].x);
-          dmma884(c2, c3, xs[k].y, xs[k].y);
-        }
-      }
-      part[warp][g * 8 + 2 * t] = c0 + c2;
-      part[warp][g * 8 + 2 * t + 1] = c1 + c3;
-      // prefetch the B fragments of the apply phase (they do not depend on R): B[k = t | t+4][n = g] = row (t | t+4), col 8 grp + g
-      double bg0[MAXG], bg1[MAXG], bv0[MAXG], bv1[MAXG];
-      {
-        const int r0 = (t < 4 ? I * 4 + t : 0), r1 = J * 4 + t;   // rows t and 4+t of the working set (t in 0..3)
-        const bool v0 = r0 < n, v1 = r1 < n;
-#pragma unroll
-        for (int k = 0; k < MAXG; k++) {
-          const int grp = warp + k * NW;
-          bg0[k] = bg1[k] = bv0[k] = bv1[k] = 0.0;
-          if (grp < ngroups) {
-            const int col = 8 * grp + g;
-            if (v0) { bg0[k] = __ldcg(GT + (size_t)r0 * ld + col); bv0[k] = __ldcg(VT + (size_t)r0 * ld + col); }
-            if (v1) { bg1[k] = __ldcg(GT + (size_t)r1 * ld + col); bv1[k] = __ldcg(VT + (size_t)r1 * ld + col); }
-          }
-        }
-      }
-      if (tid == 0) { s_rot = 0; s_max = 0ull; }
-      KCMA_TS(3);
-      __syncthreads();
-      if (tid < 64) {
-        double a = 0.0;
-#pragma unroll
-        for (int w = 0; w < NW; w++) a += part[w][tid];
-        Gam[tid >> 3][tid & 7] = a;
-        Rm[tid >> 3][tid & 7] = ((tid >> 3) == (tid & 7)) ? 1.0 : 0.0;
-      }
-      __syncthreads();
-      KCMA_TS(4);
-      // ---- (ii) rotations on Gamma, warp 0. lane = (pair k = lane>>3, index j = lane&7) ----
-      if (warp == 0) {
-        const int k = lane >> 3, j = lane & 7;
-        const int rounds = (step == 0) ? 7 : 4;
-        int my_rot = 0, my_big = 0;
-        for (int r = 0; r < rounds; r++) {
-          int p, q;
-          if (step == 0) rr_pair(8, r, k, p, q);            // full sweep over the 8 rows (intra-block pairs included)
-          else { p = k; q = 4 + ((k + r) & 3); }            // cross pairs only
-          const double alpha = Gam[p][p], beta = Gam[q][q], gamma = Gam[p][q];
-          double c = 1.0, s = 0.0;
-          const bool rot = gamma * gamma > tol * tol * alpha * beta;
-          if (rot) {
-            jacobi_cs(alpha, beta, gamma, c, s);
-            my_rot++;
-            my_big |= (gamma * gamma > 1e-20 * alpha * beta) ? 1 : 0;   // cos^2 >= (1e-10)^2: not yet in the quadratic tail
-          }
-          __syncwarp();
-          {  // rows p, q of Gamma and of R
-            const double x = Gam[p][j], y = Gam[q][j];
-            const double u = Rm[p][j], v = Rm[q][j];
-            __syncwarp();
-            Gam[p][j] = c * x - s * y; Gam[q][j] = s * x + c * y;
-            Rm[p][j] = c * u - s * v; Rm[q][j] = s * u + c * v;
-          }
-          __syncwarp();
-          {  // columns p, q of Gamma
-            const double x = Gam[j][p], y = Gam[j][q];
-            __syncwarp();
-            Gam[j][p] = c * x - s * y; Gam[j][q] = s * x + c * y;
-          }
-          __syncwarp();
-        }
-        // lanes j == 0 of the four pair groups hold the counts
-        my_rot = (j == 0) ? my_rot : 0;
-        my_rot += __shfl_xor_sync(0xffffffffu, my_rot, 8); my_rot += __shfl_xor_sync(0xffffffffu, my_rot, 16);
-        my_big = __any_sync(0xffffffffu, my_big);
-        if (lane == 0) { s_rot = my_rot; s_max = my_big ? 0x3ff0000000000000ull : 0ull; }   // "max cos^2" collapsed to {0, 1.0}
-      }
-      __syncthreads();
-      KCMA_TS(5);
-      // ---- (iii) rows <- R rows (skipped when nothing rotated) ----
-      if (s_rot != 0) {
-        const double a_lo = Rm[g][t], a_hi = Rm[g][4 + t];
-        double* gout = GT + (size_t)rowg * ld;
-        double* vout = VT + (size_t)rowg * ld;
-#pragma unroll
-        for (int k = 0; k < MAXG; k++) {
-          const int grp = warp + k * NW;
-          if (grp < ngroups) {
-            double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0;
-            dmma884(d0, d1, a_lo, bg0[k]); dmma884(d0, d1, a_hi, bg1[k]);
-            dmma884(e0, e1, a_lo, bv0[k]); dmma884(e0, e1, a_hi, bv1[k]);
-            if (rvalid) {
-              __stcg(reinterpret_cast<double2*>(gout + 8 * grp + 2 * t), make_double2(d0, d1));
-              __stcg(reinterpret_cast<double2*>(vout + 8 * grp + 2 * t), make_double2(e0, e1));
-            }
-          }
-        }
-      }
-      epoch++;
-      KCMA_TS(6);
-      __syncthreads();
-      if (tid == 0) {
-        sweep_rot += s_rot; sweep_max = max(sweep_max, s_max);
-        __threadfence();
-        volatile unsigned* rv = ready;
-        rv[I] = epoch; rv[J] = epoch;
-      }
-      KCMA_TS(7);
-    }
-    if (tid == 0 && sweep_rot) {
-      atomicAdd(&sc->jacobi_rotations, sweep_rot);
-      atomicMax(&sc->jacobi_max_rel_bits, sweep_max);
-    }
-    grid.sync();
-    const int total = *reinterpret_cast<volatile int*>(&sc->jacobi_rotations);
-    const unsigned long long mb = *reinterpret_cast<volatile unsigned long long*>(&sc->jacobi_max_rel_bits);
-    grid.sync();
-    if (total == 0 || __longlong_as_double((long long)mb) < 1e-20) break;
-  }
-#undef KCMA_TS
 }
 
 // 256-bit global accesses (SASS LDG.E.ENL2.256 / STG.E.ENL2.256, sm_100+): a lane moves 4 consecutive doubles, so the four
@@ -249,7 +44,13 @@ __device__ __forceinline__ void stcg_256(double* p, double a, double b, double c
 }
 
 // ------------------------------------------------------------------------------------------------------
-// Version 4: the same Gram-update step, WARP-SPECIALISED around what the phase timestamps of version 3 showed
+// GRAM-UPDATE one-sided Jacobi, persistent + cooperative. A CTA owns the block pair (I, J) = 8 rows per step:
+//   (i)   Gamma = G8 G8^T (8x8) in ONE pass over the 8 rows with DMMA.8x8x4 (fragment a == b);
+//   (ii)  the step's plane rotations are carried out on Gamma alone (Gamma <- J Gamma J^T is exact algebra: the dot products
+//         of the rotated rows ARE the entries of the updated Gamma), accumulating R (8x8);
+//   (iii) rows <- R rows for G and V as DMMAs, written back once.
+// Steps are ordered by point-to-point ready flags (each block is produced by one CTA and consumed by one), a grid barrier
+// only once per sweep. The kernel is WARP-SPECIALISED around what the phase timestamps of the first, uniform version showed
 // (profiles/microbench/jacobi_phases.py; 18-20k cycles per step): 40 % of a step were the 4 rotation rounds on Gamma in
 // shared memory (LDS/STS round trips queue behind the step's own global loads in the MIO pipe), 30 % the loads (G fetched
 // twice, in the Gram and in the apply layout, plus V), 20 % apply + stores of G AND V, 10 % the flag handshake. Here:
@@ -501,8 +302,8 @@ jacobi_pipe_kernel(double* GT, double* VT, int ld, int n, int nb, double tol, in
 #undef KCMA_TSV
 }
 
-// Version 3, one step per launch (N too large for one co-resident CTA per block pair, e.g. N = 4096: 512 pairs).
-// Same Gram-update step; the apply-phase operands are loaded after the rotations (no register prefetch: 32+ groups per warp).
+// One Gram-update step per launch (N too large for one co-resident CTA per block pair, e.g. N = 4096: 512 pairs).
+// Same algebra as jacobi_pipe_kernel, no pipelining: every step streams G and V through HBM (they exceed L2 at that size).
 template <int NT>
 __global__ void __launch_bounds__(NT, 1)
 jacobi_gram_step_kernel(double* GT, double* VT, int ld, int n, int nb, int step, double tol, DevScalars* sc) {
@@ -543,41 +344,22 @@ jacobi_gram_step_kernel(double* GT, double* VT, int ld, int n, int nb, int step,
     Rm[tid >> 3][tid & 7] = ((tid >> 3) == (tid & 7)) ? 1.0 : 0.0;
   }
   __syncthreads();
-  if (warp == 0) {
-    const int k = lane >> 3, j = lane & 7;
-    const int rounds = (step == 0) ? 7 : 4;
-    int my_rot = 0, my_big = 0;
-    for (int r = 0; r < rounds; r++) {
-      int p, q;
-      if (step == 0) rr_pair(8, r, k, p, q);
-      else { p = k; q = 4 + ((k + r) & 3); }
-      const double alpha = Gam[p][p], beta = Gam[q][q], gamma = Gam[p][q];
-      double c = 1.0, s = 0.0;
-      if (gamma * gamma > tol * tol * alpha * beta) {
-        jacobi_cs(alpha, beta, gamma, c, s);
-        my_rot++;
-        my_big |= (gamma * gamma > 1e-20 * alpha * beta) ? 1 : 0;
-      }
-      __syncwarp();
-      {
-        const double x = Gam[p][j], y = Gam[q][j];
-        const double u = Rm[p][j], v = Rm[q][j];
-        __syncwarp();
-        Gam[p][j] = c * x - s * y; Gam[q][j] = s * x + c * y;
-        Rm[p][j] = c * u - s * v; Rm[q][j] = s * u + c * v;
-      }
-      __syncwarp();
-      {
-        const double x = Gam[j][p], y = Gam[j][q];
-        __syncwarp();
-        Gam[j][p] = c * x - s * y; Gam[j][q] = s * x + c * y;
-      }
-      __syncwarp();
+  if (warp == 0) {   // the step's rotations on Gamma, in registers (jacobi_inner.cuh)
+    Inner8 m;
+#pragma unroll
+    for (int a = 0; a < 8; a++) {
+#pragma unroll
+      for (int b = a; b < 8; b++) m.g[a][b] = Gam[a][b];
     }
-    my_rot = (j == 0) ? my_rot : 0;
-    my_rot += __shfl_xor_sync(0xffffffffu, my_rot, 8); my_rot += __shfl_xor_sync(0xffffffffu, my_rot, 16);
-    my_big = __any_sync(0xffffffffu, my_big);
-    if (lane == 0) { s_rot = my_rot; s_max = my_big ? 0x3ff0000000000000ull : 0ull; }
+#pragma unroll
+    for (int a = 0; a < 8; a++) m.rc[a] = (a == (lane & 7)) ? 1.0 : 0.0;
+    m.rotations = 0; m.big = 0;
+    if (step == 0) inner_full(m, tol * tol); else inner_cross(m, tol * tol);
+    if (lane < 8) {
+#pragma unroll
+      for (int a = 0; a < 8; a++) Rm[a][lane] = m.rc[a];
+    }
+    if (lane == 0) { s_rot = m.rotations; s_max = m.big ? 0x3ff0000000000000ull : 0ull; }   // "max cos^2" collapsed to {0, 1.0}
   }
   __syncthreads();
   if (s_rot == 0) return;
@@ -656,7 +438,7 @@ eigen_small_kernel(const double* __restrict__ GT, int ld, int n, double* __restr
         a = warp_sum_butterfly(a); b = warp_sum_butterfly(b); g = warp_sum_butterfly(g);
         if (g * g > tol * tol * a * b) {
           double c, s;
-          jacobi_cs(a, b, g, c, s);
+          if (!jacobi_cs_fast(a, b, g, c, s)) jacobi_cs_scaled(a, b, g, c, s);
           my_rot++;
           double* vp = Vs + (size_t)p * rs; double* vq = Vs + (size_t)q * rs;
           for (int cidx = lane; cidx < n; cidx += 32) {
@@ -866,7 +648,7 @@ long long* g_jacobi_dbg = nullptr;   // device buffer of phase timestamps (KCMA_
 bool launch_jacobi_persistent(cudaStream_t st, double* GT, double* VT, int ld, int n, double tol, int max_sweeps, DevScalars* sc,
                               int num_sms, unsigned* ready) {
   int nb = ((n + 3) / 4 + 1) & ~1;
-  if (nb / 2 > num_sms || ld > 8 * 16 * 10) return false;
+  if (nb / 2 > num_sms || ld > 1280) return false;
   const char* e = getenv("KCMA_JACOBI_PERSISTENT");
   if (e && atoi(e) == 0) return false;
   static int coop = -1;
@@ -874,31 +656,24 @@ bool launch_jacobi_persistent(cudaStream_t st, double* GT, double* VT, int ld, i
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    if (coop && cudaFuncSetAttribute(jacobi_pipe_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem - 16 * 1024) != cudaSuccess)
+      coop = 0;
   }
   if (!coop) return false;
-  static long long* dbg = nullptr;
-  if (getenv("KCMA_JACOBI_DEBUG") && !dbg) {
-    cudaMalloc(&dbg, sizeof(long long) * (2560 + 1024));
-    cudaMemset(dbg, 0, sizeof(long long) * (2560 + 1024));
+  static long long* dbg = nullptr;   // phase timestamps, only with KCMA_JACOBI_DEBUG=<sweep to trace>
+  const char* de = getenv("KCMA_JACOBI_DEBUG");
+  if (de && !dbg) {
+    cudaMalloc(&dbg, sizeof(long long) * 3584);
+    cudaMemset(dbg, 0, sizeof(long long) * 3584);
     g_jacobi_dbg = dbg;
   }
-  const char* pe = getenv("KCMA_JACOBI_PIPE");
-  if (!(pe && atoi(pe) == 0)) {   // version 4 (default); KCMA_JACOBI_PIPE=0 selects version 3
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(jacobi_pipe_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem - 16 * 1024); attr = true; }
-    const size_t smem = sizeof(double) * 16 * (size_t)(ld + 2);
-    cudaMemsetAsync(ready, 0, sizeof(unsigned) * 2 * nb, st);
-    unsigned* ready_v = ready + nb;
-    int dbg_sweep = getenv("KCMA_JACOBI_DEBUG") ? atoi(getenv("KCMA_JACOBI_DEBUG")) : -1;
-    int dbg_step0 = getenv("KCMA_JACOBI_DEBUG_STEP0") ? atoi(getenv("KCMA_JACOBI_DEBUG_STEP0")) : 8;
-    void* pargs[] = {&GT, &VT, &ld, &n, &nb, &tol, &max_sweeps, &sc, &ready, &ready_v, &dbg, &dbg_sweep, &dbg_step0};
-    if (cudaLaunchCooperativeKernel((void*)jacobi_pipe_kernel<256>, dim3(nb / 2), dim3(256), pargs, smem, st) == cudaSuccess) return true;
-    cudaGetLastError();
-    return false;
-  }
-  cudaMemsetAsync(ready, 0, sizeof(unsigned) * nb, st);
-  void* args[] = {&GT, &VT, &ld, &n, &nb, &tol, &max_sweeps, &sc, &ready, &dbg};
-  if (cudaLaunchCooperativeKernel((void*)jacobi_gram_kernel<512>, dim3(nb / 2), dim3(512), args, 0, st) == cudaSuccess) return true;
+  int dbg_sweep = de ? atoi(de) : -1;
+  int dbg_step0 = getenv("KCMA_JACOBI_DEBUG_STEP0") ? atoi(getenv("KCMA_JACOBI_DEBUG_STEP0")) : 8;
+  const size_t smem = sizeof(double) * 16 * (size_t)(ld + 2);   // 8 rows of G + 8 rows of V, stride ld + 2
+  cudaMemsetAsync(ready, 0, sizeof(unsigned) * 2 * nb, st);
+  unsigned* ready_v = ready + nb;
+  void* args[] = {&GT, &VT, &ld, &n, &nb, &tol, &max_sweeps, &sc, &ready, &ready_v, &dbg, &dbg_sweep, &dbg_step0};
+  if (cudaLaunchCooperativeKernel((void*)jacobi_pipe_kernel<256>, dim3(nb / 2), dim3(256), args, smem, st) == cudaSuccess) return true;
   cudaGetLastError();
   return false;
 }
