@@ -197,6 +197,7 @@ def ours_arm(args, rank, world):
     rk_ms, rk_calls = phases["rank_mu"]
     rk_avg = rk_ms / max(rk_calls, 1)
     cpu = cpu_reference_run(3, 1) if world == 1 else None
+    sweeps = s.timing("eigen_sweeps")[1] / args.steps
     line = {
         "metric": METRIC, "value": gens, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -220,7 +221,14 @@ def ours_arm(args, rank, world):
         "phases_ms_per_generation": {k: (v[0] / args.steps) for k, v in phases.items()},
         "rank_mu": {"kernel": "syrk_tt_kernel", "avg_ms": rk_avg, "achieved_tflops": (f_rank / (rk_avg * 1e-3) * 1e-12) if rk_avg > 0 else 0.0,
                     "algorithmic_flops_per_launch": f_rank},
-        "eigen_sweeps_per_generation": s.timing("eigen_sweeps")[1] / args.steps,
+        "eigen": {"kernel": "jacobi_pipe_kernel (persistent cooperative one-sided Jacobi, Gram-update steps on DMMA.8x8x4; replicated on every rank)",
+                  "avg_ms": phases["eigen"][0] / args.steps, "sweeps_per_generation": sweeps,
+                  "bound": "latency: N-1 dependent rotation rounds per sweep; a step = flag handshake + 64 KB row fetch + Gram + 4 rounds + apply",
+                  # executed flops: per step and block pair 3 x (2 * 8 * 8 * N) for Gram, apply G, apply V; (N/4 - 1) * N/8 pair-steps per sweep
+                  "executed_flops_per_sweep": 12.0 * n ** 3,
+                  "achieved_tflops": (12.0 * n ** 3 * sweeps / (phases["eigen"][0] / args.steps * 1e-3) * 1e-12) if phases["eigen"][0] > 0 else 0.0,
+                  "us_per_step_of_8_rows": (phases["eigen"][0] / args.steps * 1e3 / max(sweeps * (n / 4.0 - 1.0), 1e-9))},
+        "eigen_sweeps_per_generation": sweeps,
         "gens_per_sec_excluding_eigen": 1e3 / max(ms_step - phases["eigen"][0] / args.steps, 1e-9),
     }
     if cpu:
