@@ -80,7 +80,7 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------
-def cpu_reference_run(steps, warmup, sample_lambda=128):
+def cpu_reference_run(steps, warmup, sample_lambda=1024):
     """The reference algorithm on the host: the C restatement in oracle/ (the reference itself needs GSL/Eigen/meson and
     cannot be built here — DESIGN.md). Single thread: CMAES.cpp.base has no OpenMP and its conduits only parallelise
     the user model. One timed step = one generation on a BOUNDED SAMPLE of the population
@@ -124,6 +124,20 @@ def reference_arm(args, rank):
             "cpu_baseline": {"value": r["gens_per_sec"], "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
             "e2e": {"value": r["gens_per_sec"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def hbm_block(phases, steps, n, lam_local, mu_local, hbm_peak):
+    """Achieved GB/s of the bandwidth-side kernels (K1 rng, K3 objective, K4 sort, K5 gather-mean)."""
+    work = {"rng": ("philox_normal_kernel: Z written (FP64 Box-Muller bound)", 8.0 * n * lam_local),
+            "objective": ("objective_kernel: Y read", 8.0 * n * lam_local),
+            "sort": ("radix sort, 8 passes x 12 B x lambda (launch-latency bound: 25 launches)", 8 * 12.0 * lam_local),
+            "gather_mean": ("gather_mean + mean_reduce: selected rows read + S written", 2 * 8.0 * n * mu_local)}
+    out = {}
+    for k, (what, nbytes) in work.items():
+        ms = phases[k][0] / steps
+        gbps = nbytes / (ms * 1e-3) * 1e-9 if ms > 0 else 0.0
+        out[k] = {"what": what, "bytes": nbytes, "ms": ms, "GBps": gbps, "frac_of_hbm_peak": (gbps / hbm_peak) if hbm_peak else None}
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -196,7 +210,7 @@ def ours_arm(args, rank, world):
     peak = peaks.get("fp64_dgemm_tflops_sustained")
     rk_ms, rk_calls = phases["rank_mu"]
     rk_avg = rk_ms / max(rk_calls, 1)
-    cpu = cpu_reference_run(3, 1) if world == 1 else None
+    cpu = cpu_reference_run(8, 1) if world == 1 else None   # ~10 s of host work: 9 x 1024-sample generations + one eigendecomposition
     sweeps = s.timing("eigen_sweeps")[1] / args.steps
     line = {
         "metric": METRIC, "value": gens, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -221,6 +235,8 @@ def ours_arm(args, rank, world):
         "phases_ms_per_generation": {k: (v[0] / args.steps) for k, v in phases.items()},
         "rank_mu": {"kernel": "syrk_tt_kernel", "avg_ms": rk_avg, "achieved_tflops": (f_rank / (rk_avg * 1e-3) * 1e-12) if rk_avg > 0 else 0.0,
                     "algorithmic_flops_per_launch": f_rank},
+        # the HBM-side kernels of a generation: algorithmic bytes / phase time against the measured copy bandwidth
+        "hbm_kernels": hbm_block(phases, args.steps, n, lam // world, mu // world, peaks.get("hbm_gbs", 6547.2)),
         "eigen": {"kernel": "jacobi_pipe_kernel (persistent cooperative one-sided Jacobi, Gram-update steps on DMMA.8x8x4; replicated on every rank)",
                   "avg_ms": phases["eigen"][0] / args.steps, "sweeps_per_generation": sweeps,
                   "bound": "latency: N-1 dependent rotation rounds per sweep; a step = flag handshake + 64 KB row fetch + Gram + 4 rounds + apply",

@@ -279,7 +279,7 @@ jacobi_pipe_kernel(double* GT, double* VT, int ld, int n, int nb, double tol, in
         KCMA_TSV(13);
         asm volatile("bar.sync 2, %0;" ::"n"(NWV * 32));
         if (vtid == 0) {
-          if (rot != 0) __threadfence();
+          __threadfence();   // release: our stores, and (when nothing rotated here) the previous owners' rows we acquired above
           volatile unsigned* rv = readyV;
           rv[I] = epoch + 1; rv[J] = epoch + 1;
           v_tail = epoch + 1;
