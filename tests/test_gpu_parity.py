@@ -126,6 +126,44 @@ def test_eigen_residuals_and_eigenvalues(n, cond):
     assert np.abs(w - wo).max() < 1e-12 * lam.max()
 
 
+@pytest.mark.parametrize("n", [25, 26, 27, 31, 120, 1001, 1180, 1184, 1185])
+def test_eigen_kernel_boundaries(n):
+    """Sizes around the dispatch limits of the eigensolver: 24|25 single-CTA -> pipelined kernel, rows that do not fill the
+    last 4-row block / the even number of blocks (zero padding rows), 1184 = one CTA per SM (148 block pairs), 1185 = first
+    size on the one-launch-per-step path. Checked on the decomposition itself (residual, orthonormality, order)."""
+    rng = np.random.default_rng(1000 + n)
+    q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    lam = np.sort(10.0 ** rng.uniform(0, 3, n))
+    c = (q * lam) @ q.T
+    c = 0.5 * (c + c.T)
+    w, v = _lib.k_eigen(c)
+    assert np.all(np.diff(w) >= 0)
+    assert np.abs(v @ np.diag(w) @ v.T - c).max() < 1e-12 * np.abs(c).max()
+    assert np.abs(v.T @ v - np.eye(n)).max() < 1e-12
+    assert np.abs(w - lam).max() < 1e-11 * lam.max()
+
+
+@pytest.mark.parametrize("n", [64, 300])
+def test_eigen_clustered_and_repeated_spectrum(n):
+    """C = I + 1e-6 E (every eigenvalue in one cluster) and an exactly repeated eigenvalue: any orthonormal basis of an
+    eigenspace is acceptable, so the check is the reconstruction and the orthonormality, not the vectors."""
+    rng = np.random.default_rng(n)
+    e = rng.standard_normal((n, n))
+    c = np.eye(n) + 1e-6 * 0.5 * (e + e.T)
+    w, v = _lib.k_eigen(c)
+    assert np.abs(v @ np.diag(w) @ v.T - c).max() < 1e-13
+    assert np.abs(v.T @ v - np.eye(n)).max() < 1e-12
+    assert np.abs(w - np.linalg.eigvalsh(c)).max() < 1e-13
+    q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    lam = np.concatenate([np.full(n // 2, 2.0), np.full(n - n // 2, 5.0)])
+    c2 = (q * lam) @ q.T
+    c2 = 0.5 * (c2 + c2.T)
+    w2, v2 = _lib.k_eigen(c2)
+    assert np.abs(w2 - lam).max() < 1e-12
+    assert np.abs(v2 @ np.diag(w2) @ v2.T - c2).max() < 1e-12
+    assert np.abs(v2.T @ v2 - np.eye(n)).max() < 1e-12
+
+
 def test_eigen_identity_and_rejection():
     w, v = _lib.k_eigen(np.eye(7) * 2.0)
     assert np.allclose(w, 2.0) and np.abs(v.T @ v - np.eye(7)).max() < 1e-14
