@@ -112,6 +112,11 @@ struct kcma {
   std::vector<Pending> pending;
   std::vector<cudaEvent_t> event_pool;
   uint64_t launches = 0;
+  // CUDA graph of one whole generation (ask + eval + tell) for the launch-latency-bound configurations
+  cudaStream_t cap_stream = nullptr;
+  cudaGraphExec_t gexec = nullptr;
+  bool capturing = false, graph_failed = false;
+  uint64_t g_launches = 0, g_evals = 0;   // host-side counters one replay stands for
   std::string err, warn, reason;
   char warn_out[4096];
 };
@@ -244,6 +249,7 @@ int pull_scalars(kcma* h) {
   return 0;
 }
 int push_scalars(kcma* h) {
+  h->hSc->gen = h->gen - 1;   // device copy of the generation counter = last completed generation
   CUDA_OK(h, cudaMemcpyAsync(h->dSc, h->hSc, sizeof(DevScalars), cudaMemcpyHostToDevice, h->stream));
   CUDA_OK(h, cudaStreamSynchronize(h->stream));
   return 0;
@@ -413,6 +419,9 @@ int update_eigensystem(kcma* h, const double* dM) {
   return 0;
 }
 
+// by-value generation argument of the kernels; while a graph is being captured the kernels read DevScalars::gen instead
+unsigned gen_arg(const kcma* h) { return h->capturing ? kGenFromDevice : (unsigned)h->gen; }
+
 int sample_population(kcma* h) {
   const int N = h->N, ld = h->ld;
   const long long zrows = (long long)local_zrows(h);
@@ -420,7 +429,7 @@ int sample_population(kcma* h) {
   if (!h->inj_y && !h->inj_x) {
     if (!h->inj_z) {
       PhaseTimer t(h, "rng");
-      launch_philox_normal(h->stream, h->dZ, ld, zrows, N, h->cfg.seed, (unsigned)h->gen, zrow_begin, nullptr, nullptr, h->num_sms);
+      launch_philox_normal(h->stream, h->dZ, ld, zrows, N, h->cfg.seed, gen_arg(h), zrow_begin, nullptr, nullptr, h->num_sms, h->dSc);
       h->launches++;
     }
     h->inj_z = false;
@@ -735,10 +744,10 @@ int do_tell(kcma* h) {
     PhaseTimer t(h, "paths");
     double* mean_new = h->dRed + (size_t)N * ld;
     double* best_x = mean_new + ld;
-    launch_best_update(h->stream, best_x, N, (unsigned)h->gen, h->dCurBest, h->dBestEver, h->dSc, h->has_constraints ? h->dG : nullptr, h->ldg,
+    launch_best_update(h->stream, best_x, N, gen_arg(h), h->dCurBest, h->dBestEver, h->dSc, h->has_constraints ? h->dG : nullptr, h->ldg,
                        (int)h->n_con, h->dBestCon);
     launch_paths(h->stream, mean_new, h->dMean, h->dMeanOld, h->dMeanUpd, h->dT, h->dPs, h->dPc, h->dB, ld, h->dD, N,
-                 h->cfg.diagonal_covariance, h->cs, h->cc, h->mueff, h->chi_n, (unsigned)h->gen, h->dSc);
+                 h->cfg.diagonal_covariance, h->cs, h->cc, h->mueff, h->chi_n, gen_arg(h), h->dSc);
     const double c1 = 2.0 / (pow(N + 1.3, 2) + h->mueff);
     const double cmu = std::min(1.0 - c1, 2.0 * (h->mueff - 2. + 1. / h->mueff) / (pow(N + 2.0, 2) + h->mueff));
     if (multi) launch_adapt_c(h->stream, h->dC, ld, h->dRed, ld, 1, N, h->dPc, c1, cmu, h->cc, h->cfg.diagonal_covariance, h->dSc);
@@ -824,10 +833,14 @@ const char* kcma_take_warnings(kcma_t* h) {
   return h->warn_out;
 }
 
+namespace { void invalidate_graph(kcma* h); }
+
 void kcma_destroy(kcma_t* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
+  invalidate_graph(h);
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   void* ptrs[] = {h->dC, h->dB, h->dA, h->dD, h->dVT, h->dVTw, h->dGT, h->dEv, h->dPerm, h->dMean, h->dMeanOld, h->dMeanUpd, h->dT,
                   h->dPs, h->dPc, h->dZ, h->dY, h->dX, h->dF, h->dIdx, h->dSortWs, h->dW, h->dSelW, h->dSelS, h->dCount, h->dS,
@@ -992,11 +1005,13 @@ int kcma_create(const kcma_cfg* cfg, kcma_t** out) {
 }
 
 int kcma_set_host_objective(kcma_t* h, kcma_host_objective_fn fn, void* user) {
+  invalidate_graph(h);
   if (fn && !h->cfg.keep_population) return fail(h, "a host objective needs keep_population = 1 (X is copied to the host every generation)");
   h->host_obj = fn; h->host_obj_user = user;
   return 0;
 }
 int kcma_set_host_constraints(kcma_t* h, kcma_host_constraints_fn fn, void* user) {
+  invalidate_graph(h);
   if (!h->has_constraints) return fail(h, "the problem has no constraints (n_constraints = 0)");
   if (fn && !h->cfg.keep_population) return fail(h, "host constraints need keep_population = 1 (X is copied to the host)");
   h->host_con = fn; h->host_con_user = user;
@@ -1041,8 +1056,77 @@ int kcma_tell(kcma_t* h) {
   return end_of_generation(h);
 }
 
+namespace {
+
+__global__ void set_gen_kernel(DevScalars* sc, unsigned long long gen) { sc->gen = gen; }
+__global__ void inc_gen_kernel(DevScalars* sc) { sc->gen += 1; }
+
+void invalidate_graph(kcma* h) {
+  if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+}
+
+// A whole generation can be replayed as ONE CUDA graph when it is a fixed sequence of launches: single rank, built-in
+// objective, no constraint path (its loops are host-driven), no resampling rounds, no pending injection, no phase timers,
+// eigensolver = one launch (N <= 1184 or diagonal). Small configurations are launch-latency bound (44-47 launches of a few
+// microseconds each per generation): the graph removes the per-launch host cost. KCMA_GRAPH=0 disables it.
+bool graph_eligible(const kcma* h) {
+  static const int on = getenv("KCMA_GRAPH") ? atoi(getenv("KCMA_GRAPH")) : 1;
+  if (!on || h->graph_failed || h->timing || h->cfg.nranks > 1 || h->host_obj || h->host_con || h->has_constraints) return false;
+  if (h->cfg.objective == KCMA_OBJ_EXTERNAL) return false;
+  if (h->has_bounds && h->cfg.max_infeasible_resamplings != 0) return false;
+  if (h->inj_z || h->inj_bd || h->inj_y || h->inj_x || h->inj_f || h->sampled_pending || !h->vt_valid) return false;
+  if (!h->cfg.diagonal_covariance && ((h->N + 3) / 4 + 1) / 2 > h->num_sms) return false;   // eigensolver with a host loop
+  return h->gen >= 3;   // the first generations run eagerly (lazy one-time initialisations happen there)
+}
+
+// Capture ask + eval + tell of the NEXT generation; the capture pass only records, so the host-side bookkeeping it did is
+// rolled back and re-applied per replay. Returns false (and never tries again) when anything in the sequence cannot be captured.
+bool build_graph(kcma* h) {
+  if (!h->cap_stream && cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking) != cudaSuccess) { h->graph_failed = true; return false; }
+  set_gen_kernel<<<1, 1, 0, h->stream>>>(h->dSc, h->gen - 1);
+  const uint64_t gen0 = h->gen, launches0 = h->launches, evals0 = h->model_evals;
+  const cudaStream_t saved = h->stream;
+  h->capturing = true;
+  h->stream = h->cap_stream;
+  cudaGraph_t graph = nullptr;
+  int rc = 1;
+  if (cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+    inc_gen_kernel<<<1, 1, 0, h->stream>>>(h->dSc);
+    h->launches++;
+    rc = do_ask(h) || do_eval(h) || do_tell(h);
+    if (cudaStreamEndCapture(h->cap_stream, &graph) != cudaSuccess) rc = 1;
+  }
+  h->stream = saved;
+  h->capturing = false;
+  h->g_launches = h->launches - launches0;
+  h->g_evals = h->model_evals - evals0;
+  h->gen = gen0; h->launches = launches0; h->model_evals = evals0;
+  h->sampled_pending = false;
+  h->scalars_fresh = false;
+  if (!rc && cudaGraphInstantiate(&h->gexec, graph, 0) != cudaSuccess) rc = 1;
+  if (graph) cudaGraphDestroy(graph);
+  if (rc) {
+    cudaGetLastError();
+    h->gexec = nullptr;
+    h->graph_failed = true;
+    h->err.clear();
+    return false;
+  }
+  return true;
+}
+
+}  // namespace
+
 int kcma_run_generation(kcma_t* h) {
   CUDA_OK(h, cudaSetDevice(h->device));
+  if (graph_eligible(h) && (h->gexec || build_graph(h))) {
+    CUDA_OK(h, cudaGraphLaunch(h->gexec, h->stream));
+    h->gen++;
+    h->launches += h->g_launches;
+    h->model_evals += h->g_evals;
+    h->scalars_fresh = false;
+    return end_of_generation(h);
+  }
   PhaseTimer* t = h->timing ? new PhaseTimer(h, "generation") : nullptr;
   int rc = do_ask(h) || do_eval(h) || do_tell(h);
   delete t;
@@ -1096,6 +1180,7 @@ static int upload_rows(kcma* h, double* dst, const double* src, size_t rows) {
 }
 
 int kcma_inject(kcma_t* h, int kind, const double* src, size_t count) {
+  invalidate_graph(h);
   CUDA_OK(h, cudaSetDevice(h->device));
   const size_t N = h->N;
   const size_t zunit = h->cfg.mirrored_sampling ? 2 : 1;
@@ -1222,6 +1307,7 @@ int kcma_get_array(kcma_t* h, const char* key, double* out, size_t cap, size_t* 
 }
 
 int kcma_set_array(kcma_t* h, const char* key, const double* in, size_t count) {
+  invalidate_graph(h);
   CUDA_OK(h, cudaSetDevice(h->device));
   ArrRef r;
   if (!find_array(h, key, &r)) return fail(h, "unknown array key '%s'", key);
@@ -1309,6 +1395,7 @@ int kcma_get_scalar(kcma_t* h, const char* key, double* out) {
 }
 
 int kcma_set_scalar(kcma_t* h, const char* key, double v) {
+  invalidate_graph(h);
   CUDA_OK(h, cudaSetDevice(h->device));
   if (double* p = find_host_scalar(h, key)) { *p = v; return 0; }
   if (pull_scalars(h)) return 1;
@@ -1328,7 +1415,7 @@ extern "C" int kcma_debug_jacobi_timestamps(long long* out3584) {
   if (!kc::g_jacobi_dbg) return 1;
   return cudaMemcpy(out3584, kc::g_jacobi_dbg, sizeof(long long) * 3584, cudaMemcpyDeviceToHost) != cudaSuccess;
 }
-int kcma_timing_enable(kcma_t* h, int on) { h->timing = on != 0; return 0; }
+int kcma_timing_enable(kcma_t* h, int on) { h->timing = on != 0; return 0; }   // the graph path is skipped while timing
 int kcma_timing_get(kcma_t* h, const char* phase, double* ms, uint64_t* calls) {
   resolve_timers(h);
   auto it = h->phases.find(phase);

@@ -76,7 +76,11 @@ struct DevScalars {
   int warn_minsd;            // "Sigma increased due to minimal standard deviation."
   int best_updated;          // best-ever was replaced this generation
   int jacobi_rotations;      // rotations applied in the last Jacobi sweep
-  int pad0, pad1;
+  unsigned long long gen;    // generation counter for CUDA-graph replays (kernels launched with generation == kGenFromDevice read it)
 };
+
+// Sentinel for the by-value `generation` kernel argument: take the counter from DevScalars::gen instead. A captured CUDA graph
+// bakes its kernel arguments, so the replayed generation loop keeps the one argument that changes per generation on the device.
+constexpr unsigned kGenFromDevice = 0xffffffffu;
 
 }  // namespace kc

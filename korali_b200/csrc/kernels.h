@@ -23,7 +23,8 @@ bool launch_syrk_tt_tma(cudaStream_t st, int n, int K, const int* kptr, const do
 
 // rng.cu
 void launch_philox_normal(cudaStream_t st, double* Z, int ldz, long long rows, int n, unsigned long long seed, unsigned generation,
-                          unsigned long long row_begin, const unsigned* attempt, const int* row_list, int num_sms);
+                          unsigned long long row_begin, const unsigned* attempt, const int* row_list, int num_sms,
+                          const DevScalars* gen_src = nullptr /* read when generation == kGenFromDevice */);
 void launch_philox_raw(cudaStream_t st, const uint32_t* in6, uint32_t* out4);
 
 // objective.cu

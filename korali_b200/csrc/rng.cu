@@ -35,7 +35,8 @@ __device__ __forceinline__ double unit_open52(uint32_t lo, uint32_t hi) {
 __global__ void __launch_bounds__(256)
 philox_normal_kernel(double* __restrict__ Z, int ldz, long long rows, int n, unsigned long long seed, unsigned generation,
                      unsigned long long row_begin, const unsigned* __restrict__ attempt,
-                     const int* __restrict__ row_list) {
+                     const int* __restrict__ row_list, const DevScalars* __restrict__ gen_src) {
+  if (generation == kGenFromDevice) generation = (unsigned)gen_src->gen;   // CUDA-graph replay
   const int npairs = (n + 1) >> 1;
   const long long total = rows * npairs;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -70,13 +71,13 @@ __global__ void philox_raw_kernel(const uint32_t* in, uint32_t* out) {
 
 void launch_philox_normal(cudaStream_t st, double* Z, int ldz, long long rows, int n, unsigned long long seed,
                           unsigned generation, unsigned long long row_begin, const unsigned* attempt,
-                          const int* row_list, int num_sms) {
+                          const int* row_list, int num_sms, const DevScalars* gen_src) {
   if (rows <= 0) return;
   const long long total = rows * ((n + 1) / 2);
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)num_sms * 16;
   if (blocks > cap) blocks = cap;
-  philox_normal_kernel<<<(unsigned)blocks, 256, 0, st>>>(Z, ldz, rows, n, seed, generation, row_begin, attempt, row_list);
+  philox_normal_kernel<<<(unsigned)blocks, 256, 0, st>>>(Z, ldz, rows, n, seed, generation, row_begin, attempt, row_list, gen_src);
 }
 
 void launch_philox_raw(cudaStream_t st, const uint32_t* in6, uint32_t* out4) {

@@ -176,6 +176,7 @@ best_update_kernel(const double* __restrict__ best_x, int n, unsigned generation
                    long long ldg, int n_con, double* __restrict__ best_con_evals) {
   __shared__ int upd;
   if (threadIdx.x == 0) {
+    if (generation == kGenFromDevice) generation = (unsigned)sc->gen;   // CUDA-graph replay
     upd = (sc->current_best_value > sc->best_ever_value) || generation == 1;
     sc->best_updated = upd;
   }
@@ -259,6 +260,7 @@ hsig_pc_kernel(const double* __restrict__ ps, const double* __restrict__ y, doub
     for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += wsum[w];
     const double norm = sqrt(s);
     sc->ps_l2norm = norm;
+    if (generation == kGenFromDevice) generation = (unsigned)sc->gen;   // CUDA-graph replay
     const int hsig = (1.4 + 2.0 / (n + 1) > norm / sqrt(1. - pow(1. - cs, 2.0 * (1.0 + generation))) / chi_n);
     sc->hsig = hsig;
     hs = hsig;

@@ -45,7 +45,7 @@ def test_philox_independent_of_sharding():
 
 
 # ---------------------------------------------------------------- K4 sort -----------------------------------
-@pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 2047, 2048, 2049, 4096, 8192, 65536, 100003, 1 << 20])
+@pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 255, 256, 257, 511, 512, 513, 2047, 2048, 2049, 4096, 8192, 16384, 16385, 65536, 100003, 1 << 20])
 def test_sort_index_bit_exact(n):
     rng = np.random.default_rng(n)
     f = rng.standard_normal(n) * 10.0 ** rng.integers(-30, 30, n)
@@ -54,12 +54,13 @@ def test_sort_index_bit_exact(n):
 
 def test_sort_index_ties_and_signed_zero():
     rng = np.random.default_rng(1)
-    f = rng.integers(-3, 4, 50000).astype(np.float64)
-    f[::7] = -0.0
-    f[3::11] = 0.0
-    got = _lib.k_sort_index(f)
-    assert np.array_equal(got, O.sort_index(f))
-    assert np.array_equal(got, np.argsort(-f, kind="stable").astype(np.uint64))
+    for n in (50000, 9000, 700):   # radix passes | rank-by-counting (n <= 16384), several candidate chunks | one chunk pair
+        f = rng.integers(-3, 4, n).astype(np.float64)
+        f[::7] = -0.0
+        f[3::11] = 0.0
+        got = _lib.k_sort_index(f)
+        assert np.array_equal(got, O.sort_index(f))
+        assert np.array_equal(got, np.argsort(-f, kind="stable").astype(np.uint64))
     const = np.full(5000, -2.5)
     assert np.array_equal(_lib.k_sort_index(const), np.arange(5000, dtype=np.uint64))
     ext = np.array([1e308, -1e308, 5e-324, -5e-324, 0.0, 1.0, -1.0, 2.2250738585072014e-308])
@@ -359,6 +360,37 @@ def test_free_running_matches_oracle_philox_stream():
     case = dict(n=16, population_size=48, objective="NegRosenbrock", initial_value=0.1, initial_stddev=0.7, seed=99)
     s = _lib.Solver(**case); o = O.Oracle(**case); o.set_scalar("Oracle/RNG Kind", 1)
     _track(s, o, 25, 1e-8, label="rosenbrock")
+
+
+@pytest.mark.parametrize("case", [
+    dict(n=10, population_size=32, objective="NegRosenbrock", initial_value=0.0, initial_stddev=0.5, seed=7),                       # single-CTA eigensolver
+    dict(n=100, population_size=512, objective="NegAckley", initial_value=1.0, initial_stddev=3.0, seed=8),                           # pipelined eigensolver
+    dict(n=40, population_size=64, objective="NegSphere", initial_value=2.0, initial_stddev=1.0, seed=9, mirrored_sampling=1),
+    dict(n=40, population_size=64, objective="NegEllipsoid", initial_value=2.0, initial_stddev=1.0, seed=10, diagonal_covariance=1),
+    dict(n=12, population_size=24, objective="NegSphere", initial_value=1.0, initial_stddev=1.0, seed=11, lower_bound=-5.0, upper_bound=5.0),
+])
+def test_graph_replay_is_bit_identical_to_eager_launches(case):
+    """kcma_run_generation replays one captured CUDA graph per generation from the third generation on (launch-latency-bound
+    configurations); kcma_ask / kcma_eval / kcma_tell always launch eagerly. Same kernels, same arguments except
+    the generation counter (read from the device in the graph): every piece of state must be bit-identical."""
+    a = _lib.Solver(**case); b = _lib.Solver(**case)
+    for g in range(40):
+        a.run_generation()
+        b.ask(); b.eval(); b.tell()
+        if g in (0, 1, 2, 3, 10, 39):
+            for k in ["Current Mean", "Evolution Path", "Conjugate Evolution Path", "Covariance Matrix", "Covariance Eigenvector Matrix",
+                      "Axis Lengths", "Value Vector", "Best Ever Variables"]:
+                assert np.array_equal(a.get(k), b.get(k)), (g, k)
+            for k in ["Sigma", "Best Ever Value", "Current Best Value", "Conjugate Evolution Path L2 Norm", "Current Generation",
+                      "Model Evaluation Count", "Infeasible Sample Count"]:
+                assert a.scalar(k) == b.scalar(k), (g, k)
+    # state changes through the API drop the graph; the next generation is captured again and still agrees
+    a.set_scalar("Sigma", 0.5); b.set_scalar("Sigma", 0.5)
+    for g in range(5):
+        a.run_generation()
+        b.ask(); b.eval(); b.tell()
+    assert np.array_equal(a.get("Covariance Matrix"), b.get("Covariance Matrix")) and a.scalar("Sigma") == b.scalar("Sigma")
+    a.close(); b.close()
 
 
 def _constrained_problem(n):
