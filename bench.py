@@ -222,7 +222,8 @@ def ours_arm(args, rank, world):
         "e2e": {"value": done / t_e2e, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 256,
                 "note": "kcma_run(): Experiment::run loop with the termination chain evaluated on the host every generation (device scalars "
                         "copied back each step); the generation loop takes no per-step host input (samples are drawn on the device from "
-                        "Philox(seed, generation) counters)"},
+                        "Philox(seed, generation) counters). Runs without phase timers (one CUDA-graph replay per generation), "
+                        "whereas `value` is timed with the per-phase CUDA events and the per-generation sweep-count readback enabled"},
         "gpu_launches": int(launches),
         "clocks": clk,
         "roofline": {"kernel": "gemm_tn_tma_kernel (sampling GEMM Y = Z (B D)^T, TMA + mbarrier + DMMA.8x8x4)", "bound": "tensor",
