@@ -392,7 +392,8 @@ int update_eigensystem(kcma* h, const double* dM) {
   // GT = VT * M  (M symmetric): GT[i][j] = sum_k VT[i][k] M[j][k]
   launch_gemm_tn(h->stream, N, N, N, h->dVTw, ld, dM, ld, h->dGT, ld);
   h->launches += 1;
-  if (launch_jacobi_persistent(h->stream, h->dGT, h->dVTw, ld, N, tol, max_sweeps, h->dSc, h->num_sms, (unsigned*)h->dPerm)) {
+  const bool persistent = launch_jacobi_persistent(h->stream, h->dGT, h->dVTw, ld, N, tol, max_sweeps, h->dSc, h->num_sms, (unsigned*)h->dPerm);
+  if (persistent) {
     h->launches += 1;
     h->scalars_fresh = false;
     if (h->timing) { if (pull_scalars(h)) return 1; h->phases["eigen_sweeps"].calls += h->hSc->jacobi_sweeps; }
@@ -411,6 +412,7 @@ int update_eigensystem(kcma* h, const double* dM) {
     memcpy(&max_rel, &h->hSc->jacobi_max_rel_bits, sizeof(double));
     if (max_rel < 1e-20) break;   // the kernels record the SQUARED cosine
   }
+  if (!persistent) { int l = 0; launch_jacobi_block_flush(h->stream, h->dGT, h->dVTw, ld, N, tol, h->dSc, &l); h->launches += l; }
   launch_rayleigh(h->stream, h->dGT, h->dVTw, ld, N, h->dEv, h->dT);   // dT (scratch of tell()) holds the signs here
   launch_eig_order(h->stream, h->dEv, N, h->dPerm, h->dSc);
   launch_eig_commit(h->stream, h->dVTw, ld, N, h->dPerm, h->dEv, h->dT, h->dB, h->dA, h->dD, h->dVT, h->dSc);

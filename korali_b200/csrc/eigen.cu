@@ -694,128 +694,14 @@ constexpr int BIG_LDS = BIG_R + 1;    // padded leading dimension of Gamma and R
 
 __device__ __forceinline__ int big_row(int I, int J, int i) { return i < BIG_B ? I * BIG_B + i : J * BIG_B + (i - BIG_B); }
 
-template <int NT>
-__global__ void __launch_bounds__(NT, 1)
-jacobi_big_step_kernel(double* GT, double* VT, int ld, int n, int nsb, int step, double tol, DevScalars* sc) {
-  constexpr int NW = NT / 32;
-  extern __shared__ __align__(16) double big_smem[];
-  double* part = big_smem;                               // [NW][BIG_TILES][64] partial Gram tiles
-  double* Gam = part + NW * BIG_TILES * 64;              // [32][33]
-  double* Rm = Gam + BIG_R * BIG_LDS;                    // [32][33], rows_new = R rows_old
-  __shared__ int s_rot, s_big;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int nspans = ld >> 4;
-  int I, J;
-  rr_pair(nsb, step, blockIdx.x, I, J);
-  if (tid == 0) { s_rot = 0; s_big = 0; }
+constexpr int BIG_RLOG = BIG_R * BIG_R + 8;   // doubles per pair in the R log: R (row-major 32 x 32) + rotation count
 
-  // ---- (i) Gamma: lane (g,t) holds columns 4t..4t+3 of a 16-column span for the four 8-row groups ----
-  {
-    double acc[BIG_TILES][2];
-#pragma unroll
-    for (int q = 0; q < BIG_TILES; q++) acc[q][0] = acc[q][1] = 0.0;
-    const double* rowp[4];
-    bool rok[4];
-#pragma unroll
-    for (int r = 0; r < 4; r++) {
-      const int row = big_row(I, J, 8 * r + g);
-      rok[r] = row < n;
-      rowp[r] = GT + (size_t)(rok[r] ? row : 0) * ld + 4 * t;
-    }
-    for (int h0 = warp; h0 < nspans; h0 += 2 * NW) {   // two spans (8 x 256-bit loads) in flight per lane
-      double4x x[2][4];
-#pragma unroll
-      for (int u = 0; u < 2; u++) {
-        const int h = h0 + u * NW;
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-          x[u][r].a = x[u][r].b = x[u][r].c = x[u][r].d = 0.0;
-          if (h < nspans && rok[r]) x[u][r] = ldcg_256(rowp[r] + 16 * h);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 2; u++) {
-        int q = 0;
-#pragma unroll
-        for (int r1 = 0; r1 < 4; r1++) {
-#pragma unroll
-          for (int r2 = r1; r2 < 4; r2++, q++) {   // tile (r1, r2): Gamma[8 r1 + m][8 r2 + n]
-            dmma884(acc[q][0], acc[q][1], x[u][r1].a, x[u][r2].a);
-            dmma884(acc[q][0], acc[q][1], x[u][r1].b, x[u][r2].b);
-            dmma884(acc[q][0], acc[q][1], x[u][r1].c, x[u][r2].c);
-            dmma884(acc[q][0], acc[q][1], x[u][r1].d, x[u][r2].d);
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < BIG_TILES; q++) {
-      part[(warp * BIG_TILES + q) * 64 + g * 8 + 2 * t] = acc[q][0];
-      part[(warp * BIG_TILES + q) * 64 + g * 8 + 2 * t + 1] = acc[q][1];
-    }
-  }
-  __syncthreads();
-  for (int e = tid; e < BIG_TILES * 64; e += NT) {
-    double a = 0.0;
-#pragma unroll
-    for (int w = 0; w < NW; w++) a += part[w * BIG_TILES * 64 + e];
-    const int q = e >> 6, m = (e >> 3) & 7, nn = e & 7;
-    int r1 = 0, base = 0;   // tile index -> (r1, r2): rows of tiles start at 0, 4, 7, 9
-    if (q >= 9) { r1 = 3; base = 9; } else if (q >= 7) { r1 = 2; base = 7; } else if (q >= 4) { r1 = 1; base = 4; }
-    const int r2 = r1 + (q - base);
-    const int i = 8 * r1 + m, j = 8 * r2 + nn;
-    Gam[i * BIG_LDS + j] = a;
-    if (r1 != r2) Gam[j * BIG_LDS + i] = a;
-  }
-  for (int e = tid; e < BIG_R * BIG_R; e += NT) Rm[(e >> 5) * BIG_LDS + (e & 31)] = ((e >> 5) == (e & 31)) ? 1.0 : 0.0;
-  __syncthreads();
-
-  // ---- (ii) the step's rotations on Gamma: BIG_B disjoint pairs per round, pair k on warp slot k, lane j = column index ----
-  {
-    const double tol2 = tol * tol;
-    const int rounds = (step == 0) ? BIG_R - 1 : BIG_B;   // first step of a sweep: all pairs of the 32 rows
-    int my_rot = 0, my_big = 0;
-    for (int r = 0; r < rounds; r++) {
-      double cc[BIG_B / NW], ss[BIG_B / NW];
-      int pp[BIG_B / NW], qq[BIG_B / NW];
-#pragma unroll
-      for (int u = 0; u < BIG_B / NW; u++) {   // rows p, q of Gamma and of R
-        const int k = warp + u * NW;
-        int p, q;
-        if (step == 0) rr_pair(BIG_R, r, k, p, q); else { p = k; q = BIG_B + ((k + r) & (BIG_B - 1)); }
-        const double alpha = Gam[p * BIG_LDS + p], beta = Gam[q * BIG_LDS + q], gamma = Gam[p * BIG_LDS + q];
-        const double g2 = gamma * gamma, ab = alpha * beta;
-        const bool on = g2 > tol2 * ab;
-        double c = 1.0, sn = 0.0;
-        if (on) {
-          if (!jacobi_cs_fast(alpha, beta, gamma, c, sn)) jacobi_cs_scaled(alpha, beta, gamma, c, sn);
-          my_rot++;
-          my_big |= (g2 > 1e-20 * ab) ? 1 : 0;
-        }
-        const double x = Gam[p * BIG_LDS + lane], y = Gam[q * BIG_LDS + lane];
-        const double a = Rm[p * BIG_LDS + lane], b = Rm[q * BIG_LDS + lane];
-        __syncwarp();
-        Gam[p * BIG_LDS + lane] = c * x - sn * y; Gam[q * BIG_LDS + lane] = sn * x + c * y;
-        Rm[p * BIG_LDS + lane] = c * a - sn * b;  Rm[q * BIG_LDS + lane] = sn * a + c * b;
-        cc[u] = c; ss[u] = sn; pp[u] = p; qq[u] = q;
-      }
-      __syncthreads();
-#pragma unroll
-      for (int u = 0; u < BIG_B / NW; u++) {   // columns p, q of Gamma
-        const double x = Gam[lane * BIG_LDS + pp[u]], y = Gam[lane * BIG_LDS + qq[u]];
-        Gam[lane * BIG_LDS + pp[u]] = cc[u] * x - ss[u] * y;
-        Gam[lane * BIG_LDS + qq[u]] = ss[u] * x + cc[u] * y;
-      }
-      __syncthreads();
-    }
-    if (lane == 0 && my_rot) { atomicAdd(&s_rot, my_rot); if (my_big) atomicOr(&s_big, 1); }
-  }
-  __syncthreads();
-  if (s_rot == 0) return;
-
-  // ---- (iii) rows <- R rows for G and V: per 16-column span 4 M-tiles x 2 N-tiles x 8 k-steps ----
-  // N-tile A takes the columns 4q, 4q+2 and N-tile B the columns 4q+1, 4q+3 of the span (q = 0..3), so that lane g loads ONE
-  // 16-byte operand per k-row (columns 2g, 2g+1) and lane t stores 4 consecutive doubles (columns 4t..4t+3).
+// rows <- R rows for the 32 rows of the block pair (I, J) of M (G or V), on the spans w0, w0 + nw, ... Rs = R in shared memory.
+// Per 16-column span 4 M-tiles x 2 N-tiles x 8 k-steps. N-tile A takes the columns 4q, 4q+2 and N-tile B the columns 4q+1, 4q+3
+// of the span (q = 0..3), so that lane g loads ONE 16-byte operand per k-row (columns 2g, 2g+1) and lane t stores 4 consecutive
+// doubles (columns 4t..4t+3). Every warp owns whole spans and reads all 32 rows of a span before writing it: in place is safe.
+__device__ __forceinline__ void big_apply(double* M, int ld, int n, int I, int J, const double* Rs, int w0, int nw, int lane, int nspans) {
+  const int g = lane >> 2, t = lane & 3;
   size_t soff[8];   // operand offsets: k-row 4 ks + t, columns 2g, 2g+1 of the span
   bool sok[8];
 #pragma unroll
@@ -827,62 +713,250 @@ jacobi_big_step_kernel(double* GT, double* VT, int ld, int n, int nsb, int step,
   int orow[4];
 #pragma unroll
   for (int m = 0; m < 4; m++) orow[m] = big_row(I, J, 8 * m + g);
-  for (int pass = 0; pass < 2; pass++) {
-    double* M = pass == 0 ? GT : VT;
-    for (int h0 = warp; h0 < nspans; h0 += 2 * NW) {   // two spans (16 operand loads) in flight per lane
-      double2 b[2][8];
+  constexpr int SP = 4;   // spans in flight per lane (32 x 16-byte operand loads = 16 KB per warp): HBM latency x bandwidth
+  for (int h0 = w0; h0 < nspans; h0 += SP * nw) {
+    double2 b[SP][8];
 #pragma unroll
-      for (int u = 0; u < 2; u++) {
-        const int h = h0 + u * NW;
+    for (int u = 0; u < SP; u++) {
+      const int h = h0 + u * nw;
+#pragma unroll
+      for (int ks = 0; ks < 8; ks++) {
+        b[u][ks] = make_double2(0.0, 0.0);
+        if (h < nspans && sok[ks]) b[u][ks] = __ldcg(reinterpret_cast<const double2*>(M + soff[ks] + 16 * h));
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+      double af[8];   // A fragments of M-tile m: R[8m + g][4 ks + t]
+#pragma unroll
+      for (int ks = 0; ks < 8; ks++) af[ks] = Rs[(8 * m + g) * BIG_LDS + 4 * ks + t];
+#pragma unroll
+      for (int u = 0; u < SP; u++) {
+        const int h = h0 + u * nw;
+        double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0;
 #pragma unroll
         for (int ks = 0; ks < 8; ks++) {
-          b[u][ks] = make_double2(0.0, 0.0);
-          if (h < nspans && sok[ks]) b[u][ks] = __ldcg(reinterpret_cast<const double2*>(M + soff[ks] + 16 * h));
+          dmma884(d0, d1, af[ks], b[u][ks].x);   // tile A: columns 4q, 4q+2 -> lane t gets columns 4t, 4t+2
+          dmma884(e0, e1, af[ks], b[u][ks].y);   // tile B: columns 4q+1, 4q+3 -> lane t gets columns 4t+1, 4t+3
         }
-      }
-      __syncwarp();   // the warp has read its spans (all 32 rows x 16 columns each) before any lane overwrites them
-#pragma unroll
-      for (int m = 0; m < 4; m++) {
-        double af[8];   // A fragments of M-tile m: R[8m + g][4 ks + t]
-#pragma unroll
-        for (int ks = 0; ks < 8; ks++) af[ks] = Rm[(8 * m + g) * BIG_LDS + 4 * ks + t];
-#pragma unroll
-        for (int u = 0; u < 2; u++) {
-          const int h = h0 + u * NW;
-          double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0;
-#pragma unroll
-          for (int ks = 0; ks < 8; ks++) {
-            dmma884(d0, d1, af[ks], b[u][ks].x);   // tile A: columns 4q, 4q+2 -> lane t gets columns 4t, 4t+2
-            dmma884(e0, e1, af[ks], b[u][ks].y);   // tile B: columns 4q+1, 4q+3 -> lane t gets columns 4t+1, 4t+3
-          }
-          if (h < nspans && orow[m] < n) stcg_256(M + (size_t)orow[m] * ld + 16 * h + 4 * t, d0, e0, d1, e1);
-        }
+        if (h < nspans && orow[m] < n) stcg_256(M + (size_t)orow[m] * ld + 16 * h + 4 * t, d0, e0, d1, e1);
       }
     }
   }
-  if (tid == 0) {
-    atomicAdd(&sc->jacobi_rotations, s_rot);
-    if (s_big) atomicMax(&sc->jacobi_max_rel_bits, 0x3ff0000000000000ull);
+}
+
+// One tournament step. The V rows are updated ONE LAUNCH LATE: the launch of step s computes Gamma and the rotations of
+// step s on the first NWG warps (HBM-bound Gram pass, then the rotation rounds, which leave the DMMA pipe idle) while the other
+// warps apply the R of the PREVIOUS step (read back from the R log in global memory) to its V rows; then all warps apply
+// the new R to the G rows. V never feeds the rotations, so the only ordering it needs is launch order.
+// prev_step < 0: nothing pending; do_g == 0: flush launch (only the pending V update).
+template <int NT>
+__global__ void __launch_bounds__(NT, 1)
+jacobi_big_step_kernel(double* GT, double* VT, int ld, int n, int nsb, int step, int prev_step, int do_g, double tol, DevScalars* sc,
+                       const double* __restrict__ rlog_prev, double* __restrict__ rlog_cur) {
+  constexpr int NW = NT / 32, NWG = NW / 2, NWV = NW - NWG;
+  constexpr int PPW = BIG_B / NWG;                       // rotation pairs per warp of the G group
+  extern __shared__ __align__(16) double big_smem[];
+  double* part = big_smem;                               // [NWG][BIG_TILES][64] partial Gram tiles
+  double* Gam = part + NWG * BIG_TILES * 64;             // [32][33]
+  double* Rm = Gam + BIG_R * BIG_LDS;                    // [32][33] this step, rows_new = R rows_old
+  double* Rv = Rm + BIG_R * BIG_LDS;                     // [32][33] previous step (V update)
+  __shared__ int s_rot, s_big;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int nspans = ld >> 4;
+  if (tid == 0) { s_rot = 0; s_big = 0; }
+  __syncthreads();
+  int I = 0, J = 0;
+  if (do_g) rr_pair(nsb, step, blockIdx.x, I, J);
+
+  if (warp >= NWG) {
+    // ================= V group: the pending update of the previous step =================
+    if (prev_step >= 0) {
+      int Ip, Jp;
+      rr_pair(nsb, prev_step, blockIdx.x, Ip, Jp);
+      const double* src = rlog_prev + (size_t)blockIdx.x * BIG_RLOG;
+      if (src[BIG_R * BIG_R] != 0.0) {
+        const int vt = tid - NWG * 32;
+        for (int e = vt; e < BIG_R * BIG_R; e += NWV * 32) Rv[(e >> 5) * BIG_LDS + (e & 31)] = src[e];
+        asm volatile("bar.sync 2, %0;" ::"n"(NWV * 32));
+        big_apply(VT, ld, n, Ip, Jp, Rv, warp - NWG, NWV, lane, nspans);
+      }
+    }
+  } else if (do_g) {
+    // ================= G group: Gamma, then the step's rotations =================
+    const int gt = tid;   // 0 .. NWG*32-1
+    {
+      // (i) Gamma: lane (g,t) holds columns 4t..4t+3 of a 16-column span for the four 8-row groups
+      double acc[BIG_TILES][2];
+#pragma unroll
+      for (int q = 0; q < BIG_TILES; q++) acc[q][0] = acc[q][1] = 0.0;
+      const double* rowp[4];
+      bool rok[4];
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        const int row = big_row(I, J, 8 * r + g);
+        rok[r] = row < n;
+        rowp[r] = GT + (size_t)(rok[r] ? row : 0) * ld + 4 * t;
+      }
+      constexpr int SPG = 4;   // spans in flight per lane (16 x 256-bit loads = 16 KB per warp)
+      for (int h0 = warp; h0 < nspans; h0 += SPG * NWG) {
+        double4x x[SPG][4];
+#pragma unroll
+        for (int u = 0; u < SPG; u++) {
+          const int h = h0 + u * NWG;
+#pragma unroll
+          for (int r = 0; r < 4; r++) {
+            x[u][r].a = x[u][r].b = x[u][r].c = x[u][r].d = 0.0;
+            if (h < nspans && rok[r]) x[u][r] = ldcg_256(rowp[r] + 16 * h);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < SPG; u++) {
+          int q = 0;
+#pragma unroll
+          for (int r1 = 0; r1 < 4; r1++) {
+#pragma unroll
+            for (int r2 = r1; r2 < 4; r2++, q++) {   // tile (r1, r2): Gamma[8 r1 + m][8 r2 + n]
+              dmma884(acc[q][0], acc[q][1], x[u][r1].a, x[u][r2].a);
+              dmma884(acc[q][0], acc[q][1], x[u][r1].b, x[u][r2].b);
+              dmma884(acc[q][0], acc[q][1], x[u][r1].c, x[u][r2].c);
+              dmma884(acc[q][0], acc[q][1], x[u][r1].d, x[u][r2].d);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < BIG_TILES; q++) {
+        part[(warp * BIG_TILES + q) * 64 + g * 8 + 2 * t] = acc[q][0];
+        part[(warp * BIG_TILES + q) * 64 + g * 8 + 2 * t + 1] = acc[q][1];
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(NWG * 32));
+    for (int e = gt; e < BIG_TILES * 64; e += NWG * 32) {
+      double a = 0.0;
+#pragma unroll
+      for (int w = 0; w < NWG; w++) a += part[w * BIG_TILES * 64 + e];
+      const int q = e >> 6, m = (e >> 3) & 7, nn = e & 7;
+      int r1 = 0, base = 0;   // tile index -> (r1, r2): rows of tiles start at 0, 4, 7, 9
+      if (q >= 9) { r1 = 3; base = 9; } else if (q >= 7) { r1 = 2; base = 7; } else if (q >= 4) { r1 = 1; base = 4; }
+      const int r2 = r1 + (q - base);
+      const int i = 8 * r1 + m, j = 8 * r2 + nn;
+      Gam[i * BIG_LDS + j] = a;
+      if (r1 != r2) Gam[j * BIG_LDS + i] = a;
+    }
+    for (int e = gt; e < BIG_R * BIG_R; e += NWG * 32) Rm[(e >> 5) * BIG_LDS + (e & 31)] = ((e >> 5) == (e & 31)) ? 1.0 : 0.0;
+    asm volatile("bar.sync 1, %0;" ::"n"(NWG * 32));
+    // (ii) the step's rotations on Gamma: BIG_B disjoint pairs per round, PPW per warp, lane j = column index
+    {
+      const double tol2 = tol * tol;
+      const int rounds = (step == 0) ? BIG_R - 1 : BIG_B;   // first step of a sweep: all pairs of the 32 rows
+      int my_rot = 0, my_big = 0;
+      for (int r = 0; r < rounds; r++) {
+        double cc[PPW], ss[PPW];
+        int pp[PPW], qq[PPW];
+#pragma unroll
+        for (int u = 0; u < PPW; u++) {   // rows p, q of Gamma and of R
+          const int k = warp + u * NWG;
+          int p, q;
+          if (step == 0) rr_pair(BIG_R, r, k, p, q); else { p = k; q = BIG_B + ((k + r) & (BIG_B - 1)); }
+          const double alpha = Gam[p * BIG_LDS + p], beta = Gam[q * BIG_LDS + q], gamma = Gam[p * BIG_LDS + q];
+          const double g2 = gamma * gamma, ab = alpha * beta;
+          const bool on = g2 > tol2 * ab;
+          double c = 1.0, sn = 0.0;
+          if (on) {
+            if (!jacobi_cs_fast(alpha, beta, gamma, c, sn)) jacobi_cs_scaled(alpha, beta, gamma, c, sn);
+            my_rot++;
+            my_big |= (g2 > 1e-20 * ab) ? 1 : 0;
+          }
+          const double x = Gam[p * BIG_LDS + lane], y = Gam[q * BIG_LDS + lane];
+          const double a = Rm[p * BIG_LDS + lane], b = Rm[q * BIG_LDS + lane];
+          __syncwarp();
+          Gam[p * BIG_LDS + lane] = c * x - sn * y; Gam[q * BIG_LDS + lane] = sn * x + c * y;
+          Rm[p * BIG_LDS + lane] = c * a - sn * b;  Rm[q * BIG_LDS + lane] = sn * a + c * b;
+          cc[u] = c; ss[u] = sn; pp[u] = p; qq[u] = q;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(NWG * 32));
+#pragma unroll
+        for (int u = 0; u < PPW; u++) {   // columns p, q of Gamma
+          const double x = Gam[lane * BIG_LDS + pp[u]], y = Gam[lane * BIG_LDS + qq[u]];
+          Gam[lane * BIG_LDS + pp[u]] = cc[u] * x - ss[u] * y;
+          Gam[lane * BIG_LDS + qq[u]] = ss[u] * x + cc[u] * y;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(NWG * 32));
+      }
+      if (lane == 0 && my_rot) { atomicAdd(&s_rot, my_rot); if (my_big) atomicOr(&s_big, 1); }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(NWG * 32));
+    // R and the rotation count go to the log: the NEXT launch applies them to the V rows of this pair
+    {
+      double* dst = rlog_cur + (size_t)blockIdx.x * BIG_RLOG;
+      const int rot = s_rot;
+      if (rot) for (int e = gt; e < BIG_R * BIG_R; e += NWG * 32) dst[e] = Rm[(e >> 5) * BIG_LDS + (e & 31)];
+      if (gt == 0) dst[BIG_R * BIG_R] = (double)rot;
+    }
+  }
+  __syncthreads();
+  // (iii) rows of G <- R rows, all warps
+  if (do_g && s_rot != 0) {
+    big_apply(GT, ld, n, I, J, Rm, warp, NW, lane, nspans);
+    if (tid == 0) {
+      atomicAdd(&sc->jacobi_rotations, s_rot);
+      if (s_big) atomicMax(&sc->jacobi_max_rel_bits, 0x3ff0000000000000ull);
+    }
   }
 }
 
-// One sweep as nb-1 launches (N too large for the persistent kernel); the host checks sc->jacobi_max_rel_bits between sweeps.
-void launch_jacobi_block_sweep(cudaStream_t st, double* GT, double* VT, int ld, int n, double tol, DevScalars* sc, int* launches) {
+// One sweep of per-step launches (N too large for the persistent kernel); the host checks sc->jacobi_max_rel_bits between
+// sweeps and calls launch_jacobi_block_flush once after the last sweep (the 16-row-block kernel updates V one launch late).
+namespace {
+constexpr int BIG_NT = 256;
+double* g_rlog = nullptr;      // 2 x (pairs x BIG_RLOG) doubles, double-buffered by launch parity
+size_t g_rlog_pairs = 0;
+unsigned g_big_launch = 0;     // parity of the next launch
+int g_big_pending = -1;        // step whose V update is still pending (-1: none)
+size_t big_smem_bytes() { return sizeof(double) * ((BIG_NT / 64) * BIG_TILES * 64 + 3 * BIG_R * BIG_LDS); }
+bool big_enabled() {
   static const int big = getenv("KCMA_JACOBI_BIG") ? atoi(getenv("KCMA_JACOBI_BIG")) : 1;
+  return big != 0;
+}
+void big_launch(cudaStream_t st, double* GT, double* VT, int ld, int n, int nsb, int step, int do_g, double tol, DevScalars* sc) {
+  double* cur = g_rlog + (size_t)(g_big_launch & 1u) * g_rlog_pairs * BIG_RLOG;
+  const double* prev = g_rlog + (size_t)((g_big_launch & 1u) ^ 1u) * g_rlog_pairs * BIG_RLOG;
+  jacobi_big_step_kernel<BIG_NT><<<nsb / 2, BIG_NT, big_smem_bytes(), st>>>(GT, VT, ld, n, nsb, step, g_big_pending, do_g, tol, sc, prev, cur);
+  g_big_launch++;
+  g_big_pending = do_g ? step : -1;
+}
+}  // namespace
+
+void launch_jacobi_block_sweep(cudaStream_t st, double* GT, double* VT, int ld, int n, double tol, DevScalars* sc, int* launches) {
   reset_rotations_kernel<<<1, 1, 0, st>>>(sc);
-  if (big) {   // 16-row blocks: N/16 - 1 steps per sweep
-    constexpr int NT = 256;
-    const size_t smem = sizeof(double) * ((NT / 32) * BIG_TILES * 64 + 2 * BIG_R * BIG_LDS);
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(jacobi_big_step_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+  if (big_enabled()) {   // 16-row blocks: N/16 - 1 steps per sweep
     const int nsb = ((n + BIG_B - 1) / BIG_B + 1) & ~1;
-    for (int step = 0; step < nsb - 1; step++) jacobi_big_step_kernel<NT><<<nsb / 2, NT, smem, st>>>(GT, VT, ld, n, nsb, step, tol, sc);
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(jacobi_big_step_kernel<BIG_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_smem_bytes()); attr = true; }
+    if ((size_t)(nsb / 2) > g_rlog_pairs) {
+      cudaStreamSynchronize(st);
+      if (g_rlog) cudaFree(g_rlog);
+      g_rlog_pairs = (size_t)(nsb / 2);
+      cudaMalloc(&g_rlog, sizeof(double) * 2 * g_rlog_pairs * BIG_RLOG);
+      g_big_pending = -1;
+    }
+    for (int step = 0; step < nsb - 1; step++) big_launch(st, GT, VT, ld, n, nsb, step, 1, tol, sc);
     if (launches) *launches += nsb;
     return;
   }
   const int nb = ((n + 3) / 4 + 1) & ~1;
   for (int step = 0; step < nb - 1; step++) jacobi_gram_step_kernel<512><<<nb / 2, 512, 0, st>>>(GT, VT, ld, n, nb, step, tol, sc);
   if (launches) *launches += nb;
+}
+
+// The V update of the last step is still pending after the last sweep.
+void launch_jacobi_block_flush(cudaStream_t st, double* GT, double* VT, int ld, int n, double tol, DevScalars* sc, int* launches) {
+  if (!big_enabled() || g_big_pending < 0) return;
+  const int nsb = ((n + BIG_B - 1) / BIG_B + 1) & ~1;
+  big_launch(st, GT, VT, ld, n, nsb, 0, 0, tol, sc);
+  if (launches) *launches += 1;
 }
 
 void launch_rayleigh(cudaStream_t st, const double* GT, const double* VT, int ld, int n, double* ev, double* sign) {

@@ -81,6 +81,7 @@ void launch_eigen_small(cudaStream_t st, const double* C, int ld, int n, double*
 bool launch_jacobi_persistent(cudaStream_t st, double* GT, double* VT, int ld, int n, double tol, int max_sweeps, DevScalars* sc,
                               int num_sms, unsigned* ready);
 void launch_jacobi_block_sweep(cudaStream_t st, double* GT, double* VT, int ld, int n, double tol, DevScalars* sc, int* launches);
+void launch_jacobi_block_flush(cudaStream_t st, double* GT, double* VT, int ld, int n, double tol, DevScalars* sc, int* launches);
 void launch_rayleigh(cudaStream_t st, const double* GT, const double* VT, int ld, int n, double* ev, double* sign);
 void launch_eig_order(cudaStream_t st, const double* ev, int n, int* perm, DevScalars* sc);
 void launch_eig_commit(cudaStream_t st, const double* VTw, int ld, int n, const int* perm, const double* ev, const double* sign,
