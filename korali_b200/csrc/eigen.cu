@@ -911,21 +911,31 @@ jacobi_big_step_kernel(double* GT, double* VT, int ld, int n, int nsb, int step,
 // sweeps and calls launch_jacobi_block_flush once after the last sweep (the 16-row-block kernel updates V one launch late).
 namespace {
 constexpr int BIG_NT = 256;
-double* g_rlog = nullptr;      // 2 x (pairs x BIG_RLOG) doubles, double-buffered by launch parity
-size_t g_rlog_pairs = 0;
-unsigned g_big_launch = 0;     // parity of the next launch
-int g_big_pending = -1;        // step whose V update is still pending (-1: none)
+// R log and launch bookkeeping, per device (one process normally drives one GPU, but kcma_cfg::device is free)
+struct BigState {
+  double* rlog = nullptr;      // 2 x (pairs x BIG_RLOG) doubles, double-buffered by launch parity
+  size_t pairs = 0;
+  unsigned launch = 0;         // parity of the next launch
+  int pending = -1;            // step whose V update is still pending (-1: none)
+};
+BigState g_big[64];
+BigState& big_state() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return g_big[dev & 63];
+}
 size_t big_smem_bytes() { return sizeof(double) * ((BIG_NT / 64) * BIG_TILES * 64 + 3 * BIG_R * BIG_LDS); }
 bool big_enabled() {
   static const int big = getenv("KCMA_JACOBI_BIG") ? atoi(getenv("KCMA_JACOBI_BIG")) : 1;
   return big != 0;
 }
 void big_launch(cudaStream_t st, double* GT, double* VT, int ld, int n, int nsb, int step, int do_g, double tol, DevScalars* sc) {
-  double* cur = g_rlog + (size_t)(g_big_launch & 1u) * g_rlog_pairs * BIG_RLOG;
-  const double* prev = g_rlog + (size_t)((g_big_launch & 1u) ^ 1u) * g_rlog_pairs * BIG_RLOG;
-  jacobi_big_step_kernel<BIG_NT><<<nsb / 2, BIG_NT, big_smem_bytes(), st>>>(GT, VT, ld, n, nsb, step, g_big_pending, do_g, tol, sc, prev, cur);
-  g_big_launch++;
-  g_big_pending = do_g ? step : -1;
+  BigState& b = big_state();
+  double* cur = b.rlog + (size_t)(b.launch & 1u) * b.pairs * BIG_RLOG;
+  const double* prev = b.rlog + (size_t)((b.launch & 1u) ^ 1u) * b.pairs * BIG_RLOG;
+  jacobi_big_step_kernel<BIG_NT><<<nsb / 2, BIG_NT, big_smem_bytes(), st>>>(GT, VT, ld, n, nsb, step, b.pending, do_g, tol, sc, prev, cur);
+  b.launch++;
+  b.pending = do_g ? step : -1;
 }
 }  // namespace
 
@@ -935,12 +945,13 @@ void launch_jacobi_block_sweep(cudaStream_t st, double* GT, double* VT, int ld, 
     const int nsb = ((n + BIG_B - 1) / BIG_B + 1) & ~1;
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(jacobi_big_step_kernel<BIG_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_smem_bytes()); attr = true; }
-    if ((size_t)(nsb / 2) > g_rlog_pairs) {
+    BigState& b = big_state();
+    if ((size_t)(nsb / 2) > b.pairs) {
       cudaStreamSynchronize(st);
-      if (g_rlog) cudaFree(g_rlog);
-      g_rlog_pairs = (size_t)(nsb / 2);
-      cudaMalloc(&g_rlog, sizeof(double) * 2 * g_rlog_pairs * BIG_RLOG);
-      g_big_pending = -1;
+      if (b.rlog) cudaFree(b.rlog);
+      b.pairs = (size_t)(nsb / 2);
+      cudaMalloc(&b.rlog, sizeof(double) * 2 * b.pairs * BIG_RLOG);
+      b.pending = -1;
     }
     for (int step = 0; step < nsb - 1; step++) big_launch(st, GT, VT, ld, n, nsb, step, 1, tol, sc);
     if (launches) *launches += nsb;
@@ -953,7 +964,7 @@ void launch_jacobi_block_sweep(cudaStream_t st, double* GT, double* VT, int ld, 
 
 // The V update of the last step is still pending after the last sweep.
 void launch_jacobi_block_flush(cudaStream_t st, double* GT, double* VT, int ld, int n, double tol, DevScalars* sc, int* launches) {
-  if (!big_enabled() || g_big_pending < 0) return;
+  if (!big_enabled() || big_state().pending < 0) return;
   const int nsb = ((n + BIG_B - 1) / BIG_B + 1) & ~1;
   big_launch(st, GT, VT, ld, n, nsb, 0, 0, tol, sc);
   if (launches) *launches += 1;
