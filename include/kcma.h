@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define KCMA_ABI_VERSION 1
+#define KCMA_ABI_VERSION 2
 
 /* "Mu Type" (CMAES.cpp.base:236-245). */
 enum { KCMA_MU_LINEAR = 0, KCMA_MU_EQUAL = 1, KCMA_MU_LOGARITHMIC = 2, KCMA_MU_PROPORTIONAL = 3 };
@@ -57,6 +57,7 @@ enum {
   KCMA_INJ_BDZ = 1, /* lambda x N "BDZ Matrix" (y_i); X is recomputed as m + sigma*y            */
   KCMA_INJ_X = 2,   /* lambda x N "Sample Population" overriding the sampled X                  */
   KCMA_INJ_F = 3,   /* lambda "Value Vector"                                                    */
+  KCMA_INJ_GRAD = 5, /* lambda*N gradients dF/dx of the current population ("Gradients", row-major); with KCMA_INJ_F */
   KCMA_INJ_BD = 4   /* N*N eigenvectors (row-major, columns = vectors) followed by N axis lengths; skips the eigensolver for the NEXT ask */
 };
 
@@ -103,6 +104,11 @@ typedef struct kcma_cfg {
   int32_t rank;                         /* population shard owner, 0 <= rank < nranks             */
   int32_t nranks;                       /* 1 = single GPU                                         */
   int32_t keep_population;              /* 1: materialise "Sample Population" (X) every generation */
+  /* "Use Gradient Information" / "Gradient Step Size" (CMAES.config:43-52, CMAES.cpp.base:82-86,199-200,226-228,611-621):
+     the model also returns dF/dx per sample and the new mean takes a step along the weighted gradients */
+  int32_t use_gradient_information;     /* default 0                                              */
+  int32_t reserved1;
+  double gradient_step_size;            /* default 0.01; must be > 0 when gradients are used      */
 } kcma_cfg;
 
 typedef struct kcma kcma_t;
@@ -156,6 +162,9 @@ typedef void (*kcma_host_objective_fn)(void* user, const double* x, uint64_t row
 typedef void (*kcma_host_constraints_fn)(void* user, const double* x, uint64_t rows, uint64_t n, double* g_out,
                                          uint64_t n_constraints);
 int kcma_set_host_objective(kcma_t* h, kcma_host_objective_fn fn, void* user);
+/* operation "Evaluate With Gradients" (CMAES.cpp.base:199-200,226-228): the model fills F and the rows x n gradients */
+typedef void (*kcma_host_objective_grad_fn)(void* user, const double* x, uint64_t rows, uint64_t n, double* f_out, double* grad_out);
+int kcma_set_host_objective_grad(kcma_t* h, kcma_host_objective_grad_fn fn, void* user);
 int kcma_set_host_constraints(kcma_t* h, kcma_host_constraints_fn fn, void* user);
 
 /* ---- parity hooks ------------------------------------------------------------------- */

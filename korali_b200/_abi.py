@@ -13,7 +13,7 @@ MU_TYPES = {"Linear": 0, "Equal": 1, "Logarithmic": 2, "Proportional": 3}
 OBJECTIVES = {"NegSphere": 0, "NegRosenbrock": 1, "NegAckley": 2, "NegEllipsoid": 3, "NegSumSq": 4,
               "NegSphereSin2": 5, "External": 100}
 CONSTRAINTS = {"None": 0, "HalfSpace": 1, "External": 100}
-INJ_Z, INJ_BDZ, INJ_X, INJ_F, INJ_BD = 0, 1, 2, 3, 4
+INJ_Z, INJ_BDZ, INJ_X, INJ_F, INJ_BD, INJ_GRAD = 0, 1, 2, 3, 4, 5
 
 _dp = C.POINTER(C.c_double)
 
@@ -37,6 +37,7 @@ class KcmaCfg(C.Structure):
         ("lower_bound", _dp), ("upper_bound", _dp), ("initial_value", _dp), ("initial_stddev", _dp),
         ("min_stddev_update", _dp),
         ("device", C.c_int32), ("rank", C.c_int32), ("nranks", C.c_int32), ("keep_population", C.c_int32),
+        ("use_gradient_information", C.c_int32), ("reserved1", C.c_int32), ("gradient_step_size", C.c_double),
     ]
 
 

@@ -16,7 +16,7 @@ EXPORTS = [
     "kcma_cfg_defaults", "kcma_create", "kcma_destroy", "kcma_last_error", "kcma_take_warnings",
     "kcma_comm_unique_id", "kcma_comm_init", "kcma_shard_range",
     "kcma_run_generation", "kcma_ask", "kcma_eval", "kcma_tell", "kcma_check_termination", "kcma_run",
-    "kcma_set_host_objective", "kcma_set_host_constraints", "kcma_inject", "kcma_get_array", "kcma_set_array", "kcma_get_index_array", "kcma_get_scalar", "kcma_set_scalar",
+    "kcma_set_host_objective", "kcma_set_host_objective_grad", "kcma_set_host_constraints", "kcma_inject", "kcma_get_array", "kcma_set_array", "kcma_get_index_array", "kcma_get_scalar", "kcma_set_scalar",
     "kcma_timing_enable", "kcma_timing_get", "kcma_timing_reset", "kcma_launch_count", "kcma_flush_l2",
     "kcma_k_sort_index", "kcma_k_eigen", "kcma_k_sample", "kcma_k_rank_mu", "kcma_k_philox_normal",
     "kcma_k_philox_raw", "kcma_k_objective",
@@ -74,6 +74,18 @@ class Solver(Handle):
             np.ctypeslib.as_array(out, shape=(rows,))[:] = np.asarray(fn(xs), dtype=np.float64)
         self._host_obj = cb_t(tramp)
         self._check(self._fn("set_host_objective", C.c_int, [C.c_void_p, cb_t, C.c_void_p])(self._h, self._host_obj, None))
+
+    def set_host_objective_grad(self, fn):
+        """fn(X: ndarray[rows, n]) -> (F: ndarray[rows], dF/dX: ndarray[rows, n]); needs use_gradient_information=1."""
+        cb_t = C.CFUNCTYPE(None, C.c_void_p, _dp, C.c_uint64, C.c_uint64, _dp, _dp)
+
+        def tramp(_u, x, rows, n, out, gout):
+            xs = np.ctypeslib.as_array(x, shape=(rows, n))
+            f, g = fn(xs)
+            np.ctypeslib.as_array(out, shape=(rows,))[:] = np.asarray(f, dtype=np.float64)
+            np.ctypeslib.as_array(gout, shape=(rows, n))[:] = np.asarray(g, dtype=np.float64).reshape(rows, n)
+        self._host_obj_grad = cb_t(tramp)
+        self._check(self._fn("set_host_objective_grad", C.c_int, [C.c_void_p, cb_t, C.c_void_p])(self._h, self._host_obj_grad, None))
 
     def set_host_constraints(self, fn):
         """fn(X: ndarray[rows, n]) -> ndarray[n_constraints, rows]."""

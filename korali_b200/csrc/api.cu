@@ -72,6 +72,7 @@ struct kcma {
   int* dPerm = nullptr;
   double *dMean = nullptr, *dMeanOld = nullptr, *dMeanUpd = nullptr, *dT = nullptr, *dPs = nullptr, *dPc = nullptr;
   double *dZ = nullptr, *dY = nullptr, *dX = nullptr, *dF = nullptr;
+  double* dGrad = nullptr;   // "Gradients" of the local samples (Use Gradient Information), max_local x ld
   unsigned* dIdx = nullptr;
   void* dSortWs = nullptr;
   double *dW = nullptr, *dSelW = nullptr;
@@ -97,10 +98,12 @@ struct kcma {
   bool scalars_fresh = false;
   bool sampled_pending = false;  // ask done, tell not yet: X uses (mean, sigma); afterwards (mean_old, sigma_sampling)
   // injections
-  bool inj_z = false, inj_bd = false, inj_y = false, inj_x = false, inj_f = false;
+  bool inj_z = false, inj_bd = false, inj_y = false, inj_x = false, inj_f = false, inj_grad = false;
   bool vt_valid = false;
   // batched host conduit
   kcma_host_objective_fn host_obj = nullptr; void* host_obj_user = nullptr;
+  kcma_host_objective_grad_fn host_obj_grad = nullptr;
+  std::vector<double> hGrad;
   kcma_host_constraints_fn host_con = nullptr; void* host_con_user = nullptr;
   std::vector<double> hX, hF, hG;
   // nccl
@@ -653,7 +656,28 @@ int do_ask(kcma* h) {
 
 int do_eval(kcma* h) {
   h->model_evals += h->cur_lambda;  // ref :214
+  const bool want_grad = h->cfg.use_gradient_information != 0;   // operation "Evaluate With Gradients" (:199-200, 226-228)
+  if (want_grad && h->inj_f && !h->inj_grad)
+    return fail(h, "Use Gradient Information: inject the gradients (KCMA_INJ_GRAD) together with the values of an external model");
+  const bool have_grad = h->inj_grad;
+  h->inj_grad = false;
   if (h->inj_f) { h->inj_f = false; return 0; }
+  if (want_grad && h->host_obj_grad) {  // batched host conduit, model returns F and dF/dx
+    PhaseTimer t(h, "host_objective");
+    const size_t ls = local_samples(h), N = h->N;
+    h->hX.resize(ls * N); h->hF.resize(ls); h->hGrad.resize(ls * N);
+    CUDA_OK(h, cudaMemcpy2DAsync(h->hX.data(), sizeof(double) * N, h->dX, sizeof(double) * h->ld, sizeof(double) * N, ls, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    h->host_obj_grad(h->host_obj_user, h->hX.data(), (uint64_t)ls, (uint64_t)N, h->hF.data(), h->hGrad.data());
+    for (size_t i = 0; i < ls; i++)
+      if (!std::isfinite(h->hF[i])) return fail(h, "Non finite value of function evaluation detected: %f\n", h->hF[i]);
+    CUDA_OK(h, cudaMemcpyAsync(h->dF + h->shard_lo, h->hF.data(), sizeof(double) * ls, cudaMemcpyHostToDevice, h->stream));
+    CUDA_OK(h, cudaMemcpy2DAsync(h->dGrad, sizeof(double) * h->ld, h->hGrad.data(), sizeof(double) * N, sizeof(double) * N, ls, cudaMemcpyHostToDevice, h->stream));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    return 0;
+  }
+  if (want_grad && !have_grad && (h->host_obj || h->cfg.objective == KCMA_OBJ_EXTERNAL))
+    return fail(h, "Use Gradient Information: the model must return gradients (kcma_set_host_objective_grad or KCMA_INJ_GRAD)");
   if (h->host_obj) {  // batched host conduit
     PhaseTimer t(h, "host_objective");
     const size_t ls = local_samples(h), N = h->N;
@@ -675,6 +699,11 @@ int do_eval(kcma* h) {
                        h->dSc, h->dCoef, f_local, h->num_sms))
     return fail(h, "unknown objective id %d", h->cfg.objective);
   h->launches++;
+  if (want_grad && !have_grad) {
+    launch_objective_gradient(h->stream, h->cfg.objective, src, h->ld, ls, h->N, h->cfg.mirrored_sampling, h->inj_x ? 1 : 0, h->dMean,
+                              h->dSc, h->dCoef, h->dGrad, h->ld, h->num_sms);
+    h->launches++;
+  }
   h->scalars_fresh = false;
   return 0;
 }
@@ -715,6 +744,10 @@ int do_tell(kcma* h) {
     launch_mean_reduce(h->stream, h->dPartial, h->dCount, h->rows_per_cta, N, ld, mean_new, rows_src, ld, h->cfg.mirrored_sampling, from_x,
                        h->dMean, h->dSc, (unsigned)h->shard_lo, (unsigned)h->shard_hi, best_x);
     h->launches += 4;
+    if (h->cfg.use_gradient_information) {   // :611-621, on this rank's share of the weighted sum
+      launch_gradient_mean(h->stream, h->dGrad, ld, h->dSelS, h->dSelW, h->dCount, N, h->cfg.gradient_step_size, mean_new);
+      h->launches++;
+    }
   }
   int splits;
   {
@@ -812,6 +845,8 @@ void kcma_cfg_defaults(kcma_cfg* c) {
   c->normal_vector_learning_rate = -1.0;
   c->global_success_learning_rate = 0.2;
   c->nranks = 1;
+  c->use_gradient_information = 0;
+  c->gradient_step_size = 0.01;
 }
 
 void kcma_shard_range(uint64_t population, int mirrored, int rank, int nranks, uint64_t* begin, uint64_t* end) {
@@ -848,7 +883,7 @@ void kcma_destroy(kcma_t* h) {
                   h->dPs, h->dPc, h->dZ, h->dY, h->dX, h->dF, h->dIdx, h->dSortWs, h->dW, h->dSelW, h->dSelS, h->dCount, h->dS,
                   h->dPartial, h->dWsplit, h->dRed, h->dBestEver, h->dCurBest, h->dLower, h->dUpper, h->dMinSd, h->dCoef, h->dShift,
                   h->dSigmaSampling, h->dInfeasible, h->dFlush, h->dSc, h->dG, h->dBounds, h->dNormal, h->dCaux, h->dBestCon, h->dU, h->dViol,
-                  h->dIndicator, h->dEvSample, h->dEvCon, h->dVioRows, h->dAttempt};
+                  h->dIndicator, h->dEvSample, h->dEvCon, h->dVioRows, h->dAttempt, h->dGrad};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->hSc) cudaFreeHost(h->hSc);
   if (h->hCount) cudaFreeHost(h->hCount);
@@ -894,6 +929,11 @@ int kcma_create(const kcma_cfg* cfg, kcma_t** out) {
   }
   // ref :26-31
   uint64_t lambda = cfg->population_size, mu = cfg->mu_value, vlambda = cfg->viability_population_size, vmu = cfg->viability_mu_value;
+  if (cfg->use_gradient_information && cfg->gradient_step_size <= 0.) {   // CMAES.cpp.base:86
+    char msg[128];
+    snprintf(msg, sizeof(msg), "Gradient Step Size must be larger than 0.0 (is %f)", cfg->gradient_step_size);
+    CREATE_FAIL(msg);
+  }
   if (lambda <= 1) CREATE_FAIL("'Population Size' must be larger 1.");
   if (mu == 0) mu = lambda / 2;
   if (vmu == 0) vmu = vlambda / 2;
@@ -950,6 +990,7 @@ int kcma_create(const kcma_cfg* cfg, kcma_t** out) {
   CREATE_CUDA(dmalloc(&h->dBestEver, ld)); CREATE_CUDA(dmalloc(&h->dCurBest, ld));
   CREATE_CUDA(dmalloc(&h->dZ, h->max_zrows * ld)); CREATE_CUDA(dmalloc(&h->dY, h->max_zrows * ld));
   CREATE_CUDA(dmalloc(&h->dX, (cfg->keep_population ? h->max_local : 1) * (size_t)ld));
+  if (cfg->use_gradient_information) CREATE_CUDA(dmalloc(&h->dGrad, h->max_local * (size_t)ld));
   CREATE_CUDA(dmalloc(&h->dF, h->s_max)); CREATE_CUDA(dmalloc(&h->dIdx, h->s_max));
   CREATE_CUDA(cudaMalloc(&h->dSortWs, sort_workspace_bytes((int)h->s_max)));
   CREATE_CUDA(dmalloc(&h->dW, h->mu_max));
@@ -1010,6 +1051,13 @@ int kcma_set_host_objective(kcma_t* h, kcma_host_objective_fn fn, void* user) {
   invalidate_graph(h);
   if (fn && !h->cfg.keep_population) return fail(h, "a host objective needs keep_population = 1 (X is copied to the host every generation)");
   h->host_obj = fn; h->host_obj_user = user;
+  return 0;
+}
+int kcma_set_host_objective_grad(kcma_t* h, kcma_host_objective_grad_fn fn, void* user) {
+  invalidate_graph(h);
+  if (fn && !h->cfg.use_gradient_information) return fail(h, "a gradient-returning host objective needs Use Gradient Information");
+  if (fn && !h->cfg.keep_population) return fail(h, "a host objective needs keep_population = 1 (X is copied to the host every generation)");
+  h->host_obj_grad = fn; h->host_obj_user = user;
   return 0;
 }
 int kcma_set_host_constraints(kcma_t* h, kcma_host_constraints_fn fn, void* user) {
@@ -1073,10 +1121,10 @@ void invalidate_graph(kcma* h) {
 // microseconds each per generation): the graph removes the per-launch host cost. KCMA_GRAPH=0 disables it.
 bool graph_eligible(const kcma* h) {
   static const int on = getenv("KCMA_GRAPH") ? atoi(getenv("KCMA_GRAPH")) : 1;
-  if (!on || h->graph_failed || h->timing || h->cfg.nranks > 1 || h->host_obj || h->host_con || h->has_constraints) return false;
+  if (!on || h->graph_failed || h->timing || h->cfg.nranks > 1 || h->host_obj || h->host_obj_grad || h->host_con || h->has_constraints) return false;
   if (h->cfg.objective == KCMA_OBJ_EXTERNAL) return false;
   if (h->has_bounds && h->cfg.max_infeasible_resamplings != 0) return false;
-  if (h->inj_z || h->inj_bd || h->inj_y || h->inj_x || h->inj_f || h->sampled_pending || !h->vt_valid) return false;
+  if (h->inj_z || h->inj_bd || h->inj_y || h->inj_x || h->inj_f || h->inj_grad || h->sampled_pending || !h->vt_valid) return false;
   if (!h->cfg.diagonal_covariance && ((h->N + 3) / 4 + 1) / 2 > h->num_sms) return false;   // eigensolver with a host loop
   return h->gen >= 3;   // the first generations run eagerly (lazy one-time initialisations happen there)
 }
@@ -1220,6 +1268,13 @@ int kcma_inject(kcma_t* h, int kind, const double* src, size_t count) {
       h->inj_f = true;
       return 0;
     }
+    case KCMA_INJ_GRAD: {
+      if (!h->cfg.use_gradient_information) return fail(h, "inject Gradients: Use Gradient Information is off");
+      if (count != h->cur_lambda * N) return fail(h, "inject Gradients: expected %zu values", (size_t)(h->cur_lambda * N));
+      if (upload_rows(h, h->dGrad, src + h->shard_lo * N, local_samples(h))) return 1;
+      h->inj_grad = true;
+      return 0;
+    }
     case KCMA_INJ_BD: {
       if (count != N * N + N) return fail(h, "inject BD: expected N*N+N values");
       if (upload_rows(h, h->dB, src, N)) return 1;
@@ -1296,7 +1351,9 @@ int kcma_get_array(kcma_t* h, const char* key, double* out, size_t cap, size_t* 
     return 0;
   }
   ArrRef r;
-  if (!find_array(h, key, &r)) return fail(h, "unknown array key '%s'", key);
+  if (!strcmp(key, "Gradients") && h->dGrad) {   // LOCAL shard rows, like "Sample Population"
+    r.p = h->dGrad; r.rows = local_samples(h); r.cols = N; r.ld = h->ld;
+  } else if (!find_array(h, key, &r)) return fail(h, "unknown array key '%s'", key);
   const size_t n = r.rows * r.cols;
   if (count) *count = n;
   if (!out) return 0;

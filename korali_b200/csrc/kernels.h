@@ -54,6 +54,10 @@ void launch_gather_mean(cudaStream_t st, const double* Y, int ldy, int mirrored,
 void launch_mean_reduce(cudaStream_t st, const double* partial, const int* count_ptr, int rows_per_cta, int n, int ld,
                         double* mean_out, const double* Y, int ldy, int mirrored, int from_x, const double* mean,
                         const DevScalars* sc, unsigned lo, unsigned hi, double* best_x);
+void launch_objective_gradient(cudaStream_t st, int objective, const double* Y, int ldy, long long samples, int n, int mirrored, int from_x,
+                               const double* mean, const DevScalars* sc, const double* coef, double* G, int ldg, int num_sms);
+void launch_gradient_mean(cudaStream_t st, const double* G, int ldg, const int* sel_sample, const double* sel_weight, const int* count_ptr,
+                          int n, double step, double* mean_new);
 void launch_best_update(cudaStream_t st, const double* best_x, int n, unsigned generation, double* cur_best_vars,
                         double* best_ever_vars, DevScalars* sc, const double* con_evals, long long ldg, int n_con,
                         double* best_con_evals);

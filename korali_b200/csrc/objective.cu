@@ -95,6 +95,56 @@ objective_kernel(const double* __restrict__ Y, int ldy, long long samples, int n
   }
 }
 
+// dF/dx of the built-in objectives for every sample ("Evaluate With Gradients", CMAES.cpp.base:199-200,226-228: the
+// reference reads sample["Gradient"] from the user model, examples/optimization/stochastic/_model/model.py:10-63).
+// One warp per sample; same formulas as oracle/okcma.c objective_gradient_one.
+__global__ void __launch_bounds__(256)
+objective_gradient_kernel(int objective, const double* __restrict__ Y, int ldy, long long samples, int n, int mirrored, int from_x,
+                          const double* __restrict__ mean, const DevScalars* __restrict__ sc, const double* __restrict__ coef,
+                          double* __restrict__ G, int ldg) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const double sigma = sc->sigma;
+  for (long long s = warp; s < samples; s += nwarps) {
+    XRow x;
+    x.from_x = from_x != 0;
+    x.mean = mean;
+    if (from_x) { x.y = Y + (size_t)s * ldy; x.ssigma = sigma; }
+    else if (mirrored) { x.y = Y + (size_t)(s >> 1) * ldy; x.ssigma = (s & 1) ? -sigma : sigma; }
+    else { x.y = Y + (size_t)s * ldy; x.ssigma = sigma; }
+    double* g = G + (size_t)s * ldg;
+    double e1 = 0.0, e2 = 0.0, r = 0.0;
+    const double c = 2.0 * 3.14159265358979323846;
+    if (objective == KCMA_OBJ_NEG_ACKLEY) {
+      double s1 = 0.0, s2 = 0.0;
+      for (int i = lane; i < n; i += 32) { const double v = x(i); s1 += v * v; s2 += cos(c * v); }
+      s1 = warp_sum_butterfly(s1); s2 = warp_sum_butterfly(s2);
+      r = sqrt(s1 / (double)n);
+      e1 = 20.0 * exp(-0.2 * r); e2 = exp(s2 / (double)n);
+    }
+    for (int i = lane; i < n; i += 32) {
+      const double v = x(i);
+      double d;
+      switch (objective) {
+        case KCMA_OBJ_NEG_SPHERE: d = -v; break;
+        case KCMA_OBJ_NEG_SUMSQ: d = -2.0 * v; break;
+        case KCMA_OBJ_NEG_ELLIPSOID: d = -2.0 * coef[i] * v; break;
+        case KCMA_OBJ_NEG_ROSENBROCK: {
+          double a = 0.0;
+          if (i + 1 < n) a += -400.0 * v * (x(i + 1) - v * v) - 2.0 * (1.0 - v);
+          if (i > 0) { const double w = x(i - 1); a += 200.0 * (v - w * w); }
+          d = -a;
+          break;
+        }
+        case KCMA_OBJ_NEG_ACKLEY: d = (r > 0.0 ? e1 * (-0.2) * v / ((double)n * r) : 0.0) + e2 * (-c * sin(c * v)) / (double)n; break;
+        default: d = -(2.0 * v + 2.0 * sin(v) * cos(v)); break;   // KCMA_OBJ_NEG_SPHERE_SIN2
+      }
+      g[i] = d;
+    }
+  }
+}
+
 // isSampleFeasible (optimizer.cpp.base:5-14) for every sample + optional materialisation of X ("Sample Population").
 __global__ void __launch_bounds__(256)
 feasibility_kernel(const double* __restrict__ Y, int ldy, long long samples, int n, int mirrored,
@@ -165,6 +215,12 @@ int launch_objective(cudaStream_t st, int objective, const double* Y, int ldy, l
   }
 #undef LAUNCH
   return 0;
+}
+
+void launch_objective_gradient(cudaStream_t st, int objective, const double* Y, int ldy, long long samples, int n, int mirrored, int from_x,
+                               const double* mean, const DevScalars* sc, const double* coef, double* G, int ldg, int num_sms) {
+  if (samples <= 0) return;
+  objective_gradient_kernel<<<grid_for_warps(samples, num_sms), 256, 0, st>>>(objective, Y, ldy, samples, n, mirrored, from_x, mean, sc, coef, G, ldg);
 }
 
 void launch_feasibility(cudaStream_t st, const double* Y, int ldy, long long samples, int n, int mirrored, const double* mean,

@@ -427,6 +427,24 @@ void launch_mean_reduce(cudaStream_t st, const double* partial, const int* count
   mean_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(partial, count_ptr, rows_per_cta, n, ld, mean_out, Y, ldy, mirrored, from_x,
                                                       mean, sc, lo, hi, best_x);
 }
+// "Use Gradient Information" (CMAES.cpp.base:611-621): mean[d] += sum_i w_i * step / sqrt(N) * gradient[sel_i][d] over the selected
+// samples this rank owns (the partial means are summed by the all-reduce). One thread per dimension, ranks in order.
+__global__ void __launch_bounds__(256)
+gradient_mean_kernel(const double* __restrict__ G, int ldg, const int* __restrict__ sel_sample, const double* __restrict__ sel_weight,
+                     const int* __restrict__ count_ptr, int n, double step, double* __restrict__ mean_new) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= n) return;
+  const int count = *count_ptr;
+  const double scale = 1.0 / sqrt((double)n);
+  double m = mean_new[d];
+  for (int i = 0; i < count; i++) m += sel_weight[i] * step * scale * G[(size_t)sel_sample[i] * ldg + d];
+  mean_new[d] = m;
+}
+void launch_gradient_mean(cudaStream_t st, const double* G, int ldg, const int* sel_sample, const double* sel_weight, const int* count_ptr,
+                          int n, double step, double* mean_new) {
+  gradient_mean_kernel<<<(n + 255) / 256, 256, 0, st>>>(G, ldg, sel_sample, sel_weight, count_ptr, n, step, mean_new);
+}
+
 void launch_best_update(cudaStream_t st, const double* best_x, int n, unsigned generation, double* cur_best_vars,
                         double* best_ever_vars, DevScalars* sc, const double* con_evals, long long ldg, int n_con,
                         double* best_con_evals) {

@@ -234,8 +234,8 @@ class CMAES {
     else korali_error("Invalid setting of Mu Type (%s) (Linear, Equal, Logarithmic, or Proportional accepted).", mu_type.c_str());
     cfg.initial_sigma_cumulation_factor = s.num("Initial Sigma Cumulation Factor", -1.0);
     cfg.initial_damp_factor = s.num("Initial Damp Factor", -1.0);
-    if (s.boolean("Use Gradient Information", 0)) korali_error("'Use Gradient Information' is not part of the B200 CMA-ES path yet (SURVEY.md 8f-2)\n");
-    s.num("Gradient Step Size", 0.01);
+    cfg.use_gradient_information = s.boolean("Use Gradient Information", 0);
+    cfg.gradient_step_size = s.num("Gradient Step Size", 0.01);
     cfg.is_sigma_bounded = s.boolean("Is Sigma Bounded", 0);
     cfg.initial_cumulative_covariance = s.num("Initial Cumulative Covariance", -1.0);
     cfg.diagonal_covariance = s.boolean("Diagonal Covariance", 0);
@@ -381,6 +381,32 @@ class CMAES {
       for (uint64_t i = 0; i < rows; i++) f_out[i] = NAN;
     }
   }
+  // operation "Evaluate With Gradients" (CMAES.cpp.base:199-200, 226-228): the model sets "F(x)" and "Gradient"
+  static void host_objective_grad(void* user, const double* x, uint64_t rows, uint64_t n, double* f_out, double* grad_out) {
+    CMAES* self = (CMAES*)user;
+    try {
+      for (uint64_t i = 0; i < rows; i++) {
+        py::dict sample;
+        py::list params;
+        for (uint64_t d = 0; d < n; d++) params.append(x[i * n + d]);
+        sample["Parameters"] = params;
+        sample["Sample Id"] = i;
+        sample["Module"] = "Problem";
+        sample["Operation"] = "Evaluate With Gradients";
+        self->objective(sample);
+        if (!sample.contains("F(x)")) korali_error("The model did not set 'F(x)' for sample %zu\n", (size_t)i);
+        if (!sample.contains("Gradient")) korali_error("The model did not set 'Gradient' for sample %zu ('Use Gradient Information' is on)\n", (size_t)i);
+        f_out[i] = sample["F(x)"].cast<double>();
+        py::sequence grad = sample["Gradient"].cast<py::sequence>();
+        if ((uint64_t)py::len(grad) != n) korali_error("'Gradient' of sample %zu has %zu entries, expected %zu\n", (size_t)i, (size_t)py::len(grad), (size_t)n);
+        for (uint64_t d = 0; d < n; d++) grad_out[i * n + d] = grad[d].cast<double>();
+      }
+    } catch (const std::exception& e) {
+      self->pending_error = e.what();
+      for (uint64_t i = 0; i < rows; i++) f_out[i] = NAN;
+      for (uint64_t i = 0; i < rows * n; i++) grad_out[i] = 0.0;
+    }
+  }
   static void host_constraints(void* user, const double* x, uint64_t rows, uint64_t n, double* g_out, uint64_t nc) {
     CMAES* self = (CMAES*)user;
     try {
@@ -406,7 +432,10 @@ class CMAES {
   void initialize(int device) {
     cfg.device = device;
     if (kcma_create(&cfg, &h)) korali_error("%s", kcma_last_error(nullptr));
-    if (cfg.objective == KCMA_OBJ_EXTERNAL) check(kcma_set_host_objective(h, &CMAES::host_objective, this));
+    if (cfg.objective == KCMA_OBJ_EXTERNAL) {
+      if (cfg.use_gradient_information) check(kcma_set_host_objective_grad(h, &CMAES::host_objective_grad, this));
+      else check(kcma_set_host_objective(h, &CMAES::host_objective, this));
+    }
     if (!constraints.empty()) check(kcma_set_host_constraints(h, &CMAES::host_constraints, this));
     check(kcma_set_scalar(h, "Termination Criteria/Max Condition Covariance Matrix", tc_max_condition));
     check(kcma_set_scalar(h, "Termination Criteria/Min Standard Deviation", tc_min_sd));
@@ -472,8 +501,8 @@ class CMAES {
     js["Mu Type"] = mu_type;
     js["Initial Sigma Cumulation Factor"] = cfg.initial_sigma_cumulation_factor;
     js["Initial Damp Factor"] = cfg.initial_damp_factor;
-    js["Use Gradient Information"] = 0;
-    js["Gradient Step Size"] = (double)0.01f;
+    js["Use Gradient Information"] = cfg.use_gradient_information;
+    js["Gradient Step Size"] = cfg.gradient_step_size;
     js["Is Sigma Bounded"] = cfg.is_sigma_bounded;
     js["Initial Cumulative Covariance"] = cfg.initial_cumulative_covariance;
     js["Diagonal Covariance"] = cfg.diagonal_covariance;

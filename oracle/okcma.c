@@ -199,6 +199,43 @@ static double objective_one(int objective, uint64_t n, const double* x, const do
   }
 }
 
+/* dF/dx of the built-in objectives (the reference takes it from the user model: sample["Gradient"],
+ * examples/optimization/stochastic/_model/model.py:10-63). */
+static void objective_gradient_one(int objective, uint64_t n, const double* x, const double* coef, double* g) {
+  switch (objective) {
+    case KCMA_OBJ_NEG_SPHERE: for (uint64_t i = 0; i < n; i++) g[i] = -x[i]; return;
+    case KCMA_OBJ_NEG_SUMSQ: for (uint64_t i = 0; i < n; i++) g[i] = -2.0 * x[i]; return;
+    case KCMA_OBJ_NEG_ELLIPSOID: for (uint64_t i = 0; i < n; i++) g[i] = -2.0 * coef[i] * x[i]; return;
+    case KCMA_OBJ_NEG_ROSENBROCK:
+      for (uint64_t i = 0; i < n; i++) {
+        double d = 0.0;
+        if (i + 1 < n) d += -400.0 * x[i] * (x[i + 1] - x[i] * x[i]) - 2.0 * (1.0 - x[i]);
+        if (i > 0) d += 200.0 * (x[i] - x[i - 1] * x[i - 1]);
+        g[i] = -d;
+      }
+      return;
+    case KCMA_OBJ_NEG_ACKLEY: {
+      const double c = 2.0 * M_PI;
+      double s1 = 0.0, s2 = 0.0;
+      for (uint64_t i = 0; i < n; i++) { s1 += x[i] * x[i]; s2 += cos(c * x[i]); }
+      const double r = sqrt(s1 / (double)n);
+      const double e1 = 20.0 * exp(-0.2 * r), e2 = exp(s2 / (double)n);
+      for (uint64_t i = 0; i < n; i++) {
+        const double a = r > 0.0 ? e1 * (-0.2) * x[i] / ((double)n * r) : 0.0;
+        const double b = e2 * (-c * sin(c * x[i])) / (double)n;
+        g[i] = a + b;
+      }
+      return;
+    }
+    case KCMA_OBJ_NEG_SPHERE_SIN2: for (uint64_t i = 0; i < n; i++) g[i] = -(2.0 * x[i] + 2.0 * sin(x[i]) * cos(x[i])); return;
+    default: for (uint64_t i = 0; i < n; i++) g[i] = NAN;
+  }
+}
+
+void okcma_objective_gradient(int objective, uint64_t n, uint64_t rows, const double* x, const double* coef, double* g_out) {
+  for (uint64_t i = 0; i < rows; i++) objective_gradient_one(objective, n, x + i * n, coef, g_out + i * n);
+}
+
 void okcma_objective(int objective, uint64_t n, uint64_t rows, const double* x, const double* coef, double* f_out) {
   for (uint64_t i = 0; i < rows; i++) f_out[i] = objective_one(objective, n, x + i * n, coef);
 }
@@ -489,6 +526,7 @@ struct okcma {
   double *inj_z; uint64_t inj_z_rows, inj_z_used; int have_inj_z;
   int have_inj_bd;
   int have_inj_f;
+  double* gradients; int have_inj_grad;   /* _gradients (CMAES.cpp.base:82-86), lambda x N */
   int skip_sampling; /* BDZ or X injected for this generation */
   /* callbacks */
   okcma_objective_fn obj_fn; void* obj_user;
@@ -542,6 +580,8 @@ void okcma_cfg_defaults(kcma_cfg* c) {
   c->normal_vector_learning_rate = -1.0;
   c->global_success_learning_rate = 0.2;
   c->nranks = 1;
+  c->use_gradient_information = 0;
+  c->gradient_step_size = 0.01;
 }
 
 static double* dalloc(size_t n) { return (double*)calloc(n ? n : 1, sizeof(double)); }
@@ -648,6 +688,9 @@ int okcma_create(const kcma_cfg* cfg, okcma_t** out) {
   h->optimizer_previous_best_value = 0.0;
 
   uint64_t lambda = cfg->population_size, mu = cfg->mu_value, vlambda = cfg->viability_population_size, vmu = cfg->viability_mu_value;
+  if (cfg->use_gradient_information && cfg->gradient_step_size <= 0.) { /* ref :86 */
+    fail(NULL, "Gradient Step Size must be larger than 0.0 (is %f)", cfg->gradient_step_size); goto bad;
+  }
   if (lambda == 1) { fail(NULL, "'Population Size' must be larger 1."); goto bad; }
   if (lambda == 0) { fail(NULL, "'Population Size' must be larger 1."); goto bad; }
   if (mu == 0) mu = lambda / 2;
@@ -662,6 +705,7 @@ int okcma_create(const kcma_cfg* cfg, okcma_t** out) {
   else { h->cur_lambda = lambda; h->cur_mu = mu; }
 
   h->X = dalloc(h->s_max * N); h->BDZ = dalloc(h->s_max * N); h->aux_bdz = dalloc(N);
+  if (h->cfg.use_gradient_information) h->gradients = dalloc(h->s_max * N); /* ref :82-85 */
   h->value_vector = dalloc(h->s_max);
   h->sorting_index = (uint64_t*)calloc(h->s_max, sizeof(uint64_t));
   h->C = dalloc(N * N); h->C_aux = dalloc(N * N); h->B = dalloc(N * N); h->B_aux = dalloc(N * N);
@@ -734,7 +778,7 @@ void okcma_destroy(okcma_t* h) {
   free(h->D); free(h->D_aux); free(h->mean); free(h->mean_old); free(h->mean_update); free(h->pc); free(h->ps);
   free(h->best_ever_variables); free(h->current_best_variables); free(h->viability_boundaries);
   free(h->violation_counts); free(h->con_evals); free(h->viability_indicator); free(h->normal_approx);
-  free(h->best_con_evals); free(h->philox_attempt); free(h->inj_z);
+  free(h->best_con_evals); free(h->philox_attempt); free(h->inj_z); free(h->gradients);
   free(h);
 }
 
@@ -1080,6 +1124,11 @@ static int update_distribution(okcma_t* h) {
     h->mean[d] = 0.;
     for (uint64_t i = 0; i < h->cur_mu; ++i) h->mean[d] += h->mu_weights[i] * h->X[h->sorting_index[i] * N + d];
   }
+  if (h->cfg.use_gradient_information) { /* ref :611-621 (l2update is computed there but never used) */
+    for (uint64_t d = 0; d < N; ++d)
+      for (uint64_t i = 0; i < h->cur_mu; ++i)
+        h->mean[d] += h->mu_weights[i] * h->cfg.gradient_step_size / sqrt((double)N) * h->gradients[h->sorting_index[i] * N + d];
+  }
   for (uint64_t d = 0; d < N; ++d) h->mean_update[d] = (h->mean[d] - h->mean_old[d]) / h->sigma;
 
   for (uint64_t d = 0; d < N; ++d) {
@@ -1135,6 +1184,12 @@ int okcma_ask(okcma_t* h) {
 int okcma_eval(okcma_t* h) {
   const uint64_t N = h->N;
   h->model_evaluation_count += h->cur_lambda; /* ref :214 */
+  if (h->cfg.use_gradient_information && !h->have_inj_grad) { /* ref :199-200, 226-228: "Evaluate With Gradients" */
+    if (h->obj_fn || h->have_inj_f)
+      return fail(h, "Use Gradient Information: inject the gradients (KCMA_INJ_GRAD) together with the values of an external model");
+    for (uint64_t i = 0; i < h->cur_lambda; i++) objective_gradient_one(h->cfg.objective, N, h->X + i * N, h->obj_coef, h->gradients + i * N);
+  }
+  h->have_inj_grad = 0;
   if (h->have_inj_f) { h->have_inj_f = 0; return 0; }
   for (uint64_t i = 0; i < h->cur_lambda; i++) {
     double f;
@@ -1222,6 +1277,12 @@ int okcma_inject(okcma_t* h, int kind, const double* src, size_t count) {
       memcpy(h->value_vector, src, sizeof(double) * count);
       h->have_inj_f = 1;
       return 0;
+    case KCMA_INJ_GRAD:
+      if (!h->cfg.use_gradient_information) return fail(h, "inject Gradients: Use Gradient Information is off");
+      if (count != h->cur_lambda * N) return fail(h, "inject Gradients: expected %zu values", (size_t)(h->cur_lambda * N));
+      memcpy(h->gradients, src, sizeof(double) * count);
+      h->have_inj_grad = 1;
+      return 0;
     case KCMA_INJ_BD:
       if (count != N * N + N) return fail(h, "inject BD: expected N*N+N values");
       memcpy(h->B, src, sizeof(double) * N * N);
@@ -1253,6 +1314,7 @@ static int find_array(okcma_t* h, const char* key, arr_ref* r) {
   A("Mu Weights", h->mu_weights, h->cur_mu)
   A("Value Vector", h->value_vector, h->cur_lambda)
   A("BDZ Matrix", h->BDZ, h->cur_lambda * N)
+  if (h->gradients) { A("Gradients", h->gradients, h->cur_lambda * N) }
   A("Sample Population", h->X, h->cur_lambda * N)
   A("Best Ever Variables", h->best_ever_variables, N)
   A("Current Best Variables", h->current_best_variables, N)

@@ -62,6 +62,7 @@ void okcma_rank_mu(uint64_t n, uint64_t rows, const double* t, const double* w, 
 void okcma_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 void okcma_philox_normal(uint64_t seed, uint64_t generation, uint64_t row_begin, uint64_t rows, uint64_t n, double* z_out);
 void okcma_objective(int objective, uint64_t n, uint64_t rows, const double* x, const double* coef, double* f_out);
+void okcma_objective_gradient(int objective, uint64_t n, uint64_t rows, const double* x, const double* coef, double* g_out);
 /* gsl_rng_mt19937 seeded like gsl_rng_set(seed), `count` draws of gsl_ran_gaussian(rng, 1.0). */
 void okcma_mt19937_gaussian(uint64_t seed, uint64_t skip, uint64_t count, double* out);
 

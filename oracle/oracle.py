@@ -120,6 +120,20 @@ def objective(obj, x, coef=None):
     return f
 
 
+def objective_gradient(obj, x, coef=None):
+    from korali_b200._abi import OBJECTIVES
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    rows, n = x.shape
+    if coef is None:
+        coef = 10.0 ** (6.0 * np.arange(n) / max(n - 1, 1))
+    coef = np.ascontiguousarray(coef, dtype=np.float64)
+    g = np.empty((rows, n))
+    fn = lib().okcma_objective_gradient
+    fn.restype, fn.argtypes = None, [C.c_int, C.c_uint64, C.c_uint64, _dp, _dp, _dp]
+    fn(OBJECTIVES[obj] if isinstance(obj, str) else obj, n, rows, _as_dp(x), _as_dp(coef), _as_dp(g))
+    return g
+
+
 def mt19937_gaussian(seed, count, skip=0):
     out = np.empty(count)
     fn = lib().okcma_mt19937_gaussian

@@ -86,3 +86,15 @@ def negative_rosenbrock(p):  # examples/optimization/stochastic/_model/model.py:
     for i in range(len(x) - 1):
         res += 100 * (x[i + 1] - x[i]**2)**2 + (1 - x[i])**2
     p["F(x)"] = -res
+
+
+def negative_sphere(p):      # examples/optimization/stochastic/_model/model.py:10-20 (sets "Gradient")
+    x = p["Parameters"]
+    dim = len(x)
+    res = 0.
+    grad = [0.] * dim
+    for i in range(dim):
+        res += x[i]**2
+        grad[i] = -x[i]
+    p["F(x)"] = -0.5 * res
+    p["Gradient"] = grad

@@ -9,7 +9,7 @@ import pytest
 import torch
 from conftest import relerr
 from korali_b200 import _lib
-from korali_b200._abi import INJ_BD, INJ_BDZ, INJ_F, INJ_X, INJ_Z, KcmaError
+from korali_b200._abi import INJ_BD, INJ_BDZ, INJ_F, INJ_GRAD, INJ_X, INJ_Z, KcmaError
 from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -391,6 +391,62 @@ def test_graph_replay_is_bit_identical_to_eager_launches(case):
         b.ask(); b.eval(); b.tell()
     assert np.array_equal(a.get("Covariance Matrix"), b.get("Covariance Matrix")) and a.scalar("Sigma") == b.scalar("Sigma")
     a.close(); b.close()
+
+
+# ---------------------------------------------------------------- Use Gradient Information ------------------
+@pytest.mark.parametrize("case", [
+    dict(n=10, population_size=32, objective="NegSphere", initial_value=2.0, initial_stddev=1.5, gradient_step_size=0.01),
+    dict(n=24, population_size=48, objective="NegRosenbrock", initial_value=0.2, initial_stddev=0.4, gradient_step_size=2e-6),
+    dict(n=30, population_size=64, objective="NegEllipsoid", initial_value=1.0, initial_stddev=1.0, gradient_step_size=1e-8, mirrored_sampling=1),
+    dict(n=16, population_size=40, objective="NegAckley", initial_value=1.0, initial_stddev=2.0, gradient_step_size=0.05),
+    dict(n=12, population_size=24, objective="NegSphereSin2", initial_value=1.0, initial_stddev=1.0, gradient_step_size=0.02, mu_type="Linear"),
+], ids=lambda c: c["objective"])
+def test_gradient_information_lockstep_against_oracle(case):
+    """"Use Gradient Information" (CMAES.cpp.base:611-621): device gradients of the built-in objectives and the gradient step
+    of the mean against the oracle, in lockstep (same B, D, y, X injected)."""
+    o = O.Oracle(seed=21, use_gradient_information=1, **case)
+    s = _lib.Solver(seed=21, keep_population=1, use_gradient_information=1, **case)
+    o.set_scalar("Oracle/RNG Kind", 1)
+    n, lam = case["n"], case["population_size"]
+    for g in range(12):
+        o.ask()
+        s.inject(INJ_BD, np.concatenate([o.get("Covariance Eigenvector Matrix"), o.get("Axis Lengths")]))
+        s.inject(INJ_BDZ, o.get("BDZ Matrix"))
+        s.ask()
+        s.inject(INJ_X, o.get("Sample Population"))
+        o.eval(); s.eval()
+        go, gs = o.get("Gradients").reshape(lam, n), s.get("Gradients").reshape(lam, n)
+        assert np.abs(gs - go).max() <= 1e-12 * np.abs(go).max(), g
+        s.inject(INJ_F, o.get("Value Vector")); s.inject(INJ_GRAD, go)   # keep ranking and gradients in lockstep
+        s.set_scalar("Model Evaluation Count", s.scalar("Model Evaluation Count") - lam)
+        s.eval()
+        o.tell(); s.tell()
+        assert np.array_equal(s.get_index("Sorting Index"), o.get_index("Sorting Index")), g
+        for k in ["Current Mean", "Mean Update", "Evolution Path", "Conjugate Evolution Path", "Covariance Matrix"]:
+            assert relerr(s.get(k), o.get(k)) < 1e-11, (g, k, relerr(s.get(k), o.get(k)))
+        assert abs(s.scalar("Sigma") - o.scalar("Sigma")) <= 1e-11 * o.scalar("Sigma")
+
+
+def test_gradient_information_host_callback_injection_and_errors():
+    case = dict(n=8, population_size=16, objective="External", initial_value=1.0, initial_stddev=0.7, seed=4, keep_population=1,
+                use_gradient_information=1, gradient_step_size=0.01)
+    a = _lib.Solver(**case)
+    a.set_host_objective_grad(lambda x: (-0.5 * (x**2).sum(1), -x))
+    b = _lib.Solver(**{**case, "objective": "NegSphere"})
+    for g in range(20):
+        a.run_generation(); b.run_generation()
+    assert relerr(a.get("Current Mean"), b.get("Current Mean")) < 1e-10 and abs(a.scalar("Sigma") - b.scalar("Sigma")) < 1e-10 * b.scalar("Sigma")
+    c = _lib.Solver(**case)
+    c.ask()
+    x = c.get("Sample Population").reshape(16, 8)
+    c.inject(INJ_F, -0.5 * (x**2).sum(1))
+    with pytest.raises(KcmaError, match="inject the gradients"):
+        c.eval()
+    with pytest.raises(KcmaError, match="Gradient Step Size must be larger than 0.0"):
+        _lib.Solver(**{**case, "gradient_step_size": 0.0})
+    with pytest.raises(KcmaError, match="Use Gradient Information is off"):
+        d = _lib.Solver(n=4, population_size=8, objective="NegSphere", initial_value=1.0, initial_stddev=1.0)
+        d.ask(); d.inject(INJ_GRAD, np.zeros(32))
 
 
 def _constrained_problem(n):

@@ -330,3 +330,72 @@ def test_python_model_matches_device_objective():
         korali.Engine().run(e)
         res.append((e["Solver"]["Best Ever Value"], e["Solver"]["Sigma"]))
     assert abs(res[0][0] - res[1][0]) <= 1e-9 * abs(res[1][0]) and abs(res[0][1] - res[1][1]) <= 1e-9 * res[1][1]
+
+
+# ---------------------------------------------------------------- Use Gradient Information ------------------
+@pytest.mark.gpu
+def test_run_cmaes_gradient_example():
+    """examples/optimization/stochastic/run-cmaes-gradient.py, unchanged apart from the import and the output switches:
+    10-D negative sphere whose model also returns "Gradient" (operation "Evaluate With Gradients")."""
+    import math
+    runs = {}
+    for use_grad, obj in ((True, negative_sphere), (False, negative_sphere), (True, "Sphere")):
+        e = korali.Experiment()
+        e["Random Seed"] = 0xC0FEE
+        e["Problem"]["Type"] = "Optimization"
+        e["Problem"]["Objective Function"] = obj
+        dim = 10
+        for i in range(dim):
+            e["Variables"][i]["Name"] = "X" + str(i)
+            e["Variables"][i]["Lower Bound"] = -25.0
+            e["Variables"][i]["Upper Bound"] = +25.0
+            e["Variables"][i]["Initial Standard Deviation"] = 15.0 / math.sqrt(dim)
+        e["Solver"]["Type"] = "Optimizer/CMAES"
+        e["Solver"]["Population Size"] = 32
+        e["Solver"]["Use Gradient Information"] = use_grad
+        e["Solver"]["Termination Criteria"]["Min Value Difference Threshold"] = 1e-32
+        e["Solver"]["Termination Criteria"]["Max Generations"] = 100
+        e["Console Output"]["Verbosity"] = "Silent"
+        e["File Output"]["Enabled"] = False
+        korali.Engine().run(e)
+        runs[(use_grad, obj if isinstance(obj, str) else "python")] = (e["Solver"]["Best Ever Value"], e["Solver"]["Current Mean"], e["Current Generation"])
+        assert e["Solver"]["Use Gradient Information"] == (1 if use_grad else 0) and e["Solver"]["Gradient Step Size"] == 0.01
+    with_grad, without, device = runs[(True, "python")], runs[(False, "python")], runs[(True, "Sphere")]
+    assert with_grad[2] == without[2] == 100
+    assert abs(with_grad[0]) < 1e-6 and abs(without[0]) < 1e-6        # both converge to the optimum 0 at x = 0
+    assert not np.allclose(with_grad[1], without[1], rtol=1e-6, atol=0)   # the gradient step changes the trajectory
+    # the Python model (gradients through the host conduit) and the device objective (analytic gradients) agree
+    assert abs(with_grad[0] - device[0]) <= 1e-9 * max(abs(device[0]), 1e-300) + 1e-300
+    assert np.allclose(with_grad[1], device[1], rtol=1e-9, atol=1e-300)
+
+
+@pytest.mark.gpu
+def test_gradient_information_errors():
+    e = korali.Experiment()
+    e["Problem"]["Type"] = "Optimization"
+    e["Problem"]["Objective Function"] = evalmodel          # returns no "Gradient"
+    e["Variables"][0]["Name"] = "X"
+    e["Variables"][0]["Lower Bound"] = -10.0
+    e["Variables"][0]["Upper Bound"] = +10.0
+    e["Solver"]["Type"] = "Optimizer/CMAES"
+    e["Solver"]["Population Size"] = 8
+    e["Solver"]["Use Gradient Information"] = True
+    e["Solver"]["Termination Criteria"]["Max Generations"] = 5
+    e["Console Output"]["Verbosity"] = "Silent"
+    e["File Output"]["Enabled"] = False
+    with pytest.raises(RuntimeError, match="did not set 'Gradient'"):
+        korali.Engine().run(e)
+    e2 = korali.Experiment()
+    e2["Problem"]["Type"] = "Optimization"
+    e2["Problem"]["Objective Function"] = negative_sphere
+    e2["Variables"][0]["Name"] = "X"
+    e2["Variables"][0]["Lower Bound"] = -10.0
+    e2["Variables"][0]["Upper Bound"] = +10.0
+    e2["Solver"]["Type"] = "Optimizer/CMAES"
+    e2["Solver"]["Population Size"] = 8
+    e2["Solver"]["Use Gradient Information"] = True
+    e2["Solver"]["Gradient Step Size"] = -1.0
+    e2["Console Output"]["Verbosity"] = "Silent"
+    e2["File Output"]["Enabled"] = False
+    with pytest.raises(RuntimeError, match="Gradient Step Size must be larger than 0.0"):
+        korali.Engine().run(e2)

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 from oracle import oracle as O
 from conftest import relerr
-from korali_b200._abi import INJ_BD, INJ_F, INJ_X, INJ_BDZ
+from korali_b200._abi import INJ_BD, INJ_F, INJ_X, INJ_BDZ, INJ_GRAD, KcmaError
 
 N, LAM, MU = 10, 32, 16
 
@@ -134,3 +134,70 @@ def test_philox_normals_are_standard_normal():
     z2 = O.philox_normal(1337, 1, 0, 8, 7)
     z3 = O.philox_normal(1337, 1, 0, 8, 8)
     assert np.array_equal(z2, z3[:, :7])
+
+
+# ---------------------------------------------------------------- Use Gradient Information ------------------
+@pytest.mark.parametrize("obj", ["NegSphere", "NegSumSq", "NegEllipsoid", "NegRosenbrock", "NegAckley", "NegSphereSin2"])
+def test_builtin_objective_gradients_match_finite_differences(obj):
+    """The analytic dF/dx the built-in objectives hand to the gradient path (the reference takes them from the user model,
+    examples/optimization/stochastic/_model/model.py:10-63) against central differences of the objective itself."""
+    rng = np.random.default_rng(4)
+    n = 7
+    x = rng.standard_normal((5, n)) * 0.7 + 0.3
+    coef = 10.0 ** (2.0 * np.arange(n) / (n - 1))
+    g = O.objective_gradient(obj, x, coef)
+    h = 1e-6
+    for d in range(n):
+        e = np.zeros(n); e[d] = h
+        fd = (O.objective(obj, x + e, coef) - O.objective(obj, x - e, coef)) / (2 * h)
+        assert np.abs(g[:, d] - fd).max() < 1e-6 * max(1.0, np.abs(fd).max()), (obj, d)
+    if obj == "NegRosenbrock":   # the reference's own formula (model.py:23-34)
+        ref = np.zeros_like(x)
+        for i in range(n - 1):
+            ref[:, i] += 2. * (1 - x[:, i]) + 200. * (x[:, i + 1] - x[:, i]**2) * 2 * x[:, i]
+            ref[:, i + 1] -= 200. * (x[:, i + 1] - x[:, i]**2)
+        assert np.abs(g - ref).max() < 1e-12 * np.abs(ref).max()
+
+
+def test_gradient_step_of_the_mean_follows_the_reference_loop():
+    """CMAES.cpp.base:603-621: weighted mean, then mean[d] += sum_i w_i * step / sqrt(N) * gradient[sorted_i][d]."""
+    # (the reference's step is not normalised: Rosenbrock gradients of ~1e4 need a tiny step size or the mean runs away)
+    case = dict(n=6, population_size=16, objective="NegRosenbrock", initial_value=0.3, initial_stddev=0.8, seed=5)
+    a = O.Oracle(use_gradient_information=1, gradient_step_size=2e-5, **case)
+    for g in range(6):
+        a.ask(); a.eval()
+        x = a.get("Sample Population").reshape(16, 6)
+        grads = a.get("Gradients").reshape(16, 6)
+        assert np.array_equal(grads, O.objective_gradient("NegRosenbrock", x))
+        a.tell()
+        idx = a.get_index("Sorting Index").astype(int)
+        w = a.get("Mu Weights")
+        want = np.zeros(6)
+        for d in range(6):
+            m = 0.0
+            for i in range(len(w)):
+                m += w[i] * x[idx[i], d]
+            for i in range(len(w)):
+                m += w[i] * 2e-5 / np.sqrt(6.0) * grads[idx[i], d]
+            want[d] = m
+        assert np.array_equal(a.get("Current Mean"), want), g
+    plain = O.Oracle(**case)
+    for g in range(6):
+        plain.run_generation()
+    assert not np.allclose(plain.get("Current Mean"), a.get("Current Mean"))   # the gradient step really changes the search
+    with pytest.raises(KcmaError, match="Gradient Step Size must be larger than 0.0"):
+        O.Oracle(use_gradient_information=1, gradient_step_size=0.0, **case)
+
+
+def test_injected_gradients_replace_the_model_gradients():
+    case = dict(n=4, population_size=8, objective="External", initial_value=1.0, initial_stddev=0.5, seed=2,
+                use_gradient_information=1, gradient_step_size=0.1)
+    o = O.Oracle(**case)
+    o.ask()
+    x = o.get("Sample Population").reshape(8, 4)
+    o.inject(INJ_F, -0.5 * (x**2).sum(1))
+    with pytest.raises(KcmaError, match="inject the gradients"):
+        o.eval()
+    o.inject(INJ_F, -0.5 * (x**2).sum(1)); o.inject(INJ_GRAD, (-x).ravel())
+    o.eval(); o.tell()
+    assert np.isfinite(o.get("Current Mean")).all()
