@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define KCMA_ABI_VERSION 2
+#define KCMA_ABI_VERSION 3
 
 /* "Mu Type" (CMAES.cpp.base:236-245). */
 enum { KCMA_MU_LINEAR = 0, KCMA_MU_EQUAL = 1, KCMA_MU_LOGARITHMIC = 2, KCMA_MU_PROPORTIONAL = 3 };
@@ -109,6 +109,9 @@ typedef struct kcma_cfg {
   int32_t use_gradient_information;     /* default 0                                              */
   int32_t reserved1;
   double gradient_step_size;            /* default 0.01; must be > 0 when gradients are used      */
+  /* discrete variables (optimizer.config "Granularity"; CMAES.cpp.base:44-50, 515-544, 668, 730-734, 834-867, after Hansen 2011,
+     "A CMA-ES for Mixed-Integer Nonlinear Optimization"): length n or NULL (all continuous); 0 = continuous, < 0 is an error */
+  const double* granularity;
 } kcma_cfg;
 
 typedef struct kcma kcma_t;

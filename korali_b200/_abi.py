@@ -38,6 +38,7 @@ class KcmaCfg(C.Structure):
         ("min_stddev_update", _dp),
         ("device", C.c_int32), ("rank", C.c_int32), ("nranks", C.c_int32), ("keep_population", C.c_int32),
         ("use_gradient_information", C.c_int32), ("reserved1", C.c_int32), ("gradient_step_size", C.c_double),
+        ("granularity", _dp),
     ]
 
 
@@ -60,7 +61,7 @@ class Handle:
         n = int(kw["n"])
         for k, v in kw.items():
             if k in ("lower_bound", "upper_bound", "initial_value", "initial_stddev", "min_stddev_update",
-                     "objective_coef", "constraint_shift"):
+                     "objective_coef", "constraint_shift", "granularity"):
                 if v is None:
                     continue
                 want = int(kw.get("n_constraints", 0)) if k == "constraint_shift" else n

@@ -73,6 +73,10 @@ struct kcma {
   double *dMean = nullptr, *dMeanOld = nullptr, *dMeanUpd = nullptr, *dT = nullptr, *dPs = nullptr, *dPc = nullptr;
   double *dZ = nullptr, *dY = nullptr, *dX = nullptr, *dF = nullptr;
   double* dGrad = nullptr;   // "Gradients" of the local samples (Use Gradient Information), max_local x ld
+  // discrete variables ("Granularity"): per-variable granularity, masking matrices, "Discrete Mutations" (max_local x ld)
+  bool has_discrete = false;
+  std::vector<double> gran;
+  double *dGran = nullptr, *dMask = nullptr, *dMaskSigma = nullptr, *dDiscMut = nullptr;
   unsigned* dIdx = nullptr;
   void* dSortWs = nullptr;
   double *dW = nullptr, *dSelW = nullptr;
@@ -457,6 +461,12 @@ int sample_population(kcma* h) {
                        h->has_bounds ? h->dLower : nullptr, h->dUpper, h->has_bounds ? h->dInfeasible : nullptr,
                        h->cfg.keep_population ? h->dX : nullptr, ld, nullptr, h->num_sms);
     h->launches++;
+    if (h->has_discrete) {   // :515-544 + discretize (:453, :478-481); from here on X (not mean + sigma y) is the population
+      launch_discrete_mutation(h->stream, h->dX, ld, ls, N, h->shard_lo, h->cfg.mirrored_sampling, h->dSc, h->dMask, h->dGran, h->dBestEver,
+                               h->cfg.seed, gen_arg(h), h->dAttempt, h->dDiscMut);
+      h->launches++;
+      if (h->has_bounds) { launch_feasibility_x(h->stream, h->dX, ld, ls, N, h->dLower, h->dUpper, h->dInfeasible, h->num_sms); h->launches++; }
+    }
     if (h->has_bounds) {
       int* dRows = (int*)h->dSelS;                     // reuse: selection list is rebuilt in tell()
       unsigned* dAttempt = h->dAttempt;                // zeroed per generation
@@ -483,6 +493,7 @@ int sample_population(kcma* h) {
     }
   }
   h->inj_y = false;
+  if (h->has_discrete) h->inj_x = true;   // eval / tell read the materialised X (same mode as an injected population)
   h->sampled_pending = true;
   return 0;
 }
@@ -787,10 +798,15 @@ int do_tell(kcma* h) {
     const double cmu = std::min(1.0 - c1, 2.0 * (h->mueff - 2. + 1. / h->mueff) / (pow(N + 2.0, 2) + h->mueff));
     if (multi) launch_adapt_c(h->stream, h->dC, ld, h->dRed, ld, 1, N, h->dPc, c1, cmu, h->cc, h->cfg.diagonal_covariance, h->dSc);
     else launch_adapt_c(h->stream, h->dC, ld, h->dWsplit, ld, splits, N, h->dPc, c1, cmu, h->cc, h->cfg.diagonal_covariance, h->dSc);
+    if (h->has_discrete) {   // updateDiscreteMutationMatrix (:668): new C, sigma of before updateSigma
+      launch_discrete_matrix(h->stream, h->dC, ld, N, h->dGran, h->dPs, h->cs, (double)h->cfg.population_size, h->dMask, h->dMaskSigma, h->dSc);
+      h->launches++;
+    }
     const int viab = (h->has_constraints && h->is_viability) ? 1 : 0;
     if (viab) { launch_viability_boundaries(h->stream, h->dG, h->ldg, (int)h->n_con, h->dIdx, mu, h->dBounds); h->launches++; }
     launch_sigma(h->stream, h->dC, ld, N, h->dMinSd, h->any_min_sd ? 1 : 0, h->cs, h->damp, h->chi_n, h->trace, h->cfg.is_sigma_bounded,
-                 h->cfg.mu_value > 1 ? 1 : 0, viab, h->cfg.global_success_learning_rate, h->cfg.target_success_rate, h->dSc);
+                 h->cfg.mu_value > 1 ? 1 : 0, viab, h->cfg.global_success_learning_rate, h->cfg.target_success_rate, h->has_discrete ? 1 : 0,
+                 h->dSc);
     h->launches += 7;
   }
   h->inj_x = false;
@@ -883,7 +899,8 @@ void kcma_destroy(kcma_t* h) {
                   h->dPs, h->dPc, h->dZ, h->dY, h->dX, h->dF, h->dIdx, h->dSortWs, h->dW, h->dSelW, h->dSelS, h->dCount, h->dS,
                   h->dPartial, h->dWsplit, h->dRed, h->dBestEver, h->dCurBest, h->dLower, h->dUpper, h->dMinSd, h->dCoef, h->dShift,
                   h->dSigmaSampling, h->dInfeasible, h->dFlush, h->dSc, h->dG, h->dBounds, h->dNormal, h->dCaux, h->dBestCon, h->dU, h->dViol,
-                  h->dIndicator, h->dEvSample, h->dEvCon, h->dVioRows, h->dAttempt, h->dGrad};
+                  h->dIndicator, h->dEvSample, h->dEvCon, h->dVioRows, h->dAttempt, h->dGrad, h->dGran, h->dMask,
+                  h->dMaskSigma, h->dDiscMut};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->hSc) cudaFreeHost(h->hSc);
   if (h->hCount) cudaFreeHost(h->hCount);
@@ -917,6 +934,17 @@ int kcma_create(const kcma_cfg* cfg, kcma_t** out) {
   h->init_val = copyv(cfg->initial_value, N, NAN);
   h->init_sd = copyv(cfg->initial_stddev, N, NAN);
   h->min_sd = copyv(cfg->min_stddev_update, N, 0.0);
+  h->gran = copyv(cfg->granularity, N, 0.0);
+  h->cfg.granularity = nullptr;
+  for (int i = 0; i < N; i++) {   // CMAES.cpp.base:44-50
+    if (h->gran[i] < 0.0) { char msg[96]; snprintf(msg, sizeof(msg), "Negative granularity for variable %d.\n", i); CREATE_FAIL(msg); }
+    if (h->gran[i] > 0.0) h->has_discrete = true;
+  }
+  if (h->has_discrete) {
+    if (cfg->n_constraints > 0) CREATE_FAIL("discrete variables together with constraints are not supported");
+    if (cfg->max_infeasible_resamplings != 0) CREATE_FAIL("discrete variables with resampling rounds (Max Infeasible Resamplings > 0) are not supported");
+    h->cfg.keep_population = 1;   // after the discrete mutations X is no longer mean + sigma * y: it is materialised
+  }
   h->coef.resize(N);
   for (int i = 0; i < N; i++) h->coef[i] = cfg->objective_coef ? cfg->objective_coef[i] : (N > 1 ? pow(10.0, 6.0 * (double)i / (double)(N - 1)) : 1.0);
   h->n_con = (cfg->constraint_family == KCMA_CON_NONE && !cfg->n_constraints) ? 0 : cfg->n_constraints;
@@ -989,8 +1017,13 @@ int kcma_create(const kcma_cfg* cfg, kcma_t** out) {
   CREATE_CUDA(dmalloc(&h->dT, ld)); CREATE_CUDA(dmalloc(&h->dPs, ld)); CREATE_CUDA(dmalloc(&h->dPc, ld));
   CREATE_CUDA(dmalloc(&h->dBestEver, ld)); CREATE_CUDA(dmalloc(&h->dCurBest, ld));
   CREATE_CUDA(dmalloc(&h->dZ, h->max_zrows * ld)); CREATE_CUDA(dmalloc(&h->dY, h->max_zrows * ld));
-  CREATE_CUDA(dmalloc(&h->dX, (cfg->keep_population ? h->max_local : 1) * (size_t)ld));
+  CREATE_CUDA(dmalloc(&h->dX, (h->cfg.keep_population ? h->max_local : 1) * (size_t)ld));
   if (cfg->use_gradient_information) CREATE_CUDA(dmalloc(&h->dGrad, h->max_local * (size_t)ld));
+  if (h->has_discrete) {
+    CREATE_CUDA(dmalloc(&h->dGran, ld)); CREATE_CUDA(dmalloc(&h->dMask, ld)); CREATE_CUDA(dmalloc(&h->dMaskSigma, ld));
+    CREATE_CUDA(dmalloc(&h->dDiscMut, h->max_local * (size_t)ld));
+    CREATE_CUDA(cudaMemcpy(h->dGran, h->gran.data(), sizeof(double) * N, cudaMemcpyHostToDevice));
+  }
   CREATE_CUDA(dmalloc(&h->dF, h->s_max)); CREATE_CUDA(dmalloc(&h->dIdx, h->s_max));
   CREATE_CUDA(cudaMalloc(&h->dSortWs, sort_workspace_bytes((int)h->s_max)));
   CREATE_CUDA(dmalloc(&h->dW, h->mu_max));
@@ -1031,6 +1064,7 @@ int kcma_create(const kcma_cfg* cfg, kcma_t** out) {
   DevScalars s; memset(&s, 0, sizeof(s));
   s.best_ever_value = s.previous_best_ever_value = s.previous_best_value = s.current_best_value = -INFINITY;
   s.cur_min_sd = INFINITY; s.cur_max_sd = -INFINITY;
+  s.chi_dm = sqrt((double)N) * (1. - 1. / (4. * N) + 1. / (21. * (double)N * N));   // ref :34
   s.global_success_rate = h->has_constraints ? 0.5 : -1.0;
   s.best_valid_sample = h->has_constraints ? ~0ull : 0ull;
   *h->hSc = s;
@@ -1122,7 +1156,7 @@ void invalidate_graph(kcma* h) {
 bool graph_eligible(const kcma* h) {
   static const int on = getenv("KCMA_GRAPH") ? atoi(getenv("KCMA_GRAPH")) : 1;
   if (!on || h->graph_failed || h->timing || h->cfg.nranks > 1 || h->host_obj || h->host_obj_grad || h->host_con || h->has_constraints) return false;
-  if (h->cfg.objective == KCMA_OBJ_EXTERNAL) return false;
+  if (h->cfg.objective == KCMA_OBJ_EXTERNAL || h->has_discrete) return false;
   if (h->has_bounds && h->cfg.max_infeasible_resamplings != 0) return false;
   if (h->inj_z || h->inj_bd || h->inj_y || h->inj_x || h->inj_f || h->inj_grad || h->sampled_pending || !h->vt_valid) return false;
   if (!h->cfg.diagonal_covariance && ((h->N + 3) / 4 + 1) / 2 > h->num_sms) return false;   // eigensolver with a host loop
@@ -1353,6 +1387,12 @@ int kcma_get_array(kcma_t* h, const char* key, double* out, size_t cap, size_t* 
   ArrRef r;
   if (!strcmp(key, "Gradients") && h->dGrad) {   // LOCAL shard rows, like "Sample Population"
     r.p = h->dGrad; r.rows = local_samples(h); r.cols = N; r.ld = h->ld;
+  } else if (!strcmp(key, "Discrete Mutations") && h->dDiscMut) {
+    r.p = h->dDiscMut; r.rows = local_samples(h); r.cols = N; r.ld = h->ld;
+  } else if (!strcmp(key, "Masking Matrix") && h->dMask) {
+    r.p = h->dMask; r.rows = 1; r.cols = N; r.ld = h->ld;
+  } else if (!strcmp(key, "Masking Matrix Sigma") && h->dMaskSigma) {
+    r.p = h->dMaskSigma; r.rows = 1; r.cols = N; r.ld = h->ld;
   } else if (!find_array(h, key, &r)) return fail(h, "unknown array key '%s'", key);
   const size_t n = r.rows * r.cols;
   if (count) *count = n;
@@ -1411,7 +1451,7 @@ double* find_dev_scalar(kcma* h, const char* key) {
   S("Maximum Diagonal Covariance Matrix Element", max_diag_c) S("Minimum Diagonal Covariance Matrix Element", min_diag_c)
   S("Maximum Covariance Eigenvalue", max_eig) S("Minimum Covariance Eigenvalue", min_eig)
   S("Current Min Standard Deviation", cur_min_sd) S("Current Max Standard Deviation", cur_max_sd)
-  S("Global Success Rate", global_success_rate)
+  S("Global Success Rate", global_success_rate) S("Chi Square Number Discrete Mutations", chi_dm)
 #undef S
   return nullptr;
 }
@@ -1440,6 +1480,7 @@ int kcma_get_scalar(kcma_t* h, const char* key, double* out) {
   U("Current Generation", h->gen - 1) U("Model Evaluation Count", h->model_evals) U("Variable Count", h->N)
   U("Current Population Size", h->cur_lambda) U("Current Mu Value", h->cur_mu)
   U("Infeasible Sample Count", h->hSc->infeasible_sample_count)
+  U("Number Of Discrete Mutations", h->hSc->n_disc_mut) U("Number Masking Matrix Entries", h->hSc->n_mask)
   U("Resampled Parameter Count", h->hSc->resampled_parameter_count)
   U("Covariance Matrix Adaptation Count", h->hSc->cov_adaptation_count)
   U("Max Constraint Violation Count", h->hSc->max_violation_count)

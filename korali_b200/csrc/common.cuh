@@ -76,6 +76,11 @@ struct DevScalars {
   int warn_minsd;            // "Sigma increased due to minimal standard deviation."
   int best_updated;          // best-ever was replaced this generation
   int jacobi_rotations;      // rotations applied in the last Jacobi sweep
+  // discrete variables (CMAES.cpp.base:834-860): set by discrete_matrix_kernel after the covariance update
+  double chi_dm;             // _chiSquareNumberDiscreteMutations
+  double disc_path_l2;       // sum_d maskingMatrixSigma[d] * ps[d]^2 (:733)
+  int n_mask;                // _numberMaskingMatrixEntries
+  int n_disc_mut;            // _numberOfDiscreteMutations
   unsigned long long gen;    // generation counter for CUDA-graph replays (kernels launched with generation == kGenFromDevice read it)
 };
 

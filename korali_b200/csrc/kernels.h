@@ -73,7 +73,14 @@ void launch_signed_rank_mu(cudaStream_t st, const double* S, int lds, const int*
                            int ldw);
 void launch_sigma(cudaStream_t st, const double* C, int ldc, int n, const double* min_sd_update, int any_min_sd, double cs,
                   double damp, double chi_n, double trace, int is_sigma_bounded, int mu_value_gt1, int viability_regime,
-                  double global_success_lr, double target_success_rate, DevScalars* sc);
+                  double global_success_lr, double target_success_rate, int has_discrete, DevScalars* sc);
+void launch_discrete_mutation(cudaStream_t st, double* X, int ldx, long long samples, int n, unsigned long long sample_begin, int mirrored,
+                              const DevScalars* sc, const double* mask, const double* gran, const double* best_ever, unsigned long long seed,
+                              unsigned generation, const unsigned* attempt, double* disc_mut);
+void launch_discrete_matrix(cudaStream_t st, const double* C, int ldc, int n, const double* gran, const double* ps, double cs,
+                            double population_size, double* mask, double* mask_sigma, DevScalars* sc);
+void launch_feasibility_x(cudaStream_t st, const double* X, int ldx, long long samples, int n, const double* lower, const double* upper,
+                          unsigned char* infeasible, int num_sms);
 void launch_viability_boundaries(cudaStream_t st, const double* G, long long ldg, int n_con, const unsigned* idx, int mu,
                                  double* bounds);
 

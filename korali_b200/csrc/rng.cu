@@ -62,6 +62,66 @@ philox_normal_kernel(double* __restrict__ Z, int ldz, long long rows, int n, uns
   }
 }
 
+// Discrete mutations of the first _numberOfDiscreteMutations samples, then discretize() of every sample
+// (CMAES.cpp.base:515-544 and :453 / :478-481, :862-867; after Hansen 2011, "A CMA-ES for Mixed-Integer Nonlinear
+// Optimization"). The reference draws from its _uniformGenerator; here: a second Philox stream,
+// key = { seed_lo, seed_hi ^ "DISC" }, ctr = { block, GLOBAL sample index, resampling attempt, generation }, draw k = half
+// (k & 1) of block k >> 1 (restated in oracle/okcma.c philox_uniform). One thread per local sample; X is authoritative.
+__device__ __forceinline__ double discrete_uniform(unsigned long long seed, unsigned generation, unsigned attempt, unsigned long long sample,
+                                                   unsigned k) {
+  uint32_t r[4];
+  philox4x32_10(k >> 1, (uint32_t)sample, attempt, generation, (uint32_t)seed, (uint32_t)(seed >> 32) ^ 0x44495343u, r);
+  return (k & 1u) ? unit_open52(r[2], r[3]) : unit_open52(r[0], r[1]);
+}
+
+__global__ void __launch_bounds__(128)
+discrete_mutation_kernel(double* __restrict__ X, int ldx, long long samples, int n, unsigned long long sample_begin, int mirrored,
+                         const DevScalars* __restrict__ sc, const double* __restrict__ mask, const double* __restrict__ gran,
+                         const double* __restrict__ best_ever, unsigned long long seed, unsigned generation,
+                         const unsigned* __restrict__ attempt, double* __restrict__ disc_mut) {
+  const long long li = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (li >= samples) return;
+  if (generation == kGenFromDevice) generation = (unsigned)sc->gen;
+  const unsigned long long i = sample_begin + (unsigned long long)li;   // global sample index
+  const unsigned att = attempt ? attempt[mirrored ? (li >> 1) : li] : 0u;
+  const unsigned long long ndm = (unsigned long long)sc->n_disc_mut;
+  const int n_mask = sc->n_mask;
+  double* x = X + (size_t)li * ldx;
+  double* dm = disc_mut + (size_t)li * ldx;
+  for (int d = 0; d < n; d++) dm[d] = 0.0;
+  unsigned k = 0;
+  if ((i + 1) < ndm) {
+    const double p_geom = pow(0.7, 1.0 / (double)n_mask);
+    unsigned long long select = (unsigned long long)floor(discrete_uniform(seed, generation, att, i, k++) * (double)n_mask);
+    for (int d = 0; d < n; ++d)
+      if ((mask[d] == 1.0) && (select-- == 0)) {
+        double dmutation = 1.0;
+        while (discrete_uniform(seed, generation, att, i, k++) > p_geom) dmutation += 1.0;
+        dmutation *= gran[d];
+        if (discrete_uniform(seed, generation, att, i, k++) > 0.5) dmutation *= -1.0;
+        dm[d] = dmutation;
+        x[d] += dmutation;
+      }
+  } else if ((i + 1) == ndm) {
+    for (int d = 0; d < n; ++d)
+      if (gran[d] != 0.0) {
+        const double dmutation = round(best_ever[d] / gran[d]) * gran[d] - x[d];
+        dm[d] = dmutation;
+        x[d] += dmutation;
+      }
+  }
+  for (int d = 0; d < n; ++d)
+    if (gran[d] != 0.0) x[d] = round(x[d] / gran[d]) * gran[d];
+}
+
+void launch_discrete_mutation(cudaStream_t st, double* X, int ldx, long long samples, int n, unsigned long long sample_begin, int mirrored,
+                              const DevScalars* sc, const double* mask, const double* gran, const double* best_ever, unsigned long long seed,
+                              unsigned generation, const unsigned* attempt, double* disc_mut) {
+  if (samples <= 0) return;
+  discrete_mutation_kernel<<<(unsigned)((samples + 127) / 128), 128, 0, st>>>(X, ldx, samples, n, sample_begin, mirrored, sc, mask, gran,
+                                                                             best_ever, seed, generation, attempt, disc_mut);
+}
+
 // Raw Philox block (known-answer tests).
 __global__ void philox_raw_kernel(const uint32_t* in, uint32_t* out) {
   uint32_t r[4];

@@ -339,7 +339,7 @@ signed_rank_mu_kernel(const double* __restrict__ S, int lds, const int* __restri
 __global__ void __launch_bounds__(1024)
 sigma_kernel(const double* __restrict__ C, int ldc, int n, const double* __restrict__ min_sd_update, int any_min_sd,
              double cs, double damp, double chi_n, double trace, int is_sigma_bounded, int mu_value_gt1,
-             int viability_regime, double global_success_lr, double target_success_rate,
+             int viability_regime, double global_success_lr, double target_success_rate, int has_discrete,
              DevScalars* __restrict__ sc) {
   __shared__ double smax[32], smin[32];
   double mx = -INFINITY, mn = INFINITY;
@@ -360,6 +360,8 @@ sigma_kernel(const double* __restrict__ C, int ldc, int n, const double* __restr
     const double gsr = (1 - global_success_lr) * sc->global_success_rate;
     sc->global_success_rate = gsr;
     sigma *= exp((gsr - (target_success_rate / (1.0 - target_success_rate)) * (1 - gsr)) / damp);
+  } else if (has_discrete) {   // :730-734
+    sigma *= exp(cs / damp * (sqrt(sc->disc_path_l2) / sc->chi_dm - 1.));
   } else {
     sigma *= exp(cs / damp * (sc->ps_l2norm / chi_n - 1.));
   }
@@ -445,6 +447,73 @@ void launch_gradient_mean(cudaStream_t st, const double* G, int ldg, const int* 
   gradient_mean_kernel<<<(n + 255) / 256, 256, 0, st>>>(G, ldg, sel_sample, sel_weight, count_ptr, n, step, mean_new);
 }
 
+// updateDiscreteMutationMatrix (CMAES.cpp.base:834-860) + the masked path length of updateSigma (:733). Single block.
+// Uses the sigma of BEFORE updateSigma and the covariance of AFTER adaptC, like the reference (:665-675).
+__global__ void __launch_bounds__(256)
+discrete_matrix_kernel(const double* __restrict__ C, int ldc, int n, const double* __restrict__ gran, const double* __restrict__ ps, double cs,
+                       double population_size, double* __restrict__ mask, double* __restrict__ mask_sigma, DevScalars* __restrict__ sc) {
+  __shared__ int s_removed, s_mask;
+  __shared__ double s_path[8];
+  if (threadIdx.x == 0) { s_removed = 0; s_mask = 0; }
+  __syncthreads();
+  const double sigma = sc->sigma;
+  int removed = 0, masked = 0;
+  double path = 0.0;
+  for (int d = threadIdx.x; d < n; d += blockDim.x) {
+    const double sd = sigma * sqrt(C[(size_t)d * ldc + d]);
+    double ms = 1.0;
+    if (sd / sqrt(cs) < 0.2 * gran[d]) { ms = 0.0; removed++; }
+    mask_sigma[d] = ms;
+    double mk = 0.0;
+    if (2.0 * sd < gran[d]) { mk = 1.0; masked++; }
+    mask[d] = mk;
+    path += ms * ps[d] * ps[d];
+  }
+  path = warp_sum_butterfly(path);
+  if ((threadIdx.x & 31) == 0) s_path[threadIdx.x >> 5] = path;
+  if (removed) atomicAdd(&s_removed, removed);
+  if (masked) atomicAdd(&s_mask, masked);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double p = 0.0;
+    for (int w = 0; w < 8; w++) p += s_path[w];
+    const double entries = (double)(n + 1 - s_removed);   // +1 to prevent 0-ness
+    sc->chi_dm = sqrt(entries) * (1. - 1. / (4. * entries) + 1. / (21. * entries * entries));
+    sc->disc_path_l2 = p;
+    sc->n_mask = s_mask;
+    sc->n_disc_mut = (int)fmin(round(population_size / 10.0 + s_mask + 1), floor(population_size / 2.0) - 1);
+  }
+}
+void launch_discrete_matrix(cudaStream_t st, const double* C, int ldc, int n, const double* gran, const double* ps, double cs,
+                            double population_size, double* mask, double* mask_sigma, DevScalars* sc) {
+  discrete_matrix_kernel<<<1, 256, 0, st>>>(C, ldc, n, gran, ps, cs, population_size, mask, mask_sigma, sc);
+}
+
+// isSampleFeasible on materialised samples (after the discrete mutations X is no longer mean + sigma * y).
+__global__ void __launch_bounds__(256)
+feasibility_x_kernel(const double* __restrict__ X, int ldx, long long samples, int n, const double* __restrict__ lower,
+                     const double* __restrict__ upper, unsigned char* __restrict__ infeasible) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long s = warp; s < samples; s += nwarps) {
+    bool bad = false;
+    for (int d = lane; d < n; d += 32) {
+      const double v = X[(size_t)s * ldx + d];
+      bad |= !isfinite(v) || v < lower[d] || v > upper[d];
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, bad);
+    if (lane == 0) infeasible[s] = m ? 1 : 0;
+  }
+}
+void launch_feasibility_x(cudaStream_t st, const double* X, int ldx, long long samples, int n, const double* lower, const double* upper,
+                          unsigned char* infeasible, int num_sms) {
+  if (samples <= 0) return;
+  long long blocks = (samples + 7) / 8;
+  if (blocks > (long long)num_sms * 8) blocks = (long long)num_sms * 8;
+  feasibility_x_kernel<<<(unsigned)blocks, 256, 0, st>>>(X, ldx, samples, n, lower, upper, infeasible);
+}
+
 void launch_best_update(cudaStream_t st, const double* best_x, int n, unsigned generation, double* cur_best_vars,
                         double* best_ever_vars, DevScalars* sc, const double* con_evals, long long ldg, int n_con,
                         double* best_con_evals) {
@@ -479,9 +548,9 @@ void launch_signed_rank_mu(cudaStream_t st, const double* S, int lds, const int*
 }
 void launch_sigma(cudaStream_t st, const double* C, int ldc, int n, const double* min_sd_update, int any_min_sd, double cs,
                   double damp, double chi_n, double trace, int is_sigma_bounded, int mu_value_gt1, int viability_regime,
-                  double global_success_lr, double target_success_rate, DevScalars* sc) {
+                  double global_success_lr, double target_success_rate, int has_discrete, DevScalars* sc) {
   sigma_kernel<<<1, 1024, 0, st>>>(C, ldc, n, min_sd_update, any_min_sd, cs, damp, chi_n, trace, is_sigma_bounded, mu_value_gt1,
-                                   viability_regime, global_success_lr, target_success_rate, sc);
+                                   viability_regime, global_success_lr, target_success_rate, has_discrete, sc);
 }
 void launch_viability_boundaries(cudaStream_t st, const double* G, long long ldg, int n_con, const unsigned* idx, int mu,
                                  double* bounds) {

@@ -193,7 +193,7 @@ class CMAES {
   kcma_t* h = nullptr;
   kcma_cfg cfg;
   std::string mu_type = "Logarithmic";
-  std::vector<double> lower, upper, init_val, init_sd, min_sd;
+  std::vector<double> lower, upper, init_val, init_sd, min_sd, gran;
   std::vector<std::string> names;
   py::object objective;                 // Python callable, or a string naming a built-in device objective
   std::vector<py::object> constraints;  // Python callables
@@ -298,6 +298,7 @@ class CMAES {
     const size_t n = py::len(variables);
     if (n == 0) korali_error("Optimization Evaluation problems require at least one variable.\n");
     lower.assign(n, -INFINITY); upper.assign(n, INFINITY); init_val.assign(n, NAN); init_sd.assign(n, NAN); min_sd.assign(n, 0.0);
+    gran.assign(n, 0.0);
     names.assign(n, "");
     for (size_t i = 0; i < n; i++) {
       if (!py::isinstance<py::dict>(variables[i])) korali_error("Variable %zu is not an object\n", i);
@@ -312,14 +313,13 @@ class CMAES {
       init_sd[i] = v.num("Initial Standard Deviation", NAN);
       min_sd[i] = v.num("Minimum Standard Deviation Update", 0.0);
       if (v.has("Values")) v.take("Values");
-      const double gran = v.num("Granularity", 0.0);
-      if (gran < 0.0) korali_error("Negative granularity for variable '%s'.\n", names[i].c_str());
-      if (gran > 0.0) korali_error("Discrete variables (Granularity > 0) are not part of the B200 CMA-ES path yet (SURVEY.md 8f-2)\n");
+      gran[i] = v.num("Granularity", 0.0);
+      if (gran[i] < 0.0) korali_error("Negative granularity for variable '%s'.\n", names[i].c_str());   // CMAES.cpp.base:48
       v.finish();
     }
     cfg.n = n;
     cfg.lower_bound = lower.data(); cfg.upper_bound = upper.data(); cfg.initial_value = init_val.data();
-    cfg.initial_stddev = init_sd.data(); cfg.min_stddev_update = min_sd.data();
+    cfg.initial_stddev = init_sd.data(); cfg.min_stddev_update = min_sd.data(); cfg.granularity = gran.data();
     cfg.seed = seed;
     // problem (optimization.config)
     py::dict pcopy;

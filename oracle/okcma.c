@@ -122,6 +122,17 @@ static void philox_normal_pair(uint64_t seed, uint32_t generation, uint32_t atte
   *z1 = rad * s;
 }
 
+/* Uniform stream of the discrete mutations (the reference draws them from its _uniformGenerator, CMAES.cpp.base:520-529):
+ * a second Philox stream, key = { seed_lo, seed_hi ^ "DISC" }, ctr = { block, sample index, resampling attempt, generation };
+ * draw k is half (k & 1) of block k >> 1. Same function on the device (constraints.cu / update.cu discrete kernels). */
+static double philox_uniform(uint64_t seed, uint32_t generation, uint32_t attempt, uint64_t sample, uint32_t k) {
+  uint32_t ctr[4] = {k >> 1, (uint32_t)sample, attempt, generation};
+  uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32) ^ 0x44495343u};
+  uint32_t r[4];
+  okcma_philox4x32_10(ctr, key, r);
+  return (k & 1u) ? u64_to_unit_open(r[2], r[3]) : u64_to_unit_open(r[0], r[1]);
+}
+
 static void philox_normal_row(uint64_t seed, uint32_t generation, uint32_t attempt, uint64_t row, uint64_t n, double* z) {
   for (uint64_t p = 0; 2 * p < n; p++) {
     double a, b;
@@ -527,6 +538,11 @@ struct okcma {
   int have_inj_bd;
   int have_inj_f;
   double* gradients; int have_inj_grad;   /* _gradients (CMAES.cpp.base:82-86), lambda x N */
+  /* discrete variables (:44-50, 101-107) */
+  int has_discrete;
+  double *granularity, *masking_matrix, *masking_matrix_sigma, *discrete_mutations;
+  uint64_t n_mask, n_discrete_mutations;
+  double chi_square_number_discrete_mutations;
   int skip_sampling; /* BDZ or X injected for this generation */
   /* callbacks */
   okcma_objective_fn obj_fn; void* obj_user;
@@ -669,6 +685,12 @@ int okcma_create(const kcma_cfg* cfg, okcma_t** out) {
   h->initial_value = dcopy(cfg->initial_value, N, NAN);
   h->initial_sd = dcopy(cfg->initial_stddev, N, NAN);
   h->min_sd_update = dcopy(cfg->min_stddev_update, N, 0.0);
+  h->granularity = dcopy(cfg->granularity, N, 0.0);
+  for (uint64_t i = 0; i < N; i++) { /* ref :44-50 */
+    if (h->granularity[i] < 0.0) { fail(NULL, "Negative granularity for variable %zu.\n", (size_t)i); okcma_destroy(h); return 1; }
+    if (h->granularity[i] > 0.0) h->has_discrete = 1;
+  }
+  if (h->has_discrete && cfg->n_constraints > 0) { fail(NULL, "discrete variables together with constraints are not supported"); okcma_destroy(h); return 1; }
   h->obj_coef = dalloc(N);
   for (uint64_t i = 0; i < N; i++)
     h->obj_coef[i] = cfg->objective_coef ? cfg->objective_coef[i] : (N > 1 ? pow(10.0, 6.0 * (double)i / (double)(N - 1)) : 1.0);
@@ -706,6 +728,11 @@ int okcma_create(const kcma_cfg* cfg, okcma_t** out) {
 
   h->X = dalloc(h->s_max * N); h->BDZ = dalloc(h->s_max * N); h->aux_bdz = dalloc(N);
   if (h->cfg.use_gradient_information) h->gradients = dalloc(h->s_max * N); /* ref :82-85 */
+  if (h->has_discrete) { /* ref :101-107 */
+    h->masking_matrix = dalloc(N); h->masking_matrix_sigma = dalloc(N); h->discrete_mutations = dalloc(h->s_max * N);
+    h->n_mask = 0; h->n_discrete_mutations = 0;
+  }
+  h->chi_square_number_discrete_mutations = sqrt((double)N) * (1. - 1. / (4. * N) + 1. / (21. * N * N)); /* ref :34 */
   h->value_vector = dalloc(h->s_max);
   h->sorting_index = (uint64_t*)calloc(h->s_max, sizeof(uint64_t));
   h->C = dalloc(N * N); h->C_aux = dalloc(N * N); h->B = dalloc(N * N); h->B_aux = dalloc(N * N);
@@ -779,6 +806,7 @@ void okcma_destroy(okcma_t* h) {
   free(h->best_ever_variables); free(h->current_best_variables); free(h->viability_boundaries);
   free(h->violation_counts); free(h->con_evals); free(h->viability_indicator); free(h->normal_approx);
   free(h->best_con_evals); free(h->philox_attempt); free(h->inj_z); free(h->gradients);
+  free(h->granularity); free(h->masking_matrix); free(h->masking_matrix_sigma); free(h->discrete_mutations);
   free(h);
 }
 
@@ -809,7 +837,64 @@ static void draw_normals(okcma_t* h, uint64_t zrow, double* z) {
   }
 }
 
-/* ref: CMAES.cpp.base:494-513 (discrete-mutation block :515-544 is out of scope) */
+/* ref: CMAES.cpp.base:862-867 */
+static void discretize(const okcma_t* h, double* x) {
+  for (uint64_t d = 0; d < h->N; ++d)
+    if (h->granularity[d] != 0.0) x[d] = round(x[d] / h->granularity[d]) * h->granularity[d];
+}
+
+/* ref: CMAES.cpp.base:515-544, then the discretize() of :453 / :478-481. `attempt` = resampling attempt of this draw. */
+static void discrete_mutation(okcma_t* h, uint64_t i, uint32_t attempt) {
+  const uint64_t N = h->N;
+  uint32_t k = 0;
+#define U() philox_uniform(h->cfg.seed, (uint32_t)h->gen, attempt, i, k++)
+  if ((i + 1) < h->n_discrete_mutations) {
+    const double p_geom = pow(0.7, 1.0 / h->n_mask);
+    uint64_t select = (uint64_t)floor(U() * h->n_mask);
+    for (uint64_t d = 0; d < N; ++d)
+      if ((h->masking_matrix[d] == 1.0) && (select-- == 0)) {
+        double dmutation = 1.0;
+        while (U() > p_geom) dmutation += 1.0;
+        dmutation *= h->granularity[d];
+        if (U() > 0.5) dmutation *= -1.0;
+        h->discrete_mutations[i * N + d] = dmutation;
+        h->X[i * N + d] += dmutation;
+      }
+  } else if ((i + 1) == h->n_discrete_mutations) {
+    for (uint64_t d = 0; d < N; ++d)
+      if (h->granularity[d] != 0.0) {
+        const double dmutation = round(h->best_ever_variables[d] / h->granularity[d]) * h->granularity[d] - h->X[i * N + d];
+        h->discrete_mutations[i * N + d] = dmutation;
+        h->X[i * N + d] += dmutation;
+      }
+  }
+#undef U
+  discretize(h, h->X + i * N);
+}
+
+/* ref: CMAES.cpp.base:834-860 */
+static void update_discrete_mutation_matrix(okcma_t* h) {
+  const uint64_t N = h->N;
+  uint64_t entries = N + 1; /* +1 to prevent 0-ness */
+  for (uint64_t d = 0; d < N; ++d) h->masking_matrix_sigma[d] = 1.0;
+  for (uint64_t d = 0; d < N; ++d)
+    if (h->sigma * sqrt(h->C[d * N + d]) / sqrt(h->sigma_cumulation_factor) < 0.2 * h->granularity[d]) {
+      h->masking_matrix_sigma[d] = 0.0;
+      entries--;
+    }
+  h->chi_square_number_discrete_mutations = sqrt((double)entries) * (1. - 1. / (4. * entries) + 1. / (21. * entries * entries));
+  h->n_mask = 0;
+  for (uint64_t d = 0; d < N; ++d) h->masking_matrix[d] = 0.0;
+  for (uint64_t d = 0; d < N; ++d)
+    if (2.0 * h->sigma * sqrt(h->C[d * N + d]) < h->granularity[d]) {
+      h->masking_matrix[d] = 1.0;
+      h->n_mask++;
+    }
+  h->n_discrete_mutations = (uint64_t)fmin(round(h->cfg.population_size / 10.0 + h->n_mask + 1), floor(h->cfg.population_size / 2.0) - 1);
+  memset(h->discrete_mutations, 0, sizeof(double) * h->s_max * N);
+}
+
+/* ref: CMAES.cpp.base:494-513 */
 static void sample_single(okcma_t* h, uint64_t i, const double* z) {
   const uint64_t N = h->N;
   for (uint64_t d = 0; d < N; ++d) {
@@ -878,6 +963,7 @@ static void prepare_generation(okcma_t* h) {
       do {
         draw_normals(h, i, z);
         sample_single(h, i, z);
+        if (h->has_discrete) discrete_mutation(h, i, h->rng_kind ? (uint32_t)(h->philox_attempt[i] - 1) : 0u);
         feas = is_sample_feasible(h, h->X + i * N);
         h->infeasible_sample_count += feas ? 0 : 1;
       } while (!feas && (h->infeasible_sample_count < maxres));
@@ -890,6 +976,11 @@ static void prepare_generation(okcma_t* h) {
         for (uint64_t d = 0; d < N; ++d) z2[d] = -z[d];
         sample_single(h, i, z);
         sample_single(h, i + 1, z2);
+        if (h->has_discrete) {
+          const uint32_t att = h->rng_kind ? (uint32_t)(h->philox_attempt[i / 2] - 1) : 0u;
+          discrete_mutation(h, i, att);
+          discrete_mutation(h, i + 1, att);
+        }
         int f1 = is_sample_feasible(h, h->X + i * N);
         if (!f1) h->infeasible_sample_count++;
         int f2 = is_sample_feasible(h, h->X + (i + 1) * N);
@@ -1060,6 +1151,10 @@ static void update_sigma(okcma_t* h) {
   if (h->has_constraints && h->is_viability_regime) {
     h->global_success_rate = (1 - h->cfg.global_success_learning_rate) * h->global_success_rate;
     h->sigma *= exp((h->global_success_rate - (h->cfg.target_success_rate / (1.0 - h->cfg.target_success_rate)) * (1 - h->global_success_rate)) / h->damp_factor);
+  } else if (h->has_discrete) { /* ref :730-734 */
+    double pathL2 = 0.0;
+    for (uint64_t d = 0; d < h->N; ++d) pathL2 += h->masking_matrix_sigma[d] * h->ps[d] * h->ps[d];
+    h->sigma *= exp(h->sigma_cumulation_factor / h->damp_factor * (sqrt(pathL2) / h->chi_square_number_discrete_mutations - 1.));
   } else {
     h->sigma *= exp(h->sigma_cumulation_factor / h->damp_factor * (h->ps_l2norm / h->chi_square_number - 1.));
   }
@@ -1155,6 +1250,7 @@ static int update_distribution(okcma_t* h) {
     h->pc[d] = (1. - cc) * h->pc[d] + hsig * sqrt(cc * (2. - cc) * h->effective_mu) * h->mean_update[d];
 
   adapt_c(h, hsig);
+  if (h->has_discrete) update_discrete_mutation_matrix(h); /* ref :668 */
   if (h->has_constraints && h->is_viability_regime) update_viability_boundaries(h);
   update_sigma(h);
   numerical_error_treatment(h);
@@ -1315,6 +1411,10 @@ static int find_array(okcma_t* h, const char* key, arr_ref* r) {
   A("Value Vector", h->value_vector, h->cur_lambda)
   A("BDZ Matrix", h->BDZ, h->cur_lambda * N)
   if (h->gradients) { A("Gradients", h->gradients, h->cur_lambda * N) }
+  if (h->has_discrete) {
+    A("Masking Matrix", h->masking_matrix, N) A("Masking Matrix Sigma", h->masking_matrix_sigma, N)
+    A("Discrete Mutations", h->discrete_mutations, h->cur_lambda * N)
+  }
   A("Sample Population", h->X, h->cur_lambda * N)
   A("Best Ever Variables", h->best_ever_variables, N)
   A("Current Best Variables", h->current_best_variables, N)
@@ -1363,6 +1463,7 @@ static double* find_scalar(okcma_t* h, const char* key) {
   S("Sigma", h->sigma) S("Trace", h->trace) S("Effective Mu", h->effective_mu)
   S("Sigma Cumulation Factor", h->sigma_cumulation_factor) S("Damp Factor", h->damp_factor)
   S("Cumulative Covariance", h->cumulative_covariance) S("Chi Square Number", h->chi_square_number)
+  S("Chi Square Number Discrete Mutations", h->chi_square_number_discrete_mutations)
   S("Conjugate Evolution Path L2 Norm", h->ps_l2norm)
   S("Best Ever Value", h->best_ever_value) S("Previous Best Ever Value", h->previous_best_ever_value)
   S("Previous Best Value", h->previous_best_value) S("Current Best Value", h->current_best_value)
@@ -1387,6 +1488,7 @@ int okcma_get_scalar(okcma_t* h, const char* key, double* out) {
   if (p) { *out = *p; return 0; }
 #define U(K, V) if (!strcmp(key, K)) { *out = (double)(V); return 0; }
   U("Current Generation", h->gen - 1) U("Model Evaluation Count", h->model_evaluation_count)
+  U("Number Of Discrete Mutations", h->n_discrete_mutations) U("Number Masking Matrix Entries", h->n_mask)
   U("Variable Count", h->N) U("Current Population Size", h->cur_lambda) U("Current Mu Value", h->cur_mu)
   U("Infeasible Sample Count", h->infeasible_sample_count) U("Resampled Parameter Count", h->resampled_parameter_count)
   U("Is Viability Regime", h->is_viability_regime) U("Has Constraints", h->has_constraints)

@@ -98,3 +98,15 @@ def negative_sphere(p):      # examples/optimization/stochastic/_model/model.py:
         grad[i] = -x[i]
     p["F(x)"] = -0.5 * res
     p["Gradient"] = grad
+
+
+def discrete_model(s):       # examples/optimization/discrete/_model/model.py:5-16
+    npar = 10
+    res = 0.0
+    v = s["Parameters"]
+    for i in range(npar):
+        if (i == 0 or i == 1 or i == 3 or i == 6):
+            res += pow(10, 6.0 * i / npar) * round(v[i]) * round(v[i])
+        else:
+            res += pow(10, 6.0 * i / npar) * v[i] * v[i]
+    s["F(x)"] = -res

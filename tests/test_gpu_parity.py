@@ -449,6 +449,63 @@ def test_gradient_information_host_callback_injection_and_errors():
         d.ask(); d.inject(INJ_GRAD, np.zeros(32))
 
 
+# ---------------------------------------------------------------- discrete variables (Granularity) ----------
+@pytest.mark.parametrize("case", [
+    dict(n=6, population_size=16, objective="NegSphere", initial_value=3.3, initial_stddev=2.0, lower_bound=-20.0, upper_bound=20.0,
+         granularity=np.array([1.0, 1.0, 0.0, 0.0, 0.5, 0.0])),
+    dict(n=10, population_size=8, objective="NegEllipsoid", initial_value=1.0, lower_bound=-19.0, upper_bound=21.0,
+         granularity=np.array([1.0, 1.0, 0.0, 1.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0])),          # examples/optimization/discrete/run-cmaes.py
+    dict(n=12, population_size=24, objective="NegSumSq", initial_value=2.7, initial_stddev=1.5, mirrored_sampling=1,
+         granularity=np.array([2.0, 0.0, 0.25] * 4)),
+], ids=["sphere6", "discrete-example", "mirrored"])
+def test_discrete_variables_lockstep_against_oracle(case):
+    """Mixed-integer CMA-ES (Granularity): the device's discrete mutations (own Philox uniform stream), discretize, masking
+    matrices and masked step-size update against the oracle, in lockstep on the eigensystem and the normal draws."""
+    o = O.Oracle(seed=31, **case)
+    s = _lib.Solver(seed=31, **case)
+    o.set_scalar("Oracle/RNG Kind", 1)
+    n, lam = case["n"], case["population_size"]
+    saw_mutation = False
+    for g in range(60):
+        o.ask()
+        s.inject(INJ_BD, np.concatenate([o.get("Covariance Eigenvector Matrix"), o.get("Axis Lengths")]))
+        s.inject(INJ_BDZ, o.get("BDZ Matrix"))
+        s.ask()
+        xo, xs = o.get("Sample Population").reshape(lam, n), s.get("Sample Population").reshape(lam, n)
+        disc = case["granularity"] > 0
+        assert np.array_equal(xs[:, disc], xo[:, disc]), g                      # grid values: bit-identical
+        assert np.abs(xs - xo).max() <= 1e-12 * max(np.abs(xo).max(), 1.0), g
+        assert np.array_equal(s.get("Discrete Mutations").reshape(lam, n)[:, disc] != 0, o.get("Discrete Mutations").reshape(lam, n)[:, disc] != 0), g
+        saw_mutation |= bool(o.get("Discrete Mutations").any())
+        s.inject(INJ_X, xo.ravel())
+        o.eval(); s.eval()
+        s.inject(INJ_F, o.get("Value Vector"))
+        s.set_scalar("Model Evaluation Count", s.scalar("Model Evaluation Count") - lam)
+        s.eval()
+        o.tell(); s.tell()
+        assert np.array_equal(s.get_index("Sorting Index"), o.get_index("Sorting Index")), g
+        for k in ["Masking Matrix", "Masking Matrix Sigma"]:
+            assert np.array_equal(s.get(k), o.get(k)), (g, k)
+        for k in ["Number Of Discrete Mutations", "Number Masking Matrix Entries", "Infeasible Sample Count"]:
+            assert s.scalar(k) == o.scalar(k), (g, k)
+        assert abs(s.scalar("Chi Square Number Discrete Mutations") - o.scalar("Chi Square Number Discrete Mutations")) < 1e-14
+        for k in ["Current Mean", "Evolution Path", "Conjugate Evolution Path", "Covariance Matrix"]:
+            assert relerr(s.get(k), o.get(k)) < 1e-11, (g, k, relerr(s.get(k), o.get(k)))
+        assert abs(s.scalar("Sigma") - o.scalar("Sigma")) <= 1e-11 * o.scalar("Sigma"), g
+    assert saw_mutation
+
+
+def test_discrete_variables_free_running_reaches_the_grid_optimum():
+    gran = np.array([1.0, 1.0, 0.0, 1.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0])
+    s = _lib.Solver(n=10, population_size=8, objective="NegEllipsoid", initial_value=1.0, lower_bound=-19.0, upper_bound=21.0, granularity=gran, seed=5)
+    s.set_scalar("Termination Criteria/Max Value", -1e-9)
+    done = s.run(3000)
+    xb = s.get("Best Ever Variables")
+    assert np.all(xb[gran > 0] == 0.0) and abs(s.scalar("Best Ever Value")) < 1e-8, (done, xb)
+    with pytest.raises(KcmaError, match="Negative granularity"):
+        _lib.Solver(n=2, population_size=8, objective="NegSphere", initial_value=1.0, initial_stddev=1.0, granularity=np.array([1.0, -1.0]))
+
+
 def _constrained_problem(n):
     """4 half-space constraints g_c(x) = -(x_c - shift_c) <= 0 after helpers.py activeMax*: x_0, x_1 >= 1 (active at the
     optimum), x_2, x_3 >= -1 (violated by the initial mean -> viability regime, inactive at the optimum)."""

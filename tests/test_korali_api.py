@@ -399,3 +399,43 @@ def test_gradient_information_errors():
     e2["File Output"]["Enabled"] = False
     with pytest.raises(RuntimeError, match="Gradient Step Size must be larger than 0.0"):
         korali.Engine().run(e2)
+
+
+# ---------------------------------------------------------------- discrete variables ------------------------
+@pytest.mark.gpu
+def test_run_cmaes_discrete_example():
+    """examples/optimization/discrete/run-cmaes.py: 10 variables, four of them with Granularity 1.0."""
+    e = korali.Experiment()
+    e["Problem"]["Type"] = "Optimization"
+    e["Problem"]["Objective Function"] = discrete_model
+    for i in range(10):
+        e["Variables"][i]["Name"] = "X" + str(i)
+        e["Variables"][i]["Initial Value"] = 1.0
+        e["Variables"][i]["Lower Bound"] = -19.0
+        e["Variables"][i]["Upper Bound"] = +21.0
+    e["Variables"][0]["Granularity"] = 1.0
+    e["Variables"][1]["Granularity"] = 1.0
+    e["Variables"][3]["Granularity"] = 1.0
+    e["Variables"][6]["Granularity"] = 1.0
+    e["Solver"]["Type"] = "Optimizer/CMAES"
+    e["Solver"]["Population Size"] = 8
+    e["Solver"]["Termination Criteria"]["Min Value Difference Threshold"] = 1e-9
+    e["Solver"]["Termination Criteria"]["Max Generations"] = 5000
+    e["File Output"]["Enabled"] = False
+    e["Console Output"]["Verbosity"] = "Silent"
+    k = korali.Engine()
+    k.run(e)
+    best = e["Results"]["Best Sample"]["Parameters"]
+    assert all(best[i] == round(best[i]) for i in (0, 1, 3, 6))
+    assert abs(e["Results"]["Best Sample"]["F(x)"]) < 1e-6 and max(abs(v) for v in best) < 1e-2
+    e2 = korali.Experiment()
+    e2["Problem"]["Type"] = "Optimization"
+    e2["Problem"]["Objective Function"] = discrete_model
+    e2["Variables"][0]["Name"] = "X"
+    e2["Variables"][0]["Granularity"] = -1.0
+    e2["Solver"]["Type"] = "Optimizer/CMAES"
+    e2["Solver"]["Population Size"] = 8
+    e2["File Output"]["Enabled"] = False
+    e2["Console Output"]["Verbosity"] = "Silent"
+    with pytest.raises(RuntimeError, match="Negative granularity"):
+        korali.Engine().run(e2)

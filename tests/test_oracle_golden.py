@@ -201,3 +201,50 @@ def test_injected_gradients_replace_the_model_gradients():
     o.inject(INJ_F, -0.5 * (x**2).sum(1)); o.inject(INJ_GRAD, (-x).ravel())
     o.eval(); o.tell()
     assert np.isfinite(o.get("Current Mean")).all()
+
+
+# ---------------------------------------------------------------- discrete variables (Granularity) ----------
+def test_discrete_variables_restatement():
+    """CMAES.cpp.base:44-50, 515-544, 668, 730-734, 834-867: samples live on the grid of the discrete variables, the masking
+    matrices follow their definition, the step-size update uses the masked path length, the search reaches the grid optimum."""
+    n = 6
+    gran = np.array([1.0, 1.0, 0.0, 0.0, 0.5, 0.0])
+    o = O.Oracle(n=n, population_size=16, objective="NegSphere", initial_value=3.3, initial_stddev=2.0, seed=3, granularity=gran,
+                 lower_bound=-20.0, upper_bound=20.0)
+    o.set_scalar("Oracle/RNG Kind", 1)
+    assert o.scalar("Number Of Discrete Mutations") == 0 and o.scalar("Number Masking Matrix Entries") == 0
+    assert abs(o.scalar("Chi Square Number Discrete Mutations") - o.scalar("Chi Square Number")) < 1e-15
+    for g in range(80):
+        o.ask()
+        x = o.get("Sample Population").reshape(16, n)
+        disc = gran > 0
+        assert np.array_equal(x[:, disc], np.round(x[:, disc] / gran[disc]) * gran[disc]), g        # discretize()
+        ndm = int(o.scalar("Number Of Discrete Mutations"))
+        dm = o.get("Discrete Mutations").reshape(16, n)
+        assert not dm[ndm:].any()                                   # only the first samples are mutated ...
+        mask = o.get("Masking Matrix")
+        for i in range(max(ndm - 1, 0)):                            # ... in ONE masked dimension, by a multiple of its granularity
+            nz = np.flatnonzero(dm[i])
+            assert len(nz) <= 1 and all(mask[d] == 1.0 and abs(dm[i, d] / gran[d]) >= 1 and dm[i, d] / gran[d] == round(dm[i, d] / gran[d]) for d in nz)
+        sigma_before, ps_before = o.scalar("Sigma"), None
+        o.eval(); o.tell()
+        c = o.get("Covariance Matrix").reshape(n, n)
+        ps = o.get("Conjugate Evolution Path")
+        # updateDiscreteMutationMatrix with the sigma of before updateSigma and the new C
+        sd = sigma_before * np.sqrt(np.diag(c))
+        cs = o.scalar("Sigma Cumulation Factor")
+        msig = np.where(sd / np.sqrt(cs) < 0.2 * gran, 0.0, 1.0)
+        mk = np.where(2.0 * sd < gran, 1.0, 0.0)
+        assert np.array_equal(o.get("Masking Matrix Sigma"), msig) and np.array_equal(o.get("Masking Matrix"), mk), g
+        entries = n + 1 - int((msig == 0).sum())
+        chi = np.sqrt(entries) * (1. - 1. / (4. * entries) + 1. / (21. * entries * entries))
+        assert abs(o.scalar("Chi Square Number Discrete Mutations") - chi) < 1e-15
+        assert o.scalar("Number Of Discrete Mutations") == min(round(16 / 10.0 + mk.sum() + 1), np.floor(16 / 2.0) - 1)
+        want_sigma = sigma_before * np.exp(cs / o.scalar("Damp Factor") * (np.sqrt((msig * ps * ps).sum()) / chi - 1.))
+        # (escape-flat / sigma-bound corrections may apply on top: only check when they did not)
+        if abs(o.scalar("Sigma") - want_sigma) > 1e-12 * want_sigma:
+            assert o.scalar("Sigma") > want_sigma * 0.999
+    xb = o.get("Best Ever Variables")
+    assert np.all(xb[gran > 0] == 0.0) and np.abs(xb).max() < 1e-2 and o.scalar("Number Masking Matrix Entries") == 3
+    with pytest.raises(KcmaError, match="Negative granularity"):
+        O.Oracle(n=2, population_size=8, objective="NegSphere", initial_value=1.0, initial_stddev=1.0, granularity=np.array([1.0, -1.0]))
