@@ -89,7 +89,13 @@ class Handle:
 
     def _check(self, rc):
         if rc != 0:
-            raise KcmaError(self._fn("last_error", C.c_char_p, [C.c_void_p])(self._h).decode())
+            raise KcmaError(self._fn("last_error", C.c_char_p, [C.c_void_p])(self._live()).decode())
+
+    def _live(self):
+        """The handle, or an error instead of a NULL pointer into the library once close() was called."""
+        if not getattr(self, "_h", None):
+            raise KcmaError("the solver handle is closed")
+        return self._h
 
     def close(self):
         if getattr(self, "_h", None):
@@ -99,10 +105,10 @@ class Handle:
     __del__ = close
 
     # --- generation loop
-    def ask(self): self._check(self._fn("ask", C.c_int, [C.c_void_p])(self._h))
-    def eval(self): self._check(self._fn("eval", C.c_int, [C.c_void_p])(self._h))
-    def tell(self): self._check(self._fn("tell", C.c_int, [C.c_void_p])(self._h))
-    def run_generation(self): self._check(self._fn("run_generation", C.c_int, [C.c_void_p])(self._h))
+    def ask(self): self._check(self._fn("ask", C.c_int, [C.c_void_p])(self._live()))
+    def eval(self): self._check(self._fn("eval", C.c_int, [C.c_void_p])(self._live()))
+    def tell(self): self._check(self._fn("tell", C.c_int, [C.c_void_p])(self._live()))
+    def run_generation(self): self._check(self._fn("run_generation", C.c_int, [C.c_void_p])(self._live()))
 
     def run(self, max_generations):
         done = C.c_uint64(0)
@@ -117,38 +123,38 @@ class Handle:
         return bool(fin.value), (reason.value or b"").decode()
 
     def take_warnings(self):
-        return self._fn("take_warnings", C.c_char_p, [C.c_void_p])(self._h).decode()
+        return self._fn("take_warnings", C.c_char_p, [C.c_void_p])(self._live()).decode()
 
     def inject(self, kind, data):
         a = np.ascontiguousarray(data, dtype=np.float64).ravel()
-        self._check(self._fn("inject", C.c_int, [C.c_void_p, C.c_int, _dp, C.c_size_t])(self._h, kind, _as_dp(a), a.size))
+        self._check(self._fn("inject", C.c_int, [C.c_void_p, C.c_int, _dp, C.c_size_t])(self._live(), kind, _as_dp(a), a.size))
 
     # --- state
     def get(self, key):
         """Array by Korali key (1-D float64)."""
         f = self._fn("get_array", C.c_int, [C.c_void_p, C.c_char_p, _dp, C.c_size_t, C.POINTER(C.c_size_t)])
         cnt = C.c_size_t(0)
-        self._check(f(self._h, key.encode(), None, 0, C.byref(cnt)))
+        self._check(f(self._live(), key.encode(), None, 0, C.byref(cnt)))
         out = np.empty(cnt.value, dtype=np.float64)
-        self._check(f(self._h, key.encode(), _as_dp(out), out.size, C.byref(cnt)))
+        self._check(f(self._live(), key.encode(), _as_dp(out), out.size, C.byref(cnt)))
         return out
 
     def set(self, key, data):
         a = np.ascontiguousarray(data, dtype=np.float64).ravel()
-        self._check(self._fn("set_array", C.c_int, [C.c_void_p, C.c_char_p, _dp, C.c_size_t])(self._h, key.encode(), _as_dp(a), a.size))
+        self._check(self._fn("set_array", C.c_int, [C.c_void_p, C.c_char_p, _dp, C.c_size_t])(self._live(), key.encode(), _as_dp(a), a.size))
 
     def get_index(self, key):
         f = self._fn("get_index_array", C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_uint64), C.c_size_t, C.POINTER(C.c_size_t)])
         cnt = C.c_size_t(0)
-        self._check(f(self._h, key.encode(), None, 0, C.byref(cnt)))
+        self._check(f(self._live(), key.encode(), None, 0, C.byref(cnt)))
         out = np.empty(cnt.value, dtype=np.uint64)
-        self._check(f(self._h, key.encode(), out.ctypes.data_as(C.POINTER(C.c_uint64)), out.size, C.byref(cnt)))
+        self._check(f(self._live(), key.encode(), out.ctypes.data_as(C.POINTER(C.c_uint64)), out.size, C.byref(cnt)))
         return out
 
     def scalar(self, key):
         v = C.c_double(math.nan)
-        self._check(self._fn("get_scalar", C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_double)])(self._h, key.encode(), C.byref(v)))
+        self._check(self._fn("get_scalar", C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_double)])(self._live(), key.encode(), C.byref(v)))
         return v.value
 
     def set_scalar(self, key, value):
-        self._check(self._fn("set_scalar", C.c_int, [C.c_void_p, C.c_char_p, C.c_double])(self._h, key.encode(), float(value)))
+        self._check(self._fn("set_scalar", C.c_int, [C.c_void_p, C.c_char_p, C.c_double])(self._live(), key.encode(), float(value)))

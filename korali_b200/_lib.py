@@ -48,13 +48,13 @@ class Solver(Handle):
 
     def comm_init(self, unique_id):
         buf = (C.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
-        self._check(self._fn("comm_init", C.c_int, [C.c_void_p, C.POINTER(C.c_uint8)])(self._h, buf))
+        self._check(self._fn("comm_init", C.c_int, [C.c_void_p, C.POINTER(C.c_uint8)])(self._live(), buf))
 
     def timing_enable(self, on=True):
-        self._fn("timing_enable", C.c_int, [C.c_void_p, C.c_int])(self._h, int(on))
+        self._fn("timing_enable", C.c_int, [C.c_void_p, C.c_int])(self._live(), int(on))
 
     def timing_reset(self):
-        self._fn("timing_reset", C.c_int, [C.c_void_p])(self._h)
+        self._fn("timing_reset", C.c_int, [C.c_void_p])(self._live())
 
     def timing(self, phase):
         ms, calls = C.c_double(0), C.c_uint64(0)
@@ -63,7 +63,7 @@ class Solver(Handle):
         return ms.value, calls.value
 
     def launch_count(self):
-        return self._fn("launch_count", C.c_uint64, [C.c_void_p])(self._h)
+        return self._fn("launch_count", C.c_uint64, [C.c_void_p])(self._live())
 
     def set_host_objective(self, fn):
         """fn(X: ndarray[rows, n]) -> ndarray[rows]; the batched host conduit (needs keep_population=1)."""
@@ -73,7 +73,7 @@ class Solver(Handle):
             xs = np.ctypeslib.as_array(x, shape=(rows, n))
             np.ctypeslib.as_array(out, shape=(rows,))[:] = np.asarray(fn(xs), dtype=np.float64)
         self._host_obj = cb_t(tramp)
-        self._check(self._fn("set_host_objective", C.c_int, [C.c_void_p, cb_t, C.c_void_p])(self._h, self._host_obj, None))
+        self._check(self._fn("set_host_objective", C.c_int, [C.c_void_p, cb_t, C.c_void_p])(self._live(), self._host_obj, None))
 
     def set_host_objective_grad(self, fn):
         """fn(X: ndarray[rows, n]) -> (F: ndarray[rows], dF/dX: ndarray[rows, n]); needs use_gradient_information=1."""
@@ -85,7 +85,7 @@ class Solver(Handle):
             np.ctypeslib.as_array(out, shape=(rows,))[:] = np.asarray(f, dtype=np.float64)
             np.ctypeslib.as_array(gout, shape=(rows, n))[:] = np.asarray(g, dtype=np.float64).reshape(rows, n)
         self._host_obj_grad = cb_t(tramp)
-        self._check(self._fn("set_host_objective_grad", C.c_int, [C.c_void_p, cb_t, C.c_void_p])(self._h, self._host_obj_grad, None))
+        self._check(self._fn("set_host_objective_grad", C.c_int, [C.c_void_p, cb_t, C.c_void_p])(self._live(), self._host_obj_grad, None))
 
     def set_host_constraints(self, fn):
         """fn(X: ndarray[rows, n]) -> ndarray[n_constraints, rows]."""
@@ -95,10 +95,10 @@ class Solver(Handle):
             xs = np.ctypeslib.as_array(x, shape=(rows, n))
             np.ctypeslib.as_array(out, shape=(nc, rows))[:] = np.asarray(fn(xs), dtype=np.float64).reshape(nc, rows)
         self._host_con = cb_t(tramp)
-        self._check(self._fn("set_host_constraints", C.c_int, [C.c_void_p, cb_t, C.c_void_p])(self._h, self._host_con, None))
+        self._check(self._fn("set_host_constraints", C.c_int, [C.c_void_p, cb_t, C.c_void_p])(self._live(), self._host_con, None))
 
     def flush_l2(self):
-        self._check(self._fn("flush_l2", C.c_int, [C.c_void_p])(self._h))
+        self._check(self._fn("flush_l2", C.c_int, [C.c_void_p])(self._live()))
 
 
 def comm_unique_id():

@@ -1,6 +1,7 @@
 """Worker of tests/test_multi_gpu.py (launched with torch.distributed.run, one process per GPU): a population sharded
 over WORLD_SIZE ranks must reproduce the single-GPU run: same Philox samples (counters are global sample indices),
 identical ranking, and mean / paths / sigma / C equal up to the all-reduce summation order."""
+import faulthandler
 import os
 import sys
 import numpy as np
@@ -17,12 +18,19 @@ def relerr(a, b):
 
 
 def main():
+    faulthandler.enable()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     cases = [dict(n=64, population_size=512, objective="NegRosenbrock", initial_value=0.2, initial_stddev=0.8, seed=21),
              dict(n=130, population_size=1024, objective="NegEllipsoid", mirrored_sampling=1, initial_value=3.0, initial_stddev=1.0, seed=5),
-             dict(n=40, population_size=256, objective="NegSphere", diagonal_covariance=1, initial_value=1.0, initial_stddev=1.0, seed=9)]
+             dict(n=40, population_size=256, objective="NegSphere", diagonal_covariance=1, initial_value=1.0, initial_stddev=1.0, seed=9),
+             # gradient step of the mean: every rank adds its share of sum_i w_i step/sqrt(N) grad_i to the partial mean (all-reduced)
+             dict(n=48, population_size=256, objective="NegSphereSin2", initial_value=1.5, initial_stddev=1.0, seed=13,
+                  use_gradient_information=1, gradient_step_size=0.02),
+             # discrete variables: the mutations are keyed by the GLOBAL sample index, so the sharding must not change them
+             dict(n=24, population_size=128, objective="NegEllipsoid", initial_value=2.2, initial_stddev=1.5, seed=17, mirrored_sampling=1,
+                  granularity=np.array([1.0, 0.0, 0.5, 0.0] * 6))]
     verbose = os.environ.get("KCMA_TEST_VERBOSE")
     for case in cases:
         if verbose:
@@ -34,7 +42,7 @@ def main():
         dist.broadcast(uid, 0)
         s.comm_init(bytes(uid.cpu().tolist()))
         ref = _lib.Solver(device=local, **case) if rank == 0 else None
-        for g in range(12):
+        for g in range(40 if "granularity" in case else 12):   # discrete: long enough for the masking matrix to switch on
             if verbose:
                 print("rank", rank, "gen", g, flush=True)
             s.run_generation()
@@ -45,7 +53,7 @@ def main():
                     assert np.array_equal(s.get_index("Sorting Index"), ref.get_index("Sorting Index")), (case["objective"], g)
                     tol = 1e-13
                 else:        # the all-reduce sums C in a different order: last-bit differences feed back through the eigenvectors
-                    tol = 1e-9
+                    tol = 1e-9 if g < 12 else 1e-6   # (and keep growing over a long free run)
                 assert relerr(s.get("Value Vector"), ref.get("Value Vector")) < tol, (case["objective"], g)
                 for k in ["Current Mean", "Evolution Path", "Conjugate Evolution Path", "Covariance Matrix"]:
                     e = relerr(s.get(k), ref.get(k))
@@ -58,6 +66,8 @@ def main():
         assert torch.equal(c, c0), "replicated covariance differs between ranks"
         lo, hi = int(s.scalar("Shard Begin")), int(s.scalar("Shard End"))
         assert (lo, hi) == _lib.shard_range(case["population_size"], case.get("mirrored_sampling", 0), rank, world)
+        if "granularity" in case:
+            assert s.scalar("Number Of Discrete Mutations") > 0
         s.close()
         if rank == 0:
             print("ok", case["objective"], "world", world, flush=True)
