@@ -1082,12 +1082,14 @@ int kcma_create(const kcma_cfg* cfg, kcma_t** out) {
 }
 
 int kcma_set_host_objective(kcma_t* h, kcma_host_objective_fn fn, void* user) {
+  if (!h) return fail(nullptr, "null solver handle");
   invalidate_graph(h);
   if (fn && !h->cfg.keep_population) return fail(h, "a host objective needs keep_population = 1 (X is copied to the host every generation)");
   h->host_obj = fn; h->host_obj_user = user;
   return 0;
 }
 int kcma_set_host_objective_grad(kcma_t* h, kcma_host_objective_grad_fn fn, void* user) {
+  if (!h) return fail(nullptr, "null solver handle");
   invalidate_graph(h);
   if (fn && !h->cfg.use_gradient_information) return fail(h, "a gradient-returning host objective needs Use Gradient Information");
   if (fn && !h->cfg.keep_population) return fail(h, "a host objective needs keep_population = 1 (X is copied to the host every generation)");
@@ -1095,6 +1097,7 @@ int kcma_set_host_objective_grad(kcma_t* h, kcma_host_objective_grad_fn fn, void
   return 0;
 }
 int kcma_set_host_constraints(kcma_t* h, kcma_host_constraints_fn fn, void* user) {
+  if (!h) return fail(nullptr, "null solver handle");
   invalidate_graph(h);
   if (!h->has_constraints) return fail(h, "the problem has no constraints (n_constraints = 0)");
   if (fn && !h->cfg.keep_population) return fail(h, "host constraints need keep_population = 1 (X is copied to the host)");
@@ -1112,6 +1115,7 @@ int kcma_comm_unique_id(uint8_t id_out[128]) {
 }
 
 int kcma_comm_init(kcma_t* h, const uint8_t id_in[128]) {
+  if (!h) return fail(nullptr, "null solver handle");
   std::string err;
   if (!g_nccl.load(err)) return fail(h, "%s", err.c_str());
   CUDA_OK(h, cudaSetDevice(h->device));
@@ -1120,9 +1124,14 @@ int kcma_comm_init(kcma_t* h, const uint8_t id_in[128]) {
   return nccl_check(h, g_nccl.CommInitRank(&h->comm, h->cfg.nranks, id, h->cfg.rank), "ncclCommInitRank");
 }
 
-int kcma_ask(kcma_t* h) { CUDA_OK(h, cudaSetDevice(h->device)); return do_ask(h); }
+int kcma_ask(kcma_t* h) {
+  if (!h) return fail(nullptr, "null solver handle");
+  CUDA_OK(h, cudaSetDevice(h->device));
+  return do_ask(h);
+}
 
 int kcma_eval(kcma_t* h) {
+  if (!h) return fail(nullptr, "null solver handle");
   CUDA_OK(h, cudaSetDevice(h->device));
   if (do_eval(h)) return 1;
   if (pull_scalars(h)) return 1;
@@ -1135,6 +1144,7 @@ int kcma_eval(kcma_t* h) {
 }
 
 int kcma_tell(kcma_t* h) {
+  if (!h) return fail(nullptr, "null solver handle");
   CUDA_OK(h, cudaSetDevice(h->device));
   if (do_tell(h)) return 1;
   return end_of_generation(h);
@@ -1202,6 +1212,7 @@ bool build_graph(kcma* h) {
 }  // namespace
 
 int kcma_run_generation(kcma_t* h) {
+  if (!h) return fail(nullptr, "null solver handle");
   CUDA_OK(h, cudaSetDevice(h->device));
   if (graph_eligible(h) && (h->gexec || build_graph(h))) {
     CUDA_OK(h, cudaGraphLaunch(h->gexec, h->stream));
@@ -1219,6 +1230,7 @@ int kcma_run_generation(kcma_t* h) {
 }
 
 int kcma_check_termination(kcma_t* h, int* finished, const char** reason) {
+  if (!h) return fail(nullptr, "null solver handle");
   if (pull_scalars(h)) return 1;
   const DevScalars& s = *h->hSc;
   int fin = 0;
@@ -1243,6 +1255,7 @@ int kcma_check_termination(kcma_t* h, int* finished, const char** reason) {
 }
 
 int kcma_run(kcma_t* h, uint64_t max_generations, uint64_t* done) {
+  if (!h) return fail(nullptr, "null solver handle");
   uint64_t n = 0;
   int fin = 0;
   while (n < max_generations) {
@@ -1264,6 +1277,7 @@ static int upload_rows(kcma* h, double* dst, const double* src, size_t rows) {
 }
 
 int kcma_inject(kcma_t* h, int kind, const double* src, size_t count) {
+  if (!h) return fail(nullptr, "null solver handle");
   invalidate_graph(h);
   CUDA_OK(h, cudaSetDevice(h->device));
   const size_t N = h->N;
@@ -1359,6 +1373,7 @@ bool find_array(kcma* h, const char* key, ArrRef* r) {
 }  // namespace
 
 int kcma_get_array(kcma_t* h, const char* key, double* out, size_t cap, size_t* count) {
+  if (!h) return fail(nullptr, "null solver handle");
   CUDA_OK(h, cudaSetDevice(h->device));
   const size_t N = h->N;
   if (!strcmp(key, "BDZ Matrix") || !strcmp(key, "Sample Population")) {
@@ -1406,6 +1421,7 @@ int kcma_get_array(kcma_t* h, const char* key, double* out, size_t cap, size_t* 
 }
 
 int kcma_set_array(kcma_t* h, const char* key, const double* in, size_t count) {
+  if (!h) return fail(nullptr, "null solver handle");
   invalidate_graph(h);
   CUDA_OK(h, cudaSetDevice(h->device));
   ArrRef r;
@@ -1420,6 +1436,7 @@ int kcma_set_array(kcma_t* h, const char* key, const double* in, size_t count) {
 }
 
 int kcma_get_index_array(kcma_t* h, const char* key, uint64_t* out, size_t cap, size_t* count) {
+  if (!h) return fail(nullptr, "null solver handle");
   CUDA_OK(h, cudaSetDevice(h->device));
   const size_t n = h->cur_lambda;
   if (!strcmp(key, "Sample Constraint Violation Counts")) {
@@ -1472,6 +1489,7 @@ double* find_host_scalar(kcma* h, const char* key) {
 }  // namespace
 
 int kcma_get_scalar(kcma_t* h, const char* key, double* out) {
+  if (!h) return fail(nullptr, "null solver handle");
   CUDA_OK(h, cudaSetDevice(h->device));
   if (double* p = find_host_scalar(h, key)) { *out = *p; return 0; }
   if (pull_scalars(h)) return 1;
@@ -1495,6 +1513,7 @@ int kcma_get_scalar(kcma_t* h, const char* key, double* out) {
 }
 
 int kcma_set_scalar(kcma_t* h, const char* key, double v) {
+  if (!h) return fail(nullptr, "null solver handle");
   invalidate_graph(h);
   CUDA_OK(h, cudaSetDevice(h->device));
   if (double* p = find_host_scalar(h, key)) { *p = v; return 0; }
@@ -1515,17 +1534,19 @@ extern "C" int kcma_debug_jacobi_timestamps(long long* out3584) {
   if (!kc::g_jacobi_dbg) return 1;
   return cudaMemcpy(out3584, kc::g_jacobi_dbg, sizeof(long long) * 3584, cudaMemcpyDeviceToHost) != cudaSuccess;
 }
-int kcma_timing_enable(kcma_t* h, int on) { h->timing = on != 0; return 0; }   // the graph path is skipped while timing
+int kcma_timing_enable(kcma_t* h, int on) { if (!h) return fail(nullptr, "null solver handle"); h->timing = on != 0; return 0; }   // the graph path is skipped while timing
 int kcma_timing_get(kcma_t* h, const char* phase, double* ms, uint64_t* calls) {
+  if (!h) return fail(nullptr, "null solver handle");
   resolve_timers(h);
   auto it = h->phases.find(phase);
   if (ms) *ms = it == h->phases.end() ? 0.0 : it->second.ms;
   if (calls) *calls = it == h->phases.end() ? 0 : it->second.calls;
   return 0;
 }
-int kcma_timing_reset(kcma_t* h) { resolve_timers(h); h->phases.clear(); return 0; }
+int kcma_timing_reset(kcma_t* h) { if (!h) return fail(nullptr, "null solver handle"); resolve_timers(h); h->phases.clear(); return 0; }
 uint64_t kcma_launch_count(const kcma_t* h) { return h->launches; }
 int kcma_flush_l2(kcma_t* h) {
+  if (!h) return fail(nullptr, "null solver handle");
   CUDA_OK(h, cudaSetDevice(h->device));
   if (!h->dFlush) { h->flush_bytes = 256ull << 20; CUDA_OK(h, cudaMalloc(&h->dFlush, h->flush_bytes)); }
   flush_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>((double*)h->dFlush, h->flush_bytes / sizeof(double));

@@ -70,3 +70,20 @@ def test_no_cpu_fallback():
         _lib.Solver(n=4, population_size=8, initial_value=np.zeros(4), initial_stddev=np.ones(4))
     with pytest.raises(KcmaError):
         _lib.k_sort_index(np.arange(4.0))
+
+
+def test_null_handle_is_an_error_not_a_crash():
+    """Every entry point that takes a handle returns non-zero for NULL (kcma_last_error(NULL) explains), and the Python
+    wrapper refuses to pass a closed handle into the library."""
+    import ctypes as C
+    lib = _lib.lib()
+    for name, extra in [("kcma_run_generation", []), ("kcma_ask", []), ("kcma_eval", []), ("kcma_tell", []),
+                        ("kcma_timing_enable", [C.c_int(1)]), ("kcma_timing_reset", []), ("kcma_flush_l2", [])]:
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = C.c_int, [C.c_void_p] + [type(a) for a in extra]
+        assert fn(None, *extra) != 0, name
+    out = C.c_double()
+    lib.kcma_get_scalar.restype, lib.kcma_get_scalar.argtypes = C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_double)]
+    assert lib.kcma_get_scalar(None, b"Sigma", C.byref(out)) != 0
+    lib.kcma_last_error.restype, lib.kcma_last_error.argtypes = C.c_char_p, [C.c_void_p]
+    assert b"null solver handle" in lib.kcma_last_error(None)
