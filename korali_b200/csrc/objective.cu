@@ -27,12 +27,30 @@ struct XRow {
 template <int OBJ>
 __device__ __forceinline__ double eval_row(const XRow& x, int n, const double* __restrict__ coef, int lane) {
   double p = 0.0, p2 = 0.0;
+  // The lane-strided partial sums are accumulated in index order (the canonical order shared with the oracle); the loads of
+  // 8 consecutive terms are issued together so that every warp keeps 2 KB in flight (HBM latency x bandwidth).
   if (OBJ == KCMA_OBJ_NEG_SPHERE || OBJ == KCMA_OBJ_NEG_SUMSQ) {
-    for (int i = lane; i < n; i += 32) { const double v = x(i); p = __dadd_rn(p, __dmul_rn(v, v)); }
+    int i = lane;
+    for (; i + 32 * 7 < n; i += 32 * 8) {
+      double v[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) v[k] = x(i + 32 * k);
+#pragma unroll
+      for (int k = 0; k < 8; k++) p = __dadd_rn(p, __dmul_rn(v[k], v[k]));
+    }
+    for (; i < n; i += 32) { const double v = x(i); p = __dadd_rn(p, __dmul_rn(v, v)); }
     const double s = warp_sum_butterfly(p);
     return OBJ == KCMA_OBJ_NEG_SPHERE ? __dmul_rn(-0.5, s) : -s;
   } else if (OBJ == KCMA_OBJ_NEG_ELLIPSOID) {
-    for (int i = lane; i < n; i += 32) { const double v = x(i); p = __dadd_rn(p, __dmul_rn(coef[i], __dmul_rn(v, v))); }
+    int i = lane;
+    for (; i + 32 * 7 < n; i += 32 * 8) {
+      double v[8], c[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) { v[k] = x(i + 32 * k); c[k] = coef[i + 32 * k]; }
+#pragma unroll
+      for (int k = 0; k < 8; k++) p = __dadd_rn(p, __dmul_rn(c[k], __dmul_rn(v[k], v[k])));
+    }
+    for (; i < n; i += 32) { const double v = x(i); p = __dadd_rn(p, __dmul_rn(coef[i], __dmul_rn(v, v))); }
     return -warp_sum_butterfly(p);
   } else if (OBJ == KCMA_OBJ_NEG_ROSENBROCK) {
     for (int i = lane; i + 1 < n; i += 32) {

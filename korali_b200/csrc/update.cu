@@ -154,7 +154,15 @@ mean_reduce_kernel(const double* __restrict__ partial, const int* __restrict__ c
   if (d >= n) return;
   const int nparts = (*count_ptr + rows_per_cta - 1) / rows_per_cta;
   double a = 0.0;
-  for (int p = 0; p < nparts; p++) a += partial[(size_t)p * ld + d];
+  int p = 0;
+  for (; p + 16 <= nparts; p += 16) {   // 16 loads in flight, added in the same fixed order
+    double v[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) v[k] = partial[(size_t)(p + k) * ld + d];
+#pragma unroll
+    for (int k = 0; k < 16; k++) a += v[k];
+  }
+  for (; p < nparts; p++) a += partial[(size_t)p * ld + d];
   mean_out[d] = a;
   const unsigned long long b = sc->best_valid_sample;
   double bx = 0.0;
