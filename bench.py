@@ -184,6 +184,7 @@ def ours_arm(args, rank, world):
     ms = e0.elapsed_time(e1)
     launches = s.launch_count() - l0
     phases = {p: s.timing(p) for p in ["eigen", "rng", "sample_gemm", "objective", "sort", "gather_mean", "rank_mu", "paths", "collectives", "generation"]}
+    sweeps = s.timing("eigen_sweeps")[1] / args.steps   # (counted on the device: read before the e2e leg adds its own)
     s.timing_enable(False)
     # ---- end-to-end through the reference-facing call: kcma_run (Experiment::run loop incl. termination chain) ----
     barrier()
@@ -211,7 +212,6 @@ def ours_arm(args, rank, world):
     rk_ms, rk_calls = phases["rank_mu"]
     rk_avg = rk_ms / max(rk_calls, 1)
     cpu = cpu_reference_run(8, 1) if world == 1 else None   # ~10 s of host work: 9 x 1024-sample generations + one eigendecomposition
-    sweeps = s.timing("eigen_sweeps")[1] / args.steps
     line = {
         "metric": METRIC, "value": gens, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -223,7 +223,9 @@ def ours_arm(args, rank, world):
                 "note": "kcma_run(): Experiment::run loop with the termination chain evaluated on the host every generation (device scalars "
                         "copied back each step); the generation loop takes no per-step host input (samples are drawn on the device from "
                         "Philox(seed, generation) counters). Runs without phase timers (one CUDA-graph replay per generation), "
-                        "whereas `value` is timed with the per-phase CUDA events and the per-generation sweep-count readback enabled"},
+                        "whereas `value` is timed with eager launches and the per-phase CUDA events enabled. The e2e leg continues from the "
+                        "state the timed leg left (generations K+W+1 .. 2K+W): the spectrum has spread a little more by then and the "
+                        "warm-started eigensolver needs about one sweep less per generation"},
         "gpu_launches": int(launches),
         "clocks": clk,
         "roofline": {"kernel": "gemm_tn_tma_kernel (sampling GEMM Y = Z (B D)^T, TMA + mbarrier + DMMA.8x8x4)", "bound": "tensor",

@@ -119,6 +119,7 @@ struct kcma {
   std::vector<Pending> pending;
   std::vector<cudaEvent_t> event_pool;
   uint64_t launches = 0;
+  uint64_t sweeps_base = 0;   // DevScalars::jacobi_sweeps_total at the last kcma_timing_reset
   // CUDA graph of one whole generation (ask + eval + tell) for the launch-latency-bound configurations
   cudaStream_t cap_stream = nullptr;
   cudaGraphExec_t gexec = nullptr;
@@ -403,7 +404,7 @@ int update_eigensystem(kcma* h, const double* dM) {
   if (persistent) {
     h->launches += 1;
     h->scalars_fresh = false;
-    if (h->timing) { if (pull_scalars(h)) return 1; h->phases["eigen_sweeps"].calls += h->hSc->jacobi_sweeps; }
+    // (sweep count: accumulated on the device in DevScalars::jacobi_sweeps_total and read by kcma_timing_get, no sync here)
   } else
   for (int sweep = 0; sweep < max_sweeps; sweep++) {
     int l = 0;
@@ -1541,9 +1542,22 @@ int kcma_timing_get(kcma_t* h, const char* phase, double* ms, uint64_t* calls) {
   auto it = h->phases.find(phase);
   if (ms) *ms = it == h->phases.end() ? 0.0 : it->second.ms;
   if (calls) *calls = it == h->phases.end() ? 0 : it->second.calls;
+  if (calls && !strcmp(phase, "eigen_sweeps")) {   // persistent kernel: counted on the device; per-step path: counted by the host loop
+    h->scalars_fresh = false;
+    if (pull_scalars(h)) return 1;
+    *calls += h->hSc->jacobi_sweeps_total - h->sweeps_base;
+  }
   return 0;
 }
-int kcma_timing_reset(kcma_t* h) { if (!h) return fail(nullptr, "null solver handle"); resolve_timers(h); h->phases.clear(); return 0; }
+int kcma_timing_reset(kcma_t* h) {
+  if (!h) return fail(nullptr, "null solver handle");
+  resolve_timers(h);
+  h->phases.clear();
+  h->scalars_fresh = false;
+  if (pull_scalars(h)) return 1;
+  h->sweeps_base = h->hSc->jacobi_sweeps_total;
+  return 0;
+}
 uint64_t kcma_launch_count(const kcma_t* h) { return h->launches; }
 int kcma_flush_l2(kcma_t* h) {
   if (!h) return fail(nullptr, "null solver handle");

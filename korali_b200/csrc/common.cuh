@@ -81,6 +81,7 @@ struct DevScalars {
   double disc_path_l2;       // sum_d maskingMatrixSigma[d] * ps[d]^2 (:733)
   int n_mask;                // _numberMaskingMatrixEntries
   int n_disc_mut;            // _numberOfDiscreteMutations
+  unsigned long long jacobi_sweeps_total;   // sweeps of the persistent Jacobi kernel since creation (read once by the timers)
   unsigned long long gen;    // generation counter for CUDA-graph replays (kernels launched with generation == kGenFromDevice read it)
 };
 

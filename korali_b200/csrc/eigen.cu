@@ -94,7 +94,10 @@ jacobi_pipe_kernel(double* GT, double* VT, int ld, int n, int nb, double tol, in
   __syncthreads();
 
   for (int sweep = 0; sweep < max_sweeps; sweep++) {
-    if (blockIdx.x == 0 && tid == 0) { sc->jacobi_rotations = 0; sc->jacobi_max_rel_bits = 0ull; sc->jacobi_sweeps = sweep + 1; }
+    if (blockIdx.x == 0 && tid == 0) {
+      sc->jacobi_rotations = 0; sc->jacobi_max_rel_bits = 0ull; sc->jacobi_sweeps = sweep + 1;
+      sc->jacobi_sweeps_total += 1;
+    }
     int sweep_rot = 0, sweep_big = 0;
     grid.sync();
     if (warp < NWG) {
