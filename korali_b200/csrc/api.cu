@@ -414,8 +414,8 @@ int update_eigensystem(kcma* h, const double* dM) {
     h->scalars_fresh = false;
     if (pull_scalars(h)) return 1;
     if (h->hSc->jacobi_rotations == 0) break;
-    // quadratic convergence: once every rotated pair was already orthogonal to 1e-10, what is left after this sweep is
-    // ~1e-20/gap and the confirmation sweep (a full pass that rotates nothing) can be skipped
+    // quadratic convergence: once every pair of the sweep was already orthogonal to 1e-8 (KC_QUAD_TAIL), what is left after
+    // this sweep is ~1e-16 * lambda / gap and the confirmation sweep (a full pass that rotates nothing) can be skipped
     double max_rel;
     memcpy(&max_rel, &h->hSc->jacobi_max_rel_bits, sizeof(double));
     if (max_rel < 1e-20) break;   // the kernels record the SQUARED cosine

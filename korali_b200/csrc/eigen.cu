@@ -870,7 +870,7 @@ jacobi_big_step_kernel(double* GT, double* VT, int ld, int n, int nsb, int step,
           if (on) {
             if (!jacobi_cs_fast(alpha, beta, gamma, c, sn)) jacobi_cs_scaled(alpha, beta, gamma, c, sn);
             my_rot++;
-            my_big |= (g2 > 1e-20 * ab) ? 1 : 0;
+            my_big |= (g2 > KC_QUAD_TAIL * ab) ? 1 : 0;
           }
           const double x = Gam[p * BIG_LDS + lane], y = Gam[q * BIG_LDS + lane];
           const double a = Rm[p * BIG_LDS + lane], b = Rm[q * BIG_LDS + lane];

@@ -24,6 +24,12 @@
 
 namespace kc {
 
+// A sweep in which every rotated pair already had cos^2 below this value is the last one: the rotations of that sweep leave
+// cos ~ (cos_before)^2 * (lambda / gap), so the confirmation sweep (a full pass that rotates nothing) would be redundant.
+#ifndef KC_QUAD_TAIL
+#define KC_QUAD_TAIL 1e-16
+#endif
+
 KC_HD double rsqrt_seed(double a) {   // ~2^-22 relative
 #if defined(__CUDA_ARCH__)
   double r;
@@ -103,7 +109,7 @@ struct Inner8 {
   double g[8][8];
   double rc[8];       // column (lane & 7) of R
   int rotations;      // plane rotations applied
-  int big;            // some rotated pair still had cos^2 >= 1e-20 (not yet in the quadratic tail)
+  int big;            // some pair still had cos^2 >= KC_QUAD_TAIL (not yet in the quadratic tail)
 };
 
 template <int I, int J>
@@ -172,12 +178,12 @@ KC_HD void round4(Inner8& m, double tol2) {
   rot_apply<P3, Q3>(m, c3, s3, t3);
 }
 
-// cos^2 of the pair (P, Q) above tol2? Also records whether it is still >= 1e-20 (not yet in the quadratic tail).
+// cos^2 of the pair (P, Q) above tol2? Also records whether it is still >= KC_QUAD_TAIL (not yet in the quadratic tail).
 template <int P, int Q>
 KC_HD bool pair_on(Inner8& m, double tol2) {
   const double gamma = m.g[P][Q];
   const double g2 = gamma * gamma, ab = m.g[P][P] * m.g[Q][Q];
-  m.big |= (g2 > 1e-20 * ab) ? 1 : 0;
+  m.big |= (g2 > KC_QUAD_TAIL * ab) ? 1 : 0;
   return g2 > tol2 * ab;
 }
 
