@@ -6,8 +6,10 @@
 // ~c1+cmu per generation), form G = C V0 with the FP64 tensor-core GEMM and orthogonalise the columns of G by plane
 // rotations accumulated into V. At convergence C V = G has orthogonal columns: V holds the eigenvectors and
 // lambda_i = v_i . g_i (Rayleigh quotient, signed). Vectors are stored as ROWS (VT, GT) so rotations touch contiguous memory.
-// Kernels: eigen_small_kernel (tiny N, everything in one launch), jacobi_pipe_kernel (persistent cooperative, warp-specialised
-// Gram-update steps on the DMMA pipe), jacobi_gram_step_kernel (the same step, one launch each, for large N). DESIGN.md section 6.
+// Kernels: eigen_small_kernel (tiny N, everything in one launch), jacobi_pipe_kernel (24 < N <= 1184: persistent cooperative,
+// warp-specialised Gram-update steps on the DMMA pipe, 4-row blocks), jacobi_big_step_kernel (larger N: one launch per
+// tournament step, 16-row blocks, V updated one launch late), jacobi_gram_step_kernel (4-row blocks per launch, A/B only).
+// DESIGN.md section 6.
 #include <cooperative_groups.h>
 #include <stdlib.h>
 
