@@ -219,7 +219,7 @@ def ours_arm(args, rank, world):
         "config": {"workload": WORKLOAD_NAME, "n": n, "lambda": lam, "mu": mu, "parallelism": "population sharded x%d" % world,
                    "l2_hygiene": "inputs larger than L2: Z and Y are %.0f MB each per rank, re-streamed every generation" % (8.0 * n * lam / world / 1e6),
                    "best_ever_value_after_run": best},
-        "e2e": {"value": done / t_e2e, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 256,
+        "e2e": {"value": done / t_e2e, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 288,   # sizeof(DevScalars): the termination chain reads it once per generation
                 "note": "kcma_run(): Experiment::run loop with the termination chain evaluated on the host every generation (device scalars "
                         "copied back each step); the generation loop takes no per-step host input (samples are drawn on the device from "
                         "Philox(seed, generation) counters). Runs without phase timers (one CUDA-graph replay per generation), "
