@@ -1,0 +1,107 @@
+"""CPU simulation (numpy) of the blocked one-sided Jacobi used by korali_b200/csrc/eigen.cu: how many sweeps do different
+block sizes / orderings / inner strategies need on the kind of matrix config 3 produces early on (clustered spectrum,
+cold or warm start)? Evidence for DESIGN.md section 10 - not part of the product.
+
+    python profiles/microbench/jacobi_orderings_sim.py [N]
+"""
+import sys
+import numpy as np
+
+
+def rr_pairs(nb, step):
+    m = nb - 1
+    out = []
+    for k in range(nb // 2):
+        a, b = (m, step) if k == 0 else ((step + k) % m, (step - k + m) % m)
+        out.append((min(a, b), max(a, b)))
+    return out
+
+
+def rotate_pairs(gam, R, pairs, tol2, big_thr):
+    """gam: [P, r, r] Gram matrices, R: [P, r, r]; pairs: list of disjoint (p, q). One round, vectorised over P."""
+    rot = 0
+    big = False
+    for p, q in pairs:
+        a, b, g = gam[:, p, p], gam[:, q, q], gam[:, p, q]
+        on = g * g > tol2 * a * b
+        big |= bool(np.any(g * g > big_thr * a * b))
+        rot += int(on.sum())
+        d = b - a
+        g2 = 2 * g
+        h = np.sqrt(d * d + g2 * g2)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            t = np.where(on, np.sign(np.where(d == 0, 1.0, d)) * g2 / (np.abs(d) + h), 0.0)
+        t = np.nan_to_num(t)
+        c = 1.0 / np.sqrt(1 + t * t)
+        s = c * t
+        c, s = c[:, None], s[:, None]
+        for M in (gam, R):                      # rows
+            x, y = M[:, p, :].copy(), M[:, q, :].copy()
+            M[:, p, :] = c * x - s * y
+            M[:, q, :] = s * x + c * y
+        x, y = gam[:, :, p].copy(), gam[:, :, q].copy()      # columns of gamma
+        gam[:, :, p] = c * x - s * y
+        gam[:, :, q] = s * x + c * y
+    return rot, big
+
+
+def sweep(G, b, tol2, big_thr, inner_passes=1, sort_rows=False):
+    n = G.shape[0]
+    nb = n // b
+    rot_total, big_any = 0, False
+    for step in range(nb - 1):
+        prs = rr_pairs(nb, step)
+        idx = np.array([list(range(I * b, I * b + b)) + list(range(J * b, J * b + b)) for I, J in prs])   # [P, 2b]
+        rows = G[idx]                                                                                     # [P, 2b, n]
+        gam = np.einsum("pik,pjk->pij", rows, rows)
+        R = np.tile(np.eye(2 * b), (len(prs), 1, 1))
+        for _ in range(inner_passes):
+            if step == 0:    # all pairs of the 2b rows
+                for r in range(2 * b - 1):
+                    ro, bg = rotate_pairs(gam, R, rr_pairs(2 * b, r), tol2, big_thr)
+                    rot_total += ro; big_any |= bg
+            else:            # cross pairs only
+                for r in range(b):
+                    ro, bg = rotate_pairs(gam, R, [(k, b + (k + r) % b) for k in range(b)], tol2, big_thr)
+                    rot_total += ro; big_any |= bg
+        G[idx] = np.einsum("pij,pjk->pik", R, rows)
+    if sort_rows:   # de Rijk: keep the rows ordered by decreasing norm
+        G[:] = G[np.argsort(-np.einsum("ij,ij->i", G, G), kind="stable")]
+    return rot_total, big_any
+
+
+def solve(C, V0, b, inner_passes=1, sort_rows=False, big_thr=1e-16, max_sweeps=40):
+    n = C.shape[0]
+    G = (C @ V0).T.copy()
+    tol2 = (4 * 2.2e-16 * np.sqrt(n)) ** 2
+    for s in range(1, max_sweeps + 1):
+        rot, big = sweep(G, b, tol2, big_thr, inner_passes, sort_rows)
+        if rot == 0 or not big:
+            break
+    lam = np.sqrt(np.einsum("ij,ij->i", G, G))
+    off = np.abs((G / lam[:, None]) @ (G / lam[:, None]).T - np.eye(n)).max()
+    return s, off
+
+
+if __name__ == "__main__":
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+    rng = np.random.default_rng(0)
+    # config-3-like early covariance: C = (1 - cmu) I + cmu * sample covariance of mu_eff-ish samples, a few generations deep
+    def gen_c(c, cmu=0.035, m=4 * n):
+        z = rng.standard_normal((m, n)) @ np.linalg.cholesky(c).T
+        return (1 - cmu) * c + cmu * (z.T @ z) / m
+    c = np.eye(n)
+    for _ in range(4):
+        c_prev, c = c, gen_c(c)
+    w_prev, v_prev = np.linalg.eigh(c_prev)
+    print("N = %d, spectrum spread of C: %.3g .. %.3g" % (n, *np.linalg.eigvalsh(c)[[0, -1]]))
+    for name, kw in [("4-row blocks, one cross pass (the kernels)", dict(b=4)),
+                     ("4-row blocks, two cross passes per step", dict(b=4, inner_passes=2)),
+                     ("8-row blocks, one cross pass", dict(b=8)),
+                     ("16-row blocks, one cross pass (large-N kernel)", dict(b=16)),
+                     ("4-row blocks + rows re-sorted by norm after each sweep", dict(b=4, sort_rows=True)),
+                     ("4-row blocks, last-sweep criterion 1e-20 (old)", dict(b=4, big_thr=1e-20)),
+                     ("4-row blocks, last-sweep criterion 1e-14", dict(b=4, big_thr=1e-14))]:
+        cold = solve(c, np.eye(n), **kw)
+        warm = solve(c, v_prev, **kw)
+        print("  %-58s cold start: %2d sweeps (max |cos| left %.1e)   warm start: %2d sweeps (%.1e)" % (name, cold[0], cold[1], warm[0], warm[1]))
