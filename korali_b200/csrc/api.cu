@@ -935,6 +935,7 @@ int kcma_create(const kcma_cfg* cfg, kcma_t** out) {
   h->init_val = copyv(cfg->initial_value, N, NAN);
   h->init_sd = copyv(cfg->initial_stddev, N, NAN);
   h->min_sd = copyv(cfg->min_stddev_update, N, 0.0);
+  h->cfg.gradient_step_size = (double)(float)cfg->gradient_step_size;   // _gradientStepSize is a float (CMAES.hpp:61)
   h->gran = copyv(cfg->granularity, N, 0.0);
   h->cfg.granularity = nullptr;
   for (int i = 0; i < N; i++) {   // CMAES.cpp.base:44-50

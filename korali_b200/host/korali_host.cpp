@@ -235,7 +235,7 @@ class CMAES {
     cfg.initial_sigma_cumulation_factor = s.num("Initial Sigma Cumulation Factor", -1.0);
     cfg.initial_damp_factor = s.num("Initial Damp Factor", -1.0);
     cfg.use_gradient_information = s.boolean("Use Gradient Information", 0);
-    cfg.gradient_step_size = s.num("Gradient Step Size", 0.01);
+    cfg.gradient_step_size = (double)(float)s.num("Gradient Step Size", 0.01);   // a float in the reference: dumps 0.009999999776...
     cfg.is_sigma_bounded = s.boolean("Is Sigma Bounded", 0);
     cfg.initial_cumulative_covariance = s.num("Initial Cumulative Covariance", -1.0);
     cfg.diagonal_covariance = s.boolean("Diagonal Covariance", 0);

@@ -728,6 +728,7 @@ int okcma_create(const kcma_cfg* cfg, okcma_t** out) {
 
   h->X = dalloc(h->s_max * N); h->BDZ = dalloc(h->s_max * N); h->aux_bdz = dalloc(N);
   if (h->cfg.use_gradient_information) h->gradients = dalloc(h->s_max * N); /* ref :82-85 */
+  h->cfg.gradient_step_size = (double)(float)h->cfg.gradient_step_size; /* _gradientStepSize is a float (CMAES.hpp:61) */
   if (h->has_discrete) { /* ref :101-107 */
     h->masking_matrix = dalloc(N); h->masking_matrix_sigma = dalloc(N); h->discrete_mutations = dalloc(h->s_max * N);
     h->n_mask = 0; h->n_discrete_mutations = 0;

@@ -359,7 +359,7 @@ def test_run_cmaes_gradient_example():
         e["File Output"]["Enabled"] = False
         korali.Engine().run(e)
         runs[(use_grad, obj if isinstance(obj, str) else "python")] = (e["Solver"]["Best Ever Value"], e["Solver"]["Current Mean"], e["Current Generation"])
-        assert e["Solver"]["Use Gradient Information"] == (1 if use_grad else 0) and e["Solver"]["Gradient Step Size"] == 0.01
+        assert e["Solver"]["Use Gradient Information"] == (1 if use_grad else 0) and e["Solver"]["Gradient Step Size"] == float(np.float32(0.01))   # a float in the reference
     with_grad, without, device = runs[(True, "python")], runs[(False, "python")], runs[(True, "Sphere")]
     assert with_grad[2] == without[2] == 100
     assert abs(with_grad[0]) < 1e-6 and abs(without[0]) < 1e-6        # both converge to the optimum 0 at x = 0

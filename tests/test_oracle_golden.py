@@ -178,7 +178,7 @@ def test_gradient_step_of_the_mean_follows_the_reference_loop():
             for i in range(len(w)):
                 m += w[i] * x[idx[i], d]
             for i in range(len(w)):
-                m += w[i] * 2e-5 / np.sqrt(6.0) * grads[idx[i], d]
+                m += w[i] * float(np.float32(2e-5)) / np.sqrt(6.0) * grads[idx[i], d]   # the step size is a float in the reference (Q9)
             want[d] = m
         assert np.array_equal(a.get("Current Mean"), want), g
     plain = O.Oracle(**case)
