@@ -73,6 +73,9 @@ def test_koralijson_cursor_semantics():
     (lambda e: e["Solver"].__setitem__("Population Size", "eight"), "Population Size"),
     (lambda e: e["Solver"].__setitem__("Mu Type", "Quadratic"), "Invalid setting of Mu Type"),
     (lambda e: e["Variables"][0].__setitem__("Granularity", -1.0), "Negative granularity"),
+    (lambda e: e["Variables"][0].__setitem__("Granularity", "coarse"), "Granularity"),
+    (lambda e: e["Solver"].__setitem__("Use Gradient Information", "yes"), "Use Gradient Information"),
+    (lambda e: e["Solver"].__setitem__("Gradient Step Size", "big"), "Gradient Step Size"),
     (lambda e: e["Variables"][0].__setitem__("Colour", "red"), "Unrecognized settings"),
     (lambda e: e["Solver"]["Termination Criteria"].__setitem__("Max Fun", 1), "Unrecognized settings"),
     (lambda e: e["Solver"].__setitem__("Type", "Optimizer/DEA"), "only 'Optimizer/CMAES'"),
