@@ -12,6 +12,7 @@
 // DESIGN.md section 6.
 #include <cooperative_groups.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "jacobi_inner.cuh"
@@ -24,13 +25,10 @@ namespace kc {
 __global__ void reset_rotations_kernel(DevScalars* sc) { sc->jacobi_rotations = 0; sc->jacobi_max_rel_bits = 0ull; }
 
 
-// Round-robin (chess tournament) schedule over np = even number of players; step in [0, np-1), k in [0, np/2).
-__device__ __forceinline__ void rr_pair(int np, int step, int k, int& p, int& q) {
-  const int m = np - 1;
-  int a, b;
-  if (k == 0) { a = m; b = step; }
-  else { a = (step + k) % m; b = (step - k + m) % m; }
-  p = min(a, b); q = max(a, b);
+// (rr_pair / ring_pair: the tournament schedules, jacobi_inner.cuh)
+template <int ORDER>
+__device__ __forceinline__ void tournament_pair(int np, int step, int k, int& p, int& q) {
+  if (ORDER == 1) ring_pair(np, step, k, p, q); else rr_pair(np, step, k, p, q);
 }
 
 // 256-bit global accesses (SASS LDG.E.ENL2.256 / STG.E.ENL2.256, sm_100+): a lane moves 4 consecutive doubles, so the four
@@ -52,7 +50,8 @@ __device__ __forceinline__ void stcg_256(double* p, double a, double b, double c
 //         of the rotated rows ARE the entries of the updated Gamma), accumulating R (8x8);
 //   (iii) rows <- R rows for G and V as DMMAs, written back once.
 // Steps are ordered by point-to-point ready flags (each block is produced by one CTA and consumed by one), a grid barrier
-// only once per sweep. The kernel is WARP-SPECIALISED around what the phase timestamps of the first, uniform version showed
+// only once per sweep. The pairing of a step comes from tournament_pair<ORDER>: the ring order (ORDER = 1, power-of-two block
+// count, the default whenever its phantom blocks cost <= 1/8 more steps) or the round-robin order (ORDER = 0). The kernel is WARP-SPECIALISED around what the phase timestamps of the first, uniform version showed
 // (profiles/microbench/jacobi_phases.py; 18-20k cycles per step): 40 % of a step were the 4 rotation rounds on Gamma in
 // shared memory (LDS/STS round trips queue behind the step's own global loads in the MIO pipe), 30 % the loads (G fetched
 // twice, in the Gram and in the apply layout, plus V), 20 % apply + stores of G AND V, 10 % the flag handshake. Here:
@@ -62,7 +61,7 @@ __device__ __forceinline__ void stcg_256(double* p, double a, double b, double c
 //   * V group (the last NWV warps, none on warp 0's scheduler) applies the same R to the V rows behind it, decoupled:
 //     R travels through a small ring in shared memory, V blocks have their own ready flags, nothing on the G path waits for V.
 // ------------------------------------------------------------------------------------------------------
-template <int NT>
+template <int NT, int ORDER /* 0: round-robin, 1: ring (nb = power of two) */>
 __global__ void __launch_bounds__(NT, 1)
 jacobi_pipe_kernel(double* GT, double* VT, int ld, int n, int nb, double tol, int max_sweeps, DevScalars* sc, unsigned* readyG,
                    unsigned* readyV, long long* dbg /* nullable: phase timestamps (profiles/microbench/jacobi_phases.py) */, int dbg_sweep, int dbg_step0) {
@@ -106,7 +105,7 @@ jacobi_pipe_kernel(double* GT, double* VT, int ld, int n, int nb, double tol, in
       // =========================== G group: the critical path ===========================
       for (int step = 0; step < nb - 1; step++) {
         int I, J;
-        rr_pair(nb, step, blockIdx.x, I, J);
+        tournament_pair<ORDER>(nb, step, blockIdx.x, I, J);
         const int slot = epoch & (RING - 1);
         KCMA_TS(0);
         if (dbg && blockIdx.x == 1 && tid == 0 && sweep == dbg_sweep && step < 1024) dbg[512 + step] = clock64();
@@ -225,7 +224,7 @@ jacobi_pipe_kernel(double* GT, double* VT, int ld, int n, int nb, double tol, in
       const int vtid = tid - NWG * 32, vw = warp - NWG;
       for (int step = 0; step < nb - 1; step++) {
         int I, J;
-        rr_pair(nb, step, blockIdx.x, I, J);
+        tournament_pair<ORDER>(nb, step, blockIdx.x, I, J);
         const int slot = epoch & (RING - 1);
         KCMA_TSV(9);
         if (dbg && blockIdx.x == 1 && tid == NWG * 32 && sweep == dbg_sweep && step < 1024) dbg[512 + 1024 + step] = clock64();
@@ -656,12 +655,22 @@ bool launch_jacobi_persistent(cudaStream_t st, double* GT, double* VT, int ld, i
   if (nb / 2 > num_sms || ld > 1280) return false;
   const char* e = getenv("KCMA_JACOBI_PERSISTENT");
   if (e && atoi(e) == 0) return false;
+  // Tournament order (read per call so that one process can A/B both): the ring order needs a power-of-two block count;
+  // it is used when the phantom blocks that pads in cost less than the sweep it saves (<= 1/8 more steps) and the padded
+  // round is still co-resident; otherwise, or with KCMA_JACOBI_ORDER=rr, the round-robin order. Measured on config 3 (same box,
+  // profiles/r01_jacobi_order_ab.log): 7.80 instead of 8.65 sweeps per decomposition, 13.2 instead of 14.6 ms.
+  int nb_ring = 2;
+  while (nb_ring < nb) nb_ring <<= 1;
+  const char* oe = getenv("KCMA_JACOBI_ORDER");
+  const bool ring = !(oe && strcmp(oe, "rr") == 0) && nb_ring / 2 <= num_sms && (nb_ring - nb) * 8 <= nb && 2 * nb_ring <= ld;
+  if (ring) nb = nb_ring;
   static int coop = -1;
   if (coop < 0) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-    if (coop && cudaFuncSetAttribute(jacobi_pipe_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem - 16 * 1024) != cudaSuccess)
+    if (coop && (cudaFuncSetAttribute(jacobi_pipe_kernel<256, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem - 16 * 1024) != cudaSuccess ||
+                 cudaFuncSetAttribute(jacobi_pipe_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem - 16 * 1024) != cudaSuccess))
       coop = 0;
   }
   if (!coop) return false;
@@ -678,7 +687,8 @@ bool launch_jacobi_persistent(cudaStream_t st, double* GT, double* VT, int ld, i
   cudaMemsetAsync(ready, 0, sizeof(unsigned) * 2 * nb, st);
   unsigned* ready_v = ready + nb;
   void* args[] = {&GT, &VT, &ld, &n, &nb, &tol, &max_sweeps, &sc, &ready, &ready_v, &dbg, &dbg_sweep, &dbg_step0};
-  if (cudaLaunchCooperativeKernel((void*)jacobi_pipe_kernel<256>, dim3(nb / 2), dim3(256), args, smem, st) == cudaSuccess) return true;
+  const void* fn = ring ? (const void*)jacobi_pipe_kernel<256, 1> : (const void*)jacobi_pipe_kernel<256, 0>;
+  if (cudaLaunchCooperativeKernel(fn, dim3(nb / 2), dim3(256), args, smem, st) == cudaSuccess) return true;
   cudaGetLastError();
   return false;
 }

@@ -24,6 +24,30 @@
 
 namespace kc {
 
+// Round-robin (chess tournament) schedule over np = even number of players; step in [0, np-1), k in [0, np/2).
+KC_HD void rr_pair(int np, int step, int k, int& p, int& q) {
+  const int m = np - 1;
+  int a, b;
+  if (k == 0) { a = m; b = step; }
+  else { a = (step + k) % m; b = (step - k + m) % m; }
+  p = a < b ? a : b; q = a < b ? b : a;
+}
+
+// Ring tournament over np = power-of-two players: the first half A anchors, the second half B travels round a ring — in step s
+// slot k pairs A[k] with B[(k + s) mod np/2] — and after np/2 steps the tournaments inside A and inside B run side by side with
+// the same construction (slots 0..np/4-1 and np/4..np/2-1). np - 1 steps of np/2 disjoint pairs, every pair exactly once
+// (profiles/microbench/jacobi_orderings_sim.py checks the 1-factorisation and the sweep counts: one sweep fewer than the
+// round-robin order on CMA-ES covariances, warm-started or not). Players >= the real block count are phantom blocks (rows >= n).
+KC_HD void ring_pair(int np, int step, int k, int& p, int& q) {
+  int base = 0;
+  for (;;) {
+    const int h = np >> 1;
+    if (step < h) { p = base + k; q = base + h + ((k + step) & (h - 1)); return; }
+    step -= h;
+    if (k >= (h >> 1)) { base += h; k -= h >> 1; }
+    np = h;
+  }
+}
 // A sweep in which every rotated pair already had cos^2 below this value is the last one: the rotations of that sweep leave
 // cos ~ (cos_before)^2 * (lambda / gap), so the confirmation sweep (a full pass that rotates nothing) would be redundant.
 #ifndef KC_QUAD_TAIL

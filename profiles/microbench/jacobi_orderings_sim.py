@@ -17,6 +17,37 @@ def rr_pairs(nb, step):
     return out
 
 
+def ring_schedule(blocks):
+    """Tournament in which one block of every pair STAYS with its CTA for long runs of steps.
+    blocks: list whose length is a power of two. First half = anchors A, second half = movers B: in step s anchor A[i] meets
+    B[(i + s) mod n/2] (the movers travel round a ring, one neighbour hop per step, the anchors never move: n/2 steps); then the
+    tournaments inside A and inside B run side by side with the same construction (anchors of A keep their CTA again).
+    n - 1 steps of n/2 disjoint pairs, every pair exactly once; an anchor changes only log2(n) times per sweep."""
+    n = len(blocks)
+    if n == 2:
+        return [[(blocks[0], blocks[1])]]
+    h = n // 2
+    A, B = blocks[:h], blocks[h:]
+    steps = [[(A[i], B[(i + s) % h]) for i in range(h)] for s in range(h)]
+    for x, y in zip(ring_schedule(A), ring_schedule(B)):
+        steps.append(x + y)
+    return steps
+
+
+def check_schedule(steps, nb):
+    seen = set()
+    for st in steps:
+        used = [b for pr in st for b in pr]
+        assert len(used) == nb and len(set(used)) == nb            # every block exactly once per step
+        for a, b in st:
+            key = (min(a, b), max(a, b))
+            assert key not in seen
+            seen.add(key)
+    assert len(seen) == nb * (nb - 1) // 2 and len(steps) == nb - 1    # every pair exactly once per sweep
+    stay = sum(1 for s in range(1, len(steps)) for k in range(nb // 2) if steps[s][k][0] == steps[s - 1][k][0])
+    return stay / ((len(steps) - 1) * (nb // 2))
+
+
 def rotate_pairs(gam, R, pairs, tol2, big_thr):
     """gam: [P, r, r] Gram matrices, R: [P, r, r]; pairs: list of disjoint (p, q). One round, vectorised over P."""
     rot = 0
@@ -45,12 +76,13 @@ def rotate_pairs(gam, R, pairs, tol2, big_thr):
     return rot, big
 
 
-def sweep(G, b, tol2, big_thr, inner_passes=1, sort_rows=False):
+def sweep(G, b, tol2, big_thr, inner_passes=1, sort_rows=False, ordering="round-robin"):
     n = G.shape[0]
     nb = n // b
     rot_total, big_any = 0, False
+    ring = ring_schedule(list(range(nb))) if ordering == "ring" else None
     for step in range(nb - 1):
-        prs = rr_pairs(nb, step)
+        prs = [(min(a, c), max(a, c)) for a, c in ring[step]] if ring else rr_pairs(nb, step)
         idx = np.array([list(range(I * b, I * b + b)) + list(range(J * b, J * b + b)) for I, J in prs])   # [P, 2b]
         rows = G[idx]                                                                                     # [P, 2b, n]
         gam = np.einsum("pik,pjk->pij", rows, rows)
@@ -70,12 +102,12 @@ def sweep(G, b, tol2, big_thr, inner_passes=1, sort_rows=False):
     return rot_total, big_any
 
 
-def solve(C, V0, b, inner_passes=1, sort_rows=False, big_thr=1e-16, max_sweeps=40):
+def solve(C, V0, b, inner_passes=1, sort_rows=False, big_thr=1e-16, max_sweeps=40, ordering="round-robin"):
     n = C.shape[0]
     G = (C @ V0).T.copy()
     tol2 = (4 * 2.2e-16 * np.sqrt(n)) ** 2
     for s in range(1, max_sweeps + 1):
-        rot, big = sweep(G, b, tol2, big_thr, inner_passes, sort_rows)
+        rot, big = sweep(G, b, tol2, big_thr, inner_passes, sort_rows, ordering)
         if rot == 0 or not big:
             break
     lam = np.sqrt(np.einsum("ij,ij->i", G, G))
@@ -95,7 +127,11 @@ if __name__ == "__main__":
         c_prev, c = c, gen_c(c)
     w_prev, v_prev = np.linalg.eigh(c_prev)
     print("N = %d, spectrum spread of C: %.3g .. %.3g" % (n, *np.linalg.eigvalsh(c)[[0, -1]]))
+    for nb in (8, 64, 256):
+        print("  ring schedule, %3d blocks: valid 1-factorisation, the first block of a CTA's pair stays in %.1f %% of the step transitions"
+              % (nb, 100 * check_schedule(ring_schedule(list(range(nb))), nb)))
     for name, kw in [("4-row blocks, one cross pass (the kernels)", dict(b=4)),
+                     ("4-row blocks, ring schedule (one block of each pair stays put)", dict(b=4, ordering="ring")),
                      ("4-row blocks, two cross passes per step", dict(b=4, inner_passes=2)),
                      ("8-row blocks, one cross pass", dict(b=8)),
                      ("16-row blocks, one cross pass (large-N kernel)", dict(b=16)),

@@ -25,4 +25,8 @@ void jacobi_cs_host(double alpha, double beta, double gamma, double* c, double* 
   *safe = kc::jacobi_cs_fast(alpha, beta, gamma, *c, *s) ? 1 : 0;
   if (!*safe) kc::jacobi_cs_scaled(alpha, beta, gamma, *c, *s);
 }
+// Tournament schedules of the persistent eigensolver: order 0 = round-robin, 1 = ring (np = power of two).
+void jacobi_pair_host(int order, int np, int step, int k, int* p, int* q) {
+  if (order == 1) kc::ring_pair(np, step, k, *p, *q); else kc::rr_pair(np, step, k, *p, *q);
+}
 }

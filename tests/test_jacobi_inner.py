@@ -34,6 +34,7 @@ def inner(tmp_path_factory):
         lib.jacobi_cs_host(a, b, g, C.byref(c), C.byref(s), C.byref(safe))
         return c.value, s.value, safe.value
     run.cs = cs
+    run.lib = lib
     return run
 
 
@@ -119,3 +120,32 @@ def test_inner_solver_quadratic_tail_and_noop(inner):
     G4 = G.copy(); G4[6:, :] = 0.0; G4[:, 6:] = 0.0
     R4, Go4, rot4, _ = inner(G4, 1e-14, 0)
     assert np.isfinite(R4).all() and np.isfinite(Go4).all() and np.array_equal(R4[6:, 6:], np.eye(2))
+
+
+@pytest.mark.parametrize("order,sizes", [(0, [2, 4, 6, 8, 26, 250, 296]), (1, [2, 4, 8, 16, 32, 256])])
+def test_tournament_schedules_are_one_factorisations(inner, order, sizes):
+    """Both tournament orders of jacobi_pipe_kernel (rr_pair / ring_pair, the code the kernel runs): every step pairs every
+    block exactly once, every pair of blocks meets exactly once per sweep, p < q. The ring order additionally keeps the
+    first block of slot k in place for all but log2(np) - 1 of the step transitions (what a resident-anchor kernel needs)."""
+    so = inner.lib
+    for nb in sizes:
+        seen = set()
+        prev_p, stays = None, 0
+        for step in range(nb - 1):
+            used, ps = [], []
+            for k in range(nb // 2):
+                p, q = C.c_int(-1), C.c_int(-1)
+                so.jacobi_pair_host(order, nb, step, k, C.byref(p), C.byref(q))
+                assert 0 <= p.value < q.value < nb
+                used += [p.value, q.value]
+                ps.append(p.value)
+                assert (p.value, q.value) not in seen
+                seen.add((p.value, q.value))
+            assert sorted(used) == list(range(nb))
+            if prev_p is not None:
+                stays += sum(1 for a, b in zip(ps, prev_p) if a == b)
+            prev_p = ps
+        assert len(seen) == nb * (nb - 1) // 2
+        if order == 1 and nb >= 8:
+            # slot k changes its first block only when a sub-tournament hands it a block of the B half: at most once per level
+            assert stays >= (nb - 2) * (nb // 2) - (nb // 2) * (int(np.log2(nb)) - 1)
