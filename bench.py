@@ -31,6 +31,16 @@ def flops_per_generation(n, lam, mu):
     return 2.0 * n * n * lam, float(n) * (n + 1) * mu
 
 
+def jacobi_blocks(n, num_sms=148):
+    """(real 4-row blocks, blocks the tournament runs over, ring order?) — the dispatch rule of launch_jacobi_persistent (eigen.cu)."""
+    nb = ((n + 3) // 4 + 1) & ~1
+    nb_ring = 2
+    while nb_ring < nb:
+        nb_ring *= 2
+    ring = os.environ.get("KCMA_JACOBI_ORDER") != "rr" and nb_ring // 2 <= num_sms and (nb_ring - nb) * 8 <= nb
+    return nb, (nb_ring if ring else nb), ring
+
+
 def load_peaks():
     out = {}
     for name in ("MEASURED_PEAKS.json", "MEASURED_FP64.json"):
@@ -242,11 +252,13 @@ def ours_arm(args, rank, world):
         "hbm_kernels": hbm_block(phases, args.steps, n, lam // world, mu // world, peaks.get("hbm_gbs", 6547.2)),
         "eigen": {"kernel": "jacobi_pipe_kernel (persistent cooperative one-sided Jacobi, Gram-update steps on DMMA.8x8x4; replicated on every rank)",
                   "avg_ms": phases["eigen"][0] / args.steps, "sweeps_per_generation": sweeps,
-                  "bound": "latency: N-1 dependent rotation rounds per sweep; a step = flag handshake + 64 KB row fetch + Gram + 4 rounds + apply",
+                  "bound": "latency: one dependent tournament step per pair of 4-row blocks and sweep; a step = flag handshake + 64 KB row fetch + Gram + 4 rounds + apply",
                   # executed flops: per step and block pair 3 x (2 * 8 * 8 * N) for Gram, apply G, apply V; (N/4 - 1) * N/8 pair-steps per sweep
                   "executed_flops_per_sweep": 12.0 * n ** 3,
                   "achieved_tflops": (12.0 * n ** 3 * sweeps / (phases["eigen"][0] / args.steps * 1e-3) * 1e-12) if phases["eigen"][0] > 0 else 0.0,
-                  "us_per_step_of_8_rows": (phases["eigen"][0] / args.steps * 1e3 / max(sweeps * (n / 4.0 - 1.0), 1e-9))},
+                  "tournament": "ring order, %d steps per sweep (%d real + %d phantom 4-row blocks)" % (jacobi_blocks(n)[1] - 1, jacobi_blocks(n)[0], jacobi_blocks(n)[1] - jacobi_blocks(n)[0])
+                                if jacobi_blocks(n)[2] else "round-robin order, %d steps per sweep" % (jacobi_blocks(n)[0] - 1),
+                  "us_per_step_of_8_rows": (phases["eigen"][0] / args.steps * 1e3 / max(sweeps * (jacobi_blocks(n)[1] - 1.0), 1e-9))},
         "eigen_sweeps_per_generation": sweeps,
         "gens_per_sec_excluding_eigen": 1e3 / max(ms_step - phases["eigen"][0] / args.steps, 1e-9),
     }
