@@ -80,15 +80,22 @@ def sweep(G, b, tol2, big_thr, inner_passes=1, sort_rows=False, ordering="round-
     n = G.shape[0]
     nb = n // b
     rot_total, big_any = 0, False
-    ring = ring_schedule(list(range(nb))) if ordering == "ring" else None
-    for step in range(nb - 1):
+    ring = ring_schedule(list(range(nb))) if ordering.startswith("ring") else None
+    if ordering == "ring-reversed":      # innermost sub-tournaments first, the A x B phase of the top level last
+        ring = ring[::-1]
+    if ordering.startswith("ring+local"):   # "ring+local<m>x<r>": after the sweep, r more passes of the sub-tournaments inside
+        m, r = (int(x) for x in ordering[len("ring+local"):].split("x"))   # groups of m consecutive blocks (the last m - 1 steps)
+        ring = ring + ring[-(m - 1):] * r
+    for step in range(len(ring) if ring else nb - 1):
         prs = [(min(a, c), max(a, c)) for a, c in ring[step]] if ring else rr_pairs(nb, step)
+        if step == 0:
+            first_prs = prs
         idx = np.array([list(range(I * b, I * b + b)) + list(range(J * b, J * b + b)) for I, J in prs])   # [P, 2b]
         rows = G[idx]                                                                                     # [P, 2b, n]
         gam = np.einsum("pik,pjk->pij", rows, rows)
         R = np.tile(np.eye(2 * b), (len(prs), 1, 1))
         for _ in range(inner_passes):
-            if step == 0:    # all pairs of the 2b rows
+            if step == 0 or (ring and step >= nb - 1 and prs == first_prs):    # all pairs of the 2b rows
                 for r in range(2 * b - 1):
                     ro, bg = rotate_pairs(gam, R, rr_pairs(2 * b, r), tol2, big_thr)
                     rot_total += ro; big_any |= bg
@@ -107,7 +114,10 @@ def solve(C, V0, b, inner_passes=1, sort_rows=False, big_thr=1e-16, max_sweeps=4
     G = (C @ V0).T.copy()
     tol2 = (4 * 2.2e-16 * np.sqrt(n)) ** 2
     for s in range(1, max_sweeps + 1):
-        rot, big = sweep(G, b, tol2, big_thr, inner_passes, sort_rows, ordering)
+        o = ordering
+        if ordering == "ring-alternating":   # forward on odd sweeps, reversed on even ones
+            o = "ring" if s % 2 else "ring-reversed"
+        rot, big = sweep(G, b, tol2, big_thr, inner_passes, sort_rows, o)
         if rot == 0 or not big:
             break
     lam = np.sqrt(np.einsum("ij,ij->i", G, G))

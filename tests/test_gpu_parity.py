@@ -165,6 +165,24 @@ def test_eigen_clustered_and_repeated_spectrum(n):
     assert np.abs(v2.T @ v2 - np.eye(n)).max() < 1e-12
 
 
+@pytest.mark.parametrize("order", ["rr", "ring"])
+@pytest.mark.parametrize("n", [31, 120, 1000])
+def test_eigen_tournament_orders(order, n, monkeypatch):
+    """Both tournament orders of jacobi_pipe_kernel (KCMA_JACOBI_ORDER, read per launch; the ring order is the default at
+    these sizes: 8, 32 and 256 blocks) give a decomposition of the same quality; the eigenvalues agree to round-off."""
+    monkeypatch.setenv("KCMA_JACOBI_ORDER", order)
+    rng = np.random.default_rng(77 + n)
+    q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    lam = np.sort(10.0 ** rng.uniform(0, 3, n))
+    c = (q * lam) @ q.T
+    c = 0.5 * (c + c.T)
+    w, v = _lib.k_eigen(c)
+    assert np.all(np.diff(w) >= 0)
+    assert np.abs(v @ np.diag(w) @ v.T - c).max() < 1e-12 * np.abs(c).max()
+    assert np.abs(v.T @ v - np.eye(n)).max() < 1e-12
+    assert np.abs(w - lam).max() < 1e-11 * lam.max()
+
+
 def test_eigen_identity_and_rejection():
     w, v = _lib.k_eigen(np.eye(7) * 2.0)
     assert np.allclose(w, 2.0) and np.abs(v.T @ v - np.eye(7)).max() < 1e-14
