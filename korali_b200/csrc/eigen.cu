@@ -768,8 +768,8 @@ __device__ __forceinline__ void big_apply(double* M, int ld, int n, int I, int J
 // prev_step < 0: nothing pending; do_g == 0: flush launch (only the pending V update).
 template <int NT>
 __global__ void __launch_bounds__(NT, 1)
-jacobi_big_step_kernel(double* GT, double* VT, int ld, int n, int nsb, int step, int prev_step, int do_g, double tol, DevScalars* sc,
-                       const double* __restrict__ rlog_prev, double* __restrict__ rlog_cur) {
+jacobi_big_step_kernel(double* GT, double* VT, int ld, int n, int nsb, int order /* 0: round-robin, 1: ring (nsb = 2^k) */, int step,
+                       int prev_step, int do_g, double tol, DevScalars* sc, const double* __restrict__ rlog_prev, double* __restrict__ rlog_cur) {
   constexpr int NW = NT / 32, NWG = NW / 2, NWV = NW - NWG;
   constexpr int PPW = BIG_B / NWG;                       // rotation pairs per warp of the G group
   extern __shared__ __align__(16) double big_smem[];
@@ -783,13 +783,13 @@ jacobi_big_step_kernel(double* GT, double* VT, int ld, int n, int nsb, int step,
   if (tid == 0) { s_rot = 0; s_big = 0; }
   __syncthreads();
   int I = 0, J = 0;
-  if (do_g) rr_pair(nsb, step, blockIdx.x, I, J);
+  if (do_g) { if (order == 1) ring_pair(nsb, step, blockIdx.x, I, J); else rr_pair(nsb, step, blockIdx.x, I, J); }
 
   if (warp >= NWG) {
     // ================= V group: the pending update of the previous step =================
     if (prev_step >= 0) {
       int Ip, Jp;
-      rr_pair(nsb, prev_step, blockIdx.x, Ip, Jp);
+      if (order == 1) ring_pair(nsb, prev_step, blockIdx.x, Ip, Jp); else rr_pair(nsb, prev_step, blockIdx.x, Ip, Jp);
       const double* src = rlog_prev + (size_t)blockIdx.x * BIG_RLOG;
       if (src[BIG_R * BIG_R] != 0.0) {
         const int vt = tid - NWG * 32;
@@ -944,11 +944,22 @@ bool big_enabled() {
   static const int big = getenv("KCMA_JACOBI_BIG") ? atoi(getenv("KCMA_JACOBI_BIG")) : 1;
   return big != 0;
 }
-void big_launch(cudaStream_t st, double* GT, double* VT, int ld, int n, int nsb, int step, int do_g, double tol, DevScalars* sc) {
+// Block count and tournament order of the 16-row-block path: the ring order (jacobi_inner.cuh) when padding the block count
+// to a power of two costs <= 1/8 more steps (N = 4096: 256 blocks, no padding), else (or KCMA_JACOBI_ORDER=rr) round-robin.
+int big_blocks(int n, int* order) {
+  int nsb = ((n + BIG_B - 1) / BIG_B + 1) & ~1;
+  int nsb_ring = 2;
+  while (nsb_ring < nsb) nsb_ring <<= 1;
+  const char* oe = getenv("KCMA_JACOBI_ORDER");
+  const bool ring = !(oe && strcmp(oe, "rr") == 0) && (nsb_ring - nsb) * 8 <= nsb;
+  *order = ring ? 1 : 0;
+  return ring ? nsb_ring : nsb;
+}
+void big_launch(cudaStream_t st, double* GT, double* VT, int ld, int n, int nsb, int order, int step, int do_g, double tol, DevScalars* sc) {
   BigState& b = big_state();
   double* cur = b.rlog + (size_t)(b.launch & 1u) * b.pairs * BIG_RLOG;
   const double* prev = b.rlog + (size_t)((b.launch & 1u) ^ 1u) * b.pairs * BIG_RLOG;
-  jacobi_big_step_kernel<BIG_NT><<<nsb / 2, BIG_NT, big_smem_bytes(), st>>>(GT, VT, ld, n, nsb, step, b.pending, do_g, tol, sc, prev, cur);
+  jacobi_big_step_kernel<BIG_NT><<<nsb / 2, BIG_NT, big_smem_bytes(), st>>>(GT, VT, ld, n, nsb, order, step, b.pending, do_g, tol, sc, prev, cur);
   b.launch++;
   b.pending = do_g ? step : -1;
 }
@@ -957,7 +968,8 @@ void big_launch(cudaStream_t st, double* GT, double* VT, int ld, int n, int nsb,
 void launch_jacobi_block_sweep(cudaStream_t st, double* GT, double* VT, int ld, int n, double tol, DevScalars* sc, int* launches) {
   reset_rotations_kernel<<<1, 1, 0, st>>>(sc);
   if (big_enabled()) {   // 16-row blocks: N/16 - 1 steps per sweep
-    const int nsb = ((n + BIG_B - 1) / BIG_B + 1) & ~1;
+    int order = 0;
+    const int nsb = big_blocks(n, &order);
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(jacobi_big_step_kernel<BIG_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_smem_bytes()); attr = true; }
     BigState& b = big_state();
@@ -968,7 +980,7 @@ void launch_jacobi_block_sweep(cudaStream_t st, double* GT, double* VT, int ld, 
       cudaMalloc(&b.rlog, sizeof(double) * 2 * b.pairs * BIG_RLOG);
       b.pending = -1;
     }
-    for (int step = 0; step < nsb - 1; step++) big_launch(st, GT, VT, ld, n, nsb, step, 1, tol, sc);
+    for (int step = 0; step < nsb - 1; step++) big_launch(st, GT, VT, ld, n, nsb, order, step, 1, tol, sc);
     if (launches) *launches += nsb;
     return;
   }
@@ -980,8 +992,9 @@ void launch_jacobi_block_sweep(cudaStream_t st, double* GT, double* VT, int ld, 
 // The V update of the last step is still pending after the last sweep.
 void launch_jacobi_block_flush(cudaStream_t st, double* GT, double* VT, int ld, int n, double tol, DevScalars* sc, int* launches) {
   if (!big_enabled() || big_state().pending < 0) return;
-  const int nsb = ((n + BIG_B - 1) / BIG_B + 1) & ~1;
-  big_launch(st, GT, VT, ld, n, nsb, 0, 0, tol, sc);
+  int order = 0;
+  const int nsb = big_blocks(n, &order);
+  big_launch(st, GT, VT, ld, n, nsb, order, 0, 0, tol, sc);
   if (launches) *launches += 1;
 }
 

@@ -183,6 +183,23 @@ def test_eigen_tournament_orders(order, n, monkeypatch):
     assert np.abs(w - lam).max() < 1e-11 * lam.max()
 
 
+@pytest.mark.parametrize("order", ["rr", "ring"])
+def test_eigen_tournament_orders_large_n_path(order, monkeypatch):
+    """N = 2000 runs on the one-launch-per-step path with 16-row blocks (126 blocks, 128 with the ring order's two phantom
+    blocks): both orders must deliver the decomposition; clustered CMA-ES-like spectrum."""
+    monkeypatch.setenv("KCMA_JACOBI_ORDER", order)
+    n = 2000
+    rng = np.random.default_rng(2000)
+    z = rng.standard_normal((2 * n, n))
+    c = 0.965 * np.eye(n) + 0.035 * (z.T @ z) / (2 * n)
+    c = 0.5 * (c + c.T)
+    w, v = _lib.k_eigen(c)
+    assert np.all(np.diff(w) >= 0)
+    assert np.abs(v @ np.diag(w) @ v.T - c).max() < 1e-12 * np.abs(c).max()
+    assert np.abs(v.T @ v - np.eye(n)).max() < 1e-12
+    assert np.abs(w - np.linalg.eigvalsh(c)).max() < 1e-12 * np.abs(w).max()
+
+
 def test_eigen_identity_and_rejection():
     w, v = _lib.k_eigen(np.eye(7) * 2.0)
     assert np.allclose(w, 2.0) and np.abs(v.T @ v - np.eye(7)).max() < 1e-14
