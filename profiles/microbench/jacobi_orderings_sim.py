@@ -34,6 +34,33 @@ def ring_schedule(blocks):
     return steps
 
 
+def xor_schedule(nb, order="descending"):
+    """Step s pairs block i with block i XOR s (nb = power of two): a 1-factorisation for s = 1 .. nb-1 in any order.
+    descending: s = nb-1 .. 1 (partners differing in the top bit first, neighbours i ^ 1 last); ascending: the reverse;
+    gray: s runs through the top-bit-first levels like the ring order, inside a level in Gray-code order."""
+    ss = list(range(nb - 1, 0, -1)) if order == "descending" else list(range(1, nb))
+    if order == "gray":
+        ss, h = [], nb // 2
+        while h >= 1:
+            ss += [h + (j ^ (j >> 1)) for j in range(h)]
+            h //= 2
+    return [[(i, i ^ s) for i in range(nb) if i < (i ^ s)] for s in ss]
+
+
+def oddeven_schedule(nb):
+    """Odd-even transposition: the blocks sit on a line; even steps pair positions (0,1)(2,3).., odd steps (1,2)(3,4).. and
+    the two blocks of a pair swap places after meeting. nb steps; a step of the odd phase leaves the two end blocks idle."""
+    pos = list(range(nb))
+    steps = []
+    for s in range(nb):
+        st = []
+        for a in range(s % 2, nb - 1, 2):
+            st.append((pos[a], pos[a + 1]))
+            pos[a], pos[a + 1] = pos[a + 1], pos[a]
+        steps.append(st)
+    return steps
+
+
 def check_schedule(steps, nb):
     seen = set()
     for st in steps:
@@ -81,6 +108,10 @@ def sweep(G, b, tol2, big_thr, inner_passes=1, sort_rows=False, ordering="round-
     nb = n // b
     rot_total, big_any = 0, False
     ring = ring_schedule(list(range(nb))) if ordering.startswith("ring") else None
+    if ordering.startswith("xor-"):
+        ring = xor_schedule(nb, ordering[4:])
+    if ordering == "odd-even":
+        ring = oddeven_schedule(nb)
     if ordering == "ring-reversed":      # innermost sub-tournaments first, the A x B phase of the top level last
         ring = ring[::-1]
     if ordering.startswith("ring+local"):   # "ring+local<m>x<r>": after the sweep, r more passes of the sub-tournaments inside
