@@ -75,6 +75,9 @@ def check_schedule(steps, nb):
     return stay / ((len(steps) - 1) * (nb // 2))
 
 
+INNER_SUBBLOCK = False   # set by callers: order of the cross pairs inside a step (see sweep)
+
+
 def rotate_pairs(gam, R, pairs, tol2, big_thr):
     """gam: [P, r, r] Gram matrices, R: [P, r, r]; pairs: list of disjoint (p, q). One round, vectorised over P."""
     rot = 0
@@ -130,6 +133,13 @@ def sweep(G, b, tol2, big_thr, inner_passes=1, sort_rows=False, ordering="round-
                 for r in range(2 * b - 1):
                     ro, bg = rotate_pairs(gam, R, rr_pairs(2 * b, r), tol2, big_thr)
                     rot_total += ro; big_any |= bg
+            elif INNER_SUBBLOCK and b % 2 == 0:   # cross pairs as two local phases of half-block problems: (A0,B0) | (A1,B1), then (A0,B1) | (A1,B0)
+                hb = b // 2
+                for ph in range(2):
+                    for r in range(hb):
+                        prs_in = [(k, b + ph * hb + (k + r) % hb) for k in range(hb)] + [(hb + k, b + (1 - ph) * hb + (k + r) % hb) for k in range(hb)]
+                        ro, bg = rotate_pairs(gam, R, prs_in, tol2, big_thr)
+                        rot_total += ro; big_any |= bg
             else:            # cross pairs only
                 for r in range(b):
                     ro, bg = rotate_pairs(gam, R, [(k, b + (k + r) % b) for k in range(b)], tol2, big_thr)
