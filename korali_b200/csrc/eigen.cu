@@ -28,7 +28,7 @@ __global__ void reset_rotations_kernel(DevScalars* sc) { sc->jacobi_rotations = 
 // (rr_pair / ring_pair: the tournament schedules, jacobi_inner.cuh)
 template <int ORDER>
 __device__ __forceinline__ void tournament_pair(int np, int step, int k, int& p, int& q) {
-  if (ORDER == 1) ring_pair(np, step, k, p, q); else rr_pair(np, step, k, p, q);
+  if (ORDER >= 1) ring_pair(np, step, k, p, q); else rr_pair(np, step, k, p, q);
 }
 
 // 256-bit global accesses (SASS LDG.E.ENL2.256 / STG.E.ENL2.256, sm_100+): a lane moves 4 consecutive doubles, so the four
@@ -61,13 +61,17 @@ __device__ __forceinline__ void stcg_256(double* p, double a, double b, double c
 //   * V group (the last NWV warps, none on warp 0's scheduler) applies the same R to the V rows behind it, decoupled:
 //     R travels through a small ring in shared memory, V blocks have their own ready flags, nothing on the G path waits for V.
 // ------------------------------------------------------------------------------------------------------
-template <int NT, int ORDER /* 0: round-robin, 1: ring (nb = power of two) */>
+template <int NT, int ORDER /* 0: round-robin, 1: ring (nb = power of two), 2: ring + the slot's first block resident in shared memory */>
 __global__ void __launch_bounds__(NT, 1)
 jacobi_pipe_kernel(double* GT, double* VT, int ld, int n, int nb, double tol, int max_sweeps, DevScalars* sc, unsigned* readyG,
                    unsigned* readyV, long long* dbg /* nullable: phase timestamps (profiles/microbench/jacobi_phases.py) */, int dbg_sweep, int dbg_step0) {
   cg::grid_group grid = cg::this_grid();
 #define KCMA_TS(slot) do { if (dbg && blockIdx.x == 1 && tid == 0 && sweep == dbg_sweep && step >= dbg_step0 && step < dbg_step0 + 32) dbg[(step - dbg_step0) * 16 + (slot)] = clock64(); } while (0)
 #define KCMA_TSV(slot) do { if (dbg && blockIdx.x == 1 && tid == NWG * 32 && sweep == dbg_sweep && step >= dbg_step0 && step < dbg_step0 + 32) dbg[(step - dbg_step0) * 16 + (slot)] = clock64(); } while (0)
+  // ORDER 2 (experimental): in the ring order the first block I of a slot stays the same for all but log2(nb) - 1 of the
+  // nb - 2 step transitions of a sweep. Its 4 rows of G (and of V) then stay in rows 0-3 of Gs (Vs) from step to step: they are
+  // neither re-fetched nor written back nor flagged while the slot keeps them; only the travelling block J goes through L2.
+  constexpr bool ANCHOR = (ORDER == 2);
   constexpr int NW = NT / 32;                       // 8: warp 0 | data warps 1..4 | V warps 5..7
   constexpr int NWV = 3;                            // V warps on schedulers 1, 2, 3 (none shares the FP64 pipe of warp 0)
   constexpr int NWG = NW - NWV;                     // G group: warp 0 (flags, rotations) + NWD data warps
@@ -91,6 +95,7 @@ jacobi_pipe_kernel(double* GT, double* VT, int ld, int n, int nb, double tol, in
   const int nspans = ld >> 4;
   const double tol2 = tol * tol;
   unsigned epoch = 0;                               // steps completed by this group of this CTA
+  bool g_dirty = false, v_valid = false, v_dirty = false;   // ORDER 2: resident anchor rows newer than global / present in Vs
   if (tid == 0) { g_head = 0; v_tail = 0; }
   __syncthreads();
 
@@ -106,11 +111,18 @@ jacobi_pipe_kernel(double* GT, double* VT, int ld, int n, int nb, double tol, in
       for (int step = 0; step < nb - 1; step++) {
         int I, J;
         tournament_pair<ORDER>(nb, step, blockIdx.x, I, J);
+        bool keep_prev = false, keep_next = false;    // block I was / stays this slot's first block: its rows are / stay in Gs[0..3]
+        if (ANCHOR) {
+          int Ia, Ja;
+          if (step > 0) { ring_pair(nb, step - 1, blockIdx.x, Ia, Ja); keep_prev = (Ia == I); }
+          if (step + 2 < nb) { ring_pair(nb, step + 1, blockIdx.x, Ia, Ja); keep_next = (Ia == I); }
+          if (!keep_prev) g_dirty = false;
+        }
         const int slot = epoch & (RING - 1);
         KCMA_TS(0);
         if (dbg && blockIdx.x == 1 && tid == 0 && sweep == dbg_sweep && step < 1024) dbg[512 + step] = clock64();
         if (warp == 0) {   // lanes 0 and 1 each watch one flag (acquire loads: no fence, no serialised round trips)
-          if (lane < 2) {
+          if (lane < 2 && !(ANCHOR && lane == 0 && keep_prev)) {
             const unsigned* f = readyG + (lane == 0 ? I : J);
             unsigned v;
             do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory"); } while (v < epoch);
@@ -132,12 +144,20 @@ jacobi_pipe_kernel(double* GT, double* VT, int ld, int n, int nb, double tol, in
             for (int k = 0; k < BG; k++) {
               const int h = dw + (kb + k) * NWD;
               xs[k].a = xs[k].b = xs[k].c = xs[k].d = 0.0;
-              if (rvalid && h < nspans) xs[k] = ldcg_256(grow + 16 * h + 4 * t);
+              if (rvalid && h < nspans) {
+                if (ANCHOR && keep_prev && g < 4) {   // resident anchor rows: from shared memory
+                  const double* sp = Gs + g * S + 16 * h + 4 * t;
+                  const double2 u = *reinterpret_cast<const double2*>(sp), v = *reinterpret_cast<const double2*>(sp + 2);
+                  xs[k].a = u.x; xs[k].b = u.y; xs[k].c = v.x; xs[k].d = v.y;
+                } else {
+                  xs[k] = ldcg_256(grow + 16 * h + 4 * t);
+                }
+              }
             }
 #pragma unroll
             for (int k = 0; k < BG; k++) {   // two independent accumulator chains
               const int h = dw + (kb + k) * NWD;
-              if (h < nspans) {
+              if (h < nspans && !(ANCHOR && keep_prev && g < 4)) {
                 double* dst = Gs + g * S + 16 * h + 4 * t;
                 *reinterpret_cast<double2*>(dst) = make_double2(xs[k].a, xs[k].b);
                 *reinterpret_cast<double2*>(dst + 2) = make_double2(xs[k].c, xs[k].d);
@@ -198,13 +218,36 @@ jacobi_pipe_kernel(double* GT, double* VT, int ld, int n, int nb, double tol, in
               bA0[k] = ok ? src[0] : 0.0;         bB0[k] = ok ? src[2] : 0.0;
               bA1[k] = ok ? src[4 * S] : 0.0;     bB1[k] = ok ? src[4 * S + 2] : 0.0;
             }
+            if (ANCHOR) __syncwarp();   // every operand of the batch is read before a resident row of these spans is overwritten
 #pragma unroll
             for (int k = 0; k < 8; k++) {
               const int h = h0 + k * NWD;
               double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0;
               dmma884(d0, d1, a_lo, bA0[k]); dmma884(e0, e1, a_lo, bB0[k]);
               dmma884(d0, d1, a_hi, bA1[k]); dmma884(e0, e1, a_hi, bB1[k]);
-              if (h < nspans && rvalid) stcg_256(gout + 16 * h + 4 * t, d0, d1, e0, e1);
+              if (h < nspans && rvalid) {
+                if (ANCHOR && keep_next && g < 4) {   // the anchor block stays: update it in place in shared memory
+                  double* dst = Gs + g * S + 16 * h + 4 * t;
+                  *reinterpret_cast<double2*>(dst) = make_double2(d0, d1);
+                  *reinterpret_cast<double2*>(dst + 2) = make_double2(e0, e1);
+                } else {
+                  stcg_256(gout + 16 * h + 4 * t, d0, d1, e0, e1);
+                }
+              }
+            }
+          }
+        }
+        if (ANCHOR) {
+          // kept: newer than global; released: written to global just now. While the block is kept, rotation-free steps leave
+          // the flag alone: the copy in shared memory stays ahead of global until the block is released.
+          if (rot != 0) g_dirty = keep_next;
+          else if (!keep_next && g_dirty && warp != 0 && g < 4 && rvalid) {
+            // released without a rotation in this step, but updated in shared memory since it was fetched: write it back
+            double* gout = GT + (size_t)rowg * ld;
+            for (int h = warp - 1; h < nspans; h += NWD) {
+              const double* sp = Gs + g * S + 16 * h + 4 * t;
+              const double2 u = *reinterpret_cast<const double2*>(sp), v = *reinterpret_cast<const double2*>(sp + 2);
+              stcg_256(gout + 16 * h + 4 * t, u.x, u.y, v.x, v.y);
             }
           }
         }
@@ -213,7 +256,8 @@ jacobi_pipe_kernel(double* GT, double* VT, int ld, int n, int nb, double tol, in
         if (tid == 0) {
           __threadfence();                          // gpu scope: the G rows; also orders Rring before g_head for the V group
           volatile unsigned* rg = readyG;
-          rg[I] = epoch + 1; rg[J] = epoch + 1;
+          if (!(ANCHOR && keep_next)) rg[I] = epoch + 1;
+          rg[J] = epoch + 1;
           g_head = epoch + 1;
         }
         KCMA_TS(6);
@@ -225,6 +269,13 @@ jacobi_pipe_kernel(double* GT, double* VT, int ld, int n, int nb, double tol, in
       for (int step = 0; step < nb - 1; step++) {
         int I, J;
         tournament_pair<ORDER>(nb, step, blockIdx.x, I, J);
+        bool keep_prev = false, keep_next = false;
+        if (ANCHOR) {
+          int Ia, Ja;
+          if (step > 0) { ring_pair(nb, step - 1, blockIdx.x, Ia, Ja); keep_prev = (Ia == I); }
+          if (step + 2 < nb) { ring_pair(nb, step + 1, blockIdx.x, Ia, Ja); keep_next = (Ia == I); }
+          if (!keep_prev) { v_valid = false; v_dirty = false; }
+        }
         const int slot = epoch & (RING - 1);
         KCMA_TSV(9);
         if (dbg && blockIdx.x == 1 && tid == NWG * 32 && sweep == dbg_sweep && step < 1024) dbg[512 + 1024 + step] = clock64();
@@ -235,7 +286,7 @@ jacobi_pipe_kernel(double* GT, double* VT, int ld, int n, int nb, double tol, in
         asm volatile("bar.sync 2, %0;" ::"n"(NWV * 32));
         KCMA_TSV(10);
         const int rot = rot_ring[slot];
-        if (vtid < 2) {                             // the previous owners are done with these V blocks (also when nothing rotates here:
+        if (vtid < 2 && !(ANCHOR && vtid == 0 && keep_prev)) {   // the previous owners are done with these V blocks (also when nothing rotates here:
           const unsigned* f = readyV + (vtid == 0 ? I : J);   // publishing them early would let the next owner overtake a pending update)
           unsigned v;
           do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory"); } while (v < epoch);
@@ -245,7 +296,7 @@ jacobi_pipe_kernel(double* GT, double* VT, int ld, int n, int nb, double tol, in
           asm volatile("bar.sync 2, %0;" ::"n"(NWV * 32));
           const int chunks = ld >> 1;   // 16-byte chunks per row
 #pragma unroll
-          for (int r = 0; r < 8; r++) {
+          for (int r = (ANCHOR && v_valid) ? 4 : 0; r < 8; r++) {   // (resident anchor rows are not fetched again)
             const int row = (r < 4 ? I * 4 + r : J * 4 + (r - 4));
             const bool ok = row < n;
             const double* src = VT + (ok ? (size_t)row * ld : 0);
@@ -270,13 +321,34 @@ jacobi_pipe_kernel(double* GT, double* VT, int ld, int n, int nb, double tol, in
               bA0[k] = ok ? src[0] : 0.0;         bB0[k] = ok ? src[2] : 0.0;
               bA1[k] = ok ? src[4 * S] : 0.0;     bB1[k] = ok ? src[4 * S + 2] : 0.0;
             }
+            if (ANCHOR) __syncwarp();
 #pragma unroll
             for (int k = 0; k < 8; k++) {
               const int h = h0 + k * NWV;
               double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0;
               dmma884(d0, d1, a_lo, bA0[k]); dmma884(e0, e1, a_lo, bB0[k]);
               dmma884(d0, d1, a_hi, bA1[k]); dmma884(e0, e1, a_hi, bB1[k]);
-              if (h < nspans && prow < n) stcg_256(vout + 16 * h + 4 * t, d0, d1, e0, e1);
+              if (h < nspans && prow < n) {
+                if (ANCHOR && keep_next && g < 4) {
+                  double* dst = Vs + g * S + 16 * h + 4 * t;
+                  *reinterpret_cast<double2*>(dst) = make_double2(d0, d1);
+                  *reinterpret_cast<double2*>(dst + 2) = make_double2(e0, e1);
+                } else {
+                  stcg_256(vout + 16 * h + 4 * t, d0, d1, e0, e1);
+                }
+              }
+            }
+          }
+          if (ANCHOR) { v_valid = keep_next; v_dirty = keep_next; }   // (released: rows 0-3 of Vs hold the pre-rotation rows)
+        } else if (ANCHOR && !keep_next && v_dirty) {
+          // released without a rotation in this step, but updated in shared memory since it was fetched: write it back
+          const int prow = I * 4 + g;
+          if (g < 4 && prow < n) {
+            double* vout = VT + (size_t)prow * ld;
+            for (int h = vw; h < nspans; h += NWV) {
+              const double* sp = Vs + g * S + 16 * h + 4 * t;
+              const double2 u = *reinterpret_cast<const double2*>(sp), v = *reinterpret_cast<const double2*>(sp + 2);
+              stcg_256(vout + 16 * h + 4 * t, u.x, u.y, v.x, v.y);
             }
           }
         }
@@ -285,7 +357,8 @@ jacobi_pipe_kernel(double* GT, double* VT, int ld, int n, int nb, double tol, in
         if (vtid == 0) {
           __threadfence();   // release: our stores, and (when nothing rotated here) the previous owners' rows we acquired above
           volatile unsigned* rv = readyV;
-          rv[I] = epoch + 1; rv[J] = epoch + 1;
+          if (!(ANCHOR && keep_next)) rv[I] = epoch + 1;
+          rv[J] = epoch + 1;
           v_tail = epoch + 1;
         }
         KCMA_TSV(15);
@@ -663,6 +736,7 @@ bool launch_jacobi_persistent(cudaStream_t st, double* GT, double* VT, int ld, i
   while (nb_ring < nb) nb_ring <<= 1;
   const char* oe = getenv("KCMA_JACOBI_ORDER");
   const bool ring = !(oe && strcmp(oe, "rr") == 0) && nb_ring / 2 <= num_sms && (nb_ring - nb) * 8 <= nb && 2 * nb_ring <= ld;
+  bool anchor = ring && oe && strcmp(oe, "anchor") == 0;   // EXPERIMENTAL, opt-in only: ring order + resident first block (ORDER 2)
   if (ring) nb = nb_ring;
   static int coop = -1;
   if (coop < 0) {
@@ -674,6 +748,14 @@ bool launch_jacobi_persistent(cudaStream_t st, double* GT, double* VT, int ld, i
       coop = 0;
   }
   if (!coop) return false;
+  if (anchor) {   // set up lazily so that the experimental instantiation can never disable the product path
+    static int anchor_ok = -1;
+    if (anchor_ok < 0) {
+      anchor_ok = cudaFuncSetAttribute(jacobi_pipe_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem - 16 * 1024) == cudaSuccess;
+      if (!anchor_ok) cudaGetLastError();
+    }
+    anchor = anchor_ok == 1;
+  }
   static long long* dbg = nullptr;   // phase timestamps, only with KCMA_JACOBI_DEBUG=<sweep to trace>
   const char* de = getenv("KCMA_JACOBI_DEBUG");
   if (de && !dbg) {
@@ -687,7 +769,7 @@ bool launch_jacobi_persistent(cudaStream_t st, double* GT, double* VT, int ld, i
   cudaMemsetAsync(ready, 0, sizeof(unsigned) * 2 * nb, st);
   unsigned* ready_v = ready + nb;
   void* args[] = {&GT, &VT, &ld, &n, &nb, &tol, &max_sweeps, &sc, &ready, &ready_v, &dbg, &dbg_sweep, &dbg_step0};
-  const void* fn = ring ? (const void*)jacobi_pipe_kernel<256, 1> : (const void*)jacobi_pipe_kernel<256, 0>;
+  const void* fn = anchor ? (const void*)jacobi_pipe_kernel<256, 2> : ring ? (const void*)jacobi_pipe_kernel<256, 1> : (const void*)jacobi_pipe_kernel<256, 0>;
   if (cudaLaunchCooperativeKernel(fn, dim3(nb / 2), dim3(256), args, smem, st) == cudaSuccess) return true;
   cudaGetLastError();
   return false;

@@ -2,7 +2,7 @@
 (1) the decomposition itself under the ring order at sizes on both sides of its dispatch rule (cold start);
 (2) config 3 (N = 1000, lambda = 65536): ms per generation, eigen ms and sweeps per decomposition for both orders.
 
-    python profiles/microbench/jacobi_order_ab.py [generations]
+    python profiles/microbench/jacobi_order_ab.py [generations] [orders, comma separated]
 """
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
@@ -10,6 +10,7 @@ import numpy as np
 from korali_b200 import _lib
 
 gens = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+orders = sys.argv[2].split(",") if len(sys.argv) > 2 else ["rr", "ring", "rr", "ring"]   # e.g. "ring,anchor,ring,anchor"
 os.environ["KCMA_JACOBI_ORDER"] = "ring"
 for n in (25, 31, 64, 120, 300, 1000, 1001):
     rng = np.random.default_rng(n)
@@ -29,7 +30,7 @@ print("ring clustered N=64  residual %.2e  orthonormality %.2e  eigenvalues %.2e
     np.abs(v @ np.diag(w) @ v.T - c).max(), np.abs(v.T @ v - np.eye(n)).max(), np.abs(w - np.linalg.eigvalsh(c)).max()), flush=True)
 
 case = dict(n=1000, population_size=65536, objective="NegEllipsoid", initial_value=3.0, initial_stddev=1.0, seed=1337)
-for order in ("rr", "ring", "rr", "ring"):
+for order in orders:
     os.environ["KCMA_JACOBI_ORDER"] = order
     s = _lib.Solver(**case)
     s.set_scalar("Termination Criteria/Max Model Evaluations", 1e18)
