@@ -203,6 +203,11 @@ int kcma_k_sort_index(int device, const double* f, uint64_t n, uint64_t* index_o
 /* eigen (CMAES.cpp.base:896-938): symmetric N x N (row-major) -> eigenvalues ascending,
  * eigenvectors as COLUMNS of Q (row-major). */
 int kcma_k_eigen(int device, uint64_t n, const double* c, double* eigenvalues, double* q);
+/* Stages of the tridiagonalisation-based eigensolver (the Householder + QL halves of gsl_eigen_symmv, CMAES.cpp.base:917-936).
+ * mode 0: C (n x n) -> tridiagonal d[n], e[n-1 used of n], reflector scalars tau[n], reflector rows vr (n x n);
+ * mode 1: (d, e) -> eigenvalues lam ascending, eigenvectors of the tridiagonal as ROWS of zt (n x n). Unused pointers may be NULL. */
+int kcma_k_tridiag_stage(int device, int mode, uint64_t n, const double* c, double* d, double* e, double* tau, double* vr,
+                         double* lam, double* zt);
 /* sampleSingle (CMAES.cpp.base:494-513) for a batch: Y = Z (B diag(D))^T, X = m + sigma Y. */
 int kcma_k_sample(int device, uint64_t n, uint64_t rows, const double* z, const double* b, const double* d,
                   const double* mean, double sigma, double* y_out, double* x_out);

@@ -18,7 +18,7 @@ EXPORTS = [
     "kcma_run_generation", "kcma_ask", "kcma_eval", "kcma_tell", "kcma_check_termination", "kcma_run",
     "kcma_set_host_objective", "kcma_set_host_objective_grad", "kcma_set_host_constraints", "kcma_inject", "kcma_get_array", "kcma_set_array", "kcma_get_index_array", "kcma_get_scalar", "kcma_set_scalar",
     "kcma_timing_enable", "kcma_timing_get", "kcma_timing_reset", "kcma_launch_count", "kcma_flush_l2",
-    "kcma_k_sort_index", "kcma_k_eigen", "kcma_k_sample", "kcma_k_rank_mu", "kcma_k_philox_normal",
+    "kcma_k_sort_index", "kcma_k_eigen", "kcma_k_tridiag_stage", "kcma_k_sample", "kcma_k_rank_mu", "kcma_k_philox_normal",
     "kcma_k_philox_raw", "kcma_k_objective",
 ]
 
@@ -138,6 +138,31 @@ def k_eigen(c, device=0):
     if fn(device, n, _as_dp(c), _as_dp(w), _as_dp(q)) != 0:
         raise _kerr()
     return w, q
+
+
+def k_sytrd(c, device=0):
+    """Householder tridiagonalisation on the device: returns (d, e, tau, vr) with vr[i] = reflector i."""
+    c = np.ascontiguousarray(c, dtype=np.float64)
+    n = c.shape[0]
+    d, e, tau, vr = np.zeros(n), np.zeros(n), np.zeros(n), np.zeros((n, n))
+    fn = lib().kcma_k_tridiag_stage
+    fn.restype, fn.argtypes = C.c_int, [C.c_int, C.c_int, C.c_uint64] + [_dp] * 7
+    if fn(device, 0, n, _as_dp(c), _as_dp(d), _as_dp(e), _as_dp(tau), _as_dp(vr), None, None) != 0:
+        raise _kerr()
+    return d, e[:n - 1], tau, vr
+
+
+def k_stedc(d, e, device=0):
+    """Divide & conquer on the tridiagonal (d, e): returns (lam ascending, zt with eigenvectors as rows)."""
+    d = np.ascontiguousarray(d, dtype=np.float64)
+    n = d.size
+    ee = np.zeros(n); ee[:n - 1] = e
+    lam, zt = np.zeros(n), np.zeros((n, n))
+    fn = lib().kcma_k_tridiag_stage
+    fn.restype, fn.argtypes = C.c_int, [C.c_int, C.c_int, C.c_uint64] + [_dp] * 7
+    if fn(device, 1, n, None, _as_dp(d), _as_dp(ee), None, None, _as_dp(lam), _as_dp(zt)) != 0:
+        raise _kerr()
+    return lam, zt
 
 
 def k_sample(z, b, d, mean, sigma, device=0):

@@ -14,7 +14,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall"] + ARCH
 # files whose arithmetic must round like the reference's scalar code (no fused multiply-add)
 NO_FMA = {"objective.cu", "update.cu", "constraints.cu"}
-SOURCES = ["api.cu", "gemm.cu", "gemm_tma.cu", "rng.cu", "objective.cu", "sort.cu", "update.cu", "eigen.cu", "constraints.cu"]
+SOURCES = ["api.cu", "gemm.cu", "gemm_tma.cu", "rng.cu", "objective.cu", "sort.cu", "update.cu", "eigen.cu", "constraints.cu", "gemm_batched.cu", "tridiag.cu", "dc.cu"]
 
 
 def _newer(src, dst):

@@ -110,6 +110,8 @@ struct kcma {
   std::vector<double> hGrad;
   kcma_host_constraints_fn host_con = nullptr; void* host_con_user = nullptr;
   std::vector<double> hX, hF, hG;
+  // tridiagonalisation-based eigensolver (created on first use)
+  kc::TridiagWs* tri = nullptr;
   // nccl
   ncclComm_t comm = nullptr;
   // timing
@@ -375,6 +377,14 @@ int ensure_vt(kcma* h) {
   return 0;
 }
 
+// Which eigensolver runs above the single-CTA size: KCMA_EIGEN=tridiag (default) | jacobi (the round-1 warm-started one-sided
+// Jacobi kernels, kept for A/B runs). Read per call so that one process can time both.
+bool eigen_use_tridiag(const kcma* h) {
+  const char* e = getenv("KCMA_EIGEN");
+  if (e && !strcmp(e, "jacobi")) return false;
+  return h->N >= 4 && (size_t)h->N * 5 * sizeof(double) + 4096 <= 226 * 1024;
+}
+
 // updateEigensystem (CMAES.cpp.base:869-890) + eigen (:896-938)
 int update_eigensystem(kcma* h, const double* dM) {
   PhaseTimer t(h, "eigen");
@@ -393,6 +403,28 @@ int update_eigensystem(kcma* h, const double* dM) {
   if (eigen_small_fits(N) && N <= small_max) {  // the whole solver in one launch, everything in one SM's shared memory
     launch_eigen_small(h->stream, dM, ld, N, h->dVT, h->dGT, h->dB, h->dA, h->dD, tol, max_sweeps, h->dSc);
     h->launches += 2;
+    h->scalars_fresh = false;
+    return 0;
+  }
+  if (eigen_use_tridiag(h)) {
+    // Householder tridiagonalisation + divide & conquer + WY back-transform (tridiag.cu, dc.cu); no host round trip
+    if (!h->tri) {
+      char msg[512] = "";
+      h->tri = tridiag_ws_create(N, ld, h->num_sms, msg, sizeof(msg));
+      if (!h->tri) return fail(h, "%s", msg);
+    }
+    int l = 4;
+    bool ok;
+    { PhaseTimer t1(h, "eigen_sytrd"); ok = tridiag_stage_sytrd(h->stream, h->tri, dM); }
+    if (ok) { PhaseTimer t2(h, "eigen_dc"); ok = tridiag_stage_dc(h->stream, h->tri, &l); }
+    if (ok) { PhaseTimer t3(h, "eigen_back"); ok = tridiag_stage_back(h->stream, h->tri, &l); }
+    if (!ok) return fail(h, "the tridiagonal eigensolver could not be launched: %s", cudaGetErrorString(cudaGetLastError()));
+    const double* vt = tridiag_result_vectors(h->tri);
+    const double* ev = tridiag_result_values(h->tri);
+    launch_eig_sign(h->stream, vt, ld, N, h->dT);   // dT (scratch of tell()) holds the signs here
+    launch_eig_order(h->stream, ev, N, h->dPerm, h->dSc);
+    launch_eig_commit(h->stream, vt, ld, N, h->dPerm, ev, h->dT, h->dB, h->dA, h->dD, h->dVT, h->dSc);
+    h->launches += l + 3;
     h->scalars_fresh = false;
     return 0;
   }
@@ -896,6 +928,7 @@ void kcma_destroy(kcma_t* h) {
   invalidate_graph(h);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  kc::tridiag_ws_destroy(h->tri);
   void* ptrs[] = {h->dC, h->dB, h->dA, h->dD, h->dVT, h->dVTw, h->dGT, h->dEv, h->dPerm, h->dMean, h->dMeanOld, h->dMeanUpd, h->dT,
                   h->dPs, h->dPc, h->dZ, h->dY, h->dX, h->dF, h->dIdx, h->dSortWs, h->dW, h->dSelW, h->dSelS, h->dCount, h->dS,
                   h->dPartial, h->dWsplit, h->dRed, h->dBestEver, h->dCurBest, h->dLower, h->dUpper, h->dMinSd, h->dCoef, h->dShift,
@@ -1697,6 +1730,41 @@ int kcma_k_eigen(int device, uint64_t n, const double* c, double* eigenvalues, d
     for (uint64_t i = 0; i < n; i++) eigenvalues[i] *= eigenvalues[i];
   } else if (h->err.size()) strncpy(g_create_err, h->err.c_str(), sizeof(g_create_err) - 1);
   kcma_destroy(h);
+  return rc;
+}
+
+
+// Stages of the tridiagonalisation-based eigensolver on host buffers (parity tests only).
+// mode 0: C (n x n) -> d, e, tau, reflector rows vr (n x n); mode 1: (d, e) -> eigenvalues lam, eigenvectors as rows zt (n x n).
+int kcma_k_tridiag_stage(int device, int mode, uint64_t n, const double* c, double* d, double* e, double* tau, double* vr,
+                         double* lam, double* zt) {
+  if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, "no CUDA device %d (libkcma has no CPU fallback)", device);
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  const int N = (int)n, ld = round_up(N, 16);
+  char msg[512] = "";
+  TridiagWs* ws = tridiag_ws_create(N, ld, prop.multiProcessorCount, msg, sizeof(msg));
+  if (!ws) return fail(nullptr, "%s", msg);
+  int rc = 0, l = 0;
+  if (mode == 0) {
+    double* dM = nullptr;
+    cudaMalloc(&dM, sizeof(double) * (size_t)N * ld);
+    cudaMemset(dM, 0, sizeof(double) * (size_t)N * ld);
+    cudaMemcpy2D(dM, sizeof(double) * ld, c, sizeof(double) * N, sizeof(double) * N, N, cudaMemcpyHostToDevice);
+    if (!tridiag_stage_sytrd(0, ws, dM)) rc = fail(nullptr, "sytrd launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (!rc && cudaDeviceSynchronize() != cudaSuccess) rc = fail(nullptr, "sytrd failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (!rc) tridiag_get_tridiagonal(ws, d, e, tau, vr);
+    cudaFree(dM);
+  } else {
+    tridiag_set_tridiagonal(ws, d, e);
+    if (!tridiag_stage_dc(0, ws, &l)) rc = fail(nullptr, "divide & conquer launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (!rc && cudaDeviceSynchronize() != cudaSuccess) rc = fail(nullptr, "divide & conquer failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (!rc) {
+      cudaMemcpy(lam, tridiag_result_values(ws), sizeof(double) * N, cudaMemcpyDeviceToHost);
+      cudaMemcpy2D(zt, sizeof(double) * N, tridiag_result_vectors(ws), sizeof(double) * ld, sizeof(double) * N, N, cudaMemcpyDeviceToHost);
+    }
+  }
+  tridiag_ws_destroy(ws);
   return rc;
 }
 

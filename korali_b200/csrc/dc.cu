@@ -1,0 +1,422 @@
+// dc.cu — K8b: divide & conquer eigensolver of the symmetric tridiagonal T = (dT, eT) produced by sytrd_kernel (tridiag.cu).
+// Cuppen's method with Gu & Eisenstat's stable eigenvectors, laid out for the GPU:
+//
+//   tear     T = blockdiag(T_1 .. T_L) + sum_b |e_b| u_b u_b^T at every leaf boundary b (dc_tear_kernel)
+//   leaves   <= 32 x 32 each, one warp per leaf: cyclic two-sided Jacobi in shared memory (dc_leaf_kernel)
+//   merges   level by level, ALL merges of a level per launch, no host round trip:
+//            dc_setup_kernel    z = [last row of Q1 | +-first row of Q2]/sqrt2, rho = 2|e_b|, merge the two sorted spectra,
+//                               deflate (tiny z_i; close poles by a Givens rotation of two eigenvector columns)
+//            dc_secular_kernel  one warp per root: secular_root() (dc_inner.cuh), pole differences DELTA[j][i] = dl_i - lam_j
+//            dc_loewner_kernel  w_hat_i^2 = prod_j (lam_j - dl_i) / prod_{j != i} (dl_j - dl_i)  (orthogonal vectors without
+//                               extended precision)
+//            dc_vectors_kernel  final sorted position of every root / deflated value, row of U^T (n_merge wide, zero or a
+//                               unit vector where deflated): the merge is "deflation oblivious" — it always multiplies at
+//                               full size, so its shapes are static and the level needs no device -> host count
+//            gemm_tn_batched    Q_new = blockdiag(Q1, Q2) * U on the FP64 tensor cores (k-range halved while Q is block
+//                               diagonal); the last merge is written transposed (rows = eigenvectors) for the back-transform
+// NumPy statement of the same algorithm: profiles/microbench/tridiag_dc_proto.py. Replaces the QL iteration half of
+// gsl_eigen_symmv (CMAES.cpp.base:917-936).
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "dc_inner.cuh"
+#include "jacobi_inner.cuh"
+#include "tridiag.h"
+
+namespace kc {
+
+namespace {
+
+constexpr double kEps = 2.220446049250313e-16;
+
+struct WarpLanes {
+  __device__ __forceinline__ int lane() const { return threadIdx.x & 31; }
+  __device__ __forceinline__ int width() const { return 32; }
+  __device__ __forceinline__ double sum(double v) const { return warp_sum_butterfly(v); }
+};
+
+__device__ __forceinline__ int warp_sum_int(int v) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+
+// ---- tear: d_out[i] = dT[i] - |e| of the leaf boundaries next to row i --------------------------------------------
+__global__ void __launch_bounds__(256)
+dc_tear_kernel(const double* __restrict__ dT, const double* __restrict__ eT, const int* __restrict__ bounds, int leaves, int n,
+               double* __restrict__ dout) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  // leaf of row i: largest k with bounds[k] <= i
+  int lo = 0, hi = leaves;
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (bounds[mid] <= i) lo = mid; else hi = mid; }
+  double v = dT[i];
+  if (lo > 0 && i == bounds[lo]) v -= fabs(eT[i - 1]);                 // first row of a leaf that has a left neighbour
+  if (lo + 1 < leaves && i == bounds[lo + 1] - 1) v -= fabs(eT[i]);     // last row of a leaf that has a right neighbour
+  dout[i] = v;
+}
+
+// ---- leaves: one warp per leaf, two-sided cyclic Jacobi (round-robin order) on the dense <= 32 x 32 block --------------
+constexpr int LEAF_MAX = 32;
+constexpr int LEAF_LD = LEAF_MAX + 1;
+constexpr int LEAF_WARPS = 2;   // 2 x (A + V) = 34 KB of static shared memory
+
+__global__ void __launch_bounds__(LEAF_WARPS * 32)
+dc_leaf_kernel(const int* __restrict__ bounds, int leaves, const double* __restrict__ dtorn, const double* __restrict__ eT,
+               double* __restrict__ dout, double* __restrict__ Q, int ld) {
+  __shared__ double As[LEAF_WARPS][LEAF_MAX * LEAF_LD], Vs[LEAF_WARPS][LEAF_MAX * LEAF_LD];
+  __shared__ double cs_c[LEAF_WARPS][LEAF_MAX / 2], cs_s[LEAF_WARPS][LEAF_MAX / 2], diag[LEAF_WARPS][LEAF_MAX];
+  __shared__ int cs_p[LEAF_WARPS][LEAF_MAX / 2], cs_q[LEAF_WARPS][LEAF_MAX / 2], rnk[LEAF_WARPS][LEAF_MAX];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int leaf = blockIdx.x * LEAF_WARPS + warp;
+  if (leaf >= leaves) return;
+  const int off = bounds[leaf], m = bounds[leaf + 1] - off;
+  double* A = As[warp];
+  double* V = Vs[warp];
+  double nrm = 0.0;
+  if (lane < m) {
+    for (int j = 0; j < m; j++) { A[lane * LEAF_LD + j] = 0.0; V[lane * LEAF_LD + j] = (j == lane) ? 1.0 : 0.0; }
+    const double dd = dtorn[off + lane];
+    A[lane * LEAF_LD + lane] = dd;
+    nrm = fabs(dd);
+    if (lane + 1 < m) {
+      const double ee = eT[off + lane];
+      A[lane * LEAF_LD + lane + 1] = ee;
+      A[(lane + 1) * LEAF_LD + lane] = ee;
+      nrm = fmax(nrm, fabs(ee));
+    }
+  }
+  nrm = warp_max(nrm);
+  const double thr = 0.25 * kEps * nrm;
+  __syncwarp();
+  const int np = (m + 1) & ~1;
+  for (int sweep = 0; sweep < 60 && m > 1; sweep++) {
+    int rotated = 0;
+    for (int round = 0; round < np - 1; round++) {
+      if (lane < np / 2) {
+        int p, q;
+        rr_pair(np, round, lane, p, q);
+        if (p > q) { const int t = p; p = q; q = t; }
+        double c = 1.0, s = 0.0;
+        if (q < m) {
+          const double apq = A[p * LEAF_LD + q];
+          if (fabs(apq) > thr) {
+            const double theta = (A[q * LEAF_LD + q] - A[p * LEAF_LD + p]) / (2.0 * apq);
+            const double t = copysign(1.0, theta) / (fabs(theta) + sqrt(theta * theta + 1.0));
+            c = 1.0 / sqrt(t * t + 1.0);
+            s = t * c;
+            rotated = 1;
+          }
+        } else { p = 0; q = 0; }
+        cs_c[warp][lane] = c; cs_s[warp][lane] = s; cs_p[warp][lane] = p; cs_q[warp][lane] = q;
+      }
+      __syncwarp();
+      if (lane < m) {   // A <- A J, V <- V J : this lane's row, all pairs of the round
+        for (int k = 0; k < np / 2; k++) {
+          const double s = cs_s[warp][k];
+          if (s == 0.0) continue;
+          const double c = cs_c[warp][k];
+          const int p = cs_p[warp][k], q = cs_q[warp][k];
+          const double ap = A[lane * LEAF_LD + p], aq = A[lane * LEAF_LD + q];
+          A[lane * LEAF_LD + p] = c * ap - s * aq;
+          A[lane * LEAF_LD + q] = s * ap + c * aq;
+          const double vp = V[lane * LEAF_LD + p], vq = V[lane * LEAF_LD + q];
+          V[lane * LEAF_LD + p] = c * vp - s * vq;
+          V[lane * LEAF_LD + q] = s * vp + c * vq;
+        }
+      }
+      __syncwarp();
+      if (lane < m) {   // A <- J^T A : this lane's column
+        for (int k = 0; k < np / 2; k++) {
+          const double s = cs_s[warp][k];
+          if (s == 0.0) continue;
+          const double c = cs_c[warp][k];
+          const int p = cs_p[warp][k], q = cs_q[warp][k];
+          const double ap = A[p * LEAF_LD + lane], aq = A[q * LEAF_LD + lane];
+          A[p * LEAF_LD + lane] = c * ap - s * aq;
+          A[q * LEAF_LD + lane] = s * ap + c * aq;
+        }
+      }
+      __syncwarp();
+    }
+    if (!__any_sync(0xffffffffu, rotated)) break;
+  }
+  // ascending order, columns of Q = eigenvectors
+  if (lane < m) diag[warp][lane] = A[lane * LEAF_LD + lane];
+  __syncwarp();
+  if (lane < m) {
+    const double v = diag[warp][lane];
+    int r = 0;
+    for (int j = 0; j < m; j++) { const double o = diag[warp][j]; r += (o < v) || (o == v && j < lane); }
+    rnk[warp][lane] = r;
+    dout[off + r] = v;
+  }
+  __syncwarp();
+  if (lane < m)
+    for (int c = 0; c < m; c++) Q[(size_t)(off + lane) * ld + off + rnk[warp][c]] = V[lane * LEAF_LD + c];
+}
+
+// ---- merge set-up + deflation: one CTA per merge ------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+dc_setup_kernel(const DcNode* __restrict__ nodes, int node0, const double* __restrict__ dcur, const double* __restrict__ eT,
+                double* __restrict__ Q, int ld, double* __restrict__ dl, double* __restrict__ w, double* __restrict__ defl_val,
+                int* __restrict__ col2k, int* __restrict__ nd_col, int* __restrict__ defl_col, double* __restrict__ rho_out,
+                int* __restrict__ Kcnt, int* __restrict__ mixed, int* __restrict__ rot_p, int* __restrict__ rot_q,
+                double* __restrict__ rot_c, double* __restrict__ rot_s) {
+  extern __shared__ __align__(16) double sm[];
+  const int node = node0 + blockIdx.x;
+  const DcNode nd = nodes[node];
+  const int off = nd.off, n1 = nd.n1, n = nd.n, n2 = n - n1, tid = threadIdx.x, nt = blockDim.x;
+  double* d_s = sm;
+  double* z_s = sm + n;
+  int* ord = reinterpret_cast<int*>(sm + 2 * n);
+  __shared__ double red[16];
+  __shared__ int s_K, s_M, s_nrot, s_mixed;
+  const double beta = eT[off + n1 - 1];
+  const double sgn = beta < 0.0 ? -1.0 : 1.0, rho = 2.0 * fabs(beta);
+  double dmax = 0.0, zmax = 0.0;
+  for (int i = tid; i < n; i += nt) {
+    const double dv = dcur[off + i];
+    const double zv = (i < n1 ? Q[(size_t)(off + n1 - 1) * ld + off + i] : sgn * Q[(size_t)(off + n1) * ld + off + i]) * 0.70710678118654752440;
+    d_s[i] = dv; z_s[i] = zv;
+    dmax = fmax(dmax, fabs(dv)); zmax = fmax(zmax, fabs(zv));
+  }
+  dmax = warp_max(dmax); zmax = warp_max(zmax);
+  if ((tid & 31) == 0) { red[tid >> 5] = dmax; red[8 + (tid >> 5)] = zmax; }
+  __syncthreads();
+  dmax = 0.0; zmax = 0.0;
+  for (int k = 0; k < (nt >> 5); k++) { dmax = fmax(dmax, red[k]); zmax = fmax(zmax, red[8 + k]); }
+  const double tol = 8.0 * kEps * fmax(dmax, zmax);
+  // merge of the two ascending halves (ties: first half first)
+  for (int i = tid; i < n; i += nt) {
+    const double v = d_s[i];
+    int lo, hi, pos;
+    if (i < n1) {   // number of second-half values < v
+      lo = 0; hi = n2;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (d_s[n1 + mid] < v) lo = mid + 1; else hi = mid; }
+      pos = i + lo;
+    } else {        // number of first-half values <= v
+      lo = 0; hi = n1;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (d_s[mid] <= v) lo = mid + 1; else hi = mid; }
+      pos = (i - n1) + lo;
+    }
+    ord[pos] = i;
+  }
+  __syncthreads();
+  if (tid == 0) {   // the deflation scan is sequential by nature (dlaed2); rotations are recorded and applied by the whole CTA below
+    int K = 0, M = 0, nrot = 0, mix = 0;
+    if (rho * zmax <= tol) {
+      for (int pos = 0; pos < n; pos++) defl_col[off + M++] = ord[pos];
+    } else {
+      int pj = -1;
+      for (int pos = 0; pos < n; pos++) {
+        const int i = ord[pos];
+        if (rho * fabs(z_s[i]) <= tol) { defl_col[off + M++] = i; continue; }
+        if (pj < 0) { pj = i; continue; }
+        double s = z_s[pj], c = z_s[i];
+        const double t = hypot(c, s), tt = d_s[i] - d_s[pj];
+        c /= t; s = -s / t;
+        if (fabs(tt * c * s) <= tol) {
+          z_s[i] = t; z_s[pj] = 0.0;
+          rot_p[off + nrot] = pj; rot_q[off + nrot] = i; rot_c[off + nrot] = c; rot_s[off + nrot] = s; nrot++;
+          const double tn = d_s[pj] * c * c + d_s[i] * s * s;
+          d_s[i] = d_s[pj] * s * s + d_s[i] * c * c;
+          d_s[pj] = tn;
+          defl_col[off + M++] = pj;
+          if ((pj < n1) != (i < n1)) mix = 1;
+          pj = i;
+        } else {
+          nd_col[off + K++] = pj;
+          pj = i;
+        }
+      }
+      if (pj >= 0) nd_col[off + K++] = pj;
+    }
+    s_K = K; s_M = M; s_nrot = nrot; s_mixed = mix;
+    Kcnt[node] = K; mixed[node] = mix; rho_out[node] = rho;
+  }
+  __syncthreads();
+  const int K = s_K, M = s_M, nrot = s_nrot;
+  for (int i = tid; i < n; i += nt) col2k[off + i] = -1;
+  __syncthreads();
+  for (int k = tid; k < K; k += nt) {
+    const int c = nd_col[off + k];
+    col2k[off + c] = k;
+    dl[off + k] = d_s[c];
+    w[off + k] = z_s[c];
+  }
+  for (int m = tid; m < M; m += nt) defl_val[off + m] = d_s[defl_col[off + m]];
+  // Givens rotations of eigenvector columns (x' = c x + s y, y' = c y - s x); a thread owns its rows, so the chain needs no barrier
+  for (int t = 0; t < nrot; t++) {
+    const int p = rot_p[off + t], q = rot_q[off + t];
+    const double c = rot_c[off + t], s = rot_s[off + t];
+    for (int r = tid; r < n; r += nt) {
+      double* row = Q + (size_t)(off + r) * ld + off;
+      const double x = row[p], y = row[q];
+      row[p] = c * x + s * y;
+      row[q] = c * y - s * x;
+    }
+  }
+}
+
+// ---- secular equation: one warp per root -------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+dc_secular_kernel(const DcNode* __restrict__ nodes, const int* __restrict__ row2node, int n_total, const double* __restrict__ dl,
+                  const double* __restrict__ w, const double* __restrict__ rho, const int* __restrict__ Kcnt,
+                  double* __restrict__ lam, double* __restrict__ DELTA, int ld) {
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (g >= n_total) return;
+  const int node = row2node[g];
+  const int off = nodes[node].off, j = g - off, K = Kcnt[node];
+  if (j >= K) return;
+  const double* dlp = dl + off;
+  const double* wp = w + off;
+  int o; double mu;
+  WarpLanes cx;
+  secular_root(cx, j, K, dlp, wp, rho[node], o, mu);
+  const double dorg = dlp[o];
+  if (lane == 0) lam[off + j] = dorg + mu;
+  double* row = DELTA + (size_t)(off + j) * ld + off;
+  for (int i = lane; i < K; i += 32) row[i] = (dlp[i] - dorg) - mu;
+}
+
+// ---- Loewner weights: block = 32 consecutive poles x 8 slices of the product over the roots ----------------------------
+__global__ void __launch_bounds__(256)
+dc_loewner_kernel(const DcNode* __restrict__ nodes, const int* __restrict__ row2node, int n_total, const double* __restrict__ dl,
+                  const double* __restrict__ w, const int* __restrict__ Kcnt, const double* __restrict__ DELTA, int ld,
+                  double* __restrict__ what) {
+  __shared__ double part[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int g = blockIdx.x * 32 + tx;
+  double prod = 1.0;
+  bool live = false;
+  int off = 0, i = 0;
+  if (g < n_total) {
+    const int node = row2node[g];
+    off = nodes[node].off; i = g - off;
+    const int K = Kcnt[node];
+    if (i < K) {
+      live = true;
+      const double di = dl[off + i];
+      for (int j = ty; j < K; j += 8) {
+        const double dji = DELTA[(size_t)(off + j) * ld + off + i];
+        prod *= (j == i) ? dji : dji / (di - dl[off + j]);
+      }
+    }
+  }
+  part[ty][tx] = prod;
+  __syncthreads();
+  if (ty == 0 && live) {
+    double p = part[0][tx];
+#pragma unroll
+    for (int k = 1; k < 8; k++) p *= part[k][tx];
+    what[off + i] = copysign(sqrt(fabs(p)), w[off + i]);
+  }
+}
+
+// ---- rows of U^T at their final (ascending) positions, new eigenvalues: one warp per root / deflated value ----------
+__global__ void __launch_bounds__(256)
+dc_vectors_kernel(const DcNode* __restrict__ nodes, const int* __restrict__ row2node, int n_total, const double* __restrict__ lam,
+                  const double* __restrict__ defl_val, const int* __restrict__ defl_col, const int* __restrict__ col2k,
+                  const int* __restrict__ Kcnt, const double* __restrict__ what, const double* __restrict__ DELTA, int ld,
+                  double* __restrict__ UT, double* __restrict__ dnext) {
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (g >= n_total) return;
+  const int node = row2node[g];
+  const int off = nodes[node].off, n = nodes[node].n, t = g - off, K = Kcnt[node], M = n - K;
+  const bool is_root = t < K;
+  const int m = t - K;
+  const double val = is_root ? lam[off + t] : defl_val[off + m];
+  // total order: value, roots before deflated values, then index
+  int cnt = 0;
+  if (is_root) {
+    for (int k = lane; k < M; k += 32) cnt += defl_val[off + k] < val;
+    cnt = warp_sum_int(cnt) + t;
+  } else {
+    for (int k = lane; k < K; k += 32) cnt += lam[off + k] <= val;
+    for (int k = lane; k < M; k += 32) { const double o = defl_val[off + k]; cnt += (o < val) || (o == val && k < m); }
+    cnt = warp_sum_int(cnt);
+  }
+  const int pos = cnt;
+  if (lane == 0) dnext[off + pos] = val;
+  double* urow = UT + (size_t)(off + pos) * ld + off;
+  if (is_root) {
+    const double* drow = DELTA + (size_t)(off + t) * ld + off;
+    double nn = 0.0;
+    for (int k = lane; k < K; k += 32) { const double u = what[off + k] / drow[k]; nn += u * u; }
+    nn = warp_sum_butterfly(nn);
+    const double inv = 1.0 / sqrt(nn);
+    for (int c = lane; c < n; c += 32) {
+      const int k = col2k[off + c];
+      urow[c] = (k >= 0) ? what[off + k] / drow[k] * inv : 0.0;
+    }
+  } else {
+    const int dc = defl_col[off + m];
+    for (int c = lane; c < n; c += 32) urow[c] = (c == dc) ? 1.0 : 0.0;
+  }
+}
+
+__global__ void __launch_bounds__(256) dc_transpose_kernel(const double* __restrict__ in, double* __restrict__ out, int ld, int n) {
+  __shared__ double tile[32][33];
+  const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) tile[r][tx] = (y0 + r < n && x0 + tx < n) ? in[(size_t)(y0 + r) * ld + x0 + tx] : 0.0;
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8)
+    if (x0 + r < n && y0 + tx < n) out[(size_t)(x0 + r) * ld + y0 + tx] = tile[tx][r];
+}
+
+}  // namespace
+
+void launch_transpose(cudaStream_t st, const double* in, double* out, int ld, int n) {
+  dim3 grid((n + 31) / 32, (n + 31) / 32);
+  dc_transpose_kernel<<<grid, 256, 0, st>>>(in, out, ld, n);
+}
+
+// Eigen-decomposition of the tridiagonal (ws->dT, ws->eT): rows of ws->XT = eigenvectors, ws->ev_final = ascending eigenvalues.
+bool dc_solve(cudaStream_t st, TridiagWs* ws, int* launches) {
+  const int n = ws->n, ld = ws->ld;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(dc_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr = true;
+  }
+  const size_t mat = sizeof(double) * (size_t)n * ld;
+  cudaMemsetAsync(ws->Qa, 0, mat, st);
+  if (ws->levels > 1) cudaMemsetAsync(ws->Qb, 0, mat, st);
+  dc_tear_kernel<<<(n + 255) / 256, 256, 0, st>>>(ws->dT, ws->eT, ws->d_bounds, ws->leaf_count, n, ws->dB);
+  dc_leaf_kernel<<<(ws->leaf_count + LEAF_WARPS - 1) / LEAF_WARPS, LEAF_WARPS * 32, 0, st>>>(ws->d_bounds, ws->leaf_count, ws->dB,
+                                                                                             ws->eT, ws->dA, ws->Qa, ld);
+  *launches += 2;
+  double *dcur = ws->dA, *dnext = ws->dB;
+  double *qsrc = ws->Qa;
+  if (ws->levels == 0) {
+    launch_transpose(st, ws->Qa, ws->XT, ld, n);
+    *launches += 1;
+    ws->ev_final = dcur;
+    return cudaGetLastError() == cudaSuccess;
+  }
+  const int warp_blocks = (n * 32 + 255) / 256;
+  for (int l = 1; l <= ws->levels; l++) {
+    const std::vector<DcNode>& nodes = ws->lvl[l - 1];
+    const int node0 = ws->lvl_node_begin[l - 1], cnt = (int)nodes.size();
+    int nmax = 0;
+    for (const DcNode& nd : nodes) nmax = nd.n > nmax ? nd.n : nmax;
+    const int* r2n = ws->d_row2node + (size_t)(l - 1) * n;
+    const size_t smem = sizeof(double) * 2 * nmax + sizeof(int) * nmax;
+    dc_setup_kernel<<<cnt, 256, smem, st>>>(ws->d_nodes, node0, dcur, ws->eT, qsrc, ld, ws->dl, ws->w, ws->defl_val, ws->col2k,
+                                            ws->nd_col, ws->defl_col, ws->rho, ws->Kcnt, ws->mixed, ws->rot_p, ws->rot_q, ws->rot_c,
+                                            ws->rot_s);
+    dc_secular_kernel<<<warp_blocks, 256, 0, st>>>(ws->d_nodes, r2n, n, ws->dl, ws->w, ws->rho, ws->Kcnt, ws->lam, ws->DELTA, ld);
+    dc_loewner_kernel<<<(n + 31) / 32, 256, 0, st>>>(ws->d_nodes, r2n, n, ws->dl, ws->w, ws->Kcnt, ws->DELTA, ld, ws->what);
+    dc_vectors_kernel<<<warp_blocks, 256, 0, st>>>(ws->d_nodes, r2n, n, ws->lam, ws->defl_val, ws->defl_col, ws->col2k, ws->Kcnt,
+                                                   ws->what, ws->DELTA, ld, ws->UT, dnext);
+    launch_gemm_batched(st, ws->d_desc + ws->desc_level_begin[l - 1], cnt, nmax, nmax, 1);
+    *launches += 5;
+    double* t = dcur; dcur = dnext; dnext = t;
+    qsrc = (qsrc == ws->Qa) ? ws->Qb : ws->Qa;
+  }
+  ws->ev_final = dcur;
+  return cudaGetLastError() == cudaSuccess;
+}
+
+}  // namespace kc

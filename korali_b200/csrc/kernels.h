@@ -21,6 +21,39 @@ bool launch_gemm_tn_tma(cudaStream_t st, int M, int Nc, int K, const double* A, 
 bool launch_syrk_tt_tma(cudaStream_t st, int n, int K, const int* kptr, const double* S, int lds, long long s_rows, double* W, int ldw,
                         int splits);
 
+// gemm_batched.cu (descriptor-driven batched GEMM of the tridiagonalisation-based eigensolver)
+struct GemmDesc {
+  const double* A; const double* B; double* C;   // C[M x Nc] = beta*C + alpha * A[M x K] * B[Nc x K]^T
+  int M, Nc, K, lda, ldb, ldc;
+  double alpha, beta;
+  int krule;            // 0: full k-range; 1 / 2: A / B is block diagonal with first block n1 x n1 (tile-wise k-range) unless *mixed
+  int n1;
+  const int* mixed;
+  int splits;           // > 1: split-K, slab s stored (not accumulated) at C + s*split_stride
+  long long split_stride;
+};
+size_t gemm_batched_smem_bytes();
+void launch_gemm_batched(cudaStream_t st, const GemmDesc* d_descs, int batch, int max_m, int max_nc, int max_splits);
+void launch_reduce_slabs(cudaStream_t st, const double* slabs, long long stride, int splits, int rows, int cols, int ld, double* out,
+                         int num_sms);
+
+// tridiag.cu + dc.cu: Householder tridiagonalisation, divide & conquer, compact-WY back-transform
+struct TridiagWs;
+TridiagWs* tridiag_ws_create(int n, int ld, int num_sms, char* err, size_t errlen);
+void tridiag_ws_destroy(TridiagWs* ws);
+// eigenvectors of the symmetric M as the ROWS of *VT_out (n x ld, owned by the workspace), ascending eigenvalues in *ev_out;
+// false when a launch failed
+bool launch_eigen_tridiag(cudaStream_t st, TridiagWs* ws, const double* M, double** VT_out, double** ev_out, int* launches);
+// stage entry points for the parity tests (kcma_k_sytrd / kcma_k_stedc)
+bool tridiag_stage_sytrd(cudaStream_t st, TridiagWs* ws, const double* M);
+bool tridiag_stage_dc(cudaStream_t st, TridiagWs* ws, int* launches);
+bool tridiag_stage_back(cudaStream_t st, TridiagWs* ws, int* launches);
+const double* tridiag_result_vectors(const TridiagWs* ws);
+const double* tridiag_result_values(const TridiagWs* ws);
+void tridiag_get_tridiagonal(TridiagWs* ws, double* d, double* e, double* tau, double* vr /* n x n row-major reflectors */);
+void tridiag_set_tridiagonal(TridiagWs* ws, const double* d, const double* e);
+void launch_eig_sign(cudaStream_t st, const double* VT, int ld, int n, double* sign);
+
 // rng.cu
 void launch_philox_normal(cudaStream_t st, double* Z, int ldz, long long rows, int n, unsigned long long seed, unsigned generation,
                           unsigned long long row_begin, const unsigned* attempt, const int* row_list, int num_sms,

@@ -1,0 +1,464 @@
+// tridiag.cu — K8b: symmetric eigendecomposition by Householder tridiagonalisation + divide & conquer + compact-WY
+// back-transform (the default eigensolver above N = 24). Replaces eigen() (CMAES.cpp.base:896-938: gsl_eigen_symmv is the same
+// three stages with a QL iteration in the middle); DESIGN.md section 6.
+//
+//   stage 1  sytrd_kernel     C = Q T Q^T. ONE persistent cooperative launch, one CTA per SM; CTA b owns the columns
+//                             b, b+G, b+2G, ... of the (symmetric) trailing matrix — in SHARED MEMORY up to N ~ 1600 — and
+//                             the N-1 dependent Householder steps cost ONE all-to-all exchange each:
+//                               receive  p = A v (every CTA's slice) and the next column (from its owner)
+//                               every CTA redundantly: w = tau p - (tau^2 p.v / 2) v, the column's own rank-2 update, the
+//                                         next reflector (v', tau')            [bitwise identical on all CTAs]
+//                               one pass over the CTA's columns: A -= v w^T + w v^T, then p' = A v'; publish.
+//                             The exchange is an LL protocol (value + step tag in one 16-byte store/load, double-buffered by
+//                             step parity): no fence, no flag, no grid barrier.
+//   stage 2  dc_solve         T = Z diag(lam) Z^T (dc.cu)
+//   stage 3  back-transform   X^T = Z^T H_{N-3} ... H_0 with compact-WY panels (I - V T V^T) of nb reflectors: the panel
+//                             factors T_p and T_p V_p^T come from three batched launches that do not depend on Z; each
+//                             panel is then two tensor-core GEMMs, W = X^T (T_p V_p^T)^T (split-K) and X^T -= W V_p^T.
+// NumPy statement of all three stages: profiles/microbench/tridiag_dc_proto.py.
+#include <algorithm>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "tridiag.h"
+
+namespace kc {
+
+void launch_transpose(cudaStream_t st, const double* in, double* out, int ld, int n);   // dc.cu
+
+namespace {
+
+constexpr int SY_NT = 256;
+constexpr int SY_NW = SY_NT / 32;
+constexpr size_t kSmemCap = 227 * 1024 - 1024;
+
+struct __align__(16) LL { double v; unsigned long long tag; };
+
+__device__ __forceinline__ void ll_store(LL* p, double v, unsigned long long tag) {
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"((unsigned long long)__double_as_longlong(v)), "l"(tag) : "memory");
+}
+__device__ __forceinline__ double ll_wait(const LL* p, unsigned long long tag) {
+  unsigned long long a, b;
+  do {
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+  } while (b != tag);
+  return __longlong_as_double((long long)a);
+}
+
+// sum over the block, identical bits in every thread (and in every CTA: same thread count, same order)
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  v = warp_sum_butterfly(v);
+  __syncthreads();                       // red[] free again
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < SY_NW; k++) s += red[k];
+  return s;
+}
+
+template <bool RESIDENT>
+__global__ void __launch_bounds__(SY_NT, 1)
+sytrd_kernel(const double* __restrict__ M, double* __restrict__ Awork, int ld, int n, int ns /* smem vector stride */,
+             LL* __restrict__ xP, LL* __restrict__ xC, double* __restrict__ dT, double* __restrict__ eT, double* __restrict__ tauv,
+             double* __restrict__ VR) {
+  extern __shared__ __align__(16) double sm[];
+  const int G = gridDim.x, b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  double* vold = sm;
+  double* vnew = sm + ns;
+  double* wv = sm + 2 * ns;
+  double* ps = sm + 3 * ns;
+  double* cs = sm + 4 * ns;
+  double* red = sm + 5 * ns;       // 32 doubles
+  double* Acol = red + 32;         // RESIDENT: nloc x ns
+  const int nloc = b < n ? (n - b + G - 1) / G : 0;
+  if (RESIDENT) {
+    for (int s = warp; s < nloc; s += SY_NW) {
+      const double* src = M + (size_t)(b + s * G) * ld;   // column c of a symmetric matrix = its row c
+      for (int r = lane; r < n; r += 32) Acol[(size_t)s * ns + r] = src[r];
+    }
+  }
+  for (int r = tid; r < n; r += SY_NT) { vold[r] = 0.0; wv[r] = 0.0; }
+  if (b == 0) {   // owner of column 0 publishes it for step 0
+    const double* src = M;
+    for (int r = tid; r < n; r += SY_NT) ll_store(xC + r, src[r], 1ull);
+  }
+  __syncthreads();
+  double tau_old = 0.0;
+  for (int i = 0; i < n; i++) {
+    const int par = i & 1;
+    const unsigned long long tag = (unsigned long long)i + 1ull;
+    const LL* Pin = xP + (size_t)par * n;
+    const LL* Cin = xC + (size_t)par * n;
+    for (int r = i + tid; r < n; r += SY_NT) {
+      cs[r] = ll_wait(Cin + r, tag);
+      if (i > 0) ps[r] = ll_wait(Pin + r, tag);
+    }
+    __syncthreads();
+    if (i > 0) {
+      double part = 0.0;
+      for (int r = i + tid; r < n; r += SY_NT) part += ps[r] * vold[r];
+      const double pv = block_sum(part, red);
+      const double alpha = -0.5 * tau_old * (tau_old * pv);
+      for (int r = i + tid; r < n; r += SY_NT) wv[r] = tau_old * ps[r] + alpha * vold[r];
+      __syncthreads();
+      const double wi = wv[i], vi = vold[i];
+      for (int r = i + tid; r < n; r += SY_NT) cs[r] -= vold[r] * wi + wv[r] * vi;
+      __syncthreads();
+    }
+    const double di = cs[i];
+    if (i == n - 1) {
+      if (b == 0 && tid == 0) dT[i] = di;
+      break;
+    }
+    const double alph = cs[i + 1];
+    double part = 0.0;
+    for (int r = i + 2 + tid; r < n; r += SY_NT) part += cs[r] * cs[r];
+    const double xn2 = block_sum(part, red);
+    double tau = 0.0, scale = 0.0, ei = alph;
+    if (xn2 > 0.0) {
+      const double beta = -copysign(sqrt(alph * alph + xn2), alph);
+      tau = (beta - alph) / beta;
+      scale = 1.0 / (alph - beta);
+      ei = beta;
+    }
+    for (int r = i + 1 + tid; r < n; r += SY_NT) vnew[r] = (r == i + 1) ? 1.0 : cs[r] * scale;
+    if (b == i % G) {   // the owner of the retired column records the step
+      if (tid == 0) { dT[i] = di; eT[i] = ei; tauv[i] = tau; }
+      double* vr = VR + (size_t)i * ld;
+      for (int r = tid; r < ld; r += SY_NT) vr[r] = (r <= i || r >= n) ? 0.0 : (r == i + 1 ? 1.0 : cs[r] * scale);
+    }
+    __syncthreads();
+    // one pass over this CTA's columns c >= i+1: rank-2 update of step i-1, then p = A v_new; the owner of column i+1 publishes it
+    LL* Pout = xP + (size_t)(par ^ 1) * n;
+    LL* Cout = xC + (size_t)(par ^ 1) * n;
+    const unsigned long long otag = tag + 1ull;
+    const int s0 = (i + 1 > b) ? (i + 1 - b + G - 1) / G : 0;
+    for (int s = s0 + warp; s < nloc; s += SY_NW) {
+      const int c = b + s * G;
+      double* col = RESIDENT ? (Acol + (size_t)s * ns) : (Awork + (size_t)c * ld);
+      const double wc = wv[c], vc = vold[c];
+      const bool pub = (c == i + 1);
+      double dot = 0.0;
+      if (RESIDENT) {
+        for (int r = i + 1 + lane; r < n; r += 32) {
+          double a = col[r];
+          a -= vold[r] * wc + wv[r] * vc;
+          col[r] = a;
+          dot += a * vnew[r];
+          if (pub) ll_store(Cout + r, a, otag);
+        }
+      } else {
+        int r = i + 1 + lane;
+        for (; r + 96 < n; r += 128) {   // four loads in flight per lane (the columns stream from L2 / HBM)
+          double a0 = col[r], a1 = col[r + 32], a2 = col[r + 64], a3 = col[r + 96];
+          a0 -= vold[r] * wc + wv[r] * vc;
+          a1 -= vold[r + 32] * wc + wv[r + 32] * vc;
+          a2 -= vold[r + 64] * wc + wv[r + 64] * vc;
+          a3 -= vold[r + 96] * wc + wv[r + 96] * vc;
+          col[r] = a0; col[r + 32] = a1; col[r + 64] = a2; col[r + 96] = a3;
+          dot += a0 * vnew[r]; dot += a1 * vnew[r + 32]; dot += a2 * vnew[r + 64]; dot += a3 * vnew[r + 96];
+          if (pub) { ll_store(Cout + r, a0, otag); ll_store(Cout + r + 32, a1, otag); ll_store(Cout + r + 64, a2, otag); ll_store(Cout + r + 96, a3, otag); }
+        }
+        for (; r < n; r += 32) {
+          double a = col[r];
+          a -= vold[r] * wc + wv[r] * vc;
+          col[r] = a;
+          dot += a * vnew[r];
+          if (pub) ll_store(Cout + r, a, otag);
+        }
+      }
+      dot = warp_sum_butterfly(dot);
+      if (lane == 0) ll_store(Pout + c, dot, otag);
+    }
+    double* t = vold; vold = vnew; vnew = t;
+    tau_old = tau;
+    // no barrier here: the pass reads vold / vnew / wv only; the next step overwrites ps / cs first and reaches wv and the other
+    // v buffer only behind block-wide barriers that every warp passes after leaving this loop
+  }
+}
+
+// ---- compact-WY panel factor (dlarft, forward / columnwise): T upper triangular, nb x nb, from G = V^T V and tau ------------
+__global__ void __launch_bounds__(256)
+larft_kernel(const double* __restrict__ Gbuf, const double* __restrict__ tauv, int n_refl, int nb, double* __restrict__ Tbuf) {
+  extern __shared__ __align__(16) double sm[];
+  double* T = sm;                 // nb x (nb+1): thread q walks row q, stride nb+1 = conflict-free
+  const double* __restrict__ G = Gbuf + (size_t)blockIdx.x * nb * nb;   // G[m][p]: one address per step for all threads (broadcast)
+  const int panel = blockIdx.x, p0 = panel * nb, kb = min(nb, n_refl - p0), tid = threadIdx.x, lt = nb + 1;
+  for (int i = tid; i < nb * lt; i += blockDim.x) T[i] = 0.0;
+  __syncthreads();
+  for (int p = 0; p < kb; p++) {
+    const double tp = tauv[p0 + p];
+    // T[q][p] = -tau_p * sum_{m = q .. p-1} T[q][m] G[m][p]   (q < p)
+    for (int q = tid; q < p; q += blockDim.x) {
+      double s = 0.0;
+      for (int m = q; m < p; m++) s += T[q * lt + m] * G[m * nb + p];
+      T[q * lt + p] = -tp * s;
+    }
+    if (tid == 0) T[p * lt + p] = tp;
+    __syncthreads();
+  }
+  for (int i = tid; i < nb * nb; i += blockDim.x) Tbuf[(size_t)panel * nb * nb + i] = T[(i / nb) * lt + (i % nb)];
+}
+
+// sign[i] = -1 if the component of largest magnitude of row i (first on ties) is negative — the convention of rayleigh_kernel
+__global__ void __launch_bounds__(256)
+eig_sign_kernel(const double* __restrict__ VT, int ld, int n, double* __restrict__ sign) {
+  const int lane = threadIdx.x & 31;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (i >= n) return;
+  double best = -1.0, bval = 0.0;
+  int bidx = 0x7fffffff;
+  for (int k = lane; k < n; k += 32) {
+    const double v = VT[(size_t)i * ld + k];
+    if (fabs(v) > best) { best = fabs(v); bval = v; bidx = k; }
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const double ob = __shfl_xor_sync(0xffffffffu, best, off), ov = __shfl_xor_sync(0xffffffffu, bval, off);
+    const int oi = __shfl_xor_sync(0xffffffffu, bidx, off);
+    if (ob > best || (ob == best && oi < bidx)) { best = ob; bval = ov; bidx = oi; }
+  }
+  if (lane == 0) sign[i] = bval < 0.0 ? -1.0 : 1.0;
+}
+
+template <typename T>
+bool ws_alloc(TridiagWs* ws, T** p, size_t count) {
+  if (cudaMalloc((void**)p, sizeof(T) * (count ? count : 1)) != cudaSuccess) return false;
+  cudaMemset(*p, 0, sizeof(T) * (count ? count : 1));
+  ws->allocs.push_back(*p);
+  return true;
+}
+
+int round_even(double x) { return 2 * (int)(x / 2.0 + 0.5); }
+
+}  // namespace
+
+void launch_eig_sign(cudaStream_t st, const double* VT, int ld, int n, double* sign) {
+  eig_sign_kernel<<<(n * 32 + 255) / 256, 256, 0, st>>>(VT, ld, n, sign);
+}
+
+TridiagWs* tridiag_ws_create(int n, int ld, int num_sms, char* err, size_t errlen) {
+  TridiagWs* ws = new TridiagWs();
+  ws->n = n; ws->ld = ld; ws->num_sms = num_sms;
+  auto fail = [&](const char* what) { if (err) snprintf(err, errlen, "tridiagonal eigensolver workspace: %s", what); tridiag_ws_destroy(ws); return (TridiagWs*)nullptr; };
+  const size_t mat = (size_t)n * ld;
+  // ---- stage 1 geometry
+  const int ns = (n + 1) & ~1;
+  int grid = num_sms < 1 ? 1 : num_sms;
+  if (grid > (n + 3) / 4) grid = (n + 3) / 4;        // at least ~4 columns per CTA: fewer slices to collect per step at small N
+  if (grid < 1) grid = 1;
+  const int nloc_max = (n + grid - 1) / grid;
+  const size_t vec_bytes = sizeof(double) * (5 * (size_t)ns + 32);
+  const size_t res_bytes = vec_bytes + sizeof(double) * (size_t)nloc_max * ns;
+  if (vec_bytes > kSmemCap) return fail("N too large for the shared-memory vectors of sytrd_kernel");
+  const char* force = getenv("KCMA_SYTRD_RESIDENT");
+  ws->resident = res_bytes <= kSmemCap && !(force && atoi(force) == 0);
+  ws->sy_grid = grid;
+  ws->sy_smem = ws->resident ? res_bytes : vec_bytes;
+  bool ok = true;
+  if (!ws->resident) ok = ok && ws_alloc(ws, &ws->Awork, mat);
+  ok = ok && ws_alloc(ws, &ws->dT, n) && ws_alloc(ws, &ws->eT, n) && ws_alloc(ws, &ws->tau, n) && ws_alloc(ws, &ws->VR, mat) &&
+       ws_alloc(ws, &ws->VC, mat);
+  LL* xb = nullptr;
+  ok = ok && ws_alloc(ws, &xb, 4 * (size_t)n);
+  ws->xbuf = xb;
+  // ---- stage 2 tree: uniform depth, even leaf boundaries, leaves of 2..32 rows
+  int levels = 0;
+  if (n > 32)
+    while ((n + (1 << levels) - 1) / (1 << levels) > 30) levels++;
+  const int leaves = 1 << levels;
+  ws->bounds.resize(leaves + 1);
+  for (int k = 0; k <= leaves; k++) ws->bounds[k] = (k == leaves) ? n : round_even((double)k * n / leaves);
+  for (int k = 0; k < leaves; k++) {
+    const int m = ws->bounds[k + 1] - ws->bounds[k];
+    if (m > 32 || (leaves > 1 && m < 2)) return fail("could not build the divide & conquer tree");
+  }
+  ws->levels = levels; ws->leaf_count = leaves;
+  std::vector<DcNode> all_nodes;
+  std::vector<int> row2node((size_t)std::max(levels, 1) * n, 0);
+  for (int l = 1; l <= levels; l++) {
+    std::vector<DcNode> v;
+    const int span = 1 << l;
+    ws->lvl_node_begin.push_back((int)all_nodes.size());
+    for (int k = 0; k < leaves; k += span) {
+      DcNode nd;
+      nd.off = ws->bounds[k];
+      nd.n1 = ws->bounds[k + span / 2] - nd.off;
+      nd.n = ws->bounds[k + span] - nd.off;
+      for (int r = nd.off; r < nd.off + nd.n; r++) row2node[(size_t)(l - 1) * n + r] = (int)all_nodes.size();
+      v.push_back(nd);
+      all_nodes.push_back(nd);
+    }
+    ws->lvl.push_back(v);
+  }
+  const size_t nn = all_nodes.size() ? all_nodes.size() : 1;
+  ok = ok && ws_alloc(ws, &ws->d_nodes, nn) && ws_alloc(ws, &ws->d_bounds, leaves + 1) && ws_alloc(ws, &ws->d_row2node, row2node.size());
+  ok = ok && ws_alloc(ws, &ws->dA, n) && ws_alloc(ws, &ws->dB, n) && ws_alloc(ws, &ws->Qa, mat) && ws_alloc(ws, &ws->XT, mat);
+  if (levels > 0) {
+    ok = ok && ws_alloc(ws, &ws->UT, mat) && ws_alloc(ws, &ws->DELTA, mat);
+    if (levels > 1) ok = ok && ws_alloc(ws, &ws->Qb, mat);
+    ok = ok && ws_alloc(ws, &ws->dl, n) && ws_alloc(ws, &ws->w, n) && ws_alloc(ws, &ws->what, n) && ws_alloc(ws, &ws->lam, n) &&
+         ws_alloc(ws, &ws->defl_val, n) && ws_alloc(ws, &ws->col2k, n) && ws_alloc(ws, &ws->nd_col, n) && ws_alloc(ws, &ws->defl_col, n) &&
+         ws_alloc(ws, &ws->rho, nn) && ws_alloc(ws, &ws->Kcnt, nn) && ws_alloc(ws, &ws->mixed, nn) && ws_alloc(ws, &ws->rot_c, n) &&
+         ws_alloc(ws, &ws->rot_s, n) && ws_alloc(ws, &ws->rot_p, n) && ws_alloc(ws, &ws->rot_q, n);
+  }
+  if (!ok) return fail("out of device memory");
+  if (!all_nodes.empty()) cudaMemcpy(ws->d_nodes, all_nodes.data(), sizeof(DcNode) * all_nodes.size(), cudaMemcpyHostToDevice);
+  cudaMemcpy(ws->d_bounds, ws->bounds.data(), sizeof(int) * (leaves + 1), cudaMemcpyHostToDevice);
+  cudaMemcpy(ws->d_row2node, row2node.data(), sizeof(int) * row2node.size(), cudaMemcpyHostToDevice);
+  // ---- stage 3 geometry
+  const int n_refl = n - 1;     // reflectors 0 .. n-2 (the last one is the identity, tau = 0)
+  const char* nbe = getenv("KCMA_WY_NB");
+  ws->nb = nbe ? atoi(nbe) : 128;
+  if (ws->nb < 16 || ws->nb > 128 || (ws->nb & 1)) ws->nb = 128;
+  ws->nbld = ws->nb;
+  ws->npanels = n_refl > 0 ? (n_refl + ws->nb - 1) / ws->nb : 0;
+  const int row_tiles = (n + 127) / 128;
+  ws->split1 = std::max(1, std::min(16, (num_sms + row_tiles - 1) / row_tiles));
+  if (ws->npanels > 0) {
+    ok = ok && ws_alloc(ws, &ws->Gbuf, (size_t)ws->npanels * ws->nb * ws->nb) && ws_alloc(ws, &ws->Tbuf, (size_t)ws->npanels * ws->nb * ws->nb) &&
+         ws_alloc(ws, &ws->VtilR, mat) && ws_alloc(ws, &ws->W2, (size_t)n * ws->nbld) &&
+         ws_alloc(ws, &ws->slabs, (size_t)ws->split1 * n * ws->nbld);
+    if (!ok) return fail("out of device memory");
+  }
+  // ---- static GEMM descriptors
+  std::vector<GemmDesc> descs;
+  for (int l = 1; l <= levels; l++) {
+    ws->desc_level_begin.push_back((int)descs.size());
+    const bool src_a = (l & 1) == 1;                 // leaves write Qa; level 1 reads Qa and writes Qb; ...
+    double* src = src_a ? ws->Qa : ws->Qb;
+    double* dst = src_a ? ws->Qb : ws->Qa;
+    const int node0 = ws->lvl_node_begin[l - 1];
+    for (size_t k = 0; k < ws->lvl[l - 1].size(); k++) {
+      const DcNode& nd = ws->lvl[l - 1][k];
+      GemmDesc g;
+      memset(&g, 0, sizeof(g));
+      const size_t o = (size_t)nd.off * ld + nd.off;
+      g.K = nd.n; g.alpha = 1.0; g.beta = 0.0; g.n1 = nd.n1; g.mixed = ws->mixed + node0 + k; g.splits = 1; g.split_stride = 0;
+      g.lda = g.ldb = g.ldc = ld;
+      if (l < levels) {          // Q_new[r][c] = sum_k Q[r][k] U^T[c][k]
+        g.A = src + o; g.B = ws->UT + o; g.C = dst + o; g.M = nd.n; g.Nc = nd.n; g.krule = 1;
+      } else {                   // last merge, transposed: X^T[r][c] = sum_k U^T[r][k] Q[c][k]
+        g.A = ws->UT + o; g.B = src + o; g.C = ws->XT + o; g.M = nd.n; g.Nc = nd.n; g.krule = 2;
+      }
+      descs.push_back(g);
+    }
+  }
+  const int nb = ws->nb;
+  ws->desc_g = (int)descs.size();
+  for (int p = 0; p < ws->npanels; p++) {      // G_p = V_p^T V_p  (rows of VR)
+    const int p0 = p * nb, kb = std::min(nb, n_refl - p0);
+    GemmDesc g; memset(&g, 0, sizeof(g));
+    g.A = ws->VR + (size_t)p0 * ld + p0; g.B = g.A; g.C = ws->Gbuf + (size_t)p * nb * nb;
+    g.M = kb; g.Nc = kb; g.K = n - p0; g.lda = g.ldb = ld; g.ldc = nb; g.alpha = 1.0; g.splits = 1;
+    descs.push_back(g);
+  }
+  ws->desc_vtil = (int)descs.size();
+  for (int p = 0; p < ws->npanels; p++) {      // VtilR_p[q][c] = sum_k T_p[q][k] V[c][p0 + k]
+    const int p0 = p * nb, kb = std::min(nb, n_refl - p0);
+    GemmDesc g; memset(&g, 0, sizeof(g));
+    g.A = ws->Tbuf + (size_t)p * nb * nb; g.B = ws->VC + (size_t)p0 * ld + p0; g.C = ws->VtilR + (size_t)p0 * ld + p0;
+    g.M = kb; g.Nc = n - p0; g.K = kb; g.lda = nb; g.ldb = ld; g.ldc = ld; g.alpha = 1.0; g.splits = 1;
+    descs.push_back(g);
+  }
+  ws->desc_gemm1 = (int)descs.size();
+  for (int p = 0; p < ws->npanels; p++) {      // slabs: W[r][q] = sum_c X^T[r][c] VtilR_p[q][c], c >= p0
+    const int p0 = p * nb, kb = std::min(nb, n_refl - p0);
+    GemmDesc g; memset(&g, 0, sizeof(g));
+    g.A = ws->XT + p0; g.B = ws->VtilR + (size_t)p0 * ld + p0; g.C = ws->slabs;
+    g.M = n; g.Nc = kb; g.K = n - p0; g.lda = ld; g.ldb = ld; g.ldc = ws->nbld; g.alpha = 1.0; g.splits = ws->split1;
+    g.split_stride = (long long)n * ws->nbld;
+    descs.push_back(g);
+  }
+  ws->desc_gemm2 = (int)descs.size();
+  for (int p = 0; p < ws->npanels; p++) {      // X^T[r][c] -= sum_q W[r][q] V[c][p0 + q], c >= p0
+    const int p0 = p * nb, kb = std::min(nb, n_refl - p0);
+    GemmDesc g; memset(&g, 0, sizeof(g));
+    g.A = ws->W2; g.B = ws->VC + (size_t)p0 * ld + p0; g.C = ws->XT + p0;
+    g.M = n; g.Nc = n - p0; g.K = kb; g.lda = ws->nbld; g.ldb = ld; g.ldc = ld; g.alpha = -1.0; g.beta = 1.0; g.splits = 1;
+    descs.push_back(g);
+  }
+  if (!ws_alloc(ws, &ws->d_desc, descs.size() ? descs.size() : 1)) return fail("out of device memory");
+  if (!descs.empty()) cudaMemcpy(ws->d_desc, descs.data(), sizeof(GemmDesc) * descs.size(), cudaMemcpyHostToDevice);
+  // kernel attributes
+  cudaError_t e1 = cudaFuncSetAttribute(sytrd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCap);
+  cudaError_t e2 = cudaFuncSetAttribute(sytrd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCap);
+  cudaError_t e3 = cudaFuncSetAttribute(larft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 128 * 129));
+  if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) return fail("cudaFuncSetAttribute failed");
+  if (cudaDeviceSynchronize() != cudaSuccess) return fail("CUDA error while building the workspace");
+  return ws;
+}
+
+void tridiag_ws_destroy(TridiagWs* ws) {
+  if (!ws) return;
+  for (void* p : ws->allocs) cudaFree(p);
+  delete ws;
+}
+
+bool tridiag_stage_sytrd(cudaStream_t st, TridiagWs* ws, const double* M) {
+  int n = ws->n, ld = ws->ld, ns = (n + 1) & ~1;
+  LL* xP = (LL*)ws->xbuf;
+  LL* xC = xP + 2 * (size_t)n;
+  cudaMemsetAsync(ws->xbuf, 0, sizeof(LL) * 4 * (size_t)n, st);
+  double* Awork = ws->Awork;
+  if (!ws->resident) cudaMemcpyAsync(Awork, M, sizeof(double) * (size_t)n * ld, cudaMemcpyDeviceToDevice, st);
+  double *dT = ws->dT, *eT = ws->eT, *tau = ws->tau, *VR = ws->VR;
+  void* args[] = {&M, &Awork, &ld, &n, &ns, &xP, &xC, &dT, &eT, &tau, &VR};
+  const void* fn = ws->resident ? (const void*)sytrd_kernel<true> : (const void*)sytrd_kernel<false>;
+  if (cudaLaunchCooperativeKernel(fn, dim3(ws->sy_grid), dim3(SY_NT), args, ws->sy_smem, st) != cudaSuccess) return false;
+  // row n-1 of VR (no reflector) and tau[n-1] stay zero from the allocation; VC = VR^T
+  launch_transpose(st, ws->VR, ws->VC, ld, n);
+  return cudaGetLastError() == cudaSuccess;
+}
+
+bool tridiag_stage_dc(cudaStream_t st, TridiagWs* ws, int* launches) { return dc_solve(st, ws, launches); }
+
+bool tridiag_stage_back(cudaStream_t st, TridiagWs* ws, int* launches) {
+  const int n = ws->n, nb = ws->nb, n_refl = n - 1;
+  if (ws->npanels == 0) return true;
+  launch_gemm_batched(st, ws->d_desc + ws->desc_g, ws->npanels, nb, nb, 1);
+  larft_kernel<<<ws->npanels, 256, sizeof(double) * nb * (nb + 1), st>>>(ws->Gbuf, ws->tau, n_refl, nb, ws->Tbuf);
+  launch_gemm_batched(st, ws->d_desc + ws->desc_vtil, ws->npanels, nb, n, 1);
+  *launches += 3;
+  for (int p = ws->npanels - 1; p >= 0; p--) {
+    const int p0 = p * nb, kb = std::min(nb, n_refl - p0);
+    launch_gemm_batched(st, ws->d_desc + ws->desc_gemm1 + p, 1, n, kb, ws->split1);
+    launch_reduce_slabs(st, ws->slabs, (long long)n * ws->nbld, ws->split1, n, kb, ws->nbld, ws->W2, ws->num_sms);
+    launch_gemm_batched(st, ws->d_desc + ws->desc_gemm2 + p, 1, n, n - p0, 1);
+    *launches += 3;
+  }
+  return cudaGetLastError() == cudaSuccess;
+}
+
+bool launch_eigen_tridiag(cudaStream_t st, TridiagWs* ws, const double* M, double** VT_out, double** ev_out, int* launches) {
+  if (!tridiag_stage_sytrd(st, ws, M)) return false;
+  *launches += 4;
+  if (!dc_solve(st, ws, launches)) return false;
+  if (!tridiag_stage_back(st, ws, launches)) return false;
+  *VT_out = ws->XT;
+  *ev_out = ws->ev_final;
+  return true;
+}
+
+const double* tridiag_result_vectors(const TridiagWs* ws) { return ws->XT; }
+const double* tridiag_result_values(const TridiagWs* ws) { return ws->ev_final; }
+
+void tridiag_get_tridiagonal(TridiagWs* ws, double* d, double* e, double* tau, double* vr) {
+  const int n = ws->n;
+  cudaMemcpy(d, ws->dT, sizeof(double) * n, cudaMemcpyDeviceToHost);
+  cudaMemcpy(e, ws->eT, sizeof(double) * n, cudaMemcpyDeviceToHost);
+  cudaMemcpy(tau, ws->tau, sizeof(double) * n, cudaMemcpyDeviceToHost);
+  if (vr) cudaMemcpy2D(vr, sizeof(double) * n, ws->VR, sizeof(double) * ws->ld, sizeof(double) * n, n, cudaMemcpyDeviceToHost);
+}
+
+void tridiag_set_tridiagonal(TridiagWs* ws, const double* d, const double* e) {
+  const int n = ws->n;
+  cudaMemcpy(ws->dT, d, sizeof(double) * n, cudaMemcpyHostToDevice);
+  cudaMemset(ws->eT, 0, sizeof(double) * n);
+  if (n > 1) cudaMemcpy(ws->eT, e, sizeof(double) * (n - 1), cudaMemcpyHostToDevice);
+}
+
+}  // namespace kc

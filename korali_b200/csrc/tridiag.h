@@ -1,0 +1,53 @@
+// tridiag.h — workspace of the tridiagonalisation-based eigensolver (internal; shared by tridiag.cu and dc.cu).
+#pragma once
+#include <vector>
+
+#include "kernels.h"
+
+namespace kc {
+
+struct DcNode { int off, n1, n; };   // a merge: rows/columns [off, off + n), children [off, off + n1) and [off + n1, off + n)
+
+struct TridiagWs {
+  int n = 0, ld = 0, num_sms = 148;
+  // ---- stage 1: Householder tridiagonalisation (sytrd_kernel)
+  bool resident = false;       // this CTA's columns live in shared memory (N <= ~1600), else in the global working copy
+  int sy_grid = 0; size_t sy_smem = 0;
+  double* Awork = nullptr;     // n x ld working copy (global variant only)
+  double *dT = nullptr, *eT = nullptr, *tau = nullptr;   // diagonal, off-diagonal, reflector scalars
+  double *VR = nullptr;        // row i = reflector v_i (support i+1.., v_i[i+1] = 1)
+  double *VC = nullptr;        // VR^T (column i = v_i)
+  void* xbuf = nullptr;        // LL exchange slots: [P | C] x 2 parities x n x 16 B
+  // ---- stage 2: divide & conquer on (dT, eT)
+  int levels = 0, leaf_count = 0;
+  std::vector<int> bounds;                 // leaf boundaries (even), leaf_count + 1 entries
+  std::vector<std::vector<DcNode>> lvl;    // lvl[l-1] = merges of level l = 1..levels
+  std::vector<int> lvl_node_begin;         // index of the level's first node in d_nodes
+  DcNode* d_nodes = nullptr;
+  int* d_bounds = nullptr;
+  int* d_row2node = nullptr;               // levels x n: global node index of the merge that owns row g at that level
+  double *dA = nullptr, *dB = nullptr;     // eigenvalues of the current / next level (ping-pong), n each
+  double *Qa = nullptr, *Qb = nullptr;     // eigenvector blocks (natural layout: columns = vectors), n x ld each (ping-pong)
+  double *UT = nullptr, *DELTA = nullptr;  // secular eigenvectors (rows) and pole differences, n x ld each
+  double *dl = nullptr, *w = nullptr, *what = nullptr, *lam = nullptr, *defl_val = nullptr;   // n each, indexed off + k
+  int *col2k = nullptr, *nd_col = nullptr, *defl_col = nullptr;                              // n each
+  double *rho = nullptr; int *Kcnt = nullptr, *mixed = nullptr, *nrot = nullptr;              // per node
+  double *rot_c = nullptr, *rot_s = nullptr; int *rot_p = nullptr, *rot_q = nullptr;          // n each (per-node lists at off)
+  double* XT = nullptr;                    // result: rows = eigenvectors (n x ld)
+  double* ev_final = nullptr;              // points at dA or dB
+  // ---- stage 3: compact-WY back-transform
+  int nb = 128, npanels = 0, split1 = 1, nbld = 128;
+  double *Gbuf = nullptr, *Tbuf = nullptr;   // npanels x nb x nb
+  double *VtilR = nullptr;                   // rows p = (T V^T)[p][:] per panel, n x ld
+  double *W2 = nullptr, *slabs = nullptr;    // n x nbld, split1 x n x nbld
+  // ---- descriptors (static: built once on the host)
+  GemmDesc* d_desc = nullptr;
+  std::vector<int> desc_level_begin;         // per merge level
+  int desc_g = 0, desc_vtil = 0, desc_gemm1 = 0, desc_gemm2 = 0;
+  std::vector<void*> allocs;
+};
+
+// dc.cu
+bool dc_solve(cudaStream_t st, TridiagWs* ws, int* launches);
+
+}  // namespace kc
