@@ -126,6 +126,7 @@ struct kcma {
   cudaStream_t cap_stream = nullptr;
   cudaGraphExec_t gexec = nullptr;
   bool capturing = false, graph_failed = false;
+  uint64_t dev_gen = ~0ull;   // value DevScalars::gen is known to hold on the device (~0 = unknown): the graph replay reads it
   uint64_t g_launches = 0, g_evals = 0;   // host-side counters one replay stands for
   std::string err, warn, reason;
   char warn_out[4096];
@@ -262,6 +263,7 @@ int push_scalars(kcma* h) {
   h->hSc->gen = h->gen - 1;   // device copy of the generation counter = last completed generation
   CUDA_OK(h, cudaMemcpyAsync(h->dSc, h->hSc, sizeof(DevScalars), cudaMemcpyHostToDevice, h->stream));
   CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  h->dev_gen = h->gen - 1;
   return 0;
 }
 
@@ -1213,6 +1215,7 @@ bool graph_eligible(const kcma* h) {
 bool build_graph(kcma* h) {
   if (!h->cap_stream && cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking) != cudaSuccess) { h->graph_failed = true; return false; }
   set_gen_kernel<<<1, 1, 0, h->stream>>>(h->dSc, h->gen - 1);
+  h->dev_gen = h->gen - 1;
   const uint64_t gen0 = h->gen, launches0 = h->launches, evals0 = h->model_evals;
   const cudaStream_t saved = h->stream;
   h->capturing = true;
@@ -1250,8 +1253,12 @@ int kcma_run_generation(kcma_t* h) {
   if (!h) return fail(nullptr, "null solver handle");
   CUDA_OK(h, cudaSetDevice(h->device));
   if (graph_eligible(h) && (h->gexec || build_graph(h))) {
+    // The replay takes the generation from DevScalars::gen (inc_gen_kernel is its first node). Eager generations in between
+    // (kcma_ask/eval/tell, or kcma_timing_enable) advance only the host counter: re-seed the device copy when it is behind.
+    if (h->dev_gen != h->gen - 1) { set_gen_kernel<<<1, 1, 0, h->stream>>>(h->dSc, h->gen - 1); h->launches++; }
     CUDA_OK(h, cudaGraphLaunch(h->gexec, h->stream));
     h->gen++;
+    h->dev_gen = h->gen - 1;
     h->launches += h->g_launches;
     h->model_evals += h->g_evals;
     h->scalars_fresh = false;
@@ -1753,7 +1760,7 @@ int kcma_k_tridiag_stage(int device, int mode, uint64_t n, const double* c, doub
     cudaMemcpy2D(dM, sizeof(double) * ld, c, sizeof(double) * N, sizeof(double) * N, N, cudaMemcpyHostToDevice);
     if (!tridiag_stage_sytrd(0, ws, dM)) rc = fail(nullptr, "sytrd launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     if (!rc && cudaDeviceSynchronize() != cudaSuccess) rc = fail(nullptr, "sytrd failed: %s", cudaGetErrorString(cudaGetLastError()));
-    if (!rc) tridiag_get_tridiagonal(ws, d, e, tau, vr);
+    if (!rc) { tridiag_get_tridiagonal(ws, d, e, tau, vr); tridiag_dump_prof(ws); }
     cudaFree(dM);
   } else {
     tridiag_set_tridiagonal(ws, d, e);

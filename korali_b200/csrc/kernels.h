@@ -52,6 +52,7 @@ const double* tridiag_result_vectors(const TridiagWs* ws);
 const double* tridiag_result_values(const TridiagWs* ws);
 void tridiag_get_tridiagonal(TridiagWs* ws, double* d, double* e, double* tau, double* vr /* n x n row-major reflectors */);
 void tridiag_set_tridiagonal(TridiagWs* ws, const double* d, const double* e);
+void tridiag_dump_prof(TridiagWs* ws);   // KCMA_SYTRD_PROF=step0[,cta]: prints the phase stamps of sytrd_kernel to stderr
 void launch_eig_sign(cudaStream_t st, const double* VT, int ld, int n, double* sign);
 
 // rng.cu

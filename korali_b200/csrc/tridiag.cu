@@ -47,23 +47,38 @@ __device__ __forceinline__ double ll_wait(const LL* p, unsigned long long tag) {
   return __longlong_as_double((long long)a);
 }
 
-// sum over the block, identical bits in every thread (and in every CTA: same thread count, same order)
-__device__ __forceinline__ double block_sum(double v, double* red) {
+__device__ __forceinline__ void ll_load(const LL* p, unsigned long long& a, unsigned long long& b) {
+  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+
+// Sum over the block, identical bits in every thread (and in every CTA: same thread count, same order). ONE barrier: `slot`
+// (SY_NW doubles) must not be rewritten before every thread has read it — the caller alternates four slots (2 sums x step parity),
+// so a slot is reused two steps (six barriers) later.
+__device__ __forceinline__ double block_sum(double v, double* slot) {
   v = warp_sum_butterfly(v);
-  __syncthreads();                       // red[] free again
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  if ((threadIdx.x & 31) == 0) slot[threadIdx.x >> 5] = v;
   __syncthreads();
   double s = 0.0;
 #pragma unroll
-  for (int k = 0; k < SY_NW; k++) s += red[k];
+  for (int k = 0; k < SY_NW; k++) s += slot[k];
   return s;
 }
 
+// The two element formulas of a step, with explicit roundings: they are evaluated per row by the row's thread AND for rows i, i+1
+// by every thread (scalars), and both must give the same bits.
+__device__ __forceinline__ double w_of(double tau, double p, double alpha, double v) { return __fma_rn(tau, p, __dmul_rn(alpha, v)); }
+__device__ __forceinline__ double col_upd(double c, double v, double wi, double w, double vi) {
+  return __dsub_rn(c, __fma_rn(v, wi, __dmul_rn(w, vi)));
+}
+
+// A step of thread t works on the rows r = t (mod SY_NT), r >= i, in every phase, so the received column (cs), the received
+// product (ps) and the reflector entries are thread-private although they live in shared memory: three block-wide barriers per
+// step (the two sums and the one in front of the pass over the columns).
 template <bool RESIDENT>
 __global__ void __launch_bounds__(SY_NT, 1)
 sytrd_kernel(const double* __restrict__ M, double* __restrict__ Awork, int ld, int n, int ns /* smem vector stride */,
              LL* __restrict__ xP, LL* __restrict__ xC, double* __restrict__ dT, double* __restrict__ eT, double* __restrict__ tauv,
-             double* __restrict__ VR) {
+             double* __restrict__ VR, long long* __restrict__ prof, int prof_step0, int prof_cta) {
   extern __shared__ __align__(16) double sm[];
   const int G = gridDim.x, b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   double* vold = sm;
@@ -71,8 +86,9 @@ sytrd_kernel(const double* __restrict__ M, double* __restrict__ Awork, int ld, i
   double* wv = sm + 2 * ns;
   double* ps = sm + 3 * ns;
   double* cs = sm + 4 * ns;
-  double* red = sm + 5 * ns;       // 32 doubles
-  double* Acol = red + 32;         // RESIDENT: nloc x ns
+  double* red = sm + 5 * ns;       // 4 slots x SY_NW doubles
+  double* bc = red + 32;           // 2 parities x {c_i, p_i, c_{i+1}, p_{i+1}}
+  double* Acol = red + 48;         // RESIDENT: nloc x ns
   const int nloc = b < n ? (n - b + G - 1) / G : 0;
   if (RESIDENT) {
     for (int s = warp; s < nloc; s += SY_NW) {
@@ -80,7 +96,7 @@ sytrd_kernel(const double* __restrict__ M, double* __restrict__ Awork, int ld, i
       for (int r = lane; r < n; r += 32) Acol[(size_t)s * ns + r] = src[r];
     }
   }
-  for (int r = tid; r < n; r += SY_NT) { vold[r] = 0.0; wv[r] = 0.0; }
+  for (int r = tid; r < ns; r += SY_NT) { vold[r] = 0.0; vnew[r] = 0.0; wv[r] = 0.0; ps[r] = 0.0; }
   if (b == 0) {   // owner of column 0 publishes it for step 0
     const double* src = M;
     for (int r = tid; r < n; r += SY_NT) ll_store(xC + r, src[r], 1ull);
@@ -92,31 +108,64 @@ sytrd_kernel(const double* __restrict__ M, double* __restrict__ Awork, int ld, i
     const unsigned long long tag = (unsigned long long)i + 1ull;
     const LL* Pin = xP + (size_t)par * n;
     const LL* Cin = xC + (size_t)par * n;
-    for (int r = i + tid; r < n; r += SY_NT) {
-      cs[r] = ll_wait(Cin + r, tag);
-      if (i > 0) ps[r] = ll_wait(Pin + r, tag);
+    const bool have_p = i > 0;
+    const bool pr = prof && b == prof_cta && tid == 0 && i >= prof_step0 && i < prof_step0 + 32;
+    if (pr) prof[(i - prof_step0) * 8 + 0] = clock64();
+    const int r0 = i + ((tid - i) & (SY_NT - 1));   // first row >= i of this thread
+    // ---- receive column i and p = A v_{i-1}: up to 8 slots polled together, so that their L2 round trips overlap
+    for (int rb = r0; rb < n; rb += 4 * SY_NT) {
+      unsigned long long va[8], ta[8];
+      unsigned pend = 0;
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        if (rb + k * SY_NT < n) pend |= (1u << k) | (have_p ? (16u << k) : 0u);
+      const unsigned want = pend;
+      while (pend) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          if (pend & (1u << k)) ll_load(Cin + rb + k * SY_NT, va[k], ta[k]);
+          if (pend & (16u << k)) ll_load(Pin + rb + k * SY_NT, va[4 + k], ta[4 + k]);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+          if ((pend >> k & 1u) && ta[k] == tag) pend &= ~(1u << k);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        if (want & (1u << k)) cs[rb + k * SY_NT] = __longlong_as_double((long long)va[k]);
+        if (want & (16u << k)) ps[rb + k * SY_NT] = __longlong_as_double((long long)va[4 + k]);
+      }
     }
-    __syncthreads();
-    if (i > 0) {
-      double part = 0.0;
-      for (int r = i + tid; r < n; r += SY_NT) part += ps[r] * vold[r];
-      const double pv = block_sum(part, red);
-      const double alpha = -0.5 * tau_old * (tau_old * pv);
-      for (int r = i + tid; r < n; r += SY_NT) wv[r] = tau_old * ps[r] + alpha * vold[r];
-      __syncthreads();
-      const double wi = wv[i], vi = vold[i];
-      for (int r = i + tid; r < n; r += SY_NT) cs[r] -= vold[r] * wi + wv[r] * vi;
-      __syncthreads();
+    if (pr) prof[(i - prof_step0) * 8 + 1] = clock64();
+    // ---- p.v (own rows), the four scalars every thread needs
+    double part = 0.0;
+    if (have_p)
+      for (int r = r0; r < n; r += SY_NT) part = __fma_rn(ps[r], vold[r], part);
+    double* bcp = bc + par * 4;
+    if (tid == (i & (SY_NT - 1))) { bcp[0] = cs[i]; bcp[1] = ps[i]; }
+    if (i + 1 < n && tid == ((i + 1) & (SY_NT - 1))) { bcp[2] = cs[i + 1]; bcp[3] = ps[i + 1]; }
+    const double pv = block_sum(part, red + (par * 2 + 0) * SY_NW);
+    const double alpha = -0.5 * tau_old * (tau_old * pv);
+    const double vi = vold[i];
+    const double wi = w_of(tau_old, bcp[1], alpha, vi);
+    // ---- w = tau p + alpha v and the column's own rank-2 update, own rows
+    double xpart = 0.0;
+    for (int r = r0; r < n; r += SY_NT) {
+      const double v = vold[r];
+      const double w = w_of(tau_old, ps[r], alpha, v);
+      wv[r] = w;
+      const double c = col_upd(cs[r], v, wi, w, vi);
+      cs[r] = c;
+      if (r >= i + 2) xpart = __fma_rn(c, c, xpart);
     }
-    const double di = cs[i];
+    const double di = col_upd(bcp[0], vi, wi, wi, vi);
     if (i == n - 1) {
       if (b == 0 && tid == 0) dT[i] = di;
       break;
     }
-    const double alph = cs[i + 1];
-    double part = 0.0;
-    for (int r = i + 2 + tid; r < n; r += SY_NT) part += cs[r] * cs[r];
-    const double xn2 = block_sum(part, red);
+    const double vi1 = vold[i + 1];
+    const double alph = col_upd(bcp[2], vi1, wi, w_of(tau_old, bcp[3], alpha, vi1), vi);
+    const double xn2 = block_sum(xpart, red + (par * 2 + 1) * SY_NW);
     double tau = 0.0, scale = 0.0, ei = alph;
     if (xn2 > 0.0) {
       const double beta = -copysign(sqrt(alph * alph + xn2), alph);
@@ -124,13 +173,10 @@ sytrd_kernel(const double* __restrict__ M, double* __restrict__ Awork, int ld, i
       scale = 1.0 / (alph - beta);
       ei = beta;
     }
-    for (int r = i + 1 + tid; r < n; r += SY_NT) vnew[r] = (r == i + 1) ? 1.0 : cs[r] * scale;
-    if (b == i % G) {   // the owner of the retired column records the step
-      if (tid == 0) { dT[i] = di; eT[i] = ei; tauv[i] = tau; }
-      double* vr = VR + (size_t)i * ld;
-      for (int r = tid; r < ld; r += SY_NT) vr[r] = (r <= i || r >= n) ? 0.0 : (r == i + 1 ? 1.0 : cs[r] * scale);
-    }
+    for (int r = (r0 > i ? r0 : r0 + SY_NT); r < n; r += SY_NT) vnew[r] = (r == i + 1) ? 1.0 : cs[r] * scale;
+    if (b == i % G && tid == 0) { dT[i] = di; eT[i] = ei; tauv[i] = tau; }   // the owner of the retired column records the step
     __syncthreads();
+    if (pr) prof[(i - prof_step0) * 8 + 2] = clock64();
     // one pass over this CTA's columns c >= i+1: rank-2 update of step i-1, then p = A v_new; the owner of column i+1 publishes it
     LL* Pout = xP + (size_t)(par ^ 1) * n;
     LL* Cout = xC + (size_t)(par ^ 1) * n;
@@ -173,10 +219,15 @@ sytrd_kernel(const double* __restrict__ M, double* __restrict__ Awork, int ld, i
       dot = warp_sum_butterfly(dot);
       if (lane == 0) ll_store(Pout + c, dot, otag);
     }
+    if (pr) prof[(i - prof_step0) * 8 + 3] = clock64();
+    if (b == i % G) {   // reflector i for the back-transform: off the critical path (the other CTAs' products are in flight meanwhile)
+      double* vr = VR + (size_t)i * ld;       // entries r <= i and r >= n stay zero from the allocation: no step ever writes them
+      for (int r = i + 1 + tid; r < n; r += SY_NT) vr[r] = vnew[r];
+    }
     double* t = vold; vold = vnew; vnew = t;
     tau_old = tau;
-    // no barrier here: the pass reads vold / vnew / wv only; the next step overwrites ps / cs first and reaches wv and the other
-    // v buffer only behind block-wide barriers that every warp passes after leaving this loop
+    // no barrier here: the pass reads vold / vnew / wv only; the next step writes its thread-private cs / ps rows first and reaches
+    // wv and the other v buffer only behind the barrier of its first sum, which every warp passes after leaving this loop
   }
 }
 
@@ -251,7 +302,7 @@ TridiagWs* tridiag_ws_create(int n, int ld, int num_sms, char* err, size_t errle
   if (grid > (n + 3) / 4) grid = (n + 3) / 4;        // at least ~4 columns per CTA: fewer slices to collect per step at small N
   if (grid < 1) grid = 1;
   const int nloc_max = (n + grid - 1) / grid;
-  const size_t vec_bytes = sizeof(double) * (5 * (size_t)ns + 32);
+  const size_t vec_bytes = sizeof(double) * (5 * (size_t)ns + 48);
   const size_t res_bytes = vec_bytes + sizeof(double) * (size_t)nloc_max * ns;
   if (vec_bytes > kSmemCap) return fail("N too large for the shared-memory vectors of sytrd_kernel");
   const char* force = getenv("KCMA_SYTRD_RESIDENT");
@@ -265,6 +316,11 @@ TridiagWs* tridiag_ws_create(int n, int ld, int num_sms, char* err, size_t errle
   LL* xb = nullptr;
   ok = ok && ws_alloc(ws, &xb, 4 * (size_t)n);
   ws->xbuf = xb;
+  if (const char* pe = getenv("KCMA_SYTRD_PROF")) {   // "step0[,cta]": clock64 stamps of 32 steps of one CTA (tridiag_dump_prof)
+    ws->prof_step0 = atoi(pe);
+    if (const char* comma = strchr(pe, ',')) ws->prof_cta = atoi(comma + 1);
+    ok = ok && ws_alloc(ws, &ws->prof, 32 * 8);
+  }
   // ---- stage 2 tree: uniform depth, even leaf boundaries, leaves of 2..32 rows
   int levels = 0;
   if (n > 32)
@@ -406,7 +462,9 @@ bool tridiag_stage_sytrd(cudaStream_t st, TridiagWs* ws, const double* M) {
   double* Awork = ws->Awork;
   if (!ws->resident) cudaMemcpyAsync(Awork, M, sizeof(double) * (size_t)n * ld, cudaMemcpyDeviceToDevice, st);
   double *dT = ws->dT, *eT = ws->eT, *tau = ws->tau, *VR = ws->VR;
-  void* args[] = {&M, &Awork, &ld, &n, &ns, &xP, &xC, &dT, &eT, &tau, &VR};
+  long long* prof = ws->prof;
+  int prof_step0 = ws->prof_step0, prof_cta = ws->prof_cta;
+  void* args[] = {&M, &Awork, &ld, &n, &ns, &xP, &xC, &dT, &eT, &tau, &VR, &prof, &prof_step0, &prof_cta};
   const void* fn = ws->resident ? (const void*)sytrd_kernel<true> : (const void*)sytrd_kernel<false>;
   if (cudaLaunchCooperativeKernel(fn, dim3(ws->sy_grid), dim3(SY_NT), args, ws->sy_smem, st) != cudaSuccess) return false;
   // row n-1 of VR (no reflector) and tau[n-1] stay zero from the allocation; VC = VR^T
@@ -452,6 +510,19 @@ void tridiag_get_tridiagonal(TridiagWs* ws, double* d, double* e, double* tau, d
   cudaMemcpy(e, ws->eT, sizeof(double) * n, cudaMemcpyDeviceToHost);
   cudaMemcpy(tau, ws->tau, sizeof(double) * n, cudaMemcpyDeviceToHost);
   if (vr) cudaMemcpy2D(vr, sizeof(double) * n, ws->VR, sizeof(double) * ws->ld, sizeof(double) * n, n, cudaMemcpyDeviceToHost);
+}
+
+void tridiag_dump_prof(TridiagWs* ws) {
+  if (!ws->prof) return;
+  long long h[32 * 8];
+  cudaMemcpy(h, ws->prof, sizeof(h), cudaMemcpyDeviceToHost);
+  fprintf(stderr, "sytrd_kernel phase stamps (clock64 cycles), CTA %d, n = %d, grid %d, %s:\n  step   receive   vectors      pass   to-next-step\n",
+          ws->prof_cta, ws->n, ws->sy_grid, ws->resident ? "shared-memory resident" : "global working copy");
+  for (int k = 0; k < 32; k++) {
+    const long long* r = h + k * 8;
+    if (!r[0] || !r[3]) continue;
+    fprintf(stderr, "  %4d  %8lld  %8lld  %8lld  %8lld\n", ws->prof_step0 + k, r[1] - r[0], r[2] - r[1], r[3] - r[2], k < 31 && h[(k + 1) * 8] ? h[(k + 1) * 8] - r[3] : 0ll);
+  }
 }
 
 void tridiag_set_tridiagonal(TridiagWs* ws, const double* d, const double* e) {

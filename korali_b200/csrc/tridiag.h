@@ -18,6 +18,7 @@ struct TridiagWs {
   double *VR = nullptr;        // row i = reflector v_i (support i+1.., v_i[i+1] = 1)
   double *VC = nullptr;        // VR^T (column i = v_i)
   void* xbuf = nullptr;        // LL exchange slots: [P | C] x 2 parities x n x 16 B
+  long long* prof = nullptr; int prof_step0 = 0, prof_cta = 0;   // optional clock64 phase stamps of 32 steps (KCMA_SYTRD_PROF)
   // ---- stage 2: divide & conquer on (dT, eT)
   int levels = 0, leaf_count = 0;
   std::vector<int> bounds;                 // leaf boundaries (even), leaf_count + 1 entries

@@ -450,6 +450,38 @@ def test_graph_replay_is_bit_identical_to_eager_launches(case):
     a.close(); b.close()
 
 
+@pytest.mark.parametrize("mode", ["ask_tell", "timing"])
+def test_graph_then_eager_then_graph_keeps_the_generation_counter(mode):
+    """The graph replay reads the generation (Philox counter, hsig exponent :658) from DevScalars::gen; eager generations in
+    between (kcma_ask/eval/tell, or kcma_timing_enable(1) as bench.py does) advance only the host counter. The device copy must
+    be re-seeded before the next replay, otherwise earlier generations' z draws are reused."""
+    case = dict(n=20, population_size=64, objective="NegRosenbrock", initial_value=0.1, initial_stddev=0.6, seed=21)
+    a = _lib.Solver(**case); b = _lib.Solver(**case)
+    def eager(s, k):
+        for _ in range(k):
+            s.ask(); s.eval(); s.tell()
+    eager(b, 22)
+    for _ in range(6):
+        a.run_generation()                      # 1-2 eager, 3-6 graph
+    if mode == "ask_tell":
+        eager(a, 5)                             # 7-11 eager; the graph stays alive
+    else:
+        a.timing_enable(True)
+        for _ in range(5):
+            a.run_generation()
+        a.timing_enable(False)
+    for _ in range(4):
+        a.run_generation()                      # 12-15 graph again
+    eager(a, 3)
+    for _ in range(4):
+        a.run_generation()                      # 19-22
+    assert a.scalar("Current Generation") == b.scalar("Current Generation") == 22
+    for k in ["Current Mean", "Evolution Path", "Conjugate Evolution Path", "Covariance Matrix", "Value Vector", "Best Ever Variables"]:
+        assert np.array_equal(a.get(k), b.get(k)), k
+    assert a.scalar("Sigma") == b.scalar("Sigma") and a.scalar("Best Ever Value") == b.scalar("Best Ever Value")
+    a.close(); b.close()
+
+
 # ---------------------------------------------------------------- Use Gradient Information ------------------
 @pytest.mark.parametrize("case", [
     dict(n=10, population_size=32, objective="NegSphere", initial_value=2.0, initial_stddev=1.5, gradient_step_size=0.01),
