@@ -31,16 +31,6 @@ def flops_per_generation(n, lam, mu):
     return 2.0 * n * n * lam, float(n) * (n + 1) * mu
 
 
-def jacobi_blocks(n, num_sms=148):
-    """(real 4-row blocks, blocks the tournament runs over, ring order?) — the dispatch rule of launch_jacobi_persistent (eigen.cu)."""
-    nb = ((n + 3) // 4 + 1) & ~1
-    nb_ring = 2
-    while nb_ring < nb:
-        nb_ring *= 2
-    ring = os.environ.get("KCMA_JACOBI_ORDER") != "rr" and nb_ring // 2 <= num_sms and (nb_ring - nb) * 8 <= nb
-    return nb, (nb_ring if ring else nb), ring
-
-
 def load_peaks():
     out = {}
     for name in ("MEASURED_PEAKS.json", "MEASURED_FP64.json"):
@@ -90,12 +80,13 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------
-def cpu_reference_run(steps, warmup, sample_lambda=1024):
-    """The reference algorithm on the host: the C restatement in oracle/ (the reference itself needs GSL/Eigen/meson and
-    cannot be built here — DESIGN.md). Single thread: CMAES.cpp.base has no OpenMP and its conduits only parallelise
-    the user model. One timed step = one generation on a BOUNDED SAMPLE of the population
-    (sample_lambda of the 65536 samples, all N = 1000 dimensions); the N x N eigendecomposition, whose cost does
-    not depend on lambda, is timed once. generations/s at the full population is extrapolated linearly in lambda."""
+def cpu_bounded_sample(steps, warmup, sample_lambda=1024):
+    """cpu_baseline leg of the default run (about 10-20 s of host work): the C restatement in oracle/ (the reference itself needs
+    GSL/Eigen/meson and cannot be built here — DESIGN.md), one thread (CMAES.cpp.base has no OpenMP and its conduits only
+    parallelise the user model), on a BOUNDED SAMPLE of the population: sample_lambda of the 65536 samples with all
+    N = 1000 dimensions per step, plus ONE full 1000 x 1000 eigendecomposition; extrapolated linearly in lambda. The extrapolation
+    FLATTERS the CPU: at the full population adaptC's double-indirect gather (CMAES.cpp.base:703-704) no longer fits the caches
+    (measured: `--impl reference`, which runs real full-size generations)."""
     from oracle import oracle as O
     from korali_b200._abi import INJ_BD
     n, lam = WORKLOAD["n"], WORKLOAD["population_size"]
@@ -119,20 +110,45 @@ def cpu_reference_run(steps, warmup, sample_lambda=1024):
             "ms_per_step": 1e3 * t_full}
 
 
+REF_MAX_GENERATIONS = 3        # real full-size generations timed by --impl reference ...
+REF_TIME_BUDGET_S = 1200.0     # ... as long as the next one is expected to end inside this budget (at least one is always run)
+
+
 def reference_arm(args, rank):
+    """--impl reference: REAL config-3 generations (N = 1000, lambda = 65536, own eigendecomposition, the reference's own RNG:
+    MT19937 + polar Box-Muller) of the reference algorithm on the host — oracle/okcma.c, the loop-for-loop C restatement of
+    CMAES.cpp.base (the reference itself cannot be built in this image: GSL, Eigen and meson-generated sources are absent,
+    DESIGN.md section 5). One thread, because the reference solver is single-threaded (no OpenMP in CMAES.cpp.base; the
+    Concurrent / Distributed conduits only parallelise the user model, which is 0.1 % of a generation here). A generation costs
+    minutes on a host core, so at most REF_MAX_GENERATIONS are timed inside REF_TIME_BUDGET_S, without warm-up generations
+    (nothing to warm on the CPU); `steps` in the line is the number actually timed."""
     if rank != 0:
         return
-    r = cpu_reference_run(args.steps, args.warmup)
+    from oracle import oracle as O
     lam = WORKLOAD["population_size"]
-    sample = ("oracle/okcma.c (C restatement of CMAES.cpp.base, gcc -O2, 1 thread); per step %d of %d samples x all 1000 dims "
-              "(%.3f s) extrapolated linearly in lambda + one full 1000x1000 eigendecomposition (%.2f s)"
-              % (r["sample_lambda"], lam, r["t_population_sample_s"], r["t_eigen_s"]))
-    line = {"impl": "reference", "metric": METRIC, "value": r["gens_per_sec"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "samples_per_sec": r["gens_per_sec"] * lam,
-            "config": {"workload": WORKLOAD_NAME},
-            "cpu_baseline": {"value": r["gens_per_sec"], "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
-            "e2e": {"value": r["gens_per_sec"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    o = O.Oracle(**WORKLOAD)
+    o.set_scalar("Termination Criteria/Max Model Evaluations", 1e18)
+    times, phases = [], []
+    t_begin = time.perf_counter()
+    for g in range(max(1, min(args.steps, REF_MAX_GENERATIONS))):
+        t0 = time.perf_counter(); o.ask(); t1 = time.perf_counter(); o.eval(); t2 = time.perf_counter(); o.tell(); t3 = time.perf_counter()
+        times.append(t3 - t0); phases.append((t1 - t0, t2 - t1, t3 - t2))
+        print("reference arm: generation %d  ask %.1f s  eval %.1f s  tell %.1f s" % (g + 1, t1 - t0, t2 - t1, t3 - t2), file=sys.stderr, flush=True)
+        if (time.perf_counter() - t_begin) + max(times) > REF_TIME_BUDGET_S:
+            break
+    t_gen = float(np.mean(times))
+    gps = 1.0 / t_gen
+    ph = np.mean(np.array(phases), axis=0)
+    sample = ("oracle/okcma.c (C restatement of CMAES.cpp.base, gcc -O2 -ffp-contract=off), 1 thread, %d REAL generation(s) at the full "
+              "size N=1000 lambda=65536 incl. the eigendecomposition: prepareGeneration %.1f s, evaluation %.1f s, updateDistribution %.1f s "
+              "per generation" % (len(times), ph[0], ph[1], ph[2]))
+    line = {"impl": "reference", "metric": METRIC, "value": gps, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+            "warmup": 0, "requested_steps": args.steps, "requested_warmup": args.warmup, "ms_per_step": 1e3 * t_gen,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "samples_per_sec": gps * lam,
+            "config": {"workload": WORKLOAD_NAME, "n": WORKLOAD["n"], "lambda": lam, "mu": lam // 2},
+            "cpu_baseline": {"value": gps, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+            "e2e": {"value": gps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
@@ -150,7 +166,73 @@ def hbm_block(phases, steps, n, lam_local, mu_local, hbm_peak):
     return out
 
 
+def gemm_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the shipped (persistent) gemm_tn_tma_kernel at config 3 on one
+    GPU, from the committed `ncu --set full` summary (profiles/r02_ncu_gemm_tn_tma.json; written by profiles/ncu_summary.py)."""
+    p = os.path.join(ROOT, "profiles", "r02_ncu_gemm_tn_tma.json")
+    if not os.path.exists(p):
+        return None, "no ncu capture committed"
+    d = json.load(open(p))
+    return d.get("dram_bytes_read", 0) + d.get("dram_bytes_write", 0), os.path.relpath(p, ROOT)
+
+
+def korali_experiment(max_generations):
+    """The user-facing call: a Korali script for config 3 (device conduit, built-in device objective)."""
+    import korali_b200 as korali
+    e = korali.Experiment()
+    e["Random Seed"] = WORKLOAD["seed"]
+    e["Problem"]["Type"] = "Optimization"
+    e["Problem"]["Objective Function"] = "Ellipsoid"
+    for i in range(WORKLOAD["n"]):
+        e["Variables"][i]["Name"] = "X%d" % i
+        e["Variables"][i]["Initial Value"] = WORKLOAD["initial_value"]
+        e["Variables"][i]["Initial Standard Deviation"] = WORKLOAD["initial_stddev"]
+    e["Solver"]["Type"] = "Optimizer/CMAES"
+    e["Solver"]["Population Size"] = WORKLOAD["population_size"]
+    e["Solver"]["Termination Criteria"]["Max Generations"] = max_generations
+    e["Solver"]["Termination Criteria"]["Max Model Evaluations"] = 1e18
+    e["Console Output"]["Verbosity"] = "Silent"
+    e["File Output"]["Enabled"] = False
+    return korali, e
+
+
+def e2e_through_engine(steps, warmup, devices):
+    """generations/s of generations warmup+1 .. warmup+steps through korali_b200.Engine().run(e), wall clock around the calls:
+    (time of a run of warmup+steps generations) - (time of a run of warmup generations), both from a fresh Experiment with the same
+    seed (same trajectory), so that experiment set-up, handle creation and the first-use allocations cancel."""
+    out = {}
+    for label, gens in (("short", warmup), ("long", warmup + steps)):
+        korali, e = korali_experiment(gens)
+        k = korali.Engine()
+        k["Conduit"]["Type"] = "Device"
+        if devices > 1:
+            k["Conduit"]["Devices"] = devices
+        t0 = time.perf_counter()
+        k.run(e)
+        best = e["Results"]["Best Sample"]["F(x)"]      # host read of the result
+        out[label] = time.perf_counter() - t0
+        out[label + "_generations"] = e["Current Generation"]
+        out["best"] = best
+    out["gens_per_sec"] = steps / max(out["long"] - out["short"], 1e-9)
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------------
+def timed_leg(s, steps, timers, torch, barrier):
+    """K generations between two CUDA events on the launching stream (libkcma uses the legacy default stream = torch's)."""
+    if timers:
+        s.timing_enable(True); s.timing_reset()
+    barrier()
+    l0 = s.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        s.run_generation()
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1), s.launch_count() - l0
+
+
 def ours_arm(args, rank, world):
     import torch
     import torch.distributed as dist
@@ -161,56 +243,84 @@ def ours_arm(args, rank, world):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n, lam = WORKLOAD["n"], WORKLOAD["population_size"]
     mu = lam // 2
-    s = _lib.Solver(device=local_rank, rank=rank, nranks=world, **WORKLOAD)
-    s.set_scalar("Termination Criteria/Max Model Evaluations", 1e18)
-    if world > 1:
-        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            uid = torch.tensor(list(_lib.comm_unique_id()), dtype=torch.uint8, device="cuda")
-        dist.broadcast(uid, 0)
-        s.comm_init(bytes(uid.cpu().tolist()))
+
+    def make_solver(nranks=world, r=rank):
+        s = _lib.Solver(device=local_rank, rank=r, nranks=nranks, **WORKLOAD)
+        s.set_scalar("Termination Criteria/Max Model Evaluations", 1e18)
+        if nranks > 1:
+            uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                uid = torch.tensor(list(_lib.comm_unique_id()), dtype=torch.uint8, device="cuda")
+            dist.broadcast(uid, 0)
+            s.comm_init(bytes(uid.cpu().tolist()))
+        return s
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- leg A (`value`): the product path as shipped — generations W+1 .. W+K from a fresh state, one kcma_run_generation per
+    # step (N = 1: one CUDA-graph replay per generation from the third generation on), no phase timers
+    s = make_solver()
     for _ in range(args.warmup):
         s.run_generation()
-    # ---- device-timed region: K generations, state resident in HBM --------------------------------------
-    s.timing_enable(True); s.timing_reset()
     clocks = ClockSampler(local_rank)
-    barrier()
-    l0 = s.launch_count()
     if rank == 0:
         clocks.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        s.run_generation()
-    e1.record()
-    barrier()
+    ms, launches = timed_leg(s, args.steps, False, torch, barrier)
     clk = clocks.stop() if rank == 0 else None
-    ms = e0.elapsed_time(e1)
-    launches = s.launch_count() - l0
-    phases = {p: s.timing(p) for p in ["eigen", "rng", "sample_gemm", "objective", "sort", "gather_mean", "rank_mu", "paths", "collectives", "generation"]}
-    sweeps = s.timing("eigen_sweeps")[1] / args.steps   # (counted on the device: read before the e2e leg adds its own)
-    s.timing_enable(False)
-    # ---- end-to-end through the reference-facing call: kcma_run (Experiment::run loop incl. termination chain) ----
+    best = s.scalar("Best Ever Value")
+    # ---- e2e through kcma_run (termination chain on the host every generation) on the same handle, next K generations
     barrier()
     t0 = time.perf_counter()
     done = s.run(args.steps)
-    best = s.scalar("Best Ever Value")       # device -> host read of the step's result
+    s.scalar("Best Ever Value")                 # device -> host read of the step's result
     torch.cuda.synchronize()
-    t_e2e = time.perf_counter() - t0
+    t_run = time.perf_counter() - t0
+    s.close()
+    # ---- leg B (phases, roofline): the SAME generations W+1 .. W+K from a fresh state with eager launches and a CUDA-event pair
+    # around every phase (the events keep the kernels of a generation from overlapping: slightly slower than leg A)
+    s = make_solver()
+    for _ in range(args.warmup):
+        s.run_generation()
+    ms_eager, launches_eager = timed_leg(s, args.steps, True, torch, barrier)
+    phase_names = ["eigen", "eigen_sytrd", "eigen_dc", "eigen_back", "rng", "sample_gemm", "objective", "sort", "gather_mean", "rank_mu",
+                   "paths", "collectives", "generation"]
+    phases = {p: s.timing(p) for p in phase_names}
+    sweeps = s.timing("eigen_sweeps")[1] / args.steps
+    s.timing_enable(False)
+    # ---- N > 1: correctness of the sharded run next to its speed — 3 generations from a fresh state against a 1-rank replica
+    parity = None
     if world > 1:
-        t = torch.tensor([ms, t_e2e * 1e3], device="cuda", dtype=torch.float64)
+        sh = make_solver()
+        rep = _lib.Solver(device=local_rank, **WORKLOAD) if rank == 0 else None
+        parity = {}
+        for g in range(3):
+            sh.run_generation()
+            if rep is not None:
+                rep.run_generation()
+                if g == 0:
+                    parity["value_vector_bit_exact_g1"] = bool(np.array_equal(sh.get("Value Vector"), rep.get("Value Vector")))
+                    parity["sorting_index_equal_g1"] = bool(np.array_equal(sh.get_index("Sorting Index"), rep.get_index("Sorting Index")))
+                c, c1 = sh.get("Covariance Matrix"), rep.get("Covariance Matrix")
+                parity["relerr_C_g%d" % (g + 1)] = float(np.abs(c - c1).max() / np.abs(c1).max())
+                m, m1 = sh.get("Current Mean"), rep.get("Current Mean")
+                parity["relerr_mean_g%d" % (g + 1)] = float(np.abs(m - m1).max() / np.abs(m1).max())
+                parity["relerr_sigma_g%d" % (g + 1)] = abs(sh.scalar("Sigma") - rep.scalar("Sigma")) / rep.scalar("Sigma")
+        sh.close()
+        if rep is not None:
+            rep.close()
+        t = torch.tensor([ms, t_run * 1e3, ms_eager], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, t_e2e = float(t[0]), float(t[1]) * 1e-3
+        ms, t_run, ms_eager = float(t[0]), float(t[1]) * 1e-3, float(t[2])
+    s.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+    # ---- e2e through the user-facing API (N = 1; N > 1 behind Engine: "Devices")
+    eng = e2e_through_engine(args.steps, args.warmup, world) if world == 1 else None
     peaks = load_peaks()
     ms_step = ms / args.steps
     gens = 1e3 / ms_step
@@ -221,51 +331,66 @@ def ours_arm(args, rank, world):
     peak = peaks.get("fp64_dgemm_tflops_sustained")
     rk_ms, rk_calls = phases["rank_mu"]
     rk_avg = rk_ms / max(rk_calls, 1)
-    cpu = cpu_reference_run(8, 1) if world == 1 else None   # ~10 s of host work: 9 x 1024-sample generations + one eigendecomposition
+    cpu = cpu_bounded_sample(8, 1) if world == 1 else None   # ~10-20 s of host work
+    traffic, traffic_src = gemm_traffic() if world == 1 else (None, None)
+    eig_ms = phases["eigen"][0] / args.steps
+    tridiag = phases["eigen_sytrd"][1] > 0
+    e2e_value = eng["gens_per_sec"] if eng else done / t_run
     line = {
         "metric": METRIC, "value": gens, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "samples_per_sec": gens * lam,
         "config": {"workload": WORKLOAD_NAME, "n": n, "lambda": lam, "mu": mu, "parallelism": "population sharded x%d" % world,
                    "l2_hygiene": "inputs larger than L2: Z and Y are %.0f MB each per rank, re-streamed every generation" % (8.0 * n * lam / world / 1e6),
+                   "host_io": "the generation loop takes no per-step host input (samples are drawn on the device from Philox(seed, generation) "
+                              "counters, the objective is a device kernel): h2d 0 B, d2h 288 B = sizeof(DevScalars) for the termination chain",
+                   "generations_timed": "%d..%d from a fresh state (value, phases and e2e all cover the same generations)" % (args.warmup + 1, args.warmup + args.steps),
                    "best_ever_value_after_run": best},
-        "e2e": {"value": done / t_e2e, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 288,   # sizeof(DevScalars): the termination chain reads it once per generation
-                "note": "kcma_run(): Experiment::run loop with the termination chain evaluated on the host every generation (device scalars "
-                        "copied back each step); the generation loop takes no per-step host input (samples are drawn on the device from "
-                        "Philox(seed, generation) counters). Runs without phase timers (one CUDA-graph replay per generation), "
-                        "whereas `value` is timed with eager launches and the per-phase CUDA events enabled. The e2e leg continues from the "
-                        "state the timed leg left (generations K+W+1 .. 2K+W): the spectrum has spread a little more by then and the "
-                        "warm-started eigensolver needs about one sweep less per generation"},
+        "value_path": "kcma_run_generation x K, CUDA events on the launching stream" + (", one CUDA-graph replay per generation" if world == 1 else ", eager launches + NCCL"),
+        "value_eager_with_phase_timers": 1e3 / (ms_eager / args.steps),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 288,
+                "through": "korali_b200.Engine().run(e) (Conduit Device, Objective Function 'Ellipsoid'), wall clock; (run of W+K generations) - (run of W generations)" if eng
+                           else "kcma_run() on each rank (Experiment::run loop with the termination chain on the host every generation), wall clock, max over ranks",
+                "engine_run_seconds": {"W_generations": eng["short"], "W_plus_K_generations": eng["long"]} if eng else None,
+                "kcma_run_generations_per_sec": done / t_run,
+                "note": "no per-step host input exists on this path: h2d is 0 by construction, d2h is the scalar block the termination chain reads"},
         "gpu_launches": int(launches),
+        "gpu_launches_eager_leg": int(launches_eager),
         "clocks": clk,
         "roofline": {"kernel": "gemm_tn_tma_kernel (sampling GEMM Y = Z (B D)^T, TMA + mbarrier + DMMA.8x8x4)", "bound": "tensor",
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if peak else None,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch at N=1 (profiles/r01_ncu_full_summary.md):
-                     # 537.5 MB + 492.0 MB = the algorithmic Z read + Y write, i.e. no re-reads
-                     "traffic": 1029548288 if world == 1 else None, "traffic_unit": "bytes per launch",
-                     "peak_source": "MEASURED_FP64.json: cuBLAS DGEMM 8192^3 sustained on this pool's B200 (FP64 DMMA issue peak 37.1)",
+                     "traffic": traffic, "traffic_unit": "bytes per launch", "traffic_source": traffic_src,
+                     "peak_source": "MEASURED_FP64.json (builder-measured; the driver's MEASURED_PEAKS.json has no FP64 entry): cuBLAS DGEMM 8192^3 "
+                                    "sustained 35.44 TFLOP/s on this pool's B200; raw DMMA.8x8x4 issue peak 37.1 TFLOP/s",
+                     "frac_of_dmma_issue_peak": (achieved / peaks["fp64_dmma_issue_tflops"]) if peaks.get("fp64_dmma_issue_tflops") else None,
                      "algorithmic_flops_per_launch": f_sample, "avg_launch_ms": gemm_avg},
         "phases_ms_per_generation": {k: (v[0] / args.steps) for k, v in phases.items()},
-        "rank_mu": {"kernel": "syrk_tt_kernel", "avg_ms": rk_avg, "achieved_tflops": (f_rank / (rk_avg * 1e-3) * 1e-12) if rk_avg > 0 else 0.0,
+        "rank_mu": {"kernel": "syrk_tt_tma_kernel", "avg_ms": rk_avg, "achieved_tflops": (f_rank / (rk_avg * 1e-3) * 1e-12) if rk_avg > 0 else 0.0,
                     "algorithmic_flops_per_launch": f_rank},
         # the HBM-side kernels of a generation: algorithmic bytes / phase time against the measured copy bandwidth
         "hbm_kernels": hbm_block(phases, args.steps, n, lam // world, mu // world, peaks.get("hbm_gbs", 6547.2)),
-        "eigen": {"kernel": "jacobi_pipe_kernel (persistent cooperative one-sided Jacobi, Gram-update steps on DMMA.8x8x4; replicated on every rank)",
-                  "avg_ms": phases["eigen"][0] / args.steps, "sweeps_per_generation": sweeps,
-                  "bound": "latency: one dependent tournament step per pair of 4-row blocks and sweep; a step = flag handshake + 64 KB row fetch + Gram + 4 rounds + apply",
-                  # executed flops: per step and block pair 3 x (2 * 8 * 8 * N) for Gram, apply G, apply V; (N/4 - 1) * N/8 pair-steps per sweep
-                  "executed_flops_per_sweep": 12.0 * n ** 3,
-                  "achieved_tflops": (12.0 * n ** 3 * sweeps / (phases["eigen"][0] / args.steps * 1e-3) * 1e-12) if phases["eigen"][0] > 0 else 0.0,
-                  "tournament": "ring order, %d steps per sweep (%d real + %d phantom 4-row blocks)" % (jacobi_blocks(n)[1] - 1, jacobi_blocks(n)[0], jacobi_blocks(n)[1] - jacobi_blocks(n)[0])
-                                if jacobi_blocks(n)[2] else "round-robin order, %d steps per sweep" % (jacobi_blocks(n)[0] - 1),
-                  "us_per_step_of_8_rows": (phases["eigen"][0] / args.steps * 1e3 / max(sweeps * (jacobi_blocks(n)[1] - 1.0), 1e-9))},
-        "eigen_sweeps_per_generation": sweeps,
-        "gens_per_sec_excluding_eigen": 1e3 / max(ms_step - phases["eigen"][0] / args.steps, 1e-9),
+        "gens_per_sec_excluding_eigen": 1e3 / max(ms_eager / args.steps - eig_ms, 1e-9),
     }
+    if tridiag:
+        line["eigen"] = {"solver": "Householder tridiagonalisation (sytrd_kernel: one persistent cooperative launch, matrix resident in shared memory, "
+                                   "one LL all-to-all exchange per column) + divide & conquer (dc.cu) + compact-WY back-transform on DMMA GEMMs; replicated on every rank",
+                         "avg_ms": eig_ms, "sytrd_ms": phases["eigen_sytrd"][0] / args.steps, "dc_ms": phases["eigen_dc"][0] / args.steps,
+                         "back_transform_ms": phases["eigen_back"][0] / args.steps,
+                         "bound": "latency: N-1 dependent Householder steps, each one exchange through L2",
+                         "us_per_householder_step": phases["eigen_sytrd"][0] / args.steps * 1e3 / (n - 1),
+                         "nominal_flops": 4.0 / 3.0 * n ** 3 + 4.0 / 3.0 * n ** 3 + 4.0 * n ** 3,
+                         "achieved_tflops": ((4.0 / 3.0 + 4.0 / 3.0 + 4.0) * n ** 3 / (eig_ms * 1e-3) * 1e-12) if eig_ms > 0 else 0.0}
+    else:
+        line["eigen"] = {"solver": "jacobi_pipe_kernel (KCMA_EIGEN=jacobi: persistent cooperative one-sided Jacobi; replicated on every rank)",
+                         "avg_ms": eig_ms, "sweeps_per_generation": sweeps, "executed_flops_per_sweep": 12.0 * n ** 3}
+    if parity is not None:
+        line["parity_vs_n1"] = parity
     if cpu:
         line["cpu_baseline"] = {"value": cpu["gens_per_sec"], "unit": UNIT, "cores": 1, "kind": "port",
                                 "sample": "oracle/okcma.c, 1 thread: %d of %d samples per step (%.3f s) extrapolated linearly in lambda + one "
-                                          "1000x1000 eigendecomposition (%.2f s)" % (cpu["sample_lambda"], lam, cpu["t_population_sample_s"], cpu["t_eigen_s"])}
+                                          "1000x1000 eigendecomposition (%.2f s). The extrapolation flatters the CPU (adaptC's gather leaves the caches at "
+                                          "the full population): `bench.py --impl reference` times real full-size generations"
+                                          % (cpu["sample_lambda"], lam, cpu["t_population_sample_s"], cpu["t_eigen_s"])}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -133,6 +133,11 @@ const char* kcma_take_warnings(kcma_t* h);
 /* NCCL bootstrap: rank 0 makes an id, the launcher broadcasts the 128 bytes, every rank calls comm_init. */
 int kcma_comm_unique_id(uint8_t id_out[128]);
 int kcma_comm_init(kcma_t* h, const uint8_t id[128]);
+/* One process driving several devices (the Engine's k["Conduit"]["Devices"] = G; the reference analogue selects its Distributed
+ * conduit purely from k["Conduit"], distributed.cpp.base:13-90, engine.cpp:69-128): handles[r] was created with rank = r,
+ * nranks = count on its own device; builds the communicator of all of them. Afterwards kcma_run_generation must be called for every
+ * handle of a generation from its own host thread (the calls meet in the collectives). */
+int kcma_comm_init_all(kcma_t** handles, int count);
 /* Shard arithmetic used by every rank (pairs stay together when mirrored). Pure host code. */
 void kcma_shard_range(uint64_t population, int mirrored, int rank, int nranks, uint64_t* begin, uint64_t* end);
 

@@ -30,6 +30,8 @@ struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
   ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -39,7 +41,7 @@ struct NcclApi {
     if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
     if (!lib) { err = std::string("cannot load libnccl.so.2: ") + dlerror(); return false; }
 #define SYM(F) F = (decltype(F))dlsym(lib, "nccl" #F); if (!F) { err = "missing symbol nccl" #F; return false; }
-    SYM(GetUniqueId) SYM(CommInitRank) SYM(CommDestroy) SYM(AllGather) SYM(AllReduce) SYM(GetErrorString)
+    SYM(GetUniqueId) SYM(CommInitRank) SYM(CommDestroy) SYM(GroupStart) SYM(GroupEnd) SYM(AllGather) SYM(AllReduce) SYM(GetErrorString)
 #undef SYM
     return true;
   }
@@ -86,6 +88,9 @@ struct kcma {
   double *dLower = nullptr, *dUpper = nullptr, *dMinSd = nullptr, *dCoef = nullptr, *dShift = nullptr;
   double* dSigmaSampling = nullptr;
   unsigned char* dInfeasible = nullptr;
+  unsigned char* dFresh = nullptr;              // mirrored resampling rounds: pair was drawn in the previous round
+  unsigned long long* dRound = nullptr;         // {infeasible members, rows to redraw} of a resampling round (all-reduced over the ranks)
+  unsigned long long* hRound = nullptr;         // pinned
   // constraint path (K9)
   double *dG = nullptr, *dBounds = nullptr, *dNormal = nullptr, *dCaux = nullptr, *dBestCon = nullptr, *dU = nullptr;
   unsigned long long* dViol = nullptr;
@@ -252,6 +257,11 @@ int init_covariance(kcma* h) {
   return 0;
 }
 
+int nccl_check(kcma* h, ncclResult_t r, const char* what) {
+  if (r == ncclSuccess) return 0;
+  return fail(h, "NCCL error in %s: %s", what, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+}
+
 int pull_scalars(kcma* h) {
   if (h->scalars_fresh) return 0;
   CUDA_OK(h, cudaMemcpyAsync(h->hSc, h->dSc, sizeof(DevScalars), cudaMemcpyDeviceToHost, h->stream));
@@ -291,7 +301,8 @@ __global__ void copy_sigma_kernel(const DevScalars* sc, double* out) { *out = sc
 // infeasible flags -> list of z-rows to resample + counters (prepareGeneration :455-459, :484-490). Single block.
 __global__ void __launch_bounds__(1024)
 infeasible_compact_kernel(const unsigned char* __restrict__ flags, int samples, int mirrored, int* __restrict__ rows,
-                          int* __restrict__ count_out, DevScalars* __restrict__ sc) {
+                          int* __restrict__ count_out, DevScalars* __restrict__ sc, unsigned char* __restrict__ fresh,
+                          unsigned long long* __restrict__ round_out) {
   __shared__ int warp_tot[32];
   __shared__ int carry;
   __shared__ unsigned long long bad_total;
@@ -305,6 +316,9 @@ infeasible_compact_kernel(const unsigned char* __restrict__ flags, int samples, 
     if (j < items) {
       if (mirrored) { bad = flags[2 * j] + flags[2 * j + 1]; take = (bad == 2); }
       else { bad = flags[j]; take = bad != 0; }
+      // the reference counts an infeasible member once per DRAW (:457, :485-487): a mirrored pair with one feasible member is
+      // accepted and not drawn again, so it must not be counted again in the following rounds
+      if (fresh) { if (!fresh[j]) bad = 0; fresh[j] = take ? 1 : 0; }
     }
     if (bad) atomicAdd(&bad_total, (unsigned long long)bad);
     const unsigned m = __ballot_sync(0xffffffffu, take);
@@ -322,7 +336,7 @@ infeasible_compact_kernel(const unsigned char* __restrict__ flags, int samples, 
     if (threadIdx.x == 0) carry = c + warp_tot[31];
     __syncthreads();
   }
-  if (threadIdx.x == 0) { *count_out = carry; sc->infeasible_this_round = bad_total; }
+  if (threadIdx.x == 0) { *count_out = carry; sc->infeasible_this_round = bad_total; round_out[0] = bad_total; round_out[1] = (unsigned long long)carry; }
 }
 
 __global__ void bump_attempts_kernel(unsigned* attempt, const int* rows, int count) {
@@ -356,7 +370,7 @@ diag_sample_kernel(const double* __restrict__ Z, double* __restrict__ Y, int ld,
   }
 }
 
-__global__ void add_infeasible_from_round_kernel(DevScalars* sc) { sc->infeasible_sample_count += sc->infeasible_this_round; }
+__global__ void add_infeasible_from_round_kernel(DevScalars* sc, const unsigned long long* round) { sc->infeasible_sample_count += round[0]; }
 __global__ void flush_kernel(double* p, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = (double)i;
 }
@@ -418,8 +432,9 @@ int update_eigensystem(kcma* h, const double* dM) {
     int l = 4;
     bool ok;
     { PhaseTimer t1(h, "eigen_sytrd"); ok = tridiag_stage_sytrd(h->stream, h->tri, dM); }
+    if (ok) ok = tridiag_stage_back_fork(h->stream, h->tri, &l);   // Q accumulation on the side stream, next to stage 2
     if (ok) { PhaseTimer t2(h, "eigen_dc"); ok = tridiag_stage_dc(h->stream, h->tri, &l); }
-    if (ok) { PhaseTimer t3(h, "eigen_back"); ok = tridiag_stage_back(h->stream, h->tri, &l); }
+    if (ok) { PhaseTimer t3(h, "eigen_back"); ok = tridiag_stage_back_join(h->stream, h->tri, &l); }
     if (!ok) return fail(h, "the tridiagonal eigensolver could not be launched: %s", cudaGetErrorString(cudaGetLastError()));
     const double* vt = tridiag_result_vectors(h->tri);
     const double* ev = tridiag_result_values(h->tri);
@@ -506,24 +521,34 @@ int sample_population(kcma* h) {
       int* dRows = (int*)h->dSelS;                     // reuse: selection list is rebuilt in tell()
       unsigned* dAttempt = h->dAttempt;                // zeroed per generation
       const uint64_t maxres = h->cfg.max_infeasible_resamplings;
+      const bool multi = h->cfg.nranks > 1;
+      unsigned char* dFresh = (h->cfg.mirrored_sampling && maxres != 0) ? h->dFresh : nullptr;
+      if (dFresh) CUDA_OK(h, cudaMemsetAsync(dFresh, 1, local_zrows(h), h->stream));
       for (int round = 0; round < 1000000; round++) {
-        infeasible_compact_kernel<<<1, 1024, 0, h->stream>>>(h->dInfeasible, (int)ls, h->cfg.mirrored_sampling, dRows, h->dCount, h->dSc);
-        add_infeasible_from_round_kernel<<<1, 1, 0, h->stream>>>(h->dSc);
+        infeasible_compact_kernel<<<1, 1024, 0, h->stream>>>(h->dInfeasible, (int)ls, h->cfg.mirrored_sampling, dRows, h->dCount, h->dSc, dFresh,
+                                                             h->dRound);
+        // 'Infeasible Sample Count' and the decision to go on resampling are GLOBAL: every rank must leave this loop in the same
+        // round (the loop holds a collective) and must see the same counter in the termination chain
+        if (multi && nccl_check(h, g_nccl.AllReduce(h->dRound, h->dRound, 2, ncclUint64, ncclSum, h->comm, h->stream), "all-reduce(infeasible)")) return 1;
+        add_infeasible_from_round_kernel<<<1, 1, 0, h->stream>>>(h->dSc, h->dRound);
         h->launches += 2;
         h->scalars_fresh = false;
         if (maxres == 0) break;  // reference release build: size_t(Infinity) == 0 -> never resamples
         CUDA_OK(h, cudaMemcpyAsync(h->hCount, h->dCount, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_OK(h, cudaMemcpyAsync(h->hRound, h->dRound, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
         if (pull_scalars(h)) return 1;
         const int cnt = *h->hCount;
-        if (cnt == 0 || h->hSc->infeasible_sample_count >= maxres) break;
-        bump_attempts_kernel<<<(cnt + 255) / 256, 256, 0, h->stream>>>(dAttempt, dRows, cnt);
-        launch_philox_normal(h->stream, h->dZ, ld, cnt, N, h->cfg.seed, (unsigned)h->gen, zrow_begin, dAttempt, dRows, h->num_sms);
-        dim3 grid((N + 7) / 8, cnt);
-        resample_rows_kernel<<<grid, 256, 0, h->stream>>>(h->dZ, h->dY, ld, h->dA, N, dRows, h->cfg.diagonal_covariance, h->dD);
-        // re-check only the resampled rows (sample list = z-rows, or both members when mirrored)
-        launch_feasibility(h->stream, h->dY, ld, ls, N, h->cfg.mirrored_sampling, h->dMean, h->dSc, h->dLower, h->dUpper,
-                           h->dInfeasible, h->cfg.keep_population ? h->dX : nullptr, ld, nullptr, h->num_sms);
-        h->launches += 4;
+        if (h->hRound[1] == 0 || h->hSc->infeasible_sample_count >= maxres) break;
+        if (cnt > 0) {
+          bump_attempts_kernel<<<(cnt + 255) / 256, 256, 0, h->stream>>>(dAttempt, dRows, cnt);
+          launch_philox_normal(h->stream, h->dZ, ld, cnt, N, h->cfg.seed, (unsigned)h->gen, zrow_begin, dAttempt, dRows, h->num_sms);
+          dim3 grid((N + 7) / 8, cnt);
+          resample_rows_kernel<<<grid, 256, 0, h->stream>>>(h->dZ, h->dY, ld, h->dA, N, dRows, h->cfg.diagonal_covariance, h->dD);
+          // re-check only the resampled rows (sample list = z-rows, or both members when mirrored)
+          launch_feasibility(h->stream, h->dY, ld, ls, N, h->cfg.mirrored_sampling, h->dMean, h->dSc, h->dLower, h->dUpper,
+                             h->dInfeasible, h->cfg.keep_population ? h->dX : nullptr, ld, nullptr, h->num_sms);
+          h->launches += 4;
+        }
       }
     }
   }
@@ -754,11 +779,6 @@ int do_eval(kcma* h) {
   return 0;
 }
 
-int nccl_check(kcma* h, ncclResult_t r, const char* what) {
-  if (r == ncclSuccess) return 0;
-  return fail(h, "NCCL error in %s: %s", what, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
-}
-
 int do_tell(kcma* h) {
   const int N = h->N, ld = h->ld;
   const int lambda = (int)h->cur_lambda, mu = (int)h->cur_mu;
@@ -940,6 +960,8 @@ void kcma_destroy(kcma_t* h) {
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->hSc) cudaFreeHost(h->hSc);
   if (h->hCount) cudaFreeHost(h->hCount);
+  if (h->hRound) cudaFreeHost(h->hRound);
+  cudaFree(h->dFresh); cudaFree(h->dRound);
   for (auto& p : h->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (auto e : h->event_pool) cudaEventDestroy(e);
   delete h;
@@ -1091,6 +1113,8 @@ int kcma_create(const kcma_cfg* cfg, kcma_t** out) {
   }
   CREATE_CUDA(cudaMallocHost((void**)&h->hSc, sizeof(DevScalars)));
   CREATE_CUDA(cudaMallocHost((void**)&h->hCount, 4 * sizeof(int)));
+  CREATE_CUDA(cudaMallocHost((void**)&h->hRound, 2 * sizeof(unsigned long long)));
+  CREATE_CUDA(dmalloc(&h->dRound, 2)); CREATE_CUDA(dmalloc(&h->dFresh, h->max_local + 16));
   memset(h->hSc, 0, sizeof(DevScalars));
   CREATE_CUDA(cudaMemcpy(h->dLower, h->lower.data(), sizeof(double) * N, cudaMemcpyHostToDevice));
   CREATE_CUDA(cudaMemcpy(h->dUpper, h->upper.data(), sizeof(double) * N, cudaMemcpyHostToDevice));
@@ -1159,6 +1183,30 @@ int kcma_comm_init(kcma_t* h, const uint8_t id_in[128]) {
   ncclUniqueId id;
   memcpy(id.internal, id_in, 128);
   return nccl_check(h, g_nccl.CommInitRank(&h->comm, h->cfg.nranks, id, h->cfg.rank), "ncclCommInitRank");
+}
+
+// All ranks of ONE process (one handle per device, rank r = handles[r]): the communicator is built inside an NCCL group.
+int kcma_comm_init_all(kcma_t** handles, int count) {
+  if (!handles || count < 1) return fail(nullptr, "kcma_comm_init_all: no handles");
+  std::string err;
+  if (!g_nccl.load(err)) return fail(handles[0], "%s", err.c_str());
+  for (int r = 0; r < count; r++) {
+    if (!handles[r]) return fail(nullptr, "null solver handle");
+    if (handles[r]->cfg.nranks != count || handles[r]->cfg.rank != r)
+      return fail(handles[r], "kcma_comm_init_all: handle %d was created as rank %d of %d, expected rank %d of %d", r, handles[r]->cfg.rank,
+                  handles[r]->cfg.nranks, r, count);
+  }
+  ncclUniqueId id;
+  if (g_nccl.GetUniqueId(&id) != ncclSuccess) return fail(handles[0], "ncclGetUniqueId failed");
+  if (nccl_check(handles[0], g_nccl.GroupStart(), "ncclGroupStart")) return 1;
+  int rc = 0;
+  for (int r = 0; r < count && !rc; r++) {
+    if (cudaSetDevice(handles[r]->device) != cudaSuccess) { rc = fail(handles[r], "cudaSetDevice(%d) failed", handles[r]->device); break; }
+    rc = nccl_check(handles[r], g_nccl.CommInitRank(&handles[r]->comm, count, id, r), "ncclCommInitRank");
+  }
+  const ncclResult_t ge = g_nccl.GroupEnd();
+  if (!rc) rc = nccl_check(handles[0], ge, "ncclGroupEnd");
+  return rc;
 }
 
 int kcma_ask(kcma_t* h) {
@@ -1567,6 +1615,20 @@ int kcma_set_scalar(kcma_t* h, const char* key, double v) {
   U("Termination Criteria/Max Infeasible Resamplings", h->cfg.max_infeasible_resamplings = (uint64_t)v)
 #undef U
   if (!strcmp(key, "Infeasible Sample Count")) { h->hSc->infeasible_sample_count = (unsigned long long)v; return push_scalars(h); }
+  // counters of the constraint path (restored by loadState: CMAES.cpp:1042-1560 reads every internal setting back)
+#define C(K, F) if (!strcmp(key, K)) { h->hSc->F = (unsigned long long)(long long)v; return push_scalars(h); }
+  C("Resampled Parameter Count", resampled_parameter_count) C("Covariance Matrix Adaptation Count", cov_adaptation_count)
+  C("Max Constraint Violation Count", max_violation_count) C("Constraint Evaluation Count", constraint_evaluation_count)
+  C("Best Valid Sample", best_valid_sample)
+#undef C
+  if (!strcmp(key, "Is Viability Regime")) {
+    // the regime decides population size, mu and the weights (:52-62, :336-344); unlike checkMeanAndSetRegime this restores a
+    // saved regime and therefore must NOT re-initialise C, sigma and the boundaries
+    if (!h->has_constraints) return (v != 0.0) ? fail(h, "'Is Viability Regime' needs a constrained problem") : 0;
+    h->is_viability = v != 0.0 ? 1 : 0;
+    set_population(h, h->is_viability ? h->vlambda : h->lambda, h->is_viability ? h->vmu : h->mu);
+    return init_mu_weights(h, h->cur_mu);
+  }
   return fail(h, "unknown scalar key '%s'", key);
 }
 

@@ -56,104 +56,110 @@ dc_tear_kernel(const double* __restrict__ dT, const double* __restrict__ eT, con
   dout[i] = v;
 }
 
-// ---- leaves: one warp per leaf, two-sided cyclic Jacobi (round-robin order) on the dense <= 32 x 32 block --------------
+// ---- leaves: one CTA per leaf, two-sided cyclic Jacobi (round-robin order) on the dense <= 32 x 32 block ------------------
+// A round = np/2 disjoint rotations: parameters (one thread per pair), then A <- A J and V <- V J as (row, pair) work items, then
+// A <- J^T A as (column, pair) work items: three barriers per round, all 256 threads busy.
 constexpr int LEAF_MAX = 32;
 constexpr int LEAF_LD = LEAF_MAX + 1;
-constexpr int LEAF_WARPS = 2;   // 2 x (A + V) = 34 KB of static shared memory
+constexpr int LEAF_NT = 256;
 
-__global__ void __launch_bounds__(LEAF_WARPS * 32)
+__global__ void __launch_bounds__(LEAF_NT)
 dc_leaf_kernel(const int* __restrict__ bounds, int leaves, const double* __restrict__ dtorn, const double* __restrict__ eT,
                double* __restrict__ dout, double* __restrict__ Q, int ld) {
-  __shared__ double As[LEAF_WARPS][LEAF_MAX * LEAF_LD], Vs[LEAF_WARPS][LEAF_MAX * LEAF_LD];
-  __shared__ double cs_c[LEAF_WARPS][LEAF_MAX / 2], cs_s[LEAF_WARPS][LEAF_MAX / 2], diag[LEAF_WARPS][LEAF_MAX];
-  __shared__ int cs_p[LEAF_WARPS][LEAF_MAX / 2], cs_q[LEAF_WARPS][LEAF_MAX / 2], rnk[LEAF_WARPS][LEAF_MAX];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int leaf = blockIdx.x * LEAF_WARPS + warp;
+  __shared__ double A[LEAF_MAX * LEAF_LD], V[LEAF_MAX * LEAF_LD];
+  __shared__ double cs_c[LEAF_MAX / 2], cs_s[LEAF_MAX / 2], diag[LEAF_MAX], nrm_s[LEAF_MAX];
+  __shared__ int cs_p[LEAF_MAX / 2], cs_q[LEAF_MAX / 2], rnk[LEAF_MAX], rotated;
+  const int tid = threadIdx.x;
+  const int leaf = blockIdx.x;
   if (leaf >= leaves) return;
   const int off = bounds[leaf], m = bounds[leaf + 1] - off;
-  double* A = As[warp];
-  double* V = Vs[warp];
-  double nrm = 0.0;
-  if (lane < m) {
-    for (int j = 0; j < m; j++) { A[lane * LEAF_LD + j] = 0.0; V[lane * LEAF_LD + j] = (j == lane) ? 1.0 : 0.0; }
-    const double dd = dtorn[off + lane];
-    A[lane * LEAF_LD + lane] = dd;
-    nrm = fabs(dd);
-    if (lane + 1 < m) {
-      const double ee = eT[off + lane];
-      A[lane * LEAF_LD + lane + 1] = ee;
-      A[(lane + 1) * LEAF_LD + lane] = ee;
-      nrm = fmax(nrm, fabs(ee));
+  for (int i = tid; i < LEAF_MAX * LEAF_LD; i += LEAF_NT) { A[i] = 0.0; V[i] = 0.0; }
+  __syncthreads();
+  if (tid < m) {
+    const double dd = dtorn[off + tid];
+    A[tid * LEAF_LD + tid] = dd;
+    V[tid * LEAF_LD + tid] = 1.0;
+    double nv = fabs(dd);
+    if (tid + 1 < m) {
+      const double ee = eT[off + tid];
+      A[tid * LEAF_LD + tid + 1] = ee;
+      A[(tid + 1) * LEAF_LD + tid] = ee;
+      nv = fmax(nv, fabs(ee));
     }
+    nrm_s[tid] = nv;
   }
-  nrm = warp_max(nrm);
+  __syncthreads();
+  double nrm = 0.0;
+  for (int k = 0; k < m; k++) nrm = fmax(nrm, nrm_s[k]);
   const double thr = 0.25 * kEps * nrm;
-  __syncwarp();
-  const int np = (m + 1) & ~1;
+  const int np = (m + 1) & ~1, hp = np / 2;
   for (int sweep = 0; sweep < 60 && m > 1; sweep++) {
-    int rotated = 0;
+    if (tid == 0) rotated = 0;
+    __syncthreads();
     for (int round = 0; round < np - 1; round++) {
-      if (lane < np / 2) {
+      if (tid < hp) {
         int p, q;
-        rr_pair(np, round, lane, p, q);
+        rr_pair(np, round, tid, p, q);
         if (p > q) { const int t = p; p = q; q = t; }
-        double c = 1.0, s = 0.0;
+        double c = 1.0, sn = 0.0;
         if (q < m) {
           const double apq = A[p * LEAF_LD + q];
           if (fabs(apq) > thr) {
             const double theta = (A[q * LEAF_LD + q] - A[p * LEAF_LD + p]) / (2.0 * apq);
             const double t = copysign(1.0, theta) / (fabs(theta) + sqrt(theta * theta + 1.0));
             c = 1.0 / sqrt(t * t + 1.0);
-            s = t * c;
+            sn = t * c;
             rotated = 1;
           }
         } else { p = 0; q = 0; }
-        cs_c[warp][lane] = c; cs_s[warp][lane] = s; cs_p[warp][lane] = p; cs_q[warp][lane] = q;
+        cs_c[tid] = c; cs_s[tid] = sn; cs_p[tid] = p; cs_q[tid] = q;
       }
-      __syncwarp();
-      if (lane < m) {   // A <- A J, V <- V J : this lane's row, all pairs of the round
-        for (int k = 0; k < np / 2; k++) {
-          const double s = cs_s[warp][k];
-          if (s == 0.0) continue;
-          const double c = cs_c[warp][k];
-          const int p = cs_p[warp][k], q = cs_q[warp][k];
-          const double ap = A[lane * LEAF_LD + p], aq = A[lane * LEAF_LD + q];
-          A[lane * LEAF_LD + p] = c * ap - s * aq;
-          A[lane * LEAF_LD + q] = s * ap + c * aq;
-          const double vp = V[lane * LEAF_LD + p], vq = V[lane * LEAF_LD + q];
-          V[lane * LEAF_LD + p] = c * vp - s * vq;
-          V[lane * LEAF_LD + q] = s * vp + c * vq;
-        }
+      __syncthreads();
+      for (int it = tid; it < m * hp; it += LEAF_NT) {   // A <- A J, V <- V J: (row, pair)
+        const int row = it / hp, k = it - row * hp;
+        const double sn = cs_s[k];
+        if (sn == 0.0) continue;
+        const double c = cs_c[k];
+        const int p = cs_p[k], q = cs_q[k];
+        const double ap = A[row * LEAF_LD + p], aq = A[row * LEAF_LD + q];
+        A[row * LEAF_LD + p] = c * ap - sn * aq;
+        A[row * LEAF_LD + q] = sn * ap + c * aq;
+        const double vp = V[row * LEAF_LD + p], vq = V[row * LEAF_LD + q];
+        V[row * LEAF_LD + p] = c * vp - sn * vq;
+        V[row * LEAF_LD + q] = sn * vp + c * vq;
       }
-      __syncwarp();
-      if (lane < m) {   // A <- J^T A : this lane's column
-        for (int k = 0; k < np / 2; k++) {
-          const double s = cs_s[warp][k];
-          if (s == 0.0) continue;
-          const double c = cs_c[warp][k];
-          const int p = cs_p[warp][k], q = cs_q[warp][k];
-          const double ap = A[p * LEAF_LD + lane], aq = A[q * LEAF_LD + lane];
-          A[p * LEAF_LD + lane] = c * ap - s * aq;
-          A[q * LEAF_LD + lane] = s * ap + c * aq;
-        }
+      __syncthreads();
+      for (int it = tid; it < m * hp; it += LEAF_NT) {   // A <- J^T A: (column, pair)
+        const int k = it / m, col = it - k * m;
+        const double sn = cs_s[k];
+        if (sn == 0.0) continue;
+        const double c = cs_c[k];
+        const int p = cs_p[k], q = cs_q[k];
+        const double ap = A[p * LEAF_LD + col], aq = A[q * LEAF_LD + col];
+        A[p * LEAF_LD + col] = c * ap - sn * aq;
+        A[q * LEAF_LD + col] = sn * ap + c * aq;
       }
-      __syncwarp();
+      __syncthreads();
     }
-    if (!__any_sync(0xffffffffu, rotated)) break;
+    const int any = rotated;   // written before the last barrier of the sweep
+    __syncthreads();           // every thread has read it before the next sweep re-arms it
+    if (!any) break;
   }
   // ascending order, columns of Q = eigenvectors
-  if (lane < m) diag[warp][lane] = A[lane * LEAF_LD + lane];
-  __syncwarp();
-  if (lane < m) {
-    const double v = diag[warp][lane];
+  if (tid < m) diag[tid] = A[tid * LEAF_LD + tid];
+  __syncthreads();
+  if (tid < m) {
+    const double val = diag[tid];
     int r = 0;
-    for (int j = 0; j < m; j++) { const double o = diag[warp][j]; r += (o < v) || (o == v && j < lane); }
-    rnk[warp][lane] = r;
-    dout[off + r] = v;
+    for (int j = 0; j < m; j++) { const double o = diag[j]; r += (o < val) || (o == val && j < tid); }
+    rnk[tid] = r;
+    dout[off + r] = val;
   }
-  __syncwarp();
-  if (lane < m)
-    for (int c = 0; c < m; c++) Q[(size_t)(off + lane) * ld + off + rnk[warp][c]] = V[lane * LEAF_LD + c];
+  __syncthreads();
+  for (int it = tid; it < m * m; it += LEAF_NT) {
+    const int row = it / m, c = it - row * m;
+    Q[(size_t)(off + row) * ld + off + rnk[c]] = V[row * LEAF_LD + c];
+  }
 }
 
 // ---- merge set-up + deflation: one CTA per merge ------------------------------------------------------------------
@@ -208,26 +214,34 @@ dc_setup_kernel(const DcNode* __restrict__ nodes, int node0, const double* __res
     if (rho * zmax <= tol) {
       for (int pos = 0; pos < n; pos++) defl_col[off + M++] = ord[pos];
     } else {
+      // (pj, z_pj, d_pj) = the previous survivor, kept in registers; the close-pole test |tt c s| <= tol with c = z_i / t,
+      // s = -z_pj / t, t = hypot(z_i, z_pj) is evaluated without square root or division: |tt z_i z_pj| <= tol (z_i^2 + z_pj^2)
       int pj = -1;
+      double zpj = 0.0, dpj = 0.0;
+      int inext = ord[0];
+      double znext = z_s[inext], dnext = d_s[inext];
       for (int pos = 0; pos < n; pos++) {
-        const int i = ord[pos];
-        if (rho * fabs(z_s[i]) <= tol) { defl_col[off + M++] = i; continue; }
-        if (pj < 0) { pj = i; continue; }
-        double s = z_s[pj], c = z_s[i];
-        const double t = hypot(c, s), tt = d_s[i] - d_s[pj];
-        c /= t; s = -s / t;
-        if (fabs(tt * c * s) <= tol) {
+        const int i = inext;
+        const double zi = znext, dv = dnext;
+        if (pos + 1 < n) { inext = ord[pos + 1]; znext = z_s[inext]; dnext = d_s[inext]; }
+        if (rho * fabs(zi) <= tol) { defl_col[off + M++] = i; continue; }
+        if (pj < 0) { pj = i; zpj = zi; dpj = dv; continue; }
+        const double tt = dv - dpj, t2 = zi * zi + zpj * zpj;
+        if (fabs(tt * zi * zpj) <= tol * t2) {
+          const double t = sqrt(t2);
+          const double c = zi / t, sn = -zpj / t;
           z_s[i] = t; z_s[pj] = 0.0;
-          rot_p[off + nrot] = pj; rot_q[off + nrot] = i; rot_c[off + nrot] = c; rot_s[off + nrot] = s; nrot++;
-          const double tn = d_s[pj] * c * c + d_s[i] * s * s;
-          d_s[i] = d_s[pj] * s * s + d_s[i] * c * c;
+          rot_p[off + nrot] = pj; rot_q[off + nrot] = i; rot_c[off + nrot] = c; rot_s[off + nrot] = sn; nrot++;
+          const double tn = dpj * c * c + dv * sn * sn;
+          const double di = dpj * sn * sn + dv * c * c;
+          d_s[i] = di;
           d_s[pj] = tn;
           defl_col[off + M++] = pj;
           if ((pj < n1) != (i < n1)) mix = 1;
-          pj = i;
+          pj = i; zpj = t; dpj = di;
         } else {
           nd_col[off + K++] = pj;
-          pj = i;
+          pj = i; zpj = zi; dpj = dv;
         }
       }
       if (pj >= 0) nd_col[off + K++] = pj;
@@ -375,17 +389,13 @@ void launch_transpose(cudaStream_t st, const double* in, double* out, int ld, in
 // Eigen-decomposition of the tridiagonal (ws->dT, ws->eT): rows of ws->XT = eigenvectors, ws->ev_final = ascending eigenvalues.
 bool dc_solve(cudaStream_t st, TridiagWs* ws, int* launches) {
   const int n = ws->n, ld = ws->ld;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(dc_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr = true;
-  }
+  static std::atomic<unsigned long long> attr{0};
+  if (first_call_on_device(attr)) cudaFuncSetAttribute(dc_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   const size_t mat = sizeof(double) * (size_t)n * ld;
   cudaMemsetAsync(ws->Qa, 0, mat, st);
   if (ws->levels > 1) cudaMemsetAsync(ws->Qb, 0, mat, st);
   dc_tear_kernel<<<(n + 255) / 256, 256, 0, st>>>(ws->dT, ws->eT, ws->d_bounds, ws->leaf_count, n, ws->dB);
-  dc_leaf_kernel<<<(ws->leaf_count + LEAF_WARPS - 1) / LEAF_WARPS, LEAF_WARPS * 32, 0, st>>>(ws->d_bounds, ws->leaf_count, ws->dB,
-                                                                                             ws->eT, ws->dA, ws->Qa, ld);
+  dc_leaf_kernel<<<ws->leaf_count, LEAF_NT, 0, st>>>(ws->d_bounds, ws->leaf_count, ws->dB, ws->eT, ws->dA, ws->Qa, ld);
   *launches += 2;
   double *dcur = ws->dA, *dnext = ws->dB;
   double *qsrc = ws->Qa;

@@ -712,8 +712,8 @@ bool eigen_small_fits(int n) { return eigen_small_smem_bytes(n) <= kMaxDynSmem; 
 void launch_eigen_small(cudaStream_t st, const double* C, int ld, int n, double* VT, double* GT, double* B, double* A, double* D,
                         double tol, int max_sweeps, DevScalars* sc) {
   launch_gemm_tn(st, n, n, n, VT, ld, C, ld, GT, ld);   // GT[i][j] = sum_k VT[i][k] C[j][k]
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(eigen_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem); attr = true; }
+  static std::atomic<unsigned long long> attr{0};
+  if (first_call_on_device(attr)) cudaFuncSetAttribute(eigen_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
   eigen_small_kernel<<<1, 1024, eigen_small_smem_bytes(n), st>>>(GT, ld, n, VT, B, A, D, tol, max_sweeps, sc);
 }
 
@@ -739,15 +739,17 @@ bool launch_jacobi_persistent(cudaStream_t st, double* GT, double* VT, int ld, i
   bool anchor = ring && oe && strcmp(oe, "anchor") == 0;   // EXPERIMENTAL, opt-in only: ring order + resident first block (ORDER 2)
   if (ring) nb = nb_ring;
   static int coop = -1;
-  if (coop < 0) {
-    int dev = 0;
+  static std::atomic<unsigned long long> attr{0};
+  if (first_call_on_device(attr)) {
+    int dev = 0, c = 0;
     cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-    if (coop && (cudaFuncSetAttribute(jacobi_pipe_kernel<256, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem - 16 * 1024) != cudaSuccess ||
-                 cudaFuncSetAttribute(jacobi_pipe_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem - 16 * 1024) != cudaSuccess))
-      coop = 0;
+    cudaDeviceGetAttribute(&c, cudaDevAttrCooperativeLaunch, dev);
+    if (c && (cudaFuncSetAttribute(jacobi_pipe_kernel<256, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem - 16 * 1024) != cudaSuccess ||
+              cudaFuncSetAttribute(jacobi_pipe_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem - 16 * 1024) != cudaSuccess))
+      c = 0;
+    if (coop != 0) coop = c;
   }
-  if (!coop) return false;
+  if (coop <= 0) return false;
   if (anchor) {   // set up lazily so that the experimental instantiation can never disable the product path
     static int anchor_ok = -1;
     if (anchor_ok < 0) {
@@ -1052,8 +1054,8 @@ void launch_jacobi_block_sweep(cudaStream_t st, double* GT, double* VT, int ld, 
   if (big_enabled()) {   // 16-row blocks: N/16 - 1 steps per sweep
     int order = 0;
     const int nsb = big_blocks(n, &order);
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(jacobi_big_step_kernel<BIG_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_smem_bytes()); attr = true; }
+    static std::atomic<unsigned long long> attr{0};
+    if (first_call_on_device(attr)) cudaFuncSetAttribute(jacobi_big_step_kernel<BIG_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_smem_bytes());
     BigState& b = big_state();
     if ((size_t)(nsb / 2) > b.pairs) {
       cudaStreamSynchronize(st);

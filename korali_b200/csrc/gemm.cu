@@ -215,12 +215,11 @@ syrk_tt_kernel(int n, int K, const int* __restrict__ kptr, const double* __restr
 }
 
 // ---- host launchers ------------------------------------------------------------------------------
-static bool g_attr_set = false;
+static std::atomic<unsigned long long> g_attr_set{0};
 static void ensure_attrs() {
-  if (g_attr_set) return;
+  if (!first_call_on_device(g_attr_set)) return;
   cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_tn_smem_bytes());
   cudaFuncSetAttribute(syrk_tt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)syrk_tt_smem_bytes());
-  g_attr_set = true;
 }
 
 size_t gemm_tn_smem_bytes() { return sizeof(double) * STAGES * (BM + BN) * PADK; }

@@ -153,11 +153,8 @@ reduce_slabs_kernel(const double* __restrict__ slabs, long long stride, int spli
 }
 
 void launch_gemm_batched(cudaStream_t st, const GemmDesc* d_descs, int batch, int max_m, int max_nc, int max_splits) {
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(gemm_tn_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_batched_smem_bytes());
-    attr = true;
-  }
+  static std::atomic<unsigned long long> attr{0};
+  if (first_call_on_device(attr)) cudaFuncSetAttribute(gemm_tn_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_batched_smem_bytes());
   if (batch <= 0 || max_m <= 0 || max_nc <= 0) return;
   dim3 grid((max_nc + BN - 1) / BN, (max_m + BM - 1) / BM, batch * max_splits);
   gemm_tn_batched_kernel<<<grid, THREADS, gemm_batched_smem_bytes(), st>>>(d_descs, max_splits);

@@ -260,6 +260,12 @@ static EncodeTiledFn g_encode = nullptr;
 static int g_tma_state = 0;  // 0 unknown, 1 ok, -1 unavailable
 
 static bool tma_ready() {
+  static std::atomic<unsigned long long> attr{0};
+  if (first_call_on_device(attr)) {   // the shared-memory limits are per device; the driver entry point is per process
+    if (cudaFuncSetAttribute(gemm_tn_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(syrk_tt_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM) != cudaSuccess)
+      g_tma_state = -1;
+  }
   if (g_tma_state) return g_tma_state > 0;
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult q;
@@ -268,11 +274,6 @@ static bool tma_ready() {
     return false;
   }
   g_encode = (EncodeTiledFn)fn;
-  if (cudaFuncSetAttribute(gemm_tn_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM) != cudaSuccess ||
-      cudaFuncSetAttribute(syrk_tt_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM) != cudaSuccess) {
-    g_tma_state = -1;
-    return false;
-  }
   g_tma_state = 1;
   return true;
 }

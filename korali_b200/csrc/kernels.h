@@ -1,10 +1,21 @@
 // kernels.h — host-side launchers of the libkcma CUDA kernels (internal; the public surface is include/kcma.h).
 #pragma once
 #include <cuda_runtime.h>
+
+#include <atomic>
 #include <stddef.h>
 #include <stdint.h>
 
 namespace kc {
+
+// True exactly once per device of this process. Function attributes (dynamic shared-memory limits) are per device, and one
+// process may drive several devices (Engine: k["Conduit"]["Devices"], one host thread per device).
+inline bool first_call_on_device(std::atomic<unsigned long long>& mask) {
+  int d = 0;
+  cudaGetDevice(&d);
+  const unsigned long long bit = 1ull << (d & 63);
+  return !(mask.fetch_or(bit) & bit);
+}
 struct DevScalars;
 
 // gemm.cu
@@ -47,7 +58,8 @@ bool launch_eigen_tridiag(cudaStream_t st, TridiagWs* ws, const double* M, doubl
 // stage entry points for the parity tests (kcma_k_sytrd / kcma_k_stedc)
 bool tridiag_stage_sytrd(cudaStream_t st, TridiagWs* ws, const double* M);
 bool tridiag_stage_dc(cudaStream_t st, TridiagWs* ws, int* launches);
-bool tridiag_stage_back(cudaStream_t st, TridiagWs* ws, int* launches);
+bool tridiag_stage_back_fork(cudaStream_t st, TridiagWs* ws, int* launches);   // Q accumulation on the side stream (before stage 2)
+bool tridiag_stage_back_join(cudaStream_t st, TridiagWs* ws, int* launches);   // X^T = Z^T Q^T (after stage 2)
 const double* tridiag_result_vectors(const TridiagWs* ws);
 const double* tridiag_result_values(const TridiagWs* ws);
 void tridiag_get_tridiagonal(TridiagWs* ws, double* d, double* e, double* tau, double* vr /* n x n row-major reflectors */);

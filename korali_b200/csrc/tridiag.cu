@@ -71,10 +71,65 @@ __device__ __forceinline__ double col_upd(double c, double v, double wi, double 
   return __dsub_rn(c, __fma_rn(v, wi, __dmul_rn(w, vi)));
 }
 
+// One column of the trailing matrix in the pass of a step: rank-2 update of the previous step, product with the new reflector,
+// optional publication (LL stores) of the updated column. Two rows per lane and access (16-byte shared / global accesses), PU
+// independent accesses in flight per lane; rows [rs, ne) with rs = (i+1) rounded down to even (row i is dead data: it is updated
+// along, its reflector entry is zero) and ne = n rounded up to even (zero pads). The same code and summation order for the
+// shared-memory and the global-memory variant: their results are bitwise equal.
+constexpr int PU = 8;
+template <bool PUB>
+__device__ __forceinline__ double pass_column(double* __restrict__ col, const double* __restrict__ vold, const double* __restrict__ wv,
+                                              const double* __restrict__ vnew, double wc, double vc, int i, int ne, int n, int lane,
+                                              LL* __restrict__ Cout, unsigned long long otag) {
+  double dot[PU];
+#pragma unroll
+  for (int u = 0; u < PU; u++) dot[u] = 0.0;
+  int r = ((i + 1) & ~1) + 2 * lane;
+  for (; r + 64 * (PU - 1) < ne; r += 64 * PU) {
+    double2 a[PU];
+#pragma unroll
+    for (int u = 0; u < PU; u++) a[u] = *reinterpret_cast<const double2*>(col + r + 64 * u);
+#pragma unroll
+    for (int u = 0; u < PU; u++) {
+      const double2 vo = *reinterpret_cast<const double2*>(vold + r + 64 * u);
+      const double2 w2 = *reinterpret_cast<const double2*>(wv + r + 64 * u);
+      const double2 vn = *reinterpret_cast<const double2*>(vnew + r + 64 * u);
+      a[u].x -= vo.x * wc + w2.x * vc;
+      a[u].y -= vo.y * wc + w2.y * vc;
+      *reinterpret_cast<double2*>(col + r + 64 * u) = a[u];
+      dot[u] += a[u].x * vn.x;
+      dot[u] += a[u].y * vn.y;
+      if (PUB) {
+        if (r + 64 * u > i) ll_store(Cout + r + 64 * u, a[u].x, otag);
+        if (r + 64 * u + 1 < n) ll_store(Cout + r + 64 * u + 1, a[u].y, otag);
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < PU; u++) {
+    const int q = r + 64 * u;
+    if (q < ne) {
+      double2 a = *reinterpret_cast<const double2*>(col + q);
+      const double2 vo = *reinterpret_cast<const double2*>(vold + q);
+      const double2 w2 = *reinterpret_cast<const double2*>(wv + q);
+      const double2 vn = *reinterpret_cast<const double2*>(vnew + q);
+      a.x -= vo.x * wc + w2.x * vc;
+      a.y -= vo.y * wc + w2.y * vc;
+      *reinterpret_cast<double2*>(col + q) = a;
+      dot[u] += a.x * vn.x;
+      dot[u] += a.y * vn.y;
+      if (PUB) {
+        if (q > i) ll_store(Cout + q, a.x, otag);
+        if (q + 1 < n) ll_store(Cout + q + 1, a.y, otag);
+      }
+    }
+  }
+  return ((dot[0] + dot[1]) + (dot[2] + dot[3])) + ((dot[4] + dot[5]) + (dot[6] + dot[7]));
+}
+
 // A step of thread t works on the rows r = t (mod SY_NT), r >= i, in every phase, so the received column (cs), the received
 // product (ps) and the reflector entries are thread-private although they live in shared memory: three block-wide barriers per
 // step (the two sums and the one in front of the pass over the columns).
-template <bool RESIDENT>
 __global__ void __launch_bounds__(SY_NT, 1)
 sytrd_kernel(const double* __restrict__ M, double* __restrict__ Awork, int ld, int n, int ns /* smem vector stride */,
              LL* __restrict__ xP, LL* __restrict__ xC, double* __restrict__ dT, double* __restrict__ eT, double* __restrict__ tauv,
@@ -88,14 +143,7 @@ sytrd_kernel(const double* __restrict__ M, double* __restrict__ Awork, int ld, i
   double* cs = sm + 4 * ns;
   double* red = sm + 5 * ns;       // 4 slots x SY_NW doubles
   double* bc = red + 32;           // 2 parities x {c_i, p_i, c_{i+1}, p_{i+1}}
-  double* Acol = red + 48;         // RESIDENT: nloc x ns
   const int nloc = b < n ? (n - b + G - 1) / G : 0;
-  if (RESIDENT) {
-    for (int s = warp; s < nloc; s += SY_NW) {
-      const double* src = M + (size_t)(b + s * G) * ld;   // column c of a symmetric matrix = its row c
-      for (int r = lane; r < n; r += 32) Acol[(size_t)s * ns + r] = src[r];
-    }
-  }
   for (int r = tid; r < ns; r += SY_NT) { vold[r] = 0.0; vnew[r] = 0.0; wv[r] = 0.0; ps[r] = 0.0; }
   if (b == 0) {   // owner of column 0 publishes it for step 0
     const double* src = M;
@@ -112,7 +160,13 @@ sytrd_kernel(const double* __restrict__ M, double* __restrict__ Awork, int ld, i
     const bool pr = prof && b == prof_cta && tid == 0 && i >= prof_step0 && i < prof_step0 + 32;
     if (pr) prof[(i - prof_step0) * 8 + 0] = clock64();
     const int r0 = i + ((tid - i) & (SY_NT - 1));   // first row >= i of this thread
-    // ---- receive column i and p = A v_{i-1}: up to 8 slots polled together, so that their L2 round trips overlap
+    // ---- receive column i and p = A v_{i-1}. One lane per warp spins on ONE slot first (148 CTAs x 256 threads x 8 slots of
+    // back-to-back polling saturate the L2 and delay the very stores they wait for); then up to 8 slots are polled together, so
+    // that their L2 round trips overlap — nearly always a single round.
+    if (have_p) {
+      if (lane == 0 && r0 < n) (void)ll_wait(Pin + r0, tag);
+      __syncwarp();
+    }
     for (int rb = r0; rb < n; rb += 4 * SY_NT) {
       unsigned long long va[8], ta[8];
       unsigned pend = 0;
@@ -173,6 +227,7 @@ sytrd_kernel(const double* __restrict__ M, double* __restrict__ Awork, int ld, i
       scale = 1.0 / (alph - beta);
       ei = beta;
     }
+    if (r0 == i) vnew[i] = 0.0;   // row i rides along in the pass when i+1 is odd (16-byte accesses): it must not enter the product
     for (int r = (r0 > i ? r0 : r0 + SY_NT); r < n; r += SY_NT) vnew[r] = (r == i + 1) ? 1.0 : cs[r] * scale;
     if (b == i % G && tid == 0) { dT[i] = di; eT[i] = ei; tauv[i] = tau; }   // the owner of the retired column records the step
     __syncthreads();
@@ -184,38 +239,10 @@ sytrd_kernel(const double* __restrict__ M, double* __restrict__ Awork, int ld, i
     const int s0 = (i + 1 > b) ? (i + 1 - b + G - 1) / G : 0;
     for (int s = s0 + warp; s < nloc; s += SY_NW) {
       const int c = b + s * G;
-      double* col = RESIDENT ? (Acol + (size_t)s * ns) : (Awork + (size_t)c * ld);
+      double* col = Awork + (size_t)c * ld;
       const double wc = wv[c], vc = vold[c];
-      const bool pub = (c == i + 1);
-      double dot = 0.0;
-      if (RESIDENT) {
-        for (int r = i + 1 + lane; r < n; r += 32) {
-          double a = col[r];
-          a -= vold[r] * wc + wv[r] * vc;
-          col[r] = a;
-          dot += a * vnew[r];
-          if (pub) ll_store(Cout + r, a, otag);
-        }
-      } else {
-        int r = i + 1 + lane;
-        for (; r + 96 < n; r += 128) {   // four loads in flight per lane (the columns stream from L2 / HBM)
-          double a0 = col[r], a1 = col[r + 32], a2 = col[r + 64], a3 = col[r + 96];
-          a0 -= vold[r] * wc + wv[r] * vc;
-          a1 -= vold[r + 32] * wc + wv[r + 32] * vc;
-          a2 -= vold[r + 64] * wc + wv[r + 64] * vc;
-          a3 -= vold[r + 96] * wc + wv[r + 96] * vc;
-          col[r] = a0; col[r + 32] = a1; col[r + 64] = a2; col[r + 96] = a3;
-          dot += a0 * vnew[r]; dot += a1 * vnew[r + 32]; dot += a2 * vnew[r + 64]; dot += a3 * vnew[r + 96];
-          if (pub) { ll_store(Cout + r, a0, otag); ll_store(Cout + r + 32, a1, otag); ll_store(Cout + r + 64, a2, otag); ll_store(Cout + r + 96, a3, otag); }
-        }
-        for (; r < n; r += 32) {
-          double a = col[r];
-          a -= vold[r] * wc + wv[r] * vc;
-          col[r] = a;
-          dot += a * vnew[r];
-          if (pub) ll_store(Cout + r, a, otag);
-        }
-      }
+      double dot = (c == i + 1) ? pass_column<true>(col, vold, wv, vnew, wc, vc, i, ns, n, lane, Cout, otag)
+                                : pass_column<false>(col, vold, wv, vnew, wc, vc, i, ns, n, lane, Cout, otag);
       dot = warp_sum_butterfly(dot);
       if (lane == 0) ll_store(Pout + c, dot, otag);
     }
@@ -231,27 +258,232 @@ sytrd_kernel(const double* __restrict__ M, double* __restrict__ Awork, int ld, i
   }
 }
 
-// ---- compact-WY panel factor (dlarft, forward / columnwise): T upper triangular, nb x nb, from G = V^T V and tau ------------
-__global__ void __launch_bounds__(256)
-larft_kernel(const double* __restrict__ Gbuf, const double* __restrict__ tauv, int n_refl, int nb, double* __restrict__ Tbuf) {
+// ---- register-resident variant (N <= 1536) -----------------------------------------------------------------------------------
+// The 148 register files hold 37 MB: the trailing matrix lives in REGISTERS. Thread t owns the row pairs (2u, 2u+1), u = t + 256 k
+// (k < KU), in every phase: it receives their entries of the column and of p = A v (one 256-bit load per pair of LL slots), keeps
+// their entries of the reflectors and of w, and holds the entries A[r][c] of all NC columns of its CTA for its rows. A pass over
+// the columns is then register arithmetic (the shared-memory variant moved 250 KB per step through the 128 B/clk shared-memory
+// pipe); shared memory only carries what is looked up by COLUMN index (w[c], v[c]) and the per-thread partial products.
+__device__ __forceinline__ void ll_load2(const LL* p, unsigned long long (&q)[4]) {
+  asm volatile("ld.volatile.global.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(q[0]), "=l"(q[1]), "=l"(q[2]), "=l"(q[3]) : "l"(p) : "memory");
+}
+
+template <int KU, int NC>
+__global__ void __launch_bounds__(SY_NT, 1)
+sytrd_reg_kernel(const double* __restrict__ M, int ld, int n, int ns /* n rounded up to even: LL stride per parity, vector stride */,
+                 LL* __restrict__ xP, LL* __restrict__ xC, double* __restrict__ dT, double* __restrict__ eT, double* __restrict__ tauv,
+                 double* __restrict__ VR, long long* __restrict__ prof, int prof_step0, int prof_cta, int opt) {
   extern __shared__ __align__(16) double sm[];
-  double* T = sm;                 // nb x (nb+1): thread q walks row q, stride nb+1 = conflict-free
-  const double* __restrict__ G = Gbuf + (size_t)blockIdx.x * nb * nb;   // G[m][p]: one address per step for all threads (broadcast)
+  const int G = gridDim.x, b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  double* vs_old = sm;             // reflector v_{i-1} by index (lookups v[c], v[i+1])
+  double* vs_new = sm + ns;
+  double* wsm = sm + 2 * ns;       // w_{i-1} by index (lookups w[c])
+  double* red = sm + 3 * ns;       // 4 slots x SY_NW
+  double* bc = red + 32;           // 2 parities x {c_i, p_i, c_{i+1}, p_{i+1}}
+  double* pp = red + 48;           // NC x SY_NT partial products of the pass
+  const int nloc = b < n ? (n - b + G - 1) / G : 0;
+  double A[KU][NC][2], v[2 * KU], w[2 * KU], vnw[2 * KU];
+#pragma unroll
+  for (int k = 0; k < KU; k++) {
+    const int r = 2 * (tid + SY_NT * k);
+#pragma unroll
+    for (int s = 0; s < NC; s++) {
+      const double* src = M + (size_t)(b + s * G) * ld;   // column c of a symmetric matrix = its row c
+      A[k][s][0] = (s < nloc && r < n) ? src[r] : 0.0;
+      A[k][s][1] = (s < nloc && r + 1 < n) ? src[r + 1] : 0.0;
+    }
+    v[2 * k] = v[2 * k + 1] = w[2 * k] = w[2 * k + 1] = vnw[2 * k] = vnw[2 * k + 1] = 0.0;
+  }
+  for (int r = tid; r < ns; r += SY_NT) { vs_old[r] = 0.0; vs_new[r] = 0.0; wsm[r] = 0.0; }
+  if (b == 0)   // owner of column 0 publishes it for step 0
+    for (int r = tid; r < n; r += SY_NT) ll_store(xC + r, M[r], 1ull);
+  __syncthreads();
+  double tau_old = 0.0;
+  for (int i = 0; i < n; i++) {
+    const int par = i & 1;
+    const unsigned long long tag = (unsigned long long)i + 1ull;
+    const LL* Pin = xP + (size_t)par * ns;
+    const LL* Cin = xC + (size_t)par * ns;
+    const bool have_p = i > 0;
+    const bool pr = prof && b == prof_cta && tid == 0 && i >= prof_step0 && i < prof_step0 + 32;
+    if (pr) prof[(i - prof_step0) * 8 + 0] = clock64();
+    // ---- receive column i and p = A v_{i-1} for this thread's rows >= i
+    double cv[2 * KU], pq[2 * KU];
+    unsigned need = 0;
+#pragma unroll
+    for (int j = 0; j < 2 * KU; j++) {
+      const int r = 2 * (tid + SY_NT * (j >> 1)) + (j & 1);
+      if (r >= i && r < n) need |= 1u << j;
+      cv[j] = 0.0; pq[j] = 0.0;
+    }
+    if (have_p && (opt & 1)) {   // one lane per warp spins on one slot first: 148 x 256 threads polling everything back to back saturate the L2
+      if (lane == 0 && need) {
+        const int j0 = __ffs(need) - 1;
+        (void)ll_wait(Pin + 2 * (tid + SY_NT * (j0 >> 1)) + (j0 & 1), tag);
+      }
+      __syncwarp();
+    }
+    {
+      unsigned pc = need, ppn = have_p ? need : 0u;
+      while (pc | ppn) {
+        unsigned long long qc[KU][4], qp[KU][4];
+#pragma unroll
+        for (int k = 0; k < KU; k++) {
+          if ((pc >> (2 * k)) & 3u) ll_load2(Cin + 2 * (tid + SY_NT * k), qc[k]);
+          if ((ppn >> (2 * k)) & 3u) ll_load2(Pin + 2 * (tid + SY_NT * k), qp[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < KU; k++)
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            const unsigned bit = 1u << (2 * k + h);
+            if ((pc & bit) && qc[k][2 * h + 1] == tag) { cv[2 * k + h] = __longlong_as_double((long long)qc[k][2 * h]); pc &= ~bit; }
+            if ((ppn & bit) && qp[k][2 * h + 1] == tag) { pq[2 * k + h] = __longlong_as_double((long long)qp[k][2 * h]); ppn &= ~bit; }
+          }
+        if ((pc | ppn) && (opt & 2)) __nanosleep(100);
+      }
+    }
+    if (pr) prof[(i - prof_step0) * 8 + 1] = clock64();
+    // ---- p.v over the own rows; the four scalars every thread needs
+    double part = 0.0;
+    double* bcp = bc + par * 4;
+#pragma unroll
+    for (int j = 0; j < 2 * KU; j++) {
+      const int r = 2 * (tid + SY_NT * (j >> 1)) + (j & 1);
+      if (need & (1u << j)) part = __fma_rn(pq[j], v[j], part);
+      if (r == i) { bcp[0] = cv[j]; bcp[1] = pq[j]; }
+      if (r == i + 1 && r < n) { bcp[2] = cv[j]; bcp[3] = pq[j]; }
+    }
+    const double pv = block_sum(part, red + (par * 2 + 0) * SY_NW);
+    const double alpha = -0.5 * tau_old * (tau_old * pv);
+    const double vi = vs_old[i];
+    const double wi = w_of(tau_old, bcp[1], alpha, vi);
+    double xpart = 0.0;
+#pragma unroll
+    for (int j = 0; j < 2 * KU; j++) {
+      const int r = 2 * (tid + SY_NT * (j >> 1)) + (j & 1);
+      if (need & (1u << j)) {
+        w[j] = w_of(tau_old, pq[j], alpha, v[j]);
+        wsm[r] = w[j];
+        cv[j] = col_upd(cv[j], v[j], wi, w[j], vi);
+        if (r >= i + 2) xpart = __fma_rn(cv[j], cv[j], xpart);
+      } else {
+        w[j] = 0.0;
+      }
+    }
+    const double di = col_upd(bcp[0], vi, wi, wi, vi);
+    if (i == n - 1) {
+      if (b == 0 && tid == 0) dT[i] = di;
+      break;
+    }
+    const double vi1 = vs_old[i + 1];
+    const double alph = col_upd(bcp[2], vi1, wi, w_of(tau_old, bcp[3], alpha, vi1), vi);
+    const double xn2 = block_sum(xpart, red + (par * 2 + 1) * SY_NW);
+    double tau = 0.0, scale = 0.0, ei = alph;
+    if (xn2 > 0.0) {
+      const double beta = -copysign(sqrt(alph * alph + xn2), alph);
+      tau = (beta - alph) / beta;
+      scale = 1.0 / (alph - beta);
+      ei = beta;
+    }
+#pragma unroll
+    for (int j = 0; j < 2 * KU; j++) {
+      const int r = 2 * (tid + SY_NT * (j >> 1)) + (j & 1);
+      vnw[j] = (r == i + 1) ? 1.0 : ((r >= i + 2 && r < n) ? cv[j] * scale : 0.0);
+      if (r < ns) vs_new[r] = vnw[j];
+    }
+    if (b == i % G && tid == 0) { dT[i] = di; eT[i] = ei; tauv[i] = tau; }   // the owner of the retired column records the step
+    __syncthreads();
+    if (pr) prof[(i - prof_step0) * 8 + 2] = clock64();
+    // ---- pass over this CTA's columns c >= i+1 (registers): rank-2 update of step i-1, partial p = A v_i, publication of column i+1
+    LL* Pout = xP + (size_t)(par ^ 1) * ns;
+    LL* Cout = xC + (size_t)(par ^ 1) * ns;
+    const unsigned long long otag = tag + 1ull;
+    const int s0 = (i + 1 > b) ? (i + 1 - b + G - 1) / G : 0;
+#pragma unroll
+    for (int s = 0; s < NC; s++) {
+      if (s >= s0 && s < nloc) {
+        const int c = b + s * G;
+        const double wc = wsm[c], vc = vs_old[c];
+        double dot = 0.0;
+#pragma unroll
+        for (int k = 0; k < KU; k++) {
+          double a0 = A[k][s][0], a1 = A[k][s][1];
+          a0 -= v[2 * k] * wc + w[2 * k] * vc;
+          a1 -= v[2 * k + 1] * wc + w[2 * k + 1] * vc;
+          A[k][s][0] = a0; A[k][s][1] = a1;
+          dot += a0 * vnw[2 * k];
+          dot += a1 * vnw[2 * k + 1];
+          if (c == i + 1) {
+            const int r = 2 * (tid + SY_NT * k);
+            if (r > i && r < n) ll_store(Cout + r, a0, otag);
+            if (r + 1 > i && r + 1 < n) ll_store(Cout + r + 1, a1, otag);
+          }
+        }
+        pp[s * SY_NT + tid] = dot;
+      }
+    }
+    __syncthreads();
+    for (int s = warp; s < NC; s += SY_NW)   // a warp finishes column s: 256 partials in a fixed order
+      if (s >= s0 && s < nloc) {
+        double x = 0.0;
+#pragma unroll
+        for (int j = 0; j < SY_NW; j++) x += pp[s * SY_NT + lane + 32 * j];
+        x = warp_sum_butterfly(x);
+        if (lane == 0) ll_store(Pout + b + s * G, x, otag);
+      }
+    if (pr) prof[(i - prof_step0) * 8 + 3] = clock64();
+    if (b == i % G) {   // reflector i for the back-transform (entries r <= i and r >= n stay zero from the allocation)
+      double* vr = VR + (size_t)i * ld;
+#pragma unroll
+      for (int j = 0; j < 2 * KU; j++) {
+        const int r = 2 * (tid + SY_NT * (j >> 1)) + (j & 1);
+        if (r > i && r < n) vr[r] = vnw[j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 2 * KU; j++) v[j] = vnw[j];
+    double* t = vs_old; vs_old = vs_new; vs_new = t;
+    tau_old = tau;
+  }
+}
+
+// ---- compact-WY panel factor (dlarft, forward / columnwise): T upper triangular, nb x nb, from G = V^T V and tau ------------
+// Column p: T[0:p, p] = -tau_p T[0:p, 0:p] G[0:p, p]. The columns are sequential; inside a column two threads share a row's
+// inner product (interleaved terms, one shuffle). G arrives as `gsplits` split-K slabs (summed here in a fixed order) and is read
+// by rows (G is symmetric), one row per step, prefetched one step ahead.
+constexpr int LARFT_NT = 256;
+__global__ void __launch_bounds__(LARFT_NT)
+larft_kernel(const double* __restrict__ Gbuf, long long gstride, int gsplits, const double* __restrict__ tauv, int n_refl, int nb,
+             double* __restrict__ Tbuf) {
+  extern __shared__ __align__(16) double sm[];
+  double* T = sm;                 // nb x (nb+1)
+  double* grow = sm + nb * (nb + 1);
+  const double* __restrict__ G = Gbuf + (size_t)blockIdx.x * nb * nb;
   const int panel = blockIdx.x, p0 = panel * nb, kb = min(nb, n_refl - p0), tid = threadIdx.x, lt = nb + 1;
-  for (int i = tid; i < nb * lt; i += blockDim.x) T[i] = 0.0;
+  const int q = tid >> 1, h = tid & 1;
+  auto gload = [&](int row) {
+    double g = 0.0;
+    for (int k = 0; k < gsplits; k++) g += G[(size_t)k * gstride + (size_t)row * nb + tid];
+    return g;
+  };
+  for (int i = tid; i < nb * lt; i += LARFT_NT) T[i] = 0.0;
+  double gn = (tid < nb && kb > 0) ? gload(0) : 0.0;
   __syncthreads();
   for (int p = 0; p < kb; p++) {
+    if (tid < nb) grow[tid] = gn;
+    __syncthreads();
+    if (tid < nb && p + 1 < kb) gn = gload(p + 1);
     const double tp = tauv[p0 + p];
-    // T[q][p] = -tau_p * sum_{m = q .. p-1} T[q][m] G[m][p]   (q < p)
-    for (int q = tid; q < p; q += blockDim.x) {
-      double s = 0.0;
-      for (int m = q; m < p; m++) s += T[q * lt + m] * G[m * nb + p];
-      T[q * lt + p] = -tp * s;
-    }
+    double sacc = 0.0;
+    if (q < p)
+      for (int m = q + h; m < p; m += 2) sacc += T[q * lt + m] * grow[m];
+    sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+    if (h == 0 && q < p) T[q * lt + p] = -tp * sacc;
     if (tid == 0) T[p * lt + p] = tp;
     __syncthreads();
   }
-  for (int i = tid; i < nb * nb; i += blockDim.x) Tbuf[(size_t)panel * nb * nb + i] = T[(i / nb) * lt + (i % nb)];
+  for (int i = tid; i < nb * nb; i += LARFT_NT) Tbuf[(size_t)panel * nb * nb + i] = T[(i / nb) * lt + (i % nb)];
 }
 
 // sign[i] = -1 if the component of largest magnitude of row i (first on ties) is negative — the convention of rayleigh_kernel
@@ -303,18 +535,26 @@ TridiagWs* tridiag_ws_create(int n, int ld, int num_sms, char* err, size_t errle
   if (grid < 1) grid = 1;
   const int nloc_max = (n + grid - 1) / grid;
   const size_t vec_bytes = sizeof(double) * (5 * (size_t)ns + 48);
-  const size_t res_bytes = vec_bytes + sizeof(double) * (size_t)nloc_max * ns;
   if (vec_bytes > kSmemCap) return fail("N too large for the shared-memory vectors of sytrd_kernel");
+  // register-resident instantiations <KU, NC>: row pairs per thread x columns per CTA
   const char* force = getenv("KCMA_SYTRD_RESIDENT");
-  ws->resident = res_bytes <= kSmemCap && !(force && atoi(force) == 0);
+  const int units = ns / 2;
+  ws->reg_variant = 0;
+  if (!(force && atoi(force) == 0)) {
+    if (units <= SY_NT && nloc_max <= 4) ws->reg_variant = 1;
+    else if (units <= 2 * SY_NT && nloc_max <= 7) ws->reg_variant = 2;
+    else if (units <= 3 * SY_NT && nloc_max <= 11) ws->reg_variant = 3;
+  }
+  ws->resident = ws->reg_variant != 0;
   ws->sy_grid = grid;
-  ws->sy_smem = ws->resident ? res_bytes : vec_bytes;
+  static const int kNC[4] = {0, 4, 7, 11};
+  ws->sy_smem = ws->resident ? sizeof(double) * (3 * (size_t)ns + 48 + (size_t)kNC[ws->reg_variant] * SY_NT) : vec_bytes;
   bool ok = true;
   if (!ws->resident) ok = ok && ws_alloc(ws, &ws->Awork, mat);
   ok = ok && ws_alloc(ws, &ws->dT, n) && ws_alloc(ws, &ws->eT, n) && ws_alloc(ws, &ws->tau, n) && ws_alloc(ws, &ws->VR, mat) &&
        ws_alloc(ws, &ws->VC, mat);
   LL* xb = nullptr;
-  ok = ok && ws_alloc(ws, &xb, 4 * (size_t)n);
+  ok = ok && ws_alloc(ws, &xb, 4 * (size_t)ns);
   ws->xbuf = xb;
   if (const char* pe = getenv("KCMA_SYTRD_PROF")) {   // "step0[,cta]": clock64 stamps of 32 steps of one CTA (tridiag_dump_prof)
     ws->prof_step0 = atoi(pe);
@@ -375,10 +615,19 @@ TridiagWs* tridiag_ws_create(int n, int ld, int num_sms, char* err, size_t errle
   const int row_tiles = (n + 127) / 128;
   ws->split1 = std::max(1, std::min(16, (num_sms + row_tiles - 1) / row_tiles));
   if (ws->npanels > 0) {
-    ok = ok && ws_alloc(ws, &ws->Gbuf, (size_t)ws->npanels * ws->nb * ws->nb) && ws_alloc(ws, &ws->Tbuf, (size_t)ws->npanels * ws->nb * ws->nb) &&
+    ws->gsplits = std::max(1, std::min(8, num_sms / std::max(1, ws->npanels)));
+    ok = ok && ws_alloc(ws, &ws->Gbuf, (size_t)ws->gsplits * ws->npanels * ws->nb * ws->nb) && ws_alloc(ws, &ws->Tbuf, (size_t)ws->npanels * ws->nb * ws->nb) &&
          ws_alloc(ws, &ws->VtilR, mat) && ws_alloc(ws, &ws->W2, (size_t)n * ws->nbld) &&
-         ws_alloc(ws, &ws->slabs, (size_t)ws->split1 * n * ws->nbld);
+         ws_alloc(ws, &ws->slabs, (size_t)ws->split1 * n * ws->nbld) && ws_alloc(ws, &ws->QT, mat) && ws_alloc(ws, &ws->QF, mat) &&
+         ws_alloc(ws, &ws->XF, mat);
+    const int tiles = row_tiles * row_tiles;
+    ws->splitF = std::max(1, std::min(8, num_sms / std::max(1, tiles)));
+    if (ws->splitF > 1) ok = ok && ws_alloc(ws, &ws->slabsF, (size_t)ws->splitF * mat);
     if (!ok) return fail("out of device memory");
+    if (cudaStreamCreateWithFlags(&ws->st2, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ws->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ws->ev_join, cudaEventDisableTiming) != cudaSuccess)
+      return fail("could not create the side stream of the back-transform");
   }
   // ---- static GEMM descriptors
   std::vector<GemmDesc> descs;
@@ -409,7 +658,8 @@ TridiagWs* tridiag_ws_create(int n, int ld, int num_sms, char* err, size_t errle
     const int p0 = p * nb, kb = std::min(nb, n_refl - p0);
     GemmDesc g; memset(&g, 0, sizeof(g));
     g.A = ws->VR + (size_t)p0 * ld + p0; g.B = g.A; g.C = ws->Gbuf + (size_t)p * nb * nb;
-    g.M = kb; g.Nc = kb; g.K = n - p0; g.lda = g.ldb = ld; g.ldc = nb; g.alpha = 1.0; g.splits = 1;
+    g.M = kb; g.Nc = kb; g.K = n - p0; g.lda = g.ldb = ld; g.ldc = nb; g.alpha = 1.0; g.splits = ws->gsplits;
+    g.split_stride = (long long)ws->npanels * nb * nb;
     descs.push_back(g);
   }
   ws->desc_vtil = (int)descs.size();
@@ -421,28 +671,37 @@ TridiagWs* tridiag_ws_create(int n, int ld, int num_sms, char* err, size_t errle
     descs.push_back(g);
   }
   ws->desc_gemm1 = (int)descs.size();
-  for (int p = 0; p < ws->npanels; p++) {      // slabs: W[r][q] = sum_c X^T[r][c] VtilR_p[q][c], c >= p0
+  // Q^T = H_{n-2} ... H_0 is accumulated from the identity, last panel first; before panel p is applied Q^T differs from the
+  // identity only in rows / columns > p0 + nb, and V_p has no rows <= p0: only the block [p0, n) x [p0, n) takes part.
+  for (int p = 0; p < ws->npanels; p++) {      // slabs: W[r][q] = sum_c Q^T[r][c] VtilR_p[q][c], r, c >= p0
     const int p0 = p * nb, kb = std::min(nb, n_refl - p0);
     GemmDesc g; memset(&g, 0, sizeof(g));
-    g.A = ws->XT + p0; g.B = ws->VtilR + (size_t)p0 * ld + p0; g.C = ws->slabs;
-    g.M = n; g.Nc = kb; g.K = n - p0; g.lda = ld; g.ldb = ld; g.ldc = ws->nbld; g.alpha = 1.0; g.splits = ws->split1;
+    g.A = ws->QT + (size_t)p0 * ld + p0; g.B = ws->VtilR + (size_t)p0 * ld + p0; g.C = ws->slabs;
+    g.M = n - p0; g.Nc = kb; g.K = n - p0; g.lda = ld; g.ldb = ld; g.ldc = ws->nbld; g.alpha = 1.0; g.splits = ws->split1;
     g.split_stride = (long long)n * ws->nbld;
     descs.push_back(g);
   }
   ws->desc_gemm2 = (int)descs.size();
-  for (int p = 0; p < ws->npanels; p++) {      // X^T[r][c] -= sum_q W[r][q] V[c][p0 + q], c >= p0
+  for (int p = 0; p < ws->npanels; p++) {      // Q^T[r][c] -= sum_q W[r][q] V[c][p0 + q], r, c >= p0
     const int p0 = p * nb, kb = std::min(nb, n_refl - p0);
     GemmDesc g; memset(&g, 0, sizeof(g));
-    g.A = ws->W2; g.B = ws->VC + (size_t)p0 * ld + p0; g.C = ws->XT + p0;
-    g.M = n; g.Nc = n - p0; g.K = kb; g.lda = ws->nbld; g.ldb = ld; g.ldc = ld; g.alpha = -1.0; g.beta = 1.0; g.splits = 1;
+    g.A = ws->W2; g.B = ws->VC + (size_t)p0 * ld + p0; g.C = ws->QT + (size_t)p0 * ld + p0;
+    g.M = n - p0; g.Nc = n - p0; g.K = kb; g.lda = ws->nbld; g.ldb = ld; g.ldc = ld; g.alpha = -1.0; g.beta = 1.0; g.splits = 1;
+    descs.push_back(g);
+  }
+  ws->desc_final = (int)descs.size();
+  if (ws->npanels > 0) {                       // X^T[r][c] = sum_k Z^T[r][k] Q[c][k]   (Z^T = the last merge's output in XT, Q = (Q^T)^T in QF)
+    GemmDesc g; memset(&g, 0, sizeof(g));
+    g.A = ws->XT; g.B = ws->QF; g.C = ws->splitF > 1 ? ws->slabsF : ws->XF;
+    g.M = n; g.Nc = n; g.K = n; g.lda = g.ldb = g.ldc = ld; g.alpha = 1.0; g.splits = ws->splitF; g.split_stride = (long long)mat;
     descs.push_back(g);
   }
   if (!ws_alloc(ws, &ws->d_desc, descs.size() ? descs.size() : 1)) return fail("out of device memory");
   if (!descs.empty()) cudaMemcpy(ws->d_desc, descs.data(), sizeof(GemmDesc) * descs.size(), cudaMemcpyHostToDevice);
   // kernel attributes
-  cudaError_t e1 = cudaFuncSetAttribute(sytrd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCap);
-  cudaError_t e2 = cudaFuncSetAttribute(sytrd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCap);
-  cudaError_t e3 = cudaFuncSetAttribute(larft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 128 * 129));
+  cudaError_t e1 = cudaFuncSetAttribute(sytrd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCap);
+  cudaError_t e2 = cudaFuncSetAttribute(sytrd_reg_kernel<3, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  cudaError_t e3 = cudaFuncSetAttribute(larft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (128 * 129 + 128)));
   if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) return fail("cudaFuncSetAttribute failed");
   if (cudaDeviceSynchronize() != cudaSuccess) return fail("CUDA error while building the workspace");
   return ws;
@@ -450,6 +709,9 @@ TridiagWs* tridiag_ws_create(int n, int ld, int num_sms, char* err, size_t errle
 
 void tridiag_ws_destroy(TridiagWs* ws) {
   if (!ws) return;
+  if (ws->st2) { cudaStreamSynchronize(ws->st2); cudaStreamDestroy(ws->st2); }
+  if (ws->ev_fork) cudaEventDestroy(ws->ev_fork);
+  if (ws->ev_join) cudaEventDestroy(ws->ev_join);
   for (void* p : ws->allocs) cudaFree(p);
   delete ws;
 }
@@ -457,51 +719,85 @@ void tridiag_ws_destroy(TridiagWs* ws) {
 bool tridiag_stage_sytrd(cudaStream_t st, TridiagWs* ws, const double* M) {
   int n = ws->n, ld = ws->ld, ns = (n + 1) & ~1;
   LL* xP = (LL*)ws->xbuf;
-  LL* xC = xP + 2 * (size_t)n;
-  cudaMemsetAsync(ws->xbuf, 0, sizeof(LL) * 4 * (size_t)n, st);
+  LL* xC = xP + 2 * (size_t)(ws->resident ? ns : n);   // per-parity stride: ns (32-byte aligned slot pairs) in the register variant
+  cudaMemsetAsync(ws->xbuf, 0, sizeof(LL) * 4 * (size_t)ns, st);
   double* Awork = ws->Awork;
   if (!ws->resident) cudaMemcpyAsync(Awork, M, sizeof(double) * (size_t)n * ld, cudaMemcpyDeviceToDevice, st);
   double *dT = ws->dT, *eT = ws->eT, *tau = ws->tau, *VR = ws->VR;
   long long* prof = ws->prof;
   int prof_step0 = ws->prof_step0, prof_cta = ws->prof_cta;
   void* args[] = {&M, &Awork, &ld, &n, &ns, &xP, &xC, &dT, &eT, &tau, &VR, &prof, &prof_step0, &prof_cta};
-  const void* fn = ws->resident ? (const void*)sytrd_kernel<true> : (const void*)sytrd_kernel<false>;
-  if (cudaLaunchCooperativeKernel(fn, dim3(ws->sy_grid), dim3(SY_NT), args, ws->sy_smem, st) != cudaSuccess) return false;
+  int opt = 1;
+  if (const char* oe = getenv("KCMA_SYTRD_OPT")) opt = atoi(oe);
+  void* rargs[] = {&M, &ld, &n, &ns, &xP, &xC, &dT, &eT, &tau, &VR, &prof, &prof_step0, &prof_cta, &opt};
+  const void* fn = ws->reg_variant == 1 ? (const void*)sytrd_reg_kernel<1, 4> : ws->reg_variant == 2 ? (const void*)sytrd_reg_kernel<2, 7>
+                   : ws->reg_variant == 3 ? (const void*)sytrd_reg_kernel<3, 11> : (const void*)sytrd_kernel;
+  if (cudaLaunchCooperativeKernel(fn, dim3(ws->sy_grid), dim3(SY_NT), ws->resident ? rargs : args, ws->sy_smem, st) != cudaSuccess) return false;
   // row n-1 of VR (no reflector) and tau[n-1] stay zero from the allocation; VC = VR^T
   launch_transpose(st, ws->VR, ws->VC, ld, n);
   return cudaGetLastError() == cudaSuccess;
 }
 
-bool tridiag_stage_dc(cudaStream_t st, TridiagWs* ws, int* launches) { return dc_solve(st, ws, launches); }
+bool tridiag_stage_dc(cudaStream_t st, TridiagWs* ws, int* launches) {
+  const bool ok = dc_solve(st, ws, launches);
+  ws->result = ws->XT;
+  return ok;
+}
 
-bool tridiag_stage_back(cudaStream_t st, TridiagWs* ws, int* launches) {
-  const int n = ws->n, nb = ws->nb, n_refl = n - 1;
+// Stage 3 runs in two parts. fork: Q^T = H_{n-2} ... H_0 from the reflectors alone (panel factors, then two GEMMs per panel),
+// on the workspace's side stream — it does not depend on the tridiagonal eigenvectors, so it runs NEXT TO the divide & conquer
+// stage, whose kernels leave most SMs idle. join: X^T = Z^T Q^T, one GEMM on the caller's stream.
+bool tridiag_stage_back_fork(cudaStream_t st, TridiagWs* ws, int* launches) {
+  const int n = ws->n, nb = ws->nb, n_refl = n - 1, ld = ws->ld;
   if (ws->npanels == 0) return true;
-  launch_gemm_batched(st, ws->d_desc + ws->desc_g, ws->npanels, nb, nb, 1);
-  larft_kernel<<<ws->npanels, 256, sizeof(double) * nb * (nb + 1), st>>>(ws->Gbuf, ws->tau, n_refl, nb, ws->Tbuf);
-  launch_gemm_batched(st, ws->d_desc + ws->desc_vtil, ws->npanels, nb, n, 1);
-  *launches += 3;
+  cudaStream_t s2 = ws->st2;
+  cudaEventRecord(ws->ev_fork, st);
+  cudaStreamWaitEvent(s2, ws->ev_fork, 0);
+  launch_set_identity(s2, ws->QT, ld, n);
+  launch_gemm_batched(s2, ws->d_desc + ws->desc_g, ws->npanels, nb, nb, ws->gsplits);
+  larft_kernel<<<ws->npanels, LARFT_NT, sizeof(double) * (nb * (nb + 1) + nb), s2>>>(ws->Gbuf, (long long)ws->npanels * nb * nb, ws->gsplits,
+                                                                                   ws->tau, n_refl, nb, ws->Tbuf);
+  launch_gemm_batched(s2, ws->d_desc + ws->desc_vtil, ws->npanels, nb, n, 1);
+  *launches += 4;
   for (int p = ws->npanels - 1; p >= 0; p--) {
     const int p0 = p * nb, kb = std::min(nb, n_refl - p0);
-    launch_gemm_batched(st, ws->d_desc + ws->desc_gemm1 + p, 1, n, kb, ws->split1);
-    launch_reduce_slabs(st, ws->slabs, (long long)n * ws->nbld, ws->split1, n, kb, ws->nbld, ws->W2, ws->num_sms);
-    launch_gemm_batched(st, ws->d_desc + ws->desc_gemm2 + p, 1, n, n - p0, 1);
+    launch_gemm_batched(s2, ws->d_desc + ws->desc_gemm1 + p, 1, n - p0, kb, ws->split1);
+    launch_reduce_slabs(s2, ws->slabs, (long long)n * ws->nbld, ws->split1, n - p0, kb, ws->nbld, ws->W2, ws->num_sms);
+    launch_gemm_batched(s2, ws->d_desc + ws->desc_gemm2 + p, 1, n - p0, n - p0, 1);
     *launches += 3;
   }
+  launch_transpose(s2, ws->QT, ws->QF, ld, n);
+  *launches += 1;
+  cudaEventRecord(ws->ev_join, s2);
+  return cudaGetLastError() == cudaSuccess;
+}
+
+bool tridiag_stage_back_join(cudaStream_t st, TridiagWs* ws, int* launches) {
+  const int n = ws->n;
+  if (ws->npanels == 0) return true;
+  cudaStreamWaitEvent(st, ws->ev_join, 0);
+  launch_gemm_batched(st, ws->d_desc + ws->desc_final, 1, n, n, ws->splitF);
+  *launches += 1;
+  if (ws->splitF > 1) {
+    launch_reduce_slabs(st, ws->slabsF, (long long)n * ws->ld, ws->splitF, n, n, ws->ld, ws->XF, ws->num_sms);
+    *launches += 1;
+  }
+  ws->result = ws->XF;
   return cudaGetLastError() == cudaSuccess;
 }
 
 bool launch_eigen_tridiag(cudaStream_t st, TridiagWs* ws, const double* M, double** VT_out, double** ev_out, int* launches) {
   if (!tridiag_stage_sytrd(st, ws, M)) return false;
   *launches += 4;
-  if (!dc_solve(st, ws, launches)) return false;
-  if (!tridiag_stage_back(st, ws, launches)) return false;
-  *VT_out = ws->XT;
+  if (!tridiag_stage_back_fork(st, ws, launches)) return false;
+  if (!tridiag_stage_dc(st, ws, launches)) return false;
+  if (!tridiag_stage_back_join(st, ws, launches)) return false;
+  *VT_out = ws->result;
   *ev_out = ws->ev_final;
   return true;
 }
 
-const double* tridiag_result_vectors(const TridiagWs* ws) { return ws->XT; }
+const double* tridiag_result_vectors(const TridiagWs* ws) { return ws->result; }
 const double* tridiag_result_values(const TridiagWs* ws) { return ws->ev_final; }
 
 void tridiag_get_tridiagonal(TridiagWs* ws, double* d, double* e, double* tau, double* vr) {
@@ -517,7 +813,7 @@ void tridiag_dump_prof(TridiagWs* ws) {
   long long h[32 * 8];
   cudaMemcpy(h, ws->prof, sizeof(h), cudaMemcpyDeviceToHost);
   fprintf(stderr, "sytrd_kernel phase stamps (clock64 cycles), CTA %d, n = %d, grid %d, %s:\n  step   receive   vectors      pass   to-next-step\n",
-          ws->prof_cta, ws->n, ws->sy_grid, ws->resident ? "shared-memory resident" : "global working copy");
+          ws->prof_cta, ws->n, ws->sy_grid, ws->resident ? "register resident" : "global working copy");
   for (int k = 0; k < 32; k++) {
     const long long* r = h + k * 8;
     if (!r[0] || !r[3]) continue;

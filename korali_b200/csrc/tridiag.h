@@ -11,7 +11,8 @@ struct DcNode { int off, n1, n; };   // a merge: rows/columns [off, off + n), ch
 struct TridiagWs {
   int n = 0, ld = 0, num_sms = 148;
   // ---- stage 1: Householder tridiagonalisation (sytrd_kernel)
-  bool resident = false;       // this CTA's columns live in shared memory (N <= ~1600), else in the global working copy
+  bool resident = false;       // this CTA's columns live in REGISTERS (N <= 1536: sytrd_reg_kernel), else in the global working copy
+  int reg_variant = 0;         // 1, 2, 3 = sytrd_reg_kernel<1,4>, <2,7>, <3,11>
   int sy_grid = 0; size_t sy_smem = 0;
   double* Awork = nullptr;     // n x ld working copy (global variant only)
   double *dT = nullptr, *eT = nullptr, *tau = nullptr;   // diagonal, off-diagonal, reflector scalars
@@ -37,10 +38,16 @@ struct TridiagWs {
   double* XT = nullptr;                    // result: rows = eigenvectors (n x ld)
   double* ev_final = nullptr;              // points at dA or dB
   // ---- stage 3: compact-WY back-transform
-  int nb = 128, npanels = 0, split1 = 1, nbld = 128;
+  int nb = 128, npanels = 0, split1 = 1, nbld = 128, gsplits = 1;
   double *Gbuf = nullptr, *Tbuf = nullptr;   // npanels x nb x nb
   double *VtilR = nullptr;                   // rows p = (T V^T)[p][:] per panel, n x ld
   double *W2 = nullptr, *slabs = nullptr;    // n x nbld, split1 x n x nbld
+  double *QT = nullptr, *QF = nullptr;       // Q^T = H_{n-2} ... H_0 accumulated from the identity (side stream), and its transpose Q
+  double *XF = nullptr, *slabsF = nullptr;   // X^T = Z^T Q^T (final result), split-K slabs of that product
+  int splitF = 1, desc_final = 0;
+  cudaStream_t st2 = nullptr;                // side stream: the Q accumulation runs next to the divide & conquer stage
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  double* result = nullptr;                  // rows = eigenvectors of the last stage run (XT after stage 2, XF after stage 3)
   // ---- descriptors (static: built once on the host)
   GemmDesc* d_desc = nullptr;
   std::vector<int> desc_level_begin;         // per merge level

@@ -22,6 +22,10 @@
 #include <cstdio>
 #include <stdexcept>
 #include <string>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include "../../include/kcma.h"
@@ -187,10 +191,60 @@ enum Verbosity { SILENT = 0, MINIMAL = 1, NORMAL = 2, DETAILED = 3 };
 
 class Experiment;
 
+// One persistent host thread per additional device: with k["Conduit"]["Devices"] = G the population is sharded over G handles
+// of this process, and the G calls of a generation must be in flight together (they meet in the NCCL collectives).
+class RankPool {
+ public:
+  explicit RankPool(int n) : n_(n), rc_(n, 0) {
+    for (int r = 1; r < n; r++) th_.emplace_back([this, r] { loop(r); });
+  }
+  ~RankPool() {
+    { std::lock_guard<std::mutex> lk(m_); stop_ = true; epoch_++; }
+    cv_.notify_all();
+    for (auto& t : th_) t.join();
+  }
+  // fn(r) for every rank r (rank 0 on the caller's thread); returns the first failing rank + 1, or 0
+  int run(const std::function<int(int)>& fn) {
+    { std::lock_guard<std::mutex> lk(m_); fn_ = &fn; pending_ = n_ - 1; epoch_++; }
+    cv_.notify_all();
+    rc_[0] = fn(0);
+    { std::unique_lock<std::mutex> lk(m_); done_.wait(lk, [&] { return pending_ == 0; }); }
+    for (int r = 0; r < n_; r++) if (rc_[r]) return r + 1;
+    return 0;
+  }
+ private:
+  void loop(int r) {
+    uint64_t seen = 0;
+    for (;;) {
+      std::unique_lock<std::mutex> lk(m_);
+      cv_.wait(lk, [&] { return epoch_ != seen; });
+      seen = epoch_;
+      if (stop_) return;
+      const std::function<int(int)>* f = fn_;
+      lk.unlock();
+      const int rc = (*f)(r);
+      lk.lock();
+      rc_[r] = rc;
+      if (--pending_ == 0) done_.notify_one();
+    }
+  }
+  int n_;
+  std::vector<int> rc_;
+  std::vector<std::thread> th_;
+  std::mutex m_;
+  std::condition_variable cv_, done_;
+  const std::function<int(int)>* fn_ = nullptr;
+  uint64_t epoch_ = 0;
+  int pending_ = 0;
+  bool stop_ = false;
+};
+
 // ---- the solver plug-in: Optimizer/CMAES on libkcma ----------------------------------------------------------
 class CMAES {
  public:
-  kcma_t* h = nullptr;
+  kcma_t* h = nullptr;                  // rank 0 (the replicated state is read from it)
+  std::vector<kcma_t*> hs;              // all ranks, one per device
+  std::unique_ptr<RankPool> pool;
   kcma_cfg cfg;
   std::string mu_type = "Logarithmic";
   std::vector<double> lower, upper, init_val, init_sd, min_sd, gran;
@@ -204,7 +258,13 @@ class CMAES {
   std::string pending_error;
   int devices = 1;
 
-  ~CMAES() { if (h) kcma_destroy(h); }
+  ~CMAES() {
+    pool.reset();
+    for (kcma_t* x : hs) if (x) kcma_destroy(x);
+  }
+  void each(const std::function<int(kcma_t*)>& fn) {
+    for (kcma_t* x : hs) if (fn(x)) korali_error("%s", kcma_last_error(x));
+  }
 
   void check(int rc) {
     if (rc) korali_error("%s", kcma_last_error(h));
@@ -429,21 +489,36 @@ class CMAES {
     }
   }
 
-  void initialize(int device) {
-    cfg.device = device;
-    if (kcma_create(&cfg, &h)) korali_error("%s", kcma_last_error(nullptr));
+  void initialize(const std::vector<int>& device_ids) {
+    const int G = (int)device_ids.size();
+    if (G > 1 && (cfg.objective == KCMA_OBJ_EXTERNAL || !constraints.empty()))
+      korali_error("k['Conduit']['Devices'] > 1 shards the population over several GPUs of this process: it needs a device objective "
+                   "(e['Problem']['Objective Function'] = 'Ellipsoid' ...) and no constraints; Python models run on one device\n");
+    for (int r = 0; r < G; r++) {
+      cfg.device = device_ids[r]; cfg.rank = r; cfg.nranks = G;
+      kcma_t* x = nullptr;
+      if (kcma_create(&cfg, &x)) korali_error("%s", kcma_last_error(nullptr));
+      hs.push_back(x);
+    }
+    h = hs[0];
+    if (G > 1) {
+      if (kcma_comm_init_all(hs.data(), G)) korali_error("%s", kcma_last_error(h));
+      pool = std::make_unique<RankPool>(G);
+    }
     if (cfg.objective == KCMA_OBJ_EXTERNAL) {
       if (cfg.use_gradient_information) check(kcma_set_host_objective_grad(h, &CMAES::host_objective_grad, this));
       else check(kcma_set_host_objective(h, &CMAES::host_objective, this));
     }
     if (!constraints.empty()) check(kcma_set_host_constraints(h, &CMAES::host_constraints, this));
-    check(kcma_set_scalar(h, "Termination Criteria/Max Condition Covariance Matrix", tc_max_condition));
-    check(kcma_set_scalar(h, "Termination Criteria/Min Standard Deviation", tc_min_sd));
-    check(kcma_set_scalar(h, "Termination Criteria/Max Standard Deviation", tc_max_sd));
-    check(kcma_set_scalar(h, "Termination Criteria/Max Value", tc_max_value));
-    check(kcma_set_scalar(h, "Termination Criteria/Min Value Difference Threshold", tc_min_value_diff));
-    check(kcma_set_scalar(h, "Termination Criteria/Max Model Evaluations", tc_max_model_evaluations));
-    check(kcma_set_scalar(h, "Termination Criteria/Max Generations", tc_max_generations));
+    each([&](kcma_t* x) {
+      return kcma_set_scalar(x, "Termination Criteria/Max Condition Covariance Matrix", tc_max_condition) ||
+             kcma_set_scalar(x, "Termination Criteria/Min Standard Deviation", tc_min_sd) ||
+             kcma_set_scalar(x, "Termination Criteria/Max Standard Deviation", tc_max_sd) ||
+             kcma_set_scalar(x, "Termination Criteria/Max Value", tc_max_value) ||
+             kcma_set_scalar(x, "Termination Criteria/Min Value Difference Threshold", tc_min_value_diff) ||
+             kcma_set_scalar(x, "Termination Criteria/Max Model Evaluations", tc_max_model_evaluations) ||
+             kcma_set_scalar(x, "Termination Criteria/Max Generations", tc_max_generations);
+    });
   }
 
   // restore "Internal Settings" of a loaded state (CMAES.cpp:1042-1560): resume continues from the saved generation
@@ -452,22 +527,37 @@ class CMAES {
     auto arr = [&](const char* k) {
       if (!saved_internal.contains(k)) return;
       std::vector<double> v = py::cast<std::vector<double>>(saved_internal[k]);
-      check(kcma_set_array(h, k, v.data(), v.size()));
+      each([&](kcma_t* x) { return kcma_set_array(x, k, v.data(), v.size()); });
     };
     auto sca = [&](const char* k) {
       if (!saved_internal.contains(k)) return;
-      check(kcma_set_scalar(h, k, saved_internal[k].cast<double>()));
+      const double v = saved_internal[k].cast<double>();
+      each([&](kcma_t* x) { return kcma_set_scalar(x, k, v); });
     };
+    // the regime first: it fixes the population size / mu the arrays below are sized by, and re-derives the weights
+    if (!constraints.empty()) sca("Is Viability Regime");
     for (const char* k : {"Covariance Matrix", "Current Mean", "Previous Mean", "Evolution Path", "Conjugate Evolution Path",
                           "Best Ever Variables", "Current Best Variables", "Axis Lengths", "Covariance Eigenvector Matrix", "Mean Update"})
       arr(k);
+    if (saved_internal.contains("Mu Weights") && mu_type == "Proportional") arr("Mu Weights");   // data-dependent weights (:584-600)
+    if (!constraints.empty()) {
+      for (const char* k : {"Viability Boundaries", "Best Constraint Evaluations"}) arr(k);
+      if (saved_internal.contains("Normal Constraint Approximation")) {   // saved as a C x N array of arrays
+        std::vector<double> flat;
+        for (auto row : saved_internal["Normal Constraint Approximation"]) for (auto x : row) flat.push_back(x.cast<double>());
+        if (!flat.empty()) each([&](kcma_t* x) { return kcma_set_array(x, "Normal Constraint Approximation", flat.data(), flat.size()); });
+      }
+      for (const char* k : {"Global Success Rate", "Resampled Parameter Count", "Covariance Matrix Adaptation Count",
+                            "Max Constraint Violation Count", "Constraint Evaluation Count", "Best Valid Sample"})
+        sca(k);
+    }
     for (const char* k : {"Sigma", "Best Ever Value", "Current Best Value", "Previous Best Value", "Previous Best Ever Value",
                           "Conjugate Evolution Path L2 Norm", "Infeasible Sample Count", "Model Evaluation Count",
                           "Maximum Covariance Eigenvalue", "Minimum Covariance Eigenvalue", "Current Min Standard Deviation",
                           "Current Max Standard Deviation", "Maximum Diagonal Covariance Matrix Element",
                           "Minimum Diagonal Covariance Matrix Element"})
       sca(k);
-    check(kcma_set_scalar(h, "Current Generation", (double)generation));
+    each([&](kcma_t* x) { return kcma_set_scalar(x, "Current Generation", (double)generation); });
   }
 
   bool checkTermination() {
@@ -487,6 +577,11 @@ class CMAES {
 
   void runGeneration() {
     pending_error.clear();
+    if (pool) {   // one call per device, in flight together
+      const int failed = pool->run([this](int r) { return kcma_run_generation(hs[r]); });
+      if (failed) korali_error("%s", kcma_last_error(hs[failed - 1]));
+      return;
+    }
     const int rc = kcma_run_generation(h);
     if (!pending_error.empty()) { std::string e = pending_error; pending_error.clear(); throw std::runtime_error(e); }
     check(rc);
@@ -565,6 +660,10 @@ class CMAES {
     if (!constraints.empty()) {
       js["Viability Boundaries"] = array("Viability Boundaries");
       js["Best Constraint Evaluations"] = array("Best Constraint Evaluations");
+      std::vector<double> flat = array("Normal Constraint Approximation");
+      py::list rows;
+      for (size_t c = 0; c * n < flat.size(); c++) rows.append(std::vector<double>(flat.begin() + c * n, flat.begin() + (c + 1) * n));
+      js["Normal Constraint Approximation"] = rows;
     }
   }
 };
@@ -609,7 +708,7 @@ class Experiment : public KoraliJson {
   }
 
   // Experiment::initialize (experiment.cpp.base:165-206): defaults, seed, setConfiguration (strict), solver creation
-  void initialize(int device) {
+  void initialize(const std::vector<int>& devices) {
     reset();
     py::dict js;
     for (auto kv : _js) js[kv.first] = kv.second;   // shallow copy: consumed keys are erased from the copy
@@ -659,7 +758,7 @@ class Experiment : public KoraliJson {
     top.finish();
     solver = std::make_unique<CMAES>();
     solver->setConfiguration(solver_js, variables, problem_js, random_seed);   // Normal Generator gets seed S (distribution.cpp.base:36-37)
-    solver->initialize(device);
+    solver->initialize(devices);
     solver->restore(current_generation);
     is_finished = false;
   }
@@ -763,27 +862,37 @@ class Experiment : public KoraliJson {
 // ---- Engine -------------------------------------------------------------------------------------------------------
 class Engine : public KoraliJson {
  public:
-  int device() {
-    int dev = 0;
+  // k["Conduit"]: "Type" (Sequential / Concurrent / Distributed dispatch one JSON sample at a time in the reference,
+  // conduit.cpp.base:29-88; here they all map onto the batched device conduit "Device", which evaluates the whole population in
+  // one launch), "Device" (ordinal of the single GPU) or "Devices" (G, or a list of ordinals: the population is sharded over G
+  // GPUs of this process — the reference selects its Distributed conduit the same way, purely from k["Conduit"]).
+  std::vector<int> devices() {
+    std::vector<int> dev{0};
     if (_js.contains("Conduit") && py::isinstance<py::dict>(_js["Conduit"])) {
       py::dict c = py::reinterpret_borrow<py::dict>(_js["Conduit"]);
       if (c.contains("Type")) {
         const std::string t = canon(c["Type"].cast<std::string>());
-        // Sequential / Concurrent / Distributed dispatch one JSON sample at a time (conduit.cpp.base:29-88); here they all
-        // map onto the batched device conduit ("Device"), which evaluates the whole population in one launch.
         if (t != "device" && t != "sequential" && t != "concurrent" && t != "distributed") korali_error("Unknown Conduit Type '%s'\n", t.c_str());
       }
-      if (c.contains("Device")) dev = c["Device"].cast<int>();
+      if (c.contains("Device")) dev[0] = c["Device"].cast<int>();
+      if (c.contains("Devices")) {
+        py::object d = c["Devices"];
+        dev.clear();
+        if (py::isinstance<py::list>(d) || py::isinstance<py::tuple>(d)) for (auto x : d) dev.push_back(x.cast<int>());
+        else if (is_number(d)) for (int r = 0; r < d.cast<int>(); r++) dev.push_back(r);
+        else korali_error(" + Object: [ Engine ] \n + Key:    ['Conduit']['Devices']\n + Reason: a device count or a list of device ordinals was expected\n");
+        if (dev.empty()) korali_error("k['Conduit']['Devices'] names no device\n");
+      }
     }
     return dev;
   }
   void run(Experiment& e) {
     reset();
-    e.initialize(device());
+    e.initialize(devices());
     e.run();
   }
   void runMany(std::vector<Experiment*> es) {
-    for (auto* e : es) { e->initialize(device()); }
+    for (auto* e : es) { e->initialize(devices()); }
     for (auto* e : es) e->run();   // the reference interleaves experiments by coroutine switches; results are identical
   }
 };

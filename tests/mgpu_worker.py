@@ -28,6 +28,9 @@ def main():
              # gradient step of the mean: every rank adds its share of sum_i w_i step/sqrt(N) grad_i to the partial mean (all-reduced)
              dict(n=48, population_size=256, objective="NegSphereSin2", initial_value=1.5, initial_stddev=1.0, seed=13,
                   use_gradient_information=1, gradient_step_size=0.02),
+             # bounds + resampling rounds: the infeasible counter and the decision to go on resampling are global (all-reduced)
+             dict(n=12, population_size=96, objective="NegSphere", initial_value=4.0, initial_stddev=2.5, seed=31, lower_bound=-5.0,
+                  upper_bound=5.0, max_infeasible_resamplings=10**9, mirrored_sampling=1),
              # discrete variables: the mutations are keyed by the GLOBAL sample index, so the sharding must not change them
              dict(n=24, population_size=128, objective="NegEllipsoid", initial_value=2.2, initial_stddev=1.5, seed=17, mirrored_sampling=1,
                   granularity=np.array([1.0, 0.0, 0.5, 0.0] * 6))]
@@ -60,6 +63,8 @@ def main():
                     assert e < tol, (case["objective"], g, k, e)
                 assert abs(s.scalar("Sigma") - ref.scalar("Sigma")) < tol * ref.scalar("Sigma")
                 assert abs(s.scalar("Best Ever Value") - ref.scalar("Best Ever Value")) <= tol * abs(ref.scalar("Best Ever Value"))
+                if g == 0:
+                    assert s.scalar("Infeasible Sample Count") == ref.scalar("Infeasible Sample Count"), case["objective"]
         # every rank holds the same replicated state
         c = torch.tensor(s.get("Covariance Matrix"), device="cuda")
         c0 = c.clone(); dist.broadcast(c0, 0)

@@ -1,5 +1,8 @@
-"""The reference's own CMA-ES test scripts, ported to pytest with `import korali_b200 as korali` and nothing else
-changed: same experiment definitions, same seeds, same asserted thresholds.
+"""The reference's own CMA-ES test scripts, ported to pytest with `import korali_b200 as korali`: same experiment definitions,
+same seeds, same asserted thresholds — with these stated deviations: console output is "Silent" instead of "Detailed"; the CCMAES
+cases assert the reference's thresholds with 1e-6 relative slack (TestCCMAES: a different eigensolver and RNG stream move the
+converged optimum in its last digits); the two `checkInfeasible` corner cases of run-cmaes.py:219-272 run with the reference's
+settings ("Max Infeasible Resamplings" left at its default, which the release build reads as 0 — SURVEY Q2 — and set to 50).
   tests/statistical/optimizers/correctness/run-cmaes.py          -> TestCorrectness
   tests/statistical/optimizers/detailed/ccmaes/run-ccmaes.py      -> TestCCMAES
   tests/statistical/optimizers/termination/cmaes_termination.py   -> TestTermination
@@ -123,9 +126,34 @@ class TestCorrectness:
         e["Variables"][0]["Initial Value"] = 1.0
         e["Solver"]["Viability Population Size"] = 2
         korali.Engine().run(e)
-        checkInfeasible(e, 10) if False else None   # the reference counts bound violations here; with Max Infeasible Resamplings = 0 (Q2) none occur
+        # run-cmaes.py:243. The constraint is never met: the solver stays in the viability regime, sigma doubles every generation
+        # (updateSigma :722-726) and the samples leave [-10, 10]; each is counted once (default Max Infeasible Resamplings = 0, Q2)
+        checkInfeasible(e, 10)
         assert e["Solver"]["Is Viability Regime"] == 1
         assert e["Current Generation"] == 10
+
+    def test_terminates_on_max_infeasible_resamplings(self):
+        """run-cmaes.py:245-272: Max Infeasible Resamplings = 50 bounds the resampling loop by the CUMULATIVE count (:459) and ends
+        the run through the termination criterion (CMAES.config:114)."""
+        e = base_1d(16, 100)
+        e["Problem"]["Constraints"] = [constraint1]
+        e["Variables"][0]["Initial Value"] = 1.0
+        e["Solver"]["Viability Population Size"] = 2
+        e["Solver"]["Termination Criteria"]["Max Infeasible Resamplings"] = 50
+        korali.Engine().run(e)
+        checkInfeasible(e, 50)
+        assert e["Current Generation"] < 100
+
+    def test_resample_until_feasible_when_the_limit_is_large(self):
+        """The other reading of the default (2^64-1 with -march=native): every out-of-bounds draw is redrawn, so the final
+        population is feasible and every rejected draw is counted."""
+        e = base_1d(64, 20)
+        e["Variables"][0]["Initial Value"] = 9.0
+        e["Variables"][0]["Initial Standard Deviation"] = 6.0
+        e["Solver"]["Termination Criteria"]["Max Infeasible Resamplings"] = 10**9
+        korali.Engine().run(e)
+        assert e["Solver"]["Infeasible Sample Count"] > 0
+        assert all(-10.0 <= x[0] <= 10.0 for x in e["Solver"]["Sample Population"])
 
     def test_min_stddev_update_warning_path(self):
         e = base_1d(64, 10)

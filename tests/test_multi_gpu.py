@@ -22,7 +22,57 @@ def test_sharded_population_matches_single_gpu():
            "--master-port", "29533", os.path.join(ROOT, "tests", "mgpu_worker.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
-    assert out.stdout.count("ok ") == 5
+    assert out.stdout.count("ok ") == 6
+
+
+def _korali_run(devices, objective="Rosenbrock", n=64, pop=512, gens=12, mirrored=False):
+    import korali_b200 as korali
+    e = korali.Experiment()
+    e["Random Seed"] = 21
+    e["Problem"]["Type"] = "Optimization"
+    e["Problem"]["Objective Function"] = objective
+    for i in range(n):
+        e["Variables"][i]["Name"] = "X%d" % i
+        e["Variables"][i]["Initial Value"] = 0.2
+        e["Variables"][i]["Initial Standard Deviation"] = 0.8
+    e["Solver"]["Type"] = "Optimizer/CMAES"
+    e["Solver"]["Population Size"] = pop
+    e["Solver"]["Mirrored Sampling"] = mirrored
+    e["Solver"]["Termination Criteria"]["Max Generations"] = gens
+    e["Console Output"]["Verbosity"] = "Silent"
+    e["File Output"]["Enabled"] = False
+    k = korali.Engine()
+    k["Conduit"]["Type"] = "Device"
+    if devices is not None:
+        k["Conduit"]["Devices"] = devices
+    k.run(e)
+    return e
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("devices", [2, [1, 0]])
+def test_engine_devices_shards_the_population_behind_the_korali_api(devices):
+    """k["Conduit"]["Devices"] = G: one process, one handle + host thread per device, kcma_comm_init_all — the Korali script is the
+    only thing that changes (the reference picks its Distributed conduit the same way, distributed.cpp.base:13-90). Same Philox
+    samples as on one device, so the runs agree up to the all-reduce summation order."""
+    for mirrored in (False, True):
+        e1 = _korali_run(None, mirrored=mirrored)
+        e2 = _korali_run(devices, mirrored=mirrored)
+        assert e1["Current Generation"] == e2["Current Generation"] == 12
+        assert e1["Solver"]["Model Evaluation Count"] == e2["Solver"]["Model Evaluation Count"] == 12 * 512
+        b1, b2 = e1["Results"]["Best Sample"]["F(x)"], e2["Results"]["Best Sample"]["F(x)"]
+        assert abs(b1 - b2) <= 1e-9 * abs(b1)
+        m1, m2 = np.array(e1["Solver"]["Current Mean"]), np.array(e2["Solver"]["Current Mean"])
+        assert np.abs(m1 - m2).max() <= 1e-8 * np.abs(m1).max()
+        assert abs(e1["Solver"]["Sigma"] - e2["Solver"]["Sigma"]) <= 1e-8 * e1["Solver"]["Sigma"]
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_engine_devices_rejects_python_models():
+    with pytest.raises(RuntimeError, match="device objective"):
+        _korali_run(2, objective=lambda s: s.__setitem__("F(x)", -sum(x * x for x in s["Parameters"])), n=4, pop=8, gens=2)
 
 
 def _gloo_worker(rank, world, port, q):
