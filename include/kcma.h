@@ -174,6 +174,13 @@ int kcma_set_host_objective(kcma_t* h, kcma_host_objective_fn fn, void* user);
 typedef void (*kcma_host_objective_grad_fn)(void* user, const double* x, uint64_t rows, uint64_t n, double* f_out, double* grad_out);
 int kcma_set_host_objective_grad(kcma_t* h, kcma_host_objective_grad_fn fn, void* user);
 int kcma_set_host_constraints(kcma_t* h, kcma_host_constraints_fn fn, void* user);
+/* User objective that stays on the device (the whole population in ONE call instead of the reference's lambda
+ * per-sample Sample trips, conduit.cpp.base:29-88): the callback receives the device pointer of this rank's samples
+ * (rows x n, leading dimension ldx doubles, row-major) and writes F(x) for every row to f_dev. It must enqueue its work on
+ * `stream` (the handle's stream) or synchronise before it returns. Needs keep_population = 1; non-finite values are an error
+ * like everywhere else (optimization.cpp.base:32-33). */
+typedef void (*kcma_device_objective_fn)(void* user, const double* x_dev, uint64_t rows, uint64_t n, uint64_t ldx, double* f_dev, void* stream);
+int kcma_set_device_objective(kcma_t* h, kcma_device_objective_fn fn, void* user);
 
 /* ---- parity hooks ------------------------------------------------------------------- */
 int kcma_inject(kcma_t* h, int kind, const double* host, size_t count);

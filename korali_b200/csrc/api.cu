@@ -91,6 +91,7 @@ struct kcma {
   unsigned char* dFresh = nullptr;              // mirrored resampling rounds: pair was drawn in the previous round
   unsigned long long* dRound = nullptr;         // {infeasible members, rows to redraw} of a resampling round (all-reduced over the ranks)
   unsigned long long* hRound = nullptr;         // pinned
+  unsigned long long* dRoundV = nullptr;        // one slot per rank (settling the resampling budget)
   // constraint path (K9)
   double *dG = nullptr, *dBounds = nullptr, *dNormal = nullptr, *dCaux = nullptr, *dBestCon = nullptr, *dU = nullptr;
   unsigned long long* dViol = nullptr;
@@ -114,6 +115,7 @@ struct kcma {
   kcma_host_objective_grad_fn host_obj_grad = nullptr;
   std::vector<double> hGrad;
   kcma_host_constraints_fn host_con = nullptr; void* host_con_user = nullptr;
+  kcma_device_objective_fn dev_obj = nullptr; void* dev_obj_user = nullptr;   // user objective on the device pointer of X
   std::vector<double> hX, hF, hG;
   // tridiagonalisation-based eigensolver (created on first use)
   kc::TridiagWs* tri = nullptr;
@@ -297,6 +299,13 @@ __global__ void transpose_kernel(const double* __restrict__ in, double* __restri
 }
 
 __global__ void copy_sigma_kernel(const DevScalars* sc, double* out) { *out = sc->sigma; }
+__global__ void check_finite_kernel(const double* __restrict__ f, long long n, DevScalars* sc) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    if (!isfinite(f[i])) atomicExch(&sc->nonfinite, 1);
+}
+void launch_check_finite(cudaStream_t st, const double* f, long long n, DevScalars* sc) {
+  if (n > 0) check_finite_kernel<<<(int)std::min<long long>((n + 255) / 256, 1024), 256, 0, st>>>(f, n, sc);
+}
 
 // infeasible flags -> list of z-rows to resample + counters (prepareGeneration :455-459, :484-490). Single block.
 __global__ void __launch_bounds__(1024)
@@ -481,6 +490,148 @@ int update_eigensystem(kcma* h, const double* dM) {
 // by-value generation argument of the kernels; while a graph is being captured the kernels read DevScalars::gen instead
 unsigned gen_arg(const kcma* h) { return h->capturing ? kGenFromDevice : (unsigned)h->gen; }
 
+// ---- bounds rejection (prepareGeneration :439-492) ------------------------------------------------------------------------------
+// The reference redraws ONE sample at a time until it is feasible or the cumulative 'Infeasible Sample Count' reaches 'Max
+// Infeasible Resamplings' (:459, :490). The draws are Philox(sample, attempt), so the attempts of a sample do not depend on the
+// order in which samples are visited: the device redraws ALL infeasible samples once per ROUND (attempt r in round r) until every
+// sample is feasible, which gives the reference's population and counter whenever the budget is not exhausted. When it is, the
+// reference's visiting order matters (samples before the exhaustion point are fully resampled, the one that exhausts the budget
+// keeps an infeasible draw, every later sample keeps its FIRST draw): settle_resampling_budget() replays that order on the host
+// from the per-sample attempt counts and re-generates the draws the reference would have kept.
+int settle_resampling_budget(kcma* h, long long ls, unsigned long long zrow_begin, unsigned long long count_before,
+                             unsigned long long local_counted, unsigned long long cap) {
+  const int N = h->N, ld = h->ld, mirrored = h->cfg.mirrored_sampling;
+  const unsigned long long maxres = h->cfg.max_infeasible_resamplings;
+  const long long zrows = mirrored ? ls / 2 : ls;
+  const int nr = h->cfg.nranks, rank = h->cfg.rank;
+  std::vector<unsigned> att((size_t)zrows);
+  std::vector<unsigned char> flag((size_t)ls);
+  CUDA_OK(h, cudaMemcpyAsync(att.data(), h->dAttempt, sizeof(unsigned) * zrows, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(h, cudaMemcpyAsync(flag.data(), h->dInfeasible, (size_t)ls, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  // count at the first sample of this rank if every earlier rank resampled to the end (exact as long as no earlier rank exhausts it)
+  std::vector<unsigned long long> per_rank((size_t)nr, 0ull);
+  per_rank[rank] = local_counted;
+  if (nr > 1) {
+    CUDA_OK(h, cudaMemcpyAsync(h->dRoundV, per_rank.data(), sizeof(unsigned long long) * nr, cudaMemcpyHostToDevice, h->stream));
+    if (nccl_check(h, g_nccl.AllReduce(h->dRoundV, h->dRoundV, nr, ncclUint64, ncclSum, h->comm, h->stream), "all-reduce(resampling per rank)")) return 1;
+    CUDA_OK(h, cudaMemcpyAsync(per_rank.data(), h->dRoundV, sizeof(unsigned long long) * nr, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  }
+  unsigned long long c = count_before;
+  for (int q = 0; q < rank; q++) c += per_rank[q];   // >= maxres once an earlier rank exhausted the budget: then only "c >= maxres" matters
+  const unsigned long long c_start = c;
+  std::vector<int> rows;            // z rows whose kept draw is not the one the rounds ended with
+  std::vector<unsigned> keep;       // ... and the attempt the reference keeps
+  for (long long j = 0; j < zrows; j++) {
+    const unsigned k = att[j];      // failed draws before the current one
+    unsigned long long t;
+    unsigned final_att;
+    if (!mirrored) {
+      const bool feasible_now = flag[j] == 0;
+      const unsigned long long kk = feasible_now ? k : (unsigned long long)k + 1;   // infeasible draws seen so far (all of them if never feasible)
+      const bool endless = !feasible_now;                                            // still infeasible at the cap: treat as "never"
+      if (kk == 0) continue;
+      const unsigned long long room = c < maxres ? maxres - c : 0ull;
+      t = std::max(1ull, room);                                   // infeasible draws the reference makes before it gives up
+      if (!endless && kk < t) { c += kk; continue; }              // feasible before the budget runs out: the rounds' draw stands
+      if (endless && t > kk) t = kk;                              // (cannot happen with cap >= maxres; keeps the index in range)
+      c += t;
+      final_att = (unsigned)(t - 1);
+    } else {
+      const int m = flag[2 * j] + flag[2 * j + 1];                // infeasible members of the current draw
+      const bool accepted = m < 2;
+      const unsigned long long kf = accepted ? k : (unsigned long long)k + 1;        // draws with BOTH members infeasible
+      if (kf == 0) { c += (unsigned long long)m; continue; }
+      const unsigned long long room = c < maxres ? maxres - c : 0ull;
+      t = std::max(1ull, (room + 1) / 2);                         // smallest t >= 1 with c + 2 t >= maxres
+      if (accepted && kf < t) { c += 2 * kf + (unsigned long long)m; continue; }
+      if (t > kf) t = kf;
+      c += 2 * t;
+      final_att = (unsigned)(t - 1);
+    }
+    if (final_att != k) { rows.push_back((int)j); keep.push_back(final_att); }
+  }
+  const unsigned long long contributed = c - c_start;
+  // exact global counter = before + sum of what every rank contributes under the reference's order
+  unsigned long long total = count_before + contributed;
+  if (nr > 1) {
+    std::fill(per_rank.begin(), per_rank.end(), 0ull);
+    per_rank[rank] = contributed;
+    CUDA_OK(h, cudaMemcpyAsync(h->dRoundV, per_rank.data(), sizeof(unsigned long long) * nr, cudaMemcpyHostToDevice, h->stream));
+    if (nccl_check(h, g_nccl.AllReduce(h->dRoundV, h->dRoundV, nr, ncclUint64, ncclSum, h->comm, h->stream), "all-reduce(resampling settled)")) return 1;
+    CUDA_OK(h, cudaMemcpyAsync(per_rank.data(), h->dRoundV, sizeof(unsigned long long) * nr, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    total = count_before;
+    for (int q = 0; q < nr; q++) total += per_rank[q];
+  }
+  (void)cap;
+  if (!rows.empty()) {   // re-generate the draws the reference keeps: z = Philox(row, attempt), y = B D z, x, feasibility flags
+    const int cnt = (int)rows.size();
+    for (int i = 0; i < cnt; i++) att[rows[i]] = keep[i];
+    int* dRows = (int*)h->dSelS;
+    CUDA_OK(h, cudaMemcpyAsync(h->dAttempt, att.data(), sizeof(unsigned) * zrows, cudaMemcpyHostToDevice, h->stream));
+    CUDA_OK(h, cudaMemcpyAsync(dRows, rows.data(), sizeof(int) * cnt, cudaMemcpyHostToDevice, h->stream));
+    launch_philox_normal(h->stream, h->dZ, ld, cnt, N, h->cfg.seed, (unsigned)h->gen, zrow_begin, h->dAttempt, dRows, h->num_sms);
+    dim3 grid((N + 7) / 8, cnt);
+    resample_rows_kernel<<<grid, 256, 0, h->stream>>>(h->dZ, h->dY, ld, h->dA, N, dRows, h->cfg.diagonal_covariance, h->dD);
+    launch_feasibility(h->stream, h->dY, ld, ls, N, mirrored, h->dMean, h->dSc, h->dLower, h->dUpper, h->dInfeasible,
+                       h->cfg.keep_population ? h->dX : nullptr, ld, nullptr, h->num_sms);
+    h->launches += 3;
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));   // `att` / `rows` are host vectors
+  }
+  h->scalars_fresh = false;
+  if (pull_scalars(h)) return 1;
+  h->hSc->infeasible_sample_count = total;
+  return push_scalars(h);
+}
+
+int resample_infeasible(kcma* h, long long ls, unsigned long long zrow_begin) {
+  const int N = h->N, ld = h->ld;
+  int* dRows = (int*)h->dSelS;                     // reuse: the selection list is rebuilt in tell()
+  unsigned* dAttempt = h->dAttempt;                // zeroed per generation
+  const unsigned long long maxres = h->cfg.max_infeasible_resamplings;
+  const bool multi = h->cfg.nranks > 1;
+  unsigned char* dFresh = (h->cfg.mirrored_sampling && maxres != 0) ? h->dFresh : nullptr;
+  if (dFresh) CUDA_OK(h, cudaMemsetAsync(dFresh, 1, local_zrows(h), h->stream));
+  unsigned long long count_before = 0, local_counted = 0;
+  if (maxres != 0) {
+    if (pull_scalars(h)) return 1;
+    count_before = h->hSc->infeasible_sample_count;
+  }
+  // no sample needs more redraws than the budget holds; the hard cap keeps a never-feasible sample from spinning forever
+  const unsigned long long cap = std::min<unsigned long long>(maxres, 100000ull);
+  for (unsigned long long round = 0;; round++) {
+    infeasible_compact_kernel<<<1, 1024, 0, h->stream>>>(h->dInfeasible, (int)ls, h->cfg.mirrored_sampling, dRows, h->dCount, h->dSc, dFresh,
+                                                         h->dRound);
+    // 'Infeasible Sample Count' and the decision to go on resampling are GLOBAL: every rank must leave this loop in the same
+    // round (the loop holds a collective) and must see the same counter in the termination chain
+    if (multi && nccl_check(h, g_nccl.AllReduce(h->dRound, h->dRound, 2, ncclUint64, ncclSum, h->comm, h->stream), "all-reduce(infeasible)")) return 1;
+    add_infeasible_from_round_kernel<<<1, 1, 0, h->stream>>>(h->dSc, h->dRound);
+    h->launches += 2;
+    h->scalars_fresh = false;
+    if (maxres == 0) return 0;  // reference release build: size_t(Infinity) == 0 -> never resamples
+    CUDA_OK(h, cudaMemcpyAsync(h->hCount, h->dCount, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(h, cudaMemcpyAsync(h->hRound, h->dRound, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    if (pull_scalars(h)) return 1;
+    local_counted += h->hSc->infeasible_this_round;
+    const int cnt = *h->hCount;
+    if (h->hRound[1] == 0 || round >= cap) break;
+    if (cnt > 0) {
+      bump_attempts_kernel<<<(cnt + 255) / 256, 256, 0, h->stream>>>(dAttempt, dRows, cnt);
+      launch_philox_normal(h->stream, h->dZ, ld, cnt, N, h->cfg.seed, (unsigned)h->gen, zrow_begin, dAttempt, dRows, h->num_sms);
+      dim3 grid((N + 7) / 8, cnt);
+      resample_rows_kernel<<<grid, 256, 0, h->stream>>>(h->dZ, h->dY, ld, h->dA, N, dRows, h->cfg.diagonal_covariance, h->dD);
+      // re-check (sample list = z-rows, or both members when mirrored)
+      launch_feasibility(h->stream, h->dY, ld, ls, N, h->cfg.mirrored_sampling, h->dMean, h->dSc, h->dLower, h->dUpper,
+                         h->dInfeasible, h->cfg.keep_population ? h->dX : nullptr, ld, nullptr, h->num_sms);
+      h->launches += 4;
+    }
+  }
+  if (h->hSc->infeasible_sample_count >= maxres) return settle_resampling_budget(h, ls, zrow_begin, count_before, local_counted, cap);
+  return 0;
+}
+
 int sample_population(kcma* h) {
   const int N = h->N, ld = h->ld;
   const long long zrows = (long long)local_zrows(h);
@@ -517,40 +668,7 @@ int sample_population(kcma* h) {
       h->launches++;
       if (h->has_bounds) { launch_feasibility_x(h->stream, h->dX, ld, ls, N, h->dLower, h->dUpper, h->dInfeasible, h->num_sms); h->launches++; }
     }
-    if (h->has_bounds) {
-      int* dRows = (int*)h->dSelS;                     // reuse: selection list is rebuilt in tell()
-      unsigned* dAttempt = h->dAttempt;                // zeroed per generation
-      const uint64_t maxres = h->cfg.max_infeasible_resamplings;
-      const bool multi = h->cfg.nranks > 1;
-      unsigned char* dFresh = (h->cfg.mirrored_sampling && maxres != 0) ? h->dFresh : nullptr;
-      if (dFresh) CUDA_OK(h, cudaMemsetAsync(dFresh, 1, local_zrows(h), h->stream));
-      for (int round = 0; round < 1000000; round++) {
-        infeasible_compact_kernel<<<1, 1024, 0, h->stream>>>(h->dInfeasible, (int)ls, h->cfg.mirrored_sampling, dRows, h->dCount, h->dSc, dFresh,
-                                                             h->dRound);
-        // 'Infeasible Sample Count' and the decision to go on resampling are GLOBAL: every rank must leave this loop in the same
-        // round (the loop holds a collective) and must see the same counter in the termination chain
-        if (multi && nccl_check(h, g_nccl.AllReduce(h->dRound, h->dRound, 2, ncclUint64, ncclSum, h->comm, h->stream), "all-reduce(infeasible)")) return 1;
-        add_infeasible_from_round_kernel<<<1, 1, 0, h->stream>>>(h->dSc, h->dRound);
-        h->launches += 2;
-        h->scalars_fresh = false;
-        if (maxres == 0) break;  // reference release build: size_t(Infinity) == 0 -> never resamples
-        CUDA_OK(h, cudaMemcpyAsync(h->hCount, h->dCount, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-        CUDA_OK(h, cudaMemcpyAsync(h->hRound, h->dRound, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
-        if (pull_scalars(h)) return 1;
-        const int cnt = *h->hCount;
-        if (h->hRound[1] == 0 || h->hSc->infeasible_sample_count >= maxres) break;
-        if (cnt > 0) {
-          bump_attempts_kernel<<<(cnt + 255) / 256, 256, 0, h->stream>>>(dAttempt, dRows, cnt);
-          launch_philox_normal(h->stream, h->dZ, ld, cnt, N, h->cfg.seed, (unsigned)h->gen, zrow_begin, dAttempt, dRows, h->num_sms);
-          dim3 grid((N + 7) / 8, cnt);
-          resample_rows_kernel<<<grid, 256, 0, h->stream>>>(h->dZ, h->dY, ld, h->dA, N, dRows, h->cfg.diagonal_covariance, h->dD);
-          // re-check only the resampled rows (sample list = z-rows, or both members when mirrored)
-          launch_feasibility(h->stream, h->dY, ld, ls, N, h->cfg.mirrored_sampling, h->dMean, h->dSc, h->dLower, h->dUpper,
-                             h->dInfeasible, h->cfg.keep_population ? h->dX : nullptr, ld, nullptr, h->num_sms);
-          h->launches += 4;
-        }
-      }
-    }
+    if (h->has_bounds && resample_infeasible(h, ls, zrow_begin)) return 1;
   }
   h->inj_y = false;
   if (h->has_discrete) h->inj_x = true;   // eval / tell read the materialised X (same mode as an injected population)
@@ -749,6 +867,15 @@ int do_eval(kcma* h) {
   }
   if (want_grad && !have_grad && (h->host_obj || h->cfg.objective == KCMA_OBJ_EXTERNAL))
     return fail(h, "Use Gradient Information: the model must return gradients (kcma_set_host_objective_grad or KCMA_INJ_GRAD)");
+  if (h->dev_obj) {   // user objective on the device: one call for the whole shard, X and F never leave HBM
+    PhaseTimer t(h, "device_objective");
+    const long long ls = (long long)local_samples(h);
+    h->dev_obj(h->dev_obj_user, h->dX, (uint64_t)ls, (uint64_t)h->N, (uint64_t)h->ld, h->dF + h->shard_lo, (void*)h->stream);
+    launch_check_finite(h->stream, h->dF + h->shard_lo, ls, h->dSc);
+    h->launches++;
+    h->scalars_fresh = false;
+    return 0;
+  }
   if (h->host_obj) {  // batched host conduit
     PhaseTimer t(h, "host_objective");
     const size_t ls = local_samples(h), N = h->N;
@@ -961,7 +1088,7 @@ void kcma_destroy(kcma_t* h) {
   if (h->hSc) cudaFreeHost(h->hSc);
   if (h->hCount) cudaFreeHost(h->hCount);
   if (h->hRound) cudaFreeHost(h->hRound);
-  cudaFree(h->dFresh); cudaFree(h->dRound);
+  cudaFree(h->dFresh); cudaFree(h->dRound); cudaFree(h->dRoundV);
   for (auto& p : h->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (auto e : h->event_pool) cudaEventDestroy(e);
   delete h;
@@ -1115,6 +1242,7 @@ int kcma_create(const kcma_cfg* cfg, kcma_t** out) {
   CREATE_CUDA(cudaMallocHost((void**)&h->hCount, 4 * sizeof(int)));
   CREATE_CUDA(cudaMallocHost((void**)&h->hRound, 2 * sizeof(unsigned long long)));
   CREATE_CUDA(dmalloc(&h->dRound, 2)); CREATE_CUDA(dmalloc(&h->dFresh, h->max_local + 16));
+  CREATE_CUDA(dmalloc(&h->dRoundV, (size_t)(h->cfg.nranks > 0 ? h->cfg.nranks : 1)));
   memset(h->hSc, 0, sizeof(DevScalars));
   CREATE_CUDA(cudaMemcpy(h->dLower, h->lower.data(), sizeof(double) * N, cudaMemcpyHostToDevice));
   CREATE_CUDA(cudaMemcpy(h->dUpper, h->upper.data(), sizeof(double) * N, cudaMemcpyHostToDevice));
@@ -1155,6 +1283,14 @@ int kcma_set_host_objective_grad(kcma_t* h, kcma_host_objective_grad_fn fn, void
   if (fn && !h->cfg.use_gradient_information) return fail(h, "a gradient-returning host objective needs Use Gradient Information");
   if (fn && !h->cfg.keep_population) return fail(h, "a host objective needs keep_population = 1 (X is copied to the host every generation)");
   h->host_obj_grad = fn; h->host_obj_user = user;
+  return 0;
+}
+int kcma_set_device_objective(kcma_t* h, kcma_device_objective_fn fn, void* user) {
+  if (!h) return fail(nullptr, "null solver handle");
+  invalidate_graph(h);
+  if (fn && !h->cfg.keep_population) return fail(h, "a device objective needs keep_population = 1 (it reads the materialised X)");
+  if (fn && h->cfg.use_gradient_information) return fail(h, "a device objective cannot return gradients: use kcma_set_host_objective_grad");
+  h->dev_obj = fn; h->dev_obj_user = user;
   return 0;
 }
 int kcma_set_host_constraints(kcma_t* h, kcma_host_constraints_fn fn, void* user) {
@@ -1250,7 +1386,7 @@ void invalidate_graph(kcma* h) {
 // microseconds each per generation): the graph removes the per-launch host cost. KCMA_GRAPH=0 disables it.
 bool graph_eligible(const kcma* h) {
   static const int on = getenv("KCMA_GRAPH") ? atoi(getenv("KCMA_GRAPH")) : 1;
-  if (!on || h->graph_failed || h->timing || h->cfg.nranks > 1 || h->host_obj || h->host_obj_grad || h->host_con || h->has_constraints) return false;
+  if (!on || h->graph_failed || h->timing || h->cfg.nranks > 1 || h->host_obj || h->host_obj_grad || h->dev_obj || h->host_con || h->has_constraints) return false;
   if (h->cfg.objective == KCMA_OBJ_EXTERNAL || h->has_discrete) return false;
   if (h->has_bounds && h->cfg.max_infeasible_resamplings != 0) return false;
   if (h->inj_z || h->inj_bd || h->inj_y || h->inj_x || h->inj_f || h->inj_grad || h->sampled_pending || !h->vt_valid) return false;

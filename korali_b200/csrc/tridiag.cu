@@ -272,7 +272,7 @@ template <int KU, int NC>
 __global__ void __launch_bounds__(SY_NT, 1)
 sytrd_reg_kernel(const double* __restrict__ M, int ld, int n, int ns /* n rounded up to even: LL stride per parity, vector stride */,
                  LL* __restrict__ xP, LL* __restrict__ xC, double* __restrict__ dT, double* __restrict__ eT, double* __restrict__ tauv,
-                 double* __restrict__ VR, long long* __restrict__ prof, int prof_step0, int prof_cta, int opt) {
+                 double* __restrict__ VR, long long* __restrict__ prof, int prof_step0, int prof_cta, int opt, int copies) {
   extern __shared__ __align__(16) double sm[];
   const int G = gridDim.x, b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   double* vs_old = sm;             // reflector v_{i-1} by index (lookups v[c], v[i+1])
@@ -295,15 +295,20 @@ sytrd_reg_kernel(const double* __restrict__ M, int ld, int n, int ns /* n rounde
     v[2 * k] = v[2 * k + 1] = w[2 * k] = w[2 * k + 1] = vnw[2 * k] = vnw[2 * k + 1] = 0.0;
   }
   for (int r = tid; r < ns; r += SY_NT) { vs_old[r] = 0.0; vs_new[r] = 0.0; wsm[r] = 0.0; }
+  // Every slot exists `copies` times (stride cstride): all CTAs poll the same 2 n slots, and 148 requests per 128-byte line and
+  // polling round serialise in the L2 slice that owns the line; CTA b reads copy b % copies, the producers write all copies.
+  const size_t cstride = 4 * (size_t)ns;
+  const size_t my_copy = (size_t)(b % copies) * cstride;
   if (b == 0)   // owner of column 0 publishes it for step 0
-    for (int r = tid; r < n; r += SY_NT) ll_store(xC + r, M[r], 1ull);
+    for (int r = tid; r < n; r += SY_NT)
+      for (int q = 0; q < copies; q++) ll_store(xC + q * cstride + r, M[r], 1ull);
   __syncthreads();
   double tau_old = 0.0;
   for (int i = 0; i < n; i++) {
     const int par = i & 1;
     const unsigned long long tag = (unsigned long long)i + 1ull;
-    const LL* Pin = xP + (size_t)par * ns;
-    const LL* Cin = xC + (size_t)par * ns;
+    const LL* Pin = xP + my_copy + (size_t)par * ns;
+    const LL* Cin = xC + my_copy + (size_t)par * ns;
     const bool have_p = i > 0;
     const bool pr = prof && b == prof_cta && tid == 0 && i >= prof_step0 && i < prof_step0 + 32;
     if (pr) prof[(i - prof_step0) * 8 + 0] = clock64();
@@ -416,8 +421,10 @@ sytrd_reg_kernel(const double* __restrict__ M, int ld, int n, int ns /* n rounde
           dot += a1 * vnw[2 * k + 1];
           if (c == i + 1) {
             const int r = 2 * (tid + SY_NT * k);
-            if (r > i && r < n) ll_store(Cout + r, a0, otag);
-            if (r + 1 > i && r + 1 < n) ll_store(Cout + r + 1, a1, otag);
+            for (int q = 0; q < copies; q++) {
+              if (r > i && r < n) ll_store(Cout + q * cstride + r, a0, otag);
+              if (r + 1 > i && r + 1 < n) ll_store(Cout + q * cstride + r + 1, a1, otag);
+            }
           }
         }
         pp[s * SY_NT + tid] = dot;
@@ -430,7 +437,7 @@ sytrd_reg_kernel(const double* __restrict__ M, int ld, int n, int ns /* n rounde
 #pragma unroll
         for (int j = 0; j < SY_NW; j++) x += pp[s * SY_NT + lane + 32 * j];
         x = warp_sum_butterfly(x);
-        if (lane == 0) ll_store(Pout + b + s * G, x, otag);
+        if (lane < copies) ll_store(Pout + lane * cstride + b + s * G, x, otag);
       }
     if (pr) prof[(i - prof_step0) * 8 + 3] = clock64();
     if (b == i % G) {   // reflector i for the back-transform (entries r <= i and r >= n stay zero from the allocation)
@@ -531,6 +538,7 @@ TridiagWs* tridiag_ws_create(int n, int ld, int num_sms, char* err, size_t errle
   // ---- stage 1 geometry
   const int ns = (n + 1) & ~1;
   int grid = num_sms < 1 ? 1 : num_sms;
+  if (const char* ge = getenv("KCMA_SYTRD_GRID")) { const int g = atoi(ge); if (g >= 1 && g <= grid) grid = g; }   // A/B runs
   if (grid > (n + 3) / 4) grid = (n + 3) / 4;        // at least ~4 columns per CTA: fewer slices to collect per step at small N
   if (grid < 1) grid = 1;
   const int nloc_max = (n + grid - 1) / grid;
@@ -543,18 +551,21 @@ TridiagWs* tridiag_ws_create(int n, int ld, int num_sms, char* err, size_t errle
   if (!(force && atoi(force) == 0)) {
     if (units <= SY_NT && nloc_max <= 4) ws->reg_variant = 1;
     else if (units <= 2 * SY_NT && nloc_max <= 7) ws->reg_variant = 2;
+    else if (units <= 2 * SY_NT && nloc_max <= 14) ws->reg_variant = 4;
     else if (units <= 3 * SY_NT && nloc_max <= 11) ws->reg_variant = 3;
   }
   ws->resident = ws->reg_variant != 0;
   ws->sy_grid = grid;
-  static const int kNC[4] = {0, 4, 7, 11};
+  static const int kNC[5] = {0, 4, 7, 11, 14};
   ws->sy_smem = ws->resident ? sizeof(double) * (3 * (size_t)ns + 48 + (size_t)kNC[ws->reg_variant] * SY_NT) : vec_bytes;
   bool ok = true;
   if (!ws->resident) ok = ok && ws_alloc(ws, &ws->Awork, mat);
   ok = ok && ws_alloc(ws, &ws->dT, n) && ws_alloc(ws, &ws->eT, n) && ws_alloc(ws, &ws->tau, n) && ws_alloc(ws, &ws->VR, mat) &&
        ws_alloc(ws, &ws->VC, mat);
   LL* xb = nullptr;
-  ok = ok && ws_alloc(ws, &xb, 4 * (size_t)ns);
+  ws->ll_copies = 2;
+  if (const char* ce = getenv("KCMA_SYTRD_COPIES")) { const int c = atoi(ce); if (c >= 1 && c <= 16) ws->ll_copies = c; }
+  ok = ok && ws_alloc(ws, &xb, (size_t)ws->ll_copies * 4 * (size_t)ns);
   ws->xbuf = xb;
   if (const char* pe = getenv("KCMA_SYTRD_PROF")) {   // "step0[,cta]": clock64 stamps of 32 steps of one CTA (tridiag_dump_prof)
     ws->prof_step0 = atoi(pe);
@@ -701,6 +712,7 @@ TridiagWs* tridiag_ws_create(int n, int ld, int num_sms, char* err, size_t errle
   // kernel attributes
   cudaError_t e1 = cudaFuncSetAttribute(sytrd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCap);
   cudaError_t e2 = cudaFuncSetAttribute(sytrd_reg_kernel<3, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(sytrd_reg_kernel<2, 14>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
   cudaError_t e3 = cudaFuncSetAttribute(larft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (128 * 129 + 128)));
   if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) return fail("cudaFuncSetAttribute failed");
   if (cudaDeviceSynchronize() != cudaSuccess) return fail("CUDA error while building the workspace");
@@ -720,7 +732,7 @@ bool tridiag_stage_sytrd(cudaStream_t st, TridiagWs* ws, const double* M) {
   int n = ws->n, ld = ws->ld, ns = (n + 1) & ~1;
   LL* xP = (LL*)ws->xbuf;
   LL* xC = xP + 2 * (size_t)(ws->resident ? ns : n);   // per-parity stride: ns (32-byte aligned slot pairs) in the register variant
-  cudaMemsetAsync(ws->xbuf, 0, sizeof(LL) * 4 * (size_t)ns, st);
+  cudaMemsetAsync(ws->xbuf, 0, sizeof(LL) * 4 * (size_t)ns * (ws->resident ? ws->ll_copies : 1), st);
   double* Awork = ws->Awork;
   if (!ws->resident) cudaMemcpyAsync(Awork, M, sizeof(double) * (size_t)n * ld, cudaMemcpyDeviceToDevice, st);
   double *dT = ws->dT, *eT = ws->eT, *tau = ws->tau, *VR = ws->VR;
@@ -729,9 +741,11 @@ bool tridiag_stage_sytrd(cudaStream_t st, TridiagWs* ws, const double* M) {
   void* args[] = {&M, &Awork, &ld, &n, &ns, &xP, &xC, &dT, &eT, &tau, &VR, &prof, &prof_step0, &prof_cta};
   int opt = 1;
   if (const char* oe = getenv("KCMA_SYTRD_OPT")) opt = atoi(oe);
-  void* rargs[] = {&M, &ld, &n, &ns, &xP, &xC, &dT, &eT, &tau, &VR, &prof, &prof_step0, &prof_cta, &opt};
+  int copies = ws->ll_copies;
+  void* rargs[] = {&M, &ld, &n, &ns, &xP, &xC, &dT, &eT, &tau, &VR, &prof, &prof_step0, &prof_cta, &opt, &copies};
   const void* fn = ws->reg_variant == 1 ? (const void*)sytrd_reg_kernel<1, 4> : ws->reg_variant == 2 ? (const void*)sytrd_reg_kernel<2, 7>
-                   : ws->reg_variant == 3 ? (const void*)sytrd_reg_kernel<3, 11> : (const void*)sytrd_kernel;
+                   : ws->reg_variant == 3 ? (const void*)sytrd_reg_kernel<3, 11> : ws->reg_variant == 4 ? (const void*)sytrd_reg_kernel<2, 14>
+                   : (const void*)sytrd_kernel;
   if (cudaLaunchCooperativeKernel(fn, dim3(ws->sy_grid), dim3(SY_NT), ws->resident ? rargs : args, ws->sy_smem, st) != cudaSuccess) return false;
   // row n-1 of VR (no reflector) and tau[n-1] stay zero from the allocation; VC = VR^T
   launch_transpose(st, ws->VR, ws->VC, ld, n);

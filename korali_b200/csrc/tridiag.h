@@ -18,7 +18,8 @@ struct TridiagWs {
   double *dT = nullptr, *eT = nullptr, *tau = nullptr;   // diagonal, off-diagonal, reflector scalars
   double *VR = nullptr;        // row i = reflector v_i (support i+1.., v_i[i+1] = 1)
   double *VC = nullptr;        // VR^T (column i = v_i)
-  void* xbuf = nullptr;        // LL exchange slots: [P | C] x 2 parities x n x 16 B
+  void* xbuf = nullptr;        // LL exchange slots: copies x [P | C] x 2 parities x n x 16 B
+  int ll_copies = 2;           // replicas of every slot (spreads the polling of 148 CTAs over several L2 lines)
   long long* prof = nullptr; int prof_step0 = 0, prof_cta = 0;   // optional clock64 phase stamps of 32 steps (KCMA_SYTRD_PROF)
   // ---- stage 2: divide & conquer on (dT, eT)
   int levels = 0, leaf_count = 0;

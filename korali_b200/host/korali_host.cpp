@@ -13,6 +13,7 @@
 //   * errors are std::runtime_error -> Python RuntimeError           logger.cpp:83-99
 // What is NOT here: every other Korali module, conduit, problem type and solver (out of scope).
 // The JSON tree is held as Python objects (dict / list / float / ...): the reference's knlohmann fork is not vendored.
+#include <pybind11/numpy.h>
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
@@ -354,6 +355,12 @@ class CMAES {
     saved_internal = py::dict();
     for (const char* k : kInternal)
       if (s.has(k)) saved_internal[k] = s.take(k);
+    // Result files written by older builds of the reference (the fixture tests/python/plot/cmaes/gen*.json is one) carry a few keys
+    // that CMAES.config has since renamed or dropped; they are accepted so that such checkpoints load: 'Is Diagonal' is today's
+    // 'Diagonal Covariance', the others are internal state without a successor.
+    if (s.has("Is Diagonal")) { const int v = s.boolean("Is Diagonal", 0); if (v) cfg.diagonal_covariance = 1; }
+    for (const char* k : {"Are Constraints Defined", "Best Sample Index", "Previous Value Vector"})
+      if (s.has(k)) s.take(k);
     // variables (optimizer.config:45-82, CMAES.config Variable Defaults: Granularity 0.0)
     const size_t n = py::len(variables);
     if (n == 0) korali_error("Optimization Evaluation problems require at least one variable.\n");
@@ -413,6 +420,10 @@ class CMAES {
     } else if (PyCallable_Check(objective.ptr())) {
       cfg.objective = KCMA_OBJ_EXTERNAL;
       cfg.keep_population = 1;
+      // korali_b200.batched(fn) / korali_b200.batched_device(fn): the model takes the whole population in one call
+      batched = py::hasattr(objective, "_korali_batched") ? objective.attr("_korali_batched").cast<std::string>() : std::string();
+      if (!batched.empty() && batched != "numpy" && batched != "device") korali_error("Unknown batched model flavour '%s'\n", batched.c_str());
+      if (!batched.empty() && cfg.use_gradient_information) korali_error("Batched models do not return gradients: use a per-sample model with 'Use Gradient Information'\n");
     } else {
       korali_error(" + Object: [ Optimization ] \n + Key:    ['Objective Function']\n + Reason: neither a callable nor the name of a device objective\n");
     }
@@ -420,6 +431,31 @@ class CMAES {
   }
 
   py::dict saved_internal;
+  std::string batched;   // "", "numpy" or "device"
+
+  // korali_b200.batched(fn): ONE call per generation with X as a (rows x N) NumPy view of the host copy of the population
+  static void host_objective_batched(void* user, const double* x, uint64_t rows, uint64_t n, double* f_out) {
+    CMAES* self = (CMAES*)user;
+    try {
+      py::array_t<double> X({(py::ssize_t)rows, (py::ssize_t)n}, {(py::ssize_t)(n * sizeof(double)), (py::ssize_t)sizeof(double)}, x, py::none());
+      py::array_t<double, py::array::c_style | py::array::forcecast> F(self->objective(X));
+      if ((uint64_t)F.size() != rows) korali_error("The batched model returned %zu values for %zu samples\n", (size_t)F.size(), (size_t)rows);
+      const double* f = F.data();
+      for (uint64_t i = 0; i < rows; i++) f_out[i] = f[i];
+    } catch (const std::exception& e) {
+      self->pending_error = e.what();
+      for (uint64_t i = 0; i < rows; i++) f_out[i] = NAN;
+    }
+  }
+  // korali_b200.batched_device(fn): the wrapper receives raw device pointers and builds zero-copy tensor views itself
+  static void device_objective(void* user, const double* x_dev, uint64_t rows, uint64_t n, uint64_t ldx, double* f_dev, void* stream) {
+    CMAES* self = (CMAES*)user;
+    try {
+      self->objective((uintptr_t)x_dev, rows, n, ldx, (uintptr_t)f_dev, (uintptr_t)stream);
+    } catch (const std::exception& e) {
+      self->pending_error = e.what();
+    }
+  }
 
   static void host_objective(void* user, const double* x, uint64_t rows, uint64_t n, double* f_out) {
     CMAES* self = (CMAES*)user;
@@ -507,6 +543,8 @@ class CMAES {
     }
     if (cfg.objective == KCMA_OBJ_EXTERNAL) {
       if (cfg.use_gradient_information) check(kcma_set_host_objective_grad(h, &CMAES::host_objective_grad, this));
+      else if (batched == "device") check(kcma_set_device_objective(h, &CMAES::device_objective, this));
+      else if (batched == "numpy") check(kcma_set_host_objective(h, &CMAES::host_objective_batched, this));
       else check(kcma_set_host_objective(h, &CMAES::host_objective, this));
     }
     if (!constraints.empty()) check(kcma_set_host_constraints(h, &CMAES::host_constraints, this));

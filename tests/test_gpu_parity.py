@@ -746,6 +746,27 @@ def test_bound_violations_counted_and_resampled_like_the_oracle():
         s.eval(); o.eval(); s.tell(); o.tell()
 
 
+@pytest.mark.parametrize("mirrored", [0, 1])
+@pytest.mark.parametrize("maxres", [1, 7, 40, 41, 200])
+def test_resampling_budget_exhausted_mid_population_like_the_reference(mirrored, maxres):
+    """'Max Infeasible Resamplings' bounds the rejection loop by the CUMULATIVE counter (:459, :490), so when the budget runs out
+    the reference's sample-by-sample order decides which draws are kept: samples before that point are resampled to the end, the
+    one that exhausts the budget keeps an infeasible draw, every later sample keeps its first draw. The device redraws in rounds
+    and settles the budget afterwards (settle_resampling_budget): counter and population must equal the oracle's sequential loop."""
+    kw = dict(n=5, population_size=48, objective="NegSphere", lower_bound=-1.0, upper_bound=1.0, initial_value=0.6, initial_stddev=1.2, seed=17,
+              mirrored_sampling=mirrored, max_infeasible_resamplings=maxres)
+    s = _lib.Solver(keep_population=1, **kw); o = O.Oracle(**kw); o.set_scalar("Oracle/RNG Kind", 1)
+    for g in range(3):
+        s.ask(); o.ask()
+        assert s.scalar("Infeasible Sample Count") == o.scalar("Infeasible Sample Count"), (g, s.scalar("Infeasible Sample Count"), o.scalar("Infeasible Sample Count"))
+        assert relerr(s.get("Sample Population"), o.get("Sample Population")) < 1e-12, g
+        s.eval(); o.eval(); s.tell(); o.tell()
+        assert np.array_equal(s.get_index("Sorting Index"), o.get_index("Sorting Index")), g
+    assert s.scalar("Infeasible Sample Count") >= maxres
+    fin_s, why_s = s.check_termination(); fin_o, why_o = o.check_termination()
+    assert fin_s and fin_o and "Max Infeasible Resamplings" in why_s and why_s == why_o
+
+
 def test_nonfinite_objective_is_an_error():
     """Optimization::evaluate throws on a non-finite F(x) (optimization.cpp.base:32-33)."""
     s = _lib.Solver(n=4, population_size=8, objective="NegEllipsoid", objective_coef=[1.0, 1.0, np.inf, 1.0], initial_value=1.0, initial_stddev=1.0)

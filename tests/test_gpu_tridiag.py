@@ -54,8 +54,12 @@ def test_sytrd_global_memory_variant_matches_register_variant(monkeypatch):
         monkeypatch.setenv("KCMA_SYTRD_RESIDENT", "0")
         d1, e1, tau1, vr1 = _lib.k_sytrd(c)
         sc = lam.max()
-        assert np.abs(d0 - d1).max() <= 1e-12 * sc and np.abs(e0 - e1).max() <= 1e-12 * sc, n
-        assert np.abs(tau0 - tau1).max() <= 1e-8 and np.abs(vr0 - vr1).max() <= 1e-7, n   # round-off grows along the N-1 dependent steps
+        # the ENTRIES of T are not determined to working precision (round-off grows along the N-1 dependent steps), its spectrum is
+        t0 = np.linalg.eigvalsh(np.diag(d0) + np.diag(e0, 1) + np.diag(e0, -1))
+        t1 = np.linalg.eigvalsh(np.diag(d1) + np.diag(e1, 1) + np.diag(e1, -1))
+        assert np.abs(t0 - t1).max() <= 1e-13 * sc and np.abs(t0 - lam).max() <= 1e-13 * sc, n
+        assert np.abs(d0 - d1).max() <= 1e-7 * sc and np.abs(e0 - e1).max() <= 1e-7 * sc, n
+        assert np.abs(tau0 - tau1).max() <= 1e-6 and np.abs(vr0 - vr1).max() <= 1e-6, n
 
 
 def test_sytrd_large_n_streams_from_global_memory():

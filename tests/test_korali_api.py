@@ -339,6 +339,108 @@ def test_device_objective_and_checkpoint_resume(tmp_path):
     assert os.path.exists(str(tmp_path / "run40" / "gen00000040.json"))
 
 
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _from_reference_checkpoint(gen=50):
+    e = korali.Experiment()
+    e["Problem"]["Type"] = "Optimization"
+    e["Problem"]["Objective Function"] = "Sphere"      # the fixture's model: F = -1/2 sum x^2 (checked against its Value Vector)
+    e.loadState(os.path.join(GOLDEN, "reference_gen%08d.json" % gen))
+    e["Console Output"]["Verbosity"] = "Silent"
+    e["File Output"]["Enabled"] = False
+    return e
+
+
+@pytest.mark.skipif(HAS_GPU, reason="CPU-only behaviour")
+def test_reference_written_checkpoint_passes_the_strict_configuration():
+    """A result file the REFERENCE wrote (tests/python/plot/cmaes/gen00000050.json, kept as tests/golden/reference_gen00000050.json)
+    goes through Experiment::loadState + the strict setConfiguration: every key is consumed, so the only thing that stops the
+    run on a CPU-only box is the missing device."""
+    with pytest.raises(RuntimeError, match="no CPU fallback|CUDA device"):
+        korali.Engine().run(_from_reference_checkpoint())
+
+
+@gpu
+def test_resume_from_a_reference_written_checkpoint(tmp_path):
+    """Checkpoint interchange: e.loadState() of a file written by the reference restores its state exactly, the run
+    continues from generation 50 to the file's own Max Generations (100), and the files this build writes carry every key
+    python/korali/plot/CMAES.py:42-55 reads."""
+    ref50 = json.load(open(os.path.join(GOLDEN, "reference_gen00000050.json")))
+    ref100 = json.load(open(os.path.join(GOLDEN, "reference_gen00000100.json")))
+    k = korali.Engine()
+    # (a) nothing left to run: the state that comes back is the file's, bit for bit
+    e = _from_reference_checkpoint()
+    e["Solver"]["Termination Criteria"]["Max Generations"] = 50
+    k.run(e)
+    assert e["Current Generation"] == 50
+    for key in ["Sigma", "Best Ever Value", "Current Best Value", "Previous Best Ever Value", "Conjugate Evolution Path L2 Norm",
+                "Model Evaluation Count", "Infeasible Sample Count", "Maximum Covariance Eigenvalue", "Minimum Covariance Eigenvalue"]:
+        assert e["Solver"][key] == ref50["Solver"][key], key
+    for key in ["Current Mean", "Previous Mean", "Covariance Matrix", "Evolution Path", "Conjugate Evolution Path", "Axis Lengths",
+                "Covariance Eigenvector Matrix", "Best Ever Variables"]:
+        assert np.array_equal(np.array(e["Solver"][key], dtype=float).ravel(), np.array(ref50["Solver"][key], dtype=float).ravel()), key
+    # (b) continue: generations 51..100 on the device (own Philox stream from here on, so the trajectory is statistically, not
+    # numerically, the reference's)
+    e = _from_reference_checkpoint()
+    e["File Output"]["Enabled"] = True
+    e["File Output"]["Path"] = str(tmp_path / "cont")
+    e["File Output"]["Frequency"] = 50
+    k.run(e)
+    assert e["Current Generation"] == 100
+    assert e["Solver"]["Model Evaluation Count"] == ref100["Solver"]["Model Evaluation Count"] == 3200
+    assert e["Solver"]["Best Ever Value"] >= ref50["Solver"]["Best Ever Value"]
+    assert abs(e["Solver"]["Best Ever Value"]) < 1e-7                      # the reference reached -2.8e-10 at generation 100
+    assert 0.05 < e["Solver"]["Sigma"] / ref100["Solver"]["Sigma"] < 20.0
+    # (c) key set of the written result file
+    out = json.load(open(str(tmp_path / "cont" / "gen00000100.json")))
+    assert out["Current Generation"] == 100
+    for key in ["Maximum Covariance Eigenvalue", "Minimum Covariance Eigenvalue", "Current Best Value", "Best Ever Value", "Sigma",
+                "Conjugate Evolution Path L2 Norm", "Axis Lengths", "Current Best Variables", "Best Ever Variables", "Covariance Matrix"]:
+        assert key in out["Solver"], key
+    assert len(out["Solver"]["Covariance Matrix"]) == 100 and len(out["Solver"]["Axis Lengths"]) == 10
+    assert [v["Name"] for v in out["Variables"]] == [v["Name"] for v in ref50["Variables"]]
+    # ... and the reference's own file loads the same way as ours (same top-level layout)
+    assert {"Current Generation", "Solver", "Problem", "Variables", "Random Seed", "Is Finished"} <= set(out) & set(ref100)
+
+
+@gpu
+def test_resume_is_bitwise(tmp_path):
+    """The tridiagonalisation-based eigensolver keeps no history (the one-sided Jacobi was warm-started from the previous basis),
+    and the Philox counters are (seed, generation, sample): a run resumed from a saved state repeats the uninterrupted run bit for
+    bit."""
+    def make(gens):
+        e = korali.Experiment()
+        e["Problem"]["Type"] = "Optimization"
+        e["Problem"]["Objective Function"] = "Ellipsoid"
+        for i in range(40):
+            e["Variables"][i]["Name"] = "X%d" % i
+            e["Variables"][i]["Initial Value"] = 2.0
+            e["Variables"][i]["Initial Standard Deviation"] = 1.0
+        e["Solver"]["Type"] = "Optimizer/CMAES"
+        e["Solver"]["Population Size"] = 96
+        e["Solver"]["Termination Criteria"]["Max Generations"] = gens
+        e["Console Output"]["Verbosity"] = "Silent"
+        e["File Output"]["Path"] = str(tmp_path / ("run%d" % gens))
+        e["File Output"]["Frequency"] = 15
+        e["Random Seed"] = 4242
+        return e
+    k = korali.Engine()
+    full = make(30); k.run(full)
+    part = make(15); k.run(part)
+    r = korali.Experiment()
+    r["Problem"]["Objective Function"] = "Ellipsoid"
+    r.loadState(str(tmp_path / "run15" / "latest"))
+    r["Solver"]["Termination Criteria"]["Max Generations"] = 30
+    r["File Output"]["Enabled"] = False
+    k.run(r)
+    assert r["Current Generation"] == 30
+    for key in ["Sigma", "Best Ever Value", "Current Best Value", "Conjugate Evolution Path L2 Norm"]:
+        assert r["Solver"][key] == full["Solver"][key], key
+    for key in ["Current Mean", "Covariance Matrix", "Evolution Path", "Conjugate Evolution Path", "Best Ever Variables"]:
+        assert r["Solver"][key] == full["Solver"][key], key
+
+
 @gpu
 def test_python_model_matches_device_objective():
     """The batched host conduit (Python model, as the reference's users write it) and the device objective see the same
@@ -361,6 +463,66 @@ def test_python_model_matches_device_objective():
         korali.Engine().run(e)
         res.append((e["Solver"]["Best Ever Value"], e["Solver"]["Sigma"]))
     assert abs(res[0][0] - res[1][0]) <= 1e-9 * abs(res[1][0]) and abs(res[0][1] - res[1][1]) <= 1e-9 * res[1][1]
+
+
+@gpu
+def test_whole_population_models_numpy_and_device_tensor():
+    """user models that take the WHOLE population — korali.batched(fn) gets X as one NumPy array, korali.batched_device(fn)
+    gets a torch tensor that aliases the sample matrix in HBM — against the reference-style per-sample model (lambda Python calls
+    per generation, conduit.cpp.base:29-88). Same samples; the NumPy variants use the same arithmetic, so they agree bit for bit."""
+    def per_sample(s):
+        x = np.asarray(s["Parameters"])
+        s["F(x)"] = float(-np.sum((x - 1.5) ** 2 * np.arange(1, x.size + 1)))
+    calls = {"numpy": 0, "device": 0}
+    def whole_numpy(X):
+        calls["numpy"] += 1
+        assert X.shape == (64, 12)
+        return np.array([float(-np.sum((x - 1.5) ** 2 * np.arange(1, x.size + 1))) for x in X])
+    def whole_device(X):
+        calls["device"] += 1
+        assert X.is_cuda and X.dtype == torch.float64 and tuple(X.shape) == (64, 12)
+        w = torch.arange(1, 13, device=X.device, dtype=torch.float64)
+        return -(((X - 1.5) ** 2) * w).sum(dim=1)
+    res = {}
+    for name, obj in (("per_sample", per_sample), ("numpy", korali.batched(whole_numpy)), ("device", korali.batched_device(whole_device))):
+        e = korali.Experiment()
+        e["Problem"]["Type"] = "Optimization"
+        e["Problem"]["Objective Function"] = obj
+        for i in range(12):
+            e["Variables"][i]["Name"] = "X%d" % i
+            e["Variables"][i]["Initial Value"] = 0.0
+            e["Variables"][i]["Initial Standard Deviation"] = 1.0
+        e["Solver"]["Type"] = "Optimizer/CMAES"
+        e["Solver"]["Population Size"] = 64
+        e["Solver"]["Termination Criteria"]["Max Generations"] = 40
+        e["Console Output"]["Verbosity"] = "Silent"
+        e["File Output"]["Enabled"] = False
+        e["Random Seed"] = 77
+        korali.Engine().run(e)
+        res[name] = (e["Solver"]["Best Ever Value"], e["Solver"]["Sigma"], e["Solver"]["Current Mean"], e["Solver"]["Model Evaluation Count"])
+    assert calls == {"numpy": 40, "device": 40}                      # ONE call per generation
+    assert res["numpy"][:3] == res["per_sample"][:3]                  # same arithmetic on the same samples
+    assert res["device"][3] == res["numpy"][3] == 40 * 64
+    assert abs(res["device"][0] - res["numpy"][0]) <= 1e-9 * abs(res["numpy"][0]) + 1e-12
+    assert abs(res["device"][1] - res["numpy"][1]) <= 1e-8 * res["numpy"][1]
+
+
+@gpu
+def test_device_model_errors_surface():
+    def bad(X):
+        return torch.full((X.shape[0],), float("nan"), device=X.device, dtype=torch.float64)
+    e = base_1d(8, 5)
+    e["Variables"][0]["Initial Value"] = 1.0
+    e["Problem"]["Objective Function"] = korali.batched_device(bad)
+    with pytest.raises(RuntimeError, match="Non finite"):
+        korali.Engine().run(e)
+    def boom(X):
+        raise ValueError("model exploded")
+    e = base_1d(8, 5)
+    e["Variables"][0]["Initial Value"] = 1.0
+    e["Problem"]["Objective Function"] = korali.batched(boom)
+    with pytest.raises(RuntimeError, match="model exploded"):
+        korali.Engine().run(e)
 
 
 # ---------------------------------------------------------------- Use Gradient Information ------------------
