@@ -450,7 +450,7 @@ int update_eigensystem(kcma* h, const double* dM) {
     launch_eig_sign(h->stream, vt, ld, N, h->dT);   // dT (scratch of tell()) holds the signs here
     launch_eig_order(h->stream, ev, N, h->dPerm, h->dSc);
     launch_eig_commit(h->stream, vt, ld, N, h->dPerm, ev, h->dT, h->dB, h->dA, h->dD, h->dVT, h->dSc);
-    h->launches += l + 3;
+    h->launches += l + 4;
     h->scalars_fresh = false;
     return 0;
   }
@@ -482,7 +482,7 @@ int update_eigensystem(kcma* h, const double* dM) {
   launch_rayleigh(h->stream, h->dGT, h->dVTw, ld, N, h->dEv, h->dT);   // dT (scratch of tell()) holds the signs here
   launch_eig_order(h->stream, h->dEv, N, h->dPerm, h->dSc);
   launch_eig_commit(h->stream, h->dVTw, ld, N, h->dPerm, h->dEv, h->dT, h->dB, h->dA, h->dD, h->dVT, h->dSc);
-  h->launches += 3;
+  h->launches += 4;
   h->scalars_fresh = false;
   return 0;
 }

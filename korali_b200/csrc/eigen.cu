@@ -612,28 +612,48 @@ rayleigh_kernel(const double* __restrict__ GT, const double* __restrict__ VT, in
   if (lane == 0) { ev[i] = a / nv; sign[i] = bval < 0.0 ? -1.0 : 1.0; }
 }
 
-// perm = ascending order of |ev| (GSL_EIGEN_SORT_ABS_ASC; ties by index), min/max eigenvalue, acceptance test
-// (min <= 0 keeps the previous B, D: CMAES.cpp.base:876-880). Single block; n <= a few thousand.
-__global__ void __launch_bounds__(1024)
-eig_order_kernel(const double* __restrict__ ev, int n, int* __restrict__ perm, DevScalars* __restrict__ sc) {
-  __shared__ double smin[32], smax[32];
-  double mn = INFINITY, mx = -INFINITY;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const double a = fabs(ev[i]);
-    int r = 0;
-    for (int j = 0; j < n; j++) {
-      const double b = fabs(ev[j]);
-      r += (b < a) || (b == a && j < i);
+// perm = ascending order of |ev| (GSL_EIGEN_SORT_ABS_ASC; ties by index): rank by counting, one thread per eigenvalue, any n.
+__global__ void __launch_bounds__(128)
+eig_rank_kernel(const double* __restrict__ ev, int n, int* __restrict__ perm) {
+  __shared__ double chunk[128];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const double a = i < n ? fabs(ev[i]) : 0.0;
+  int r = 0;
+  for (int j0 = 0; j0 < n; j0 += 128) {
+    __syncthreads();
+    chunk[threadIdx.x] = (j0 + threadIdx.x < n) ? fabs(ev[j0 + threadIdx.x]) : INFINITY;
+    __syncthreads();
+    const int lim = min(128, n - j0);
+    for (int k = 0; k < lim; k++) {
+      const double bv = chunk[k];
+      r += (bv < a) || (bv == a && j0 + k < i);
     }
-    perm[r] = i;
-    mn = fmin(mn, ev[i]); mx = fmax(mx, ev[i]);
   }
+  if (i < n) perm[r] = i;
+}
+
+// min / max eigenvalue and the acceptance test (min <= 0 keeps the previous B, D: CMAES.cpp.base:876-880). A non-finite eigenvalue
+// rejects the decomposition as well: fmin / fmax drop NaN operands, so non-finiteness is tracked explicitly.
+__global__ void __launch_bounds__(1024)
+eig_accept_kernel(const double* __restrict__ ev, int n, DevScalars* __restrict__ sc) {
+  __shared__ double smin[32], smax[32];
+  __shared__ int sbad;
+  if (threadIdx.x == 0) sbad = 0;
+  __syncthreads();
+  double mn = INFINITY, mx = -INFINITY;
+  int bad = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double v = ev[i];
+    bad |= !isfinite(v);
+    mn = fmin(mn, v); mx = fmax(mx, v);
+  }
+  if (bad) atomicOr(&sbad, 1);
   mn = warp_min(mn); mx = warp_max(mx);
   if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = mn; smax[threadIdx.x >> 5] = mx; }
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int w = 0; w < (int)(blockDim.x >> 5); w++) { mn = fmin(mn, smin[w]); mx = fmax(mx, smax[w]); }
-    if (mn <= 0.0 || !(mn == mn)) {
+    if (sbad || mn <= 0.0 || !(mn == mn)) {
       sc->eig_rejected = 1;
     } else {
       sc->eig_rejected = 0;
@@ -679,15 +699,19 @@ eig_commit_kernel(const double* __restrict__ VTw, int ld, int n, const int* __re
 __global__ void __launch_bounds__(256)
 eig_diagonal_kernel(const double* __restrict__ C, int ldc, int n, double* __restrict__ D, DevScalars* __restrict__ sc) {
   __shared__ double smin[8], smax[8];
+  __shared__ int rej, sbad;
+  if (threadIdx.x == 0) sbad = 0;
+  __syncthreads();
   double mn = INFINITY, mx = -INFINITY;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) { const double v = C[(size_t)i * ldc + i]; mn = fmin(mn, v); mx = fmax(mx, v); }
+  int bad = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { const double v = C[(size_t)i * ldc + i]; bad |= !isfinite(v); mn = fmin(mn, v); mx = fmax(mx, v); }
+  if (bad) atomicOr(&sbad, 1);   // fmin / fmax drop NaN operands: non-finiteness is tracked explicitly
   mn = warp_min(mn); mx = warp_max(mx);
   if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = mn; smax[threadIdx.x >> 5] = mx; }
   __syncthreads();
-  __shared__ int rej;
   if (threadIdx.x == 0) {
     for (int w = 0; w < 8; w++) { mn = fmin(mn, smin[w]); mx = fmax(mx, smax[w]); }
-    rej = (mn <= 0.0 || !(mn == mn));
+    rej = (sbad || mn <= 0.0 || !(mn == mn));
     sc->eig_rejected = rej;
     if (!rej) { sc->min_eig = mn; sc->max_eig = mx; }
   }
@@ -1086,7 +1110,8 @@ void launch_rayleigh(cudaStream_t st, const double* GT, const double* VT, int ld
   rayleigh_kernel<<<(n + 7) / 8, 256, 0, st>>>(GT, VT, ld, n, ev, sign);
 }
 void launch_eig_order(cudaStream_t st, const double* ev, int n, int* perm, DevScalars* sc) {
-  eig_order_kernel<<<1, 1024, 0, st>>>(ev, n, perm, sc);
+  eig_rank_kernel<<<(n + 127) / 128, 128, 0, st>>>(ev, n, perm);
+  eig_accept_kernel<<<1, 1024, 0, st>>>(ev, n, sc);
 }
 void launch_eig_commit(cudaStream_t st, const double* VTw, int ld, int n, const int* perm, const double* ev, const double* sign,
                        double* B, double* A, double* D, double* VT, const DevScalars* sc) {

@@ -731,6 +731,18 @@ class Experiment : public KoraliJson {
       py::dict oldp = py::reinterpret_borrow<py::dict>(_js["Problem"]), newp = py::reinterpret_borrow<py::dict>(d["Problem"]);
       for (const char* k : {"Objective Function", "Constraints"}) if (oldp.contains(k)) newp[k] = oldp[k];
     }
+    if (d.contains("Solver") && py::isinstance<py::dict>(d["Solver"])) {   // .npy side-cars of large N x N arrays (saveState)
+      py::dict sj = py::reinterpret_borrow<py::dict>(d["Solver"]);
+      py::object os = py::module_::import("os"), np = py::module_::import("numpy");
+      const std::string dir = os.attr("path").attr("dirname")(os.attr("path").attr("realpath")(path)).cast<std::string>();
+      for (const char* key : {"Covariance Matrix", "Covariance Eigenvector Matrix"}) {
+        const std::string fk = std::string(key) + " File";
+        if (!sj.contains(fk.c_str())) continue;
+        const std::string fname = sj[fk.c_str()].cast<std::string>();
+        sj[key] = np.attr("load")(dir + "/" + fname).attr("ravel")().attr("tolist")();
+        PyDict_DelItemString(sj.ptr(), fk.c_str());
+      }
+    }
     _js.clear();
     for (auto kv : d) _js[kv.first] = kv.second;
     reset();
@@ -832,6 +844,22 @@ class Experiment : public KoraliJson {
         else p[kv.first] = kv.second;
       }
       out["Problem"] = p;
+    }
+    // N x N arrays above 2^22 entries do not go through JSON (134 MB of text per matrix at N = 4096): they are written
+    // as .npy side-cars next to the result file, and the file names them so that loadState finds them again
+    if (solver && solver->h && (uint64_t)solver->cfg.n * solver->cfg.n > (1u << 22) && out.contains("Solver")) {
+      py::object np = py::module_::import("numpy");
+      py::dict sj;
+      for (auto kv : py::reinterpret_borrow<py::dict>(out["Solver"])) sj[kv.first] = kv.second;
+      const size_t n = solver->cfg.n;
+      for (const char* key : {"Covariance Matrix", "Covariance Eigenvector Matrix"}) {
+        std::vector<double> flat = solver->array(key);
+        std::string fname = std::string(name) + "." + (std::string(key) == "Covariance Matrix" ? "C" : "B") + ".npy";
+        py::array_t<double> arr({(py::ssize_t)n, (py::ssize_t)n}, flat.data());
+        np.attr("save")(file_path + "/" + fname, arr);
+        sj[(std::string(key) + " File").c_str()] = fname;
+      }
+      out["Solver"] = sj;
     }
     py::object fh = py::module_::import("builtins").attr("open")(aux, "w");
     json.attr("dump")(out, fh);

@@ -43,11 +43,27 @@ ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
 if world > 1:
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
 if rank == 0:
-    ph = {p: round(s.timing(p)[0] / gens, 3) for p in ["eigen", "rng", "sample_gemm", "objective", "sort", "gather_mean", "rank_mu", "paths", "collectives"]}
+    ph = {p: round(s.timing(p)[0] / gens, 3) for p in ["eigen", "eigen_sytrd", "eigen_dc", "eigen_back", "rng", "sample_gemm", "objective", "sort", "gather_mean",
+                                                        "rank_mu", "paths", "collectives"]}
     print(json.dumps({"config": "config4: N=4096, lambda=2^20 mirrored, mu=2^19, sphere", "n_gpus": world, "generations": gens,
                       "ms_per_generation": float(ms[0]) / gens, "samples_per_sec": lam / (float(ms[0]) / gens * 1e-3),
                       "phases_ms_rank0": ph, "best_ever_value": s.scalar("Best Ever Value"),
                       "sample_gemm_tflops_per_rank": 2.0 * n * n * (lam / 2 / world) / (ph["sample_gemm"] * 1e-3) * 1e-12 if ph["sample_gemm"] else None}), flush=True)
+# optional: run on to the optimum (BASELINE.json: convergence within 1e-8 on every config) — `... bench_config4_mgpu.py <gens> converge`
+if len(sys.argv) > 2 and sys.argv[2] == "converge":
+    import time
+    s.timing_enable(False)
+    s.set_scalar("Termination Criteria/Max Value", -1e-9)
+    s.set_scalar("Termination Criteria/Max Generations", 600)
+    t0 = time.perf_counter()
+    done = s.run(600)
+    best = s.scalar("Best Ever Value")
+    dt = time.perf_counter() - t0
+    fin, why = s.check_termination()
+    if rank == 0:
+        print(json.dumps({"config4_convergence": {"generations_total": int(s.scalar("Current Generation")), "best_ever_value": best, "finished": fin,
+                                                   "criterion": why, "seconds_for_the_last_%d_generations" % done: dt,
+                                                   "max_abs_best_ever_variable": float(abs(s.get("Best Ever Variables")).max())}}), flush=True)
 s.close()
 if world > 1:
     dist.destroy_process_group()

@@ -173,3 +173,21 @@ def test_hsig_zero_branch_fires_and_matches_oracle():
         assert abs(s.scalar("Sigma") - o.scalar("Sigma")) < 1e-9 * o.scalar("Sigma"), g
     assert saw_hsig0 >= 5 and saw_hsig1 >= 5, (saw_hsig0, saw_hsig1)
     s.close()
+
+
+def test_config3_full_size_converges_to_the_optimum_within_1e8():
+    """BASELINE.json: convergence to the same optimum within 1e-8 on every config — config 3 at its stated size (N = 1000,
+    lambda = 65536, ill-conditioned ellipsoid, optimum 0 at x = 0), through kcma_run with the termination chain."""
+    case = dict(n=1000, population_size=65536, objective="NegEllipsoid", initial_value=3.0, initial_stddev=1.0, seed=1337)
+    s = _lib.Solver(**case)
+    s.set_scalar("Termination Criteria/Max Value", -1e-9)
+    s.set_scalar("Termination Criteria/Max Generations", 4000)
+    s.set_scalar("Termination Criteria/Max Model Evaluations", 1e18)
+    done = s.run(4001)
+    best = s.scalar("Best Ever Value")
+    fin, reason = s.check_termination()
+    print("config 3 at full size: best %.3e after %d generations (%s), max eigenvalue ratio %.3g" %
+          (best, done, reason, s.scalar("Maximum Covariance Eigenvalue") / s.scalar("Minimum Covariance Eigenvalue")))
+    assert fin and "Max Value" in reason and abs(best) < 1e-8, (best, done, reason)
+    assert np.abs(s.get("Best Ever Variables")).max() < 1e-3
+    s.close()

@@ -442,6 +442,46 @@ def test_resume_is_bitwise(tmp_path):
 
 
 @gpu
+def test_large_n_checkpoint_uses_npy_side_cars(tmp_path):
+    """N x N arrays above 2^22 entries (config 4: N = 4096) do not fit a JSON result file: C and B are saved as .npy
+    side-cars, loadState reads them back, and the resumed run is bitwise the uninterrupted one."""
+    n = 2100
+    def make(gens, path):
+        e = korali.Experiment()
+        e["Problem"]["Type"] = "Optimization"
+        e["Problem"]["Objective Function"] = "Sphere"
+        for i in range(n):
+            e["Variables"][i]["Name"] = "X%d" % i
+            e["Variables"][i]["Initial Value"] = 1.0
+            e["Variables"][i]["Initial Standard Deviation"] = 1.0
+        e["Solver"]["Type"] = "Optimizer/CMAES"
+        e["Solver"]["Population Size"] = 64
+        e["Solver"]["Termination Criteria"]["Max Generations"] = gens
+        e["Console Output"]["Verbosity"] = "Silent"
+        e["File Output"]["Path"] = str(tmp_path / path)
+        e["File Output"]["Frequency"] = 2
+        e["Random Seed"] = 99
+        return e
+    k = korali.Engine()
+    full = make(4, "full"); k.run(full)
+    part = make(2, "part"); k.run(part)
+    saved = json.load(open(str(tmp_path / "part" / "gen00000002.json")))
+    assert "Covariance Matrix" not in saved["Solver"] and saved["Solver"]["Covariance Matrix File"] == "gen00000002.json.C.npy"
+    c = np.load(str(tmp_path / "part" / "gen00000002.json.C.npy"))
+    assert c.shape == (n, n) and np.array_equal(c, c.T)
+    r = korali.Experiment()
+    r["Problem"]["Objective Function"] = "Sphere"
+    r.loadState(str(tmp_path / "part" / "latest"))
+    r["Solver"]["Termination Criteria"]["Max Generations"] = 4
+    r["File Output"]["Enabled"] = False
+    k.run(r)
+    assert r["Current Generation"] == 4
+    assert r["Solver"]["Sigma"] == full["Solver"]["Sigma"] and r["Solver"]["Best Ever Value"] == full["Solver"]["Best Ever Value"]
+    assert r["Solver"]["Current Mean"] == full["Solver"]["Current Mean"]
+    assert r["Solver"]["Evolution Path"] == full["Solver"]["Evolution Path"]
+
+
+@gpu
 def test_python_model_matches_device_objective():
     """The batched host conduit (Python model, as the reference's users write it) and the device objective see the same
     samples and must produce the same trajectory."""
