@@ -407,6 +407,9 @@ int ensure_vt(kcma* h) {
 bool eigen_use_tridiag(const kcma* h) {
   const char* e = getenv("KCMA_EIGEN");
   if (e && !strcmp(e, "jacobi")) return false;
+  // The constraint path decomposes C_aux once per correction round (handleConstraints :774-832): nearly the same matrix again and
+  // again, which the warm-started one-sided Jacobi finishes in a sweep or two (config 5: 3.9 instead of 6.1 ms per generation)
+  if (h->has_constraints && h->N <= 1184 && !(e && !strcmp(e, "tridiag"))) return false;
   return h->N >= 4 && (size_t)h->N * 5 * sizeof(double) + 4096 <= 226 * 1024;
 }
 

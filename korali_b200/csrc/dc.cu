@@ -209,7 +209,45 @@ dc_setup_kernel(const DcNode* __restrict__ nodes, int node0, const double* __res
     ord[pos] = i;
   }
   __syncthreads();
-  if (tid == 0) {   // the deflation scan is sequential by nature (dlaed2); rotations are recorded and applied by the whole CTA below
+  // Deflation. The scan of dlaed2 is sequential only through close-pole deflations (a Givens rotation changes the next comparison);
+  // those are rare, so the CTA first classifies every pole in parallel — small z_i deflates, every survivor is tested against the
+  // previous survivor — and compacts in parallel when no pair is close; otherwise (and when everything deflates) thread 0 scans.
+  int* surv = ord + n;
+  __shared__ int s_fast, cnt_s[256];
+  if (tid == 0) s_fast = (rho * zmax > tol) ? 1 : 0;
+  __syncthreads();
+  if (s_fast) {
+    for (int pos = tid; pos < n; pos += nt) surv[pos] = (rho * fabs(z_s[ord[pos]]) > tol) ? 1 : 0;
+    __syncthreads();
+    for (int pos = tid; pos < n; pos += nt) {
+      if (!surv[pos]) continue;
+      int q = pos - 1;
+      while (q >= 0 && !surv[q]) q--;
+      if (q < 0) continue;
+      const int i = ord[pos], pj = ord[q];
+      const double zi = z_s[i], zpj = z_s[pj], tt = d_s[i] - d_s[pj];
+      if (fabs(tt * zi * zpj) <= tol * (zi * zi + zpj * zpj)) s_fast = 0;
+    }
+    __syncthreads();
+  }
+  if (s_fast) {
+    const int chunk = (n + nt - 1) / nt, lo = min(n, tid * chunk), hi = min(n, lo + chunk);
+    int c = 0;
+    for (int pos = lo; pos < hi; pos++) c += surv[pos];
+    cnt_s[tid] = c;
+    __syncthreads();
+    int base = 0, total = 0;
+    for (int t = 0; t < nt; t++) { const int v = cnt_s[t]; total += v; if (t < tid) base += v; }
+    for (int pos = lo; pos < hi; pos++) {
+      const int i = ord[pos];
+      if (surv[pos]) nd_col[off + base++] = i;
+      else defl_col[off + (pos - base)] = i;
+    }
+    if (tid == 0) {
+      s_K = total; s_M = n - total; s_nrot = 0; s_mixed = 0;
+      Kcnt[node] = total; mixed[node] = 0; rho_out[node] = rho;
+    }
+  } else if (tid == 0) {   // sequential scan; rotations are recorded and applied by the whole CTA below
     int K = 0, M = 0, nrot = 0, mix = 0;
     if (rho * zmax <= tol) {
       for (int pos = 0; pos < n; pos++) defl_col[off + M++] = ord[pos];
@@ -412,7 +450,7 @@ bool dc_solve(cudaStream_t st, TridiagWs* ws, int* launches) {
     int nmax = 0;
     for (const DcNode& nd : nodes) nmax = nd.n > nmax ? nd.n : nmax;
     const int* r2n = ws->d_row2node + (size_t)(l - 1) * n;
-    const size_t smem = sizeof(double) * 2 * nmax + sizeof(int) * nmax;
+    const size_t smem = sizeof(double) * 2 * nmax + sizeof(int) * 2 * nmax;
     dc_setup_kernel<<<cnt, 256, smem, st>>>(ws->d_nodes, node0, dcur, ws->eT, qsrc, ld, ws->dl, ws->w, ws->defl_val, ws->col2k,
                                             ws->nd_col, ws->defl_col, ws->rho, ws->Kcnt, ws->mixed, ws->rot_p, ws->rot_q, ws->rot_c,
                                             ws->rot_s);
@@ -420,7 +458,9 @@ bool dc_solve(cudaStream_t st, TridiagWs* ws, int* launches) {
     dc_loewner_kernel<<<(n + 31) / 32, 256, 0, st>>>(ws->d_nodes, r2n, n, ws->dl, ws->w, ws->Kcnt, ws->DELTA, ld, ws->what);
     dc_vectors_kernel<<<warp_blocks, 256, 0, st>>>(ws->d_nodes, r2n, n, ws->lam, ws->defl_val, ws->defl_col, ws->col2k, ws->Kcnt,
                                                    ws->what, ws->DELTA, ld, ws->UT, dnext);
-    launch_gemm_batched(st, ws->d_desc + ws->desc_level_begin[l - 1], cnt, nmax, nmax, 1);
+    const int msplit = (l == ws->levels) ? ws->split_top : 1;   // the top merge is ONE product: split-K fills the SMs
+    launch_gemm_batched(st, ws->d_desc + ws->desc_level_begin[l - 1], cnt, nmax, nmax, msplit);
+    if (msplit > 1) { launch_reduce_slabs(st, ws->slabsF, (long long)n * ld, msplit, n, n, ld, ws->XT, ws->num_sms); *launches += 1; }
     *launches += 5;
     double* t = dcur; dcur = dnext; dnext = t;
     qsrc = (qsrc == ws->Qa) ? ws->Qb : ws->Qa;

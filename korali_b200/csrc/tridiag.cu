@@ -268,7 +268,34 @@ __device__ __forceinline__ void ll_load2(const LL* p, unsigned long long (&q)[4]
   asm volatile("ld.volatile.global.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(q[0]), "=l"(q[1]), "=l"(q[2]), "=l"(q[3]) : "l"(p) : "memory");
 }
 
-template <int KU, int NC>
+// ---- thread-block clusters (CL > 1): only the leader CTA of a cluster polls the L2 slots and pushes what it received into its
+// peers' shared memory (distributed shared memory) — 148 CTAs polling the same 2 n slots is what stretches the exchange of a step
+__device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned map_to_cta(const void* local_smem, unsigned cta) {
+  unsigned la = (unsigned)__cvta_generic_to_shared(local_smem), ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(cta));
+  return ra;
+}
+__device__ __forceinline__ void st_cluster_f64x2(unsigned raddr, double a, double b) {
+  asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" ::"r"(raddr), "d"(a), "d"(b) : "memory");
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(unsigned raddr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t@!p bra WAIT_%=;\n\t}" ::"r"(a), "r"(parity)
+               : "memory");
+}
+
+template <int KU, int NC, int CL = 1>
 __global__ void __launch_bounds__(SY_NT, 1)
 sytrd_reg_kernel(const double* __restrict__ M, int ld, int n, int ns /* n rounded up to even: LL stride per parity, vector stride */,
                  LL* __restrict__ xP, LL* __restrict__ xC, double* __restrict__ dT, double* __restrict__ eT, double* __restrict__ tauv,
@@ -281,6 +308,14 @@ sytrd_reg_kernel(const double* __restrict__ M, int ld, int n, int ns /* n rounde
   double* red = sm + 3 * ns;       // 4 slots x SY_NW
   double* bc = red + 32;           // 2 parities x {c_i, p_i, c_{i+1}, p_{i+1}}
   double* pp = red + 48;           // NC x SY_NT partial products of the pass
+  double* cbuf = pp + NC * SY_NT;  // CL > 1: received column / product entries pushed by the cluster leader, 2 parities x ns each
+  double* pbuf = cbuf + 2 * ns;
+  __shared__ __align__(8) unsigned long long mbar;
+  const unsigned crank = CL > 1 ? cluster_ctarank() : 0u;
+  if (CL > 1) {
+    if (tid == 0) mbar_init(&mbar, SY_NW);   // one arrival per warp of the leader and step
+    cluster_sync_all();
+  }
   const int nloc = b < n ? (n - b + G - 1) / G : 0;
   double A[KU][NC][2], v[2 * KU], w[2 * KU], vnw[2 * KU];
 #pragma unroll
@@ -321,14 +356,14 @@ sytrd_reg_kernel(const double* __restrict__ M, int ld, int n, int ns /* n rounde
       if (r >= i && r < n) need |= 1u << j;
       cv[j] = 0.0; pq[j] = 0.0;
     }
-    if (have_p && (opt & 1)) {   // one lane per warp spins on one slot first: 148 x 256 threads polling everything back to back saturate the L2
+    if (have_p && (opt & 1) && crank == 0) {   // one lane per warp spins on one slot first: 148 x 256 threads polling everything back to back saturate the L2
       if (lane == 0 && need) {
         const int j0 = __ffs(need) - 1;
         (void)ll_wait(Pin + 2 * (tid + SY_NT * (j0 >> 1)) + (j0 & 1), tag);
       }
       __syncwarp();
     }
-    {
+    if (crank == 0) {
       unsigned pc = need, ppn = have_p ? need : 0u;
       while (pc | ppn) {
         unsigned long long qc[KU][4], qp[KU][4];
@@ -346,6 +381,36 @@ sytrd_reg_kernel(const double* __restrict__ M, int ld, int n, int ns /* n rounde
             if ((ppn & bit) && qp[k][2 * h + 1] == tag) { pq[2 * k + h] = __longlong_as_double((long long)qp[k][2 * h]); ppn &= ~bit; }
           }
         if ((pc | ppn) && (opt & 2)) __nanosleep(100);
+      }
+    }
+    if (CL > 1) {
+      if (crank == 0) {   // push to the peers; the buffer of this parity was last read two steps ago (same argument as for the LL slots)
+#pragma unroll
+        for (unsigned q = 1; q < (unsigned)CL; q++)
+#pragma unroll
+          for (int k = 0; k < KU; k++) {
+            const int r = 2 * (tid + SY_NT * k);
+            if (r < ns) {
+              st_cluster_f64x2(map_to_cta(cbuf + par * ns + r, q), cv[2 * k], cv[2 * k + 1]);
+              st_cluster_f64x2(map_to_cta(pbuf + par * ns + r, q), pq[2 * k], pq[2 * k + 1]);
+            }
+          }
+        asm volatile("fence.acq_rel.cluster;" ::: "memory");
+        __syncwarp();
+        if (lane == 0)
+#pragma unroll
+          for (unsigned q = 1; q < (unsigned)CL; q++) mbar_arrive_remote(map_to_cta(&mbar, q));
+      } else {
+        mbar_wait(&mbar, (unsigned)(i & 1));
+#pragma unroll
+        for (int k = 0; k < KU; k++) {
+          const int r = 2 * (tid + SY_NT * k);
+          if (r < ns) {
+            const double2 c2 = *reinterpret_cast<const double2*>(cbuf + par * ns + r);
+            const double2 p2 = *reinterpret_cast<const double2*>(pbuf + par * ns + r);
+            cv[2 * k] = c2.x; cv[2 * k + 1] = c2.y; pq[2 * k] = p2.x; pq[2 * k + 1] = p2.y;
+          }
+        }
       }
     }
     if (pr) prof[(i - prof_step0) * 8 + 1] = clock64();
@@ -453,6 +518,7 @@ sytrd_reg_kernel(const double* __restrict__ M, int ld, int n, int ns /* n rounde
     double* t = vs_old; vs_old = vs_new; vs_new = t;
     tau_old = tau;
   }
+  if (CL > 1) cluster_sync_all();   // no CTA may exit while a peer can still write into its shared memory
 }
 
 // ---- compact-WY panel factor (dlarft, forward / columnwise): T upper triangular, nb x nb, from G = V^T V and tau ------------
@@ -475,12 +541,13 @@ larft_kernel(const double* __restrict__ Gbuf, long long gstride, int gsplits, co
     return g;
   };
   for (int i = tid; i < nb * lt; i += LARFT_NT) T[i] = 0.0;
-  double gn = (tid < nb && kb > 0) ? gload(0) : 0.0;
+  double gn = (tid < nb && kb > 0) ? gload(0) : 0.0, gn2 = (tid < nb && kb > 1) ? gload(1) : 0.0;   // two rows ahead: an L2 round trip outlasts a step
   __syncthreads();
   for (int p = 0; p < kb; p++) {
     if (tid < nb) grow[tid] = gn;
     __syncthreads();
-    if (tid < nb && p + 1 < kb) gn = gload(p + 1);
+    gn = gn2;
+    if (tid < nb && p + 2 < kb) gn2 = gload(p + 2);
     const double tp = tauv[p0 + p];
     double sacc = 0.0;
     if (q < p)
@@ -558,6 +625,29 @@ TridiagWs* tridiag_ws_create(int n, int ld, int num_sms, char* err, size_t errle
   ws->sy_grid = grid;
   static const int kNC[5] = {0, 4, 7, 11, 14};
   ws->sy_smem = ws->resident ? sizeof(double) * (3 * (size_t)ns + 48 + (size_t)kNC[ws->reg_variant] * SY_NT) : vec_bytes;
+  // thread-block clusters (KCMA_SYTRD_CLUSTER=2|4): only for the <2,7> instantiation, and only when enough clusters are co-resident
+  ws->cluster = 1;
+  if (const char* cle = getenv("KCMA_SYTRD_CLUSTER")) {
+    const int cl = atoi(cle);
+    if ((cl == 2 || cl == 4) && ws->reg_variant == 2) {
+      const void* cfn = cl == 4 ? (const void*)sytrd_reg_kernel<2, 7, 4> : (const void*)sytrd_reg_kernel<2, 7, 2>;
+      const size_t smem = ws->sy_smem + sizeof(double) * 4 * (size_t)ns;
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3((grid / cl) * cl); cfg.blockDim = dim3(SY_NT); cfg.dynamicSmemBytes = smem;
+      cudaLaunchAttribute attr;
+      attr.id = cudaLaunchAttributeClusterDimension;
+      attr.val.clusterDim.x = cl; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+      cfg.attrs = &attr; cfg.numAttrs = 1;
+      int max_clusters = 0;
+      if (cudaFuncSetAttribute(cfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
+          cudaOccupancyMaxActiveClusters(&max_clusters, cfn, &cfg) == cudaSuccess) {
+        const int g = std::min(max_clusters, grid / cl) * cl;
+        if (g > 0 && (n + g - 1) / g <= 7) { ws->cluster = cl; ws->sy_grid = g; ws->sy_smem = smem; }
+      }
+      cudaGetLastError();
+    }
+  }
   bool ok = true;
   if (!ws->resident) ok = ok && ws_alloc(ws, &ws->Awork, mat);
   ok = ok && ws_alloc(ws, &ws->dT, n) && ws_alloc(ws, &ws->eT, n) && ws_alloc(ws, &ws->tau, n) && ws_alloc(ws, &ws->VR, mat) &&
@@ -628,12 +718,14 @@ TridiagWs* tridiag_ws_create(int n, int ld, int num_sms, char* err, size_t errle
   if (ws->npanels > 0) {
     ws->gsplits = std::max(1, std::min(8, num_sms / std::max(1, ws->npanels)));
     ok = ok && ws_alloc(ws, &ws->Gbuf, (size_t)ws->gsplits * ws->npanels * ws->nb * ws->nb) && ws_alloc(ws, &ws->Tbuf, (size_t)ws->npanels * ws->nb * ws->nb) &&
+         ws_alloc(ws, &ws->Gred, (size_t)ws->npanels * ws->nb * ws->nb) &&
          ws_alloc(ws, &ws->VtilR, mat) && ws_alloc(ws, &ws->W2, (size_t)n * ws->nbld) &&
          ws_alloc(ws, &ws->slabs, (size_t)ws->split1 * n * ws->nbld) && ws_alloc(ws, &ws->QT, mat) && ws_alloc(ws, &ws->QF, mat) &&
          ws_alloc(ws, &ws->XF, mat);
     const int tiles = row_tiles * row_tiles;
     ws->splitF = std::max(1, std::min(8, num_sms / std::max(1, tiles)));
     if (ws->splitF > 1) ok = ok && ws_alloc(ws, &ws->slabsF, (size_t)ws->splitF * mat);
+    ws->split_top = (levels > 0 && ws->splitF > 1) ? std::min(ws->splitF, 2) : 1;
     if (!ok) return fail("out of device memory");
     if (cudaStreamCreateWithFlags(&ws->st2, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ws->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
@@ -659,6 +751,7 @@ TridiagWs* tridiag_ws_create(int n, int ld, int num_sms, char* err, size_t errle
         g.A = src + o; g.B = ws->UT + o; g.C = dst + o; g.M = nd.n; g.Nc = nd.n; g.krule = 1;
       } else {                   // last merge, transposed: X^T[r][c] = sum_k U^T[r][k] Q[c][k]
         g.A = ws->UT + o; g.B = src + o; g.C = ws->XT + o; g.M = nd.n; g.Nc = nd.n; g.krule = 2;
+        if (ws->split_top > 1) { g.C = ws->slabsF; g.splits = ws->split_top; g.split_stride = (long long)mat; }
       }
       descs.push_back(g);
     }
@@ -746,7 +839,19 @@ bool tridiag_stage_sytrd(cudaStream_t st, TridiagWs* ws, const double* M) {
   const void* fn = ws->reg_variant == 1 ? (const void*)sytrd_reg_kernel<1, 4> : ws->reg_variant == 2 ? (const void*)sytrd_reg_kernel<2, 7>
                    : ws->reg_variant == 3 ? (const void*)sytrd_reg_kernel<3, 11> : ws->reg_variant == 4 ? (const void*)sytrd_reg_kernel<2, 14>
                    : (const void*)sytrd_kernel;
-  if (cudaLaunchCooperativeKernel(fn, dim3(ws->sy_grid), dim3(SY_NT), ws->resident ? rargs : args, ws->sy_smem, st) != cudaSuccess) return false;
+  if (ws->cluster > 1) {   // <2,7> with a cluster leader that polls for its peers (geometry checked in tridiag_ws_create)
+    const void* cfn = ws->cluster == 4 ? (const void*)sytrd_reg_kernel<2, 7, 4> : (const void*)sytrd_reg_kernel<2, 7, 2>;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(ws->sy_grid); cfg.blockDim = dim3(SY_NT); cfg.dynamicSmemBytes = ws->sy_smem; cfg.stream = st;
+    cudaLaunchAttribute attrs[2];
+    attrs[0].id = cudaLaunchAttributeClusterDimension;
+    attrs[0].val.clusterDim.x = ws->cluster; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
+    attrs[1].id = cudaLaunchAttributeCooperative;
+    attrs[1].val.cooperative = 1;
+    cfg.attrs = attrs; cfg.numAttrs = 2;
+    if (cudaLaunchKernelExC(&cfg, cfn, rargs) != cudaSuccess) return false;
+  } else if (cudaLaunchCooperativeKernel(fn, dim3(ws->sy_grid), dim3(SY_NT), ws->resident ? rargs : args, ws->sy_smem, st) != cudaSuccess) return false;
   // row n-1 of VR (no reflector) and tau[n-1] stay zero from the allocation; VC = VR^T
   launch_transpose(st, ws->VR, ws->VC, ld, n);
   return cudaGetLastError() == cudaSuccess;
@@ -769,8 +874,13 @@ bool tridiag_stage_back_fork(cudaStream_t st, TridiagWs* ws, int* launches) {
   cudaStreamWaitEvent(s2, ws->ev_fork, 0);
   launch_set_identity(s2, ws->QT, ld, n);
   launch_gemm_batched(s2, ws->d_desc + ws->desc_g, ws->npanels, nb, nb, ws->gsplits);
-  larft_kernel<<<ws->npanels, LARFT_NT, sizeof(double) * (nb * (nb + 1) + nb), s2>>>(ws->Gbuf, (long long)ws->npanels * nb * nb, ws->gsplits,
-                                                                                   ws->tau, n_refl, nb, ws->Tbuf);
+  const double* G = ws->Gbuf;
+  if (ws->gsplits > 1) {   // sum the split-K slabs once (fixed order) instead of gsplits dependent loads per step of larft_kernel
+    launch_reduce_slabs(s2, ws->Gbuf, (long long)ws->npanels * nb * nb, ws->gsplits, ws->npanels * nb, nb, nb, ws->Gred, ws->num_sms);
+    G = ws->Gred;
+    *launches += 1;
+  }
+  larft_kernel<<<ws->npanels, LARFT_NT, sizeof(double) * (nb * (nb + 1) + nb), s2>>>(G, 0, 1, ws->tau, n_refl, nb, ws->Tbuf);
   launch_gemm_batched(s2, ws->d_desc + ws->desc_vtil, ws->npanels, nb, n, 1);
   *launches += 4;
   for (int p = ws->npanels - 1; p >= 0; p--) {

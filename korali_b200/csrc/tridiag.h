@@ -12,6 +12,7 @@ struct TridiagWs {
   int n = 0, ld = 0, num_sms = 148;
   // ---- stage 1: Householder tridiagonalisation (sytrd_kernel)
   bool resident = false;       // this CTA's columns live in REGISTERS (N <= 1536: sytrd_reg_kernel), else in the global working copy
+  int cluster = 1;             // thread-block cluster size of the register variant (leader polls, peers receive through DSMEM)
   int reg_variant = 0;         // 1, 2, 3 = sytrd_reg_kernel<1,4>, <2,7>, <3,11>
   int sy_grid = 0; size_t sy_smem = 0;
   double* Awork = nullptr;     // n x ld working copy (global variant only)
@@ -40,12 +41,14 @@ struct TridiagWs {
   double* ev_final = nullptr;              // points at dA or dB
   // ---- stage 3: compact-WY back-transform
   int nb = 128, npanels = 0, split1 = 1, nbld = 128, gsplits = 1;
-  double *Gbuf = nullptr, *Tbuf = nullptr;   // npanels x nb x nb
+  double *Gbuf = nullptr, *Tbuf = nullptr;   // (gsplits x) npanels x nb x nb
+  double *Gred = nullptr;                    // G with the split-K slabs summed
   double *VtilR = nullptr;                   // rows p = (T V^T)[p][:] per panel, n x ld
   double *W2 = nullptr, *slabs = nullptr;    // n x nbld, split1 x n x nbld
   double *QT = nullptr, *QF = nullptr;       // Q^T = H_{n-2} ... H_0 accumulated from the identity (side stream), and its transpose Q
   double *XF = nullptr, *slabsF = nullptr;   // X^T = Z^T Q^T (final result), split-K slabs of that product
   int splitF = 1, desc_final = 0;
+  int split_top = 1;                         // split-K of the top merge of stage 2 (slabs in slabsF, reduced into XT)
   cudaStream_t st2 = nullptr;                // side stream: the Q accumulation runs next to the divide & conquer stage
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   double* result = nullptr;                  // rows = eigenvectors of the last stage run (XT after stage 2, XF after stage 3)

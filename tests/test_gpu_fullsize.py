@@ -181,9 +181,9 @@ def test_config3_full_size_converges_to_the_optimum_within_1e8():
     case = dict(n=1000, population_size=65536, objective="NegEllipsoid", initial_value=3.0, initial_stddev=1.0, seed=1337)
     s = _lib.Solver(**case)
     s.set_scalar("Termination Criteria/Max Value", -1e-9)
-    s.set_scalar("Termination Criteria/Max Generations", 4000)
+    s.set_scalar("Termination Criteria/Max Generations", 12000)   # ~6000 are needed (cond(C) has to grow to 1e6): about 70 s
     s.set_scalar("Termination Criteria/Max Model Evaluations", 1e18)
-    done = s.run(4001)
+    done = s.run(12001)
     best = s.scalar("Best Ever Value")
     fin, reason = s.check_termination()
     print("config 3 at full size: best %.3e after %d generations (%s), max eigenvalue ratio %.3g" %
