@@ -5,6 +5,9 @@ over --gpus N B200s of one box (strong scaling: the population is fixed, each ra
 
 A "step" is one full generation of the hot path: eigendecomposition, Philox sampling, sampling GEMM, batched
 objective, ranking, mean/path updates, rank-mu covariance update (+ all-gather(F) and all-reduce(C partial) for N > 1).
+Legs: `value` = the shipped path (CUDA-graph replay on one GPU), the same generations again with eager launches
+and phase timers (roofline, phases), `e2e` through korali_b200.Engine().run(e) (k["Conduit"]["Devices"] = N), `parity_vs_n1` for N > 1,
+`cpu_baseline` on a bounded sample; `--impl reference` times REAL full-size generations of the reference algorithm on the host.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 Under torchrun (N > 1) every rank runs this file; rank 0 prints ONE JSON line.
@@ -385,8 +388,9 @@ def ours_arm(args, rank, world):
         "gens_per_sec_excluding_eigen": 1e3 / max(ms_eager / args.steps - eig_ms, 1e-9),
     }
     if tridiag:
-        line["eigen"] = {"solver": "Householder tridiagonalisation (sytrd_kernel: one persistent cooperative launch, matrix resident in shared memory, "
-                                   "one LL all-to-all exchange per column) + divide & conquer (dc.cu) + compact-WY back-transform on DMMA GEMMs; replicated on every rank",
+        line["eigen"] = {"solver": "Householder tridiagonalisation (sytrd_reg_kernel: one persistent cooperative launch, trailing matrix resident in the register "
+                                   "files of all SMs, one LL all-to-all exchange through L2 per column) + divide & conquer (dc.cu) + compact-WY back-transform on "
+                                   "DMMA GEMMs (Q accumulated on a side stream beside the divide & conquer stage); replicated on every rank",
                          "avg_ms": eig_ms, "sytrd_ms": phases["eigen_sytrd"][0] / args.steps, "dc_ms": phases["eigen_dc"][0] / args.steps,
                          "back_transform_ms": phases["eigen_back"][0] / args.steps,
                          "bound": "latency: N-1 dependent Householder steps, each one exchange through L2",

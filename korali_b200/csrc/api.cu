@@ -299,6 +299,10 @@ __global__ void transpose_kernel(const double* __restrict__ in, double* __restri
 }
 
 __global__ void copy_sigma_kernel(const DevScalars* sc, double* out) { *out = sc->sigma; }
+__global__ void fold_error_flag_kernel(double* slot, DevScalars* sc, int unfold) {
+  if (!unfold) *slot = sc->nonfinite ? 1.0 : 0.0;
+  else if (*slot > 0.0) sc->nonfinite = 1;
+}
 __global__ void check_finite_kernel(const double* __restrict__ f, long long n, DevScalars* sc) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     if (!isfinite(f[i])) atomicExch(&sc->nonfinite, 1);
@@ -887,7 +891,13 @@ int do_eval(kcma* h) {
     CUDA_OK(h, cudaStreamSynchronize(h->stream));
     h->host_obj(h->host_obj_user, h->hX.data(), (uint64_t)ls, (uint64_t)N, h->hF.data());
     for (size_t i = 0; i < ls; i++)  // ref: optimization.cpp.base:32-33
-      if (!std::isfinite(h->hF[i])) return fail(h, "Non finite value of function evaluation detected: %f\n", h->hF[i]);
+      if (!std::isfinite(h->hF[i])) {
+        if (h->cfg.nranks == 1) return fail(h, "Non finite value of function evaluation detected: %f\n", h->hF[i]);
+        if (pull_scalars(h)) return 1;      // several ranks: fail collectively at the end of the generation (flag in the all-reduce)
+        h->hSc->nonfinite = 1;
+        if (push_scalars(h)) return 1;
+        h->hF[i] = -1e300;
+      }
     CUDA_OK(h, cudaMemcpyAsync(h->dF + h->shard_lo, h->hF.data(), sizeof(double) * ls, cudaMemcpyHostToDevice, h->stream));
     return 0;
   }
@@ -968,8 +978,13 @@ int do_tell(kcma* h) {
   }
   if (multi) {
     PhaseTimer t(h, "collectives");
-    const size_t cnt = (size_t)N * ld + 2 * (size_t)ld;
+    // the error flag rides along, so that a non-finite F(x) on ONE rank fails the generation on EVERY rank instead of leaving the
+    // others blocked in the next collective
+    const size_t cnt = (size_t)N * ld + 2 * (size_t)ld + 1;
+    fold_error_flag_kernel<<<1, 1, 0, h->stream>>>(h->dRed + cnt - 1, h->dSc, 0);
     if (nccl_check(h, g_nccl.AllReduce(h->dRed, h->dRed, cnt, ncclFloat64, ncclSum, h->comm, h->stream), "all-reduce(P|mean|best)")) return 1;
+    fold_error_flag_kernel<<<1, 1, 0, h->stream>>>(h->dRed + cnt - 1, h->dSc, 1);
+    h->launches += 2;
   }
   {
     PhaseTimer t(h, "paths");
@@ -1222,7 +1237,7 @@ int kcma_create(const kcma_cfg* cfg, kcma_t** out) {
   CREATE_CUDA(dmalloc(&h->dS, (size_t)h->s_rows_padded * ld));
   CREATE_CUDA(dmalloc(&h->dPartial, ((size_t)h->s_rows_padded / h->rows_per_cta + 2) * ld));
   CREATE_CUDA(dmalloc(&h->dWsplit, (size_t)h->max_splits * nn));
-  CREATE_CUDA(dmalloc(&h->dRed, nn + 2 * (size_t)ld));
+  CREATE_CUDA(dmalloc(&h->dRed, nn + 2 * (size_t)ld + 16));
   CREATE_CUDA(dmalloc(&h->dLower, ld)); CREATE_CUDA(dmalloc(&h->dUpper, ld)); CREATE_CUDA(dmalloc(&h->dMinSd, ld));
   CREATE_CUDA(dmalloc(&h->dCoef, ld)); CREATE_CUDA(dmalloc(&h->dShift, h->n_con + 1));
   CREATE_CUDA(dmalloc(&h->dSigmaSampling, 2)); CREATE_CUDA(dmalloc(&h->dInfeasible, h->max_local + 16));

@@ -64,6 +64,17 @@ __device__ __forceinline__ double block_sum(double v, double* slot) {
   return s;
 }
 
+template <int NW>
+__device__ __forceinline__ double block_sum_n(double v, double* slot) {
+  v = warp_sum_butterfly(v);
+  if ((threadIdx.x & 31) == 0) slot[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < NW; k++) s += slot[k];
+  return s;
+}
+
 // The two element formulas of a step, with explicit roundings: they are evaluated per row by the row's thread AND for rows i, i+1
 // by every thread (scalars), and both must give the same bits.
 __device__ __forceinline__ double w_of(double tau, double p, double alpha, double v) { return __fma_rn(tau, p, __dmul_rn(alpha, v)); }
@@ -295,8 +306,8 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
                : "memory");
 }
 
-template <int KU, int NC, int CL = 1>
-__global__ void __launch_bounds__(SY_NT, 1)
+template <int KU, int NC, int CL = 1, int NT = SY_NT>
+__global__ void __launch_bounds__(NT, 1)
 sytrd_reg_kernel(const double* __restrict__ M, int ld, int n, int ns /* n rounded up to even: LL stride per parity, vector stride */,
                  LL* __restrict__ xP, LL* __restrict__ xC, double* __restrict__ dT, double* __restrict__ eT, double* __restrict__ tauv,
                  double* __restrict__ VR, long long* __restrict__ prof, int prof_step0, int prof_cta, int opt, int copies) {
@@ -305,22 +316,22 @@ sytrd_reg_kernel(const double* __restrict__ M, int ld, int n, int ns /* n rounde
   double* vs_old = sm;             // reflector v_{i-1} by index (lookups v[c], v[i+1])
   double* vs_new = sm + ns;
   double* wsm = sm + 2 * ns;       // w_{i-1} by index (lookups w[c])
-  double* red = sm + 3 * ns;       // 4 slots x SY_NW
-  double* bc = red + 32;           // 2 parities x {c_i, p_i, c_{i+1}, p_{i+1}}
-  double* pp = red + 48;           // NC x SY_NT partial products of the pass
-  double* cbuf = pp + NC * SY_NT;  // CL > 1: received column / product entries pushed by the cluster leader, 2 parities x ns each
+  double* red = sm + 3 * ns;       // 4 slots x (NT / 32)
+  double* bc = red + 64;           // 2 parities x {c_i, p_i, c_{i+1}, p_{i+1}}
+  double* pp = red + 80;           // NC x NT partial products of the pass
+  double* cbuf = pp + NC * NT;  // CL > 1: received column / product entries pushed by the cluster leader, 2 parities x ns each
   double* pbuf = cbuf + 2 * ns;
   __shared__ __align__(8) unsigned long long mbar;
   const unsigned crank = CL > 1 ? cluster_ctarank() : 0u;
   if (CL > 1) {
-    if (tid == 0) mbar_init(&mbar, SY_NW);   // one arrival per warp of the leader and step
+    if (tid == 0) mbar_init(&mbar, (NT / 32));   // one arrival per warp of the leader and step
     cluster_sync_all();
   }
   const int nloc = b < n ? (n - b + G - 1) / G : 0;
   double A[KU][NC][2], v[2 * KU], w[2 * KU], vnw[2 * KU];
 #pragma unroll
   for (int k = 0; k < KU; k++) {
-    const int r = 2 * (tid + SY_NT * k);
+    const int r = 2 * (tid + NT * k);
 #pragma unroll
     for (int s = 0; s < NC; s++) {
       const double* src = M + (size_t)(b + s * G) * ld;   // column c of a symmetric matrix = its row c
@@ -329,13 +340,13 @@ sytrd_reg_kernel(const double* __restrict__ M, int ld, int n, int ns /* n rounde
     }
     v[2 * k] = v[2 * k + 1] = w[2 * k] = w[2 * k + 1] = vnw[2 * k] = vnw[2 * k + 1] = 0.0;
   }
-  for (int r = tid; r < ns; r += SY_NT) { vs_old[r] = 0.0; vs_new[r] = 0.0; wsm[r] = 0.0; }
+  for (int r = tid; r < ns; r += NT) { vs_old[r] = 0.0; vs_new[r] = 0.0; wsm[r] = 0.0; }
   // Every slot exists `copies` times (stride cstride): all CTAs poll the same 2 n slots, and 148 requests per 128-byte line and
   // polling round serialise in the L2 slice that owns the line; CTA b reads copy b % copies, the producers write all copies.
   const size_t cstride = 4 * (size_t)ns;
   const size_t my_copy = (size_t)(b % copies) * cstride;
   if (b == 0)   // owner of column 0 publishes it for step 0
-    for (int r = tid; r < n; r += SY_NT)
+    for (int r = tid; r < n; r += NT)
       for (int q = 0; q < copies; q++) ll_store(xC + q * cstride + r, M[r], 1ull);
   __syncthreads();
   double tau_old = 0.0;
@@ -352,14 +363,14 @@ sytrd_reg_kernel(const double* __restrict__ M, int ld, int n, int ns /* n rounde
     unsigned need = 0;
 #pragma unroll
     for (int j = 0; j < 2 * KU; j++) {
-      const int r = 2 * (tid + SY_NT * (j >> 1)) + (j & 1);
+      const int r = 2 * (tid + NT * (j >> 1)) + (j & 1);
       if (r >= i && r < n) need |= 1u << j;
       cv[j] = 0.0; pq[j] = 0.0;
     }
     if (have_p && (opt & 1) && crank == 0) {   // one lane per warp spins on one slot first: 148 x 256 threads polling everything back to back saturate the L2
       if (lane == 0 && need) {
         const int j0 = __ffs(need) - 1;
-        (void)ll_wait(Pin + 2 * (tid + SY_NT * (j0 >> 1)) + (j0 & 1), tag);
+        (void)ll_wait(Pin + 2 * (tid + NT * (j0 >> 1)) + (j0 & 1), tag);
       }
       __syncwarp();
     }
@@ -369,8 +380,8 @@ sytrd_reg_kernel(const double* __restrict__ M, int ld, int n, int ns /* n rounde
         unsigned long long qc[KU][4], qp[KU][4];
 #pragma unroll
         for (int k = 0; k < KU; k++) {
-          if ((pc >> (2 * k)) & 3u) ll_load2(Cin + 2 * (tid + SY_NT * k), qc[k]);
-          if ((ppn >> (2 * k)) & 3u) ll_load2(Pin + 2 * (tid + SY_NT * k), qp[k]);
+          if ((pc >> (2 * k)) & 3u) ll_load2(Cin + 2 * (tid + NT * k), qc[k]);
+          if ((ppn >> (2 * k)) & 3u) ll_load2(Pin + 2 * (tid + NT * k), qp[k]);
         }
 #pragma unroll
         for (int k = 0; k < KU; k++)
@@ -389,7 +400,7 @@ sytrd_reg_kernel(const double* __restrict__ M, int ld, int n, int ns /* n rounde
         for (unsigned q = 1; q < (unsigned)CL; q++)
 #pragma unroll
           for (int k = 0; k < KU; k++) {
-            const int r = 2 * (tid + SY_NT * k);
+            const int r = 2 * (tid + NT * k);
             if (r < ns) {
               st_cluster_f64x2(map_to_cta(cbuf + par * ns + r, q), cv[2 * k], cv[2 * k + 1]);
               st_cluster_f64x2(map_to_cta(pbuf + par * ns + r, q), pq[2 * k], pq[2 * k + 1]);
@@ -404,7 +415,7 @@ sytrd_reg_kernel(const double* __restrict__ M, int ld, int n, int ns /* n rounde
         mbar_wait(&mbar, (unsigned)(i & 1));
 #pragma unroll
         for (int k = 0; k < KU; k++) {
-          const int r = 2 * (tid + SY_NT * k);
+          const int r = 2 * (tid + NT * k);
           if (r < ns) {
             const double2 c2 = *reinterpret_cast<const double2*>(cbuf + par * ns + r);
             const double2 p2 = *reinterpret_cast<const double2*>(pbuf + par * ns + r);
@@ -419,19 +430,19 @@ sytrd_reg_kernel(const double* __restrict__ M, int ld, int n, int ns /* n rounde
     double* bcp = bc + par * 4;
 #pragma unroll
     for (int j = 0; j < 2 * KU; j++) {
-      const int r = 2 * (tid + SY_NT * (j >> 1)) + (j & 1);
+      const int r = 2 * (tid + NT * (j >> 1)) + (j & 1);
       if (need & (1u << j)) part = __fma_rn(pq[j], v[j], part);
       if (r == i) { bcp[0] = cv[j]; bcp[1] = pq[j]; }
       if (r == i + 1 && r < n) { bcp[2] = cv[j]; bcp[3] = pq[j]; }
     }
-    const double pv = block_sum(part, red + (par * 2 + 0) * SY_NW);
+    const double pv = block_sum_n<NT / 32>(part, red + (par * 2 + 0) * (NT / 32));
     const double alpha = -0.5 * tau_old * (tau_old * pv);
     const double vi = vs_old[i];
     const double wi = w_of(tau_old, bcp[1], alpha, vi);
     double xpart = 0.0;
 #pragma unroll
     for (int j = 0; j < 2 * KU; j++) {
-      const int r = 2 * (tid + SY_NT * (j >> 1)) + (j & 1);
+      const int r = 2 * (tid + NT * (j >> 1)) + (j & 1);
       if (need & (1u << j)) {
         w[j] = w_of(tau_old, pq[j], alpha, v[j]);
         wsm[r] = w[j];
@@ -448,7 +459,7 @@ sytrd_reg_kernel(const double* __restrict__ M, int ld, int n, int ns /* n rounde
     }
     const double vi1 = vs_old[i + 1];
     const double alph = col_upd(bcp[2], vi1, wi, w_of(tau_old, bcp[3], alpha, vi1), vi);
-    const double xn2 = block_sum(xpart, red + (par * 2 + 1) * SY_NW);
+    const double xn2 = block_sum_n<NT / 32>(xpart, red + (par * 2 + 1) * (NT / 32));
     double tau = 0.0, scale = 0.0, ei = alph;
     if (xn2 > 0.0) {
       const double beta = -copysign(sqrt(alph * alph + xn2), alph);
@@ -458,7 +469,7 @@ sytrd_reg_kernel(const double* __restrict__ M, int ld, int n, int ns /* n rounde
     }
 #pragma unroll
     for (int j = 0; j < 2 * KU; j++) {
-      const int r = 2 * (tid + SY_NT * (j >> 1)) + (j & 1);
+      const int r = 2 * (tid + NT * (j >> 1)) + (j & 1);
       vnw[j] = (r == i + 1) ? 1.0 : ((r >= i + 2 && r < n) ? cv[j] * scale : 0.0);
       if (r < ns) vs_new[r] = vnw[j];
     }
@@ -485,22 +496,22 @@ sytrd_reg_kernel(const double* __restrict__ M, int ld, int n, int ns /* n rounde
           dot += a0 * vnw[2 * k];
           dot += a1 * vnw[2 * k + 1];
           if (c == i + 1) {
-            const int r = 2 * (tid + SY_NT * k);
+            const int r = 2 * (tid + NT * k);
             for (int q = 0; q < copies; q++) {
               if (r > i && r < n) ll_store(Cout + q * cstride + r, a0, otag);
               if (r + 1 > i && r + 1 < n) ll_store(Cout + q * cstride + r + 1, a1, otag);
             }
           }
         }
-        pp[s * SY_NT + tid] = dot;
+        pp[s * NT + tid] = dot;
       }
     }
     __syncthreads();
-    for (int s = warp; s < NC; s += SY_NW)   // a warp finishes column s: 256 partials in a fixed order
+    for (int s = warp; s < NC; s += (NT / 32))   // a warp finishes column s: 256 partials in a fixed order
       if (s >= s0 && s < nloc) {
         double x = 0.0;
 #pragma unroll
-        for (int j = 0; j < SY_NW; j++) x += pp[s * SY_NT + lane + 32 * j];
+        for (int j = 0; j < (NT / 32); j++) x += pp[s * NT + lane + 32 * j];
         x = warp_sum_butterfly(x);
         if (lane < copies) ll_store(Pout + lane * cstride + b + s * G, x, otag);
       }
@@ -509,7 +520,7 @@ sytrd_reg_kernel(const double* __restrict__ M, int ld, int n, int ns /* n rounde
       double* vr = VR + (size_t)i * ld;
 #pragma unroll
       for (int j = 0; j < 2 * KU; j++) {
-        const int r = 2 * (tid + SY_NT * (j >> 1)) + (j & 1);
+        const int r = 2 * (tid + NT * (j >> 1)) + (j & 1);
         if (r > i && r < n) vr[r] = vnw[j];
       }
     }
@@ -621,10 +632,11 @@ TridiagWs* tridiag_ws_create(int n, int ld, int num_sms, char* err, size_t errle
     else if (units <= 2 * SY_NT && nloc_max <= 14) ws->reg_variant = 4;
     else if (units <= 3 * SY_NT && nloc_max <= 11) ws->reg_variant = 3;
   }
+  ws->sy_threads = SY_NT;   // (74 CTAs x 512 threads, <1, 14, 1, 512>, was measured and dropped: 6.1 instead of 4.3 ms, profiles/r02_eigen_ab10.log)
   ws->resident = ws->reg_variant != 0;
   ws->sy_grid = grid;
   static const int kNC[5] = {0, 4, 7, 11, 14};
-  ws->sy_smem = ws->resident ? sizeof(double) * (3 * (size_t)ns + 48 + (size_t)kNC[ws->reg_variant] * SY_NT) : vec_bytes;
+  ws->sy_smem = ws->resident ? sizeof(double) * (3 * (size_t)ns + 80 + (size_t)kNC[ws->reg_variant] * ws->sy_threads) : vec_bytes;
   // thread-block clusters (KCMA_SYTRD_CLUSTER=2|4): only for the <2,7> instantiation, and only when enough clusters are co-resident
   ws->cluster = 1;
   if (const char* cle = getenv("KCMA_SYTRD_CLUSTER")) {
@@ -851,7 +863,7 @@ bool tridiag_stage_sytrd(cudaStream_t st, TridiagWs* ws, const double* M) {
     attrs[1].val.cooperative = 1;
     cfg.attrs = attrs; cfg.numAttrs = 2;
     if (cudaLaunchKernelExC(&cfg, cfn, rargs) != cudaSuccess) return false;
-  } else if (cudaLaunchCooperativeKernel(fn, dim3(ws->sy_grid), dim3(SY_NT), ws->resident ? rargs : args, ws->sy_smem, st) != cudaSuccess) return false;
+  } else if (cudaLaunchCooperativeKernel(fn, dim3(ws->sy_grid), dim3(ws->sy_threads), ws->resident ? rargs : args, ws->sy_smem, st) != cudaSuccess) return false;
   // row n-1 of VR (no reflector) and tau[n-1] stay zero from the allocation; VC = VR^T
   launch_transpose(st, ws->VR, ws->VC, ld, n);
   return cudaGetLastError() == cudaSuccess;

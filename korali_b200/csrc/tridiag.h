@@ -14,7 +14,7 @@ struct TridiagWs {
   bool resident = false;       // this CTA's columns live in REGISTERS (N <= 1536: sytrd_reg_kernel), else in the global working copy
   int cluster = 1;             // thread-block cluster size of the register variant (leader polls, peers receive through DSMEM)
   int reg_variant = 0;         // 1, 2, 3 = sytrd_reg_kernel<1,4>, <2,7>, <3,11>
-  int sy_grid = 0; size_t sy_smem = 0;
+  int sy_grid = 0, sy_threads = 256; size_t sy_smem = 0;
   double* Awork = nullptr;     // n x ld working copy (global variant only)
   double *dT = nullptr, *eT = nullptr, *tau = nullptr;   // diagonal, off-diagonal, reflector scalars
   double *VR = nullptr;        // row i = reflector v_i (support i+1.., v_i[i+1] = 1)

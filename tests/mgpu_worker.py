@@ -76,6 +76,33 @@ def main():
         s.close()
         if rank == 0:
             print("ok", case["objective"], "world", world, flush=True)
+    # error path: a non-finite F(x) on ONE rank must fail the generation on EVERY rank (the flag rides in the all-reduce) instead of
+    # leaving the other ranks blocked in a collective
+    from korali_b200._abi import KcmaError
+    s = _lib.Solver(device=local, rank=rank, nranks=world, n=8, population_size=64, objective="External", keep_population=1,
+                    initial_value=1.0, initial_stddev=1.0, seed=3)
+    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        uid = torch.tensor(list(_lib.comm_unique_id()), dtype=torch.uint8, device="cuda")
+    dist.broadcast(uid, 0)
+    s.comm_init(bytes(uid.cpu().tolist()))
+    calls = [0]
+    def model(X):
+        calls[0] += 1
+        f = -np.sum(X * X, axis=1)
+        if calls[0] == 3 and rank == world - 1:
+            f[0] = np.nan
+        return f
+    s.set_host_objective(model)
+    s.run_generation(); s.run_generation()
+    try:
+        s.run_generation()
+        raise AssertionError("rank %d: the non-finite value of rank %d went unnoticed" % (rank, world - 1))
+    except KcmaError as exc:
+        assert "Non finite" in str(exc), str(exc)
+    s.close()
+    if rank == 0:
+        print("ok collective-error world", world, flush=True)
     dist.barrier()
     dist.destroy_process_group()
 
