@@ -20,6 +20,10 @@ EXPORTS = [
     "kcma_timing_enable", "kcma_timing_get", "kcma_timing_reset", "kcma_launch_count", "kcma_flush_l2",
     "kcma_k_sort_index", "kcma_k_eigen", "kcma_k_tridiag_stage", "kcma_k_sample", "kcma_k_rank_mu", "kcma_k_philox_normal",
     "kcma_k_philox_raw", "kcma_k_objective",
+    # include/kdea.h
+    "kdea_cfg_defaults", "kdea_create", "kdea_destroy", "kdea_last_error", "kdea_run_generation", "kdea_ask", "kdea_eval", "kdea_tell",
+    "kdea_set_host_objective", "kdea_inject_f", "kdea_check_termination", "kdea_run", "kdea_get_array", "kdea_set_array",
+    "kdea_get_scalar", "kdea_set_scalar", "kdea_launch_count",
 ]
 
 

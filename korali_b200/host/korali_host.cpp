@@ -30,6 +30,7 @@
 #include <vector>
 
 #include "../../include/kcma.h"
+#include "../../include/kdea.h"
 
 namespace py = pybind11;
 
@@ -192,6 +193,37 @@ enum Verbosity { SILENT = 0, MINIMAL = 1, NORMAL = 2, DETAILED = 3 };
 
 class Experiment;
 
+// ---- the solver plug-in interface of this shim (the virtuals of Solver / Module that Experiment::initialize / run call,
+// module.hpp:51-99, solver.hpp.base:65-85); selected by e["Solver"]["Type"] like Module::getModule (module.cpp:103-150)
+class SolverBase {
+ public:
+  std::vector<double> lower, upper;
+  std::vector<std::string> termination_criteria;
+  std::string pending_error;
+  virtual ~SolverBase() {}
+  virtual const char* name() const = 0;
+  virtual void setConfiguration(py::dict solver, py::list variables, py::dict problem, uint64_t seed) = 0;
+  virtual void initialize(const std::vector<int>& device_ids) = 0;
+  virtual void restore(uint64_t generation) = 0;
+  virtual bool checkTermination() = 0;
+  virtual void runGeneration() = 0;
+  virtual void getConfiguration(py::dict js) = 0;
+  virtual double scalar(const char* key) = 0;
+  virtual std::vector<double> array(const char* key) = 0;
+  virtual void printGeneration(const std::function<void(int, const char*)>& log) = 0;   // printGenerationAfter
+  virtual std::string takeWarnings() { return ""; }
+  virtual std::vector<std::pair<std::string, std::string>> sideCars() { return {}; }      // (key, file suffix) of N x N arrays saved as .npy
+  virtual size_t variableCount() const = 0;
+  void splitReasons(const char* reason) {
+    termination_criteria.clear();
+    std::string r(reason), item;
+    for (char c : r) {
+      if (c == ';') { if (!item.empty()) termination_criteria.push_back(item); item.clear(); }
+      else item += c;
+    }
+  }
+};
+
 // One persistent host thread per additional device: with k["Conduit"]["Devices"] = G the population is sharded over G handles
 // of this process, and the G calls of a generation must be in flight together (they meet in the NCCL collectives).
 class RankPool {
@@ -241,23 +273,39 @@ class RankPool {
 };
 
 // ---- the solver plug-in: Optimizer/CMAES on libkcma ----------------------------------------------------------
-class CMAES {
+class CMAES : public SolverBase {
  public:
   kcma_t* h = nullptr;                  // rank 0 (the replicated state is read from it)
   std::vector<kcma_t*> hs;              // all ranks, one per device
   std::unique_ptr<RankPool> pool;
   kcma_cfg cfg;
   std::string mu_type = "Logarithmic";
-  std::vector<double> lower, upper, init_val, init_sd, min_sd, gran;
+  std::vector<double> init_val, init_sd, min_sd, gran;
   std::vector<std::string> names;
   py::object objective;                 // Python callable, or a string naming a built-in device objective
   std::vector<py::object> constraints;  // Python callables
   // termination criteria as given
   double tc_max_generations = 1e10, tc_max_model_evaluations = 1e9, tc_max_value = INFINITY, tc_min_value_diff = -INFINITY;
   double tc_max_infeasible = 0, tc_max_condition = INFINITY, tc_min_sd = -INFINITY, tc_max_sd = INFINITY;
-  std::vector<std::string> termination_criteria;
-  std::string pending_error;
   int devices = 1;
+
+  const char* name() const override { return "Optimizer/CMAES"; }
+  size_t variableCount() const override { return cfg.n; }
+  std::string takeWarnings() override { const char* w = kcma_take_warnings(h); return w ? w : ""; }
+  std::vector<std::pair<std::string, std::string>> sideCars() override {
+    if ((uint64_t)cfg.n * cfg.n <= (1u << 22)) return {};
+    return {{"Covariance Matrix", "C"}, {"Covariance Eigenvector Matrix", "B"}};
+  }
+  void printGeneration(const std::function<void(int, const char*)>& log) override {   // CMAES::printGenerationAfter :952-992
+    char b[256];
+    snprintf(b, sizeof(b), "Sigma:                        %+6.3e\n", scalar("Sigma")); log(NORMAL, b);
+    snprintf(b, sizeof(b), "Current Function Value: Max = %+6.3e - Best = %+6.3e\n", scalar("Current Best Value"), scalar("Best Ever Value")); log(NORMAL, b);
+    snprintf(b, sizeof(b), "Diagonal Covariance:    Min = %+6.3e -  Max = %+6.3e\n", scalar("Minimum Diagonal Covariance Matrix Element"),
+             scalar("Maximum Diagonal Covariance Matrix Element")); log(NORMAL, b);
+    snprintf(b, sizeof(b), "Covariance Eigenvalues: Min = %+6.3e -  Max = %+6.3e\n", scalar("Minimum Covariance Eigenvalue"), scalar("Maximum Covariance Eigenvalue"));
+    log(NORMAL, b);
+    snprintf(b, sizeof(b), "Number of Infeasible Samples: %zu\n", (size_t)scalar("Infeasible Sample Count")); log(DETAILED, b);
+  }
 
   ~CMAES() {
     pool.reset();
@@ -271,8 +319,8 @@ class CMAES {
     if (rc) korali_error("%s", kcma_last_error(h));
   }
 
-  double scalar(const char* key) { double v = NAN; check(kcma_get_scalar(h, key, &v)); return v; }
-  std::vector<double> array(const char* key) {
+  double scalar(const char* key) override { double v = NAN; check(kcma_get_scalar(h, key, &v)); return v; }
+  std::vector<double> array(const char* key) override {
     size_t n = 0;
     check(kcma_get_array(h, key, nullptr, 0, &n));
     std::vector<double> v(n);
@@ -281,7 +329,7 @@ class CMAES {
   }
 
   // generated CMAES::setConfiguration + Optimizer:: + Solver:: (strict)
-  void setConfiguration(py::dict solver, py::list variables, py::dict problem, uint64_t seed) {
+  void setConfiguration(py::dict solver, py::list variables, py::dict problem, uint64_t seed) override {
     kcma_cfg_defaults(&cfg);
     Settings s(solver, "CMAES");
     s.take("Type");
@@ -525,7 +573,7 @@ class CMAES {
     }
   }
 
-  void initialize(const std::vector<int>& device_ids) {
+  void initialize(const std::vector<int>& device_ids) override {
     const int G = (int)device_ids.size();
     if (G > 1 && (cfg.objective == KCMA_OBJ_EXTERNAL || !constraints.empty()))
       korali_error("k['Conduit']['Devices'] > 1 shards the population over several GPUs of this process: it needs a device objective "
@@ -560,7 +608,7 @@ class CMAES {
   }
 
   // restore "Internal Settings" of a loaded state (CMAES.cpp:1042-1560): resume continues from the saved generation
-  void restore(uint64_t generation) {
+  void restore(uint64_t generation) override {
     if (generation == 0) return;
     auto arr = [&](const char* k) {
       if (!saved_internal.contains(k)) return;
@@ -598,22 +646,15 @@ class CMAES {
     each([&](kcma_t* x) { return kcma_set_scalar(x, "Current Generation", (double)generation); });
   }
 
-  bool checkTermination() {
+  bool checkTermination() override {
     int fin = 0;
     const char* reason = "";
     check(kcma_check_termination(h, &fin, &reason));
-    if (fin) {
-      termination_criteria.clear();
-      std::string r(reason), item;
-      for (char c : r) {
-        if (c == ';') { if (!item.empty()) termination_criteria.push_back(item); item.clear(); }
-        else item += c;
-      }
-    }
+    if (fin) splitReasons(reason);
     return fin != 0;
   }
 
-  void runGeneration() {
+  void runGeneration() override {
     pending_error.clear();
     if (pool) {   // one call per device, in flight together
       const int failed = pool->run([this](int r) { return kcma_run_generation(hs[r]); });
@@ -627,7 +668,7 @@ class CMAES {
 
   // generated getConfiguration (CMAES.cpp:1784-1881): settings + internal state under Korali's key names.
   // Size policy: lambda x N arrays are exported only when small (they cannot be serialised at scale).
-  void getConfiguration(py::dict js) {
+  void getConfiguration(py::dict js) override {
     js["Type"] = "Optimizer/CMAES";
     js["Population Size"] = cfg.population_size;
     js["Mu Value"] = cfg.mu_value;
@@ -706,10 +747,256 @@ class CMAES {
   }
 };
 
+// ---- the solver plug-in: Optimizer/DEA on libkcma (include/kdea.h) -------------------------------------------------
+class DEA : public SolverBase {
+ public:
+  kdea_t* h = nullptr;
+  kdea_cfg cfg;
+  std::string mutation_rule = "Fixed", parent_rule = "Random", accept_rule = "Greedy", batched;
+  py::object objective;
+  double tc_max_generations = 1e10, tc_max_model_evaluations = 1e9, tc_max_value = INFINITY, tc_min_value_diff = -INFINITY;
+  double tc_max_infeasible = 1e7, tc_min_value = -INFINITY, tc_min_step = -INFINITY;
+  py::dict saved_internal;
+
+  ~DEA() override { if (h) kdea_destroy(h); }
+  const char* name() const override { return "Optimizer/DEA"; }
+  size_t variableCount() const override { return cfg.n; }
+  void check(int rc) { if (rc) korali_error("%s", kdea_last_error(h)); }
+  double scalar(const char* key) override { double v = NAN; check(kdea_get_scalar(h, key, &v)); return v; }
+  std::vector<double> array(const char* key) override {
+    size_t n = 0;
+    check(kdea_get_array(h, key, nullptr, 0, &n));
+    std::vector<double> v(n);
+    if (n) check(kdea_get_array(h, key, v.data(), n, &n));
+    return v;
+  }
+
+  // generated DEA::setConfiguration (DEA.config) + Optimizer:: + Solver:: (strict)
+  void setConfiguration(py::dict solver, py::list variables, py::dict problem, uint64_t seed) override {
+    kdea_cfg_defaults(&cfg);
+    uint64_t uniform_seed = 0;
+    Settings s(solver, "DEA");
+    s.take("Type");
+    cfg.population_size = s.uint("Population Size", 200);
+    cfg.crossover_rate = s.num("Crossover Rate", 0.9);
+    cfg.mutation_rate = s.num("Mutation Rate", 0.5);
+    mutation_rule = s.str("Mutation Rule", "Fixed");
+    parent_rule = s.str("Parent Selection Rule", "Random");
+    accept_rule = s.str("Accept Rule", "Greedy");
+    cfg.fix_infeasible = s.boolean("Fix Infeasible", 1);
+    if (mutation_rule == "Fixed") cfg.mutation_rule = KDEA_MUTATION_FIXED;
+    else if (mutation_rule == "Self Adaptive") korali_error("Mutation Rule 'Self Adaptive' is not built on the B200 path (DEA.cpp.base:136-156)\n");
+    else korali_error("Invalid setting of Mutation Rule (%s) (Fixed or Self Adaptive accepted).\n", mutation_rule.c_str());
+    if (parent_rule == "Random") cfg.parent_selection_rule = KDEA_PARENT_RANDOM;
+    else if (parent_rule == "Best") cfg.parent_selection_rule = KDEA_PARENT_BEST;
+    else korali_error("Invalid setting of Parent Selection Rule (%s) (Random or Best accepted).\n", parent_rule.c_str());
+    if (accept_rule == "Best") cfg.accept_rule = KDEA_ACCEPT_BEST;
+    else if (accept_rule == "Greedy") cfg.accept_rule = KDEA_ACCEPT_GREEDY;
+    else if (accept_rule == "Improved") cfg.accept_rule = KDEA_ACCEPT_IMPROVED;
+    else if (accept_rule == "Iterative") cfg.accept_rule = KDEA_ACCEPT_ITERATIVE;
+    else korali_error("Accept Rule (%s) not recognized.\n", accept_rule.c_str());
+    if (s.has("Termination Criteria")) {
+      py::object tco = s.take("Termination Criteria");
+      if (!py::isinstance<py::dict>(tco)) korali_error(" + Object: [ DEA ] \n + Key:    ['Termination Criteria']\n + Reason: not an object\n");
+      py::dict tcd;
+      for (auto kv : py::reinterpret_borrow<py::dict>(tco)) tcd[kv.first] = kv.second;
+      Settings tc(tcd, "DEA['Termination Criteria']");
+      tc_max_infeasible = tc.num("Max Infeasible Resamplings", 1e7);
+      tc_min_value = tc.num("Min Value", -INFINITY);
+      tc_min_step = tc.num("Min Step Size", -INFINITY);
+      tc_max_value = tc.num("Max Value", INFINITY);
+      tc_min_value_diff = tc.num("Min Value Difference Threshold", -INFINITY);
+      tc_max_model_evaluations = tc.num("Max Model Evaluations", 1e9);
+      tc_max_generations = tc.num("Max Generations", 1e10);
+      tc.finish();
+    }
+    for (const char* g : {"Normal Generator", "Uniform Generator"}) {
+      if (!s.has(g)) continue;
+      py::object go = s.take(g);
+      if (std::string(g) == "Uniform Generator" && py::isinstance<py::dict>(go)) {
+        py::dict gd = py::reinterpret_borrow<py::dict>(go);
+        if (gd.contains("Random Seed") && is_number(gd["Random Seed"]) && gd["Random Seed"].cast<double>() > 0) uniform_seed = (uint64_t)gd["Random Seed"].cast<double>();
+      }
+    }
+    static const char* kInternal[] = {"Value Vector", "Previous Value Vector", "Sample Population", "Candidate Population", "Best Sample Index",
+                                      "Best Ever Value", "Previous Best Ever Value", "Current Best Value", "Previous Best Value", "Current Mean",
+                                      "Previous Mean", "Best Ever Variables", "Current Best Variables", "Max Distances", "Infeasible Sample Count",
+                                      "Current Minimum Step Size", "Variable Count", "Model Evaluation Count"};
+    saved_internal = py::dict();
+    for (const char* k : kInternal)
+      if (s.has(k)) saved_internal[k] = s.take(k);
+    const size_t n = py::len(variables);
+    if (n == 0) korali_error("Optimization Evaluation problems require at least one variable.\n");
+    lower.assign(n, -INFINITY); upper.assign(n, INFINITY);
+    for (size_t i = 0; i < n; i++) {
+      if (!py::isinstance<py::dict>(variables[i])) korali_error("Variable %zu is not an object\n", i);
+      py::dict vcopy;
+      for (auto kv : py::reinterpret_borrow<py::dict>(variables[i])) vcopy[kv.first] = kv.second;
+      Settings v(vcopy, "Variable");
+      v.str("Name", "");
+      lower[i] = v.num("Lower Bound", -INFINITY);
+      upper[i] = v.num("Upper Bound", INFINITY);
+      for (const char* k : {"Initial Value", "Initial Mean", "Initial Standard Deviation", "Minimum Standard Deviation Update", "Granularity"}) v.num(k, NAN);
+      if (v.has("Values")) v.take("Values");
+      v.finish();
+    }
+    cfg.n = n; cfg.lower_bound = lower.data(); cfg.upper_bound = upper.data();
+    cfg.seed = uniform_seed ? uniform_seed : seed + 1;   // Uniform Generator = S + 1 (distribution.cpp.base:36-37: Normal S, Uniform S + 1); a saved state carries its own
+    py::dict pcopy;
+    for (auto kv : problem) pcopy[kv.first] = kv.second;
+    Settings p(pcopy, "Optimization");
+    const std::string ptype = canon(p.str("Type", ""));
+    if (ptype != "optimization") korali_error("Only Problem Type 'Optimization' is served by the B200 path (got '%s')\n", ptype.c_str());
+    if (!p.has("Objective Function")) korali_error(" + Object: [ Optimization ] \n + Key:    ['Objective Function']\n + Reason: mandatory setting missing\n");
+    objective = p.take("Objective Function");
+    p.uint("Num Objectives", 1);
+    p.boolean("Has Discrete Variables", 0);
+    if (p.has("Constraints")) {
+      py::object c = p.take("Constraints");
+      if (py::isinstance<py::list>(c) && py::len(c) > 0) korali_error("Optimizer/DEA does not take constraints\n");
+    }
+    p.finish();
+    if (py::isinstance<py::str>(objective)) {
+      const std::string o = canon(objective.cast<std::string>());
+      if (o == "negsphere" || o == "sphere") cfg.objective = KCMA_OBJ_NEG_SPHERE;
+      else if (o == "negrosenbrock" || o == "rosenbrock") cfg.objective = KCMA_OBJ_NEG_ROSENBROCK;
+      else if (o == "negackley" || o == "ackley") cfg.objective = KCMA_OBJ_NEG_ACKLEY;
+      else if (o == "negellipsoid" || o == "ellipsoid") cfg.objective = KCMA_OBJ_NEG_ELLIPSOID;
+      else if (o == "negsumsq") cfg.objective = KCMA_OBJ_NEG_SUMSQ;
+      else if (o == "negspheresin2") cfg.objective = KCMA_OBJ_NEG_SPHERE_SIN2;
+      else korali_error("Unknown device objective '%s' (Sphere, Rosenbrock, Ackley, Ellipsoid, NegSumSq, NegSphereSin2)\n", o.c_str());
+    } else if (PyCallable_Check(objective.ptr())) {
+      cfg.objective = KCMA_OBJ_EXTERNAL;
+      batched = py::hasattr(objective, "_korali_batched") ? objective.attr("_korali_batched").cast<std::string>() : std::string();
+      if (batched == "device") korali_error("Optimizer/DEA takes per-sample models and korali.batched(fn) models (not device-tensor models)\n");
+    } else {
+      korali_error(" + Object: [ Optimization ] \n + Key:    ['Objective Function']\n + Reason: neither a callable nor the name of a device objective\n");
+    }
+    s.finish();
+  }
+
+  static void host_objective(void* user, const double* x, uint64_t rows, uint64_t n, double* f_out) {
+    DEA* self = (DEA*)user;
+    try {
+      if (self->batched == "numpy") {
+        py::array_t<double> X({(py::ssize_t)rows, (py::ssize_t)n}, {(py::ssize_t)(n * sizeof(double)), (py::ssize_t)sizeof(double)}, x, py::none());
+        py::array_t<double, py::array::c_style | py::array::forcecast> F(self->objective(X));
+        if ((uint64_t)F.size() != rows) korali_error("The batched model returned %zu values for %zu samples\n", (size_t)F.size(), (size_t)rows);
+        for (uint64_t i = 0; i < rows; i++) f_out[i] = F.data()[i];
+        return;
+      }
+      for (uint64_t i = 0; i < rows; i++) {
+        py::dict sample;
+        py::list params;
+        for (uint64_t d = 0; d < n; d++) params.append(x[i * n + d]);
+        sample["Parameters"] = params;
+        sample["Sample Id"] = i;
+        sample["Module"] = "Problem";
+        sample["Operation"] = "Evaluate";
+        self->objective(sample);
+        if (!sample.contains("F(x)")) korali_error("The model did not set 'F(x)' for sample %zu\n", (size_t)i);
+        f_out[i] = sample["F(x)"].cast<double>();
+      }
+    } catch (const std::exception& e) {
+      self->pending_error = e.what();
+      for (uint64_t i = 0; i < rows; i++) f_out[i] = NAN;
+    }
+  }
+
+  void initialize(const std::vector<int>& device_ids) override {
+    if (device_ids.size() > 1) korali_error("Optimizer/DEA runs on one device (k['Conduit']['Devices'] > 1 is built for Optimizer/CMAES)\n");
+    cfg.device = device_ids[0];
+    if (kdea_create(&cfg, &h)) korali_error("%s", kdea_last_error(nullptr));
+    if (cfg.objective == KCMA_OBJ_EXTERNAL) check(kdea_set_host_objective(h, &DEA::host_objective, this));
+    check(kdea_set_scalar(h, "Termination Criteria/Max Infeasible Resamplings", tc_max_infeasible));
+    check(kdea_set_scalar(h, "Termination Criteria/Min Value", tc_min_value));
+    check(kdea_set_scalar(h, "Termination Criteria/Min Step Size", tc_min_step));
+    check(kdea_set_scalar(h, "Termination Criteria/Max Value", tc_max_value));
+    check(kdea_set_scalar(h, "Termination Criteria/Min Value Difference Threshold", tc_min_value_diff));
+    check(kdea_set_scalar(h, "Termination Criteria/Max Model Evaluations", tc_max_model_evaluations));
+    check(kdea_set_scalar(h, "Termination Criteria/Max Generations", tc_max_generations));
+  }
+
+  void restore(uint64_t generation) override {
+    if (generation == 0) return;
+    auto flat = [&](py::handle o) {
+      std::vector<double> v;
+      for (auto row : o) {
+        if (py::isinstance<py::list>(row) || py::isinstance<py::tuple>(row)) for (auto x : row) v.push_back(x.cast<double>());
+        else v.push_back(row.cast<double>());
+      }
+      return v;
+    };
+    for (const char* k : {"Sample Population", "Candidate Population", "Value Vector", "Previous Value Vector", "Current Mean", "Previous Mean",
+                          "Best Ever Variables", "Current Best Variables", "Max Distances"})
+      if (saved_internal.contains(k)) { std::vector<double> v = flat(saved_internal[k]); check(kdea_set_array(h, k, v.data(), v.size())); }
+    for (const char* k : {"Best Ever Value", "Previous Best Ever Value", "Current Best Value", "Previous Best Value", "Best Sample Index",
+                          "Infeasible Sample Count", "Model Evaluation Count"})
+      if (saved_internal.contains(k)) check(kdea_set_scalar(h, k, saved_internal[k].cast<double>()));
+    check(kdea_set_scalar(h, "Current Generation", (double)generation));
+  }
+
+  bool checkTermination() override {
+    int fin = 0;
+    const char* reason = "";
+    check(kdea_check_termination(h, &fin, &reason));
+    if (fin) splitReasons(reason);
+    return fin != 0;
+  }
+
+  void runGeneration() override {
+    pending_error.clear();
+    const int rc = kdea_run_generation(h);
+    if (!pending_error.empty()) { std::string e = pending_error; pending_error.clear(); throw std::runtime_error(e); }
+    check(rc);
+  }
+
+  void printGeneration(const std::function<void(int, const char*)>& log) override {   // DEA::printGenerationAfter :290-299
+    char b[256];
+    snprintf(b, sizeof(b), "Current Function Value: Max = %+6.3e - Best = %+6.3e\n", scalar("Current Best Value"), scalar("Best Ever Value")); log(NORMAL, b);
+    snprintf(b, sizeof(b), "Number of Infeasible Samples: %zu\n", (size_t)scalar("Infeasible Sample Count")); log(DETAILED, b);
+  }
+
+  // generated getConfiguration: settings + internal state under Korali's key names (DEA.config)
+  void getConfiguration(py::dict js) override {
+    js["Type"] = "Optimizer/DEA";
+    js["Population Size"] = cfg.population_size;
+    js["Crossover Rate"] = cfg.crossover_rate;
+    js["Mutation Rate"] = cfg.mutation_rate;
+    js["Mutation Rule"] = mutation_rule;
+    js["Parent Selection Rule"] = parent_rule;
+    js["Accept Rule"] = accept_rule;
+    js["Fix Infeasible"] = cfg.fix_infeasible;
+    py::dict tc;
+    tc["Max Infeasible Resamplings"] = tc_max_infeasible; tc["Min Value"] = tc_min_value; tc["Min Step Size"] = tc_min_step;
+    tc["Max Value"] = tc_max_value; tc["Min Value Difference Threshold"] = tc_min_value_diff;
+    tc["Max Model Evaluations"] = tc_max_model_evaluations; tc["Max Generations"] = tc_max_generations;
+    js["Termination Criteria"] = tc;
+    py::dict ng, ug;
+    ng["Type"] = "Univariate/Normal"; ng["Mean"] = 0.0; ng["Standard Deviation"] = 1.0; ng["Random Seed"] = cfg.seed - 1;
+    ug["Type"] = "Univariate/Uniform"; ug["Minimum"] = 0.0; ug["Maximum"] = 1.0; ug["Random Seed"] = cfg.seed;
+    js["Normal Generator"] = ng; js["Uniform Generator"] = ug;
+    for (const char* k : {"Best Ever Value", "Previous Best Ever Value", "Current Best Value", "Previous Best Value", "Current Minimum Step Size"})
+      js[k] = scalar(k);
+    for (const char* k : {"Best Sample Index", "Infeasible Sample Count", "Model Evaluation Count", "Variable Count"}) js[k] = (long long)scalar(k);
+    for (const char* k : {"Current Mean", "Previous Mean", "Best Ever Variables", "Current Best Variables", "Max Distances", "Value Vector",
+                          "Previous Value Vector"})
+      js[k] = array(k);
+    const uint64_t n = cfg.n, lam = cfg.population_size;
+    if (lam * n <= (1u << 22))
+      for (const char* k : {"Sample Population", "Candidate Population"}) {
+        std::vector<double> flat = array(k);
+        py::list pop;
+        for (uint64_t i = 0; i * n < flat.size(); i++) pop.append(std::vector<double>(flat.begin() + i * n, flat.begin() + (i + 1) * n));
+        js[k] = pop;
+      }
+  }
+};
+
 // ---- Experiment ------------------------------------------------------------------------------------------------
 class Experiment : public KoraliJson {
  public:
-  std::unique_ptr<CMAES> solver;
+  std::unique_ptr<SolverBase> solver;
   uint64_t current_generation = 0;
   uint64_t random_seed = 0;
   Verbosity verbosity = NORMAL;
@@ -771,8 +1058,8 @@ class Experiment : public KoraliJson {
     py::dict problem_js = py::reinterpret_borrow<py::dict>(top.take("Problem"));
     py::list variables = py::reinterpret_borrow<py::list>(top.take("Variables"));
     const std::string stype = canon(solver_js.contains("Type") && py::isinstance<py::str>(solver_js["Type"]) ? solver_js["Type"].cast<std::string>() : "");
-    if (stype != "optimizer/cmaes" && stype != "cmaes")
-      korali_error("Solver Type '%s' is not served by korali_b200: only 'Optimizer/CMAES' is built (SURVEY.md scope)\n", stype.c_str());
+    if (stype != "optimizer/cmaes" && stype != "cmaes" && stype != "optimizer/dea" && stype != "dea")
+      korali_error("Solver Type '%s' is not served by korali_b200: only 'Optimizer/CMAES' and 'Optimizer/DEA' are built (SURVEY.md scope)\n", stype.c_str());
     random_seed = top.uint("Random Seed", 0);
     if (random_seed == 0) random_seed = (uint64_t)std::chrono::system_clock::now().time_since_epoch().count();  // experiment.cpp.base:235-251
     top.boolean("Preserve Random Number Generator States", 0);
@@ -806,7 +1093,8 @@ class Experiment : public KoraliJson {
       f.finish();
     }
     top.finish();
-    solver = std::make_unique<CMAES>();
+    if (stype == "optimizer/dea" || stype == "dea") solver = std::make_unique<DEA>();
+    else solver = std::make_unique<CMAES>();
     solver->setConfiguration(solver_js, variables, problem_js, random_seed);   // Normal Generator gets seed S (distribution.cpp.base:36-37)
     solver->initialize(devices);
     solver->restore(current_generation);
@@ -847,17 +1135,17 @@ class Experiment : public KoraliJson {
     }
     // N x N arrays above 2^22 entries do not go through JSON (134 MB of text per matrix at N = 4096): they are written
     // as .npy side-cars next to the result file, and the file names them so that loadState finds them again
-    if (solver && solver->h && (uint64_t)solver->cfg.n * solver->cfg.n > (1u << 22) && out.contains("Solver")) {
+    if (solver && !solver->sideCars().empty() && out.contains("Solver")) {
       py::object np = py::module_::import("numpy");
       py::dict sj;
       for (auto kv : py::reinterpret_borrow<py::dict>(out["Solver"])) sj[kv.first] = kv.second;
-      const size_t n = solver->cfg.n;
-      for (const char* key : {"Covariance Matrix", "Covariance Eigenvector Matrix"}) {
-        std::vector<double> flat = solver->array(key);
-        std::string fname = std::string(name) + "." + (std::string(key) == "Covariance Matrix" ? "C" : "B") + ".npy";
+      const size_t n = solver->variableCount();
+      for (auto& kf : solver->sideCars()) {
+        std::vector<double> flat = solver->array(kf.first.c_str());
+        std::string fname = std::string(name) + "." + kf.second + ".npy";
         py::array_t<double> arr({(py::ssize_t)n, (py::ssize_t)n}, flat.data());
         np.attr("save")(file_path + "/" + fname, arr);
-        sj[(std::string(key) + " File").c_str()] = fname;
+        sj[(kf.first + " File").c_str()] = fname;
       }
       out["Solver"] = sj;
     }
@@ -886,18 +1174,12 @@ class Experiment : public KoraliJson {
       solver->runGeneration();
       auto g1 = std::chrono::steady_clock::now();
       if (print && verbosity >= NORMAL) {
-        log(NORMAL, "Sigma:                        %+6.3e\n", solver->scalar("Sigma"));
-        log(NORMAL, "Current Function Value: Max = %+6.3e - Best = %+6.3e\n", solver->scalar("Current Best Value"), solver->scalar("Best Ever Value"));
-        log(NORMAL, "Diagonal Covariance:    Min = %+6.3e -  Max = %+6.3e\n", solver->scalar("Minimum Diagonal Covariance Matrix Element"),
-            solver->scalar("Maximum Diagonal Covariance Matrix Element"));
-        log(NORMAL, "Covariance Eigenvalues: Min = %+6.3e -  Max = %+6.3e\n", solver->scalar("Minimum Covariance Eigenvalue"),
-            solver->scalar("Maximum Covariance Eigenvalue"));
-        log(DETAILED, "Number of Infeasible Samples: %zu\n", (size_t)solver->scalar("Infeasible Sample Count"));
+        solver->printGeneration([this](int level, const char* line) { log((Verbosity)level, "%s", line); });
         log(DETAILED, "Experiment: 0 - Generation Time: %.3fs\n", std::chrono::duration<double>(g1 - g0).count());
       }
       if (verbosity >= DETAILED) {
-        const char* w = kcma_take_warnings(solver->h);
-        if (w && w[0]) fprintf(stderr, "[Korali] Warning: %s", w);
+        const std::string w = solver->takeWarnings();
+        if (!w.empty()) fprintf(stderr, "[Korali] Warning: %s", w.c_str());
       }
       if (file_enabled && file_frequency > 0 && current_generation % file_frequency == 0) { getConfiguration(); saveState(); }
       current_generation++;

@@ -18,7 +18,7 @@ def lib():
     global _LIB
     if _LIB is None:
         path = os.path.join(_HERE, "libokcma.so")
-        if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(os.path.join(_HERE, "okcma.c")):
+        if not os.path.exists(path) or os.path.getmtime(path) < max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("okcma.c", "odea.c")):
             build()
         _LIB = C.CDLL(path)
     return _LIB
@@ -47,6 +47,23 @@ class Oracle(Handle):
                 out[c] = float(fns[c](xv))
         self._con_cb = CON_CB(tramp)
         self._fn("set_constraints_callback", None, [C.c_void_p, CON_CB, C.c_void_p])(self._h, self._con_cb, None)
+
+
+class OracleDEA:
+    """The DEA oracle (oracle/odea.c) behind the vocabulary of korali_b200._dea.DeaHandle."""
+
+    def __new__(cls, **kw):
+        from korali_b200._dea import DeaHandle
+        kw.pop("device", None)
+        h = DeaHandle(lib(), "odea_", **kw)
+
+        def set_objective(fn, h=h):
+            def tramp(_u, x, n, out):
+                out[0] = float(fn(np.ctypeslib.as_array(x, shape=(n,)).copy()))
+            h._obj_cb = OBJ_CB(tramp)
+            h._fn("set_objective_callback", None, [C.c_void_p, OBJ_CB, C.c_void_p])(h._h, h._obj_cb, None)
+        h.set_objective = set_objective
+        return h
 
 
 def sort_index(f):
