@@ -244,23 +244,58 @@ __global__ void dea_best_ever_kernel(DeaScalars* sc) {
   sc->min_step = INFINITY;   // :280-281: the result of std::min is discarded in the reference — the value stays +Inf
 }
 
-// mean in sample order (:271-273: every term divided by lambda, added for i = 0, 1, ...), max - min per dimension (:275-285)
-__global__ void __launch_bounds__(128)
+// mean in sample order (:271-273: every term divided by lambda, added for i = 0, 1, ...), max - min per dimension (:275-285).
+// The additions of a dimension are one dependent chain (the reference's rounding), lambda x 8 cycles long; everything else is taken
+// off that chain: a block owns 32 dimensions, all 256 threads fetch the next tile of 256 samples x 32 dimensions (32 loads in flight
+// per thread, coalesced) and divide, while warp 0 adds the current tile from shared memory, one lane per dimension.
+constexpr int DM_TS = 256, DM_NT = 256, DM_LD = 33;
+__global__ void __launch_bounds__(DM_NT)
 dea_mean_kernel(const double* __restrict__ X, int ld, long long lambda, int n, double* __restrict__ mean, double* __restrict__ prev_mean,
                 double* __restrict__ maxdist) {
-  const int d = blockIdx.x * blockDim.x + threadIdx.x;
-  if (d >= n) return;
-  prev_mean[d] = mean[d];
+  extern __shared__ double tile[];                 // DM_TS x DM_LD quotients
+  __shared__ double smx[DM_NT], smn[DM_NT];
+  const int tid = threadIdx.x, dd = tid & 31, srow = tid >> 5, d0 = blockIdx.x * 32, d = d0 + dd;
   const double inv = (double)lambda;
+  constexpr int PER = DM_TS * 32 / DM_NT;          // 32 elements per thread and tile: samples srow, srow + 8, ...
   double m = 0.0, mx = -INFINITY, mn = INFINITY;
-  for (long long i = 0; i < lambda; i++) {
-    const double v = X[(size_t)i * ld + d];
-    m = __dadd_rn(m, __ddiv_rn(v, inv));
-    if (v > mx) mx = v;
-    if (v < mn) mn = v;
+  double reg[PER];
+  auto fetch = [&](long long t0) {
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+      const long long i = t0 + srow + 8 * k;
+      reg[k] = (i < lambda && d < n) ? X[(size_t)i * ld + d] : 0.0;
+    }
+  };
+  fetch(0);
+  for (long long t0 = 0; t0 < lambda; t0 += DM_TS) {
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+      const long long i = t0 + srow + 8 * k;
+      if (i < lambda && d < n) { if (reg[k] > mx) mx = reg[k]; if (reg[k] < mn) mn = reg[k]; }
+      tile[(srow + 8 * k) * DM_LD + dd] = __ddiv_rn(reg[k], inv);
+    }
+    __syncthreads();
+    if (t0 + DM_TS < lambda) fetch(t0 + DM_TS);    // in flight while warp 0 walks the chain
+    if (tid < 32) {
+      const int cnt = (int)min((long long)DM_TS, lambda - t0);
+      for (int sidx = 0; sidx < cnt; sidx++) m = __dadd_rn(m, tile[sidx * DM_LD + dd]);
+    }
+    __syncthreads();
   }
-  mean[d] = m;
-  maxdist[d] = __dsub_rn(mx, mn);
+  smx[tid] = mx; smn[tid] = mn;
+  __syncthreads();
+  if (tid < 32 && d < n) {
+    for (int k = 1; k < 8; k++) { mx = fmax(mx, smx[tid + 32 * k]); mn = fmin(mn, smn[tid + 32 * k]); }
+    prev_mean[d] = mean[d];
+    mean[d] = m;
+    maxdist[d] = __dsub_rn(mx, mn);
+  }
+}
+void launch_dea_mean(cudaStream_t st, const double* X, int ld, long long lambda, int n, double* mean, double* prev_mean, double* maxdist) {
+  static std::atomic<unsigned long long> attr{0};
+  const size_t smem = sizeof(double) * DM_TS * DM_LD;
+  if (first_call_on_device(attr)) cudaFuncSetAttribute(dea_mean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  dea_mean_kernel<<<(n + 31) / 32, DM_NT, smem, st>>>(X, ld, lambda, n, mean, prev_mean, maxdist);
 }
 
 char g_dea_create_err[512] = "";
@@ -395,7 +430,7 @@ int kdea_create(const kdea_cfg* cfg, kdea_t** out) {
   DC(cudaMemcpy(h->dF, ninf.data(), sizeof(double) * L, cudaMemcpyHostToDevice));
   DC(cudaMemcpy(h->dFprev, ninf.data(), sizeof(double) * L, cudaMemcpyHostToDevice));
   dea_init_kernel<<<h->num_sms * 4, 256, 0, h->stream>>>(h->dX, h->dXc, ld, h->lambda, N, h->dLower, h->dUpper, cfg->seed);
-  dea_mean_kernel<<<(N + 127) / 128, 128, 0, h->stream>>>(h->dX, ld, h->lambda, N, h->dMean, h->dPrevMean, h->dMaxDist);   // :60-63
+  launch_dea_mean(h->stream, h->dX, ld, h->lambda, N, h->dMean, h->dPrevMean, h->dMaxDist);   // :60-63
   DC(cudaMemset(h->dPrevMean, 0, sizeof(double) * ld));
   DC(cudaMemset(h->dMaxDist, 0, sizeof(double) * ld));
   h->launches += 2;
@@ -501,7 +536,7 @@ int kdea_tell(kdea_t* h) {
   dea_accept_kernel<<<h->num_sms * 4, 256, 0, h->stream>>>(h->dX, h->dXc, ld, L, N, h->dF, h->dFprev, h->cfg.accept_rule, h->dIterAccept, h->dSc,
                                                          h->dCurBest, h->dBestEver);
   dea_best_ever_kernel<<<1, 1, 0, h->stream>>>(h->dSc);
-  dea_mean_kernel<<<(N + 127) / 128, 128, 0, h->stream>>>(h->dX, ld, L, N, h->dMean, h->dPrevMean, h->dMaxDist);
+  launch_dea_mean(h->stream, h->dX, ld, L, N, h->dMean, h->dPrevMean, h->dMaxDist);
   h->launches += 4;
   h->scalars_fresh = false;
   h->gen++;

@@ -46,9 +46,12 @@ def test_lockstep_bit_exact_against_oracle(parent, accept, fix):
     s.close()
 
 
-@pytest.mark.parametrize("n,lam,obj", [(1, 10, "NegSphere"), (33, 257, "NegEllipsoid"), (100, 4096, "NegSphere"), (1000, 2048, "NegEllipsoid")])
-def test_shapes_bit_exact(n, lam, obj):
-    kw = dict(n=n, population_size=lam, objective=obj, lower_bound=-3.0, upper_bound=5.0, seed=5)
+@pytest.mark.parametrize("n,lam,obj,cr", [(1, 10, "NegSphere", 0.9), (33, 257, "NegEllipsoid", 0.9), (100, 4096, "NegSphere", 0.3),
+                                           (1000, 2048, "NegEllipsoid", 0.01)])
+def test_shapes_bit_exact(n, lam, obj, cr):
+    # (with many dimensions and a high crossover rate nearly every mutant leaves the box and the reference's rejection loop :107-118
+    # spins for ever — DEA's own behaviour; the wide cases therefore cross over few dimensions)
+    kw = dict(n=n, population_size=lam, objective=obj, lower_bound=-3.0, upper_bound=5.0, seed=5, crossover_rate=cr)
     s = _dea.Solver(**kw); o = O.OracleDEA(**kw)
     for g in range(4):
         s.run_generation(); o.run_generation()
@@ -82,7 +85,9 @@ def test_host_conduit_matches_device_objective():
 
 
 def test_converges_and_terminates():
-    s = _dea.Solver(n=10, population_size=200, objective="NegSphere", lower_bound=-5.0, upper_bound=5.0, seed=1)
+    # (of the rule combinations only Greedy + Best parent converges fast — Greedy compares a candidate with the PREVIOUS CANDIDATE's value,
+    # :120 and :233, so with random parents the population drifts; the oracle behaves the same way)
+    s = _dea.Solver(n=10, population_size=200, objective="NegSphere", lower_bound=-5.0, upper_bound=5.0, seed=1, parent_selection_rule="Best")
     s.set_scalar("Termination Criteria/Min Value", 1e-9)
     done = s.run(5000)
     fin, why = s.check_termination()
