@@ -123,34 +123,26 @@ dea_mutate_kernel(const double* __restrict__ X, double* __restrict__ Xc, int ld,
   if (lane == 0) infeasible[i] = ok ? 0 : 1;
 }
 
-// infeasible flags -> list of samples to mutate again, their attempt counters, the infeasible counter (:116). Single block.
-__global__ void __launch_bounds__(1024)
+// infeasible flags -> list of samples to mutate again (any order: the mutation of a sample depends on no other candidate), their
+// attempt counters, the infeasible counter (:116). Warp-aggregated atomics on the counter in DeaScalars (zeroed by the caller).
+__global__ void __launch_bounds__(256)
 dea_compact_kernel(const unsigned char* __restrict__ flags, long long lambda, int* __restrict__ rows, unsigned* __restrict__ attempt, DeaScalars* __restrict__ sc) {
-  __shared__ int warp_tot[32];
-  __shared__ int carry;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (long long base = 0; base < lambda; base += 1024) {
+  const int lane = threadIdx.x & 31;
+  for (long long base = (long long)blockIdx.x * blockDim.x; base < lambda; base += (long long)gridDim.x * blockDim.x) {
     const long long j = base + threadIdx.x;
     const bool take = j < lambda && flags[j] != 0;
     const unsigned m = __ballot_sync(0xffffffffu, take);
-    if (lane == 0) warp_tot[warp] = __popc(m);
-    __syncthreads();
-    if (warp == 0) {
-      int x = warp_tot[lane];
-      for (int off = 1; off < 32; off <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, off); if (lane >= off) x += y; }
-      warp_tot[lane] = x;
+    if (m == 0) continue;
+    int pos = 0;
+    if (lane == 0) {
+      pos = atomicAdd(&sc->redo_count, __popc(m));
+      atomicAdd(&sc->infeasible, (unsigned long long)__popc(m));
     }
-    __syncthreads();
-    const int c0 = carry;
-    if (take) { rows[c0 + (warp ? warp_tot[warp - 1] : 0) + __popc(m & ((1u << lane) - 1u))] = (int)j; attempt[j]++; }
-    __syncthreads();
-    if (threadIdx.x == 0) carry = c0 + warp_tot[31];
-    __syncthreads();
+    pos = __shfl_sync(0xffffffffu, pos, 0);
+    if (take) { rows[pos + __popc(m & ((1u << lane) - 1u))] = (int)j; attempt[j]++; }
   }
-  if (threadIdx.x == 0) { sc->redo_count = carry; sc->infeasible += (unsigned long long)carry; }
 }
+__global__ void dea_zero_redo_kernel(DeaScalars* sc) { sc->redo_count = 0; }
 
 // _bestSampleIndex = first maximum of F (std::max_element, :209), previous / current best values (:210-212). Single block.
 __global__ void __launch_bounds__(1024)
@@ -278,7 +270,15 @@ dea_mean_kernel(const double* __restrict__ X, int ld, long long lambda, int n, d
     if (t0 + DM_TS < lambda) fetch(t0 + DM_TS);    // in flight while warp 0 walks the chain
     if (tid < 32) {
       const int cnt = (int)min((long long)DM_TS, lambda - t0);
-      for (int sidx = 0; sidx < cnt; sidx++) m = __dadd_rn(m, tile[sidx * DM_LD + dd]);
+      int sidx = 0;
+      for (; sidx + 16 <= cnt; sidx += 16) {   // 16 quotients loaded together, added in order: the chain runs at the DADD latency
+        double q[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) q[k] = tile[(sidx + k) * DM_LD + dd];
+#pragma unroll
+        for (int k = 0; k < 16; k++) m = __dadd_rn(m, q[k]);
+      }
+      for (; sidx < cnt; sidx++) m = __dadd_rn(m, tile[sidx * DM_LD + dd]);
     }
     __syncthreads();
   }
@@ -470,8 +470,9 @@ int kdea_ask(kdea_t* h) {
                                                                             h->cfg.fix_infeasible, h->cfg.seed, (unsigned)h->gen, h->dSc, h->dInfeasible);
     h->launches++;
     for (int round = 0;; round++) {
-      dea_compact_kernel<<<1, 1024, 0, h->stream>>>(h->dInfeasible, L, h->dRows, h->dAttempt, h->dSc);
-      h->launches++;
+      dea_zero_redo_kernel<<<1, 1, 0, h->stream>>>(h->dSc);
+      dea_compact_kernel<<<(unsigned)std::min<long long>((L + 255) / 256, (long long)h->num_sms * 4), 256, 0, h->stream>>>(h->dInfeasible, L, h->dRows, h->dAttempt, h->dSc);
+      h->launches += 2;
       h->scalars_fresh = false;
       if (dea_pull(h)) return 1;
       const int cnt = h->hSc->redo_count;
