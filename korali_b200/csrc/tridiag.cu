@@ -306,7 +306,11 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
                : "memory");
 }
 
-template <int KU, int NC, int CL = 1, int NT = SY_NT>
+// PF (column prefetch): column c travels ONE STEP EARLIER than it is needed — its owner publishes it in the pass of step c-2 (with the
+// rank-2 updates of the steps <= c-3), every CTA reads it in the pass of step c-1 (long after it was stored: one polling round,
+// off the critical path, its latency hidden behind the pass arithmetic) and applies the updates of the steps c-2 and c-1 itself.
+// The exchange a step waits for is then p = A v alone: half the polled bytes, and the column's stores leave the chain.
+template <int KU, int NC, int CL = 1, int NT = SY_NT, bool PF = false>
 __global__ void __launch_bounds__(NT, 1)
 sytrd_reg_kernel(const double* __restrict__ M, int ld, int n, int ns /* n rounded up to even: LL stride per parity, vector stride */,
                  LL* __restrict__ xP, LL* __restrict__ xC, double* __restrict__ dT, double* __restrict__ eT, double* __restrict__ tauv,
@@ -322,6 +326,7 @@ sytrd_reg_kernel(const double* __restrict__ M, int ld, int n, int ns /* n rounde
   double* cbuf = pp + NC * NT;  // CL > 1: received column / product entries pushed by the cluster leader, 2 parities x ns each
   double* pbuf = cbuf + 2 * ns;
   __shared__ __align__(8) unsigned long long mbar;
+  static_assert(!(PF && CL > 1), "the prefetch variant has no cluster path");
   const unsigned crank = CL > 1 ? cluster_ctarank() : 0u;
   if (CL > 1) {
     if (tid == 0) mbar_init(&mbar, (NT / 32));   // one arrival per warp of the leader and step
@@ -345,7 +350,13 @@ sytrd_reg_kernel(const double* __restrict__ M, int ld, int n, int ns /* n rounde
   // polling round serialise in the L2 slice that owns the line; CTA b reads copy b % copies, the producers write all copies.
   const size_t cstride = 4 * (size_t)ns;
   const size_t my_copy = (size_t)(b % copies) * cstride;
-  if (b == 0)   // owner of column 0 publishes it for step 0
+  double cn[2 * KU];   // PF: column i with the updates of the steps <= i-2, this thread's rows (columns 0 and 1 come from M itself)
+#pragma unroll
+  for (int j = 0; j < 2 * KU; j++) {
+    const int r = 2 * (tid + NT * (j >> 1)) + (j & 1);
+    cn[j] = (PF && r < n) ? M[r] : 0.0;
+  }
+  if (!PF && b == 0)   // owner of column 0 publishes it for step 0
     for (int r = tid; r < n; r += NT)
       for (int q = 0; q < copies; q++) ll_store(xC + q * cstride + r, M[r], 1ull);
   __syncthreads();
@@ -365,9 +376,27 @@ sytrd_reg_kernel(const double* __restrict__ M, int ld, int n, int ns /* n rounde
     for (int j = 0; j < 2 * KU; j++) {
       const int r = 2 * (tid + NT * (j >> 1)) + (j & 1);
       if (r >= i && r < n) need |= 1u << j;
-      cv[j] = 0.0; pq[j] = 0.0;
+      cv[j] = (PF && r >= i && r < n) ? cn[j] : 0.0; pq[j] = 0.0;
     }
-    if (have_p && (opt & 1) && crank == 0) {   // one lane per warp spins on one slot first: 148 x 256 threads polling everything back to back saturate the L2
+    if (have_p && (opt & 4) && crank == 0) {
+      // Gate: a few lanes spin on ONE slot per producer — the products of the last G columns (every CTA that still owns a column
+      // publishes exactly one of them), plus the last row of the column when it travels in this step — and only then does the
+      // block read its 2 x 16 KB of slots, once. A round of everybody polling everything is ~1000 cycles of L2 traffic
+      // (148 CTAs x 32 KB) that the late producers' stores queue behind (profiles/r02_pf_stamps.log).
+      const int lo = max(i, n - G) & ~1;
+      const int npairs = (ns - lo) >> 1;
+      if (tid < npairs) {
+        const int r0 = lo + 2 * tid;
+        const bool n0 = r0 >= i && r0 < n, n1 = r0 + 1 < n;
+        unsigned long long q[4];
+        do { ll_load2(Pin + r0, q); } while ((n0 && q[1] != tag) || (n1 && q[3] != tag));
+      } else if (!PF && tid == NT - 1) {
+        unsigned long long q[4];
+        const bool n0 = ns - 2 >= i, n1 = ns - 1 < n;
+        do { ll_load2(Cin + ns - 2, q); } while ((n0 && q[1] != tag) || (n1 && q[3] != tag));
+      }
+      __syncthreads();
+    } else if (have_p && (opt & 1) && crank == 0) {   // one lane per warp spins on one slot first: 148 x 256 threads polling everything back to back saturate the L2
       if (lane == 0 && need) {
         const int j0 = __ffs(need) - 1;
         (void)ll_wait(Pin + 2 * (tid + NT * (j0 >> 1)) + (j0 & 1), tag);
@@ -375,7 +404,7 @@ sytrd_reg_kernel(const double* __restrict__ M, int ld, int n, int ns /* n rounde
       __syncwarp();
     }
     if (crank == 0) {
-      unsigned pc = need, ppn = have_p ? need : 0u;
+      unsigned pc = PF ? 0u : need, ppn = have_p ? need : 0u;
       while (pc | ppn) {
         unsigned long long qc[KU][4], qp[KU][4];
 #pragma unroll
@@ -478,9 +507,27 @@ sytrd_reg_kernel(const double* __restrict__ M, int ld, int n, int ns /* n rounde
     if (pr) prof[(i - prof_step0) * 8 + 2] = clock64();
     // ---- pass over this CTA's columns c >= i+1 (registers): rank-2 update of step i-1, partial p = A v_i, publication of column i+1
     LL* Pout = xP + (size_t)(par ^ 1) * ns;
-    LL* Cout = xC + (size_t)(par ^ 1) * ns;
+    LL* Cout = xC + (size_t)(PF ? par : (par ^ 1)) * ns;     // PF: column i+2 (tag i+3) goes where column i was
     const unsigned long long otag = tag + 1ull;
+    const unsigned long long ctag = PF ? tag + 2ull : otag;
+    const int cpub = PF ? i + 2 : i + 1;
     const int s0 = (i + 1 > b) ? (i + 1 - b + G - 1) / G : 0;
+    // PF: column i+1 (published one step ago, tag i+2) — the loads fly during the pass
+    unsigned long long qn[KU][4];
+    unsigned pn = 0;
+    if (PF) {
+#pragma unroll
+      for (int j = 0; j < 2 * KU; j++) {
+        const int r = 2 * (tid + NT * (j >> 1)) + (j & 1);
+        if (r >= i + 1 && r < n) pn |= 1u << j;
+      }
+      if (i > 0) {
+        const LL* Cnx = xC + my_copy + (size_t)(par ^ 1) * ns;
+#pragma unroll
+        for (int k = 0; k < KU; k++)
+          if ((pn >> (2 * k)) & 3u) ll_load2(Cnx + 2 * (tid + NT * k), qn[k]);
+      }
+    }
 #pragma unroll
     for (int s = 0; s < NC; s++) {
       if (s >= s0 && s < nloc) {
@@ -495,15 +542,48 @@ sytrd_reg_kernel(const double* __restrict__ M, int ld, int n, int ns /* n rounde
           A[k][s][0] = a0; A[k][s][1] = a1;
           dot += a0 * vnw[2 * k];
           dot += a1 * vnw[2 * k + 1];
-          if (c == i + 1) {
+          if (c == cpub) {
             const int r = 2 * (tid + NT * k);
             for (int q = 0; q < copies; q++) {
-              if (r > i && r < n) ll_store(Cout + q * cstride + r, a0, otag);
-              if (r + 1 > i && r + 1 < n) ll_store(Cout + q * cstride + r + 1, a1, otag);
+              if (r > i && r < n) ll_store(Cout + q * cstride + r, a0, ctag);
+              if (r + 1 > i && r + 1 < n) ll_store(Cout + q * cstride + r + 1, a1, ctag);
             }
           }
         }
         pp[s * NT + tid] = dot;
+      }
+    }
+    if (PF) {   // column i+1 for the next step: received with the updates <= i-2, update i-1 applied here (v, w still hold step i-1)
+      const double wc1 = wsm[i + 1], vc1 = vs_old[i + 1];
+      if (i == 0) {
+        const double* src = M + (size_t)ld;
+#pragma unroll
+        for (int j = 0; j < 2 * KU; j++) {
+          const int r = 2 * (tid + NT * (j >> 1)) + (j & 1);
+          cn[j] = (pn & (1u << j)) ? src[r] : 0.0;
+        }
+      } else {
+        const LL* Cnx = xC + my_copy + (size_t)(par ^ 1) * ns;
+        unsigned left = pn;
+        for (;;) {
+#pragma unroll
+          for (int k = 0; k < KU; k++)
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+              const unsigned bit = 1u << (2 * k + h);
+              if ((left & bit) && qn[k][2 * h + 1] == otag) {
+                cn[2 * k + h] = col_upd(__longlong_as_double((long long)qn[k][2 * h]), v[2 * k + h], wc1, w[2 * k + h], vc1);
+                left &= ~bit;
+              }
+            }
+          if (!left) break;
+#pragma unroll
+          for (int k = 0; k < KU; k++)
+            if ((left >> (2 * k)) & 3u) ll_load2(Cnx + 2 * (tid + NT * k), qn[k]);
+        }
+#pragma unroll
+        for (int j = 0; j < 2 * KU; j++)
+          if (!(pn & (1u << j))) cn[j] = 0.0;
       }
     }
     __syncthreads();
@@ -844,13 +924,23 @@ bool tridiag_stage_sytrd(cudaStream_t st, TridiagWs* ws, const double* M) {
   long long* prof = ws->prof;
   int prof_step0 = ws->prof_step0, prof_cta = ws->prof_cta;
   void* args[] = {&M, &Awork, &ld, &n, &ns, &xP, &xC, &dT, &eT, &tau, &VR, &prof, &prof_step0, &prof_cta};
-  int opt = 1;
+  // exchange: 1 = one lane per warp spins on one slot before the block polls everything; 4 = a gate on one slot per producer first
+  // (same time at N = 1000, 0.33 -> 0.28 ms at N = 100 where a step is short: profiles/r02_sytrd_exchange_ab.log)
+  int opt = n <= 512 ? 4 : 1;
   if (const char* oe = getenv("KCMA_SYTRD_OPT")) opt = atoi(oe);
   int copies = ws->ll_copies;
   void* rargs[] = {&M, &ld, &n, &ns, &xP, &xC, &dT, &eT, &tau, &VR, &prof, &prof_step0, &prof_cta, &opt, &copies};
   const void* fn = ws->reg_variant == 1 ? (const void*)sytrd_reg_kernel<1, 4> : ws->reg_variant == 2 ? (const void*)sytrd_reg_kernel<2, 7>
                    : ws->reg_variant == 3 ? (const void*)sytrd_reg_kernel<3, 11> : ws->reg_variant == 4 ? (const void*)sytrd_reg_kernel<2, 14>
                    : (const void*)sytrd_kernel;
+  // column prefetch (sytrd_reg_kernel<..., PF = true>): measured and NOT adopted (config 3: sytrd 4.67 against 4.30 ms — the column's
+  // loads come back late inside the pass, profiles/r02_sytrd_exchange_ab.log); KCMA_SYTRD_PREFETCH=1 selects it for A/B runs
+  bool pf = false;
+  if (const char* pe = getenv("KCMA_SYTRD_PREFETCH")) pf = atoi(pe) != 0;
+  if (pf && ws->cluster <= 1) {
+    if (ws->reg_variant == 1) fn = (const void*)sytrd_reg_kernel<1, 4, 1, SY_NT, true>;
+    else if (ws->reg_variant == 2) fn = (const void*)sytrd_reg_kernel<2, 7, 1, SY_NT, true>;
+  }
   if (ws->cluster > 1) {   // <2,7> with a cluster leader that polls for its peers (geometry checked in tridiag_ws_create)
     const void* cfn = ws->cluster == 4 ? (const void*)sytrd_reg_kernel<2, 7, 4> : (const void*)sytrd_reg_kernel<2, 7, 2>;
     cudaLaunchConfig_t cfg;
