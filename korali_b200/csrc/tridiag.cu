@@ -35,20 +35,27 @@ constexpr int SY_NW = SY_NT / 32;
 constexpr size_t kSmemCap = 227 * 1024 - 1024;
 
 struct __align__(16) LL { double v; unsigned long long tag; };
+#ifdef KC_LL_GPU_SCOPE
+#define KC_LL_ST "st.relaxed.gpu.global"
+#define KC_LL_LD "ld.relaxed.gpu.global"
+#else
+#define KC_LL_ST "st.volatile.global"
+#define KC_LL_LD "ld.volatile.global"
+#endif
 
 __device__ __forceinline__ void ll_store(LL* p, double v, unsigned long long tag) {
-  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"((unsigned long long)__double_as_longlong(v)), "l"(tag) : "memory");
+  asm volatile(KC_LL_ST ".v2.u64 [%0], {%1, %2};" ::"l"(p), "l"((unsigned long long)__double_as_longlong(v)), "l"(tag) : "memory");
 }
 __device__ __forceinline__ double ll_wait(const LL* p, unsigned long long tag) {
   unsigned long long a, b;
   do {
-    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+    asm volatile(KC_LL_LD ".v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
   } while (b != tag);
   return __longlong_as_double((long long)a);
 }
 
 __device__ __forceinline__ void ll_load(const LL* p, unsigned long long& a, unsigned long long& b) {
-  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+  asm volatile(KC_LL_LD ".v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
 
 // Sum over the block, identical bits in every thread (and in every CTA: same thread count, same order). ONE barrier: `slot`
@@ -276,7 +283,7 @@ sytrd_kernel(const double* __restrict__ M, double* __restrict__ Awork, int ld, i
 // the columns is then register arithmetic (the shared-memory variant moved 250 KB per step through the 128 B/clk shared-memory
 // pipe); shared memory only carries what is looked up by COLUMN index (w[c], v[c]) and the per-thread partial products.
 __device__ __forceinline__ void ll_load2(const LL* p, unsigned long long (&q)[4]) {
-  asm volatile("ld.volatile.global.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(q[0]), "=l"(q[1]), "=l"(q[2]), "=l"(q[3]) : "l"(p) : "memory");
+  asm volatile(KC_LL_LD ".v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(q[0]), "=l"(q[1]), "=l"(q[2]), "=l"(q[3]) : "l"(p) : "memory");
 }
 
 // ---- thread-block clusters (CL > 1): only the leader CTA of a cluster polls the L2 slots and pushes what it received into its
@@ -503,7 +510,9 @@ sytrd_reg_kernel(const double* __restrict__ M, int ld, int n, int ns /* n rounde
       if (r < ns) vs_new[r] = vnw[j];
     }
     if (b == i % G && tid == 0) { dT[i] = di; eT[i] = ei; tauv[i] = tau; }   // the owner of the retired column records the step
-    __syncthreads();
+    // no barrier here: wsm (read by column index in the pass) was written in front of the second block sum's barrier, and vs_new
+    // is first read — as vs_old — behind the first block sum's barrier of the next step; the cluster variant keeps its barrier
+    if (CL > 1) __syncthreads();
     if (pr) prof[(i - prof_step0) * 8 + 2] = clock64();
     // ---- pass over this CTA's columns c >= i+1 (registers): rank-2 update of step i-1, partial p = A v_i, publication of column i+1
     LL* Pout = xP + (size_t)(par ^ 1) * ns;
@@ -537,11 +546,11 @@ sytrd_reg_kernel(const double* __restrict__ M, int ld, int n, int ns /* n rounde
 #pragma unroll
         for (int k = 0; k < KU; k++) {
           double a0 = A[k][s][0], a1 = A[k][s][1];
-          a0 -= v[2 * k] * wc + w[2 * k] * vc;
-          a1 -= v[2 * k + 1] * wc + w[2 * k + 1] * vc;
+          a0 = __fma_rn(-w[2 * k], vc, __fma_rn(-v[2 * k], wc, a0));              // two dependent DFMA instead of DMUL, DFMA, DADD
+          a1 = __fma_rn(-w[2 * k + 1], vc, __fma_rn(-v[2 * k + 1], wc, a1));
           A[k][s][0] = a0; A[k][s][1] = a1;
-          dot += a0 * vnw[2 * k];
-          dot += a1 * vnw[2 * k + 1];
+          dot = __fma_rn(a0, vnw[2 * k], dot);
+          dot = __fma_rn(a1, vnw[2 * k + 1], dot);
           if (c == cpub) {
             const int r = 2 * (tid + NT * k);
             for (int q = 0; q < copies; q++) {
