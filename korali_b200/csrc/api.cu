@@ -61,6 +61,11 @@ struct kcma {
   bool has_bounds = false, any_min_sd = false;
   uint64_t lambda = 0, mu = 0, vlambda = 0, vmu = 0, cur_lambda = 0, cur_mu = 0, s_max = 0, mu_max = 0;
   uint64_t shard_lo = 0, shard_hi = 0;       // this rank's samples of the CURRENT population
+  // Constraint path on several ranks: the correction loop of handleConstraints (:774-832) updates the constraint normals sample by
+  // sample in population order, so every rank draws and corrects the WHOLE population (same Philox counters, same arithmetic:
+  // bitwise the one-GPU run) and only the model evaluations are sharded: rank r evaluates [eval_lo, eval_hi), F is all-gathered.
+  bool repl = false;
+  uint64_t eval_lo = 0, eval_hi = 0;
   uint64_t max_local = 0, max_zrows = 0;     // allocation bounds
   double mueff = 0, cs = 0, cc = 0, damp = 0, chi_n = 0, trace = 0;
   std::vector<double> h_weights;
@@ -288,9 +293,13 @@ void set_population(kcma* h, uint64_t lambda, uint64_t mu) {
   h->cur_lambda = lambda;
   h->cur_mu = mu;
   kcma_shard_range(lambda, h->cfg.mirrored_sampling, h->cfg.rank, h->cfg.nranks, &h->shard_lo, &h->shard_hi);
+  h->eval_lo = h->shard_lo; h->eval_hi = h->shard_hi;
+  if (h->repl) { h->shard_lo = 0; h->shard_hi = lambda; }
 }
 
 uint64_t local_samples(const kcma* h) { return h->shard_hi - h->shard_lo; }
+uint64_t eval_samples(const kcma* h) { return h->eval_hi - h->eval_lo; }
+uint64_t eval_row0(const kcma* h) { return h->eval_lo - h->shard_lo; }     // first evaluated row of the local X / Y
 uint64_t local_zrows(const kcma* h) { return h->cfg.mirrored_sampling ? local_samples(h) / 2 : local_samples(h); }
 
 // VT = B^T (vectors as rows) after B was set from outside the eigensolver.
@@ -546,7 +555,7 @@ int settle_resampling_budget(kcma* h, long long ls, unsigned long long zrow_begi
   const int N = h->N, ld = h->ld, mirrored = h->cfg.mirrored_sampling;
   const unsigned long long maxres = h->cfg.max_infeasible_resamplings;
   const long long zrows = mirrored ? ls / 2 : ls;
-  const int nr = h->cfg.nranks, rank = h->cfg.rank;
+  const int nr = h->repl ? 1 : h->cfg.nranks, rank = h->repl ? 0 : h->cfg.rank;
   std::vector<unsigned> att((size_t)zrows);
   std::vector<unsigned char> flag((size_t)ls);
   CUDA_OK(h, cudaMemcpyAsync(att.data(), h->dAttempt, sizeof(unsigned) * zrows, cudaMemcpyDeviceToHost, h->stream));
@@ -634,7 +643,7 @@ int resample_infeasible(kcma* h, long long ls, unsigned long long zrow_begin) {
   int* dRows = (int*)h->dSelS;                     // reuse: the selection list is rebuilt in tell()
   unsigned* dAttempt = h->dAttempt;                // zeroed per generation
   const unsigned long long maxres = h->cfg.max_infeasible_resamplings;
-  const bool multi = h->cfg.nranks > 1;
+  const bool multi = h->cfg.nranks > 1 && !h->repl;
   unsigned char* dFresh = (h->cfg.mirrored_sampling && maxres != 0) ? h->dFresh : nullptr;
   if (dFresh) CUDA_OK(h, cudaMemsetAsync(dFresh, 1, local_zrows(h), h->stream));
   unsigned long long count_before = 0, local_counted = 0;
@@ -901,15 +910,15 @@ int do_eval(kcma* h) {
   if (h->inj_f) { h->inj_f = false; return 0; }
   if (want_grad && h->host_obj_grad) {  // batched host conduit, model returns F and dF/dx
     PhaseTimer t(h, "host_objective");
-    const size_t ls = local_samples(h), N = h->N;
+    const size_t ls = eval_samples(h), N = h->N;
     h->hX.resize(ls * N); h->hF.resize(ls); h->hGrad.resize(ls * N);
-    CUDA_OK(h, cudaMemcpy2DAsync(h->hX.data(), sizeof(double) * N, h->dX, sizeof(double) * h->ld, sizeof(double) * N, ls, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(h, cudaMemcpy2DAsync(h->hX.data(), sizeof(double) * N, h->dX + eval_row0(h) * h->ld, sizeof(double) * h->ld, sizeof(double) * N, ls, cudaMemcpyDeviceToHost, h->stream));
     CUDA_OK(h, cudaStreamSynchronize(h->stream));
     h->host_obj_grad(h->host_obj_user, h->hX.data(), (uint64_t)ls, (uint64_t)N, h->hF.data(), h->hGrad.data());
     for (size_t i = 0; i < ls; i++)
       if (!std::isfinite(h->hF[i])) return fail(h, "Non finite value of function evaluation detected: %f\n", h->hF[i]);
-    CUDA_OK(h, cudaMemcpyAsync(h->dF + h->shard_lo, h->hF.data(), sizeof(double) * ls, cudaMemcpyHostToDevice, h->stream));
-    CUDA_OK(h, cudaMemcpy2DAsync(h->dGrad, sizeof(double) * h->ld, h->hGrad.data(), sizeof(double) * N, sizeof(double) * N, ls, cudaMemcpyHostToDevice, h->stream));
+    CUDA_OK(h, cudaMemcpyAsync(h->dF + h->eval_lo, h->hF.data(), sizeof(double) * ls, cudaMemcpyHostToDevice, h->stream));
+    CUDA_OK(h, cudaMemcpy2DAsync(h->dGrad + eval_row0(h) * h->ld, sizeof(double) * h->ld, h->hGrad.data(), sizeof(double) * N, sizeof(double) * N, ls, cudaMemcpyHostToDevice, h->stream));
     CUDA_OK(h, cudaStreamSynchronize(h->stream));
     return 0;
   }
@@ -917,18 +926,18 @@ int do_eval(kcma* h) {
     return fail(h, "Use Gradient Information: the model must return gradients (kcma_set_host_objective_grad or KCMA_INJ_GRAD)");
   if (h->dev_obj) {   // user objective on the device: one call for the whole shard, X and F never leave HBM
     PhaseTimer t(h, "device_objective");
-    const long long ls = (long long)local_samples(h);
-    h->dev_obj(h->dev_obj_user, h->dX, (uint64_t)ls, (uint64_t)h->N, (uint64_t)h->ld, h->dF + h->shard_lo, (void*)h->stream);
-    launch_check_finite(h->stream, h->dF + h->shard_lo, ls, h->dSc);
+    const long long ls = (long long)eval_samples(h);
+    h->dev_obj(h->dev_obj_user, h->dX + eval_row0(h) * h->ld, (uint64_t)ls, (uint64_t)h->N, (uint64_t)h->ld, h->dF + h->eval_lo, (void*)h->stream);
+    launch_check_finite(h->stream, h->dF + h->eval_lo, ls, h->dSc);
     h->launches++;
     h->scalars_fresh = false;
     return 0;
   }
   if (h->host_obj) {  // batched host conduit
     PhaseTimer t(h, "host_objective");
-    const size_t ls = local_samples(h), N = h->N;
+    const size_t ls = eval_samples(h), N = h->N;
     h->hX.resize(ls * N); h->hF.resize(ls);
-    CUDA_OK(h, cudaMemcpy2DAsync(h->hX.data(), sizeof(double) * N, h->dX, sizeof(double) * h->ld, sizeof(double) * N, ls, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(h, cudaMemcpy2DAsync(h->hX.data(), sizeof(double) * N, h->dX + eval_row0(h) * h->ld, sizeof(double) * h->ld, sizeof(double) * N, ls, cudaMemcpyDeviceToHost, h->stream));
     CUDA_OK(h, cudaStreamSynchronize(h->stream));
     h->host_obj(h->host_obj_user, h->hX.data(), (uint64_t)ls, (uint64_t)N, h->hF.data());
     for (size_t i = 0; i < ls; i++)  // ref: optimization.cpp.base:32-33
@@ -939,21 +948,21 @@ int do_eval(kcma* h) {
         if (push_scalars(h)) return 1;
         h->hF[i] = -1e300;
       }
-    CUDA_OK(h, cudaMemcpyAsync(h->dF + h->shard_lo, h->hF.data(), sizeof(double) * ls, cudaMemcpyHostToDevice, h->stream));
+    CUDA_OK(h, cudaMemcpyAsync(h->dF + h->eval_lo, h->hF.data(), sizeof(double) * ls, cudaMemcpyHostToDevice, h->stream));
     return 0;
   }
   if (h->cfg.objective == KCMA_OBJ_EXTERNAL) return fail(h, "objective is External: inject the Value Vector with kcma_inject(KCMA_INJ_F) or set a host objective before eval");
   PhaseTimer t(h, "objective");
-  const long long ls = (long long)local_samples(h);
-  double* f_local = h->dF + h->shard_lo;
-  const double* src = h->inj_x ? h->dX : h->dY;
+  const long long ls = (long long)eval_samples(h);
+  double* f_local = h->dF + h->eval_lo;
+  const double* src = (h->inj_x ? h->dX : h->dY) + eval_row0(h) * h->ld;
   if (launch_objective(h->stream, h->cfg.objective, src, h->ld, ls, h->N, h->cfg.mirrored_sampling, h->inj_x ? 1 : 0, h->dMean,
                        h->dSc, h->dCoef, f_local, h->num_sms))
     return fail(h, "unknown objective id %d", h->cfg.objective);
   h->launches++;
   if (want_grad && !have_grad) {
     launch_objective_gradient(h->stream, h->cfg.objective, src, h->ld, ls, h->N, h->cfg.mirrored_sampling, h->inj_x ? 1 : 0, h->dMean,
-                              h->dSc, h->dCoef, h->dGrad, h->ld, h->num_sms);
+                              h->dSc, h->dCoef, h->dGrad + eval_row0(h) * h->ld, h->ld, h->num_sms);
     h->launches++;
   }
   h->scalars_fresh = false;
@@ -963,13 +972,17 @@ int do_eval(kcma* h) {
 int do_tell(kcma* h) {
   const int N = h->N, ld = h->ld;
   const int lambda = (int)h->cur_lambda, mu = (int)h->cur_mu;
-  const int multi = h->cfg.nranks > 1;
+  const int multi = h->cfg.nranks > 1 && !h->repl;   // repl: every rank holds the whole population, nothing to reduce
   const int from_x = h->inj_x ? 1 : 0;
   const double* rows_src = from_x ? h->dX : h->dY;
-  if (multi) {
+  if (h->cfg.nranks > 1) {
     if (!h->comm) return fail(h, "nranks > 1 but kcma_comm_init was not called");
     PhaseTimer t(h, "collectives");
-    if (nccl_check(h, g_nccl.AllGather(h->dF + h->shard_lo, h->dF, local_samples(h), ncclFloat64, h->comm, h->stream), "all-gather(F)")) return 1;
+    if (nccl_check(h, g_nccl.AllGather(h->dF + h->eval_lo, h->dF, eval_samples(h), ncclFloat64, h->comm, h->stream), "all-gather(F)")) return 1;
+    if (h->repl) {   // a non-finite F(x) of ANY rank fails the generation on EVERY rank (end_of_generation reads the flag)
+      launch_check_finite(h->stream, h->dF, (long long)h->cur_lambda, h->dSc);
+      h->launches++;
+    }
   }
   {
     PhaseTimer t(h, "sort");
@@ -1249,12 +1262,13 @@ int kcma_create(const kcma_cfg* cfg, kcma_t** out) {
     if ((cfg->target_success_rate <= 0.0) || (cfg->target_success_rate > 1.0)) CREATE_FAIL("Invalid Target Success Rate (%f), must be greater than 0.0 and less than 1.0\n", cfg->target_success_rate);
     if (cfg->covariance_matrix_adaption_strength <= 0.0) CREATE_FAIL("Invalid Adaption Size (%f), must be greater than 0.0\n", cfg->covariance_matrix_adaption_strength);
   }
+  h->repl = h->has_constraints && cfg->nranks > 1;
   set_population(h, h->is_viability ? vlambda : lambda, h->is_viability ? vmu : mu);
   {
     uint64_t lo, hi;
     kcma_shard_range(h->s_max, cfg->mirrored_sampling, cfg->rank, cfg->nranks, &lo, &hi);
     h->max_local = hi - lo;
-    if (h->has_constraints) h->max_local = (h->s_max + cfg->nranks - 1) / cfg->nranks + 1;
+    if (h->has_constraints) h->max_local = h->repl ? h->s_max + 1 : (h->s_max + cfg->nranks - 1) / cfg->nranks + 1;
     h->max_zrows = cfg->mirrored_sampling ? h->max_local / 2 : h->max_local;
   }
   const size_t nn = (size_t)N * ld;
@@ -1288,8 +1302,8 @@ int kcma_create(const kcma_cfg* cfg, kcma_t** out) {
   CREATE_CUDA(dmalloc(&h->dSc, 1));
   CREATE_CUDA(dmalloc(&h->dAttempt, h->max_zrows + 16));
   if (h->has_constraints) {
-    if (cfg->nranks > 1) CREATE_FAIL("the constraint path (viability regime) runs on one GPU in this build (nranks must be 1)");
     if (cfg->constraint_family != KCMA_CON_HALFSPACE && cfg->constraint_family != KCMA_CON_EXTERNAL) CREATE_FAIL("unknown constraint family %d", cfg->constraint_family);
+    if (cfg->nranks > 1 && cfg->use_gradient_information) CREATE_FAIL("Use Gradient Information together with constraints runs on one GPU (nranks must be 1)");
     h->ldg = (long long)h->s_max;
     h->u_rows = round_up((int)std::min<uint64_t>(h->n_con * h->s_max, 1u << 22), 16) + 32;
     CREATE_CUDA(dmalloc(&h->dG, h->n_con * h->s_max)); CREATE_CUDA(dmalloc(&h->dBounds, h->n_con)); CREATE_CUDA(dmalloc(&h->dNormal, h->n_con * ld));
@@ -1795,7 +1809,7 @@ int kcma_get_scalar(kcma_t* h, const char* key, double* out) {
   U("Is Viability Regime", h->is_viability) U("Has Constraints", h->has_constraints)
   U("Best Valid Sample", (long long)h->hSc->best_valid_sample)
   U("Termination Criteria/Max Infeasible Resamplings", h->cfg.max_infeasible_resamplings)
-  U("Shard Begin", h->shard_lo) U("Shard End", h->shard_hi)
+  U("Shard Begin", h->eval_lo) U("Shard End", h->eval_hi)   // the samples this rank evaluates
 #undef U
   return fail(h, "unknown scalar key '%s'", key);
 }

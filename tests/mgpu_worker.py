@@ -33,7 +33,13 @@ def main():
                   upper_bound=5.0, max_infeasible_resamplings=10**9, mirrored_sampling=1),
              # discrete variables: the mutations are keyed by the GLOBAL sample index, so the sharding must not change them
              dict(n=24, population_size=128, objective="NegEllipsoid", initial_value=2.2, initial_stddev=1.5, seed=17, mirrored_sampling=1,
-                  granularity=np.array([1.0, 0.0, 0.5, 0.0] * 6))]
+                  granularity=np.array([1.0, 0.0, 0.5, 0.0] * 6)),
+             # constraint path (viability regime, then the regime switch): the correction loop of handleConstraints is sequential
+             # in the population order, so every rank draws and corrects the whole population and only the model evaluations are
+             # sharded (all-gather of F) - the run is BITWISE the one-GPU run
+             dict(n=20, population_size=64, viability_population_size=64, objective="NegSphereSin2", constraint_family="HalfSpace",
+                  n_constraints=4, constraint_shift=np.array([1.0, 1.0, -1.0, -1.0]), lower_bound=-10.0, upper_bound=10.0,
+                  initial_value=np.array([4.0, 4.0, -2.0, -2.0] + [0.0] * 16), initial_stddev=1.0, is_sigma_bounded=1, seed=1337)]
     verbose = os.environ.get("KCMA_TEST_VERBOSE")
     for case in cases:
         if verbose:
@@ -45,11 +51,26 @@ def main():
         dist.broadcast(uid, 0)
         s.comm_init(bytes(uid.cpu().tolist()))
         ref = _lib.Solver(device=local, **case) if rank == 0 else None
-        for g in range(40 if "granularity" in case else 12):   # discrete: long enough for the masking matrix to switch on
+        constrained = "n_constraints" in case
+        saw_viability = saw_switch = False
+        for g in range(40 if ("granularity" in case or constrained) else 12):   # discrete: long enough for the masking matrix to switch on
             if verbose:
                 print("rank", rank, "gen", g, flush=True)
             s.run_generation()
-            if ref is not None:
+            if constrained:
+                v = s.scalar("Is Viability Regime")
+                saw_viability |= v != 0
+                saw_switch |= saw_viability and v == 0
+            if ref is not None and constrained:
+                ref.run_generation()
+                for k in ["Value Vector", "Current Mean", "Evolution Path", "Conjugate Evolution Path", "Covariance Matrix", "Viability Boundaries",
+                          "Normal Constraint Approximation"]:
+                    assert np.array_equal(s.get(k), ref.get(k)), (case["objective"], g, k)
+                assert np.array_equal(s.get_index("Sorting Index"), ref.get_index("Sorting Index")), g
+                for k in ["Sigma", "Best Ever Value", "Infeasible Sample Count", "Resampled Parameter Count", "Covariance Matrix Adaptation Count",
+                          "Constraint Evaluation Count", "Is Viability Regime", "Global Success Rate"]:
+                    assert s.scalar(k) == ref.scalar(k), (g, k, s.scalar(k), ref.scalar(k))
+            elif ref is not None:
                 ref.run_generation()
                 if g == 0:   # identical samples (global Philox counters) -> identical F and ranking, bit for bit
                     assert np.array_equal(s.get("Value Vector"), ref.get("Value Vector")), (case["objective"], g)
@@ -73,6 +94,8 @@ def main():
         assert (lo, hi) == _lib.shard_range(case["population_size"], case.get("mirrored_sampling", 0), rank, world)
         if "granularity" in case:
             assert s.scalar("Number Of Discrete Mutations") > 0
+        if constrained:
+            assert saw_viability and saw_switch, "the case must run through the viability regime and leave it"
         s.close()
         if rank == 0:
             print("ok", case["objective"], "world", world, flush=True)

@@ -22,7 +22,7 @@ def test_sharded_population_matches_single_gpu():
            "--master-port", "29533", os.path.join(ROOT, "tests", "mgpu_worker.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
-    assert out.stdout.count("ok ") == 7
+    assert out.stdout.count("ok ") == 8
 
 
 def _korali_run(devices, objective="Rosenbrock", n=64, pop=512, gens=12, mirrored=False):
