@@ -32,12 +32,40 @@ __device__ __forceinline__ double unit_open52(uint32_t lo, uint32_t hi) {
 
 // One thread per (row, column pair). Z is row-major with leading dimension ldz (even), pads stay zero.
 // row_list (nullable): regenerate only these local rows (resampling); attempt (nullable): per-row attempt counters.
+__device__ __forceinline__ void philox_normal_pair(double* __restrict__ Z, int ldz, int n, long long row, int p, unsigned long long grow,
+                                                   unsigned att, unsigned generation, unsigned long long seed) {
+  uint32_t r[4];
+  philox4x32_10((uint32_t)p, (uint32_t)grow, att, generation, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+  const double u1 = unit_open52(r[0], r[1]);
+  const double u2 = unit_open52(r[2], r[3]);
+  const double rad = sqrt(-2.0 * log(u1));
+  double s, c;
+  sincospi(2.0 * u2, &s, &c);
+  double* dst = Z + (size_t)row * ldz + 2 * p;
+  if (2 * p + 1 < n) {
+    *reinterpret_cast<double2*>(dst) = make_double2(rad * c, rad * s);
+  } else {
+    dst[0] = rad * c;
+  }
+}
+
+// WIDE = true (npairs >= 128): a CTA walks rows, its threads the pairs of a row - no 64-bit division per draw
+template <bool WIDE>
 __global__ void __launch_bounds__(256)
 philox_normal_kernel(double* __restrict__ Z, int ldz, long long rows, int n, unsigned long long seed, unsigned generation,
                      unsigned long long row_begin, const unsigned* __restrict__ attempt,
                      const int* __restrict__ row_list, const DevScalars* __restrict__ gen_src) {
   if (generation == kGenFromDevice) generation = (unsigned)gen_src->gen;   // CUDA-graph replay
   const int npairs = (n + 1) >> 1;
+  if (WIDE) {
+    for (long long li = blockIdx.x; li < rows; li += gridDim.x) {
+      const long long row = row_list ? row_list[li] : li;
+      const unsigned long long grow = row_begin + (unsigned long long)row;
+      const unsigned att = attempt ? attempt[row] : 0u;
+      for (int p = threadIdx.x; p < npairs; p += blockDim.x) philox_normal_pair(Z, ldz, n, row, p, grow, att, generation, seed);
+    }
+    return;
+  }
   const long long total = rows * npairs;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -46,19 +74,7 @@ philox_normal_kernel(double* __restrict__ Z, int ldz, long long rows, int n, uns
     const long long row = row_list ? row_list[li] : li;
     const unsigned long long grow = row_begin + (unsigned long long)row;
     const unsigned att = attempt ? attempt[row] : 0u;
-    uint32_t r[4];
-    philox4x32_10((uint32_t)p, (uint32_t)grow, att, generation, (uint32_t)seed, (uint32_t)(seed >> 32), r);
-    const double u1 = unit_open52(r[0], r[1]);
-    const double u2 = unit_open52(r[2], r[3]);
-    const double rad = sqrt(-2.0 * log(u1));
-    double s, c;
-    sincospi(2.0 * u2, &s, &c);
-    double* dst = Z + (size_t)row * ldz + 2 * p;
-    if (2 * p + 1 < n) {
-      *reinterpret_cast<double2*>(dst) = make_double2(rad * c, rad * s);
-    } else {
-      dst[0] = rad * c;
-    }
+    philox_normal_pair(Z, ldz, n, row, p, grow, att, generation, seed);
   }
 }
 
@@ -137,7 +153,14 @@ void launch_philox_normal(cudaStream_t st, double* Z, int ldz, long long rows, i
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)num_sms * 16;
   if (blocks > cap) blocks = cap;
-  philox_normal_kernel<<<(unsigned)blocks, 256, 0, st>>>(Z, ldz, rows, n, seed, generation, row_begin, attempt, row_list, gen_src);
+  const int npairs = (n + 1) / 2;
+  if (npairs >= 128) {
+    const unsigned g = (unsigned)std::min<long long>(rows, cap);
+    if (npairs <= 160) philox_normal_kernel<true><<<g, 128, 0, st>>>(Z, ldz, rows, n, seed, generation, row_begin, attempt, row_list, gen_src);
+    else philox_normal_kernel<true><<<g, 256, 0, st>>>(Z, ldz, rows, n, seed, generation, row_begin, attempt, row_list, gen_src);
+    return;
+  }
+  philox_normal_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(Z, ldz, rows, n, seed, generation, row_begin, attempt, row_list, gen_src);
 }
 
 void launch_philox_raw(cudaStream_t st, const uint32_t* in6, uint32_t* out4) {
