@@ -381,7 +381,7 @@ def ours_arm(args, rank, world):
                      "frac_of_dmma_issue_peak": (achieved / peaks["fp64_dmma_issue_tflops"]) if peaks.get("fp64_dmma_issue_tflops") else None,
                      "algorithmic_flops_per_launch": f_sample, "avg_launch_ms": gemm_avg},
         "phases_ms_per_generation": {k: (v[0] / args.steps) for k, v in phases.items()},
-        "rank_mu": {"kernel": "syrk_tt_tma_kernel", "avg_ms": rk_avg, "achieved_tflops": (f_rank / (rk_avg * 1e-3) * 1e-12) if rk_avg > 0 else 0.0,
+        "rank_mu": {"kernel": "syrk_sk_tma_kernel (stream-K over the lower-triangular tiles, triangular warp tiling of the diagonal tiles)", "avg_ms": rk_avg, "achieved_tflops": (f_rank / (rk_avg * 1e-3) * 1e-12) if rk_avg > 0 else 0.0,
                     "algorithmic_flops_per_launch": f_rank},
         # the HBM-side kernels of a generation: algorithmic bytes / phase time against the measured copy bandwidth
         "hbm_kernels": hbm_block(phases, args.steps, n, lam // world, mu // world, peaks.get("hbm_gbs", 6547.2)),

@@ -862,8 +862,7 @@ int update_and_handle_constraints(kcma* h) {
         if (!aborted) {
           const int rows_padded = std::min(h->u_rows, round_up(J, 16) + 16);
           launch_constraint_scale(h->stream, h->dU, ld, N, h->dEvSample, h->dCount, h->dViol, h->cov_adaption_factor, rows_padded);
-          splits = syrk_pick_splits(N, J, h->num_sms, h->max_splits);
-          launch_syrk_tt(h->stream, N, J, nullptr, h->dU, ld, h->u_rows, h->dWsplit, ld, splits);
+          splits = launch_syrk(h->stream, N, J, nullptr, h->dU, ld, h->u_rows, h->dWsplit, ld, J, h->num_sms, h->max_splits);
           h->launches += 2;
         }
       }
@@ -1024,8 +1023,7 @@ int do_tell(kcma* h) {
       // the number of selected samples this rank owns is only known on the device (dCount); size the split-K for its
       // expectation mu * local / lambda and let the kernel read the exact row count
       const int expect = (int)std::min<uint64_t>(max_count, (uint64_t)mu * local_samples(h) / h->cur_lambda + 1);
-      splits = syrk_pick_splits(N, expect, h->num_sms, h->max_splits);
-      launch_syrk_tt(h->stream, N, max_count, h->dCount, h->dS, ld, h->s_rows_padded, h->dWsplit, ld, splits);
+      splits = launch_syrk(h->stream, N, max_count, h->dCount, h->dS, ld, h->s_rows_padded, h->dWsplit, ld, expect, h->num_sms, h->max_splits);
     }
     h->launches++;
     if (multi) { launch_reduce_splits(h->stream, h->dWsplit, ld, splits, N, h->dRed); h->launches++; }
@@ -1934,10 +1932,9 @@ int kcma_k_rank_mu(int device, uint64_t n, uint64_t rows, const double* t, const
   }
   double *dS, *dW, *dP;
   K_CUDA(dmalloc(&dS, rp * ld));
-  const int splits = syrk_pick_splits(N, (int)rows, sms, 16);
-  K_CUDA(dmalloc(&dW, (size_t)splits * N * ld)); K_CUDA(dmalloc(&dP, (size_t)N * ld));
+  K_CUDA(dmalloc(&dW, (size_t)16 * N * ld)); K_CUDA(dmalloc(&dP, (size_t)N * ld));
   K_CUDA(cudaMemcpy2D(dS, sizeof(double) * ld, s.data(), sizeof(double) * N, sizeof(double) * N, rows, cudaMemcpyHostToDevice));
-  launch_syrk_tt(0, N, (int)rows, nullptr, dS, ld, (long long)rp, dW, ld, splits);
+  const int splits = launch_syrk(0, N, (int)rows, nullptr, dS, ld, (long long)rp, dW, ld, (int)rows, sms, 16);
   launch_reduce_splits(0, dW, ld, splits, N, dP);
   std::vector<double> p((size_t)N * N);
   K_CUDA(cudaMemcpy2D(p.data(), sizeof(double) * N, dP, sizeof(double) * ld, sizeof(double) * N, N, cudaMemcpyDeviceToHost));

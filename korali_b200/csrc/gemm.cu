@@ -268,4 +268,18 @@ void launch_syrk_tt(cudaStream_t st, int n, int K, const int* kptr, const double
   syrk_tt_kernel<<<grid, THREADS, syrk_tt_smem_bytes(), st>>>(n, K, kptr, S, lds, W, ldw);
 }
 
+// The rank-mu product with the scheduling chosen here: stream-K over the triangular tiles (gemm_tma.cu) by default, the split-K
+// kernels with KCMA_SYRK=splitk (A/B runs) or when the TMA path is unavailable. Returns the number of slabs of W to sum.
+int launch_syrk(cudaStream_t st, int n, int K, const int* kptr, const double* S, int lds, long long s_rows, double* W, int ldw,
+                int expect_rows, int num_sms, int max_splits) {
+  const char* e = getenv("KCMA_SYRK");
+  if (want_tma() && !(e && !strcmp(e, "splitk"))) {
+    const int parts = launch_syrk_sk_tma(st, n, K, kptr, S, lds, s_rows, W, ldw, num_sms, max_splits);
+    if (parts > 0) return parts;
+  }
+  const int splits = syrk_pick_splits(n, expect_rows, num_sms, max_splits);
+  launch_syrk_tt(st, n, K, kptr, S, lds, s_rows, W, ldw, splits);
+  return splits;
+}
+
 }  // namespace kc

@@ -27,7 +27,11 @@ int syrk_pick_splits(int n, int K, int num_sms, int max_splits);
 void launch_syrk_tt(cudaStream_t st, int n, int K, const int* kptr, const double* S, int lds, long long s_rows, double* W, int ldw,
                     int splits);
 
+int launch_syrk(cudaStream_t st, int n, int K, const int* kptr, const double* S, int lds, long long s_rows, double* W, int ldw,
+                int expect_rows, int num_sms, int max_splits);
 // gemm_tma.cu (TMA + mbarrier staging; return false when the tensor maps cannot be built)
+int launch_syrk_sk_tma(cudaStream_t st, int n, int K, const int* kptr, const double* S, int lds, long long s_rows, double* W, int ldw,
+                       int num_sms, int max_splits);
 bool launch_gemm_tn_tma(cudaStream_t st, int M, int Nc, int K, const double* A, int lda, const double* B, int ldb, double* C, int ldc);
 bool launch_syrk_tt_tma(cudaStream_t st, int n, int K, const int* kptr, const double* S, int lds, long long s_rows, double* W, int ldw,
                         int splits);
