@@ -5,6 +5,7 @@
 // each pass = per-block digit histogram -> single-block exclusive scan -> stable scatter. Stability inside a
 // block comes from warp-striped ownership + __match_any_sync ranks, so equal keys keep ascending index.
 // The whole sorted order is produced (weights depend on the rank of every one of the top-mu samples).
+#include <cooperative_groups.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -135,6 +136,90 @@ sort_scatter_kernel(const unsigned long long* __restrict__ keys_in, const unsign
   }
 }
 
+// ---- the eight passes in ONE cooperative launch (populations up to one 2048-key tile per SM) -----------------------------------
+// A pass keeps its tile in registers between the histogram and the scatter (the three-launch version reads it twice), the digit
+// offsets of a CTA are formed by the CTA itself from the block-major histogram table (256 threads <-> 256 digits, 32 coalesced
+// loads each at lambda = 65536), and the passes are separated by grid barriers instead of launch boundaries: 25 launches of a
+// few microseconds each become one. Same warp-striped ownership and ranks as sort_scatter_kernel: the order is bit-identical.
+__global__ void __launch_bounds__(SORT_THREADS)
+sort_fused_kernel(const double* __restrict__ f, int n, unsigned long long* k0, unsigned long long* k1, unsigned* v0, unsigned* v1,
+                  unsigned* sorted_idx, unsigned* hist) {   // (the ping-pong buffers change roles per pass: no __restrict__, L2 loads)
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  __shared__ unsigned wcount[SORT_THREADS / 32][256];
+  __shared__ unsigned dscan[256];
+  __shared__ unsigned wtot[SORT_THREADS / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nblocks = gridDim.x;
+  const int base = blockIdx.x * SORT_TILE + warp * (32 * SORT_ITEMS);
+  const unsigned lt = (1u << lane) - 1u;
+  for (int pass = 0; pass < 8; pass++) {
+    const int shift = 8 * pass;
+    for (int i = threadIdx.x; i < (SORT_THREADS / 32) * 256; i += SORT_THREADS) (&wcount[0][0])[i] = 0;
+    __syncthreads();
+    unsigned long long k[SORT_ITEMS];
+    unsigned v[SORT_ITEMS], loc[SORT_ITEMS], dig[SORT_ITEMS];
+#pragma unroll
+    for (int r = 0; r < SORT_ITEMS; r++) {
+      const int i = base + r * 32 + lane;
+      const bool ok = i < n;
+      if (pass == 0) { k[r] = ok ? desc_key(f[i]) : 0ull; v[r] = (unsigned)i; }
+      else { k[r] = ok ? __ldcg(k0 + i) : 0ull; v[r] = ok ? __ldcg(v0 + i) : 0u; }
+      dig[r] = ok ? ((unsigned)(k[r] >> shift) & 255u) : 0xffffffffu;
+      const unsigned peers = __match_any_sync(0xffffffffu, dig[r]);
+      unsigned old = 0;
+      if (ok) old = wcount[warp][dig[r]];
+      __syncwarp();
+      if (ok && (peers & lt) == 0) wcount[warp][dig[r]] = old + __popc(peers);
+      __syncwarp();
+      loc[r] = old + __popc(peers & lt);
+    }
+    __syncthreads();
+    const int d = threadIdx.x;
+    unsigned mine = 0;
+#pragma unroll
+    for (int w = 0; w < SORT_THREADS / 32; w++) mine += wcount[w][d];
+    hist[blockIdx.x * 256 + d] = mine;
+    __threadfence();
+    grid.sync();
+    // offset of digit d in this block = keys with a smaller digit anywhere + keys with digit d in earlier blocks
+    unsigned total = 0, before = 0;
+    for (int b = 0; b < nblocks; b++) {
+      const unsigned c = __ldcg(hist + b * 256 + d);
+      if (b < (int)blockIdx.x) before += c;
+      total += c;
+    }
+    unsigned x = total;   // exclusive scan of the digit totals over the 256 threads
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, x, off); if (lane >= off) x += y; }
+    if (lane == 31) wtot[warp] = x;
+    __syncthreads();
+    unsigned wbase = 0;
+#pragma unroll
+    for (int w = 0; w < SORT_THREADS / 32; w++) if (w < warp) wbase += wtot[w];
+    unsigned running = wbase + x - total + before;
+#pragma unroll
+    for (int w = 0; w < SORT_THREADS / 32; w++) {
+      const unsigned c = wcount[w][d];
+      wcount[w][d] = running;
+      running += c;
+    }
+    __syncthreads();
+    unsigned* vout = (pass == 7) ? sorted_idx : v1;
+#pragma unroll
+    for (int r = 0; r < SORT_ITEMS; r++) {
+      if (dig[r] != 0xffffffffu) {
+        const unsigned pos = wcount[warp][dig[r]] + loc[r];
+        if (pass < 7) k1[pos] = k[r];
+        vout[pos] = v[r];
+      }
+    }
+    __threadfence();
+    grid.sync();
+    unsigned long long* tk = k0; k0 = k1; k1 = tk;
+    unsigned* tv = v0; v0 = v1; v1 = tv;
+  }
+}
+
 // hist kernel uses block-striped reads; the scatter kernel uses warp-striped reads of the SAME tile, so the
 // per-block histograms agree.
 size_t sort_workspace_bytes(int n) {
@@ -194,6 +279,13 @@ int launch_sort_index(cudaStream_t st, const double* f, int n, void* workspace, 
   unsigned* v0 = (unsigned*)w; w += sizeof(unsigned) * (size_t)n;
   unsigned* v1 = (unsigned*)w; w += sizeof(unsigned) * (size_t)n;
   unsigned* hist = (unsigned*)w;
+  static const int fused_on = getenv("KCMA_SORT_FUSED") ? atoi(getenv("KCMA_SORT_FUSED")) : 1;
+  if (fused_on && nblocks <= num_sms) {   // one cooperative launch (every CTA must be resident: one tile per SM at most)
+    const double* fp = f;
+    void* args[] = {&fp, &n, &k0, &k1, &v0, &v1, &sorted_idx, &hist};
+    if (cudaLaunchCooperativeKernel((const void*)sort_fused_kernel, dim3(nblocks), dim3(SORT_THREADS), args, 0, st) == cudaSuccess) return 1;
+    cudaGetLastError();
+  }
   int gk = (n + 255) / 256;
   if (gk > num_sms * 8) gk = num_sms * 8;
   sort_make_keys_kernel<<<gk, 256, 0, st>>>(f, n, k0, v0);
