@@ -100,36 +100,52 @@ select_local_kernel(const unsigned* __restrict__ idx, const double* __restrict__
 // ---- K5: gather selected rows, weighted mean partials, and the rank-mu operand ------------------------
 // For selected entry j: sample s, weight w: x = m + (+-sigma) y_s ; t = x - m ; S[j][:] = sqrt(w) * t ;
 // partial[cta][:] += w * x  (mean, :603-609).  from_x: x is read from the injected "Sample Population".
+constexpr int GM_ROWS_MAX = 64;   // rows_per_cta of the callers
+constexpr int GM_UNROLL = 8;      // rows in flight per thread (the kernel is a 262 MB read + 262 MB write stream at config 3)
 __global__ void __launch_bounds__(256)
 gather_mean_kernel(const double* __restrict__ Y, int ldy, int mirrored, int from_x, const int* __restrict__ sel_sample,
                    const double* __restrict__ sel_weight, const int* __restrict__ count_ptr, int rows_per_cta, int n, int ld,
                    const double* __restrict__ mean, const DevScalars* __restrict__ sc, double* __restrict__ S, int lds,
                    double* __restrict__ partial) {
+  __shared__ long long row_off[GM_ROWS_MAX];   // element offset of the sample's row in Y
+  __shared__ double row_w[GM_ROWS_MAX], row_rw[GM_ROWS_MAX], row_ss[GM_ROWS_MAX];
   const int count = *count_ptr;
   const int j0 = blockIdx.x * rows_per_cta;
   const int j1 = min(count, j0 + rows_per_cta);
+  const int nr = j1 - j0;
   const double sigma = sc->sigma;
+  for (int r = threadIdx.x; r < nr; r += blockDim.x) {   // per-row quantities once per CTA instead of once per thread
+    const int s = sel_sample[j0 + r];
+    const double w = sel_weight[j0 + r];
+    row_off[r] = (long long)((from_x || !mirrored) ? s : (s >> 1)) * ldy;
+    row_w[r] = w;
+    row_rw[r] = sqrt(fabs(w));   // Proportional weights can be negative: the sign is applied by signed_rank_mu_kernel
+    row_ss[r] = (mirrored && (s & 1)) ? -sigma : sigma;
+  }
+  __syncthreads();
   for (int c = threadIdx.x; 2 * c < ld; c += blockDim.x) {
     const int d = 2 * c;
     const bool in0 = d < n, in1 = d + 1 < n;
     const double m0 = in0 ? mean[d] : 0.0, m1 = in1 ? mean[d + 1] : 0.0;
     double a0 = 0.0, a1 = 0.0;
-    for (int j = j0; j < j1; j++) {
-      const int s = sel_sample[j];
-      const double w = sel_weight[j];
-      double x0, x1;
-      if (from_x) {
-        const double2 v = *reinterpret_cast<const double2*>(Y + (size_t)s * ldy + d);
-        x0 = v.x; x1 = v.y;
-      } else {
-        const double2 v = *reinterpret_cast<const double2*>(Y + (size_t)(mirrored ? (s >> 1) : s) * ldy + d);
-        const double ss = (mirrored && (s & 1)) ? -sigma : sigma;
-        x0 = m0 + ss * v.x; x1 = m1 + ss * v.y;
+    for (int r0 = 0; r0 < nr; r0 += GM_UNROLL) {
+      double2 v[GM_UNROLL];
+#pragma unroll
+      for (int u = 0; u < GM_UNROLL; u++)
+        if (r0 + u < nr) v[u] = __ldcs(reinterpret_cast<const double2*>(Y + row_off[r0 + u] + d));
+#pragma unroll
+      for (int u = 0; u < GM_UNROLL; u++) {
+        const int r = r0 + u;
+        if (r < nr) {
+          double x0, x1;
+          if (from_x) { x0 = v[u].x; x1 = v[u].y; }
+          else { const double ss = row_ss[r]; x0 = m0 + ss * v[u].x; x1 = m1 + ss * v[u].y; }
+          const double rw = row_rw[r], w = row_w[r];
+          const double t0 = in0 ? rw * (x0 - m0) : 0.0, t1 = in1 ? rw * (x1 - m1) : 0.0;
+          *reinterpret_cast<double2*>(S + (size_t)(j0 + r) * lds + d) = make_double2(t0, t1);
+          a0 += w * x0; a1 += w * x1;      // in row order: the partial mean does not depend on the unrolling
+        }
       }
-      const double rw = sqrt(fabs(w));   // Proportional weights can be negative: the sign is applied by signed_rank_mu_kernel
-      const double t0 = in0 ? rw * (x0 - m0) : 0.0, t1 = in1 ? rw * (x1 - m1) : 0.0;
-      *reinterpret_cast<double2*>(S + (size_t)j * lds + d) = make_double2(t0, t1);
-      a0 += w * x0; a1 += w * x1;
     }
     *reinterpret_cast<double2*>(partial + (size_t)blockIdx.x * ld + d) = make_double2(in0 ? a0 : 0.0, in1 ? a1 : 0.0);
   }
