@@ -212,6 +212,7 @@ class SolverBase {
   virtual std::vector<double> array(const char* key) = 0;
   virtual void printGeneration(const std::function<void(int, const char*)>& log) = 0;   // printGenerationAfter
   virtual std::string takeWarnings() { return ""; }
+  virtual bool needsPython() const { return true; }   // a generation calls back into Python (models, constraints): the GIL stays held
   virtual std::vector<std::pair<std::string, std::string>> sideCars() { return {}; }      // (key, file suffix) of N x N arrays saved as .npy
   virtual size_t variableCount() const = 0;
   void splitReasons(const char* reason) {
@@ -661,10 +662,13 @@ class CMAES : public SolverBase {
       if (failed) korali_error("%s", kcma_last_error(hs[failed - 1]));
       return;
     }
-    const int rc = kcma_run_generation(h);
+    int rc;
+    if (!needsPython()) { py::gil_scoped_release nogil; rc = kcma_run_generation(h); }   // other experiments' threads run meanwhile
+    else rc = kcma_run_generation(h);
     if (!pending_error.empty()) { std::string e = pending_error; pending_error.clear(); throw std::runtime_error(e); }
     check(rc);
   }
+  bool needsPython() const override { return cfg.objective == KCMA_OBJ_EXTERNAL || !constraints.empty(); }
 
   // generated getConfiguration (CMAES.cpp:1784-1881): settings + internal state under Korali's key names.
   // Size policy: lambda x N arrays are exported only when small (they cannot be serialised at scale).
@@ -946,10 +950,13 @@ class DEA : public SolverBase {
 
   void runGeneration() override {
     pending_error.clear();
-    const int rc = kdea_run_generation(h);
+    int rc;
+    if (!needsPython()) { py::gil_scoped_release nogil; rc = kdea_run_generation(h); }
+    else rc = kdea_run_generation(h);
     if (!pending_error.empty()) { std::string e = pending_error; pending_error.clear(); throw std::runtime_error(e); }
     check(rc);
   }
+  bool needsPython() const override { return cfg.objective == KCMA_OBJ_EXTERNAL; }
 
   void printGeneration(const std::function<void(int, const char*)>& log) override {   // DEA::printGenerationAfter :290-299
     char b[256];
@@ -1158,6 +1165,8 @@ class Experiment : public KoraliJson {
     os.attr("link")(target, latest);
   }
 
+  bool needsPython() const { return !solver || solver->needsPython(); }
+
   // Experiment::run (experiment.cpp.base:39-118)
   void run() {
     auto t0 = std::chrono::steady_clock::now();
@@ -1239,9 +1248,39 @@ class Engine : public KoraliJson {
     e.initialize(devices());
     e.run();
   }
+  // k.run([e1, e2, ...]) (engine.cpp:98-111: the reference interleaves the experiments by coroutine switches on one core).
+  // Here, with k["Conduit"]["Devices"] = G > 1 and device objectives, the experiments run CONCURRENTLY: experiment j on device
+  // j mod G, one host thread per device, the GIL released while a generation is on the GPU (results are those of the separate
+  // runs: an experiment never spans devices in this mode). Otherwise the experiments run one after the other.
   void runMany(std::vector<Experiment*> es) {
-    for (auto* e : es) { e->initialize(devices()); }
-    for (auto* e : es) e->run();   // the reference interleaves experiments by coroutine switches; results are identical
+    const std::vector<int> dev = devices();
+    const size_t G = dev.size();
+    bool parallel = es.size() > 1 && G > 1;
+    if (parallel) {
+      for (size_t j = 0; j < es.size(); j++) es[j]->initialize({dev[j % G]});
+      for (auto* e : es) parallel = parallel && !e->needsPython();
+    }
+    if (!parallel) {
+      for (auto* e : es) { e->initialize(dev); }
+      for (auto* e : es) e->run();
+      return;
+    }
+    std::vector<std::string> errors(G);
+    {
+      py::gil_scoped_release nogil;
+      std::vector<std::thread> workers;
+      for (size_t g = 0; g < G; g++)
+        workers.emplace_back([&, g]() {
+          for (size_t j = g; j < es.size() && errors[g].empty(); j += G) {
+            py::gil_scoped_acquire gil;
+            try { es[j]->run(); }
+            catch (py::error_already_set& ex) { errors[g] = ex.what(); }
+            catch (std::exception& ex) { errors[g] = ex.what(); }
+          }
+        });
+      for (auto& w : workers) w.join();
+    }
+    for (auto& e : errors) if (!e.empty()) throw std::runtime_error(e);
   }
 };
 

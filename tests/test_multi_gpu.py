@@ -25,10 +25,10 @@ def test_sharded_population_matches_single_gpu():
     assert out.stdout.count("ok ") == 8
 
 
-def _korali_run(devices, objective="Rosenbrock", n=64, pop=512, gens=12, mirrored=False):
+def _korali_experiment(objective="Rosenbrock", n=64, pop=512, gens=12, mirrored=False, seed=21):
     import korali_b200 as korali
     e = korali.Experiment()
-    e["Random Seed"] = 21
+    e["Random Seed"] = seed
     e["Problem"]["Type"] = "Optimization"
     e["Problem"]["Objective Function"] = objective
     for i in range(n):
@@ -41,12 +41,40 @@ def _korali_run(devices, objective="Rosenbrock", n=64, pop=512, gens=12, mirrore
     e["Solver"]["Termination Criteria"]["Max Generations"] = gens
     e["Console Output"]["Verbosity"] = "Silent"
     e["File Output"]["Enabled"] = False
+    return e
+
+
+def _korali_run(devices, **kw):
+    import korali_b200 as korali
+    e = _korali_experiment(**kw)
     k = korali.Engine()
     k["Conduit"]["Type"] = "Device"
     if devices is not None:
         k["Conduit"]["Devices"] = devices
     k.run(e)
     return e
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_engine_runs_several_experiments_concurrently_on_several_devices():
+    """k.run([e1, ..., e5]) with k["Conduit"]["Devices"] = 2 (engine.cpp:98-111 interleaves experiments by coroutine switches on one
+    core): experiment j runs on device j mod 2, the two device threads run side by side. An experiment never spans devices in this
+    mode, so every result is BITWISE the result of running that experiment alone."""
+    import korali_b200 as korali
+    seeds = [3, 5, 8, 13, 21]
+    alone = [_korali_run(None, seed=s_, n=40, pop=256, gens=15) for s_ in seeds]
+    es = [_korali_experiment(seed=s_, n=40, pop=256, gens=15) for s_ in seeds]
+    k = korali.Engine()
+    k["Conduit"]["Type"] = "Device"
+    k["Conduit"]["Devices"] = 2
+    k.run(es)
+    for a, b in zip(alone, es):
+        assert b["Current Generation"] == 15
+        assert a["Results"]["Best Sample"]["F(x)"] == b["Results"]["Best Sample"]["F(x)"]
+        assert a["Solver"]["Current Mean"] == b["Solver"]["Current Mean"]
+        assert a["Solver"]["Sigma"] == b["Solver"]["Sigma"]
+    assert len({e["Results"]["Best Sample"]["F(x)"] for e in es}) == len(seeds)   # different seeds, different runs
 
 
 @pytest.mark.gpu
