@@ -332,12 +332,14 @@ dc_secular_kernel(const DcNode* __restrict__ nodes, const int* __restrict__ row2
   for (int i = lane; i < K; i += 32) row[i] = (dlp[i] - dorg) - mu;
 }
 
-// ---- Loewner weights: block = 32 consecutive poles x 8 slices of the product over the roots ----------------------------
-__global__ void __launch_bounds__(256)
+// ---- Loewner weights: block = 32 consecutive poles x 32 slices of the product over the roots (a slice is a dependent chain of
+// K / 32 divisions: 32 steps at the top merge of N = 1000 instead of the 125 of the 8-slice version) ---------------------------------
+constexpr int LW_SLICES = 32;
+__global__ void __launch_bounds__(32 * LW_SLICES)
 dc_loewner_kernel(const DcNode* __restrict__ nodes, const int* __restrict__ row2node, int n_total, const double* __restrict__ dl,
                   const double* __restrict__ w, const int* __restrict__ Kcnt, const double* __restrict__ DELTA, int ld,
                   double* __restrict__ what) {
-  __shared__ double part[8][33];
+  __shared__ double part[LW_SLICES][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int g = blockIdx.x * 32 + tx;
   double prod = 1.0;
@@ -350,7 +352,7 @@ dc_loewner_kernel(const DcNode* __restrict__ nodes, const int* __restrict__ row2
     if (i < K) {
       live = true;
       const double di = dl[off + i];
-      for (int j = ty; j < K; j += 8) {
+      for (int j = ty; j < K; j += LW_SLICES) {
         const double dji = DELTA[(size_t)(off + j) * ld + off + i];
         prod *= (j == i) ? dji : dji / (di - dl[off + j]);
       }
@@ -361,7 +363,7 @@ dc_loewner_kernel(const DcNode* __restrict__ nodes, const int* __restrict__ row2
   if (ty == 0 && live) {
     double p = part[0][tx];
 #pragma unroll
-    for (int k = 1; k < 8; k++) p *= part[k][tx];
+    for (int k = 1; k < LW_SLICES; k++) p *= part[k][tx];
     what[off + i] = copysign(sqrt(fabs(p)), w[off + i]);
   }
 }
@@ -455,7 +457,7 @@ bool dc_solve(cudaStream_t st, TridiagWs* ws, int* launches) {
                                             ws->nd_col, ws->defl_col, ws->rho, ws->Kcnt, ws->mixed, ws->rot_p, ws->rot_q, ws->rot_c,
                                             ws->rot_s);
     dc_secular_kernel<<<warp_blocks, 256, 0, st>>>(ws->d_nodes, r2n, n, ws->dl, ws->w, ws->rho, ws->Kcnt, ws->lam, ws->DELTA, ld);
-    dc_loewner_kernel<<<(n + 31) / 32, 256, 0, st>>>(ws->d_nodes, r2n, n, ws->dl, ws->w, ws->Kcnt, ws->DELTA, ld, ws->what);
+    dc_loewner_kernel<<<(n + 31) / 32, 32 * LW_SLICES, 0, st>>>(ws->d_nodes, r2n, n, ws->dl, ws->w, ws->Kcnt, ws->DELTA, ld, ws->what);
     dc_vectors_kernel<<<warp_blocks, 256, 0, st>>>(ws->d_nodes, r2n, n, ws->lam, ws->defl_val, ws->defl_col, ws->col2k, ws->Kcnt,
                                                    ws->what, ws->DELTA, ld, ws->UT, dnext);
     const int msplit = (l == ws->levels) ? ws->split_top : 1;   // the top merge is ONE product: split-K fills the SMs

@@ -621,6 +621,8 @@ sytrd_reg_kernel(const double* __restrict__ M, int ld, int n, int ns /* n rounde
   if (CL > 1) cluster_sync_all();   // no CTA may exit while a peer can still write into its shared memory
 }
 
+// (A single-CTA variant for N <= 128 — the whole matrix in the registers of one CTA, no exchange, four block barriers per step — was
+// built and measured at N = 100: 0.338 ms against 0.294 ms for the 25-CTA exchange kernel (profiles/r02_eigen_ab13.log); not kept.)
 // ---- compact-WY panel factor (dlarft, forward / columnwise): T upper triangular, nb x nb, from G = V^T V and tau ------------
 // Column p: T[0:p, p] = -tau_p T[0:p, 0:p] G[0:p, p]. The columns are sequential; inside a column two threads share a row's
 // inner product (interleaved terms, one shuffle). G arrives as `gsplits` split-K slabs (summed here in a fixed order) and is read
@@ -658,6 +660,52 @@ larft_kernel(const double* __restrict__ Gbuf, long long gstride, int gsplits, co
     __syncthreads();
   }
   for (int i = tid; i < nb * nb; i += LARFT_NT) Tbuf[(size_t)panel * nb * nb + i] = T[(i / nb) * lt + (i % nb)];
+}
+
+// The same factor, all columns at once: T is the inverse of the upper triangular S = striu(G) + diag(1 / tau) (the column recurrence of
+// dlarft is the column-by-column inverse of S), so column j follows from S t_j = e_j by back substitution on its own:
+//   t_jj = tau_j,   t_ij = -tau_i sum_{k = i+1 .. j} G_ik t_kj   (i = j-1 .. 0).
+// One WARP per column (lane l keeps t_k for k = l mod 32), rows of G prefetched four steps ahead: nb dependent steps of one shuffle
+// reduction each, instead of nb block-wide steps of two barriers each (0.20 ms -> ~0.02 ms per decomposition at N = 1000).
+// tau_j = 0 (H_j = I) gives a zero row and column like the recurrence does. Needs nb <= 128, nb % 32 == 0.
+__global__ void __launch_bounds__(256)
+larft_cols_kernel(const double* __restrict__ Gbuf, const double* __restrict__ tauv, int n_refl, int nb, double* __restrict__ Tbuf) {
+  const int panel = blockIdx.y, lane = threadIdx.x & 31;
+  const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (j >= nb) return;
+  const int p0 = panel * nb, kb = min(nb, n_refl - p0);
+  const double* __restrict__ G = Gbuf + (size_t)panel * nb * nb;
+  double* __restrict__ T = Tbuf + (size_t)panel * nb * nb;
+  double t[4] = {0.0, 0.0, 0.0, 0.0};
+  if (j < kb) {
+    constexpr int PF = 4;
+    double g[PF][4];
+    auto load = [&](int i, double (&row)[4]) {
+#pragma unroll
+      for (int q = 0; q < 4; q++) { const int k = lane + 32 * q; row[q] = (i >= 0 && k > i && k <= j) ? G[(size_t)i * nb + k] : 0.0; }
+    };
+#pragma unroll
+    for (int a = 0; a < PF; a++) load(j - 1 - a, g[a]);
+    if (lane == (j & 31)) t[j >> 5] = tauv[p0 + j];
+    for (int i0 = j - 1; i0 >= 0; i0 -= PF) {
+#pragma unroll
+      for (int a = 0; a < PF; a++) {
+        const int i = i0 - a;
+        if (i < 0) break;     // warp-uniform
+        double acc = 0.0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) acc = __fma_rn(g[a][q], t[q], acc);
+        acc = warp_sum_butterfly(acc);
+        const double ti = -tauv[p0 + i] * acc;
+#pragma unroll
+        for (int q = 0; q < 4; q++) if ((i >> 5) == q && lane == (i & 31)) t[q] = ti;
+      }
+#pragma unroll
+      for (int a = 0; a < PF; a++) load(i0 - PF - a, g[a]);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; q++) { const int i = lane + 32 * q; if (i < nb) T[(size_t)i * nb + j] = (i <= j) ? t[q] : 0.0; }
 }
 
 // sign[i] = -1 if the component of largest magnitude of row i (first on ties) is negative — the convention of rayleigh_kernel
@@ -765,8 +813,12 @@ TridiagWs* tridiag_ws_create(int n, int ld, int num_sms, char* err, size_t errle
   }
   // ---- stage 2 tree: uniform depth, even leaf boundaries, leaves of 2..32 rows
   int levels = 0;
+  // largest leaf: 12 rows (KCMA_DC_LEAF=<4..30> for A/B runs). Smaller leaves = cheaper Jacobi leaves, more merge levels: at N = 100 the
+  // stage takes 0.38 ms with leaves of 25 rows, 0.25 with 6; at N = 1000 0.79 ms with 16 rows, 0.75 with 8 (profiles/r02_eigen_ab12.log)
+  int leaf_rows = 12;
+  if (const char* le = getenv("KCMA_DC_LEAF")) { const int v = atoi(le); if (v >= 4 && v <= 30) leaf_rows = v; }
   if (n > 32)
-    while ((n + (1 << levels) - 1) / (1 << levels) > 30) levels++;
+    while ((n + (1 << levels) - 1) / (1 << levels) > leaf_rows) levels++;
   const int leaves = 1 << levels;
   ws->bounds.resize(leaves + 1);
   for (int k = 0; k <= leaves; k++) ws->bounds[k] = (k == leaves) ? n : round_even((double)k * n / leaves);
@@ -991,7 +1043,9 @@ bool tridiag_stage_back_fork(cudaStream_t st, TridiagWs* ws, int* launches) {
     G = ws->Gred;
     *launches += 1;
   }
-  larft_kernel<<<ws->npanels, LARFT_NT, sizeof(double) * (nb * (nb + 1) + nb), s2>>>(G, 0, 1, ws->tau, n_refl, nb, ws->Tbuf);
+  static const int larft_cols = getenv("KCMA_LARFT_COLS") ? atoi(getenv("KCMA_LARFT_COLS")) : 1;
+  if (larft_cols && nb <= 128 && nb % 32 == 0) larft_cols_kernel<<<dim3((nb + 7) / 8, ws->npanels), 256, 0, s2>>>(G, ws->tau, n_refl, nb, ws->Tbuf);
+  else larft_kernel<<<ws->npanels, LARFT_NT, sizeof(double) * (nb * (nb + 1) + nb), s2>>>(G, 0, 1, ws->tau, n_refl, nb, ws->Tbuf);
   launch_gemm_batched(s2, ws->d_desc + ws->desc_vtil, ws->npanels, nb, n, 1);
   *launches += 4;
   for (int p = ws->npanels - 1; p >= 0; p--) {
