@@ -56,45 +56,43 @@ proportional_weights_kernel(const double* __restrict__ f, const unsigned* __rest
   for (int i = threadIdx.x; i < mu; i += blockDim.x) w[i] = f[idx[i]] / total;
 }
 
-// Selection list of THIS rank: every rank r < mu whose sample idx[r] lies in [lo, hi) -> (local sample, weight).
-// Single block, deterministic (ordered) compaction.
+// Selection list of THIS rank: every rank r < mu whose sample idx[r] lies in [lo, hi) -> (local sample, weight), in rank order.
+// Block b compacts ranks [1024 b, 1024 (b+1)); its output offset = number of selected ranks in front of its chunk, which it counts
+// itself (b block-wide counts over the L2-resident index array) — deterministic, no inter-block communication. The single-block
+// predecessor walked all mu ranks with three barriers per 1024 (47 us at mu = 32768).
 __global__ void __launch_bounds__(1024)
 select_local_kernel(const unsigned* __restrict__ idx, const double* __restrict__ w, int mu, unsigned lo, unsigned hi,
                     int* __restrict__ sel_sample, double* __restrict__ sel_weight, int* __restrict__ count_out) {
   __shared__ int warp_tot[32];
-  __shared__ int carry;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int base = 0; base < mu; base += 1024) {
-    const int r = base + threadIdx.x;
-    unsigned s = 0;
-    bool take = false;
-    if (r < mu) { s = idx[r]; take = (s >= lo && s < hi); }
-    const unsigned m = __ballot_sync(0xffffffffu, take);
-    if (lane == 0) warp_tot[warp] = __popc(m);
-    __syncthreads();
-    if (warp == 0) {
-      int x = warp_tot[lane];
-#pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        const int y = __shfl_up_sync(0xffffffffu, x, off);
-        if (lane >= off) x += y;
-      }
-      warp_tot[lane] = x;
-    }
-    __syncthreads();
-    const int c = carry;
-    if (take) {
-      const int pos = c + (warp ? warp_tot[warp - 1] : 0) + __popc(m & ((1u << lane) - 1u));
-      sel_sample[pos] = (int)(s - lo);
-      sel_weight[pos] = w[r];
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) carry = c + warp_tot[31];
-    __syncthreads();
+  int before = 0;
+  for (int c = 0; c < (int)blockIdx.x; c++) {
+    const unsigned s = idx[c * 1024 + threadIdx.x];     // chunks in front of this block are full
+    before += __syncthreads_count(s >= lo && s < hi);
   }
-  if (threadIdx.x == 0) *count_out = carry;
+  const int r = blockIdx.x * 1024 + threadIdx.x;
+  unsigned s = 0;
+  bool take = false;
+  if (r < mu) { s = idx[r]; take = (s >= lo && s < hi); }
+  const unsigned m = __ballot_sync(0xffffffffu, take);
+  if (lane == 0) warp_tot[warp] = __popc(m);
+  __syncthreads();
+  if (warp == 0) {
+    int x = warp_tot[lane];
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, off);
+      if (lane >= off) x += y;
+    }
+    warp_tot[lane] = x;
+  }
+  __syncthreads();
+  if (take) {
+    const int pos = before + (warp ? warp_tot[warp - 1] : 0) + __popc(m & ((1u << lane) - 1u));
+    sel_sample[pos] = (int)(s - lo);
+    sel_weight[pos] = w[r];
+  }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *count_out = before + warp_tot[31];
 }
 
 // ---- K5: gather selected rows, weighted mean partials, and the rank-mu operand ------------------------
@@ -166,19 +164,31 @@ mean_reduce_kernel(const double* __restrict__ partial, const int* __restrict__ c
                    double* __restrict__ mean_out, const double* __restrict__ Y, int ldy, int mirrored, int from_x,
                    const double* __restrict__ mean, const DevScalars* __restrict__ sc, unsigned lo, unsigned hi,
                    double* __restrict__ best_x) {
-  const int d = blockIdx.x * blockDim.x + threadIdx.x;
-  if (d >= n) return;
+  // block = 32 dimensions x 8 chunks of the partial list: a chunk is summed in order (16 loads in flight), the 8 chunk sums in order
+  __shared__ double red[8][33];
+  const int dx = threadIdx.x & 31, cy = threadIdx.x >> 5;
+  const int d = blockIdx.x * 32 + dx;
   const int nparts = (*count_ptr + rows_per_cta - 1) / rows_per_cta;
+  const int chunk = (nparts + 7) / 8;
+  const int p1 = min(nparts, (cy + 1) * chunk);
   double a = 0.0;
-  int p = 0;
-  for (; p + 16 <= nparts; p += 16) {   // 16 loads in flight, added in the same fixed order
-    double v[16];
+  if (d < n) {
+    int p = cy * chunk;
+    for (; p + 16 <= p1; p += 16) {
+      double v[16];
 #pragma unroll
-    for (int k = 0; k < 16; k++) v[k] = partial[(size_t)(p + k) * ld + d];
+      for (int k = 0; k < 16; k++) v[k] = partial[(size_t)(p + k) * ld + d];
 #pragma unroll
-    for (int k = 0; k < 16; k++) a += v[k];
+      for (int k = 0; k < 16; k++) a += v[k];
+    }
+    for (; p < p1; p++) a += partial[(size_t)p * ld + d];
   }
-  for (; p < nparts; p++) a += partial[(size_t)p * ld + d];
+  red[cy][dx] = a;
+  __syncthreads();
+  if (cy != 0 || d >= n) return;
+  a = red[0][dx];
+#pragma unroll
+  for (int k = 1; k < 8; k++) a += red[k][dx];
   mean_out[d] = a;
   const unsigned long long b = sc->best_valid_sample;
   double bx = 0.0;
@@ -232,24 +242,25 @@ mean_step_kernel(const double* __restrict__ mean_new, double* __restrict__ mean,
   y[d] = (mn - mo) / sc->sigma;
 }
 
-// t[d] = (sum_e B[e][d] * y[e]) / D[d]      (z := D^-1 B^T y, :627-636). block = (32 columns, 8 e-slices)
-__global__ void __launch_bounds__(256)
+// t[d] = (sum_e B[e][d] * y[e]) / D[d]      (z := D^-1 B^T y, :627-636). block = (32 columns, 32 e-slices)
+constexpr int BTY_SLICES = 32;
+__global__ void __launch_bounds__(32 * BTY_SLICES)
 bt_y_kernel(const double* __restrict__ B, int ldb, const double* __restrict__ y, const double* __restrict__ D,
             double* __restrict__ tvec, int n, int diagonal) {
-  __shared__ double red[8][33];
+  __shared__ double red[BTY_SLICES][33];
   const int cx = threadIdx.x & 31, ey = threadIdx.x >> 5;
   const int d = blockIdx.x * 32 + cx;
   double a = 0.0;
   if (d < n) {
     if (diagonal) { if (ey == 0) a = y[d]; }
-    else for (int e = ey; e < n; e += 8) a += B[(size_t)e * ldb + d] * y[e];
+    else for (int e = ey; e < n; e += BTY_SLICES) a += B[(size_t)e * ldb + d] * y[e];
   }
   red[ey][cx] = a;
   __syncthreads();
   if (ey == 0 && d < n) {
     double s = red[0][cx];
 #pragma unroll
-    for (int k = 1; k < 8; k++) s += red[k][cx];
+    for (int k = 1; k < BTY_SLICES; k++) s += red[k][cx];
     tvec[d] = s / D[d];
   }
 }
@@ -436,7 +447,7 @@ void launch_proportional_weights(cudaStream_t st, const double* f, const unsigne
 }
 void launch_select_local(cudaStream_t st, const unsigned* idx, const double* w, int mu, unsigned lo, unsigned hi,
                          int* sel_sample, double* sel_weight, int* count_out) {
-  select_local_kernel<<<1, 1024, 0, st>>>(idx, w, mu, lo, hi, sel_sample, sel_weight, count_out);
+  select_local_kernel<<<mu > 0 ? (mu + 1023) / 1024 : 1, 1024, 0, st>>>(idx, w, mu, lo, hi, sel_sample, sel_weight, count_out);
 }
 void launch_gather_mean(cudaStream_t st, const double* Y, int ldy, int mirrored, int from_x, const int* sel_sample,
                         const double* sel_weight, const int* count_ptr, int max_count, int rows_per_cta, int n, int ld,
@@ -450,7 +461,7 @@ void launch_gather_mean(cudaStream_t st, const double* Y, int ldy, int mirrored,
 void launch_mean_reduce(cudaStream_t st, const double* partial, const int* count_ptr, int rows_per_cta, int n, int ld,
                         double* mean_out, const double* Y, int ldy, int mirrored, int from_x, const double* mean,
                         const DevScalars* sc, unsigned lo, unsigned hi, double* best_x) {
-  mean_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(partial, count_ptr, rows_per_cta, n, ld, mean_out, Y, ldy, mirrored, from_x,
+  mean_reduce_kernel<<<(n + 31) / 32, 256, 0, st>>>(partial, count_ptr, rows_per_cta, n, ld, mean_out, Y, ldy, mirrored, from_x,
                                                       mean, sc, lo, hi, best_x);
 }
 // "Use Gradient Information" (CMAES.cpp.base:611-621): mean[d] += sum_i w_i * step / sqrt(N) * gradient[sel_i][d] over the selected
@@ -547,7 +558,7 @@ void launch_paths(cudaStream_t st, const double* mean_new, double* mean, double*
                   double* ps, double* pc, const double* B, int ldb, const double* D, int n, int diagonal, double cs,
                   double cc, double mueff, double chi_n, unsigned generation, DevScalars* sc) {
   mean_step_kernel<<<(n + 255) / 256, 256, 0, st>>>(mean_new, mean, mean_old, y, n, sc);
-  bt_y_kernel<<<(n + 31) / 32, 256, 0, st>>>(B, ldb, y, D, tvec, n, diagonal);
+  bt_y_kernel<<<(n + 31) / 32, 32 * BTY_SLICES, 0, st>>>(B, ldb, y, D, tvec, n, diagonal);
   b_t_ps_kernel<<<(n + 7) / 8, 256, 0, st>>>(B, ldb, tvec, ps, n, diagonal, cs, mueff);
   hsig_pc_kernel<<<1, 1024, 0, st>>>(ps, y, pc, n, cs, cc, mueff, chi_n, generation, sc);
 }
