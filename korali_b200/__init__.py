@@ -70,3 +70,10 @@ def batched_device(fn):
             F.copy_(fn(X).to(torch.float64).reshape(rows))
     model._korali_batched = "device"
     return model
+
+
+def fCMAES(nVars, populationSize=0, muSize=0, device=0):
+    """The ask/tell surface of the reference's float CMA-ES (deepSupervisor/optimizers/fCMAES.{hpp,cpp}) on the device generation loop:
+    ``prepareGeneration()`` / ``_samplePopulation`` / ``updateDistribution(evaluations)`` / ``checkTermination()`` (korali_b200/_fcmaes.py)."""
+    from ._fcmaes import fCMAES as _F
+    return _F(nVars, populationSize, muSize, device)
