@@ -24,6 +24,10 @@ EXPORTS = [
     "kdea_cfg_defaults", "kdea_create", "kdea_destroy", "kdea_last_error", "kdea_run_generation", "kdea_ask", "kdea_eval", "kdea_tell",
     "kdea_set_host_objective", "kdea_inject_f", "kdea_check_termination", "kdea_run", "kdea_get_array", "kdea_set_array",
     "kdea_get_scalar", "kdea_set_scalar", "kdea_launch_count",
+    # include/kmocma.h
+    "kmocma_cfg_defaults", "kmocma_create", "kmocma_destroy", "kmocma_last_error", "kmocma_run_generation", "kmocma_ask", "kmocma_eval",
+    "kmocma_tell", "kmocma_set_host_objective", "kmocma_inject_f", "kmocma_check_termination", "kmocma_run", "kmocma_get_array",
+    "kmocma_get_scalar", "kmocma_set_scalar", "kmocma_launch_count",
 ]
 
 

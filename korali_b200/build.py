@@ -13,8 +13,8 @@ OBJ = os.path.join(HERE, "build")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall"] + ARCH
 # files whose arithmetic must round like the reference's scalar code (no fused multiply-add)
-NO_FMA = {"objective.cu", "update.cu", "constraints.cu", "dea.cu"}
-SOURCES = ["api.cu", "gemm.cu", "gemm_tma.cu", "rng.cu", "objective.cu", "sort.cu", "update.cu", "eigen.cu", "constraints.cu", "gemm_batched.cu", "tridiag.cu", "dc.cu", "dea.cu"]
+NO_FMA = {"objective.cu", "update.cu", "constraints.cu", "dea.cu", "mocma.cu"}
+SOURCES = ["api.cu", "gemm.cu", "gemm_tma.cu", "rng.cu", "objective.cu", "sort.cu", "update.cu", "eigen.cu", "constraints.cu", "gemm_batched.cu", "tridiag.cu", "dc.cu", "dea.cu", "mocma.cu"]
 
 
 def _newer(src, dst):
@@ -26,6 +26,7 @@ def build(force=False, verbose=False):
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     headers.append(os.path.join(HERE, "..", "include", "kcma.h"))
     headers.append(os.path.join(HERE, "..", "include", "kdea.h"))
+    headers.append(os.path.join(HERE, "..", "include", "kmocma.h"))
     objs, rebuilt = [], False
     procs = []
     for s in SOURCES:

@@ -31,6 +31,7 @@
 
 #include "../../include/kcma.h"
 #include "../../include/kdea.h"
+#include "../../include/kmocma.h"
 
 namespace py = pybind11;
 
@@ -213,6 +214,8 @@ class SolverBase {
   virtual void printGeneration(const std::function<void(int, const char*)>& log) = 0;   // printGenerationAfter
   virtual std::string takeWarnings() { return ""; }
   virtual bool needsPython() const { return true; }   // a generation calls back into Python (models, constraints): the GIL stays held
+  // finalize(): fills e["Results"] and prints the closing lines (CMAES.cpp.base:994-1010); false = the default single-objective form
+  virtual bool finalize(py::dict results, const std::function<void(int, const char*)>& log) { (void)results; (void)log; return false; }
   virtual std::vector<std::pair<std::string, std::string>> sideCars() { return {}; }      // (key, file suffix) of N x N arrays saved as .npy
   virtual size_t variableCount() const = 0;
   void splitReasons(const char* reason) {
@@ -1001,6 +1004,242 @@ class DEA : public SolverBase {
 };
 
 // ---- Experiment ------------------------------------------------------------------------------------------------
+// ---- the solver plug-in: Optimizer/MOCMAES on libkcma (include/kmocma.h) ----------------------------------------------
+class MOCMAES : public SolverBase {
+ public:
+  kmocma_t* h = nullptr;
+  kmocma_cfg cfg;
+  std::vector<double> init_val, init_sd;
+  std::string batched;
+  py::object objective;
+  double tc_max_generations = 1e10, tc_max_model_evaluations = 1e9, tc_max_value = INFINITY, tc_min_value_diff = -INFINITY;
+  double tc_min_max_value_diff = -INFINITY, tc_min_var_diff = -INFINITY, tc_min_sd = -INFINITY, tc_max_sd = INFINITY;
+
+  ~MOCMAES() override { if (h) kmocma_destroy(h); }
+  const char* name() const override { return "Optimizer/MOCMAES"; }
+  size_t variableCount() const override { return cfg.n; }
+  void check(int rc) { if (rc) korali_error("%s", kmocma_last_error(h)); }
+  double scalar(const char* key) override {
+    if (!strcmp(key, "Best Ever Value")) return NAN;    // the base-class scalars are disabled by MOCMAES (:64-66)
+    double v = NAN; check(kmocma_get_scalar(h, key, &v)); return v;
+  }
+  std::vector<double> array(const char* key) override {
+    size_t n = 0;
+    check(kmocma_get_array(h, key, nullptr, 0, &n));
+    std::vector<double> v(n);
+    if (n) check(kmocma_get_array(h, key, v.data(), n, &n));
+    return v;
+  }
+
+  // generated MOCMAES::setConfiguration (MOCMAES.config) + Optimizer:: + Solver:: (strict)
+  void setConfiguration(py::dict solver, py::list variables, py::dict problem, uint64_t seed) override {
+    kmocma_cfg_defaults(&cfg);
+    Settings s(solver, "MOCMAES");
+    s.take("Type");
+    cfg.population_size = s.uint("Population Size", 0);
+    cfg.mu_value = s.uint("Mu Value", 0);
+    cfg.evolution_path_adaption_strength = s.num("Evolution Path Adaption Strength", -1.0);
+    cfg.covariance_learning_rate = s.num("Covariance Learning Rate", -1.0);
+    cfg.target_success_rate = s.num("Target Success Rate", 0.175);
+    cfg.threshold_probability = s.num("Threshold Probability", 0.44);
+    cfg.success_learning_rate = s.num("Success Learning Rate", 0.08);
+    if (s.has("Termination Criteria")) {
+      py::object tco = s.take("Termination Criteria");
+      if (!py::isinstance<py::dict>(tco)) korali_error(" + Object: [ MOCMAES ] \n + Key:    ['Termination Criteria']\n + Reason: not an object\n");
+      py::dict tcd;
+      for (auto kv : py::reinterpret_borrow<py::dict>(tco)) tcd[kv.first] = kv.second;
+      Settings tc(tcd, "MOCMAES['Termination Criteria']");
+      tc_min_max_value_diff = tc.num("Min Max Value Difference Threshold", -INFINITY);   // parsed, but the criterion reads the base threshold
+      tc_min_var_diff = tc.num("Min Variable Difference Threshold", -INFINITY);
+      tc_min_sd = tc.num("Min Standard Deviation", -INFINITY);
+      tc_max_sd = tc.num("Max Standard Deviation", INFINITY);
+      tc_max_value = tc.num("Max Value", INFINITY);
+      tc_min_value_diff = tc.num("Min Value Difference Threshold", -INFINITY);
+      tc_max_model_evaluations = tc.num("Max Model Evaluations", 1e9);
+      tc_max_generations = tc.num("Max Generations", 1e10);
+      tc.finish();
+    }
+    for (const char* g : {"Multinormal Generator", "Uniform Generator", "Normal Generator"}) if (s.has(g)) s.take(g);
+    const size_t n = py::len(variables);
+    if (n == 0) korali_error("Optimization Evaluation problems require at least one variable.\n");
+    lower.assign(n, -INFINITY); upper.assign(n, INFINITY); init_val.assign(n, NAN); init_sd.assign(n, NAN);
+    for (size_t i = 0; i < n; i++) {
+      if (!py::isinstance<py::dict>(variables[i])) korali_error("Variable %zu is not an object\n", i);
+      py::dict vcopy;
+      for (auto kv : py::reinterpret_borrow<py::dict>(variables[i])) vcopy[kv.first] = kv.second;
+      Settings v(vcopy, "Variable");
+      v.str("Name", "");
+      lower[i] = v.num("Lower Bound", -INFINITY);
+      upper[i] = v.num("Upper Bound", INFINITY);
+      init_val[i] = v.num("Initial Value", NAN);
+      init_sd[i] = v.num("Initial Standard Deviation", NAN);
+      for (const char* k : {"Initial Mean", "Minimum Standard Deviation Update", "Granularity"}) v.num(k, NAN);
+      if (v.has("Values")) v.take("Values");
+      v.finish();
+    }
+    cfg.n = n; cfg.lower_bound = lower.data(); cfg.upper_bound = upper.data(); cfg.initial_value = init_val.data(); cfg.initial_stddev = init_sd.data();
+    cfg.seed = seed;
+    py::dict pcopy;
+    for (auto kv : problem) pcopy[kv.first] = kv.second;
+    Settings p(pcopy, "Optimization");
+    const std::string ptype = canon(p.str("Type", ""));
+    if (ptype != "optimization") korali_error("Korali problem incompatible with MO-CMAES, must be of type 'Optimization'.\n");
+    if (!p.has("Objective Function")) korali_error(" + Object: [ Optimization ] \n + Key:    ['Objective Function']\n + Reason: mandatory setting missing\n");
+    objective = p.take("Objective Function");
+    cfg.num_objectives = p.uint("Num Objectives", 1);
+    p.boolean("Has Discrete Variables", 0);
+    if (p.has("Constraints")) {
+      py::object c = p.take("Constraints");
+      if (py::isinstance<py::list>(c) && py::len(c) > 0) korali_error("Optimizer/MOCMAES does not take constraints\n");
+    }
+    p.finish();
+    if (py::isinstance<py::str>(objective)) {
+      const std::string o = canon(objective.cast<std::string>());
+      if (o == "negrosenbrockandsphere" || o == "rosenbrockandsphere") cfg.objective = KMOCMA_OBJ_NEG_ROSENBROCK_AND_SPHERE;
+      else if (o == "negrosenbrockandtwospheres" || o == "rosenbrockandtwospheres") cfg.objective = KMOCMA_OBJ_NEG_ROSENBROCK_AND_TWO_SPHERES;
+      else korali_error("Unknown multi-objective device model '%s' (RosenbrockAndSphere, RosenbrockAndTwoSpheres)\n", o.c_str());
+    } else if (PyCallable_Check(objective.ptr())) {
+      cfg.objective = KMOCMA_OBJ_EXTERNAL;
+      batched = py::hasattr(objective, "_korali_batched") ? objective.attr("_korali_batched").cast<std::string>() : std::string();
+      if (batched == "device") korali_error("Optimizer/MOCMAES takes per-sample models and korali.batched(fn) models (not device-tensor models)\n");
+    } else {
+      korali_error(" + Object: [ Optimization ] \n + Key:    ['Objective Function']\n + Reason: neither a callable nor the name of a device model\n");
+    }
+    s.finish();
+  }
+
+  // operation "Evaluate Multiple": sample["F(x)"] is a list of Num Objectives values (optimization.cpp.base)
+  static void host_objective(void* user, const double* x, uint64_t rows, uint64_t n, double* f_out, uint64_t K) {
+    MOCMAES* self = (MOCMAES*)user;
+    try {
+      if (self->batched == "numpy") {
+        py::array_t<double> X({(py::ssize_t)rows, (py::ssize_t)n}, {(py::ssize_t)(n * sizeof(double)), (py::ssize_t)sizeof(double)}, x, py::none());
+        py::array_t<double, py::array::c_style | py::array::forcecast> F(self->objective(X));
+        if ((uint64_t)F.size() != rows * K) korali_error("The batched model returned %zu values for %zu samples x %zu objectives\n", (size_t)F.size(), (size_t)rows, (size_t)K);
+        for (uint64_t i = 0; i < rows * K; i++) f_out[i] = F.data()[i];
+        return;
+      }
+      for (uint64_t i = 0; i < rows; i++) {
+        py::dict sample;
+        py::list params;
+        for (uint64_t d = 0; d < n; d++) params.append(x[i * n + d]);
+        sample["Parameters"] = params;
+        sample["Sample Id"] = i;
+        sample["Module"] = "Problem";
+        sample["Operation"] = "Evaluate Multiple";
+        self->objective(sample);
+        if (!sample.contains("F(x)")) korali_error("The model did not set 'F(x)' for sample %zu\n", (size_t)i);
+        py::object fx = sample["F(x)"];
+        if (!(py::isinstance<py::list>(fx) || py::isinstance<py::tuple>(fx)) || (uint64_t)py::len(fx) != K)
+          korali_error("Multi-objective model: 'F(x)' of sample %zu must be a list of %zu values ('Num Objectives')\n", (size_t)i, (size_t)K);
+        uint64_t k = 0;
+        for (auto v : fx) f_out[i * K + k++] = v.cast<double>();
+      }
+    } catch (const std::exception& e) {
+      self->pending_error = e.what();
+      for (uint64_t i = 0; i < rows * K; i++) f_out[i] = NAN;
+    }
+  }
+
+  void initialize(const std::vector<int>& device_ids) override {
+    if (device_ids.size() > 1) korali_error("Optimizer/MOCMAES runs on one device (k['Conduit']['Devices'] > 1 is built for Optimizer/CMAES)\n");
+    cfg.device = device_ids[0];
+    if (kmocma_create(&cfg, &h)) korali_error("%s", kmocma_last_error(nullptr));
+    if (cfg.objective == KMOCMA_OBJ_EXTERNAL) check(kmocma_set_host_objective(h, &MOCMAES::host_objective, this));
+    check(kmocma_set_scalar(h, "Termination Criteria/Min Value Difference Threshold", tc_min_value_diff));
+    check(kmocma_set_scalar(h, "Termination Criteria/Min Variable Difference Threshold", tc_min_var_diff));
+    check(kmocma_set_scalar(h, "Termination Criteria/Min Standard Deviation", tc_min_sd));
+    check(kmocma_set_scalar(h, "Termination Criteria/Max Standard Deviation", tc_max_sd));
+    check(kmocma_set_scalar(h, "Termination Criteria/Max Model Evaluations", tc_max_model_evaluations));
+    check(kmocma_set_scalar(h, "Termination Criteria/Max Generations", tc_max_generations));
+  }
+
+  void restore(uint64_t generation) override {
+    if (generation != 0) korali_error("Resuming an Optimizer/MOCMAES run from a result file is not built on the B200 path\n");
+  }
+
+  bool checkTermination() override {
+    int fin = 0;
+    const char* reason = "";
+    check(kmocma_check_termination(h, &fin, &reason));
+    if (fin) splitReasons(reason);
+    return fin != 0;
+  }
+
+  void runGeneration() override {
+    pending_error.clear();
+    int rc;
+    if (!needsPython()) { py::gil_scoped_release nogil; rc = kmocma_run_generation(h); }
+    else rc = kmocma_run_generation(h);
+    if (!pending_error.empty()) { std::string e = pending_error; pending_error.clear(); throw std::runtime_error(e); }
+    check(rc);
+  }
+  bool needsPython() const override { return cfg.objective == KMOCMA_OBJ_EXTERNAL; }
+
+  py::list rowsOf(const std::vector<double>& flat, size_t width) {
+    py::list out;
+    for (size_t i = 0; width && (i + 1) * width <= flat.size(); i++) out.append(std::vector<double>(flat.begin() + i * width, flat.begin() + (i + 1) * width));
+    return out;
+  }
+
+  void printGeneration(const std::function<void(int, const char*)>& log) override {   // MOCMAES::printGenerationAfter :524-537
+    char b[256];
+    std::vector<double> cb = array("Current Best Values"), be = array("Best Ever Values"), mn = array("Current Min Standard Deviations"),
+                        mx = array("Current Max Standard Deviations");
+    log(NORMAL, "Current Function Values = (Max, Best):\n");
+    for (size_t k = 0; k < cb.size(); k++) { snprintf(b, sizeof(b), "                              = (%+6.3e, %+6.3e)\n", cb[k], be[k]); log(NORMAL, b); }
+    snprintf(b, sizeof(b), "Standard Devs:            Min = %+6.3e - Max = %+6.3e\n", *std::min_element(mn.begin(), mn.end()), *std::max_element(mx.begin(), mx.end())); log(NORMAL, b);
+    snprintf(b, sizeof(b), "Non Dominated Samples:   Current = %zu - Overall = %zu\n", (size_t)scalar("Current Non Dominated Sample Count"), (size_t)scalar("Sample Collection Size")); log(NORMAL, b);
+    snprintf(b, sizeof(b), "Number of Infeasible Samples: %zu\n", (size_t)scalar("Infeasible Sample Count")); log(DETAILED, b);
+  }
+
+  // MOCMAES::finalize :539-552
+  bool finalize(py::dict results, const std::function<void(int, const char*)>& log) override {
+    py::dict pareto;
+    pareto["F(x)"] = rowsOf(array("Sample Value Collection"), cfg.num_objectives);
+    pareto["Parameters"] = rowsOf(array("Sample Collection"), cfg.n);
+    results["Pareto Optimal Samples"] = pareto;
+    log(MINIMAL, "--------------------------------------------------------------------\n");
+    log(MINIMAL, "Optimizer/MOCMAES finished correctly.\n");
+    return true;
+  }
+
+  // generated getConfiguration: settings + the internal state under Korali's key names (MOCMAES.config "Internal Settings")
+  void getConfiguration(py::dict js) override {
+    js["Type"] = "Optimizer/MOCMAES";
+    js["Population Size"] = (uint64_t)scalar("Population Size");
+    js["Mu Value"] = (uint64_t)scalar("Mu Value");
+    js["Evolution Path Adaption Strength"] = scalar("Evolution Path Adaption Strength");
+    js["Covariance Learning Rate"] = scalar("Covariance Learning Rate");
+    js["Target Success Rate"] = cfg.target_success_rate;
+    js["Threshold Probability"] = cfg.threshold_probability;
+    js["Success Learning Rate"] = cfg.success_learning_rate;
+    py::dict tc;
+    tc["Min Max Value Difference Threshold"] = tc_min_max_value_diff; tc["Min Variable Difference Threshold"] = tc_min_var_diff;
+    tc["Min Standard Deviation"] = tc_min_sd; tc["Max Standard Deviation"] = tc_max_sd; tc["Max Value"] = tc_max_value;
+    tc["Min Value Difference Threshold"] = tc_min_value_diff; tc["Max Model Evaluations"] = tc_max_model_evaluations;
+    tc["Max Generations"] = tc_max_generations;
+    js["Termination Criteria"] = tc;
+    const size_t n = cfg.n, K = cfg.num_objectives;
+    js["Num Objectives"] = K;
+    js["Current Non Dominated Sample Count"] = (uint64_t)scalar("Current Non Dominated Sample Count");
+    js["Infeasible Sample Count"] = (uint64_t)scalar("Infeasible Sample Count");
+    js["Model Evaluation Count"] = (uint64_t)scalar("Model Evaluation Count");
+    for (const char* k : {"Current Values", "Previous Values"}) js[k] = rowsOf(array(k), K);
+    for (const char* k : {"Parent Sample Population", "Current Sample Population", "Previous Sample Population", "Parent Evolution Paths",
+                          "Current Evolution Paths", "Best Ever Variables Vector", "Current Best Variables Vector", "Sample Collection"})
+      js[k] = rowsOf(array(k), n);
+    js["Sample Value Collection"] = rowsOf(array("Sample Value Collection"), K);
+    for (const char* k : {"Parent Covariance Matrix", "Current Covariance Matrix"}) js[k] = rowsOf(array(k), n * n);
+    for (const char* k : {"Parent Sigma", "Current Sigma", "Parent Success Probabilities", "Current Success Probabilities", "Best Ever Values",
+                          "Current Best Values", "Current Best Value Differences", "Current Best Variable Differences",
+                          "Current Min Standard Deviations", "Current Max Standard Deviations"})
+      js[k] = array(k);
+    std::vector<double> pi = array("Parent Index");
+    js["Parent Index"] = std::vector<uint64_t>(pi.begin(), pi.end());
+  }
+};
+
 class Experiment : public KoraliJson {
  public:
   std::unique_ptr<SolverBase> solver;
@@ -1065,8 +1304,8 @@ class Experiment : public KoraliJson {
     py::dict problem_js = py::reinterpret_borrow<py::dict>(top.take("Problem"));
     py::list variables = py::reinterpret_borrow<py::list>(top.take("Variables"));
     const std::string stype = canon(solver_js.contains("Type") && py::isinstance<py::str>(solver_js["Type"]) ? solver_js["Type"].cast<std::string>() : "");
-    if (stype != "optimizer/cmaes" && stype != "cmaes" && stype != "optimizer/dea" && stype != "dea")
-      korali_error("Solver Type '%s' is not served by korali_b200: only 'Optimizer/CMAES' and 'Optimizer/DEA' are built (SURVEY.md scope)\n", stype.c_str());
+    if (stype != "optimizer/cmaes" && stype != "cmaes" && stype != "optimizer/dea" && stype != "dea" && stype != "optimizer/mocmaes" && stype != "mocmaes")
+      korali_error("Solver Type '%s' is not served by korali_b200: only 'Optimizer/CMAES', 'Optimizer/DEA' and 'Optimizer/MOCMAES' are built (SURVEY.md scope)\n", stype.c_str());
     random_seed = top.uint("Random Seed", 0);
     if (random_seed == 0) random_seed = (uint64_t)std::chrono::system_clock::now().time_since_epoch().count();  // experiment.cpp.base:235-251
     top.boolean("Preserve Random Number Generator States", 0);
@@ -1101,6 +1340,7 @@ class Experiment : public KoraliJson {
     }
     top.finish();
     if (stype == "optimizer/dea" || stype == "dea") solver = std::make_unique<DEA>();
+    else if (stype == "optimizer/mocmaes" || stype == "mocmaes") solver = std::make_unique<MOCMAES>();
     else solver = std::make_unique<CMAES>();
     solver->setConfiguration(solver_js, variables, problem_js, random_seed);   // Normal Generator gets seed S (distribution.cpp.base:36-37)
     solver->initialize(devices);
@@ -1198,17 +1438,25 @@ class Experiment : public KoraliJson {
     current_generation--;
     is_finished = true;
     // finalize (CMAES.cpp.base:994-1010)
-    py::dict results, best;
-    best["F(x)"] = solver->scalar("Best Ever Value");
-    best["Parameters"] = solver->array("Best Ever Variables");
-    results["Best Sample"] = best;
+    py::dict results;
+    const bool own_finalize = solver->finalize(results, [this](int level, const char* line) { log((Verbosity)level, "%s", line); });
+    if (!own_finalize) {
+      py::dict best;
+      best["F(x)"] = solver->scalar("Best Ever Value");
+      best["Parameters"] = solver->array("Best Ever Variables");
+      results["Best Sample"] = best;
+    }
     _js["Results"] = results;
-    log(MINIMAL, "Optimum found: %e\n", solver->scalar("Best Ever Value"));
-    log(MINIMAL, "Number of Infeasible Samples: %zu\n", (size_t)solver->scalar("Infeasible Sample Count"));
+    if (!own_finalize) {
+      log(MINIMAL, "Optimum found: %e\n", solver->scalar("Best Ever Value"));
+      log(MINIMAL, "Number of Infeasible Samples: %zu\n", (size_t)solver->scalar("Infeasible Sample Count"));
+    }
     getConfiguration();
     if (file_enabled) saveState();
-    log(MINIMAL, "--------------------------------------------------------------------\n");
-    log(MINIMAL, "Optimizer/CMAES finished correctly.\n");
+    if (!own_finalize) {
+      log(MINIMAL, "--------------------------------------------------------------------\n");
+      log(MINIMAL, "%s finished correctly.\n", solver->name());
+    }
     for (auto& c : solver->termination_criteria) log(NORMAL, "Termination Criterion Met: %s\n", c.c_str());
     log(NORMAL, "Final Generation: %lu\n", (unsigned long)current_generation);
     log(NORMAL, "Elapsed Time: %.3fs\n", std::chrono::duration<double>(t1 - t0).count());

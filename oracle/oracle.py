@@ -18,7 +18,7 @@ def lib():
     global _LIB
     if _LIB is None:
         path = os.path.join(_HERE, "libokcma.so")
-        if not os.path.exists(path) or os.path.getmtime(path) < max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("okcma.c", "odea.c")):
+        if not os.path.exists(path) or os.path.getmtime(path) < max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("okcma.c", "odea.c", "omocma.c")):
             build()
         _LIB = C.CDLL(path)
     return _LIB
@@ -157,3 +157,11 @@ def mt19937_gaussian(seed, count, skip=0):
     fn.restype, fn.argtypes = None, [C.c_uint64, C.c_uint64, C.c_uint64, _dp]
     fn(seed, skip, count, _as_dp(out))
     return out
+
+
+def OracleMOCMA(**kw):
+    """The MOCMAES oracle (oracle/omocma.c) behind the vocabulary of korali_b200._mocma.MocmaHandle."""
+    from korali_b200._mocma import MocmaHandle
+    kw.pop("device", None)
+    return MocmaHandle(lib(), "omocma_", **kw)
+

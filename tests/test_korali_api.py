@@ -81,7 +81,8 @@ def test_koralijson_cursor_semantics():
     (lambda e: e["Solver"].__setitem__("Gradient Step Size", "big"), "Gradient Step Size"),
     (lambda e: e["Variables"][0].__setitem__("Colour", "red"), "Unrecognized settings"),
     (lambda e: e["Solver"]["Termination Criteria"].__setitem__("Max Fun", 1), "Unrecognized settings"),
-    (lambda e: e["Solver"].__setitem__("Type", "Optimizer/MOCMAES"), "only 'Optimizer/CMAES' and 'Optimizer/DEA'"),
+    (lambda e: e["Solver"].__setitem__("Type", "Optimizer/Adam"), "is not served by korali_b200"),
+    (lambda e: e["Solver"].__setitem__("Type", "Optimizer/MOCMAES"), "Problem requires multiple objectives"),   # MOCMAES.cpp.base:20-21
     (lambda e: e["Problem"].__setitem__("Type", "Bayesian/Custom"), "Problem Type"),
     (lambda e: e.__setitem__("Nonsense", 1), "Unrecognized settings for Korali module: Experiment"),
     (lambda e: e["Console Output"].__setitem__("Verbosity", "Loud"), "Verbosity"),
