@@ -220,9 +220,10 @@ def e2e_through_engine(steps, warmup, devices):
     run(1)
     # the difference of two wall-clock runs carries the jitter of their set-up parts (tens of ms when a communicator is built):
     # at least 100 generations keep it below a few per cent of the difference
-    # (several devices: the set-up part — communicator, one context per device — jitters by ~0.1 s: 300 generations, three runs each)
-    k_e2e = max(steps, 100 if devices == 1 else 300)
-    reps = 2 if devices == 1 else 3
+    # (the set-up part — handle creation, communicator, one context per device — jitters by ~0.1 s: 200 / 300 generations, three runs each;
+    # a 100-generation difference once gave an e2e 18 % above the device-timed value)
+    k_e2e = max(steps, 200 if devices == 1 else 300)
+    reps = 3
     out = {"short": min(run(warmup)[0] for _ in range(reps))}
     longs = [run(warmup + k_e2e) for _ in range(reps)]
     out["long"] = min(t for t, _ in longs)
@@ -367,7 +368,7 @@ def ours_arm(args, rank, world):
         "value_eager_with_phase_timers": 1e3 / (ms_eager / args.steps),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 288,
                 "through": "korali_b200.Engine().run(e) (k['Conduit']['Type'] = 'Device'%s, Objective Function 'Ellipsoid'), wall clock; "
-                           "(run of W+Ke generations) - (run of W generations), Ke = max(K, 100) on one device and max(K, 300) on several, each the fastest of two (three) runs"
+                           "(run of W+Ke generations) - (run of W generations), Ke = max(K, 200) on one device and max(K, 300) on several, each the fastest of three runs"
                            % (", k['Conduit']['Devices'] = %d" % world if world > 1 else ""),
                 "engine_run_seconds": {"W_generations": eng["short"], "W_plus_Ke_generations": eng["long"], "Ke": eng["generations"]} if eng else None,
                 "kcma_run_generations_per_sec": done / t_run,
