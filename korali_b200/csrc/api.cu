@@ -131,6 +131,7 @@ struct kcma {
   bool rng_prelaunched = false;
   // nccl
   ncclComm_t comm = nullptr;
+  bool comm_in_process = false;   // kcma_comm_init_all: the ranks are threads of one process (no graph replay there, see graph_eligible)
   // timing
   bool timing = false;
   std::map<std::string, Phase> phases;
@@ -1416,6 +1417,7 @@ int kcma_comm_init_all(kcma_t** handles, int count) {
   }
   const ncclResult_t ge = g_nccl.GroupEnd();
   if (!rc) rc = nccl_check(handles[0], ge, "ncclGroupEnd");
+  for (int r = 0; r < count; r++) handles[r]->comm_in_process = true;
   return rc;
 }
 
@@ -1454,13 +1456,20 @@ void invalidate_graph(kcma* h) {
   if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
 }
 
-// A whole generation can be replayed as ONE CUDA graph when it is a fixed sequence of launches: single rank, built-in
+// A whole generation can be replayed as ONE CUDA graph when it is a fixed sequence of launches: built-in
 // objective, no constraint path (its loops are host-driven), no resampling rounds, no pending injection, no phase timers,
 // eigensolver = one launch (N <= 1184 or diagonal). Small configurations are launch-latency bound (44-47 launches of a few
 // microseconds each per generation): the graph removes the per-launch host cost. KCMA_GRAPH=0 disables it.
 bool graph_eligible(const kcma* h) {
   static const int on = getenv("KCMA_GRAPH") ? atoi(getenv("KCMA_GRAPH")) : 1;
-  if (!on || h->graph_failed || h->timing || h->cfg.nranks > 1 || h->host_obj || h->host_obj_grad || h->dev_obj || h->host_con || h->has_constraints) return false;
+  // several ranks: the two collectives of a generation are captured with it (NCCL records them as graph nodes); every rank replays
+  // the same sequence, and a rank that falls back to eager launches still issues the same collectives in the same order
+  static const int multi_on = getenv("KCMA_GRAPH_MULTI") ? atoi(getenv("KCMA_GRAPH_MULTI")) : 1;
+  // (one process per rank: 119.8 -> 121.6 generations/s on two GPUs. With the ranks as threads of ONE process the replay of graphs that
+  // hold collectives measured slower than eager launches — 111 against 124 generations/s through Engine().run(e) — so that mode stays eager;
+  // profiles/r02_bench_2gpu_graph_ab.log)
+  if (h->cfg.nranks > 1 && (!multi_on || !h->comm || h->comm_in_process)) return false;
+  if (!on || h->graph_failed || h->timing || h->host_obj || h->host_obj_grad || h->dev_obj || h->host_con || h->has_constraints) return false;
   if (h->cfg.objective == KCMA_OBJ_EXTERNAL || h->has_discrete) return false;
   if (h->has_bounds && h->cfg.max_infeasible_resamplings != 0) return false;
   if (h->inj_z || h->inj_bd || h->inj_y || h->inj_x || h->inj_f || h->inj_grad || h->sampled_pending || !h->vt_valid) return false;
