@@ -161,7 +161,7 @@ mo_sort_kernel(const double* __restrict__ Fcur, const double* __restrict__ Fprev
   int* rank = (int*)(smd + n2);
   int* max_nb = rank + n2;
   int* list = max_nb + n2;
-  __shared__ int s_min_max, s_min_rank, s_left, s_m, s_next;
+  __shared__ int s_min_max, s_min_rank, s_left, s_m;
   __shared__ double s_ref[KMOCMA_MAX_OBJECTIVES];
   auto val = [&](int i, int k) { return i < lambda ? Fcur[(size_t)i * K + k] : Fprev[(size_t)(i - lambda) * K + k]; };
   for (int i = tid; i < n2; i += blockDim.x) { rank[i] = 0; sorted[i] = -1; }
@@ -227,7 +227,6 @@ mo_sort_kernel(const double* __restrict__ Fcur, const double* __restrict__ Fprev
         double best = hv[0];
         for (int a = 1; a < m; ++a)
           if (hv[a] > best) { best = hv[a]; next = list[a]; }
-        s_next = next;
         sorted[next] = order;
       }
       order++;

@@ -147,7 +147,6 @@ sort_fused_kernel(const double* __restrict__ f, int n, unsigned long long* k0, u
   namespace cg = cooperative_groups;
   cg::grid_group grid = cg::this_grid();
   __shared__ unsigned wcount[SORT_THREADS / 32][256];
-  __shared__ unsigned dscan[256];
   __shared__ unsigned wtot[SORT_THREADS / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nblocks = gridDim.x;
   const int base = blockIdx.x * SORT_TILE + warp * (32 * SORT_ITEMS);
