@@ -37,9 +37,9 @@ typedef struct kmocma kmocma_t;
 /* MOCMAES.config "Configuration Settings" and "Module Defaults". */
 typedef struct kmocma_cfg {
   uint32_t abi_version, reserved0;
-  uint64_t n;                 /* variables */
+  uint64_t n;                 /* variables (<= 158 on the device: one Cholesky factor per CTA in shared memory) */
   uint64_t num_objectives;    /* "Num Objectives" of the problem (>= 2, :20-21) */
-  uint64_t population_size;   /* "Population Size" (0: ceil(4 + floor(3 ln n)), :24) */
+  uint64_t population_size;   /* "Population Size" (0: ceil(4 + floor(3 ln n)), :24); <= 5120 on the device */
   uint64_t mu_value;          /* "Mu Value" (0: population / 2, :25) */
   double evolution_path_adaption_strength; /* < 0: 2 / (n + 2) (:133) */
   double covariance_learning_rate;         /* < 0: 2 / (n^2 + 6) (:134) */

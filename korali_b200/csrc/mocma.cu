@@ -445,7 +445,7 @@ int kmocma_create(const kmocma_cfg* cfg, kmocma_t** out) {
   if (cfg->target_success_rate <= 0. || cfg->target_success_rate > 1.)
     return mo_fail(nullptr, "Invalid Target Success Rate (%f), must be greater than 0.0 and less or equal to 1.0\n", cfg->target_success_rate);
   if (sample_smem((int)N) > 200 * 1024) return mo_fail(nullptr, "Optimizer/MOCMAES on the device holds one covariance factor per CTA in shared memory: n <= 158");
-  if (2 * lambda > 16384) return mo_fail(nullptr, "Optimizer/MOCMAES: population size <= 8192");
+  if (2 * lambda * (sizeof(double) + 3 * sizeof(int)) > 200 * 1024) return mo_fail(nullptr, "Optimizer/MOCMAES: the ranking of the 2 lambda merged samples runs in one CTA's shared memory: population size <= 5120");
   if (cfg->objective != KMOCMA_OBJ_EXTERNAL) {
     const uint64_t want = cfg->objective == KMOCMA_OBJ_NEG_ROSENBROCK_AND_TWO_SPHERES ? 3 : 2;
     if (cfg->objective != KMOCMA_OBJ_NEG_ROSENBROCK_AND_SPHERE && cfg->objective != KMOCMA_OBJ_NEG_ROSENBROCK_AND_TWO_SPHERES)

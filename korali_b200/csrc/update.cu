@@ -2,6 +2,9 @@
 // (:690-718), updateSigma (:720-761), numericalErrorTreatment (:763-772), updateViabilityBoundaries (:426-437).
 // All scalars live in DevScalars in HBM so a generation needs no host round trip.
 // Compiled with --fmad=false: products and sums round like the reference's scalar code.
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -453,6 +456,7 @@ void launch_gather_mean(cudaStream_t st, const double* Y, int ldy, int mirrored,
                         const double* sel_weight, const int* count_ptr, int max_count, int rows_per_cta, int n, int ld,
                         const double* mean, const DevScalars* sc, double* S, int lds, int rows_padded, double* partial) {
   const int ctas = (max_count + rows_per_cta - 1) / rows_per_cta;
+  if (rows_per_cta > GM_ROWS_MAX) { fprintf(stderr, "launch_gather_mean: rows_per_cta %d > %d\n", rows_per_cta, GM_ROWS_MAX); abort(); }
   if (ctas > 0)
     gather_mean_kernel<<<ctas, 256, 0, st>>>(Y, ldy, mirrored, from_x, sel_sample, sel_weight, count_ptr, rows_per_cta, n, ld, mean,
                                              sc, S, lds, partial);
