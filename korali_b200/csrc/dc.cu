@@ -368,6 +368,20 @@ dc_loewner_kernel(const DcNode* __restrict__ nodes, const int* __restrict__ row2
   }
 }
 
+// ---- split-K slabs of a level's merge products -> the level's output, diagonal blocks only (fixed order) ----------------------
+__global__ void __launch_bounds__(256)
+dc_reduce_blocks_kernel(const double* __restrict__ slabs, long long stride, int splits, const DcNode* __restrict__ nodes,
+                        const int* __restrict__ row2node, int ld, double* __restrict__ out) {
+  const int r = blockIdx.y;
+  const DcNode nd = nodes[row2node[r]];
+  const int cc = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cc >= nd.n) return;
+  const size_t i = (size_t)r * ld + nd.off + cc;
+  double s = 0.0;
+  for (int k = 0; k < splits; k++) s += slabs[(size_t)k * stride + i];
+  out[i] = s;
+}
+
 // ---- rows of U^T at their final (ascending) positions, new eigenvalues: one warp per root / deflated value ----------
 __global__ void __launch_bounds__(256)
 dc_vectors_kernel(const DcNode* __restrict__ nodes, const int* __restrict__ row2node, int n_total, const double* __restrict__ lam,
@@ -460,9 +474,13 @@ bool dc_solve(cudaStream_t st, TridiagWs* ws, int* launches) {
     dc_loewner_kernel<<<(n + 31) / 32, 32 * LW_SLICES, 0, st>>>(ws->d_nodes, r2n, n, ws->dl, ws->w, ws->Kcnt, ws->DELTA, ld, ws->what);
     dc_vectors_kernel<<<warp_blocks, 256, 0, st>>>(ws->d_nodes, r2n, n, ws->lam, ws->defl_val, ws->defl_col, ws->col2k, ws->Kcnt,
                                                    ws->what, ws->DELTA, ld, ws->UT, dnext);
-    const int msplit = (l == ws->levels) ? ws->split_top : 1;   // the top merge is ONE product: split-K fills the SMs
+    const int msplit = (l == ws->levels) ? ws->split_top : (ws->lvl_split.empty() || !ws->slabsF ? 1 : ws->lvl_split[l - 1]);
     launch_gemm_batched(st, ws->d_desc + ws->desc_level_begin[l - 1], cnt, nmax, nmax, msplit);
-    if (msplit > 1) { launch_reduce_slabs(st, ws->slabsF, (long long)n * ld, msplit, n, n, ld, ws->XT, ws->num_sms); *launches += 1; }
+    if (msplit > 1 && l == ws->levels) { launch_reduce_slabs(st, ws->slabsF, (long long)n * ld, msplit, n, n, ld, ws->XT, ws->num_sms); *launches += 1; }
+    else if (msplit > 1) {   // sum the slabs of the diagonal blocks into the level's output (level l writes Qb when l is odd, Qa when even)
+      dc_reduce_blocks_kernel<<<dim3((nmax + 255) / 256, n), 256, 0, st>>>(ws->slabsF, (long long)n * ld, msplit, ws->d_nodes, r2n, ld, (l & 1) ? ws->Qb : ws->Qa);
+      *launches += 1;
+    }
     *launches += 5;
     double* t = dcur; dcur = dnext; dnext = t;
     qsrc = (qsrc == ws->Qa) ? ws->Qb : ws->Qa;

@@ -877,7 +877,20 @@ TridiagWs* tridiag_ws_create(int n, int ld, int num_sms, char* err, size_t errle
          ws_alloc(ws, &ws->XF, mat);
     const int tiles = row_tiles * row_tiles;
     ws->splitF = std::max(1, std::min(8, num_sms / std::max(1, tiles)));
-    if (ws->splitF > 1) ok = ok && ws_alloc(ws, &ws->slabsF, (size_t)ws->splitF * mat);
+    // merges below the top: a level of 2 (4, 8) products of 500 (250, 125) rows is 32 (16, 8) CTAs at N = 1000; split-K fills the SMs
+    // (the slabs are summed over the diagonal blocks only, dc_reduce_blocks_kernel). Bounded by 256 MB of slabs.
+    ws->lvl_split.assign(std::max(levels, 1), 1);
+    int max_split = ws->splitF;
+    static const int lvl_split_on = getenv("KCMA_DC_SPLIT") ? atoi(getenv("KCMA_DC_SPLIT")) : 1;
+    for (int l = 1; l < levels && lvl_split_on; l++) {
+      int nmax = 0;
+      for (const DcNode& nd : ws->lvl[l - 1]) nmax = std::max(nmax, nd.n);
+      const int t = (nmax + 127) / 128, ctas = (int)ws->lvl[l - 1].size() * t * t;
+      int sp = std::min(std::min(8, num_sms / std::max(1, ctas)), nmax / 64);
+      while (sp > 1 && (size_t)sp * mat * sizeof(double) > ((size_t)256 << 20)) sp--;
+      if (sp >= 2 && nmax >= 100) { ws->lvl_split[l - 1] = sp; max_split = std::max(max_split, sp); }
+    }
+    if (max_split > 1) ok = ok && ws_alloc(ws, &ws->slabsF, (size_t)max_split * mat);
     ws->split_top = (levels > 0 && ws->splitF > 1) ? std::min(ws->splitF, 2) : 1;
     if (!ok) return fail("out of device memory");
     if (cudaStreamCreateWithFlags(&ws->st2, cudaStreamNonBlocking) != cudaSuccess ||
@@ -902,6 +915,7 @@ TridiagWs* tridiag_ws_create(int n, int ld, int num_sms, char* err, size_t errle
       g.lda = g.ldb = g.ldc = ld;
       if (l < levels) {          // Q_new[r][c] = sum_k Q[r][k] U^T[c][k]
         g.A = src + o; g.B = ws->UT + o; g.C = dst + o; g.M = nd.n; g.Nc = nd.n; g.krule = 1;
+        if (ws->npanels > 0 && ws->lvl_split[l - 1] > 1) { g.C = ws->slabsF + o; g.splits = ws->lvl_split[l - 1]; g.split_stride = (long long)mat; }
       } else {                   // last merge, transposed: X^T[r][c] = sum_k U^T[r][k] Q[c][k]
         g.A = ws->UT + o; g.B = src + o; g.C = ws->XT + o; g.M = nd.n; g.Nc = nd.n; g.krule = 2;
         if (ws->split_top > 1) { g.C = ws->slabsF; g.splits = ws->split_top; g.split_stride = (long long)mat; }

@@ -49,6 +49,7 @@ struct TridiagWs {
   double *XF = nullptr, *slabsF = nullptr;   // X^T = Z^T Q^T (final result), split-K slabs of that product
   int splitF = 1, desc_final = 0;
   int split_top = 1;                         // split-K of the top merge of stage 2 (slabs in slabsF, reduced into XT)
+  std::vector<int> lvl_split;                // split-K of the merges below the top (few, small products: 16-32 CTAs without it)
   cudaStream_t st2 = nullptr;                // side stream: the Q accumulation runs next to the divide & conquer stage
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   double* result = nullptr;                  // rows = eigenvectors of the last stage run (XT after stage 2, XF after stage 3)
