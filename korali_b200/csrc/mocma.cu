@@ -432,9 +432,6 @@ int kmocma_create(const kmocma_cfg* cfg, kmocma_t** out) {
   if (cfg->n < 1) return mo_fail(nullptr, "no variables");
   if (cfg->num_objectives < 2 || cfg->num_objectives > KMOCMA_MAX_OBJECTIVES)
     return mo_fail(nullptr, "Problem requires multiple objectives, 'Num Objectives' is set to %zu\n.", (size_t)cfg->num_objectives);
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return mo_fail(nullptr, "no CUDA device: korali_b200 has no CPU fallback");
-  if (cfg->device < 0 || cfg->device >= ndev) return mo_fail(nullptr, "invalid device %d", cfg->device);
   const uint64_t N = cfg->n, K = cfg->num_objectives;
   uint64_t lambda = cfg->population_size, mu = cfg->mu_value;
   if (lambda == 0) lambda = (uint64_t)ceil(4. + floor(3. * log((double)N)));
@@ -471,6 +468,10 @@ int kmocma_create(const kmocma_cfg* cfg, kmocma_t** out) {
     if (s < min_sdev) min_sdev = s;
     if (s > max_sdev) max_sdev = s;
   }
+  // (the configuration checks above come first, like the reference's; the device is needed from here on)
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return mo_fail(nullptr, "no CUDA device: korali_b200 has no CPU fallback");
+  if (cfg->device < 0 || cfg->device >= ndev) return mo_fail(nullptr, "invalid device %d", cfg->device);
   kmocma* h = new kmocma();
   h->cfg = *cfg;
   h->cfg.lower_bound = h->cfg.upper_bound = h->cfg.initial_value = h->cfg.initial_stddev = nullptr;

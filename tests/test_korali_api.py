@@ -46,6 +46,46 @@ def base_1d(pop=8, gens=100):
     return e
 
 
+def base_mo():
+    """examples/optimization/multiobjective/run-mocmaes.py:16-37"""
+    e = korali.Experiment()
+    e["Problem"]["Type"] = "Optimization"
+    e["Problem"]["Objective Function"] = "RosenbrockAndSphere"
+    e["Problem"]["Num Objectives"] = 2
+    for i in range(4):
+        e["Variables"][i]["Name"] = "X" + str(i)
+        e["Variables"][i]["Lower Bound"] = -25.0
+        e["Variables"][i]["Upper Bound"] = +25.0
+        e["Variables"][i]["Initial Standard Deviation"] = 3.0
+    e["Solver"]["Type"] = "Optimizer/MOCMAES"
+    e["Solver"]["Population Size"] = 32
+    e["Solver"]["Mu Value"] = 16
+    e["Console Output"]["Verbosity"] = "Silent"
+    e["File Output"]["Enabled"] = False
+    return e
+
+
+@pytest.mark.parametrize("mod,match", [
+    (lambda e: e["Solver"].__setitem__("Bogus Key", 3), "Unrecognized settings for Korali module: MOCMAES"),
+    (lambda e: e["Solver"]["Termination Criteria"].__setitem__("Max Fun", 1), "Unrecognized settings"),
+    (lambda e: e["Solver"].__setitem__("Mu Value", 33), "must be smaller or equal with population size"),       # MOCMAES.cpp.base:26-27
+    (lambda e: e["Solver"].__setitem__("Success Learning Rate", 1.5), "Invalid Global Success Learning Rate"),   # :136-137
+    (lambda e: e["Solver"].__setitem__("Target Success Rate", 0.0), "Invalid Target Success Rate"),             # :138-139
+    (lambda e: e["Problem"].__setitem__("Num Objectives", 1), "Problem requires multiple objectives"),           # :20-21
+    (lambda e: e["Problem"].__setitem__("Objective Function", "Ellipsoid"), "Unknown multi-objective device model"),
+    (lambda e: e["Problem"].__setitem__("Num Objectives", 3), "the built-in objective has 2 objectives"),
+    (lambda e: e["Variables"][0].__setitem__("Upper Bound", float("inf")), "cannot be inferred"),                # :70-82
+])
+def test_mocmaes_configuration_errors(mod, match):
+    """The configuration checks of MOCMAES::setInitialConfiguration (tests/unit/modules/solver/optimizers.cpp:2112-2180) are raised
+    before any device work."""
+    e = base_mo()
+    mod(e)
+    e["Solver"]["Type"]
+    with pytest.raises(RuntimeError, match=match):
+        korali.Engine().run(e)
+
+
 # ---------------------------------------------------------------- CPU: JSON tree + strict configuration --------
 def test_koralijson_cursor_semantics():
     e = korali.Experiment()
