@@ -356,7 +356,10 @@ sytrd_reg_kernel(const double* __restrict__ M, int ld, int n, int ns /* n rounde
   // Every slot exists `copies` times (stride cstride): all CTAs poll the same 2 n slots, and 148 requests per 128-byte line and
   // polling round serialise in the L2 slice that owns the line; CTA b reads copy b % copies, the producers write all copies.
   const size_t cstride = 4 * (size_t)ns;
-  const size_t my_copy = (size_t)(b % copies) * cstride;
+  // (`copies` packs two counts: bits 0-7 for the column slots, bits 8-15 for the product slots when they differ — the column costs its
+  // owner n stores per copy, a product entry one)
+  const int ccop = copies & 255, pcop = (copies >> 8) ? (copies >> 8) : ccop;
+  const size_t my_copy = (size_t)(b % ccop) * cstride, my_copy_p = (size_t)(b % pcop) * cstride;
   double cn[2 * KU];   // PF: column i with the updates of the steps <= i-2, this thread's rows (columns 0 and 1 come from M itself)
 #pragma unroll
   for (int j = 0; j < 2 * KU; j++) {
@@ -365,13 +368,13 @@ sytrd_reg_kernel(const double* __restrict__ M, int ld, int n, int ns /* n rounde
   }
   if (!PF && b == 0)   // owner of column 0 publishes it for step 0
     for (int r = tid; r < n; r += NT)
-      for (int q = 0; q < copies; q++) ll_store(xC + q * cstride + r, M[r], 1ull);
+      for (int q = 0; q < ccop; q++) ll_store(xC + q * cstride + r, M[r], 1ull);
   __syncthreads();
   double tau_old = 0.0;
   for (int i = 0; i < n; i++) {
     const int par = i & 1;
     const unsigned long long tag = (unsigned long long)i + 1ull;
-    const LL* Pin = xP + my_copy + (size_t)par * ns;
+    const LL* Pin = xP + my_copy_p + (size_t)par * ns;
     const LL* Cin = xC + my_copy + (size_t)par * ns;
     const bool have_p = i > 0;
     const bool pr = prof && b == prof_cta && tid == 0 && i >= prof_step0 && i < prof_step0 + 32;
@@ -553,7 +556,7 @@ sytrd_reg_kernel(const double* __restrict__ M, int ld, int n, int ns /* n rounde
           dot = __fma_rn(a1, vnw[2 * k + 1], dot);
           if (c == cpub) {
             const int r = 2 * (tid + NT * k);
-            for (int q = 0; q < copies; q++) {
+            for (int q = 0; q < ccop; q++) {
               if (r > i && r < n) ll_store(Cout + q * cstride + r, a0, ctag);
               if (r + 1 > i && r + 1 < n) ll_store(Cout + q * cstride + r + 1, a1, ctag);
             }
@@ -602,7 +605,7 @@ sytrd_reg_kernel(const double* __restrict__ M, int ld, int n, int ns /* n rounde
 #pragma unroll
         for (int j = 0; j < (NT / 32); j++) x += pp[s * NT + lane + 32 * j];
         x = warp_sum_butterfly(x);
-        if (lane < copies) ll_store(Pout + lane * cstride + b + s * G, x, otag);
+        if (lane < pcop) ll_store(Pout + lane * cstride + b + s * G, x, otag);
       }
     if (pr) prof[(i - prof_step0) * 8 + 3] = clock64();
     if (b == i % G) {   // reflector i for the back-transform (entries r <= i and r >= n stay zero from the allocation)
@@ -804,7 +807,12 @@ TridiagWs* tridiag_ws_create(int n, int ld, int num_sms, char* err, size_t errle
   LL* xb = nullptr;
   ws->ll_copies = 2;
   if (const char* ce = getenv("KCMA_SYTRD_COPIES")) { const int c = atoi(ce); if (c >= 1 && c <= 16) ws->ll_copies = c; }
-  ok = ok && ws_alloc(ws, &xb, (size_t)ws->ll_copies * 4 * (size_t)ns);
+  // product slots: four copies at large N (a copy costs a producer one more 16-byte store per entry; 37 pollers per line instead of 74:
+  // sytrd 4.17 -> 4.05 ms at N = 1000; three, six or eight copies, or more than two copies of the COLUMN slots, lose again:
+  // profiles/r02_eigen_ab15.log, r02_eigen_ab16.log)
+  ws->ll_pcopies = n > 512 ? 4 : ws->ll_copies;
+  if (const char* ce = getenv("KCMA_SYTRD_PCOPIES")) { const int c = atoi(ce); if (c >= 1 && c <= 16) ws->ll_pcopies = c; }
+  ok = ok && ws_alloc(ws, &xb, (size_t)std::max(ws->ll_copies, ws->ll_pcopies) * 4 * (size_t)ns);
   ws->xbuf = xb;
   if (const char* pe = getenv("KCMA_SYTRD_PROF")) {   // "step0[,cta]": clock64 stamps of 32 steps of one CTA (tridiag_dump_prof)
     ws->prof_step0 = atoi(pe);
@@ -992,7 +1000,7 @@ bool tridiag_stage_sytrd(cudaStream_t st, TridiagWs* ws, const double* M) {
   int n = ws->n, ld = ws->ld, ns = (n + 1) & ~1;
   LL* xP = (LL*)ws->xbuf;
   LL* xC = xP + 2 * (size_t)(ws->resident ? ns : n);   // per-parity stride: ns (32-byte aligned slot pairs) in the register variant
-  cudaMemsetAsync(ws->xbuf, 0, sizeof(LL) * 4 * (size_t)ns * (ws->resident ? ws->ll_copies : 1), st);
+  cudaMemsetAsync(ws->xbuf, 0, sizeof(LL) * 4 * (size_t)ns * (ws->resident ? std::max(ws->ll_copies, ws->ll_pcopies) : 1), st);
   double* Awork = ws->Awork;
   if (!ws->resident) cudaMemcpyAsync(Awork, M, sizeof(double) * (size_t)n * ld, cudaMemcpyDeviceToDevice, st);
   double *dT = ws->dT, *eT = ws->eT, *tau = ws->tau, *VR = ws->VR;
@@ -1003,7 +1011,7 @@ bool tridiag_stage_sytrd(cudaStream_t st, TridiagWs* ws, const double* M) {
   // (same time at N = 1000, 0.33 -> 0.28 ms at N = 100 where a step is short: profiles/r02_sytrd_exchange_ab.log)
   int opt = n <= 512 ? 4 : 1;
   if (const char* oe = getenv("KCMA_SYTRD_OPT")) opt = atoi(oe);
-  int copies = ws->ll_copies;
+  int copies = ws->ll_copies | (ws->ll_pcopies != ws->ll_copies ? ws->ll_pcopies << 8 : 0);
   void* rargs[] = {&M, &ld, &n, &ns, &xP, &xC, &dT, &eT, &tau, &VR, &prof, &prof_step0, &prof_cta, &opt, &copies};
   const void* fn = ws->reg_variant == 1 ? (const void*)sytrd_reg_kernel<1, 4> : ws->reg_variant == 2 ? (const void*)sytrd_reg_kernel<2, 7>
                    : ws->reg_variant == 3 ? (const void*)sytrd_reg_kernel<3, 11> : ws->reg_variant == 4 ? (const void*)sytrd_reg_kernel<2, 14>

@@ -21,6 +21,7 @@ struct TridiagWs {
   double *VC = nullptr;        // VR^T (column i = v_i)
   void* xbuf = nullptr;        // LL exchange slots: copies x [P | C] x 2 parities x n x 16 B
   int ll_copies = 2;           // replicas of every slot (spreads the polling of 148 CTAs over several L2 lines)
+  int ll_pcopies = 2;          // copies of the product slots (KCMA_SYTRD_PCOPIES; default = ll_copies)
   long long* prof = nullptr; int prof_step0 = 0, prof_cta = 0;   // optional clock64 phase stamps of 32 steps (KCMA_SYTRD_PROF)
   // ---- stage 2: divide & conquer on (dT, eT)
   int levels = 0, leaf_count = 0;
