@@ -9,7 +9,8 @@ import pytest
 TB, W_FULL, W_DIAG, MAX_SEG = 128, 8, 5, 64
 
 
-def partition(n, k_rows, sms, max_splits=16):
+def partition(n, k_rows, sms, max_splits=16, k_dev=None):
+    """k_rows: the host's bound on the row count (sizes the grid); k_dev: the count the kernel reads from device memory (<= k_rows)."""
     nt = (n + TB - 1) // TB
     nk = (k_rows + 15) // 16
     sw = W_FULL * (nt * (nt - 1) // 2) + W_DIAG * nt
@@ -20,6 +21,9 @@ def partition(n, k_rows, sms, max_splits=16):
     parts_bound = min(max_splits, (wmax * g + sw - 1) // sw + 1)
     if nt * (nt + 1) // 2 // g + 3 > MAX_SEG:
         return None                                   # the launcher falls back to the split-K kernel
+    if k_dev is not None:                              # a rank only knows on the device how many selected samples it owns
+        nk = (k_dev + 15) // 16
+        total = nk * sw
     bound = lambda c: c * total // g
     cover, max_seg = {}, 0
     for c in range(g):
@@ -72,3 +76,13 @@ def test_every_k_step_of_every_tile_exactly_once(n, k_rows, sms):
 def test_config3_balance():
     g, parts, segs = partition(1000, 32768, 148)
     assert (g, parts, segs) == (148, 6, 2)     # 148 CTAs, at most 6 parts per tile (the slabs the launcher zeroes), 2 segments per CTA
+
+
+@pytest.mark.parametrize("n", [10, 100, 257, 1000, 4096])
+def test_device_row_count_below_the_host_bound(n):
+    """Multi-GPU: the grid is sized for the host's bound (mu, or the shard size), the partition is computed on the device from the
+    number of selected samples the rank really owns."""
+    for k_host in (100, 8192, 1 << 17):
+        for k_dev in (0, 1, 17, k_host // 8, k_host // 2, k_host - 1):
+            partition(n, k_host, 148, k_dev=k_dev)
+
