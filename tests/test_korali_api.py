@@ -86,6 +86,22 @@ def test_mocmaes_configuration_errors(mod, match):
         korali.Engine().run(e)
 
 
+def test_sibling_solvers_run_on_one_device():
+    """k["Conduit"]["Devices"] > 1 shards the population of Optimizer/CMAES; the sibling solvers say so instead of ignoring the key."""
+    e = base_mo()
+    k = korali.Engine()
+    k["Conduit"]["Type"] = "Device"
+    k["Conduit"]["Devices"] = 2
+    with pytest.raises(RuntimeError, match="Optimizer/MOCMAES runs on one device"):
+        k.run(e)
+    e = base_1d()
+    e["Solver"]["Type"] = "Optimizer/DEA"
+    k = korali.Engine()
+    k["Conduit"]["Devices"] = [0, 1]
+    with pytest.raises(RuntimeError, match="Optimizer/DEA runs on one device"):
+        k.run(e)
+
+
 # ---------------------------------------------------------------- CPU: JSON tree + strict configuration --------
 def test_koralijson_cursor_semantics():
     e = korali.Experiment()
